@@ -1,0 +1,131 @@
+/*
+ * binfhe.c -- CGGI blind rotation (block-binary key distribution) restated over the oracle's HAL
+ * functions.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Restates: poulpy-bin-fhe/src/blind_rotation/algorithms/mod.rs:136-181 (mod_switch_2n, div_round_by_pow2),
+ *   poulpy-bin-fhe/src/blind_rotation/utils.rs:6-41 (set_xai_plus_y with y = 0),
+ *   poulpy-bin-fhe/src/blind_rotation/algorithms/cggi/key_prepared.rs:66-75 (x_pow_a table),
+ *   poulpy-bin-fhe/src/blind_rotation/algorithms/cggi/algorithm.rs:275-368 (execute_block_binary).
+ */
+#include "poulpy_oracle.h"
+
+#include <assert.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* algorithms/mod.rs:136-181 */
+void orc_mod_switch_2n(size_t n, int64_t *res, const orc_vec_znx *lwe, size_t base2k, int rot_left) {
+    size_t len = lwe->n;
+    size_t log2n = 0;
+    while (((size_t)1 << log2n) < n) log2n++; /* usize::BITS - (n-1).leading_zeros() */
+    log2n += 1;
+    memcpy(res, lwe->data, 8 * len); /* at(0, 0) */
+    if (rot_left)
+        for (size_t i = 0; i < len; i++) res[i] = -res[i];
+    if (base2k > log2n) {
+        size_t diff = base2k - (log2n - 1);
+        for (size_t i = 0; i < len; i++) res[i] = (res[i] + ((int64_t)1 << (diff - 1))) >> diff;
+    } else {
+        size_t rem = base2k - (log2n % base2k);
+        size_t size = (log2n + base2k - 1) / base2k;
+        for (size_t i = 1; i < size; i++) {
+            const int64_t *x = lwe->data + lwe->n * (i * lwe->cols);
+            if (i == size - 1 && rem != base2k) {
+                size_t k_rem = base2k - rem;
+                for (size_t j = 0; j < len; j++) res[j] = (int64_t)((uint64_t)res[j] << k_rem) + (x[j] >> rem);
+            } else {
+                for (size_t j = 0; j < len; j++) res[j] = (int64_t)((uint64_t)res[j] << base2k) + x[j];
+            }
+        }
+    }
+}
+
+static size_t prep_bytes(int flavour) { return flavour == 0 ? 32u : 8u; }
+
+/* key_prepared.rs:66-75 + utils.rs:6-41 */
+void orc_cggi_x_pow_a(int flavour, const void *mod, orc_svp_ppol *res) {
+    size_t n = res->n;
+    assert(res->cols == 2 * n);
+    int64_t *buf = (int64_t *)calloc(n, 8);
+    orc_scalar_znx sz = {buf, n, 1};
+    for (size_t ai = 0; ai < 2 * n; ai++) {
+        if (ai < n) buf[ai] = 1;
+        else buf[(ai - n) & (n - 1)] = -1;
+        if (flavour == 0) orc_ntt120_svp_prepare((const orc_ntt120_module *)mod, res, ai, &sz, 0);
+        else orc_fft64_svp_prepare((const orc_fft64_module *)mod, res, ai, &sz, 0);
+        if (ai < n) buf[ai] = 0;
+        else buf[(ai - n) & (n - 1)] = 0;
+        buf[0] = 0;
+    }
+    free(buf);
+}
+
+/* algorithm.rs:275-368 */
+void orc_cggi_blind_rotate_block_binary(int flavour, const void *mod, orc_vec_znx *res, const int64_t *lwe_2n,
+                                        size_t n_lwe, const orc_vec_znx *lut, const orc_vmp_pmat *brk,
+                                        const orc_svp_ppol *x_pow_a, size_t block_size, size_t base2k) {
+    size_t n = res->n, cols = res->cols, two_n = 2 * n;
+    size_t dnum = brk[0].rows, bsize = brk[0].size;
+    size_t pb = prep_bytes(flavour), bb = flavour == 0 ? 16u : 8u;
+    const int64_t *a = lwe_2n + 1;
+    int64_t b = lwe_2n[0];
+
+    memset(res->data, 0, 8 * n * cols * res->size);
+    orc_vec_znx_rotate(b, res, 0, lut, 0);
+
+    orc_vec_znx_dft acc_dft = {calloc(n * cols * dnum, pb), n, cols, dnum};
+    orc_vec_znx_dft vmp_res = {calloc(n * cols * bsize, pb), n, cols, bsize};
+    orc_vec_znx_dft acc_add = {calloc(n * cols * bsize, pb), n, cols, bsize};
+    orc_vec_znx_dft vmp_xai = {calloc(n * bsize, pb), n, 1, bsize};
+    orc_vec_znx_big acc_big = {calloc(n * bsize, bb), n, 1, bsize};
+
+    for (size_t blk = 0; blk + block_size <= n_lwe; blk += block_size) { /* chunks_exact */
+        for (size_t j = 0; j < cols; j++) {
+            if (flavour == 0) {
+                orc_ntt120_vec_znx_dft_apply((const orc_ntt120_module *)mod, 1, 0, &acc_dft, j, res, j);
+                orc_ntt120_vec_znx_dft_zero(&acc_add, j);
+            } else {
+                orc_fft64_vec_znx_dft_apply((const orc_fft64_module *)mod, 1, 0, &acc_dft, j, res, j);
+                orc_fft64_vec_znx_dft_zero(&acc_add, j);
+            }
+        }
+        for (size_t t = 0; t < block_size; t++) {
+            int64_t aii = a[blk + t];
+            size_t ai_pos = (size_t)((aii + (int64_t)two_n) & (int64_t)(two_n - 1));
+            const orc_vmp_pmat *sk = &brk[blk + t];
+            if (flavour == 0) {
+                const orc_ntt120_module *m = (const orc_ntt120_module *)mod;
+                orc_ntt120_vmp_apply_dft_to_dft(m, &vmp_res, &acc_dft, sk, 0);
+                for (size_t i = 0; i < cols; i++) {
+                    orc_ntt120_svp_apply_dft_to_dft(m, &vmp_xai, 0, x_pow_a, ai_pos, &vmp_res, i);
+                    orc_ntt120_vec_znx_dft_add_assign(&acc_add, i, &vmp_xai, 0);
+                    orc_ntt120_vec_znx_dft_sub_assign(&acc_add, i, &vmp_res, i);
+                }
+            } else {
+                const orc_fft64_module *m = (const orc_fft64_module *)mod;
+                orc_fft64_vmp_apply_dft_to_dft(m, &vmp_res, &acc_dft, sk, 0);
+                for (size_t i = 0; i < cols; i++) {
+                    orc_fft64_svp_apply_dft_to_dft(m, &vmp_xai, 0, x_pow_a, ai_pos, &vmp_res, i);
+                    orc_fft64_vec_znx_dft_add_assign(&acc_add, i, &vmp_xai, 0);
+                    orc_fft64_vec_znx_dft_sub_assign(&acc_add, i, &vmp_res, i);
+                }
+            }
+        }
+        for (size_t i = 0; i < cols; i++) {
+            if (flavour == 0) {
+                orc_ntt120_vec_znx_idft_apply((const orc_ntt120_module *)mod, &acc_big, 0, &acc_add, i);
+                orc_ntt120_vec_znx_big_add_small_assign(&acc_big, 0, res, i);
+                orc_ntt120_vec_znx_big_normalize(res, base2k, 0, i, &acc_big, base2k, 0, 0);
+            } else {
+                orc_fft64_vec_znx_idft_apply((const orc_fft64_module *)mod, &acc_big, 0, &acc_add, i);
+                orc_fft64_vec_znx_big_add_small_assign(&acc_big, 0, res, i);
+                orc_fft64_vec_znx_big_normalize(res, base2k, 0, i, &acc_big, base2k, 0, 0);
+            }
+        }
+    }
+    free(acc_dft.data);
+    free(vmp_res.data);
+    free(acc_add.data);
+    free(vmp_xai.data);
+    free(acc_big.data);
+}

@@ -1,0 +1,65 @@
+/*
+ * znx.c -- coefficient-domain (i64) helpers of poulpy-cpu-ref restated in C.
+ * TEST INFRASTRUCTURE ONLY (see poulpy_oracle.h).
+ *
+ * Restates: reference/vec_znx/normalize.rs:18-426 (through normalize_impl.inc
+ * instantiated for int64_t, steps of reference/znx/normalization.rs:4-323),
+ * reference/znx/rotate.rs:3-26, reference/vec_znx/rotate.rs:9-38.
+ */
+#include "poulpy_oracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+static inline int64_t *znx_at(const orc_vec_znx *v, size_t col, size_t limb) {
+    return v->data + v->n * (limb * v->cols + col);
+}
+
+#define NT int64_t
+#define NUT uint64_t
+#define NBITS 64
+#define NBIG orc_vec_znx
+#define NLIMB(v, c, l) znx_at(v, c, l)
+#define NF(name) name##_i64
+#include "normalize_impl.inc"
+#undef NT
+#undef NUT
+#undef NBITS
+#undef NBIG
+#undef NLIMB
+#undef NF
+
+/* reference/vec_znx/normalize.rs:18-50.  The reference only has op = 0 for i64. */
+void orc_vec_znx_normalize(orc_vec_znx *res, size_t res_base2k, int64_t res_offset, size_t res_col,
+                           const orc_vec_znx *a, size_t a_base2k, size_t a_col, int op) {
+    int64_t *scratch = (int64_t *)malloc(3 * res->n * sizeof(int64_t));
+    if (res_base2k == a_base2k)
+        normalize_inter_i64(res_base2k, res, res_offset, res_col, a, a_col, scratch, op);
+    else
+        normalize_cross_i64(res, res_base2k, res_offset, res_col, a, a_base2k, a_col, scratch, op);
+    free(scratch);
+}
+
+/* reference/znx/rotate.rs:3-26 */
+void orc_znx_rotate(int64_t p, int64_t *res, const int64_t *src, size_t n) {
+    size_t mp_2n = (size_t)(p & (int64_t)(2 * n - 1));
+    size_t mp_1n = mp_2n & (n - 1);
+    size_t mp_1n_neg = n - mp_1n;
+    int neg_first = mp_2n < n;
+    /* dst1 = res[..mp_1n], dst2 = res[mp_1n..]; src1 = src[..mp_1n_neg], src2 = src[mp_1n_neg..] */
+    for (size_t i = 0; i < mp_1n; i++) {
+        int64_t v = src[mp_1n_neg + i];
+        res[i] = neg_first ? (int64_t)(0 - (uint64_t)v) : v;
+    }
+    for (size_t i = 0; i < mp_1n_neg; i++) {
+        int64_t v = src[i];
+        res[mp_1n + i] = neg_first ? v : (int64_t)(0 - (uint64_t)v);
+    }
+}
+
+/* reference/vec_znx/rotate.rs:9-38 */
+void orc_vec_znx_rotate(int64_t p, orc_vec_znx *res, size_t res_col, const orc_vec_znx *a, size_t a_col) {
+    size_t mn = res->size < a->size ? res->size : a->size;
+    for (size_t j = 0; j < mn; j++) orc_znx_rotate(p, znx_at(res, res_col, j), znx_at(a, a_col, j), res->n);
+    for (size_t j = mn; j < res->size; j++) memset(znx_at(res, res_col, j), 0, 8 * res->n);
+}
