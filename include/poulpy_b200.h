@@ -1,0 +1,255 @@
+/*
+ * poulpy_b200.h -- C ABI of the B200-native poulpy-hal backend (libpoulpy_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of phantomzone-org/poulpy v0.5.0: one
+ * `extern "C"` symbol per hot `unsafe trait HalImpl<BE>` method
+ * (poulpy-hal/src/oep/hal_impl.rs:25-755), taking plain pointers and sizes.  A Rust backend
+ * crate `poulpy-gpu-b200` binds these one-to-one (see INTEGRATION.md for the `extern "C"` block
+ * and the `unsafe impl HalImpl<B200Ntt120> for B200Ntt120` stubs).  All paths below are relative
+ * to the reference root; "R#" / "F#" / "C#" are the SURVEY.md section 8(a) rows.
+ *
+ * Conventions
+ *  - Every function returns 0 on success, a negative pgb_status otherwise; pgb_last_error()
+ *    returns the message (thread-local).  The Rust shim turns non-zero into panic!, matching the
+ *    reference's assert!/panic! error model (hal_defaults/scratch.rs:79, ntt.rs:223-227).
+ *  - Layout descriptors mirror the reference's #[repr(C)] structs field for field; `data` must be
+ *    device-accessible (pgb_alloc_bytes = CUDA managed memory, host-dereferenceable as the
+ *    reference's `DataRef: AsRef<[u8]>` requires; pgb_alloc_device_bytes = plain device memory).
+ *    Limb j of column i starts at scalar offset n*(j*cols+i) (layouts/znx_base.rs:57-84).
+ *  - The non-batched entry points are logically synchronous (complete before returning:
+ *    poulpy-hal/docs/backend_safety_contract.md "Synchronization").  The *_batched twins run the
+ *    same operation on `count` independent operands laid out `stride` bytes apart, enqueue on the
+ *    module's stream and return immediately; call pgb_module_sync() before touching results.
+ *  - The backend owns the byte layout of the prepared types (Backend::ScalarPrep / ScalarBig are
+ *    backend-chosen, layouts/module.rs:28-70):
+ *      NTT120 flavour: ScalarPrep = 16 B  (4 x u32 canonical residues mod Q[k]; a DFT limb is
+ *                      four planes [k][n] of u32 in the reference's bit-reversed frequency order),
+ *                      ScalarBig  = 16 B  (little-endian i128), VmpPMat = [row][col][k][n] u32.
+ *      FFT64  flavour: ScalarPrep = 8 B (f64, limb = [re(m) | im(m)], reference frequency order),
+ *                      ScalarBig  = 8 B (i64), VmpPMat = [row][col][re(m) | im(m)].
+ *  - No CPU fallback exists: without a CUDA device pgb_module_new fails.
+ */
+#ifndef POULPY_B200_H
+#define POULPY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { PGB_NTT120 = 0, PGB_FFT64 = 1 } pgb_flavour;
+
+typedef enum {
+    PGB_OK = 0,
+    PGB_ERR_SHAPE = -1,   /* shape / argument violation (reference: assert!/debug_assert!) */
+    PGB_ERR_CUDA = -2,    /* CUDA runtime error */
+    PGB_ERR_ALIAS = -3,   /* forbidden aliasing (backend_safety_contract.md "Aliasing") */
+    PGB_ERR_SCRATCH = -4, /* scratch too small (reference: assert!(scratch.available() >= ...)) */
+    PGB_ERR_UNSUPPORTED = -5
+} pgb_status;
+
+/* Opaque module handle = `Module<B>`'s `Handle` (layouts/module.rs:84-104, oep/hal_impl.rs:320). */
+typedef struct pgb_module pgb_module;
+
+/* layouts/vec_znx.rs:33-41, vec_znx_dft.rs:25-34, vec_znx_big.rs:25-33 (same five fields). */
+typedef struct { void *data; uint64_t n, cols, size, max_size; } pgb_vec_znx;
+typedef pgb_vec_znx pgb_vec_znx_dft;
+typedef pgb_vec_znx pgb_vec_znx_big;
+/* layouts/svp_ppol.rs:23-28 and layouts/scalar_znx.rs (data, n, cols). */
+typedef struct { void *data; uint64_t n, cols; } pgb_svp_ppol;
+typedef pgb_svp_ppol pgb_scalar_znx;
+/* layouts/vmp_pmat.rs:25-33 (data, n, size, rows, cols_in, cols_out) and layouts/mat_znx.rs:28-36. */
+typedef struct { void *data; uint64_t n, size, rows, cols_in, cols_out; } pgb_vmp_pmat;
+typedef pgb_vmp_pmat pgb_mat_znx;
+
+/* Batch descriptor of the *_batched twins: operand x of item b lives at x.data + b*stride_x bytes.
+ * A stride of 0 shares the operand across the batch (e.g. one prepared key for all ciphertexts). */
+typedef struct { uint64_t count; uint64_t stride_res, stride_a, stride_b; } pgb_batch;
+
+const char *pgb_last_error(void);
+int pgb_device_count(void);
+
+/* ---- module (HalImpl::new, oep/hal_impl.rs:320; Backend::destroy, layouts/module.rs:260-266) ---- */
+int pgb_module_new(uint64_t n, int flavour, int device, pgb_module **out);
+void pgb_module_destroy(pgb_module *m);
+uint64_t pgb_module_n(const pgb_module *m);
+int pgb_module_flavour(const pgb_module *m);
+/* Use an externally owned CUDA stream (e.g. torch's current stream) for all launches; 0 = own stream. */
+int pgb_module_set_stream(pgb_module *m, void *cuda_stream);
+int pgb_module_sync(pgb_module *m);
+/* number of kernels launched by this module since creation (bench.py's gpu_launches) */
+uint64_t pgb_module_launch_count(const pgb_module *m);
+
+/* ---- memory (Backend::alloc_bytes / from_bytes, layouts/module.rs:36-39; lib.rs:146 alignment) ---- */
+void *pgb_alloc_bytes(size_t len);        /* CUDA managed, host-dereferenceable, zero-filled */
+void *pgb_alloc_device_bytes(size_t len); /* device only, zero-filled */
+void *pgb_alloc_pinned_bytes(size_t len); /* page-locked host memory for staging */
+void pgb_free(void *p);
+void pgb_free_pinned(void *p);
+int pgb_memcpy_h2d(void *dst, const void *src, size_t len);
+int pgb_memcpy_d2h(void *dst, const void *src, size_t len);
+int pgb_memcpy_d2d(void *dst, const void *src, size_t len);
+int pgb_memset(void *dst, int byte, size_t len);
+
+/* Backend::bytes_of_* (layouts/module.rs:44-70) */
+size_t pgb_size_of_scalar_prep(const pgb_module *m);
+size_t pgb_size_of_scalar_big(const pgb_module *m);
+size_t pgb_bytes_of_vec_znx(const pgb_module *m, uint64_t cols, uint64_t size);
+size_t pgb_bytes_of_vec_znx_dft(const pgb_module *m, uint64_t cols, uint64_t size);
+size_t pgb_bytes_of_vec_znx_big(const pgb_module *m, uint64_t cols, uint64_t size);
+size_t pgb_bytes_of_svp_ppol(const pgb_module *m, uint64_t cols);
+size_t pgb_bytes_of_vmp_pmat(const pgb_module *m, uint64_t rows, uint64_t cols_in, uint64_t cols_out, uint64_t size);
+
+/* ---- vec_znx_dft (oep/hal_impl.rs:529-593; R6/R7/R12, F4) -------------------------------------- */
+/* HalImpl::vec_znx_dft_apply :529  (reference/ntt120/vec_znx_dft.rs:177-215, fft64/vec_znx_dft.rs:160-200) */
+int pgb_vec_znx_dft_apply(pgb_module *m, uint64_t step, uint64_t offset, pgb_vec_znx_dft *res, uint64_t res_col,
+                          const pgb_vec_znx *a, uint64_t a_col);
+int pgb_vec_znx_dft_apply_batched(pgb_module *m, uint64_t step, uint64_t offset, pgb_vec_znx_dft *res, uint64_t res_col,
+                                  const pgb_vec_znx *a, uint64_t a_col, const pgb_batch *bt);
+/* HalImpl::vec_znx_idft_apply_tmp_bytes :534 -- the GPU path needs no scratch (returns 0). */
+size_t pgb_vec_znx_idft_apply_tmp_bytes(const pgb_module *m);
+/* HalImpl::vec_znx_idft_apply :536 (ntt120/vec_znx_dft.rs:236-268, fft64/vec_znx_dft.rs:202-232) */
+int pgb_vec_znx_idft_apply(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx_dft *a, uint64_t a_col);
+int pgb_vec_znx_idft_apply_batched(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx_dft *a,
+                                   uint64_t a_col, const pgb_batch *bt);
+/* HalImpl::vec_znx_idft_apply_tmpa :541 (a may be clobbered) */
+int pgb_vec_znx_idft_apply_tmpa(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, pgb_vec_znx_dft *a, uint64_t a_col);
+/* HalImpl::vec_znx_idft_apply_consume :546 -- in place; afterwards a->data is a VecZnxBig(n, cols, size)
+ * (ntt120/vec_znx_dft.rs:327-409: big limb k at byte offset 16*n*k; fft64/vec_znx_dft.rs:264-288). */
+int pgb_vec_znx_idft_apply_consume(pgb_module *m, pgb_vec_znx_dft *a);
+int pgb_vec_znx_idft_apply_consume_batched(pgb_module *m, pgb_vec_znx_dft *a, const pgb_batch *bt);
+/* HalImpl::vec_znx_dft_add_into :553, add_scaled_assign :559, add_assign :564, sub :569, sub_assign :575,
+ * sub_negate_assign :580, copy :585, zero :590 (ntt120/vec_znx_dft.rs:418-652, fft64/vec_znx_dft.rs:13-157,290-405) */
+int pgb_vec_znx_dft_add_into(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a, uint64_t a_col,
+                             const pgb_vec_znx_dft *b, uint64_t b_col);
+int pgb_vec_znx_dft_add_scaled_assign(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a,
+                                      uint64_t a_col, int64_t a_scale);
+int pgb_vec_znx_dft_add_assign(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a, uint64_t a_col);
+int pgb_vec_znx_dft_sub(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a, uint64_t a_col,
+                        const pgb_vec_znx_dft *b, uint64_t b_col);
+int pgb_vec_znx_dft_sub_assign(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a, uint64_t a_col);
+int pgb_vec_znx_dft_sub_negate_assign(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a,
+                                      uint64_t a_col);
+int pgb_vec_znx_dft_copy(pgb_module *m, uint64_t step, uint64_t offset, pgb_vec_znx_dft *res, uint64_t res_col,
+                         const pgb_vec_znx_dft *a, uint64_t a_col);
+int pgb_vec_znx_dft_zero(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col);
+int pgb_vec_znx_dft_add_assign_batched(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a,
+                                       uint64_t a_col, const pgb_batch *bt);
+int pgb_vec_znx_dft_sub_assign_batched(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a,
+                                       uint64_t a_col, const pgb_batch *bt);
+int pgb_vec_znx_dft_copy_batched(pgb_module *m, uint64_t step, uint64_t offset, pgb_vec_znx_dft *res, uint64_t res_col,
+                                 const pgb_vec_znx_dft *a, uint64_t a_col, const pgb_batch *bt);
+int pgb_vec_znx_dft_zero_batched(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_batch *bt);
+
+/* ---- svp (oep/hal_impl.rs:595-616; R11, F6) ------------------------------------------------------ */
+/* HalImpl::svp_prepare :595 (ntt120/svp.rs:52-70, fft64/svp.rs:9-20) */
+int pgb_svp_prepare(pgb_module *m, pgb_svp_ppol *res, uint64_t res_col, const pgb_scalar_znx *a, uint64_t a_col);
+/* HalImpl::svp_apply_dft_to_dft :606 (ntt120/svp.rs:87-133, fft64/svp.rs:57-79) */
+int pgb_svp_apply_dft_to_dft(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_svp_ppol *a, uint64_t a_col,
+                             const pgb_vec_znx_dft *b, uint64_t b_col);
+/* bt->stride_a strides the SvpPPol (0 = shared), bt->stride_b strides b. */
+int pgb_svp_apply_dft_to_dft_batched(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_svp_ppol *a,
+                                     uint64_t a_col, const pgb_vec_znx_dft *b, uint64_t b_col, const pgb_batch *bt);
+/* HalImpl::svp_apply_dft_to_dft_assign :612 (ntt120/svp.rs:148-180, fft64/svp.rs:81-94) */
+int pgb_svp_apply_dft_to_dft_assign(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_svp_ppol *a,
+                                    uint64_t a_col);
+
+/* ---- vmp (oep/hal_impl.rs:618-668; R9/R10, F5) ---------------------------------------------------- */
+/* HalImpl::vmp_prepare_tmp_bytes :618 / vmp_apply_dft_to_dft_tmp_bytes :643 -- no scratch needed (0). */
+size_t pgb_vmp_prepare_tmp_bytes(const pgb_module *m, uint64_t rows, uint64_t cols_in, uint64_t cols_out, uint64_t size);
+size_t pgb_vmp_apply_dft_to_dft_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t a_size, uint64_t rows,
+                                          uint64_t cols_in, uint64_t cols_out, uint64_t size);
+/* HalImpl::vmp_prepare :620 (ntt120/vmp.rs:64-119, fft64/vmp.rs:52-93); `a` is a MatZnx of i64. */
+int pgb_vmp_prepare(pgb_module *m, pgb_vmp_pmat *res, const pgb_mat_znx *a);
+/* HalImpl::vmp_apply_dft_to_dft :653 (ntt120/vmp.rs:301-341 + core :169-288; fft64/vmp.rs:144-264).
+ * Overwrites res; limb_offset is in limbs and is scaled by cols_out exactly as ntt120/vmp.rs:335. */
+int pgb_vmp_apply_dft_to_dft(pgb_module *m, pgb_vec_znx_dft *res, const pgb_vec_znx_dft *a, const pgb_vmp_pmat *pmat,
+                             uint64_t limb_offset);
+/* bt->stride_a strides a, bt->stride_b strides pmat (0 = one matrix shared by the whole batch). */
+int pgb_vmp_apply_dft_to_dft_batched(pgb_module *m, pgb_vec_znx_dft *res, const pgb_vec_znx_dft *a,
+                                     const pgb_vmp_pmat *pmat, uint64_t limb_offset, const pgb_batch *bt);
+/* HalImpl::vmp_zero :665 */
+int pgb_vmp_zero(pgb_module *m, pgb_vmp_pmat *res);
+
+/* ---- vec_znx_big (oep/hal_impl.rs:323-527; R13/R14, F7) -------------------------------------------- */
+/* HalImpl::vec_znx_big_normalize_tmp_bytes :428 -- carries live in registers (0). */
+size_t pgb_vec_znx_big_normalize_tmp_bytes(const pgb_module *m);
+/* HalImpl::vec_znx_big_normalize :431 (ntt120/vec_znx_big.rs:1383-1402 -> :367-446 / :453-597;
+ * fft64/vec_znx_big.rs:241-278 -> reference/vec_znx/normalize.rs:18-426) */
+int pgb_vec_znx_big_normalize(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, int64_t res_offset, uint64_t res_col,
+                              const pgb_vec_znx_big *a, uint64_t a_base2k, uint64_t a_col);
+int pgb_vec_znx_big_normalize_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, int64_t res_offset,
+                                      uint64_t res_col, const pgb_vec_znx_big *a, uint64_t a_base2k, uint64_t a_col,
+                                      const pgb_batch *bt);
+/* HalImpl::vec_znx_big_normalize_add_assign :478 / _sub_assign :498 (ntt120/vec_znx_big.rs:600-803,1405-1461) */
+int pgb_vec_znx_big_normalize_add_assign(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, int64_t res_offset,
+                                         uint64_t res_col, const pgb_vec_znx_big *a, uint64_t a_base2k, uint64_t a_col);
+int pgb_vec_znx_big_normalize_sub_assign(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, int64_t res_offset,
+                                         uint64_t res_col, const pgb_vec_znx_big *a, uint64_t a_base2k, uint64_t a_col);
+/* HalImpl::vec_znx_big_add_small_assign :362 (ntt120/vec_znx_big.rs:1128-1140) */
+int pgb_vec_znx_big_add_small_assign(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col);
+int pgb_vec_znx_big_add_small_assign_batched(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx *a,
+                                             uint64_t a_col, const pgb_batch *bt);
+/* HalImpl::vec_znx_big_from_small :323 */
+int pgb_vec_znx_big_from_small(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col);
+
+/* ---- coefficient-domain helpers used by the compositions (oep/hal_impl.rs:41-53, :225-228) ---------- */
+/* HalImpl::vec_znx_normalize :41 (reference/vec_znx/normalize.rs:18-50) */
+int pgb_vec_znx_normalize(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, int64_t res_offset, uint64_t res_col,
+                          const pgb_vec_znx *a, uint64_t a_base2k, uint64_t a_col);
+int pgb_vec_znx_normalize_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, int64_t res_offset,
+                                  uint64_t res_col, const pgb_vec_znx *a, uint64_t a_base2k, uint64_t a_col,
+                                  const pgb_batch *bt);
+/* HalImpl::vec_znx_rotate :225 (reference/vec_znx/rotate.rs:9-38) */
+int pgb_vec_znx_rotate(pgb_module *m, int64_t p, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col);
+
+/* ---- CoreImpl tier: fused, device-resident, batched pipelines (poulpy-core/src/oep/core_impl.rs:36-52,114-130) ---- */
+/* Device scratch needed by the batched pipelines below (bytes; pass a pgb_alloc_device_bytes buffer). */
+size_t pgb_glwe_keyswitch_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t a_size, uint64_t a_base2k,
+                                    const pgb_vmp_pmat *key, uint64_t key_base2k, uint64_t dsize, uint64_t batch);
+/* CoreImpl::glwe_keyswitch (poulpy-core/src/keyswitching/glwe.rs:53-109, :207-239, :298-380; C1).
+ * res/a are GLWE data VecZnx(rank+1, size); item b at data + b*stride.  key = GGLWEPrepared.data:
+ * VmpPMat(dnum, rank_in, rank_out+1, key_size), shared by the batch. */
+int pgb_glwe_keyswitch_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, const pgb_vec_znx *a, uint64_t a_base2k,
+                               const pgb_vmp_pmat *key, uint64_t key_base2k, uint64_t dsize, const pgb_batch *bt,
+                               void *scratch, size_t scratch_len);
+size_t pgb_glwe_external_product_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t a_size, uint64_t a_base2k,
+                                           const pgb_vmp_pmat *ggsw, uint64_t ggsw_base2k, uint64_t dsize, uint64_t batch);
+/* CoreImpl::glwe_external_product (poulpy-core/src/external_product/glwe.rs:99-141, :197-271; C2).
+ * ggsw = GGSWPrepared.data: VmpPMat(dnum, rank+1, rank+1, size), shared by the batch. */
+int pgb_glwe_external_product_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, const pgb_vec_znx *a,
+                                      uint64_t a_base2k, const pgb_vmp_pmat *ggsw, uint64_t ggsw_base2k, uint64_t dsize,
+                                      const pgb_batch *bt, void *scratch, size_t scratch_len);
+
+/* Host-buffer front ends: `res_host` / `a_host` are ordinary host arrays of `count` GLWE VecZnx; the
+ * library stages them through pinned memory in chunks, overlapping H2D, compute and D2H on the module's
+ * streams, and returns when `res_host` is complete.  This is what a HalImpl/CoreImpl over host-resident
+ * `Vec<u8>` buffers sees. */
+int pgb_glwe_keyswitch_host(pgb_module *m, int64_t *res_host, uint64_t res_size, uint64_t res_base2k, const int64_t *a_host,
+                            uint64_t a_size, uint64_t a_base2k, uint64_t rank_in, uint64_t rank_out,
+                            const pgb_vmp_pmat *key, uint64_t key_base2k, uint64_t dsize, uint64_t count);
+int pgb_glwe_external_product_host(pgb_module *m, int64_t *res_host, uint64_t res_size, uint64_t res_base2k,
+                                   const int64_t *a_host, uint64_t a_size, uint64_t a_base2k, uint64_t rank,
+                                   const pgb_vmp_pmat *ggsw, uint64_t ggsw_base2k, uint64_t dsize, uint64_t count);
+
+/* ---- CGGI blind rotation (poulpy-bin-fhe/src/blind_rotation/algorithms/cggi/algorithm.rs:275-368; C3) ---- */
+/* x_pow_a table of the prepared key (cggi/key_prepared.rs:66-75): SvpPPol with 2n columns, col i = X^i. */
+int pgb_cggi_x_pow_a(pgb_module *m, pgb_svp_ppol *res);
+size_t pgb_cggi_blind_rotate_tmp_bytes(const pgb_module *m, uint64_t rank, uint64_t res_size, uint64_t dnum, uint64_t brk_size,
+                                       uint64_t batch);
+/* execute_block_binary over a batch of mod-switched LWEs.
+ *   res    : `count` GLWE VecZnx(rank+1, res_size), stride bt->stride_res
+ *   lwe_2n : device int64 [count][n_lwe+1] = (b, a_0..a_{n_lwe-1}) after mod_switch_2n (algorithms/mod.rs:136-176)
+ *   lut    : VecZnx(1, lut_size) shared by the batch
+ *   brk    : n_lwe prepared GGSWs, VmpPMat(dnum, rank+1, rank+1, brk_size) each, consecutive in memory
+ *            (`brk->data` + i * bytes_of_vmp_pmat) */
+int pgb_cggi_blind_rotate_batched(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2n, uint64_t n_lwe, const pgb_vec_znx *lut,
+                                  const pgb_vmp_pmat *brk, const pgb_svp_ppol *x_pow_a, uint64_t block_size, uint64_t base2k,
+                                  const pgb_batch *bt, void *scratch, size_t scratch_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

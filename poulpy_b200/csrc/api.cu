@@ -1,0 +1,596 @@
+// api.cu -- the C ABI (include/poulpy_b200.h): module / memory management and the HalImpl-shaped entry points.
+// Shape rules (min sizes, zero tails, limb_offset, step/offset gathers) restate the reference HAL semantics cited in
+// the header; all arithmetic is in the kernels of ntt120_dft.cu, ntt120_ops.cu, fft64.cu and big.cu.
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+static thread_local char g_err[512] = "";
+void pgb_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+extern "C" const char *pgb_last_error(void) { return g_err; }
+
+extern "C" int pgb_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) return 0;
+    return c;
+}
+
+// ---- module -------------------------------------------------------------------------------------------
+extern "C" int pgb_module_new(uint64_t n, int flavour, int device, pgb_module **out) {
+    PGB_REQUIRE(out != nullptr, "pgb_module_new: out is null");
+    *out = nullptr;
+    PGB_REQUIRE(n >= 16 && n <= (1u << 16) && (n & (n - 1)) == 0, "pgb_module_new: n must be a power of two in [16, 2^16], got %llu",
+                (unsigned long long)n);
+    PGB_REQUIRE(flavour == PGB_NTT120 || flavour == PGB_FFT64, "pgb_module_new: unknown flavour %d", flavour);
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0) {
+        pgb_set_error("pgb_module_new: no CUDA device available (%s); this backend has no CPU fallback",
+                      e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return PGB_ERR_CUDA;
+    }
+    PGB_REQUIRE(device >= 0 && device < cnt, "pgb_module_new: device %d out of range [0, %d)", device, cnt);
+    PGB_CHECK_CUDA(cudaSetDevice(device));
+    pgb_module *m = (pgb_module *)calloc(1, sizeof(pgb_module));
+    m->n = n;
+    m->log_n = ilog2_u64(n);
+    m->flavour = flavour;
+    m->device = device;
+    PGB_CHECK_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    m->own_stream = true;
+    for (int i = 0; i < 2; i++) PGB_CHECK_CUDA(cudaStreamCreateWithFlags(&m->aux_stream[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) PGB_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev[i], cudaEventDisableTiming));
+    int s = flavour == PGB_NTT120 ? ntt120_module_init(m) : fft64_module_init(m);
+    if (s != PGB_OK) {
+        pgb_module_destroy(m);
+        return s;
+    }
+    *out = m;
+    return PGB_OK;
+}
+
+extern "C" void pgb_module_destroy(pgb_module *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    cudaFree(m->ntt_fwd);
+    cudaFree(m->ntt_inv);
+    cudaFree(m->fft_fwd);
+    cudaFree(m->fft_inv);
+    cudaFree(m->ws);
+    for (int i = 0; i < 4; i++)
+        if (m->pinned[i]) cudaFreeHost(m->pinned[i]);
+    if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
+    for (int i = 0; i < 2; i++)
+        if (m->aux_stream[i]) cudaStreamDestroy(m->aux_stream[i]);
+    for (int i = 0; i < 8; i++)
+        if (m->ev[i]) cudaEventDestroy(m->ev[i]);
+    free(m);
+}
+extern "C" uint64_t pgb_module_n(const pgb_module *m) { return m->n; }
+extern "C" int pgb_module_flavour(const pgb_module *m) { return m->flavour; }
+extern "C" uint64_t pgb_module_launch_count(const pgb_module *m) { return m->launches; }
+extern "C" int pgb_module_set_stream(pgb_module *m, void *cuda_stream) {
+    PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
+    if (cuda_stream == nullptr) {
+        PGB_CHECK_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+        m->own_stream = true;
+    } else {
+        m->stream = (cudaStream_t)cuda_stream;
+        m->own_stream = false;
+    }
+    return PGB_OK;
+}
+extern "C" int pgb_module_sync(pgb_module *m) {
+    PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+    return PGB_OK;
+}
+
+// ---- memory ---------------------------------------------------------------------------------------------
+extern "C" void *pgb_alloc_bytes(size_t len) {
+    void *p = nullptr;
+    if (cudaMallocManaged(&p, len ? len : 1) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, len);
+    cudaDeviceSynchronize();
+    return p;
+}
+extern "C" void *pgb_alloc_device_bytes(size_t len) {
+    void *p = nullptr;
+    if (cudaMalloc(&p, len ? len : 1) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, len);
+    return p;
+}
+extern "C" void *pgb_alloc_pinned_bytes(size_t len) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, len ? len : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void pgb_free(void *p) { cudaFree(p); }
+extern "C" void pgb_free_pinned(void *p) { cudaFreeHost(p); }
+extern "C" int pgb_memcpy_h2d(void *dst, const void *src, size_t len) {
+    PGB_CHECK_CUDA(cudaMemcpy(dst, src, len, cudaMemcpyHostToDevice));
+    return PGB_OK;
+}
+extern "C" int pgb_memcpy_d2h(void *dst, const void *src, size_t len) {
+    PGB_CHECK_CUDA(cudaMemcpy(dst, src, len, cudaMemcpyDeviceToHost));
+    return PGB_OK;
+}
+extern "C" int pgb_memcpy_d2d(void *dst, const void *src, size_t len) {
+    PGB_CHECK_CUDA(cudaMemcpy(dst, src, len, cudaMemcpyDeviceToDevice));
+    return PGB_OK;
+}
+extern "C" int pgb_memset(void *dst, int byte, size_t len) {
+    PGB_CHECK_CUDA(cudaMemset(dst, byte, len));
+    return PGB_OK;
+}
+
+extern "C" size_t pgb_size_of_scalar_prep(const pgb_module *m) { return prep_bytes(m); }
+extern "C" size_t pgb_size_of_scalar_big(const pgb_module *m) { return big_bytes(m); }
+extern "C" size_t pgb_bytes_of_vec_znx(const pgb_module *m, uint64_t cols, uint64_t size) { return m->n * cols * size * 8; }
+extern "C" size_t pgb_bytes_of_vec_znx_dft(const pgb_module *m, uint64_t cols, uint64_t size) { return m->n * cols * size * prep_bytes(m); }
+extern "C" size_t pgb_bytes_of_vec_znx_big(const pgb_module *m, uint64_t cols, uint64_t size) { return m->n * cols * size * big_bytes(m); }
+extern "C" size_t pgb_bytes_of_svp_ppol(const pgb_module *m, uint64_t cols) { return m->n * cols * prep_bytes(m); }
+extern "C" size_t pgb_bytes_of_vmp_pmat(const pgb_module *m, uint64_t rows, uint64_t cols_in, uint64_t cols_out, uint64_t size) {
+    return m->n * rows * cols_in * cols_out * size * prep_bytes(m);
+}
+
+// ---- helpers ----------------------------------------------------------------------------------------------
+static const pgb_batch ONE = {1, 0, 0, 0};
+#define CHECK_BATCH(bt)                                                                          \
+    PGB_REQUIRE((bt) != nullptr && (bt)->count <= 65535, "batch count must be <= 65535 per call (got %llu)", \
+                (unsigned long long)((bt) ? (bt)->count : 0))
+#define CHECK_N(v, what) PGB_REQUIRE((v)->n == m->n, what ": n = %llu does not match the module (%llu)", (unsigned long long)(v)->n, (unsigned long long)m->n)
+#define CHECK_COL(v, col, what) PGB_REQUIRE((col) < (v)->cols, what ": column %llu out of range (cols = %llu)", (unsigned long long)(col), (unsigned long long)(v)->cols)
+
+static int sync_if(pgb_module *m, bool sync) {
+    if (sync) PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+    return PGB_OK;
+}
+
+// ---- vec_znx_dft_apply -------------------------------------------------------------------------------------
+static int dft_apply_impl(pgb_module *m, uint64_t step, uint64_t offset, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx *a,
+                          uint64_t a_col, const pgb_batch *bt) {
+    CHECK_BATCH(bt);
+    CHECK_N(res, "vec_znx_dft_apply(res)");
+    CHECK_N(a, "vec_znx_dft_apply(a)");
+    CHECK_COL(res, res_col, "vec_znx_dft_apply(res)");
+    CHECK_COL(a, a_col, "vec_znx_dft_apply(a)");
+    PGB_REQUIRE(step > 0, "vec_znx_dft_apply: step must be > 0");
+    const uint64_t n = m->n, pb = prep_bytes(m);
+    const uint64_t steps = div_ceil64(a->size, step);
+    const uint64_t min_steps = umin64(res->size, steps);
+    // limbs j < nvalid have a source limb offset + j*step < a.size
+    uint64_t nvalid = offset < a->size ? umin64(min_steps, div_ceil64(a->size - offset, step)) : 0;
+    LimbSet in = {(char *)a->data + limb_off(n, a->cols, a_col, offset, 8), step * a->cols * n * 8, bt->stride_a};
+    LimbSet out = {(char *)res->data + limb_off(n, res->cols, res_col, 0, pb), res->cols * n * pb, bt->stride_res};
+    if (m->flavour == PGB_NTT120) {
+        PGB_TRY(ntt120_forward(m, in, out, (int)nvalid, (int)bt->count));
+        // ntt120/vec_znx_dft.rs:201-214: every other limb of the column is zeroed
+        LimbSet z = out;
+        z.base += nvalid * out.limb_stride;
+        PGB_TRY(raw_limbs(m, true, z, z, n * pb, (uint32_t)(res->size - nvalid), (uint32_t)bt->count));
+    } else {
+        PGB_TRY(fft64_forward(m, in, out, (int)nvalid, (int)bt->count));
+        // fft64/vec_znx_dft.rs:189-199: only limbs >= min_steps are zeroed; limbs in [nvalid, min_steps) stay untouched
+        LimbSet z = out;
+        z.base += min_steps * out.limb_stride;
+        PGB_TRY(raw_limbs(m, true, z, z, n * pb, (uint32_t)(res->size - min_steps), (uint32_t)bt->count));
+    }
+    return PGB_OK;
+}
+extern "C" int pgb_vec_znx_dft_apply(pgb_module *m, uint64_t step, uint64_t offset, pgb_vec_znx_dft *res, uint64_t res_col,
+                                     const pgb_vec_znx *a, uint64_t a_col) {
+    PGB_TRY(dft_apply_impl(m, step, offset, res, res_col, a, a_col, &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_vec_znx_dft_apply_batched(pgb_module *m, uint64_t step, uint64_t offset, pgb_vec_znx_dft *res, uint64_t res_col,
+                                             const pgb_vec_znx *a, uint64_t a_col, const pgb_batch *bt) {
+    return dft_apply_impl(m, step, offset, res, res_col, a, a_col, bt);
+}
+
+// ---- vec_znx_idft_apply ------------------------------------------------------------------------------------
+extern "C" size_t pgb_vec_znx_idft_apply_tmp_bytes(const pgb_module *) { return 0; }
+
+static int idft_apply_impl(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx_dft *a, uint64_t a_col,
+                           const pgb_batch *bt) {
+    CHECK_BATCH(bt);
+    CHECK_N(res, "vec_znx_idft_apply(res)");
+    CHECK_N(a, "vec_znx_idft_apply(a)");
+    CHECK_COL(res, res_col, "vec_znx_idft_apply(res)");
+    CHECK_COL(a, a_col, "vec_znx_idft_apply(a)");
+    const uint64_t n = m->n, pb = prep_bytes(m), bb = big_bytes(m);
+    const uint64_t min_size = umin64(res->size, a->size);
+    LimbSet in = {(char *)a->data + limb_off(n, a->cols, a_col, 0, pb), a->cols * n * pb, bt->stride_a};
+    LimbSet out = {(char *)res->data + limb_off(n, res->cols, res_col, 0, bb), res->cols * n * bb, bt->stride_res};
+    if (m->flavour == PGB_NTT120) PGB_TRY(ntt120_inverse_big(m, in, out, (int)min_size, (int)bt->count));
+    else PGB_TRY(fft64_inverse_big(m, in, out, (int)min_size, (int)bt->count));
+    LimbSet z = out;
+    z.base += min_size * out.limb_stride;
+    return raw_limbs(m, true, z, z, n * bb, (uint32_t)(res->size - min_size), (uint32_t)bt->count);
+}
+extern "C" int pgb_vec_znx_idft_apply(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx_dft *a, uint64_t a_col) {
+    PGB_TRY(idft_apply_impl(m, res, res_col, a, a_col, &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_vec_znx_idft_apply_batched(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx_dft *a,
+                                              uint64_t a_col, const pgb_batch *bt) {
+    return idft_apply_impl(m, res, res_col, a, a_col, bt);
+}
+extern "C" int pgb_vec_znx_idft_apply_tmpa(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, pgb_vec_znx_dft *a, uint64_t a_col) {
+    // `a` may be clobbered by the reference; this backend leaves it intact (allowed: tmpa only permits, never requires, it)
+    return pgb_vec_znx_idft_apply(m, res, res_col, a, a_col);
+}
+static int idft_consume_impl(pgb_module *m, pgb_vec_znx_dft *a, const pgb_batch *bt) {
+    CHECK_BATCH(bt);
+    CHECK_N(a, "vec_znx_idft_apply_consume(a)");
+    const uint64_t n = m->n, pb = prep_bytes(m), bb = big_bytes(m);
+    PGB_REQUIRE(bb <= pb, "vec_znx_idft_apply_consume: ScalarBig larger than ScalarPrep");
+    // flat limb k: DFT limb at k*n*pb, big limb at k*n*bb (vec_znx_dft.rs:327-409); pb == bb for both flavours here
+    LimbSet in = {(char *)a->data, n * pb, bt->stride_res};
+    LimbSet out = {(char *)a->data, n * bb, bt->stride_res};
+    const int jobs = (int)(a->cols * a->size);
+    if (m->flavour == PGB_NTT120) return ntt120_inverse_big(m, in, out, jobs, (int)bt->count);
+    return fft64_inverse_big(m, in, out, jobs, (int)bt->count);
+}
+extern "C" int pgb_vec_znx_idft_apply_consume(pgb_module *m, pgb_vec_znx_dft *a) {
+    PGB_TRY(idft_consume_impl(m, a, &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_vec_znx_idft_apply_consume_batched(pgb_module *m, pgb_vec_znx_dft *a, const pgb_batch *bt) {
+    return idft_consume_impl(m, a, bt);
+}
+
+// ---- DFT-domain add / sub / copy / zero ----------------------------------------------------------------------
+static LimbSet dft_col(const pgb_module *m, const pgb_vec_znx_dft *v, uint64_t col, uint64_t first_limb, uint64_t bstride) {
+    const uint64_t pb = prep_bytes(m);
+    LimbSet s = {(char *)v->data + limb_off(m->n, v->cols, col, first_limb, pb), v->cols * m->n * pb, bstride};
+    return s;
+}
+static int dft_ew(pgb_module *m, int op, LimbSet dst, LimbSet a, LimbSet b, uint64_t jobs, uint64_t batch) {
+    if (op == EW_COPY || op == EW_ZERO) return raw_limbs(m, op == EW_ZERO, dst, a, m->n * prep_bytes(m), (uint32_t)jobs, (uint32_t)batch);
+    if (m->flavour == PGB_NTT120) return ntt120_ew(m, op, dst, a, b, (uint32_t)jobs, (uint32_t)batch);
+    return fft64_ew(m, op, dst, a, b, (uint32_t)jobs, (uint32_t)batch);
+}
+static LimbSet shift(LimbSet s, uint64_t limbs) {
+    s.base += limbs * s.limb_stride;
+    return s;
+}
+
+// add_into / sub share the size rules of vec_znx_dft.rs:418-470 / :522-580
+static int dft_addsub_into(pgb_module *m, bool sub, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a, uint64_t a_col,
+                           const pgb_vec_znx_dft *b, uint64_t b_col) {
+    CHECK_N(res, "vec_znx_dft_add/sub(res)");
+    CHECK_N(a, "vec_znx_dft_add/sub(a)");
+    CHECK_N(b, "vec_znx_dft_add/sub(b)");
+    CHECK_COL(res, res_col, "vec_znx_dft_add/sub(res)");
+    CHECK_COL(a, a_col, "vec_znx_dft_add/sub(a)");
+    CHECK_COL(b, b_col, "vec_znx_dft_add/sub(b)");
+    LimbSet R = dft_col(m, res, res_col, 0, 0), A = dft_col(m, a, a_col, 0, 0), B = dft_col(m, b, b_col, 0, 0);
+    const uint64_t rs = res->size;
+    const bool a_small = a->size <= b->size;
+    const uint64_t sum = umin64(a_small ? a->size : b->size, rs), cpy = umin64(a_small ? b->size : a->size, rs);
+    PGB_TRY(dft_ew(m, sub ? EW_SUB : EW_ADD, R, A, B, sum, 1));
+    if (a_small) PGB_TRY(dft_ew(m, sub ? EW_NEG : EW_COPY, shift(R, sum), shift(B, sum), shift(B, sum), cpy - sum, 1));
+    else PGB_TRY(dft_ew(m, EW_COPY, shift(R, sum), shift(A, sum), shift(A, sum), cpy - sum, 1));
+    PGB_TRY(dft_ew(m, EW_ZERO, shift(R, cpy), shift(R, cpy), shift(R, cpy), rs - cpy, 1));
+    return sync_if(m, true);
+}
+extern "C" int pgb_vec_znx_dft_add_into(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a, uint64_t a_col,
+                                        const pgb_vec_znx_dft *b, uint64_t b_col) {
+    return dft_addsub_into(m, false, res, res_col, a, a_col, b, b_col);
+}
+extern "C" int pgb_vec_znx_dft_sub(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a, uint64_t a_col,
+                                   const pgb_vec_znx_dft *b, uint64_t b_col) {
+    return dft_addsub_into(m, true, res, res_col, a, a_col, b, b_col);
+}
+static int dft_assign_impl(pgb_module *m, int op, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a, uint64_t a_col,
+                           uint64_t res_first, uint64_t a_first, uint64_t count, const pgb_batch *bt) {
+    CHECK_BATCH(bt);
+    CHECK_N(res, "vec_znx_dft_*_assign(res)");
+    CHECK_N(a, "vec_znx_dft_*_assign(a)");
+    CHECK_COL(res, res_col, "vec_znx_dft_*_assign(res)");
+    CHECK_COL(a, a_col, "vec_znx_dft_*_assign(a)");
+    LimbSet R = dft_col(m, res, res_col, res_first, bt->stride_res), A = dft_col(m, a, a_col, a_first, bt->stride_a);
+    return dft_ew(m, op, R, R, A, count, bt->count); // R = R op A
+}
+extern "C" int pgb_vec_znx_dft_add_assign(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a, uint64_t a_col) {
+    PGB_TRY(dft_assign_impl(m, EW_ADD, res, res_col, a, a_col, 0, 0, umin64(res->size, a->size), &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_vec_znx_dft_add_assign_batched(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a,
+                                                  uint64_t a_col, const pgb_batch *bt) {
+    return dft_assign_impl(m, EW_ADD, res, res_col, a, a_col, 0, 0, umin64(res->size, a->size), bt);
+}
+extern "C" int pgb_vec_znx_dft_sub_assign(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a, uint64_t a_col) {
+    PGB_TRY(dft_assign_impl(m, EW_SUB, res, res_col, a, a_col, 0, 0, umin64(res->size, a->size), &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_vec_znx_dft_sub_assign_batched(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a,
+                                                  uint64_t a_col, const pgb_batch *bt) {
+    return dft_assign_impl(m, EW_SUB, res, res_col, a, a_col, 0, 0, umin64(res->size, a->size), bt);
+}
+// vec_znx_dft.rs:488-520
+extern "C" int pgb_vec_znx_dft_add_scaled_assign(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a,
+                                                 uint64_t a_col, int64_t a_scale) {
+    const uint64_t rs = res->size, as = a->size;
+    if (a_scale > 0) {
+        const uint64_t sh = umin64((uint64_t)a_scale, as), mn = umin64(as, rs);
+        PGB_TRY(dft_assign_impl(m, EW_ADD, res, res_col, a, a_col, 0, sh, mn > sh ? mn - sh : 0, &ONE));
+    } else if (a_scale < 0) {
+        const uint64_t sh = umin64((uint64_t)(-a_scale), rs);
+        PGB_TRY(dft_assign_impl(m, EW_ADD, res, res_col, a, a_col, sh, 0, umin64(as, rs - sh), &ONE));
+    } else {
+        PGB_TRY(dft_assign_impl(m, EW_ADD, res, res_col, a, a_col, 0, 0, umin64(as, rs), &ONE));
+    }
+    return sync_if(m, true);
+}
+// vec_znx_dft.rs:598-616: res = a - res over min sizes, res = -res on the remaining limbs
+extern "C" int pgb_vec_znx_dft_sub_negate_assign(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a,
+                                                 uint64_t a_col) {
+    CHECK_N(res, "vec_znx_dft_sub_negate_assign(res)");
+    CHECK_N(a, "vec_znx_dft_sub_negate_assign(a)");
+    CHECK_COL(res, res_col, "vec_znx_dft_sub_negate_assign(res)");
+    CHECK_COL(a, a_col, "vec_znx_dft_sub_negate_assign(a)");
+    const uint64_t rs = res->size, sum = umin64(rs, a->size);
+    LimbSet R = dft_col(m, res, res_col, 0, 0), A = dft_col(m, a, a_col, 0, 0);
+    PGB_TRY(dft_ew(m, EW_SUB, R, A, R, sum, 1));
+    PGB_TRY(dft_ew(m, EW_NEG, shift(R, sum), shift(R, sum), shift(R, sum), rs - sum, 1));
+    return sync_if(m, true);
+}
+static int dft_copy_impl(pgb_module *m, uint64_t step, uint64_t offset, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a,
+                         uint64_t a_col, const pgb_batch *bt) {
+    CHECK_BATCH(bt);
+    CHECK_N(res, "vec_znx_dft_copy(res)");
+    CHECK_N(a, "vec_znx_dft_copy(a)");
+    CHECK_COL(res, res_col, "vec_znx_dft_copy(res)");
+    CHECK_COL(a, a_col, "vec_znx_dft_copy(a)");
+    PGB_REQUIRE(step > 0, "vec_znx_dft_copy: step must be > 0");
+    const uint64_t steps = div_ceil64(a->size, step), min_steps = umin64(res->size, steps);
+    const uint64_t nvalid = offset < a->size ? umin64(min_steps, div_ceil64(a->size - offset, step)) : 0;
+    LimbSet R = dft_col(m, res, res_col, 0, bt->stride_res);
+    LimbSet A = dft_col(m, a, a_col, offset, bt->stride_a);
+    A.limb_stride *= step;
+    PGB_TRY(dft_ew(m, EW_COPY, R, A, A, nvalid, bt->count));
+    return dft_ew(m, EW_ZERO, shift(R, nvalid), shift(R, nvalid), shift(R, nvalid), res->size - nvalid, bt->count);
+}
+extern "C" int pgb_vec_znx_dft_copy(pgb_module *m, uint64_t step, uint64_t offset, pgb_vec_znx_dft *res, uint64_t res_col,
+                                    const pgb_vec_znx_dft *a, uint64_t a_col) {
+    PGB_TRY(dft_copy_impl(m, step, offset, res, res_col, a, a_col, &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_vec_znx_dft_copy_batched(pgb_module *m, uint64_t step, uint64_t offset, pgb_vec_znx_dft *res, uint64_t res_col,
+                                            const pgb_vec_znx_dft *a, uint64_t a_col, const pgb_batch *bt) {
+    return dft_copy_impl(m, step, offset, res, res_col, a, a_col, bt);
+}
+static int dft_zero_impl(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_batch *bt) {
+    CHECK_BATCH(bt);
+    CHECK_N(res, "vec_znx_dft_zero(res)");
+    CHECK_COL(res, res_col, "vec_znx_dft_zero(res)");
+    LimbSet R = dft_col(m, res, res_col, 0, bt->stride_res);
+    return dft_ew(m, EW_ZERO, R, R, R, res->size, bt->count);
+}
+extern "C" int pgb_vec_znx_dft_zero(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col) {
+    PGB_TRY(dft_zero_impl(m, res, res_col, &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_vec_znx_dft_zero_batched(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_batch *bt) {
+    return dft_zero_impl(m, res, res_col, bt);
+}
+
+// ---- svp ------------------------------------------------------------------------------------------------------
+extern "C" int pgb_svp_prepare(pgb_module *m, pgb_svp_ppol *res, uint64_t res_col, const pgb_scalar_znx *a, uint64_t a_col) {
+    CHECK_N(res, "svp_prepare(res)");
+    CHECK_N(a, "svp_prepare(a)");
+    CHECK_COL(res, res_col, "svp_prepare(res)");
+    CHECK_COL(a, a_col, "svp_prepare(a)");
+    const uint64_t n = m->n, pb = prep_bytes(m);
+    LimbSet in = {(char *)a->data + a_col * n * 8, 0, 0};
+    LimbSet out = {(char *)res->data + res_col * n * pb, 0, 0};
+    if (m->flavour == PGB_NTT120) PGB_TRY(ntt120_forward(m, in, out, 1, 1));
+    else PGB_TRY(fft64_forward(m, in, out, 1, 1));
+    return sync_if(m, true);
+}
+static int svp_apply_impl(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_svp_ppol *a, uint64_t a_col,
+                          const pgb_vec_znx_dft *b, uint64_t b_col, const pgb_batch *bt) {
+    CHECK_BATCH(bt);
+    CHECK_N(res, "svp_apply_dft_to_dft(res)");
+    CHECK_N(a, "svp_apply_dft_to_dft(a)");
+    CHECK_N(b, "svp_apply_dft_to_dft(b)");
+    CHECK_COL(res, res_col, "svp_apply_dft_to_dft(res)");
+    CHECK_COL(a, a_col, "svp_apply_dft_to_dft(a)");
+    CHECK_COL(b, b_col, "svp_apply_dft_to_dft(b)");
+    const uint64_t pb = prep_bytes(m);
+    const uint64_t min_size = umin64(res->size, b->size);
+    LimbSet R = dft_col(m, res, res_col, 0, bt->stride_res), B = dft_col(m, b, b_col, 0, bt->stride_b);
+    LimbSet P = {(char *)a->data + a_col * m->n * pb, 0, bt->stride_a}; // same ppol for every limb
+    PGB_TRY(dft_ew(m, EW_MUL, R, P, B, min_size, bt->count));
+    return dft_ew(m, EW_ZERO, shift(R, min_size), shift(R, min_size), shift(R, min_size), res->size - min_size, bt->count);
+}
+extern "C" int pgb_svp_apply_dft_to_dft(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_svp_ppol *a, uint64_t a_col,
+                                        const pgb_vec_znx_dft *b, uint64_t b_col) {
+    PGB_TRY(svp_apply_impl(m, res, res_col, a, a_col, b, b_col, &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_svp_apply_dft_to_dft_batched(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_svp_ppol *a,
+                                                uint64_t a_col, const pgb_vec_znx_dft *b, uint64_t b_col, const pgb_batch *bt) {
+    return svp_apply_impl(m, res, res_col, a, a_col, b, b_col, bt);
+}
+extern "C" int pgb_svp_apply_dft_to_dft_assign(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_svp_ppol *a,
+                                               uint64_t a_col) {
+    CHECK_N(res, "svp_apply_dft_to_dft_assign(res)");
+    CHECK_N(a, "svp_apply_dft_to_dft_assign(a)");
+    CHECK_COL(res, res_col, "svp_apply_dft_to_dft_assign(res)");
+    CHECK_COL(a, a_col, "svp_apply_dft_to_dft_assign(a)");
+    LimbSet R = dft_col(m, res, res_col, 0, 0);
+    LimbSet P = {(char *)a->data + a_col * m->n * prep_bytes(m), 0, 0};
+    PGB_TRY(dft_ew(m, EW_MUL, R, P, R, res->size, 1));
+    return sync_if(m, true);
+}
+
+// ---- vmp --------------------------------------------------------------------------------------------------------
+extern "C" size_t pgb_vmp_prepare_tmp_bytes(const pgb_module *, uint64_t, uint64_t, uint64_t, uint64_t) { return 0; }
+extern "C" size_t pgb_vmp_apply_dft_to_dft_tmp_bytes(const pgb_module *, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t) { return 0; }
+
+extern "C" int pgb_vmp_prepare(pgb_module *m, pgb_vmp_pmat *res, const pgb_mat_znx *a) {
+    CHECK_N(res, "vmp_prepare(res)");
+    CHECK_N(a, "vmp_prepare(a)");
+    PGB_REQUIRE(res->rows == a->rows && res->cols_in == a->cols_in && res->cols_out == a->cols_out && res->size == a->size,
+                "vmp_prepare: shape mismatch between VmpPMat and MatZnx");
+    // MatZnx poly (row_i, col_i) at n*(row_i*ncols + col_i) i64 (mat_znx.rs:161-176) -> pmat poly (row_i*ncols + col_i): one
+    // forward transform per polynomial, written straight into the [row][col] layout.
+    const uint64_t n = m->n, pb = prep_bytes(m);
+    const uint64_t polys = a->rows * a->cols_in * a->cols_out * a->size;
+    LimbSet in = {(char *)a->data, n * 8, 0};
+    LimbSet out = {(char *)res->data, n * pb, 0};
+    if (m->flavour == PGB_NTT120) PGB_TRY(ntt120_forward(m, in, out, (int)polys, 1));
+    else PGB_TRY(fft64_forward(m, in, out, (int)polys, 1));
+    return sync_if(m, true);
+}
+
+int vmp_apply_impl(pgb_module *m, pgb_vec_znx_dft *res, const pgb_vec_znx_dft *a, const pgb_vmp_pmat *pmat, uint64_t limb_offset,
+                   const pgb_batch *bt) {
+    CHECK_BATCH(bt);
+    CHECK_N(res, "vmp_apply_dft_to_dft(res)");
+    CHECK_N(a, "vmp_apply_dft_to_dft(a)");
+    CHECK_N(pmat, "vmp_apply_dft_to_dft(pmat)");
+    const uint64_t n = m->n, pb = prep_bytes(m), poly = n * pb;
+    const uint64_t nrows = pmat->cols_in * pmat->rows, ncols = pmat->cols_out * pmat->size;
+    const uint64_t a_polys = a->cols * a->size, res_polys = res->cols * res->size;
+    const uint64_t off = limb_offset * pmat->cols_out; // ntt120/vmp.rs:335, fft64/vmp.rs:177
+    const uint64_t row_max = umin64(nrows, a_polys);
+    LimbSet R = {(char *)res->data, poly, bt->stride_res};
+    if (m->flavour == PGB_NTT120) {
+        const uint64_t col_max = umin64(ncols, res_polys + off); // ntt120/vmp.rs:189-190
+        if (off >= col_max) return raw_limbs(m, true, R, R, poly, (uint32_t)res_polys, (uint32_t)bt->count);
+        const uint64_t active = col_max - off;
+        PGB_TRY(ntt120_vmp(m, (const char *)a->data, bt->stride_a, (char *)res->data, bt->stride_res, (const char *)pmat->data,
+                           bt->stride_b, (uint32_t)row_max, (uint32_t)ncols, (uint32_t)off, (uint32_t)active, (uint32_t)bt->count));
+        return raw_limbs(m, true, shift(R, active), shift(R, active), poly, (uint32_t)(res_polys - active), (uint32_t)bt->count); // :282-287
+    } else {
+        const uint64_t col_max = umin64(ncols, res_polys); // fft64/vmp.rs:214-215
+        if (off >= col_max) return raw_limbs(m, true, R, R, poly, (uint32_t)res_polys, (uint32_t)bt->count);
+        const uint64_t active = col_max - off;
+        PGB_TRY(fft64_vmp(m, (const char *)a->data, bt->stride_a, (char *)res->data, bt->stride_res, (const char *)pmat->data,
+                          bt->stride_b, (uint32_t)row_max, (uint32_t)ncols, (uint32_t)off, (uint32_t)active, (uint32_t)bt->count));
+        // fft64/vmp.rs:263 zeroes res[col_max..] only; polys in [col_max - off, col_max) keep their previous content
+        return raw_limbs(m, true, shift(R, col_max), shift(R, col_max), poly, (uint32_t)(res_polys - col_max), (uint32_t)bt->count);
+    }
+}
+extern "C" int pgb_vmp_apply_dft_to_dft(pgb_module *m, pgb_vec_znx_dft *res, const pgb_vec_znx_dft *a, const pgb_vmp_pmat *pmat,
+                                        uint64_t limb_offset) {
+    PGB_TRY(vmp_apply_impl(m, res, a, pmat, limb_offset, &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_vmp_apply_dft_to_dft_batched(pgb_module *m, pgb_vec_znx_dft *res, const pgb_vec_znx_dft *a, const pgb_vmp_pmat *pmat,
+                                                uint64_t limb_offset, const pgb_batch *bt) {
+    return vmp_apply_impl(m, res, a, pmat, limb_offset, bt);
+}
+extern "C" int pgb_vmp_zero(pgb_module *m, pgb_vmp_pmat *res) {
+    CHECK_N(res, "vmp_zero(res)");
+    PGB_CHECK_CUDA(cudaMemsetAsync(res->data, 0, pgb_bytes_of_vmp_pmat(m, res->rows, res->cols_in, res->cols_out, res->size), m->stream));
+    return sync_if(m, true);
+}
+
+// ---- vec_znx_big --------------------------------------------------------------------------------------------------
+extern "C" size_t pgb_vec_znx_big_normalize_tmp_bytes(const pgb_module *) { return 0; }
+
+int big_normalize_impl(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, int64_t res_offset, uint64_t res_col,
+                       const pgb_vec_znx_big *a, uint64_t a_base2k, uint64_t a_col, int op, bool a_is_big, const pgb_batch *bt) {
+    CHECK_BATCH(bt);
+    CHECK_N(res, "normalize(res)");
+    CHECK_N(a, "normalize(a)");
+    CHECK_COL(res, res_col, "normalize(res)");
+    CHECK_COL(a, a_col, "normalize(a)");
+    const uint64_t n = m->n;
+    const bool i128big = a_is_big && m->flavour == PGB_NTT120;
+    const uint64_t ab = i128big ? 16 : 8;
+    PGB_REQUIRE(op == 0 || i128big, "normalize_{add,sub}_assign exists only for the NTT120 big type in the reference");
+    LimbSet R = {(char *)res->data + limb_off(n, res->cols, res_col, 0, 8), res->cols * n * 8, bt->stride_res};
+    LimbSet A = {(char *)a->data + limb_off(n, a->cols, a_col, 0, ab), a->cols * n * ab, bt->stride_a};
+    return big_normalize(m, i128big, R, (int)res->size, (int)res_base2k, res_offset, A, (int)a->size, (int)a_base2k, op,
+                         (uint32_t)bt->count);
+}
+extern "C" int pgb_vec_znx_big_normalize(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, int64_t res_offset, uint64_t res_col,
+                                         const pgb_vec_znx_big *a, uint64_t a_base2k, uint64_t a_col) {
+    PGB_TRY(big_normalize_impl(m, res, res_base2k, res_offset, res_col, a, a_base2k, a_col, 0, true, &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_vec_znx_big_normalize_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, int64_t res_offset,
+                                                 uint64_t res_col, const pgb_vec_znx_big *a, uint64_t a_base2k, uint64_t a_col,
+                                                 const pgb_batch *bt) {
+    return big_normalize_impl(m, res, res_base2k, res_offset, res_col, a, a_base2k, a_col, 0, true, bt);
+}
+extern "C" int pgb_vec_znx_big_normalize_add_assign(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, int64_t res_offset,
+                                                    uint64_t res_col, const pgb_vec_znx_big *a, uint64_t a_base2k, uint64_t a_col) {
+    PGB_TRY(big_normalize_impl(m, res, res_base2k, res_offset, res_col, a, a_base2k, a_col, +1, true, &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_vec_znx_big_normalize_sub_assign(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, int64_t res_offset,
+                                                    uint64_t res_col, const pgb_vec_znx_big *a, uint64_t a_base2k, uint64_t a_col) {
+    PGB_TRY(big_normalize_impl(m, res, res_base2k, res_offset, res_col, a, a_base2k, a_col, -1, true, &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_vec_znx_normalize(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, int64_t res_offset, uint64_t res_col,
+                                     const pgb_vec_znx *a, uint64_t a_base2k, uint64_t a_col) {
+    PGB_TRY(big_normalize_impl(m, res, res_base2k, res_offset, res_col, a, a_base2k, a_col, 0, false, &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_vec_znx_normalize_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, int64_t res_offset, uint64_t res_col,
+                                             const pgb_vec_znx *a, uint64_t a_base2k, uint64_t a_col, const pgb_batch *bt) {
+    return big_normalize_impl(m, res, res_base2k, res_offset, res_col, a, a_base2k, a_col, 0, false, bt);
+}
+
+int big_add_small_impl(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col, const pgb_batch *bt) {
+    CHECK_BATCH(bt);
+    CHECK_N(res, "vec_znx_big_add_small_assign(res)");
+    CHECK_N(a, "vec_znx_big_add_small_assign(a)");
+    CHECK_COL(res, res_col, "vec_znx_big_add_small_assign(res)");
+    CHECK_COL(a, a_col, "vec_znx_big_add_small_assign(a)");
+    const uint64_t n = m->n, bb = big_bytes(m);
+    LimbSet R = {(char *)res->data + limb_off(n, res->cols, res_col, 0, bb), res->cols * n * bb, bt->stride_res};
+    LimbSet A = {(char *)a->data + limb_off(n, a->cols, a_col, 0, 8), a->cols * n * 8, bt->stride_a};
+    return big_ew(m, m->flavour == PGB_NTT120, BIG_ADD_SMALL, R, A, (uint32_t)umin64(res->size, a->size), (uint32_t)bt->count);
+}
+extern "C" int pgb_vec_znx_big_add_small_assign(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col) {
+    PGB_TRY(big_add_small_impl(m, res, res_col, a, a_col, &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_vec_znx_big_add_small_assign_batched(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx *a,
+                                                        uint64_t a_col, const pgb_batch *bt) {
+    return big_add_small_impl(m, res, res_col, a, a_col, bt);
+}
+extern "C" int pgb_vec_znx_big_from_small(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col) {
+    CHECK_N(res, "vec_znx_big_from_small(res)");
+    CHECK_N(a, "vec_znx_big_from_small(a)");
+    CHECK_COL(res, res_col, "vec_znx_big_from_small(res)");
+    CHECK_COL(a, a_col, "vec_znx_big_from_small(a)");
+    const uint64_t n = m->n, bb = big_bytes(m);
+    LimbSet R = {(char *)res->data + limb_off(n, res->cols, res_col, 0, bb), res->cols * n * bb, 0};
+    LimbSet A = {(char *)a->data + limb_off(n, a->cols, a_col, 0, 8), a->cols * n * 8, 0};
+    const uint64_t mn = umin64(res->size, a->size);
+    PGB_TRY(big_ew(m, m->flavour == PGB_NTT120, BIG_FROM_SMALL, R, A, (uint32_t)mn, 1));
+    PGB_TRY(big_ew(m, m->flavour == PGB_NTT120, BIG_ZERO, shift(R, mn), shift(R, mn), (uint32_t)(res->size - mn), 1));
+    return sync_if(m, true);
+}
+
+extern "C" int pgb_vec_znx_rotate(pgb_module *m, int64_t p, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col) {
+    CHECK_N(res, "vec_znx_rotate(res)");
+    CHECK_N(a, "vec_znx_rotate(a)");
+    CHECK_COL(res, res_col, "vec_znx_rotate(res)");
+    CHECK_COL(a, a_col, "vec_znx_rotate(a)");
+    PGB_REQUIRE(res->data != a->data, "vec_znx_rotate: res and a must not alias (use the _assign form)");
+    const uint64_t n = m->n;
+    LimbSet R = {(char *)res->data + limb_off(n, res->cols, res_col, 0, 8), res->cols * n * 8, 0};
+    LimbSet A = {(char *)a->data + limb_off(n, a->cols, a_col, 0, 8), a->cols * n * 8, 0};
+    const uint64_t mn = umin64(res->size, a->size);
+    PGB_TRY(znx_rotate(m, R, A, p, nullptr, 0, (uint32_t)mn, 1));
+    PGB_TRY(raw_limbs(m, true, shift(R, mn), shift(R, mn), n * 8, (uint32_t)(res->size - mn), 1));
+    return sync_if(m, true);
+}

@@ -1,0 +1,89 @@
+// common.cuh -- shared host-side plumbing of libpoulpy_b200.so (module handle, error model, launch helpers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/poulpy_b200.h"
+
+typedef unsigned __int128 u128;
+typedef __int128 i128;
+
+// Thread-local last error (pgb_last_error); the Rust shim turns a non-zero status into panic!.
+void pgb_set_error(const char *fmt, ...);
+
+#define PGB_CHECK_CUDA(expr)                                                                          \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            pgb_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__,      \
+                          cudaGetErrorString(_e));                                                    \
+            return PGB_ERR_CUDA;                                                                      \
+        }                                                                                             \
+    } while (0)
+
+#define PGB_REQUIRE(cond, ...)          \
+    do {                                \
+        if (!(cond)) {                  \
+            pgb_set_error(__VA_ARGS__); \
+            return PGB_ERR_SHAPE;       \
+        }                               \
+    } while (0)
+
+#define PGB_TRY(expr)             \
+    do {                          \
+        int _s = (expr);          \
+        if (_s != PGB_OK) return _s; \
+    } while (0)
+
+// Per-n constants of the NTT120 flavour handed to kernels by value.
+struct Ntt120Consts {
+    uint32_t crt_ninv[4];    // CRT_CST[k] * n^-1 mod Q[k]   (folds the 1/n of the inverse NTT into the CRT step)
+    uint32_t crt_ninv_sh[4]; // Shoup companion floor(crt_ninv * 2^32 / Q[k])
+};
+
+struct pgb_module {
+    uint64_t n;
+    int log_n;
+    int flavour;
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    cudaStream_t aux_stream[2]; // H2D / D2H staging streams of the host front ends
+    cudaEvent_t ev[8];
+    uint64_t launches;
+    // NTT120: twiddles (w, floor(w*2^32/q)) in block-twiddle (bit-reversed) order, [4][n] each direction
+    uint2 *ntt_fwd, *ntt_inv;
+    Ntt120Consts nc;
+    // FFT64: complex twiddles in block-twiddle order, [m] each direction
+    double2 *fft_fwd, *fft_inv;
+    // lazily grown device workspace for host front ends
+    void *ws;
+    size_t ws_len;
+    void *pinned[4];
+    size_t pinned_len;
+};
+
+// A strided set of limbs ("jobs"): job j of batch item b starts at base + b*batch_stride + j*limb_stride (bytes).
+struct LimbSet {
+    char *base;
+    uint64_t limb_stride;
+    uint64_t batch_stride;
+};
+
+static inline int ilog2_u64(uint64_t x) {
+    int l = 0;
+    while ((1ull << l) < x) l++;
+    return l;
+}
+
+static inline uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+static inline uint64_t div_ceil64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+// byte offset of limb (col, j) inside a limb-major / column-minor container (layouts/znx_base.rs:74)
+static inline uint64_t limb_off(uint64_t n, uint64_t cols, uint64_t col, uint64_t j, uint64_t scalar_bytes) {
+    return n * (j * cols + col) * scalar_bytes;
+}

@@ -1,0 +1,345 @@
+// core.cu -- CoreImpl-tier batched pipelines: GLWE key-switch (C1) and GGSW x GLWE external product (C2), device resident,
+// plus the host-buffer front ends that stage through pinned memory.
+//
+// The call sequences restate poulpy-core/src/keyswitching/glwe.rs:53-109, :207-239, :298-380 and
+// poulpy-core/src/external_product/glwe.rs:99-141, :197-271; every step runs over the whole batch on the module's
+// stream with no host round trip in between.
+#include "internal.h"
+
+static const uint64_t ALIGN = 256;
+static inline uint64_t align_up(uint64_t x) { return (x + ALIGN - 1) / ALIGN * ALIGN; }
+
+struct Arena {
+    char *base;
+    size_t len, used;
+    void *take(size_t bytes) {
+        size_t off = align_up(used);
+        if (off + bytes > len) return nullptr;
+        used = off + bytes;
+        return base + off;
+    }
+};
+
+static pgb_vec_znx mk(void *data, uint64_t n, uint64_t cols, uint64_t size) {
+    pgb_vec_znx v = {data, n, cols, size, size};
+    return v;
+}
+
+// glwe_normalize (poulpy-core/src/operations/glwe.rs:1286-1310) into a buffer of size ceil(a.size*a_base2k / base2k)
+static uint64_t conv_size(uint64_t a_size, uint64_t a_base2k, uint64_t base2k) { return div_ceil64(a_size * a_base2k, base2k); }
+
+// ---- gglwe_product_dft (keyswitching/glwe.rs:298-380) / the dsize loop of the external product ------------------
+// res_dft(cols_out, pmat.size) <- a_dft(cols, a_size) x pmat ; ai / tmp are scratch DFT buffers for dsize > 1.
+static int gadget_product(pgb_module *m, pgb_vec_znx_dft *res, const pgb_vec_znx_dft *a, const pgb_vmp_pmat *pmat, uint64_t dsize,
+                          bool bound_by_dnum, pgb_vec_znx_dft *ai, pgb_vec_znx_dft *tmp, uint64_t res_bs, uint64_t a_bs, uint64_t ai_bs,
+                          uint64_t tmp_bs, uint64_t batch) {
+    if (dsize == 1) {
+        pgb_batch bt = {batch, res_bs, a_bs, 0};
+        return vmp_apply_impl(m, res, a, pmat, 0, &bt);
+    }
+    const uint64_t a_size = a->size, dnum = pmat->rows, cols = a->cols, cols_out = res->cols;
+    const uint64_t res_max = res->size;
+    for (uint64_t di = 0; di < dsize; di++) {
+        uint64_t sz = (a_size + di) / dsize;
+        if (bound_by_dnum) sz = umin64(sz, dnum);
+        ai->size = sz;
+        const int64_t cut = (int64_t)(dsize - di) - 2;
+        res->size = pmat->size - (uint64_t)(cut > 0 ? cut : 0);
+        pgb_batch btc = {batch, ai_bs, a_bs, 0};
+        for (uint64_t j = 0; j < cols; j++) PGB_TRY(pgb_vec_znx_dft_copy_batched(m, dsize, dsize - di - 1, ai, j, a, j, &btc));
+        if (di == 0) {
+            pgb_batch bt = {batch, res_bs, ai_bs, 0};
+            PGB_TRY(vmp_apply_impl(m, res, ai, pmat, 0, &bt));
+        } else {
+            tmp->size = res->size;
+            pgb_batch bt = {batch, tmp_bs, ai_bs, 0};
+            PGB_TRY(vmp_apply_impl(m, tmp, ai, pmat, di, &bt));
+            pgb_batch bta = {batch, res_bs, tmp_bs, 0};
+            for (uint64_t c = 0; c < cols_out; c++) PGB_TRY(pgb_vec_znx_dft_add_assign_batched(m, res, c, tmp, c, &bta));
+        }
+    }
+    res->size = res_max;
+    return PGB_OK;
+}
+
+// ---- key-switch --------------------------------------------------------------------------------------------------------
+extern "C" size_t pgb_glwe_keyswitch_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t a_size, uint64_t a_base2k,
+                                               const pgb_vmp_pmat *key, uint64_t key_base2k, uint64_t dsize, uint64_t batch) {
+    (void)res_size;
+    const uint64_t n = m->n, pb = prep_bytes(m);
+    const uint64_t rank_in = key->cols_in, cols_out = key->cols_out;
+    const uint64_t in_size = a_base2k == key_base2k ? a_size : conv_size(a_size, a_base2k, key_base2k);
+    uint64_t t = 0;
+    t += align_up(batch * n * cols_out * key->size * pb);                       // res_dft
+    t += align_up(batch * n * rank_in * in_size * pb);                          // a_dft
+    if (a_base2k != key_base2k) t += align_up(batch * n * (rank_in + 1) * in_size * 8); // a_conv
+    if (dsize > 1) {
+        t += align_up(batch * n * rank_in * div_ceil64(in_size, dsize) * pb);   // ai_dft
+        t += align_up(batch * n * cols_out * key->size * pb);                   // res_dft_tmp
+    }
+    return t + ALIGN;
+}
+
+extern "C" int pgb_glwe_keyswitch_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, const pgb_vec_znx *a, uint64_t a_base2k,
+                                          const pgb_vmp_pmat *key, uint64_t key_base2k, uint64_t dsize, const pgb_batch *bt, void *scratch,
+                                          size_t scratch_len) {
+    PGB_REQUIRE(bt && bt->count >= 1 && bt->count <= 65535, "glwe_keyswitch: batch count must be in [1, 65535]");
+    PGB_REQUIRE(res->n == m->n && a->n == m->n && key->n == m->n, "glwe_keyswitch: ring degree mismatch");
+    PGB_REQUIRE(a->cols == key->cols_in + 1, "glwe_keyswitch: a.rank() != key.rank_in()");   // keyswitching/glwe.rs:59-65
+    PGB_REQUIRE(res->cols == key->cols_out, "glwe_keyswitch: res.rank() != key.rank_out()"); // :66-72
+    PGB_REQUIRE(dsize >= 1, "glwe_keyswitch: dsize must be >= 1");
+    const uint64_t need = pgb_glwe_keyswitch_tmp_bytes(m, res->size, a->size, a_base2k, key, key_base2k, dsize, bt->count);
+    if (scratch_len < need) {
+        pgb_set_error("glwe_keyswitch: scratch of %zu bytes < required %llu", scratch_len, (unsigned long long)need);
+        return PGB_ERR_SCRATCH;
+    }
+    const uint64_t n = m->n, pb = prep_bytes(m), B = bt->count;
+    const uint64_t rank_in = key->cols_in, cols_out = key->cols_out;
+    Arena ar = {(char *)scratch, scratch_len, 0};
+
+    // (:89-90) res_dft = take_vec_znx_dft(rank_out + 1, key.size()); zero
+    const uint64_t res_dft_bs = n * cols_out * key->size * pb;
+    pgb_vec_znx_dft res_dft = mk(ar.take(B * res_dft_bs), n, cols_out, key->size);
+    PGB_CHECK_CUDA(cudaMemsetAsync(res_dft.data, 0, B * res_dft_bs, m->stream));
+    // (:92-100) cross-base2k input conversion
+    pgb_vec_znx ain = *a;
+    uint64_t ain_bs = bt->stride_a;
+    if (a_base2k != key_base2k) {
+        const uint64_t cs = conv_size(a->size, a_base2k, key_base2k);
+        ain_bs = n * a->cols * cs * 8;
+        ain = mk(ar.take(B * ain_bs), n, a->cols, cs);
+        pgb_batch btn = {B, ain_bs, bt->stride_a, 0};
+        for (uint64_t i = 0; i < a->cols; i++)
+            PGB_TRY(big_normalize_impl(m, &ain, key_base2k, 0, i, a, a_base2k, i, 0, false, &btn));
+    }
+    // glwe_keyswitch_internal (:207-239)
+    const uint64_t a_dft_bs = n * rank_in * ain.size * pb;
+    pgb_vec_znx_dft a_dft = mk(ar.take(B * a_dft_bs), n, rank_in, ain.size);
+    pgb_batch btd = {B, a_dft_bs, ain_bs, 0};
+    for (uint64_t c = 0; c < rank_in; c++) PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &a_dft, c, &ain, c + 1, &btd));
+    pgb_vec_znx_dft ai = a_dft, tmp = res_dft;
+    uint64_t ai_bs = 0, tmp_bs = 0;
+    if (dsize > 1) {
+        const uint64_t ai_max = umin64(div_ceil64(ain.size, dsize), key->rows);
+        ai_bs = n * rank_in * ai_max * pb;
+        ai = mk(ar.take(B * ai_bs), n, rank_in, ai_max);
+        tmp_bs = res_dft_bs;
+        tmp = mk(ar.take(B * tmp_bs), n, cols_out, key->size);
+        PGB_REQUIRE(ai.data && tmp.data, "glwe_keyswitch: scratch exhausted");
+        PGB_CHECK_CUDA(cudaMemsetAsync(ai.data, 0, B * ai_bs, m->stream));   // ai_dft.zero()       (:337)
+        PGB_CHECK_CUDA(cudaMemsetAsync(tmp.data, 0, B * tmp_bs, m->stream)); // res_dft_tmp.zero()  (:342)
+    }
+    PGB_TRY(gadget_product(m, &res_dft, &a_dft, key, dsize, true, &ai, &tmp, res_dft_bs, a_dft_bs, ai_bs, tmp_bs, B));
+    pgb_batch btc = {B, res_dft_bs, 0, 0};
+    PGB_TRY(pgb_vec_znx_idft_apply_consume_batched(m, &res_dft, &btc));
+    pgb_vec_znx_big res_big = res_dft; // same memory, ScalarBig elements
+    pgb_batch bts = {B, res_dft_bs, ain_bs, 0};
+    PGB_TRY(big_add_small_impl(m, &res_big, 0, &ain, 0, &bts));
+    // (:106-108)
+    pgb_batch btn = {B, bt->stride_res, res_dft_bs, 0};
+    for (uint64_t i = 0; i < res->cols; i++)
+        PGB_TRY(big_normalize_impl(m, res, res_base2k, 0, i, &res_big, key_base2k, i, 0, true, &btn));
+    return PGB_OK;
+}
+
+// ---- external product ------------------------------------------------------------------------------------------------------
+extern "C" size_t pgb_glwe_external_product_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t a_size, uint64_t a_base2k,
+                                                      const pgb_vmp_pmat *ggsw, uint64_t ggsw_base2k, uint64_t dsize, uint64_t batch) {
+    (void)res_size;
+    const uint64_t n = m->n, pb = prep_bytes(m);
+    const uint64_t cols = ggsw->cols_in;
+    const uint64_t in_size = a_base2k == ggsw_base2k ? a_size : conv_size(a_size, a_base2k, ggsw_base2k);
+    uint64_t t = 0;
+    t += align_up(batch * n * cols * ggsw->size * pb);
+    t += align_up(batch * n * cols * in_size * pb); // a_dft (dsize == 1 uses a_size limbs, dsize > 1 uses <= a_size)
+    if (a_base2k != ggsw_base2k) t += align_up(batch * n * cols * in_size * 8);
+    if (dsize > 1) t += align_up(batch * n * cols * ggsw->size * pb);
+    return t + ALIGN;
+}
+
+extern "C" int pgb_glwe_external_product_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, const pgb_vec_znx *a,
+                                                 uint64_t a_base2k, const pgb_vmp_pmat *ggsw, uint64_t ggsw_base2k, uint64_t dsize,
+                                                 const pgb_batch *bt, void *scratch, size_t scratch_len) {
+    PGB_REQUIRE(bt && bt->count >= 1 && bt->count <= 65535, "glwe_external_product: batch count must be in [1, 65535]");
+    PGB_REQUIRE(res->n == m->n && a->n == m->n && ggsw->n == m->n, "glwe_external_product: ring degree mismatch");
+    PGB_REQUIRE(a->cols == ggsw->cols_in && res->cols == ggsw->cols_out && ggsw->cols_in == ggsw->cols_out,
+                "glwe_external_product: rank mismatch");                                     // external_product/glwe.rs:106-107
+    PGB_REQUIRE(dsize >= 1, "glwe_external_product: dsize must be >= 1");
+    const uint64_t need = pgb_glwe_external_product_tmp_bytes(m, res->size, a->size, a_base2k, ggsw, ggsw_base2k, dsize, bt->count);
+    if (scratch_len < need) {
+        pgb_set_error("glwe_external_product: scratch of %zu bytes < required %llu", scratch_len, (unsigned long long)need);
+        return PGB_ERR_SCRATCH;
+    }
+    const uint64_t n = m->n, pb = prep_bytes(m), B = bt->count, cols = ggsw->cols_in;
+    Arena ar = {(char *)scratch, scratch_len, 0};
+    const uint64_t res_dft_bs = n * cols * ggsw->size * pb;
+    pgb_vec_znx_dft res_dft = mk(ar.take(B * res_dft_bs), n, cols, ggsw->size);
+    PGB_CHECK_CUDA(cudaMemsetAsync(res_dft.data, 0, B * res_dft_bs, m->stream)); // res_dft.zero() (:123)
+    pgb_vec_znx ain = *a;
+    uint64_t ain_bs = bt->stride_a;
+    if (a_base2k != ggsw_base2k) {
+        const uint64_t cs = conv_size(a->size, a_base2k, ggsw_base2k);
+        ain_bs = n * a->cols * cs * 8;
+        ain = mk(ar.take(B * ain_bs), n, a->cols, cs);
+        pgb_batch btn = {B, ain_bs, bt->stride_a, 0};
+        for (uint64_t i = 0; i < a->cols; i++)
+            PGB_TRY(big_normalize_impl(m, &ain, ggsw_base2k, 0, i, a, a_base2k, i, 0, false, &btn));
+    }
+    // glwe_external_product_internal (:197-271)
+    const uint64_t a_size = ain.size;
+    const uint64_t a_dft_max = dsize == 1 ? a_size : div_ceil64(a_size, dsize);
+    const uint64_t a_dft_bs = n * cols * a_dft_max * pb;
+    pgb_vec_znx_dft a_dft = mk(ar.take(B * a_dft_bs), n, cols, a_dft_max);
+    if (dsize == 1) {
+        pgb_batch btd = {B, a_dft_bs, ain_bs, 0};
+        for (uint64_t j = 0; j < cols; j++) PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &a_dft, j, &ain, j, &btd));
+        pgb_batch btv = {B, res_dft_bs, a_dft_bs, 0};
+        PGB_TRY(vmp_apply_impl(m, &res_dft, &a_dft, ggsw, 0, &btv));
+    } else {
+        pgb_vec_znx_dft tmp = mk(ar.take(B * res_dft_bs), n, cols, ggsw->size);
+        PGB_REQUIRE(tmp.data, "glwe_external_product: scratch exhausted");
+        // a_dft.data_mut().fill(0) (:226): FFT64 dft_apply leaves limbs past a.size untouched inside min_steps
+        PGB_CHECK_CUDA(cudaMemsetAsync(a_dft.data, 0, B * a_dft_bs, m->stream));
+        for (uint64_t di = 0; di < dsize; di++) {
+            a_dft.size = (a_size + di) / dsize;
+            const int64_t cut = (int64_t)(dsize - di) - 2;
+            res_dft.size = ggsw->size - (uint64_t)(cut > 0 ? cut : 0);
+            pgb_batch btd = {B, a_dft_bs, ain_bs, 0};
+            for (uint64_t j = 0; j < cols; j++) PGB_TRY(pgb_vec_znx_dft_apply_batched(m, dsize, dsize - 1 - di, &a_dft, j, &ain, j, &btd));
+            if (di == 0) {
+                pgb_batch btv = {B, res_dft_bs, a_dft_bs, 0};
+                PGB_TRY(vmp_apply_impl(m, &res_dft, &a_dft, ggsw, 0, &btv));
+            } else {
+                tmp.size = res_dft.size;
+                pgb_batch btv = {B, res_dft_bs, a_dft_bs, 0};
+                PGB_TRY(vmp_apply_impl(m, &tmp, &a_dft, ggsw, di, &btv));
+                pgb_batch bta = {B, res_dft_bs, res_dft_bs, 0};
+                for (uint64_t c = 0; c < cols; c++) PGB_TRY(pgb_vec_znx_dft_add_assign_batched(m, &res_dft, c, &tmp, c, &bta));
+            }
+        }
+    }
+    pgb_batch btc = {B, res_dft_bs, 0, 0};
+    PGB_TRY(pgb_vec_znx_idft_apply_consume_batched(m, &res_dft, &btc));
+    pgb_vec_znx_big res_big = res_dft;
+    pgb_batch btn = {B, bt->stride_res, res_dft_bs, 0};
+    for (uint64_t j = 0; j < res->cols; j++)
+        PGB_TRY(big_normalize_impl(m, res, res_base2k, 0, j, &res_big, ggsw_base2k, j, 0, true, &btn));
+    return PGB_OK;
+}
+
+// ---- host-buffer front ends ---------------------------------------------------------------------------------------------------
+// Chunked three-stage pipeline (H2D on aux stream 0, compute on the module stream, D2H on aux stream 1), double buffered.
+static int ensure_ws(pgb_module *m, size_t len) {
+    if (m->ws_len >= len) return PGB_OK;
+    if (m->ws) cudaFree(m->ws);
+    m->ws = nullptr;
+    m->ws_len = 0;
+    PGB_CHECK_CUDA(cudaMalloc(&m->ws, len));
+    m->ws_len = len;
+    return PGB_OK;
+}
+static int ensure_pinned(pgb_module *m, size_t len) {
+    if (m->pinned_len >= len) return PGB_OK;
+    for (int i = 0; i < 4; i++) {
+        if (m->pinned[i]) cudaFreeHost(m->pinned[i]);
+        m->pinned[i] = nullptr;
+    }
+    m->pinned_len = 0;
+    for (int i = 0; i < 4; i++) PGB_CHECK_CUDA(cudaHostAlloc(&m->pinned[i], len, cudaHostAllocDefault));
+    m->pinned_len = len;
+    return PGB_OK;
+}
+
+typedef int (*core_fn)(pgb_module *, pgb_vec_znx *, uint64_t, const pgb_vec_znx *, uint64_t, const pgb_vmp_pmat *, uint64_t, uint64_t,
+                       const pgb_batch *, void *, size_t);
+
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// Chunk c uses slot s = c & 1 of the double-buffered device (and, for pageable callers, pinned) buffers.
+//   s_in : H2D(c)            waits compute(c-2) (d_in[s] free)
+//   s_c  : compute(c)        waits H2D(c) and D2H(c-2) (d_out[s] free)
+//   s_out: D2H(c)            waits compute(c)
+static int host_pipeline(pgb_module *m, bool ext, int64_t *res_host, uint64_t res_cols, uint64_t res_size, uint64_t res_base2k,
+                         const int64_t *a_host, uint64_t a_cols, uint64_t a_size, uint64_t a_base2k, const pgb_vmp_pmat *key,
+                         uint64_t key_base2k, uint64_t dsize, uint64_t count) {
+    if (count == 0) return PGB_OK;
+    const uint64_t n = m->n;
+    const uint64_t a_bytes = n * a_cols * a_size * 8, r_bytes = n * res_cols * res_size * 8;
+    const uint64_t chunk = umin64(count, 2048);
+    const size_t tmp = ext ? pgb_glwe_external_product_tmp_bytes(m, res_size, a_size, a_base2k, key, key_base2k, dsize, chunk)
+                           : pgb_glwe_keyswitch_tmp_bytes(m, res_size, a_size, a_base2k, key, key_base2k, dsize, chunk);
+    const size_t in_dev = align_up(chunk * a_bytes), out_dev = align_up(chunk * r_bytes);
+    PGB_TRY(ensure_ws(m, 2 * (in_dev + out_dev) + align_up(tmp) + ALIGN));
+    const bool direct = is_pinned(a_host) && is_pinned(res_host);
+    if (!direct) PGB_TRY(ensure_pinned(m, (size_t)(chunk * (a_bytes > r_bytes ? a_bytes : r_bytes))));
+    char *ws = (char *)m->ws;
+    char *d_in[2] = {ws, ws + in_dev};
+    char *d_out[2] = {ws + 2 * in_dev, ws + 2 * in_dev + out_dev};
+    char *d_tmp = ws + 2 * (in_dev + out_dev);
+    cudaStream_t s_in = m->aux_stream[0], s_out = m->aux_stream[1], s_c = m->stream;
+    cudaEvent_t *ev_in = &m->ev[0], *ev_c = &m->ev[2], *ev_out = &m->ev[4];
+    const uint64_t nchunks = div_ceil64(count, chunk);
+    core_fn fn = ext ? (core_fn)pgb_glwe_external_product_batched : (core_fn)pgb_glwe_keyswitch_batched;
+    for (uint64_t c = 0; c < nchunks; c++) {
+        const int s = (int)(c & 1);
+        const uint64_t first = c * chunk, cnt = umin64(chunk, count - first);
+        const char *src = (const char *)a_host + first * a_bytes;
+        char *dst = (char *)res_host + first * r_bytes;
+        if (c >= 2) {
+            PGB_CHECK_CUDA(cudaStreamWaitEvent(s_in, ev_c[s], 0));
+            if (!direct) { // pinned slot s is reused: drain chunk c-2 to the caller first
+                PGB_CHECK_CUDA(cudaEventSynchronize(ev_out[s]));
+                memcpy((char *)res_host + (first - 2 * chunk) * r_bytes, m->pinned[2 + s], (size_t)(chunk * r_bytes));
+            }
+        }
+        if (!direct) {
+            memcpy(m->pinned[s], src, (size_t)(cnt * a_bytes));
+            src = (const char *)m->pinned[s];
+            dst = (char *)m->pinned[2 + s];
+        }
+        PGB_CHECK_CUDA(cudaMemcpyAsync(d_in[s], src, cnt * a_bytes, cudaMemcpyHostToDevice, s_in));
+        PGB_CHECK_CUDA(cudaEventRecord(ev_in[s], s_in));
+        PGB_CHECK_CUDA(cudaStreamWaitEvent(s_c, ev_in[s], 0));
+        if (c >= 2) PGB_CHECK_CUDA(cudaStreamWaitEvent(s_c, ev_out[s], 0));
+        pgb_vec_znx av = {d_in[s], n, a_cols, a_size, a_size}, rv = {d_out[s], n, res_cols, res_size, res_size};
+        pgb_batch bt = {cnt, r_bytes, a_bytes, 0};
+        PGB_TRY(fn(m, &rv, res_base2k, &av, a_base2k, key, key_base2k, dsize, &bt, d_tmp, m->ws_len - (size_t)(d_tmp - ws)));
+        PGB_CHECK_CUDA(cudaEventRecord(ev_c[s], s_c));
+        PGB_CHECK_CUDA(cudaStreamWaitEvent(s_out, ev_c[s], 0));
+        PGB_CHECK_CUDA(cudaMemcpyAsync(dst, d_out[s], cnt * r_bytes, cudaMemcpyDeviceToHost, s_out));
+        PGB_CHECK_CUDA(cudaEventRecord(ev_out[s], s_out));
+    }
+    PGB_CHECK_CUDA(cudaStreamSynchronize(s_out));
+    if (!direct) {
+        for (uint64_t c = nchunks >= 2 ? nchunks - 2 : 0; c < nchunks; c++) {
+            const int s = (int)(c & 1);
+            const uint64_t first = c * chunk, cnt = umin64(chunk, count - first);
+            memcpy((char *)res_host + first * r_bytes, m->pinned[2 + s], (size_t)(cnt * r_bytes));
+        }
+    }
+    PGB_CHECK_CUDA(cudaStreamSynchronize(s_c));
+    PGB_CHECK_CUDA(cudaStreamSynchronize(s_in));
+    return PGB_OK;
+}
+
+extern "C" int pgb_glwe_keyswitch_host(pgb_module *m, int64_t *res_host, uint64_t res_size, uint64_t res_base2k, const int64_t *a_host,
+                                       uint64_t a_size, uint64_t a_base2k, uint64_t rank_in, uint64_t rank_out, const pgb_vmp_pmat *key,
+                                       uint64_t key_base2k, uint64_t dsize, uint64_t count) {
+    PGB_REQUIRE(key->cols_in == rank_in && key->cols_out == rank_out + 1, "glwe_keyswitch_host: key shape does not match the ranks");
+    return host_pipeline(m, false, res_host, rank_out + 1, res_size, res_base2k, a_host, rank_in + 1, a_size, a_base2k, key, key_base2k,
+                         dsize, count);
+}
+extern "C" int pgb_glwe_external_product_host(pgb_module *m, int64_t *res_host, uint64_t res_size, uint64_t res_base2k,
+                                              const int64_t *a_host, uint64_t a_size, uint64_t a_base2k, uint64_t rank,
+                                              const pgb_vmp_pmat *ggsw, uint64_t ggsw_base2k, uint64_t dsize, uint64_t count) {
+    PGB_REQUIRE(ggsw->cols_in == rank + 1 && ggsw->cols_out == rank + 1, "glwe_external_product_host: ggsw shape does not match the rank");
+    return host_pipeline(m, true, res_host, rank + 1, res_size, res_base2k, a_host, rank + 1, a_size, a_base2k, ggsw, ggsw_base2k, dsize,
+                         count);
+}

@@ -1,0 +1,402 @@
+// fft64.cu -- FFT64 flavour: batched forward / inverse negacyclic FFT (K3 / K4) and the f64 element-wise kernels
+// (vmp K6, svp K5, add/sub K8).
+//
+// Conventions (poulpy-cpu-ref/src/reference/fft64/reim/*): a real polynomial of n
+// coefficients is folded to m = n/2 complex points z_j = a_j + i*a_{j+m}; a DFT limb is [re(m) | im(m)] f64 and
+//   out[p] = sum_j z_j * zeta^(j * (4*bitrev_{log m}(p) + 1)),  zeta = exp(2*pi*i / (2n))
+// which is exactly the order the reference's fft16/bitwiddle traversal produces (tests/test_oracle_kat.py pins it).
+// The inverse is unnormalised; the 1/m and the round-half-away-from-zero of reim_to_znx_i64 (conversion.rs:43-60)
+// are fused into its last pass.  Butterflies use FMA (the reference does not): DFT-domain values agree with the
+// oracle to a stated tolerance, the rounded i64 results exactly (same contract as poulpy-cpu-avx vs poulpy-cpu-ref,
+// poulpy-cpu-avx/src/fft64/reim/fft_avx2_fma.rs:318-353).
+#include <math.h>
+
+#include "internal.h"
+
+__device__ __forceinline__ int FPAD(int idx) { return idx + (idx >> 3); }
+template <int L> struct FGeo {
+    static constexpr int M = 1 << L;
+    static constexpr int T = M >= 8 ? M / 8 : 1;
+    static constexpr int R0 = (L % 3 == 0) ? 3 : (L % 3);
+    static constexpr int PLANE = M + (M >> 3) + 2; // padded double2 elements
+};
+
+__device__ __forceinline__ void fct_bf(double2 &x, double2 &y, double2 w) { // (x + w*y, x - w*y)
+    double dr = y.x * w.x - y.y * w.y;
+    double di = y.x * w.y + y.y * w.x;
+    y = make_double2(x.x - dr, x.y - di);
+    x = make_double2(x.x + dr, x.y + di);
+}
+__device__ __forceinline__ void fgs_bf(double2 &x, double2 &y, double2 w) { // (x + y, (x - y)*w)
+    double rd = x.x - y.x, id = x.y - y.y;
+    x = make_double2(x.x + y.x, x.y + y.y);
+    y = make_double2(rd * w.x - id * w.y, rd * w.y + id * w.x);
+}
+__device__ __forceinline__ double2 ldw(const double2 *p) {
+    return make_double2(__ldg(&p->x), __ldg(&p->y));
+}
+
+template <int NLEV> __device__ __forceinline__ void fct_radix8(double2 (&x)[8], const double2 *__restrict__ tw, uint32_t hi) {
+    {
+        double2 w = ldw(tw + hi);
+#pragma unroll
+        for (int j = 0; j < 4; j++) fct_bf(x[j], x[j + 4], w);
+    }
+    if (NLEV >= 2) {
+        double2 w0 = ldw(tw + 2 * hi), w1 = ldw(tw + 2 * hi + 1);
+        fct_bf(x[0], x[2], w0);
+        fct_bf(x[1], x[3], w0);
+        fct_bf(x[4], x[6], w1);
+        fct_bf(x[5], x[7], w1);
+    }
+    if (NLEV >= 3) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) fct_bf(x[2 * j], x[2 * j + 1], ldw(tw + 4 * hi + j));
+    }
+}
+template <int NLEV> __device__ __forceinline__ void fgs_radix8(double2 (&x)[8], const double2 *__restrict__ tw, uint32_t hi) {
+    if (NLEV >= 3) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) fgs_bf(x[2 * j], x[2 * j + 1], ldw(tw + 4 * hi + j));
+    }
+    if (NLEV >= 2) {
+        double2 w0 = ldw(tw + 2 * hi), w1 = ldw(tw + 2 * hi + 1);
+        fgs_bf(x[0], x[2], w0);
+        fgs_bf(x[1], x[3], w0);
+        fgs_bf(x[4], x[6], w1);
+        fgs_bf(x[5], x[7], w1);
+    }
+    {
+        double2 w = ldw(tw + hi);
+#pragma unroll
+        for (int j = 0; j < 4; j++) fgs_bf(x[j], x[j + 4], w);
+    }
+}
+
+struct FftJobs {
+    LimbSet in, out;
+    int jobs_per_batch;
+    int total_jobs;
+};
+
+template <int L, int L0> struct FFwdMid {
+    static __device__ __forceinline__ void run(double2 *sm, double *gout, const double2 *tw, int t, bool active) {
+        typedef FGeo<L> G;
+        constexpr int SL = L - L0 - 3;
+        const int a = t >> SL, b = t & ((1 << SL) - 1);
+        const int base = (a << (SL + 3)) | b;
+        const uint32_t hi = (1u << L0) | (uint32_t)a;
+        double2 x[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) x[j] = sm[FPAD(base + (j << SL))];
+        fct_radix8<3>(x, tw, hi);
+        if (SL == 0) {
+            if (active) {
+                double2 *ore = reinterpret_cast<double2 *>(gout + base), *oim = reinterpret_cast<double2 *>(gout + G::M + base);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    ore[j] = make_double2(x[2 * j].x, x[2 * j + 1].x);
+                    oim[j] = make_double2(x[2 * j].y, x[2 * j + 1].y);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) sm[FPAD(base + (j << SL))] = x[j];
+            __syncthreads();
+        }
+        FFwdMid<L, (L0 + 3 < L) ? L0 + 3 : L>::run(sm, gout, tw, t, active);
+    }
+};
+template <int L> struct FFwdMid<L, L> {
+    static __device__ __forceinline__ void run(double2 *, double *, const double2 *, int, bool) {}
+};
+
+template <int L, int LPC> __global__ void __launch_bounds__(FGeo<L>::T *LPC) fft64_fwd_kernel(FftJobs jb, const double2 *__restrict__ tw) {
+    typedef FGeo<L> G;
+    extern __shared__ __align__(16) double2 fsm[];
+    const int slot = threadIdx.x / G::T, t = threadIdx.x % G::T;
+    const int job = blockIdx.x * LPC + slot;
+    const bool active = job < jb.total_jobs;
+    const int b = active ? job / jb.jobs_per_batch : 0, j = active ? job % jb.jobs_per_batch : 0;
+    const long long *gin = reinterpret_cast<const long long *>(jb.in.base + (size_t)b * jb.in.batch_stride + (size_t)j * jb.in.limb_stride);
+    double *gout = reinterpret_cast<double *>(jb.out.base + (size_t)b * jb.out.batch_stride + (size_t)j * jb.out.limb_stride);
+    double2 *sm = fsm + slot * G::PLANE;
+    double2 x[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+        const int idx = t + jj * G::T;
+        x[jj] = active ? make_double2((double)__ldg(gin + idx), (double)__ldg(gin + G::M + idx)) : make_double2(0.0, 0.0);
+    }
+    fct_radix8<G::R0>(x, tw, 1u);
+    if (L == G::R0) {
+        if (active) {
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) {
+                gout[jj] = x[jj].x;
+                gout[G::M + jj] = x[jj].y;
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) sm[FPAD(t + jj * G::T)] = x[jj];
+    __syncthreads();
+    FFwdMid<L, (L > G::R0) ? G::R0 : L>::run(sm, gout, tw, t, active);
+}
+
+template <int L, int L0> struct FInvMid {
+    static __device__ __forceinline__ void run(double2 *sm, const double2 *tw, int t) {
+        typedef FGeo<L> G;
+        constexpr int SL = L - L0 - 3;
+        const int a = t >> SL, b = t & ((1 << SL) - 1);
+        const int base = (a << (SL + 3)) | b;
+        const uint32_t hi = (1u << L0) | (uint32_t)a;
+        double2 x[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) x[j] = sm[FPAD(base + (j << SL))];
+        fgs_radix8<3>(x, tw, hi);
+#pragma unroll
+        for (int j = 0; j < 8; j++) sm[FPAD(base + (j << SL))] = x[j];
+        __syncthreads();
+        FInvMid<L, (L0 - 3 >= G::R0) ? L0 - 3 : -1>::run(sm, tw, t);
+    }
+};
+template <int L> struct FInvMid<L, -1> {
+    static __device__ __forceinline__ void run(double2 *, const double2 *, int) {}
+};
+
+template <int L, int LPC> __global__ void __launch_bounds__(FGeo<L>::T *LPC) fft64_inv_kernel(FftJobs jb, const double2 *__restrict__ tw, double inv_m) {
+    typedef FGeo<L> G;
+    extern __shared__ __align__(16) double2 fsm[];
+    const int slot = threadIdx.x / G::T, t = threadIdx.x % G::T;
+    const int job = blockIdx.x * LPC + slot;
+    const bool active = job < jb.total_jobs;
+    const int b = active ? job / jb.jobs_per_batch : 0, j = active ? job % jb.jobs_per_batch : 0;
+    const double *gin = reinterpret_cast<const double *>(jb.in.base + (size_t)b * jb.in.batch_stride + (size_t)j * jb.in.limb_stride);
+    long long *gout = reinterpret_cast<long long *>(jb.out.base + (size_t)b * jb.out.batch_stride + (size_t)j * jb.out.limb_stride);
+    double2 *sm = fsm + slot * G::PLANE;
+    double2 x[8];
+    if (L > G::R0) {
+        constexpr int L0 = L - 3;
+        if (active) {
+            const double2 *pre = reinterpret_cast<const double2 *>(gin + 8 * t), *pim = reinterpret_cast<const double2 *>(gin + G::M + 8 * t);
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                double2 r = pre[jj], i = pim[jj];
+                x[2 * jj] = make_double2(r.x, i.x);
+                x[2 * jj + 1] = make_double2(r.y, i.y);
+            }
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) x[jj] = make_double2(0.0, 0.0);
+        }
+        fgs_radix8<3>(x, tw, (1u << L0) | (uint32_t)t);
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) sm[FPAD(8 * t + jj)] = x[jj];
+        __syncthreads();
+        FInvMid<L, (L - 6 >= G::R0) ? L - 6 : -1>::run(sm, tw, t);
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) x[jj] = sm[FPAD(t + jj * G::T)];
+    } else {
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) x[jj] = active ? make_double2(gin[jj], gin[G::M + jj]) : make_double2(0.0, 0.0);
+        __syncthreads();
+    }
+    fgs_radix8<G::R0>(x, tw, 1u);
+    if (active) {
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) {
+            const int idx = t + jj * G::T;
+            gout[idx] = (long long)round(x[jj].x * inv_m);
+            gout[G::M + idx] = (long long)round(x[jj].y * inv_m);
+        }
+    }
+}
+
+int fft64_module_init(pgb_module *m) {
+    const uint64_t mm = m->n / 2;
+    uint64_t *E = (uint64_t *)malloc(sizeof(uint64_t) * (mm > 2 ? mm : 2));
+    E[1] = mm / 2; // numerators over 4m: root block angle 1/4 -> twiddle angle 1/8
+    for (uint64_t i = 1; 2 * i + 1 < mm; i++) {
+        E[2 * i] = E[i] / 2;
+        E[2 * i + 1] = E[i] / 2 + mm;
+    }
+    double2 *hf = (double2 *)calloc(mm, sizeof(double2)), *hi = (double2 *)calloc(mm, sizeof(double2));
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (uint64_t i = 1; i < mm; i++) {
+        long double ang = two_pi * (long double)E[i] / (long double)(4 * mm);
+        double c = (double)cosl(ang), s = (double)sinl(ang);
+        hf[i] = make_double2(c, s);
+        hi[i] = make_double2(c, -s);
+    }
+    free(E);
+    PGB_CHECK_CUDA(cudaMalloc(&m->fft_fwd, mm * sizeof(double2)));
+    PGB_CHECK_CUDA(cudaMalloc(&m->fft_inv, mm * sizeof(double2)));
+    PGB_CHECK_CUDA(cudaMemcpy(m->fft_fwd, hf, mm * sizeof(double2), cudaMemcpyHostToDevice));
+    PGB_CHECK_CUDA(cudaMemcpy(m->fft_inv, hi, mm * sizeof(double2), cudaMemcpyHostToDevice));
+    free(hf);
+    free(hi);
+    return PGB_OK;
+}
+
+template <int L> static constexpr int flpc_for() { return FGeo<L>::T >= 128 ? 1 : (128 / FGeo<L>::T > 16 ? 16 : 128 / FGeo<L>::T); }
+
+template <int L> static int flaunch_fwd(pgb_module *m, const FftJobs &jb) {
+    constexpr int LPC = flpc_for<L>();
+    typedef FGeo<L> G;
+    size_t smem = (size_t)LPC * G::PLANE * sizeof(double2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(fft64_fwd_kernel<L, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int grid = (jb.total_jobs + LPC - 1) / LPC;
+    fft64_fwd_kernel<L, LPC><<<grid, G::T * LPC, smem, m->stream>>>(jb, m->fft_fwd);
+    m->launches++;
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+template <int L> static int flaunch_inv(pgb_module *m, const FftJobs &jb) {
+    constexpr int LPC = flpc_for<L>();
+    typedef FGeo<L> G;
+    size_t smem = (size_t)LPC * G::PLANE * sizeof(double2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(fft64_inv_kernel<L, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int grid = (jb.total_jobs + LPC - 1) / LPC;
+    fft64_inv_kernel<L, LPC><<<grid, G::T * LPC, smem, m->stream>>>(jb, m->fft_inv, 1.0 / (double)(m->n / 2));
+    m->launches++;
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+
+#define FFT_DISPATCH(fn)                           \
+    switch (m->log_n - 1) {                        \
+    case 3: return fn<3>(m, jb);                   \
+    case 4: return fn<4>(m, jb);                   \
+    case 5: return fn<5>(m, jb);                   \
+    case 6: return fn<6>(m, jb);                   \
+    case 7: return fn<7>(m, jb);                   \
+    case 8: return fn<8>(m, jb);                   \
+    case 9: return fn<9>(m, jb);                   \
+    case 10: return fn<10>(m, jb);                 \
+    case 11: return fn<11>(m, jb);                 \
+    case 12: return fn<12>(m, jb);                 \
+    case 13: return fn<13>(m, jb);                 \
+    default:                                       \
+        pgb_set_error("FFT64: n = 2^%d not supported by the single-CTA path (16 <= n <= 16384)", m->log_n); \
+        return PGB_ERR_UNSUPPORTED;                \
+    }
+
+int fft64_forward(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch) {
+    FftJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch};
+    if (jb.total_jobs == 0) return PGB_OK;
+    FFT_DISPATCH(flaunch_fwd)
+}
+int fft64_inverse_big(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch) {
+    FftJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch};
+    if (jb.total_jobs == 0) return PGB_OK;
+    FFT_DISPATCH(flaunch_inv)
+}
+
+// ---- vmp / svp / add / sub on [re | im] limbs ------------------------------------------------------------
+struct FVmpArgs {
+    const char *a;  uint64_t a_bs;
+    char *res;      uint64_t res_bs;
+    const char *pm; uint64_t pm_bs;
+    uint32_t m2;     // double2 words per half limb (= m / 2)
+    uint32_t row_max, C, col0, ncols_out;
+};
+// each thread: two consecutive complex frequencies (double2 of re, double2 of im), CT output columns
+template <int CT> __global__ void __launch_bounds__(256) fft64_vmp_kernel(FVmpArgs p) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= p.m2) return;
+    const uint32_t c0 = blockIdx.y * CT;
+    const size_t poly_words = (size_t)2 * p.m2; // double2 words per poly
+    const double2 *a = reinterpret_cast<const double2 *>(p.a + (size_t)blockIdx.z * p.a_bs) + u;
+    const double2 *pm = reinterpret_cast<const double2 *>(p.pm + (size_t)blockIdx.z * p.pm_bs) + u + (size_t)(p.col0 + c0) * poly_words;
+    double2 *res = reinterpret_cast<double2 *>(p.res + (size_t)blockIdx.z * p.res_bs) + u + (size_t)c0 * poly_words;
+    const int nc = min((uint32_t)CT, p.ncols_out - c0);
+    double2 accr[CT], acci[CT];
+#pragma unroll
+    for (int c = 0; c < CT; c++) accr[c] = acci[c] = make_double2(0.0, 0.0);
+    for (uint32_t r = 0; r < p.row_max; r++) {
+        const double2 ar = __ldg(a + (size_t)r * poly_words), ai = __ldg(a + (size_t)r * poly_words + p.m2);
+        const double2 *mrow = pm + (size_t)r * p.C * poly_words;
+#pragma unroll
+        for (int c = 0; c < CT; c++) {
+            if (c < nc) {
+                const double2 br = __ldg(mrow + (size_t)c * poly_words), bi = __ldg(mrow + (size_t)c * poly_words + p.m2);
+                accr[c].x += ar.x * br.x - ai.x * bi.x;
+                accr[c].y += ar.y * br.y - ai.y * bi.y;
+                acci[c].x += ar.x * bi.x + ai.x * br.x;
+                acci[c].y += ar.y * bi.y + ai.y * br.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CT; c++) {
+        if (c < nc) {
+            res[(size_t)c * poly_words] = accr[c];
+            res[(size_t)c * poly_words + p.m2] = acci[c];
+        }
+    }
+}
+int fft64_vmp(pgb_module *m, const char *a, uint64_t a_bs, char *res, uint64_t res_bs, const char *pm, uint64_t pm_bs,
+              uint32_t row_max, uint32_t C, uint32_t col0, uint32_t ncols_out, uint32_t batch) {
+    if (ncols_out == 0 || batch == 0) return PGB_OK;
+    FVmpArgs p = {a, a_bs, res, res_bs, pm, pm_bs, (uint32_t)(m->n / 4), row_max, C, col0, ncols_out};
+    constexpr int CT = 4;
+    dim3 block(128), grid((p.m2 + 127) / 128, (ncols_out + CT - 1) / CT, batch);
+    fft64_vmp_kernel<CT><<<grid, block, 0, m->stream>>>(p);
+    m->launches++;
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+
+enum { FEW_ADD = 0, FEW_SUB = 1, FEW_NEG = 2, FEW_MUL = 5 };
+struct FEwArgs {
+    LimbSet dst, a, b;
+    uint32_t m;
+};
+template <int OP> __global__ void __launch_bounds__(256) fft64_ew_kernel(FEwArgs p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; // complex index
+    if (i >= p.m) return;
+    const uint32_t j = blockIdx.y, b = blockIdx.z;
+    double *dst = reinterpret_cast<double *>(p.dst.base + (size_t)b * p.dst.batch_stride + (size_t)j * p.dst.limb_stride);
+    const double *a = reinterpret_cast<const double *>(p.a.base + (size_t)b * p.a.batch_stride + (size_t)j * p.a.limb_stride);
+    const double ar = a[i], ai = a[i + p.m];
+    if (OP == FEW_NEG) {
+        dst[i] = -ar;
+        dst[i + p.m] = -ai;
+        return;
+    }
+    const double *bb = reinterpret_cast<const double *>(p.b.base + (size_t)b * p.b.batch_stride + (size_t)j * p.b.limb_stride);
+    const double br = bb[i], bi = bb[i + p.m];
+    if (OP == FEW_ADD) {
+        dst[i] = ar + br;
+        dst[i + p.m] = ai + bi;
+    } else if (OP == FEW_SUB) {
+        dst[i] = ar - br;
+        dst[i + p.m] = ai - bi;
+    } else {
+        dst[i] = ar * br - ai * bi;
+        dst[i + p.m] = ar * bi + ai * br;
+    }
+}
+int fft64_ew(pgb_module *m, int op, LimbSet dst, LimbSet a, LimbSet b, uint32_t jobs, uint32_t batch) {
+    if (jobs == 0 || batch == 0) return PGB_OK;
+    FEwArgs p = {dst, a, b, (uint32_t)(m->n / 2)};
+    dim3 block(256), grid((p.m + 255) / 256, jobs, batch);
+    switch (op) {
+    case FEW_ADD: fft64_ew_kernel<FEW_ADD><<<grid, block, 0, m->stream>>>(p); break;
+    case FEW_SUB: fft64_ew_kernel<FEW_SUB><<<grid, block, 0, m->stream>>>(p); break;
+    case FEW_NEG: fft64_ew_kernel<FEW_NEG><<<grid, block, 0, m->stream>>>(p); break;
+    default: fft64_ew_kernel<FEW_MUL><<<grid, block, 0, m->stream>>>(p); break;
+    }
+    m->launches++;
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}

@@ -1,0 +1,37 @@
+// internal.h -- declarations shared between the translation units of libpoulpy_b200.so (not part of the ABI).
+#pragma once
+#include "common.cuh"
+
+static inline uint64_t prep_bytes(const pgb_module *m) { return m->flavour == PGB_NTT120 ? 16 : 8; }
+static inline uint64_t big_bytes(const pgb_module *m) { return m->flavour == PGB_NTT120 ? 16 : 8; }
+
+enum { EW_ADD = 0, EW_SUB = 1, EW_NEG = 2, EW_COPY = 3, EW_ZERO = 4, EW_MUL = 5 };
+enum { BIG_ADD_SMALL = 0, BIG_FROM_SMALL = 1, BIG_ZERO = 2 };
+
+// ntt120_dft.cu
+int ntt120_module_init(pgb_module *m);
+int ntt120_forward(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch);
+int ntt120_inverse_big(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch);
+// ntt120_ops.cu
+int ntt120_vmp(pgb_module *m, const char *a, uint64_t a_bs, char *res, uint64_t res_bs, const char *pm, uint64_t pm_bs,
+               uint32_t row_max, uint32_t C, uint32_t col0, uint32_t ncols_out, uint32_t batch);
+int ntt120_ew(pgb_module *m, int op, LimbSet dst, LimbSet a, LimbSet b, uint32_t jobs, uint32_t batch);
+// fft64.cu
+int fft64_module_init(pgb_module *m);
+int fft64_forward(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch);
+int fft64_inverse_big(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch);
+int fft64_vmp(pgb_module *m, const char *a, uint64_t a_bs, char *res, uint64_t res_bs, const char *pm, uint64_t pm_bs,
+              uint32_t row_max, uint32_t C, uint32_t col0, uint32_t ncols_out, uint32_t batch);
+int fft64_ew(pgb_module *m, int op, LimbSet dst, LimbSet a, LimbSet b, uint32_t jobs, uint32_t batch);
+// big.cu
+int big_normalize(pgb_module *m, bool big_is_i128, LimbSet res, int res_size, int res_k, int64_t res_offset, LimbSet a, int a_size,
+                  int a_k, int op, uint32_t batch);
+int big_ew(pgb_module *m, bool big_is_i128, int op, LimbSet dst, LimbSet a, uint32_t jobs, uint32_t batch);
+int znx_rotate(pgb_module *m, LimbSet dst, LimbSet a, long long p, const long long *p_dev, uint32_t p_stride, uint32_t jobs, uint32_t batch);
+int raw_limbs(pgb_module *m, bool zero, LimbSet dst, LimbSet a, uint64_t limb_bytes, uint32_t jobs, uint32_t batch);
+// api.cu (used by core.cu)
+int vmp_apply_impl(pgb_module *m, pgb_vec_znx_dft *res, const pgb_vec_znx_dft *a, const pgb_vmp_pmat *pmat, uint64_t limb_offset,
+                   const pgb_batch *bt);
+int big_normalize_impl(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, int64_t res_offset, uint64_t res_col,
+                       const pgb_vec_znx_big *a, uint64_t a_base2k, uint64_t a_col, int op, bool a_is_big, const pgb_batch *bt);
+int big_add_small_impl(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col, const pgb_batch *bt);

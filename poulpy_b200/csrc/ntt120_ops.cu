@@ -1,0 +1,133 @@
+// ntt120_ops.cu -- DFT-domain element-wise kernels of the NTT120 flavour: vmp (K6), svp (K5), add/sub/copy/zero (K8).
+//
+// A DFT "poly" is 16*n bytes: four planes [k][n] of canonical u32 residues.  Every kernel here is a pure
+// stream over polys (HBM-bound): each thread owns one 128-bit word (four consecutive frequencies of one prime).
+//   vmp : res[c][k][f] = sum_r a[r][k][f] * M[r][c][k][f] mod Q[k]
+//         (poulpy-cpu-ref/src/reference/ntt120/vmp.rs:169-288, mat_vec.rs:343-447; products accumulate in u64,
+//          exact for 16 rows at a time, one Barrett-style reduction per 16 rows)
+//   svp : res[j][k][f] = ppol[k][f] * b[j][k][f] mod Q[k]      (svp.rs:87-180)
+//   add/sub/neg/copy/zero on canonical residues                   (vec_znx_dft.rs:418-652, ntt120/prim.rs:64-165)
+#include "internal.h"
+#include "ntt120.cuh"
+
+using namespace n120;
+
+struct VmpArgs {
+    const char *a;  uint64_t a_bs;     // a polys: a + b*a_bs + r*poly_bytes
+    char *res;      uint64_t res_bs;   // res polys: res + b*res_bs + c*poly_bytes
+    const char *pm; uint64_t pm_bs;    // pmat polys: pm + b*pm_bs + (r*C + c)*poly_bytes
+    uint32_t n4;                        // uint4 words per plane (= n / 4)
+    uint32_t row_max, C, col0, ncols_out;
+};
+
+template <int CT> __global__ void __launch_bounds__(256) ntt120_vmp_kernel(VmpArgs p) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; // uint4 index inside a poly, [0, 4*n4)
+    if (u >= 4 * p.n4) return;
+    const int k = u / p.n4;
+    const uint32_t c0 = blockIdx.y * CT;
+    const size_t poly_words = (size_t)4 * p.n4;
+    const uint4 *a = reinterpret_cast<const uint4 *>(p.a + (size_t)blockIdx.z * p.a_bs) + u;
+    const uint4 *pm = reinterpret_cast<const uint4 *>(p.pm + (size_t)blockIdx.z * p.pm_bs) + u + (size_t)(p.col0 + c0) * poly_words;
+    uint4 *res = reinterpret_cast<uint4 *>(p.res + (size_t)blockIdx.z * p.res_bs) + u + (size_t)c0 * poly_words;
+    const int nc = min((uint32_t)CT, p.ncols_out - c0);
+
+    unsigned long long acc[CT][4];
+#pragma unroll
+    for (int c = 0; c < CT; c++) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0;
+
+    for (uint32_t r0 = 0; r0 < p.row_max; r0 += 16) {
+        const uint32_t r1 = min(r0 + 16, p.row_max);
+        for (uint32_t r = r0; r < r1; r++) {
+            const uint4 av = __ldg(a + (size_t)r * poly_words);
+            const uint4 *mrow = pm + (size_t)r * p.C * poly_words;
+#pragma unroll
+            for (int c = 0; c < CT; c++) {
+                if (c < nc) {
+                    const uint4 mv = __ldg(mrow + (size_t)c * poly_words);
+                    acc[c][0] += (unsigned long long)av.x * mv.x;
+                    acc[c][1] += (unsigned long long)av.y * mv.y;
+                    acc[c][2] += (unsigned long long)av.z * mv.z;
+                    acc[c][3] += (unsigned long long)av.w * mv.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CT; c++) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) acc[c][i] = red64k(acc[c][i], k);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CT; c++) {
+        if (c < nc) res[(size_t)c * poly_words] = make_uint4((uint32_t)acc[c][0], (uint32_t)acc[c][1], (uint32_t)acc[c][2], (uint32_t)acc[c][3]);
+    }
+}
+
+int ntt120_vmp(pgb_module *m, const char *a, uint64_t a_bs, char *res, uint64_t res_bs, const char *pm, uint64_t pm_bs,
+               uint32_t row_max, uint32_t C, uint32_t col0, uint32_t ncols_out, uint32_t batch) {
+    if (ncols_out == 0 || batch == 0) return PGB_OK;
+    VmpArgs p = {a, a_bs, res, res_bs, pm, pm_bs, (uint32_t)(m->n / 4), row_max, C, col0, ncols_out};
+    const uint32_t words = (uint32_t)m->n; // uint4 words per poly
+    dim3 block(256);
+    constexpr int CT = 4;
+    dim3 grid((words + 255) / 256, (ncols_out + CT - 1) / CT, batch);
+    ntt120_vmp_kernel<CT><<<grid, block, 0, m->stream>>>(p);
+    m->launches++;
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+
+// ---- element-wise over limb sets ---------------------------------------------------------------------
+
+struct EwArgs {
+    LimbSet dst, a, b;
+    uint32_t n4;            // uint4 words per plane
+    uint32_t jobs_per_batch;
+};
+
+__device__ __forceinline__ uint32_t addq(uint32_t x, uint32_t y, uint32_t q) { return csub(x + y, q); }
+__device__ __forceinline__ uint32_t subq(uint32_t x, uint32_t y, uint32_t q) { return x >= y ? x - y : x - y + q; }
+__device__ __forceinline__ uint32_t negq(uint32_t x, uint32_t q) { return x == 0 ? 0 : q - x; }
+
+template <int OP> __global__ void __launch_bounds__(256) ntt120_ew_kernel(EwArgs p) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= 4 * p.n4) return;
+    const int k = u / p.n4;
+    const uint32_t q = qk(k);
+    const uint32_t j = blockIdx.y, b = blockIdx.z;
+    uint4 *dst = reinterpret_cast<uint4 *>(p.dst.base + (size_t)b * p.dst.batch_stride + (size_t)j * p.dst.limb_stride) + u;
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (OP != EW_ZERO) {
+        const uint4 x = *(reinterpret_cast<const uint4 *>(p.a.base + (size_t)b * p.a.batch_stride + (size_t)j * p.a.limb_stride) + u);
+        if (OP == EW_COPY) r = x;
+        else if (OP == EW_NEG) r = make_uint4(negq(x.x % q, q), negq(x.y % q, q), negq(x.z % q, q), negq(x.w % q, q));
+        else {
+            const uint4 y = *(reinterpret_cast<const uint4 *>(p.b.base + (size_t)b * p.b.batch_stride + (size_t)j * p.b.limb_stride) + u);
+            if (OP == EW_ADD) r = make_uint4(addq(x.x, y.x, q), addq(x.y, y.y, q), addq(x.z, y.z, q), addq(x.w, y.w, q));
+            else if (OP == EW_SUB) r = make_uint4(subq(x.x, y.x, q), subq(x.y, y.y, q), subq(x.z, y.z, q), subq(x.w, y.w, q));
+            else { // EW_MUL
+                r = make_uint4(red64k((unsigned long long)x.x * y.x, k), red64k((unsigned long long)x.y * y.y, k),
+                               red64k((unsigned long long)x.z * y.z, k), red64k((unsigned long long)x.w * y.w, k));
+            }
+        }
+    }
+    *dst = r;
+}
+
+// op over `jobs` limbs per batch item; a/b may alias dst limb for limb (pure element-wise)
+int ntt120_ew(pgb_module *m, int op, LimbSet dst, LimbSet a, LimbSet b, uint32_t jobs, uint32_t batch) {
+    if (jobs == 0 || batch == 0) return PGB_OK;
+    EwArgs p = {dst, a, b, (uint32_t)(m->n / 4), jobs};
+    dim3 block(256), grid(((uint32_t)m->n + 255) / 256, jobs, batch);
+    switch (op) {
+    case EW_ADD: ntt120_ew_kernel<EW_ADD><<<grid, block, 0, m->stream>>>(p); break;
+    case EW_SUB: ntt120_ew_kernel<EW_SUB><<<grid, block, 0, m->stream>>>(p); break;
+    case EW_NEG: ntt120_ew_kernel<EW_NEG><<<grid, block, 0, m->stream>>>(p); break;
+    case EW_COPY: ntt120_ew_kernel<EW_COPY><<<grid, block, 0, m->stream>>>(p); break;
+    case EW_ZERO: ntt120_ew_kernel<EW_ZERO><<<grid, block, 0, m->stream>>>(p); break;
+    default: ntt120_ew_kernel<EW_MUL><<<grid, block, 0, m->stream>>>(p); break;
+    }
+    m->launches++;
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
