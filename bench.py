@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the poulpy-hal hot path on B200 (contract: see the task statement).
+
+Workload (config.workload): GLWE key-switch, NTT120 flavour, the reference's own bench defaults
+(poulpy-bench/src/params.rs:112-121, poulpy-bench/benches/keyswitch.rs): n=4096, base2k=18, k=54 (3 limbs), rank=1,
+dsize=1, dnum=3, key k=72 (4 limbs); a batch of independent ciphertexts against one prepared key.
+One "step" = one pass of the hot path over one batch.  Inputs are synthetic uniform digits (the reference's HAL benches
+use random bytes, poulpy-bench/src/bench_suite/hal/vmp.rs:154-156).
+
+  value : key-switches/s, inputs resident in HBM, all N ranks (batch sharded, key replicated, no collective)
+  e2e   : same metric through pgb_glwe_keyswitch_host with pinned HOST buffers (H2D + compute + D2H in the timed region)
+  roofline : dominant kernel, algorithmic bytes / CUDA-event time vs the measured HBM copy bandwidth
+  cpu_baseline : the oracle port (C restatement of poulpy-cpu-ref) on the box's host cores, bounded sample
+
+`--impl reference` times that CPU port alone (the Rust reference cannot be built in this image).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORK = dict(n=4096, base2k=18, a_size=3, key_size=4, rank=1, dnum=3, dsize=1)
+
+
+def make_inputs(batch, seed):
+    w = WORK
+    rng = np.random.default_rng(seed)
+    lo, hi = -(1 << (w["base2k"] - 1)), 1 << (w["base2k"] - 1)
+    a = rng.integers(lo, hi, size=(batch, w["a_size"], w["rank"] + 1, w["n"]), dtype=np.int64)
+    mat = np.random.default_rng(1234).integers(lo, hi, size=(w["dnum"], w["rank"], w["key_size"], w["rank"] + 1, w["n"]), dtype=np.int64)
+    return a, mat
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, device):
+        self.device, self.samples, self.reasons, self.stop = device, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
+                 "hw_power_brake_slowdown": 0x80}
+        while not self.stop:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        if self.nv:
+            self.t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_port(sample_target_cpu_s=15.0, threads=0):
+    """Times the oracle port on the host cores on a bounded sample of the same workload."""
+    from oracle import pyoracle as O
+
+    w = WORK
+    threads = threads or O.num_threads()
+    om = O.OracleModule(w["n"], O.NTT120)
+    a, mat = make_inputs(4 * threads, 99)
+    pm = om.vmp_pmat_alloc(w["dnum"], w["rank"], w["rank"] + 1, w["key_size"])
+    om.vmp_prepare(pm, mat)
+    res = np.zeros_like(a)
+    t0 = time.perf_counter()
+    om.glwe_keyswitch_batch(res, w["base2k"], a, w["base2k"], pm, w["base2k"], w["dsize"], threads=threads)
+    per_ks_cpu_s = (time.perf_counter() - t0) * threads / a.shape[0]
+    count = int(max(4 * threads, min(sample_target_cpu_s / per_ks_cpu_s, 200000)))
+    count -= count % threads
+    a, _ = make_inputs(count, 98)
+    res = np.zeros_like(a)
+    t0 = time.perf_counter()
+    om.glwe_keyswitch_batch(res, w["base2k"], a, w["base2k"], pm, w["base2k"], w["dsize"], threads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": count / dt, "unit": "keyswitch/s", "cores": threads, "kind": "port",
+            "sample": f"{count} key-switches of the bench workload, oracle C port (restates poulpy-cpu-ref NTT120), {threads} threads"}, om, pm
+
+
+def config_dict(batch, n_gpus):
+    w = WORK
+    return {"workload": "glwe_keyswitch ntt120 n=4096 base2k=18 k=54 rank=1 dsize=1 dnum=3 key_k=72 (poulpy-bench keyswitch defaults)",
+            "batch_per_gpu": batch, "global_batch": batch * n_gpus, "flavour": "ntt120", "parallelism": f"batch-sharded x{n_gpus}, key replicated",
+            "l2": "inputs larger than L2 (batch * 196 KB in, 196 KB out per pass)", **w}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle as O
+
+    w = WORK
+    threads = O.num_threads()
+    om = O.OracleModule(w["n"], O.NTT120)
+    a, mat = make_inputs(8 * threads, 7)
+    pm = om.vmp_pmat_alloc(w["dnum"], w["rank"], w["rank"] + 1, w["key_size"])
+    om.vmp_prepare(pm, mat)
+    res = np.zeros_like(a)
+    t0 = time.perf_counter()
+    om.glwe_keyswitch_batch(res, w["base2k"], a, w["base2k"], pm, w["base2k"], w["dsize"], threads=threads)
+    per = (time.perf_counter() - t0) / a.shape[0]
+    total = args.steps + args.warmup
+    per_step = int(max(threads, min(120.0 / total, 4.0) / per))  # each step ~ <= 4 s, whole run within ~2 minutes
+    per_step -= per_step % threads
+    a, _ = make_inputs(per_step, 8)
+    res = np.zeros_like(a)
+    for _ in range(args.warmup):
+        om.glwe_keyswitch_batch(res, w["base2k"], a, w["base2k"], pm, w["base2k"], w["dsize"], threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        om.glwe_keyswitch_batch(res, w["base2k"], a, w["base2k"], pm, w["base2k"], w["dsize"], threads=threads)
+    dt = time.perf_counter() - t0
+    v = per_step * args.steps / dt
+    sample = f"{per_step} key-switches per step, oracle C port of poulpy-cpu-ref (Rust reference not buildable here), {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "glwe_keyswitch_per_s", "value": v, "unit": "keyswitch/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64 (lazy q120b residues)", "data": "synthetic", "config": config_dict(per_step, 1),
+        "cpu_baseline": {"value": v, "unit": "keyswitch/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "keyswitch/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--batch", type=int, default=4096, help="ciphertexts per GPU per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary measurements")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import poulpy_b200 as pb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w, B = WORK, args.batch
+    m = pb.Module(w["n"], pb.NTT120, device=local)
+    stream = torch.cuda.Stream(device=local)
+    m.set_stream(stream.cuda_stream)
+
+    a_np, mat = make_inputs(B, 1000 + rank)
+    pmat = m.vmp_pmat_alloc(w["dnum"], w["rank"], w["rank"] + 1, w["key_size"])
+    m.vmp_prepare(pmat, m.mat_znx_from_numpy(mat))  # key replicated once per GPU (setup, not timed)
+    a_dev = m.vec_znx_from_numpy(a_np)
+    res_dev = m.vec_znx_alloc(w["rank"] + 1, w["a_size"], B)
+    scratch = None
+    k = w["base2k"]
+
+    def step():
+        nonlocal scratch
+        scratch = m.glwe_keyswitch(res_dev, k, a_dev, k, pmat, k, w["dsize"], scratch)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    import ctypes as C
+
+    lib = pb.lib()
+    lib.pgb_profile_enable(m._h, 1)
+    launches0 = m.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as cs:
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for _ in range(args.steps):
+                step()
+            ev1.record(stream)
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    prof_ms = (C.c_double * 6)()
+    prof_n = (C.c_uint64 * 6)()
+    lib.pgb_profile_read(m._h, prof_ms, prof_n, 1)
+    lib.pgb_profile_enable(m._h, 0)
+    launches = m.launch_count - launches0
+    barrier()
+    t = torch.tensor([ms], device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max * 1e-3)
+
+    # ---- e2e: host buffers, copies inside the timed region --------------------------------------------------------
+    a_host = pb.pinned_empty(a_np.shape)
+    a_host[:] = a_np
+    r_host = pb.pinned_empty(a_np.shape)
+    e2e_steps = max(3, min(args.steps, 10))
+    m.glwe_keyswitch_host(r_host, k, a_host, k, pmat, k, w["dsize"])  # warm-up (allocates staging)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        m.glwe_keyswitch_host(r_host, k, a_host, k, pmat, k, w["dsize"])  # synchronous: returns when r_host is complete
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / float(t.item())
+    check = m.vec_znx_to_numpy(res_dev)
+    assert np.array_equal(check, r_host), "device-resident and host-path results differ"
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------------------------
+    n = w["n"]
+    cols_out, R, Cc = w["rank"] + 1, w["dnum"] * w["rank"], (w["rank"] + 1) * w["key_size"]
+    bytes_per_launch = {
+        "dft_forward": B * w["a_size"] * (8 * n + 16 * n),                # i64 limb in, 16 B/coef DFT limb out
+        "dft_inverse": B * Cc * (16 * n + 16 * n),                        # DFT limb in, i128 limb out (in place)
+        "vmp_apply": B * (R + Cc) * 16 * n + R * Cc * 16 * n,             # a + res per ciphertext, matrix once
+        "normalize": B * (w["key_size"] * 16 * n + w["a_size"] * 8 * n),  # per column: 4 i128 limbs in, 3 i64 limbs out
+        "elementwise": B * (2 * 16 * n + 8 * n),                          # add_small on one limb (RMW i128 + i64)
+    }
+    lib.pgb_profile_category_name.restype = C.c_char_p
+    names = [lib.pgb_profile_category_name(i).decode() for i in range(6)]
+    peak, peak_src = peaks()
+    kernels = {}
+    for i, nm in enumerate(names):
+        if prof_n[i] == 0:
+            continue
+        avg_ms = prof_ms[i] / prof_n[i]
+        d = {"launches": int(prof_n[i]), "avg_ms": avg_ms, "share_of_step": prof_ms[i] / ms}
+        if nm in bytes_per_launch:
+            d["algorithmic_bytes_per_launch"] = bytes_per_launch[nm]
+            d["achieved_gbs"] = bytes_per_launch[nm] / (avg_ms * 1e-3) / 1e9
+            d["frac_of_hbm_peak"] = d["achieved_gbs"] / peak
+        kernels[nm] = d
+    dom = max((k_ for k_ in kernels if "achieved_gbs" in kernels[k_]), key=lambda k_: kernels[k_]["launches"] * kernels[k_]["avg_ms"])
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "note": "algorithmic bytes per launch / CUDA-event duration on the launching stream; see DESIGN.md for the per-unit figures"}
+    # whole-pipeline view: unfused HAL-sequence bytes per key-switch in this backend's 16 B layout
+    pipeline_bytes = (bytes_per_launch["dft_forward"] + bytes_per_launch["dft_inverse"] + bytes_per_launch["vmp_apply"]
+                      + 2 * bytes_per_launch["normalize"] + bytes_per_launch["elementwise"]) / B
+    step_gbs = pipeline_bytes * B / (ms / args.steps * 1e-3) / 1e9
+
+    out = {
+        "metric": "glwe_keyswitch_per_s", "value": value, "unit": "keyswitch/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32 (canonical residues mod four 30-bit primes; i128 big)", "data": "synthetic", "config": config_dict(B, world),
+        "e2e": {"value": e2e_value, "unit": "keyswitch/s", "h2d_bytes_per_step": int(a_np.nbytes), "d2h_bytes_per_step": int(a_np.nbytes),
+                "steps": e2e_steps, "api": "pgb_glwe_keyswitch_host (pinned host buffers)"},
+        "gpu_launches": int(launches), "clocks": cs.summary(), "roofline": roofline, "kernels": kernels,
+        "pipeline": {"unfused_bytes_per_keyswitch": pipeline_bytes, "achieved_gbs": step_gbs, "frac_of_hbm_peak": step_gbs / peak},
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cb, _, _ = cpu_port()
+        out["cpu_baseline"] = cb
+    if rank == 0 and world == 1 and not args.no_aux:
+        try:
+            out["aux"] = aux_measurements(pb, torch, local, peak)
+        except Exception as e:  # auxiliary numbers must never break the headline line
+            out["aux"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _time_ms(torch, stream, fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(iters):
+            fn()
+        e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def aux_measurements(pb, torch, local, peak):
+    """Secondary numbers named by BASELINE.json: external products/s (config 2) and vmp_apply HBM GB/s (M5 shapes)."""
+    aux = {}
+    stream = torch.cuda.Stream(device=local)
+    rng = np.random.default_rng(5)
+    # GGSW x GLWE external product, n=2048, batch 4096 (BASELINE config "external product batch (4096 ciphertexts) at log_n=11")
+    for fl, nm in ((pb.NTT120, "ntt120"), (pb.FFT64, "fft64")):
+        n, B, k = 2048, 4096, 18
+        m = pb.Module(n, fl, device=local)
+        m.set_stream(stream.cuda_stream)
+        mat = rng.integers(-(1 << 17), 1 << 17, size=(3, 2, 3, 2, n), dtype=np.int64)
+        pm = m.vmp_pmat_alloc(3, 2, 2, 3)
+        m.vmp_prepare(pm, m.mat_znx_from_numpy(mat))
+        a = m.vec_znx_from_numpy(rng.integers(-(1 << 17), 1 << 17, size=(B, 3, 2, n), dtype=np.int64))
+        r = m.vec_znx_alloc(2, 3, B)
+        sc = [None]
+
+        def f():
+            sc[0] = m.glwe_external_product(r, k, a, k, pm, k, 1, sc[0])
+
+        ms = _time_ms(torch, stream, f, 10)
+        aux[f"glwe_external_product_per_s_{nm}_n2048_b4096"] = B / (ms * 1e-3)
+        del m, a, r, pm, sc
+    # key-switch in the FFT64 flavour (row M1f)
+    n, B, k = 4096, 4096, 18
+    m = pb.Module(n, pb.FFT64, device=local)
+    m.set_stream(stream.cuda_stream)
+    mat = rng.integers(-(1 << 17), 1 << 17, size=(3, 1, 4, 2, n), dtype=np.int64)
+    pm = m.vmp_pmat_alloc(3, 1, 2, 4)
+    m.vmp_prepare(pm, m.mat_znx_from_numpy(mat))
+    a = m.vec_znx_from_numpy(rng.integers(-(1 << 17), 1 << 17, size=(B, 3, 2, n), dtype=np.int64))
+    r = m.vec_znx_alloc(2, 3, B)
+    sc = [None]
+
+    def f2():
+        sc[0] = m.glwe_keyswitch(r, k, a, k, pm, k, 1, sc[0])
+
+    ms = _time_ms(torch, stream, f2, 10)
+    aux["glwe_keyswitch_per_s_fft64_n4096_b4096"] = B / (ms * 1e-3)
+    del m, a, r, pm, sc
+    # vmp_apply_dft_to_dft alone, single ciphertext, the reference's sweep (poulpy-bench/src/params.rs:75-81) + CKKS-like shape
+    vm = {}
+    for (log_n, rows, cols_in, cols_out, size) in ((12, 7, 1, 2, 8), (13, 15, 1, 2, 16)):
+        n = 1 << log_n
+        m = pb.Module(n, pb.NTT120, device=local)
+        m.set_stream(stream.cuda_stream)
+        pm = m.vmp_pmat_alloc(rows, cols_in, cols_out, size)  # content irrelevant for bandwidth
+        a = m.vec_znx_dft_alloc(cols_in, rows)
+        r = m.vec_znx_dft_alloc(cols_out, size)
+        import ctypes as C
+
+        lib = pb.lib()
+        rs, as_, ps = r.struct(), a.struct(), pm.struct()
+        bt = pb.hal._BT(1, 0, 0, 0)
+
+        def f3():
+            lib.pgb_vmp_apply_dft_to_dft_batched(m._h, C.byref(rs), C.byref(as_), C.byref(ps), C.c_uint64(0), C.byref(bt))
+
+        ms = _time_ms(torch, stream, f3, 50, warm=5)
+        R, Cc = rows * cols_in, cols_out * size
+        byts = (R + R * Cc + Cc) * n * 16
+        vm[f"log_n={log_n},rows={rows},cols_in={cols_in},cols_out={cols_out},size={size}"] = {
+            "ms": ms, "algorithmic_bytes": byts, "achieved_gbs": byts / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": byts / (ms * 1e-3) / 1e9 / peak}
+        del m, a, r, pm
+    aux["vmp_apply_dft_to_dft_ntt120"] = vm
+    return aux
+
+
+if __name__ == "__main__":
+    main()

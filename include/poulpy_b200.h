@@ -82,6 +82,14 @@ int pgb_module_sync(pgb_module *m);
 /* number of kernels launched by this module since creation (bench.py's gpu_launches) */
 uint64_t pgb_module_launch_count(const pgb_module *m);
 
+/* Optional per-kernel timing: when enabled every kernel launch is bracketed by CUDA events on the module's stream and the
+ * elapsed device time is accumulated per category (0 dft_forward, 1 dft_inverse, 2 vmp_apply, 3 normalize, 4 elementwise,
+ * 5 other).  pgb_profile_read synchronises the stream and fills ms[6] / launches[6]. */
+#define PGB_PROFILE_NCAT 6
+int pgb_profile_enable(pgb_module *m, int on);
+int pgb_profile_read(pgb_module *m, double *ms, uint64_t *launches, int reset);
+const char *pgb_profile_category_name(int category);
+
 /* ---- memory (Backend::alloc_bytes / from_bytes, layouts/module.rs:36-39; lib.rs:146 alignment) ---- */
 void *pgb_alloc_bytes(size_t len);        /* CUDA managed, host-dereferenceable, zero-filled */
 void *pgb_alloc_device_bytes(size_t len); /* device only, zero-filled */

@@ -21,6 +21,70 @@ extern "C" int pgb_device_count(void) {
     return c;
 }
 
+// ---- profiler: CUDA events on the launching stream around every kernel, accumulated per category --------------
+#include <vector>
+struct ProfState {
+    std::vector<cudaEvent_t> pool;            // start/stop pairs
+    std::vector<int> cat;                     // category of pair i
+    size_t used = 0;
+    double ms[PROF_NCAT] = {0};
+    uint64_t count[PROF_NCAT] = {0};
+};
+void prof_begin(pgb_module *m, int cat) {
+    ProfState *p = m->prof;
+    if (p->used * 2 + 2 > p->pool.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        p->pool.push_back(a);
+        p->pool.push_back(b);
+        p->cat.push_back(cat);
+    }
+    p->cat[p->used] = cat;
+    cudaEventRecord(p->pool[2 * p->used], m->stream);
+}
+void prof_end(pgb_module *m) {
+    ProfState *p = m->prof;
+    cudaEventRecord(p->pool[2 * p->used + 1], m->stream);
+    p->used++;
+}
+static int prof_collect(pgb_module *m) {
+    ProfState *p = m->prof;
+    if (!p) return PGB_OK;
+    PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+    for (size_t i = 0; i < p->used; i++) {
+        float ms = 0.f;
+        PGB_CHECK_CUDA(cudaEventElapsedTime(&ms, p->pool[2 * i], p->pool[2 * i + 1]));
+        p->ms[p->cat[i]] += ms;
+        p->count[p->cat[i]]++;
+    }
+    p->used = 0;
+    return PGB_OK;
+}
+extern "C" int pgb_profile_enable(pgb_module *m, int on) {
+    if (on && !m->prof) m->prof = new ProfState();
+    if (!on) PGB_TRY(prof_collect(m));
+    m->prof_on = on != 0;
+    return PGB_OK;
+}
+extern "C" int pgb_profile_read(pgb_module *m, double *ms, uint64_t *launches, int reset) {
+    PGB_REQUIRE(m->prof != nullptr, "pgb_profile_read: profiling was never enabled");
+    PGB_TRY(prof_collect(m));
+    for (int c = 0; c < PROF_NCAT; c++) {
+        ms[c] = m->prof->ms[c];
+        launches[c] = m->prof->count[c];
+        if (reset) {
+            m->prof->ms[c] = 0;
+            m->prof->count[c] = 0;
+        }
+    }
+    return PGB_OK;
+}
+extern "C" const char *pgb_profile_category_name(int c) {
+    static const char *names[PROF_NCAT] = {"dft_forward", "dft_inverse", "vmp_apply", "normalize", "elementwise", "other"};
+    return (c >= 0 && c < PROF_NCAT) ? names[c] : "?";
+}
+
 // ---- module -------------------------------------------------------------------------------------------
 extern "C" int pgb_module_new(uint64_t n, int flavour, int device, pgb_module **out) {
     PGB_REQUIRE(out != nullptr, "pgb_module_new: out is null");
@@ -64,6 +128,10 @@ extern "C" void pgb_module_destroy(pgb_module *m) {
     cudaFree(m->fft_fwd);
     cudaFree(m->fft_inv);
     cudaFree(m->ws);
+    if (m->prof) {
+        for (cudaEvent_t e : m->prof->pool) cudaEventDestroy(e);
+        delete m->prof;
+    }
     for (int i = 0; i < 4; i++)
         if (m->pinned[i]) cudaFreeHost(m->pinned[i]);
     if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);

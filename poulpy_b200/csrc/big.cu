@@ -227,6 +227,7 @@ int big_normalize(pgb_module *m, bool big_is_i128, LimbSet res, int res_size, in
         lo -= 1;
     }
     p.lsh = (int)lsh;
+    ProfScope _ps(m, PROF_NORMALIZE);
     dim3 block(256), grid(((uint32_t)m->n + 255) / 256, batch);
     if (res_k == a_k) {
         p.res_end = (int)clampi(-lo, 0, res_size);
@@ -277,6 +278,7 @@ template <typename T, int OP> __global__ void __launch_bounds__(256) big_ew_kern
 
 int big_ew(pgb_module *m, bool big_is_i128, int op, LimbSet dst, LimbSet a, uint32_t jobs, uint32_t batch) {
     if (jobs == 0 || batch == 0) return PGB_OK;
+    ProfScope _ps(m, PROF_ELEMENTWISE);
     BigEwArgs p = {dst, a, (uint32_t)m->n};
     dim3 block(256), grid(((uint32_t)m->n + 255) / 256, jobs, batch);
 #define LAUNCH(T, OP) big_ew_kernel<T, OP><<<grid, block, 0, m->stream>>>(p)
@@ -326,6 +328,7 @@ __global__ void __launch_bounds__(256) rotate_kernel(RotArgs q) {
 }
 int znx_rotate(pgb_module *m, LimbSet dst, LimbSet a, long long p, const long long *p_dev, uint32_t p_stride, uint32_t jobs, uint32_t batch) {
     if (jobs == 0 || batch == 0) return PGB_OK;
+    ProfScope _ps(m, PROF_OTHER);
     RotArgs q = {dst, a, (uint32_t)m->n, p_dev, p, p_stride};
     dim3 block(256), grid(((uint32_t)m->n + 255) / 256, jobs, batch);
     rotate_kernel<<<grid, block, 0, m->stream>>>(q);
@@ -349,6 +352,7 @@ __global__ void __launch_bounds__(256) raw_kernel(RawArgs p) {
 }
 int raw_limbs(pgb_module *m, bool zero, LimbSet dst, LimbSet a, uint64_t limb_bytes, uint32_t jobs, uint32_t batch) {
     if (jobs == 0 || batch == 0) return PGB_OK;
+    ProfScope _ps(m, PROF_ELEMENTWISE);
     RawArgs p = {dst, a, (uint32_t)(limb_bytes / 16), zero ? 1 : 0};
     dim3 block(256), grid((p.words + 255) / 256, jobs, batch);
     raw_kernel<<<grid, block, 0, m->stream>>>(p);

@@ -21,8 +21,9 @@ extern "C" int pgb_cggi_x_pow_a(pgb_module *m, pgb_svp_ppol *res) {
     const uint64_t n = m->n, pb = prep_bytes(m);
     long long *buf = nullptr;
     PGB_CHECK_CUDA(cudaMalloc(&buf, 2 * n * n * 8));
+    { ProfScope _ps(m, PROF_OTHER);
     xpow_fill_kernel<<<(unsigned)(2 * n), 256, 0, m->stream>>>(buf, (uint32_t)n);
-    m->launches++;
+    }
     LimbSet in = {(char *)buf, n * 8, 0}, out = {(char *)res->data, n * pb, 0};
     int s = m->flavour == PGB_NTT120 ? ntt120_forward(m, in, out, (int)(2 * n), 1) : fft64_forward(m, in, out, (int)(2 * n), 1);
     cudaStreamSynchronize(m->stream);
@@ -43,19 +44,129 @@ extern "C" size_t pgb_cggi_blind_rotate_tmp_bytes(const pgb_module *m, uint64_t 
     return t + ALIGN;
 }
 
-// res[b][j][k][f] (+)= ppol[idx[b]][k][f] * v[b][j][k][f] : svp with a per-item gathered SvpPPol column
+// acc[b][col][j] = (acc + x_pow_a[a_b] * v) - v   for every column and limb: the three HAL calls of algorithm.rs:351-355
+// (svp_apply_dft_to_dft into vmp_xai, vec_znx_dft_add_assign, vec_znx_dft_sub_assign) in one pass.
+struct XaiArgs {
+    char *acc;       uint64_t acc_bs;  // acc_add_dft polys (cols * size), batch stride
+    const char *v;   uint64_t v_bs;    // vmp_res polys
+    const char *xpa;                   // x_pow_a table: 2n polys of ScalarPrep
+    const long long *lwe; uint64_t lwe_stride; // a_i of item b at lwe[b * lwe_stride]
+    uint32_t n, polys;
+};
+#include "ntt120.cuh"
+__global__ void __launch_bounds__(256) cggi_xai_ntt120_kernel(XaiArgs p) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; // uint4 index inside a poly
+    if (u >= p.n) return;
+    const int k = u / (p.n / 4);
+    const uint32_t q = n120::qk(k);
+    const uint32_t b = blockIdx.z, poly = blockIdx.y;
+    const long long ai = p.lwe[(size_t)b * p.lwe_stride];
+    const uint32_t pos = (uint32_t)((ai + (long long)(2 * p.n)) & (long long)(2 * p.n - 1));
+    const uint4 w = __ldg(reinterpret_cast<const uint4 *>(p.xpa + (size_t)pos * p.n * 16) + u);
+    const uint4 v = *(reinterpret_cast<const uint4 *>(p.v + (size_t)b * p.v_bs + (size_t)poly * p.n * 16) + u);
+    uint4 *ap = reinterpret_cast<uint4 *>(p.acc + (size_t)b * p.acc_bs + (size_t)poly * p.n * 16) + u;
+    const uint4 a = *ap;
+    auto f = [&](uint32_t acc, uint32_t ww, uint32_t vv) {
+        uint32_t pv = n120::red64k((unsigned long long)ww * vv, k);
+        uint32_t t = n120::csub(acc + pv, q);
+        return t >= vv ? t - vv : t - vv + q;
+    };
+    *ap = make_uint4(f(a.x, w.x, v.x), f(a.y, w.y, v.y), f(a.z, w.z, v.z), f(a.w, w.w, v.w));
+}
+__global__ void __launch_bounds__(256) cggi_xai_fft64_kernel(XaiArgs p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; // complex index
+    const uint32_t m = p.n / 2;
+    if (i >= m) return;
+    const uint32_t b = blockIdx.z, poly = blockIdx.y;
+    const long long ai = p.lwe[(size_t)b * p.lwe_stride];
+    const uint32_t pos = (uint32_t)((ai + (long long)(2 * p.n)) & (long long)(2 * p.n - 1));
+    const double *w = reinterpret_cast<const double *>(p.xpa + (size_t)pos * p.n * 8);
+    const double *v = reinterpret_cast<const double *>(p.v + (size_t)b * p.v_bs + (size_t)poly * p.n * 8);
+    double *a = reinterpret_cast<double *>(p.acc + (size_t)b * p.acc_bs + (size_t)poly * p.n * 8);
+    const double wr = __ldg(w + i), wi = __ldg(w + i + m), vr = v[i], vi = v[i + m];
+    const double pr = wr * vr - wi * vi, pi = wr * vi + wi * vr; // reim_mul(ppol, v)
+    a[i] = (a[i] + pr) - vr;
+    a[i + m] = (a[i + m] + pi) - vi;
+}
+
+static pgb_vec_znx mkv(void *data, uint64_t n, uint64_t cols, uint64_t size) {
+    pgb_vec_znx v = {data, n, cols, size, size};
+    return v;
+}
+
 int cggi_blind_rotate_impl(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2n, uint64_t n_lwe, const pgb_vec_znx *lut,
                            const pgb_vmp_pmat *brk, const pgb_svp_ppol *x_pow_a, uint64_t block_size, uint64_t base2k, const pgb_batch *bt,
-                           void *scratch, size_t scratch_len);
+                           void *scratch, size_t scratch_len) {
+    PGB_REQUIRE(bt && bt->count >= 1 && bt->count <= 65535, "cggi_blind_rotate: batch count must be in [1, 65535]");
+    PGB_REQUIRE(res->n == m->n && lut->n == m->n && brk->n == m->n && x_pow_a->n == m->n, "cggi_blind_rotate: ring degree mismatch");
+    PGB_REQUIRE(x_pow_a->cols == 2 * m->n, "cggi_blind_rotate: x_pow_a must have 2n columns");
+    PGB_REQUIRE(brk->cols_in == res->cols && brk->cols_out == res->cols, "cggi_blind_rotate: brk rank does not match res");
+    PGB_REQUIRE(block_size >= 1, "cggi_blind_rotate: block_size must be >= 1");
+    const uint64_t n = m->n, pb = prep_bytes(m), bb = big_bytes(m), B = bt->count, cols = res->cols;
+    const uint64_t dnum = brk->rows, bsize = brk->size;
+    const size_t need = pgb_cggi_blind_rotate_tmp_bytes(m, cols - 1, res->size, dnum, bsize, B);
+    if (scratch_len < need) {
+        pgb_set_error("cggi_blind_rotate: scratch of %zu bytes < required %zu", scratch_len, need);
+        return PGB_ERR_SCRATCH;
+    }
+    char *sp = (char *)scratch;
+    auto take = [&](uint64_t bytes) {
+        char *p = sp;
+        sp += align_up(bytes);
+        return (void *)p;
+    };
+    const uint64_t acc_bs = n * cols * dnum * pb, vres_bs = n * cols * bsize * pb, xai_bs = n * bsize * pb, big_bs = n * bsize * bb;
+    pgb_vec_znx_dft acc_dft = mkv(take(B * acc_bs), n, cols, dnum);
+    pgb_vec_znx_dft vmp_res = mkv(take(B * vres_bs), n, cols, bsize);
+    pgb_vec_znx_dft acc_add = mkv(take(B * vres_bs), n, cols, bsize);
+    (void)take(B * xai_bs); // vmp_xai of the reference: not materialised (fused)
+    pgb_vec_znx_big acc_big = mkv(take(B * big_bs), n, 1, bsize);
+    const uint64_t brk_bytes = pgb_bytes_of_vmp_pmat(m, brk->rows, brk->cols_in, brk->cols_out, brk->size);
+    const uint64_t lwe_stride = n_lwe + 1;
 
+    // out.zero(); out[0] = X^b * LUT (algorithm.rs:317-320)
+    PGB_CHECK_CUDA(cudaMemset2DAsync(res->data, bt->stride_res, 0, n * cols * res->size * 8, B, m->stream));
+    {
+        const uint64_t mn = umin64(res->size, lut->size);
+        LimbSet R = {(char *)res->data, res->cols * n * 8, bt->stride_res};
+        LimbSet L = {(char *)lut->data, lut->cols * n * 8, 0};
+        PGB_TRY(znx_rotate(m, R, L, 0, (const long long *)lwe_2n, (uint32_t)lwe_stride, (uint32_t)mn, (uint32_t)B));
+    }
+    for (uint64_t blk = 0; blk + block_size <= n_lwe; blk += block_size) { // chunks_exact
+        pgb_batch btd = {B, acc_bs, bt->stride_res, 0};
+        for (uint64_t j = 0; j < cols; j++) PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &acc_dft, j, res, j, &btd));
+        PGB_CHECK_CUDA(cudaMemsetAsync(acc_add.data, 0, B * vres_bs, m->stream)); // vec_znx_dft_zero on every column
+        for (uint64_t t = 0; t < block_size; t++) {
+            pgb_vmp_pmat ski = *brk;
+            ski.data = (char *)brk->data + (blk + t) * brk_bytes;
+            pgb_batch btv = {B, vres_bs, acc_bs, 0};
+            PGB_TRY(vmp_apply_impl(m, &vmp_res, &acc_dft, &ski, 0, &btv));
+            XaiArgs xa = {(char *)acc_add.data, vres_bs, (const char *)vmp_res.data, vres_bs, (const char *)x_pow_a->data,
+                          (const long long *)lwe_2n + 1 + blk + t, lwe_stride, (uint32_t)n, (uint32_t)(cols * bsize)};
+            ProfScope _ps(m, PROF_ELEMENTWISE);
+            if (m->flavour == PGB_NTT120) {
+                dim3 grid(((uint32_t)n + 255) / 256, xa.polys, (uint32_t)B);
+                cggi_xai_ntt120_kernel<<<grid, 256, 0, m->stream>>>(xa);
+            } else {
+                dim3 grid(((uint32_t)(n / 2) + 255) / 256, xa.polys, (uint32_t)B);
+                cggi_xai_fft64_kernel<<<grid, 256, 0, m->stream>>>(xa);
+            }
+            PGB_CHECK_CUDA(cudaGetLastError());
+        }
+        for (uint64_t i = 0; i < cols; i++) { // algorithm.rs:361-365
+            pgb_batch bti = {B, big_bs, vres_bs, 0};
+            PGB_TRY(pgb_vec_znx_idft_apply_batched(m, &acc_big, 0, &acc_add, i, &bti));
+            pgb_batch bts = {B, big_bs, bt->stride_res, 0};
+            PGB_TRY(big_add_small_impl(m, &acc_big, 0, res, i, &bts));
+            pgb_batch btn = {B, bt->stride_res, big_bs, 0};
+            PGB_TRY(big_normalize_impl(m, res, base2k, 0, i, &acc_big, base2k, 0, 0, true, &btn));
+        }
+    }
+    return PGB_OK;
+}
 extern "C" int pgb_cggi_blind_rotate_batched(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2n, uint64_t n_lwe, const pgb_vec_znx *lut,
                                              const pgb_vmp_pmat *brk, const pgb_svp_ppol *x_pow_a, uint64_t block_size, uint64_t base2k,
                                              const pgb_batch *bt, void *scratch, size_t scratch_len) {
     return cggi_blind_rotate_impl(m, res, lwe_2n, n_lwe, lut, brk, x_pow_a, block_size, base2k, bt, scratch, scratch_len);
 }
 
-int cggi_blind_rotate_impl(pgb_module *, pgb_vec_znx *, const int64_t *, uint64_t, const pgb_vec_znx *, const pgb_vmp_pmat *,
-                           const pgb_svp_ppol *, uint64_t, uint64_t, const pgb_batch *, void *, size_t) {
-    pgb_set_error("cggi_blind_rotate: not implemented yet");
-    return PGB_ERR_UNSUPPORTED;
-}

@@ -55,6 +55,9 @@ struct pgb_module {
     cudaStream_t aux_stream[2]; // H2D / D2H staging streams of the host front ends
     cudaEvent_t ev[8];
     uint64_t launches;
+    // optional per-category kernel timing with CUDA events on the launching stream (pgb_profile_*)
+    bool prof_on;
+    struct ProfState *prof;
     // NTT120: twiddles (w, floor(w*2^32/q)) in block-twiddle (bit-reversed) order, [4][n] each direction
     uint2 *ntt_fwd, *ntt_inv;
     Ntt120Consts nc;
@@ -65,6 +68,16 @@ struct pgb_module {
     size_t ws_len;
     void *pinned[4];
     size_t pinned_len;
+};
+
+// kernel categories of the profiler
+enum { PROF_DFT_FWD = 0, PROF_DFT_INV = 1, PROF_VMP = 2, PROF_NORMALIZE = 3, PROF_ELEMENTWISE = 4, PROF_OTHER = 5, PROF_NCAT = 6 };
+void prof_begin(pgb_module *m, int cat);
+void prof_end(pgb_module *m);
+struct ProfScope {
+    pgb_module *m;
+    ProfScope(pgb_module *mm, int cat) : m(mm) { m->launches++; if (m->prof_on) prof_begin(m, cat); }
+    ~ProfScope() { if (m->prof_on) prof_end(m); }
 };
 
 // A strided set of limbs ("jobs"): job j of batch item b starts at base + b*batch_stride + j*limb_stride (bytes).

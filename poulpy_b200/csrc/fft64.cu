@@ -251,8 +251,9 @@ template <int L> static int flaunch_fwd(pgb_module *m, const FftJobs &jb) {
         attr_set = true;
     }
     int grid = (jb.total_jobs + LPC - 1) / LPC;
+    { ProfScope _ps(m, PROF_DFT_FWD);
     fft64_fwd_kernel<L, LPC><<<grid, G::T * LPC, smem, m->stream>>>(jb, m->fft_fwd);
-    m->launches++;
+    }
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;
 }
@@ -266,8 +267,9 @@ template <int L> static int flaunch_inv(pgb_module *m, const FftJobs &jb) {
         attr_set = true;
     }
     int grid = (jb.total_jobs + LPC - 1) / LPC;
+    { ProfScope _ps(m, PROF_DFT_INV);
     fft64_inv_kernel<L, LPC><<<grid, G::T * LPC, smem, m->stream>>>(jb, m->fft_inv, 1.0 / (double)(m->n / 2));
-    m->launches++;
+    }
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;
 }
@@ -350,8 +352,9 @@ int fft64_vmp(pgb_module *m, const char *a, uint64_t a_bs, char *res, uint64_t r
     FVmpArgs p = {a, a_bs, res, res_bs, pm, pm_bs, (uint32_t)(m->n / 4), row_max, C, col0, ncols_out};
     constexpr int CT = 4;
     dim3 block(128), grid((p.m2 + 127) / 128, (ncols_out + CT - 1) / CT, batch);
+    { ProfScope _ps(m, PROF_VMP);
     fft64_vmp_kernel<CT><<<grid, block, 0, m->stream>>>(p);
-    m->launches++;
+    }
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;
 }
@@ -388,6 +391,7 @@ template <int OP> __global__ void __launch_bounds__(256) fft64_ew_kernel(FEwArgs
 }
 int fft64_ew(pgb_module *m, int op, LimbSet dst, LimbSet a, LimbSet b, uint32_t jobs, uint32_t batch) {
     if (jobs == 0 || batch == 0) return PGB_OK;
+    ProfScope _ps(m, PROF_ELEMENTWISE);
     FEwArgs p = {dst, a, b, (uint32_t)(m->n / 2)};
     dim3 block(256), grid((p.m + 255) / 256, jobs, batch);
     switch (op) {
@@ -396,7 +400,6 @@ int fft64_ew(pgb_module *m, int op, LimbSet dst, LimbSet a, LimbSet b, uint32_t 
     case FEW_NEG: fft64_ew_kernel<FEW_NEG><<<grid, block, 0, m->stream>>>(p); break;
     default: fft64_ew_kernel<FEW_MUL><<<grid, block, 0, m->stream>>>(p); break;
     }
-    m->launches++;
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;
 }

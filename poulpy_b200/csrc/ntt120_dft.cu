@@ -357,8 +357,9 @@ template <int L> static int launch_fwd(pgb_module *m, const NttJobs &jb) {
         attr_set = true;
     }
     int grid = (jb.total_jobs + LPC - 1) / LPC;
+    { ProfScope _ps(m, PROF_DFT_FWD);
     ntt120_fwd_kernel<L, LPC><<<grid, G::T * LPC, smem, m->stream>>>(jb, m->ntt_fwd);
-    m->launches++;
+    }
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;
 }
@@ -372,8 +373,9 @@ template <int L> static int launch_inv(pgb_module *m, const NttJobs &jb) {
         attr_set = true;
     }
     int grid = (jb.total_jobs + LPC - 1) / LPC;
+    { ProfScope _ps(m, PROF_DFT_INV);
     ntt120_inv_kernel<L, LPC><<<grid, G::T * LPC, smem, m->stream>>>(jb, m->ntt_inv, m->nc);
-    m->launches++;
+    }
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;
 }

@@ -71,8 +71,9 @@ int ntt120_vmp(pgb_module *m, const char *a, uint64_t a_bs, char *res, uint64_t 
     dim3 block(256);
     constexpr int CT = 4;
     dim3 grid((words + 255) / 256, (ncols_out + CT - 1) / CT, batch);
+    { ProfScope _ps(m, PROF_VMP);
     ntt120_vmp_kernel<CT><<<grid, block, 0, m->stream>>>(p);
-    m->launches++;
+    }
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;
 }
@@ -117,6 +118,7 @@ template <int OP> __global__ void __launch_bounds__(256) ntt120_ew_kernel(EwArgs
 // op over `jobs` limbs per batch item; a/b may alias dst limb for limb (pure element-wise)
 int ntt120_ew(pgb_module *m, int op, LimbSet dst, LimbSet a, LimbSet b, uint32_t jobs, uint32_t batch) {
     if (jobs == 0 || batch == 0) return PGB_OK;
+    ProfScope _ps(m, PROF_ELEMENTWISE);
     EwArgs p = {dst, a, b, (uint32_t)(m->n / 4), jobs};
     dim3 block(256), grid(((uint32_t)m->n + 255) / 256, jobs, batch);
     switch (op) {
@@ -127,7 +129,6 @@ int ntt120_ew(pgb_module *m, int op, LimbSet dst, LimbSet a, LimbSet b, uint32_t
     case EW_ZERO: ntt120_ew_kernel<EW_ZERO><<<grid, block, 0, m->stream>>>(p); break;
     default: ntt120_ew_kernel<EW_MUL><<<grid, block, 0, m->stream>>>(p); break;
     }
-    m->launches++;
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;
 }

@@ -68,6 +68,9 @@ def lib():
         _lib.pgb_module_launch_count.argtypes = [C.c_void_p]
         _lib.pgb_module_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         _lib.pgb_module_sync.argtypes = [C.c_void_p]
+        _lib.pgb_profile_category_name.restype = C.c_char_p
+        _lib.pgb_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        _lib.pgb_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
         for name in ("pgb_glwe_keyswitch_tmp_bytes", "pgb_glwe_external_product_tmp_bytes", "pgb_cggi_blind_rotate_tmp_bytes",
                      "pgb_bytes_of_vmp_pmat", "pgb_size_of_scalar_prep", "pgb_size_of_scalar_big"):
             getattr(_lib, name).restype = C.c_size_t

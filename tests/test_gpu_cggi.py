@@ -1,0 +1,95 @@
+"""GPU parity of the batched CGGI blind rotation (block-binary) against the oracle, both flavours, bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import poulpy_b200 as pb
+from oracle import pyoracle as O
+from util import fill_uniform
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(n, fl, rank, dnum, brk_size, n_lwe, k, rng, trivial_secret=None):
+    g, o = pb.Module(n, fl), O.OracleModule(n, fl)
+    cols = rank + 1
+    per = n * dnum * cols * cols * brk_size * g.prep_bytes
+    gbuf = pb.DevBuf(per * n_lwe)
+    obrk = []
+    for i in range(n_lwe):
+        if trivial_secret is None:
+            mat = fill_uniform(rng, (dnum, cols, brk_size, cols, n), k)
+        else:
+            mat = np.zeros((dnum, cols, brk_size, cols, n), dtype=np.int64)
+            for d in range(dnum):
+                for c in range(cols):
+                    mat[d, c, d, c, 0] = trivial_secret[i]
+        pm = o.vmp_pmat_alloc(dnum, cols, cols, brk_size)
+        o.vmp_prepare(pm, mat)
+        obrk.append(pm)
+        gp = pb.hal.VmpPMat(gbuf, n, dnum, cols, cols, brk_size, offset=i * per)
+        g.vmp_prepare(gp, g.mat_znx_from_numpy(mat))
+    gbrk = pb.hal.VmpPMat(gbuf, n, dnum, cols, cols, brk_size)
+    return g, o, gbrk, obrk
+
+
+@pytest.mark.parametrize("fl", [pb.NTT120, pb.FFT64])
+@pytest.mark.parametrize("rank,dnum,size,brk_size", [(1, 1, 1, 2), (2, 2, 2, 3), (3, 1, 1, 2)])
+def test_blind_rotate_matches_oracle(fl, rank, dnum, size, brk_size):
+    n, k, n_lwe, block, batch = 128, 12, 12, 3, 5
+    rng = np.random.default_rng(100 * rank + dnum + fl)
+    g, o, gbrk, obrk = _setup(n, fl, rank, dnum, brk_size, n_lwe, k, rng)
+    xg, xo = g.cggi_x_pow_a(), o.cggi_x_pow_a()
+    lut = fill_uniform(rng, (size, 1, n), k)
+    lwe = rng.integers(-n, n, size=(batch, n_lwe + 1), dtype=np.int64)
+    want = np.zeros((batch, size, rank + 1, n), dtype=np.int64)
+    for b in range(batch):
+        o.cggi_blind_rotate_block_binary(want[b], lwe[b], lut, obrk, xo, block, k)
+    res = g.vec_znx_from_numpy(fill_uniform(rng, want.shape, k))  # garbage pre-fill
+    lwe_dev = pb.DevBuf(lwe.nbytes)
+    lwe_dev.upload(lwe)
+    g.cggi_blind_rotate(res, lwe_dev, n_lwe, g.vec_znx_from_numpy(lut), gbrk, xg, block, k)
+    g.sync()
+    assert np.array_equal(g.vec_znx_to_numpy(res), want)
+
+
+@pytest.mark.parametrize("fl", [pb.NTT120, pb.FFT64])
+def test_x_pow_a_table(fl):
+    n = 64
+    g, o = pb.Module(n, fl), O.OracleModule(n, fl)
+    xg, xo = g.cggi_x_pow_a(), o.cggi_x_pow_a()
+    if fl == pb.NTT120:
+        got = xg.buf.download(np.uint32, (2 * n, 4, n))
+        for k, q in enumerate(O.Q):
+            # the oracle's SvpPPol is q120c: (r, r * 2^32 mod q) packed in one u64 (reference/ntt120/types.rs:216)
+            assert np.array_equal(got[:, k, :].astype(np.uint64), xo[:, :, k] & np.uint64(0xFFFFFFFF))
+    else:
+        got = xg.buf.download(np.float64, (2 * n, n))
+        assert np.max(np.abs(got - xo)) < 1e-12
+
+
+@pytest.mark.parametrize("fl", [pb.NTT120, pb.FFT64])
+def test_blind_rotate_bench_shape_semantics(fl):
+    """BASELINE config 3 shape (n=512, rank=3, block=3, base2k=18, k_brk=36, dnum=1, k_glwe=18) with noiseless trivial keys and a
+    shortened LWE dimension: the result must be X^(b + <a, s>) * LUT exactly (L4-style functional check)."""
+    n, k, n_lwe, block, batch, rank = 512, 18, 24, 3, 7, 3
+    rng = np.random.default_rng(77 + fl)
+    s = np.zeros(n_lwe, dtype=np.int64)
+    for b0 in range(0, n_lwe, block):
+        s[b0 + rng.integers(0, block)] = rng.integers(0, 2)
+    g, o, gbrk, obrk = _setup(n, fl, rank, 1, 2, n_lwe, k, rng, trivial_secret=s)
+    xg = g.cggi_x_pow_a()
+    lut = fill_uniform(rng, (1, 1, n), k - 1)
+    lwe = rng.integers(-n, n, size=(batch, n_lwe + 1), dtype=np.int64)
+    res = g.vec_znx_alloc(rank + 1, 1, batch)
+    lwe_dev = pb.DevBuf(lwe.nbytes)
+    lwe_dev.upload(lwe)
+    g.cggi_blind_rotate(res, lwe_dev, n_lwe, g.vec_znx_from_numpy(lut), gbrk, xg, block, k)
+    g.sync()
+    got = g.vec_znx_to_numpy(res)
+    for b in range(batch):
+        shift = int(lwe[b, 0] + np.dot(lwe[b, 1:], s))
+        want = np.zeros((1, rank + 1, n), dtype=np.int64)
+        O.vec_znx_rotate(shift, want, 0, lut, 0)
+        assert np.array_equal(got[b], want), b

@@ -1,0 +1,146 @@
+"""CPU checks that pin the oracle's restatement of the compositions (no GPU).
+
+* FFT64-oracle == NTT120-oracle on normalised outputs for vmp / svp / key-switch / external product / blind rotation:
+  the reference's cross-backend procedure (poulpy-cpu-ref/src/tests.rs:47-141) applied to the two oracle flavours.
+* Semantic (decrypt-free) check of CGGI blind rotation with noiseless "trivial" GGSW keys: the accumulator must end as
+  X^(b + sum a_i s_i) * LUT (poulpy-bin-fhe/src/blind_rotation/tests/generic_blind_rotation.rs:162-172 checks the same
+  thing after decryption).
+"""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from util import fill_uniform, negacyclic_mul
+
+
+def _both(n):
+    return O.OracleModule(n, O.NTT120), O.OracleModule(n, O.FFT64)
+
+
+@pytest.mark.parametrize("cols_in,cols_out,size_in,size_out", [(1, 1, 1, 1), (1, 2, 3, 4), (2, 1, 4, 2), (2, 2, 3, 3)])
+def test_cross_backend_vmp(cols_in, cols_out, size_in, size_out):
+    n, k = 64, 12
+    rng = np.random.default_rng(1)
+    a = fill_uniform(rng, (size_in, cols_in, n), k)
+    mat = fill_uniform(rng, (size_in, cols_in, size_out, cols_out, n), k)
+    outs = []
+    for m in _both(n):
+        ad = m.vec_znx_dft_alloc(cols_in, size_in)
+        for c in range(cols_in):
+            m.vec_znx_dft_apply(1, 0, ad, c, a, c)
+        pm = m.vmp_pmat_alloc(size_in, cols_in, cols_out, size_out)
+        m.vmp_prepare(pm, mat)
+        per_off = []
+        for off in range(size_out):
+            rd = m.vec_znx_dft_alloc(cols_out, size_out)
+            m.vmp_apply_dft_to_dft(rd, ad, pm, off)
+            big = m.vec_znx_idft_apply_consume(rd)
+            out = m.vec_znx_alloc(cols_out, size_out)
+            for c in range(cols_out):
+                m.vec_znx_big_normalize(out, k, 0, c, big, k, c)
+            per_off.append(out)
+        outs.append(per_off)
+    for x, y in zip(*outs):
+        assert np.array_equal(x, y)
+    # and against the schoolbook definition for limb_offset = 0, first output poly
+    want = [0] * n
+    for r in range(size_in * cols_in):
+        limb, col = divmod(r, cols_in)
+        prod = negacyclic_mul(a[limb, col], mat[limb, col, 0, 0])
+        want = [x + y for x, y in zip(want, prod)]
+    m = O.OracleModule(n, O.NTT120)
+    ad = m.vec_znx_dft_alloc(cols_in, size_in)
+    for c in range(cols_in):
+        m.vec_znx_dft_apply(1, 0, ad, c, a, c)
+    pm = m.vmp_pmat_alloc(size_in, cols_in, cols_out, size_out)
+    m.vmp_prepare(pm, mat)
+    rd = m.vec_znx_dft_alloc(cols_out, size_out)
+    m.vmp_apply_dft_to_dft(rd, ad, pm, 0)
+    big = m.vec_znx_idft_apply_consume(rd)
+    assert list(O.i128_to_int(big[0, 0])) == want
+
+
+@pytest.mark.parametrize("dsize", [1, 2])
+def test_cross_backend_keyswitch_and_external_product(dsize):
+    """dsize >= 3 is excluded on purpose: there the two reference backends themselves disagree.  FFT64's vmp with a
+    limb_offset leaves the polys [col_max - off, col_max) of its output untouched (reference/fft64/vmp.rs:263 zeroes
+    res[col_max..] only) so the dsize loop of keyswitching/glwe.rs:346-376 folds stale limbs of the previous digit into
+    res, while NTT120 zeroes them (reference/ntt120/vmp.rs:282-287).  Each GPU flavour is checked against its own oracle
+    flavour (tests/test_gpu_core.py), which restates exactly that behaviour."""
+    n, k = 64, 12
+    rng = np.random.default_rng(2 + dsize)
+    a_size, key_size, res_size = 4, 5, 3
+    dnum = -(-a_size // dsize)
+    for rank in (1, 2):
+        a = fill_uniform(rng, (a_size, rank + 1, n), k)
+        ksk = fill_uniform(rng, (dnum, rank, key_size, rank + 1, n), k)
+        ggsw = fill_uniform(rng, (dnum, rank + 1, key_size, rank + 1, n), k)
+        res = []
+        for m in _both(n):
+            pk = m.vmp_pmat_alloc(dnum, rank, rank + 1, key_size)
+            m.vmp_prepare(pk, ksk)
+            pg = m.vmp_pmat_alloc(dnum, rank + 1, rank + 1, key_size)
+            m.vmp_prepare(pg, ggsw)
+            r1 = m.vec_znx_alloc(rank + 1, res_size)
+            m.glwe_keyswitch(r1, k, a, k, pk, k, dsize)
+            r2 = m.vec_znx_alloc(rank + 1, res_size)
+            m.glwe_external_product(r2, k, a, k, pg, k, dsize)
+            r3 = m.vec_znx_alloc(rank + 1, res_size)
+            m.glwe_keyswitch(r3, k - 2, a, k - 1, pk, k, dsize)  # mixed base2k (glwe_ct.rs:34-36)
+            res.append((r1, r2, r3))
+        for x, y in zip(*res):
+            assert np.array_equal(x, y)
+
+
+def _trivial_ggsw(n, rank, dnum, size, s):
+    """Noiseless GGSW 'encryption' of the scalar s: row (d, i) holds s at limb d, column i, coefficient 0."""
+    mat = np.zeros((dnum, rank + 1, size, rank + 1, n), dtype=np.int64)
+    for d in range(dnum):
+        for i in range(rank + 1):
+            mat[d, i, d, i, 0] = s
+    return mat
+
+
+@pytest.mark.parametrize("flavour", [O.NTT120, O.FFT64])
+@pytest.mark.parametrize("rank", [1, 2])
+def test_blind_rotation_semantics_trivial_keys(flavour, rank):
+    n, k, n_lwe, block = 64, 12, 12, 3
+    size, dnum, brk_size = 2, 2, 2
+    rng = np.random.default_rng(5 + rank)
+    m = O.OracleModule(n, flavour)
+    # block-binary secret: at most one 1 per block
+    s = np.zeros(n_lwe, dtype=np.int64)
+    for b0 in range(0, n_lwe, block):
+        if rng.integers(0, 2):
+            s[b0 + rng.integers(0, block)] = 1
+    brk = []
+    for i in range(n_lwe):
+        pm = m.vmp_pmat_alloc(dnum, rank + 1, rank + 1, brk_size)
+        m.vmp_prepare(pm, _trivial_ggsw(n, rank, dnum, brk_size, int(s[i])))
+        brk.append(pm)
+    xpa = m.cggi_x_pow_a()
+    lut = fill_uniform(rng, (size, 1, n), k - 1)
+    lwe_2n = rng.integers(-n, n, size=n_lwe + 1, dtype=np.int64)
+    res = fill_uniform(rng, (size, rank + 1, n), k)  # garbage: must be overwritten
+    m.cggi_blind_rotate_block_binary(res, lwe_2n, lut, brk, xpa, block, k)
+    shift = int(lwe_2n[0] + np.dot(lwe_2n[1:], s))
+    want = np.zeros_like(res)
+    O.vec_znx_rotate(shift, want, 0, lut, 0)
+    assert np.array_equal(res, want)
+
+
+def test_mod_switch_2n():
+    """algorithms/mod.rs:136-181: base2k > log2(2N)+1 path rounds to [-N, N); the multi-limb path concatenates limbs."""
+    rng = np.random.default_rng(9)
+    n_lwe, base2k, two_n = 10, 18, 1024
+    lwe = fill_uniform(rng, (1, 1, n_lwe + 1), base2k)
+    got = O.mod_switch_2n(two_n, lwe, base2k, rot_left=True)
+    d = base2k - 10
+    want = ((-lwe[0, 0]) + (1 << (d - 1))) >> d
+    assert np.array_equal(got, want)
+    lwe2 = fill_uniform(rng, (3, 1, n_lwe + 1), 5)
+    got2 = O.mod_switch_2n(two_n, lwe2, 5, rot_left=False)
+    # log2n = 11: size = 3 limbs, rem = 5 - 1 = 4 -> last limb contributes its top bit
+    want2 = ((lwe2[0, 0] << 5) + lwe2[1, 0])
+    want2 = (want2 << 1) + (lwe2[2, 0] >> 4)
+    assert np.array_equal(got2, want2)
