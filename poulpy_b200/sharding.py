@@ -1,0 +1,41 @@
+"""Batch sharding across the GPUs of one box: independent ciphertexts, contiguous split, prepared keys
+replicated once per GPU, no per-operation collective.  `torch.distributed` is only plumbing (barrier, max over ranks)."""
+from __future__ import annotations
+
+
+def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous [start, stop) of `total` items owned by `rank`; the first `total % world` ranks get one extra item."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} out of range for world size {world}")
+    base, extra = divmod(total, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """Max of a per-rank scalar (device time) over the process group; identity without a group."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def gather_shards(local, total: int):
+    """All-gather variable-length shards (numpy arrays split along axis 0) back into one array on every rank; used only when a
+    caller wants the results collocated -- the hot path itself never communicates."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return local
+    world = dist.get_world_size()
+    outs = [None] * world
+    dist.all_gather_object(outs, local)
+    res = np.concatenate(outs, axis=0)
+    assert res.shape[0] == total
+    return res
