@@ -57,8 +57,8 @@ struct XaiArgs {
 __global__ void __launch_bounds__(256) cggi_xai_ntt120_kernel(XaiArgs p) {
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; // uint4 index inside a poly
     if (u >= p.n) return;
-    const int k = u / (p.n / 4);
-    const uint32_t q = n120::qk(k);
+    const n120::PrimeRt pr(u / (p.n / 4));
+    const uint32_t q = pr.q;
     const uint32_t b = blockIdx.z, poly = blockIdx.y;
     const long long ai = p.lwe[(size_t)b * p.lwe_stride];
     const uint32_t pos = (uint32_t)((ai + (long long)(2 * p.n)) & (long long)(2 * p.n - 1));
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) cggi_xai_ntt120_kernel(XaiArgs p) {
     uint4 *ap = reinterpret_cast<uint4 *>(p.acc + (size_t)b * p.acc_bs + (size_t)poly * p.n * 16) + u;
     const uint4 a = *ap;
     auto f = [&](uint32_t acc, uint32_t ww, uint32_t vv) {
-        uint32_t pv = n120::red64k((unsigned long long)ww * vv, k);
+        uint32_t pv = pr.reduce((unsigned long long)ww * vv);
         uint32_t t = n120::csub(acc + pv, q);
         return t >= vv ? t - vv : t - vv + q;
     };

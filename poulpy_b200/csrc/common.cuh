@@ -68,6 +68,9 @@ struct pgb_module {
     size_t ws_len;
     void *pinned[4];
     size_t pinned_len;
+    // L2-resident carry scratch of the fused normalising kernels (16 B per coefficient per resident CTA)
+    void *carry_ws;
+    size_t carry_len;
 };
 
 // kernel categories of the profiler

@@ -4,6 +4,8 @@
 // The call sequences restate poulpy-core/src/keyswitching/glwe.rs:53-109, :207-239, :298-380 and
 // poulpy-core/src/external_product/glwe.rs:99-141, :197-271; every step runs over the whole batch on the module's
 // stream with no host round trip in between.
+#include <stdlib.h>
+
 #include "internal.h"
 
 static const uint64_t ALIGN = 256;
@@ -100,7 +102,6 @@ extern "C" int pgb_glwe_keyswitch_batched(pgb_module *m, pgb_vec_znx *res, uint6
     // (:89-90) res_dft = take_vec_znx_dft(rank_out + 1, key.size()); zero
     const uint64_t res_dft_bs = n * cols_out * key->size * pb;
     pgb_vec_znx_dft res_dft = mk(ar.take(B * res_dft_bs), n, cols_out, key->size);
-    PGB_CHECK_CUDA(cudaMemsetAsync(res_dft.data, 0, B * res_dft_bs, m->stream));
     // (:92-100) cross-base2k input conversion
     pgb_vec_znx ain = *a;
     uint64_t ain_bs = bt->stride_a;
@@ -117,6 +118,13 @@ extern "C" int pgb_glwe_keyswitch_batched(pgb_module *m, pgb_vec_znx *res, uint6
     pgb_vec_znx_dft a_dft = mk(ar.take(B * a_dft_bs), n, rank_in, ain.size);
     pgb_batch btd = {B, a_dft_bs, ain_bs, 0};
     for (uint64_t c = 0; c < rank_in; c++) PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &a_dft, c, &ain, c + 1, &btd));
+    if (dsize == 1 && res_base2k == key_base2k && ntt120_fused_supported(m) && !getenv("PGB_NO_FUSION")) {
+        // fused back end: vmp -> idft -> CRT -> add_small -> normalize per (ciphertext, column), nothing but a_dft touches HBM
+        const uint64_t R = umin64(key->rows * key->cols_in, rank_in * ain.size);
+        return ntt120_fused_back(m, (const char *)a_dft.data, a_dft_bs, (const char *)key->data, (int)R, (int)(cols_out * key->size),
+                                 (int)cols_out, (const char *)ain.data, ain_bs, ain.cols * n * 8, (int)umin64(ain.size, key->size),
+                                 (char *)res->data, bt->stride_res, res->cols * n * 8, (int)res->size, (int)key_base2k, 0, (int)B);
+    }
     pgb_vec_znx_dft ai = a_dft, tmp = res_dft;
     uint64_t ai_bs = 0, tmp_bs = 0;
     if (dsize > 1) {
@@ -129,6 +137,7 @@ extern "C" int pgb_glwe_keyswitch_batched(pgb_module *m, pgb_vec_znx *res, uint6
         PGB_CHECK_CUDA(cudaMemsetAsync(ai.data, 0, B * ai_bs, m->stream));   // ai_dft.zero()       (:337)
         PGB_CHECK_CUDA(cudaMemsetAsync(tmp.data, 0, B * tmp_bs, m->stream)); // res_dft_tmp.zero()  (:342)
     }
+    PGB_CHECK_CUDA(cudaMemsetAsync(res_dft.data, 0, B * res_dft_bs, m->stream)); // res_dft.zero() (:90)
     PGB_TRY(gadget_product(m, &res_dft, &a_dft, key, dsize, true, &ai, &tmp, res_dft_bs, a_dft_bs, ai_bs, tmp_bs, B));
     pgb_batch btc = {B, res_dft_bs, 0, 0};
     PGB_TRY(pgb_vec_znx_idft_apply_consume_batched(m, &res_dft, &btc));
@@ -174,7 +183,6 @@ extern "C" int pgb_glwe_external_product_batched(pgb_module *m, pgb_vec_znx *res
     Arena ar = {(char *)scratch, scratch_len, 0};
     const uint64_t res_dft_bs = n * cols * ggsw->size * pb;
     pgb_vec_znx_dft res_dft = mk(ar.take(B * res_dft_bs), n, cols, ggsw->size);
-    PGB_CHECK_CUDA(cudaMemsetAsync(res_dft.data, 0, B * res_dft_bs, m->stream)); // res_dft.zero() (:123)
     pgb_vec_znx ain = *a;
     uint64_t ain_bs = bt->stride_a;
     if (a_base2k != ggsw_base2k) {
@@ -193,9 +201,17 @@ extern "C" int pgb_glwe_external_product_batched(pgb_module *m, pgb_vec_znx *res
     if (dsize == 1) {
         pgb_batch btd = {B, a_dft_bs, ain_bs, 0};
         for (uint64_t j = 0; j < cols; j++) PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &a_dft, j, &ain, j, &btd));
+        if (res_base2k == ggsw_base2k && ntt120_fused_supported(m) && !getenv("PGB_NO_FUSION")) {
+            const uint64_t R = umin64(ggsw->rows * ggsw->cols_in, cols * a_size);
+            return ntt120_fused_back(m, (const char *)a_dft.data, a_dft_bs, (const char *)ggsw->data, (int)R, (int)(cols * ggsw->size),
+                                     (int)cols, nullptr, 0, 0, 0, (char *)res->data, bt->stride_res, res->cols * n * 8, (int)res->size,
+                                     (int)ggsw_base2k, 0, (int)B);
+        }
+        PGB_CHECK_CUDA(cudaMemsetAsync(res_dft.data, 0, B * res_dft_bs, m->stream)); // res_dft.zero() (:123)
         pgb_batch btv = {B, res_dft_bs, a_dft_bs, 0};
         PGB_TRY(vmp_apply_impl(m, &res_dft, &a_dft, ggsw, 0, &btv));
     } else {
+        PGB_CHECK_CUDA(cudaMemsetAsync(res_dft.data, 0, B * res_dft_bs, m->stream)); // res_dft.zero() (:123)
         pgb_vec_znx_dft tmp = mk(ar.take(B * res_dft_bs), n, cols, ggsw->size);
         PGB_REQUIRE(tmp.data, "glwe_external_product: scratch exhausted");
         // a_dft.data_mut().fill(0) (:226): FFT64 dft_apply leaves limbs past a.size untouched inside min_steps

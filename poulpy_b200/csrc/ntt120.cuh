@@ -45,13 +45,17 @@ __device__ __forceinline__ void gs_bf(uint32_t &x, uint32_t &y, uint2 w, uint32_
     y = mul_shoup(d, w.x, w.y, q);
 }
 
-// i64 -> canonical residue mod q (exact for the full i64 range, like arithmetic.rs:39-60 followed by % q)
+// i64 -> residue mod q in [0, 3q) (exact for the full i64 range, like arithmetic.rs:39-60 followed by % q; the lazy
+// butterflies accept [0, 4q)).  x = uh * 2^32 + ul - [x < 0] * 2^64 with uh, ul the unsigned halves:
+//   uh * (2^32 mod q) by Shoup -> [0, 2q);  ul - (ul >> 30) * q -> [0, 2q);  correction q - (2^64 mod q) for negatives.
 template <int K> __device__ __forceinline__ uint32_t from_i64(long long v) {
     constexpr uint32_t q = Prime<K>::q;
-    constexpr uint32_t two63 = (uint32_t)((1ull << 63) % q);
-    unsigned long long u = (unsigned long long)v;
-    uint32_t r = (uint32_t)((u & 0x7FFFFFFFFFFFFFFFull) % q);
-    if (v < 0) r = csub(r + (q - two63), q);
+    constexpr uint32_t c32 = (uint32_t)((1ull << 32) % q);
+    constexpr uint32_t c32s = (uint32_t)(((unsigned long long)c32 << 32) / q);
+    constexpr uint32_t c64 = (uint32_t)(((unsigned long long)c32 * c32) % q);
+    const uint32_t uh = (uint32_t)((unsigned long long)v >> 32), ul = (uint32_t)v;
+    uint32_t r = csub(mul_shoup(uh, c32, c32s, q) + (ul - (ul >> 30) * q), 2 * q); // [0, 2q)
+    if (v < 0) r += q - c64;                                                        // [0, 3q)
     return r;
 }
 
@@ -59,6 +63,21 @@ template <int K> __device__ __forceinline__ uint32_t from_i64(long long v) {
 template <int K> __device__ __forceinline__ uint32_t red64(unsigned long long x) {
     return (uint32_t)(x % Prime<K>::q);
 }
+// runtime-prime variants: per-thread constants selected once from k
+__host__ __device__ __forceinline__ constexpr uint32_t c32k(int k) { return (uint32_t)((1ull << 32) % qk(k)); }
+__host__ __device__ __forceinline__ constexpr uint32_t c32sk(int k) { return (uint32_t)(((unsigned long long)c32k(k) << 32) / qk(k)); }
+struct PrimeRt {
+    uint32_t q, c32, c32s;
+    __device__ __forceinline__ explicit PrimeRt(int k)
+        : q(k == 0 ? qk(0) : k == 1 ? qk(1) : k == 2 ? qk(2) : qk(3)),
+          c32(k == 0 ? c32k(0) : k == 1 ? c32k(1) : k == 2 ? c32k(2) : c32k(3)),
+          c32s(k == 0 ? c32sk(0) : k == 1 ? c32sk(1) : k == 2 ? c32sk(2) : c32sk(3)) {}
+    // any u64 -> canonical residue: hi * (2^32 mod q) by Shoup + folded low word, then two conditional subtractions
+    __device__ __forceinline__ uint32_t reduce(unsigned long long x) const {
+        const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
+        return csub(csub(mul_shoup(hi, c32, c32s, q) + (lo - (lo >> 30) * q), 2 * q), q);
+    }
+};
 __device__ __forceinline__ uint32_t red64k(unsigned long long x, int k) {
     switch (k) {
     case 0: return red64<0>(x);

@@ -9,6 +9,8 @@
 // (forward) / Gentleman-Sande form (inverse), Shoup multiplication with Harvey lazy reduction.  Global loads and
 // stores are fused into the first / last pass and are fully coalesced (i64 in: 8 B/thread contiguous per warp;
 // planes out: 32 B/thread; i128 out: 16 B/thread contiguous per warp).
+#include <stdlib.h>
+
 #include "internal.h"
 #include "ntt120.cuh"
 
@@ -33,31 +35,33 @@ template <int K, int NLEV> __device__ __forceinline__ void ct_radix8(uint32_t (&
         for (int j = 0; j < 4; j++) ct_bf(x[j], x[j + 4], w, q);
     }
     if (NLEV >= 2) {
-        uint2 w0 = __ldg(tw + 2 * hi), w1 = __ldg(tw + 2 * hi + 1);
+        const uint4 ww = __ldg(reinterpret_cast<const uint4 *>(tw + 2 * hi));
+        const uint2 w0 = make_uint2(ww.x, ww.y), w1 = make_uint2(ww.z, ww.w);
         ct_bf(x[0], x[2], w0, q);
         ct_bf(x[1], x[3], w0, q);
         ct_bf(x[4], x[6], w1, q);
         ct_bf(x[5], x[7], w1, q);
     }
     if (NLEV >= 3) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint2 w = __ldg(tw + 4 * hi + j);
-            ct_bf(x[2 * j], x[2 * j + 1], w, q);
-        }
+        const uint4 wa = __ldg(reinterpret_cast<const uint4 *>(tw + 4 * hi)), wb = __ldg(reinterpret_cast<const uint4 *>(tw + 4 * hi + 2));
+        ct_bf(x[0], x[1], make_uint2(wa.x, wa.y), q);
+        ct_bf(x[2], x[3], make_uint2(wa.z, wa.w), q);
+        ct_bf(x[4], x[5], make_uint2(wb.x, wb.y), q);
+        ct_bf(x[6], x[7], make_uint2(wb.z, wb.w), q);
     }
 }
 template <int K, int NLEV> __device__ __forceinline__ void gs_radix8(uint32_t (&x)[8], const uint2 *__restrict__ tw, uint32_t hi) {
     constexpr uint32_t q = Prime<K>::q;
     if (NLEV >= 3) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint2 w = __ldg(tw + 4 * hi + j);
-            gs_bf(x[2 * j], x[2 * j + 1], w, q);
-        }
+        const uint4 wa = __ldg(reinterpret_cast<const uint4 *>(tw + 4 * hi)), wb = __ldg(reinterpret_cast<const uint4 *>(tw + 4 * hi + 2));
+        gs_bf(x[0], x[1], make_uint2(wa.x, wa.y), q);
+        gs_bf(x[2], x[3], make_uint2(wa.z, wa.w), q);
+        gs_bf(x[4], x[5], make_uint2(wb.x, wb.y), q);
+        gs_bf(x[6], x[7], make_uint2(wb.z, wb.w), q);
     }
     if (NLEV >= 2) {
-        uint2 w0 = __ldg(tw + 2 * hi), w1 = __ldg(tw + 2 * hi + 1);
+        const uint4 ww = __ldg(reinterpret_cast<const uint4 *>(tw + 2 * hi));
+        const uint2 w0 = make_uint2(ww.x, ww.y), w1 = make_uint2(ww.z, ww.w);
         gs_bf(x[0], x[2], w0, q);
         gs_bf(x[1], x[3], w0, q);
         gs_bf(x[4], x[6], w1, q);
@@ -170,11 +174,19 @@ template <int L, int LPC> __global__ void __launch_bounds__(Geo<L>::T *LPC) ntt1
 }
 
 // ---------------------------------------------------------------------------------------------- inverse
-// bottom pass: levels L-3..L-1, inputs read from global planes (8 consecutive residues per thread)
-template <int K, int L> __device__ __forceinline__ void inv_bottom(uint32_t *__restrict__ plane, const uint32_t *__restrict__ gin,
-                                                                  const uint2 *__restrict__ tw, int t, bool active) {
+// bottom pass: levels L-3..L-1 on 8 consecutive residues per thread, results to shared memory
+template <int K, int L> __device__ __forceinline__ void inv_bottom_core(uint32_t (&x)[8], uint32_t *__restrict__ plane,
+                                                                       const uint2 *__restrict__ tw, int t) {
     constexpr int L0 = L - 3;
     const uint32_t hi = (1u << L0) | (uint32_t)t;
+    gs_radix8<K, 3>(x, tw, hi);
+    uint4 *o = reinterpret_cast<uint4 *>(plane + PAD(8 * t));
+    o[0] = make_uint4(x[0], x[1], x[2], x[3]);
+    o[1] = make_uint4(x[4], x[5], x[6], x[7]);
+}
+// inputs read from global planes
+template <int K, int L> __device__ __forceinline__ void inv_bottom(uint32_t *__restrict__ plane, const uint32_t *__restrict__ gin,
+                                                                  const uint2 *__restrict__ tw, int t, bool active) {
     uint32_t x[8];
     uint4 u0 = make_uint4(0, 0, 0, 0), u1 = u0;
     if (active) {
@@ -184,10 +196,7 @@ template <int K, int L> __device__ __forceinline__ void inv_bottom(uint32_t *__r
     }
     x[0] = u0.x; x[1] = u0.y; x[2] = u0.z; x[3] = u0.w;
     x[4] = u1.x; x[5] = u1.y; x[6] = u1.z; x[7] = u1.w;
-    gs_radix8<K, 3>(x, tw, hi);
-    uint4 *o = reinterpret_cast<uint4 *>(plane + PAD(8 * t));
-    o[0] = make_uint4(x[0], x[1], x[2], x[3]);
-    o[1] = make_uint4(x[4], x[5], x[6], x[7]);
+    inv_bottom_core<K, L>(x, plane, tw, t);
 }
 template <int K, int L, int L0> __device__ __forceinline__ void inv_mid(uint32_t *__restrict__ plane, const uint2 *__restrict__ tw, int t) {
     constexpr int SL = L - L0 - 3;
@@ -283,6 +292,195 @@ template <int L, int LPC> __global__ void __launch_bounds__(Geo<L>::T *LPC) ntt1
     if (active) {
 #pragma unroll
         for (int jj = 0; jj < 8; jj++) gout[t + jj * G::T] = crt_finish(acc[jj]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- fused back end
+// One CTA per (ciphertext, output column): for every limb from the least significant one
+//     vmp on the fly (sum_r a[r] * M[r][c], loaded straight into the bottom pass)  ->  inverse NTT  ->  CRT
+//     -> (+ small, the body column of the key-switch input)  ->  base-2^K carry step with the carry kept in registers
+// so that res_dft / res_big / add_small / normalize never touch HBM.  Restates, per coefficient and limb by limb, the sequence
+// vmp_apply_dft_to_dft + vec_znx_idft_apply_consume + vec_znx_big_add_small_assign + vec_znx_big_normalize of
+// poulpy-core/src/keyswitching/glwe.rs:229-237,106-108 and external_product/glwe.rs:231-234,270,138-140 (same-base2k path of
+// poulpy-cpu-ref/src/reference/ntt120/vec_znx_big.rs:367-446).
+struct FusedArgs {
+    const char *a_dft;  uint64_t a_bs;      // R polys (16n B each) per ciphertext
+    const char *pmat;                        // [R][C] polys
+    const char *small;  uint64_t small_bs;  uint64_t small_limb_stride; int small_size; // i64 limbs added to column 0 (or null)
+    char *res;          uint64_t res_bs;    uint64_t res_limb_stride;                    // i64 output, column c at + c*n*8
+    int R, C, cols_out;
+    // same-base2k normalisation plan (big = C / cols_out limbs)
+    int K, lsh, res_size, a_size, a_start, a_end, res_start, res_end;
+};
+
+__device__ __forceinline__ i128 nd_get_digit(int k, i128 x) { return (i128)((u128)x << (128 - k)) >> (128 - k); }
+__device__ __forceinline__ i128 nd_get_carry(int k, i128 x, i128 d) { return (i128)((u128)x - (u128)d) >> k; }
+
+// x[i] = sum_r a[r][8t+i] * m[r][8t+i] mod q, in [0, 2q)
+template <int K> __device__ __forceinline__ void vmp_rows8(uint32_t (&x)[8], const uint32_t *__restrict__ a, size_t a_stride,
+                                                           const uint32_t *__restrict__ mm, size_t m_stride, int R) {
+    constexpr uint32_t q = Prime<K>::q;
+    constexpr uint32_t c32 = (uint32_t)((1ull << 32) % q);
+    constexpr uint32_t c32s = (uint32_t)(((unsigned long long)c32 << 32) / q);
+    unsigned long long acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0;
+    if (R == 3) { // the key-switch bench shape: all 12 loads in flight before the first MAC
+        uint4 a0[3], a1[3], m0[3], m1[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const uint4 *pa = reinterpret_cast<const uint4 *>(a + (size_t)r * a_stride);
+            const uint4 *pm = reinterpret_cast<const uint4 *>(mm + (size_t)r * m_stride);
+            a0[r] = __ldg(pa); a1[r] = __ldg(pa + 1); m0[r] = __ldg(pm); m1[r] = __ldg(pm + 1);
+        }
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            acc[0] += (unsigned long long)a0[r].x * m0[r].x; acc[1] += (unsigned long long)a0[r].y * m0[r].y;
+            acc[2] += (unsigned long long)a0[r].z * m0[r].z; acc[3] += (unsigned long long)a0[r].w * m0[r].w;
+            acc[4] += (unsigned long long)a1[r].x * m1[r].x; acc[5] += (unsigned long long)a1[r].y * m1[r].y;
+            acc[6] += (unsigned long long)a1[r].z * m1[r].z; acc[7] += (unsigned long long)a1[r].w * m1[r].w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t hi = (uint32_t)(acc[i] >> 32), lo = (uint32_t)acc[i];
+            acc[i] = csub(mul_shoup(hi, c32, c32s, q) + (lo - (lo >> 30) * q), 2 * q);
+        }
+    } else
+    for (int r0 = 0; r0 < R; r0 += 16) {
+        const int r1 = min(r0 + 16, R);
+#pragma unroll 2
+        for (int r = r0; r < r1; r++) {
+            const uint4 *pa = reinterpret_cast<const uint4 *>(a + (size_t)r * a_stride);
+            const uint4 *pm = reinterpret_cast<const uint4 *>(mm + (size_t)r * m_stride);
+            const uint4 a0 = __ldg(pa), a1 = __ldg(pa + 1), m0 = __ldg(pm), m1 = __ldg(pm + 1);
+            acc[0] += (unsigned long long)a0.x * m0.x; acc[1] += (unsigned long long)a0.y * m0.y;
+            acc[2] += (unsigned long long)a0.z * m0.z; acc[3] += (unsigned long long)a0.w * m0.w;
+            acc[4] += (unsigned long long)a1.x * m1.x; acc[5] += (unsigned long long)a1.y * m1.y;
+            acc[6] += (unsigned long long)a1.z * m1.z; acc[7] += (unsigned long long)a1.w * m1.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t hi = (uint32_t)(acc[i] >> 32), lo = (uint32_t)acc[i];
+            const uint32_t r = csub(mul_shoup(hi, c32, c32s, q) + (lo - (lo >> 30) * q), 2 * q);
+            acc[i] = r;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = (uint32_t)acc[i];
+}
+
+template <int K, int L> __device__ __forceinline__ void fused_bottom(uint32_t *__restrict__ plane, const uint32_t *__restrict__ a,
+                                                                    size_t a_stride, const uint32_t *__restrict__ mm, size_t m_stride,
+                                                                    int R, const uint2 *__restrict__ tw, int t) {
+    uint32_t x[8];
+    vmp_rows8<K>(x, a + 8 * t, a_stride, mm + 8 * t, m_stride, R);
+    inv_bottom_core<K, L>(x, plane, tw, t);
+}
+
+// top pass of the fused kernel for one prime: R0 levels, scale by CRT_k / n, leave the canonical residue in the plane
+template <int K, int L> __device__ __forceinline__ void fused_top(uint32_t *__restrict__ plane, const uint2 *__restrict__ tw, int t,
+                                                                 const Ntt120Consts &nc) {
+    typedef Geo<L> G;
+    constexpr uint32_t q = Prime<K>::q;
+    uint32_t x[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) x[j] = plane[PAD(t + j * G::T)];
+    gs_radix8<K, G::R0>(x, tw, 1u);
+#pragma unroll
+    for (int j = 0; j < 8; j++) plane[PAD(t + j * G::T)] = csub(mul_shoup(x[j], nc.crt_ninv[K], nc.crt_ninv_sh[K], q), q);
+}
+
+// Persistent CTAs (two per SM): each loops over (ciphertext, column) work items; the per-coefficient i128 carries of the
+// normalisation live in a small L2-resident scratch indexed by CTA (16 B per coefficient), so the kernel fits in 64 registers.
+template <int L> __global__ void __launch_bounds__(Geo<L>::T, 2) ntt120_fused_back_kernel(FusedArgs p, const uint2 *__restrict__ tw,
+                                                                                         Ntt120Consts nc, int total_work,
+                                                                                         i128 *__restrict__ carry_scratch) {
+    typedef Geo<L> G;
+    static_assert(L > G::R0, "fused path needs at least two passes");
+    extern __shared__ __align__(16) uint32_t smem[];
+    constexpr int n = G::NB;
+    const int t = threadIdx.x;
+    const uint32_t *pm = reinterpret_cast<const uint32_t *>(p.pmat);
+    const size_t poly = (size_t)4 * n; // u32 words per poly
+    const size_t res_ls = p.res_limb_stride / 8, small_ls = p.small_limb_stride / 8;
+    const int K = p.K, lsh = p.lsh, w = lsh == 0 ? K : K - lsh;
+    i128 *carry = carry_scratch + (size_t)blockIdx.x * n;
+    const size_t m_stride = (size_t)p.C * poly;
+    const u128 M0 = ((u128)c_crt.m_hi[0] << 64) | c_crt.m_lo[0], M1 = ((u128)c_crt.m_hi[1] << 64) | c_crt.m_lo[1];
+    const u128 M2 = ((u128)c_crt.m_hi[2] << 64) | c_crt.m_lo[2], M3 = ((u128)c_crt.m_hi[3] << 64) | c_crt.m_lo[3];
+
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        const int col = work % p.cols_out;
+        const size_t b = work / p.cols_out;
+        const uint32_t *a = reinterpret_cast<const uint32_t *>(p.a_dft + b * p.a_bs);
+        long long *res = reinterpret_cast<long long *>(p.res + b * p.res_bs) + (size_t)col * n;
+        const long long *small = (p.small && col == 0) ? reinterpret_cast<const long long *>(p.small + b * p.small_bs) : nullptr;
+
+        for (int j = p.res_start; j < p.res_size; j++) {
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) res[(size_t)j * res_ls + t + jj * G::T] = 0;
+        }
+        for (int j = p.a_size - 1; j >= p.a_end; j--) {
+            const uint32_t *mc = pm + ((size_t)j * p.cols_out + col) * poly;
+            fused_bottom<0, L>(smem + 0 * G::PLANE, a + 0 * n, poly, mc + 0 * n, m_stride, p.R, tw + 0 * n, t);
+            fused_bottom<1, L>(smem + 1 * G::PLANE, a + 1 * n, poly, mc + 1 * n, m_stride, p.R, tw + 1 * n, t);
+            fused_bottom<2, L>(smem + 2 * G::PLANE, a + 2 * n, poly, mc + 2 * n, m_stride, p.R, tw + 2 * n, t);
+            fused_bottom<3, L>(smem + 3 * G::PLANE, a + 3 * n, poly, mc + 3 * n, m_stride, p.R, tw + 3 * n, t);
+            __syncthreads();
+            InvMid<L, (L - 6 >= G::R0) ? L - 6 : -1>::run(smem, tw, n, t);
+            fused_top<0, L>(smem + 0 * G::PLANE, tw + 0 * n, t, nc);
+            fused_top<1, L>(smem + 1 * G::PLANE, tw + 1 * n, t, nc);
+            fused_top<2, L>(smem + 2 * G::PLANE, tw + 2 * n, t, nc);
+            fused_top<3, L>(smem + 3 * G::PLANE, tw + 3 * n, t, nc);
+            // the residues of coefficient idx = t + jj*T sit at thread-private plane slots: no barrier needed here
+            const bool carry_only = j >= p.a_start;
+            const bool first = j == p.a_size - 1 && carry_only;
+            const bool have_carry = j != p.a_size - 1;
+            const int res_limb = j - p.a_start + p.res_start;
+            const bool add_small = small && j < p.small_size;
+#pragma unroll 2
+            for (int jj = 0; jj < 8; jj++) {
+                const int idx = t + jj * G::T;
+                const int pi = PAD(idx);
+                const u128 acc = (u128)smem[pi] * M0 + (u128)smem[G::PLANE + pi] * M1 + (u128)smem[2 * G::PLANE + pi] * M2 +
+                                 (u128)smem[3 * G::PLANE + pi] * M3;
+                i128 v = crt_finish(acc);
+                if (add_small) v = (i128)((u128)v + (u128)(i128)small[(size_t)j * small_ls + idx]);
+                if (lsh == 0) {
+                    // Same-base2k step without an intra-limb shift collapses to one digit extraction of t = v + carry_in:
+                    //   digit_K(digit_K(v) + c) = digit_K(t)   and   carry(v) + carry(digit_K(v) + c) = (t + 2^(K-1)) >> K
+                    // (vec_znx_big.rs:120-133 with lsh == 0; t cannot overflow: |v| < 2^119, |c| < 2^(120-K)).
+                    const i128 tt = (first || !have_carry) ? v : (i128)((u128)v + (u128)carry[idx]);
+                    const long long out = ((long long)(unsigned long long)tt << (64 - K)) >> (64 - K);
+                    carry[idx] = (i128)((u128)tt + ((u128)1 << (K - 1))) >> K;
+                    if (!carry_only) res[(size_t)res_limb * res_ls + idx] = out;
+                } else {
+                    const i128 d = nd_get_digit(w, v);
+                    const i128 co = nd_get_carry(w, v, d);
+                    if (first) {
+                        carry[idx] = co;
+                    } else {
+                        const i128 cin = have_carry ? carry[idx] : (i128)0;
+                        const i128 s = (i128)(((u128)d << lsh) + (u128)cin);
+                        const i128 out = nd_get_digit(K, s);
+                        carry[idx] = (i128)((u128)co + (u128)nd_get_carry(K, s, out));
+                        if (!carry_only) res[(size_t)res_limb * res_ls + idx] = (long long)out;
+                    }
+                }
+            }
+            __syncthreads(); // planes are rewritten by the next limb's bottom pass
+        }
+        const bool any = p.a_size - 1 >= p.a_end;
+        for (int j = 0; j < p.res_end; j++) {
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) {
+                const int idx = t + jj * G::T;
+                const i128 c = any ? carry[idx] : (i128)0;
+                const i128 out = nd_get_digit(K, c);
+                res[(size_t)(p.res_end - j - 1) * res_ls + idx] = (long long)out;
+                carry[idx] = nd_get_carry(K, c, out);
+            }
+        }
     }
 }
 
@@ -409,4 +607,69 @@ int ntt120_inverse_big(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batc
     NttJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch};
     if (jb.total_jobs == 0) return PGB_OK;
     NTT_DISPATCH(launch_inv)
+}
+
+template <int L> static int launch_fused(pgb_module *m, const FusedArgs &p, int batch) {
+    typedef Geo<L> G;
+    size_t smem = (size_t)4 * G::PLANE * sizeof(uint32_t);
+    static int ctas_per_sm = 0, sms = 0;
+    if (!ctas_per_sm) {
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_fused_back_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_fused_back_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        PGB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, ntt120_fused_back_kernel<L>, G::T, smem));
+        if (getenv("PGB_DEBUG")) fprintf(stderr, "[pgb] fused_back<%d>: %d CTAs/SM, smem %zu\n", L, ctas_per_sm, smem);
+        PGB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    const int total = p.cols_out * batch;
+    const int grid = total < sms * ctas_per_sm ? total : sms * ctas_per_sm;
+    const size_t need = (size_t)grid * G::NB * sizeof(i128);
+    if (m->carry_len < need) {
+        if (m->carry_ws) {
+            PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+            cudaFree(m->carry_ws);
+        }
+        m->carry_ws = nullptr;
+        m->carry_len = 0;
+        PGB_CHECK_CUDA(cudaMalloc(&m->carry_ws, need));
+        m->carry_len = need;
+    }
+    { ProfScope _ps(m, PROF_DFT_INV);
+    ntt120_fused_back_kernel<L><<<grid, G::T, smem, m->stream>>>(p, m->ntt_inv, m->nc, total, (i128 *)m->carry_ws);
+    }
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+
+bool ntt120_fused_supported(const pgb_module *m) { return m->flavour == PGB_NTT120 && m->log_n >= 9 && m->log_n <= 13; }
+
+// res(cols_out, res_size) <- normalize( idft( a_dft(R polys) x pmat[R][C] ) + small on column 0 ), same base2k, offset res_offset
+int ntt120_fused_back(pgb_module *m, const char *a_dft, uint64_t a_bs, const char *pmat, int R, int C, int cols_out, const char *small,
+                      uint64_t small_bs, uint64_t small_limb_stride, int small_size, char *res, uint64_t res_bs, uint64_t res_limb_stride,
+                      int res_size, int base2k, int64_t res_offset, int batch) {
+    FusedArgs p;
+    memset(&p, 0, sizeof p);
+    p.a_dft = a_dft; p.a_bs = a_bs; p.pmat = pmat; p.small = small; p.small_bs = small_bs; p.small_limb_stride = small_limb_stride;
+    p.small_size = small_size; p.res = res; p.res_bs = res_bs; p.res_limb_stride = res_limb_stride;
+    p.R = R; p.C = C; p.cols_out = cols_out;
+    p.K = base2k; p.res_size = res_size; p.a_size = C / cols_out;
+    int64_t lsh = res_offset % base2k, lo = res_offset / base2k;
+    if (res_offset < 0 && lsh != 0) {
+        lsh = (lsh + base2k) % base2k;
+        lo -= 1;
+    }
+    auto clampi = [](int64_t v, int64_t a, int64_t b) { return v < a ? a : (v > b ? b : v); };
+    p.lsh = (int)lsh;
+    p.res_end = (int)clampi(-lo, 0, res_size);
+    p.res_start = (int)clampi((int64_t)p.a_size - lo, 0, res_size);
+    p.a_end = (int)clampi(lo, 0, p.a_size);
+    p.a_start = (int)clampi((int64_t)res_size + lo, 0, p.a_size);
+    switch (m->log_n) {
+    case 9: return launch_fused<9>(m, p, batch);
+    case 10: return launch_fused<10>(m, p, batch);
+    case 11: return launch_fused<11>(m, p, batch);
+    case 12: return launch_fused<12>(m, p, batch);
+    case 13: return launch_fused<13>(m, p, batch);
+    default: pgb_set_error("fused back end: unsupported n"); return PGB_ERR_UNSUPPORTED;
+    }
 }

@@ -23,7 +23,7 @@ struct VmpArgs {
 template <int CT> __global__ void __launch_bounds__(256) ntt120_vmp_kernel(VmpArgs p) {
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; // uint4 index inside a poly, [0, 4*n4)
     if (u >= 4 * p.n4) return;
-    const int k = u / p.n4;
+    const PrimeRt pr(u / p.n4);
     const uint32_t c0 = blockIdx.y * CT;
     const size_t poly_words = (size_t)4 * p.n4;
     const uint4 *a = reinterpret_cast<const uint4 *>(p.a + (size_t)blockIdx.z * p.a_bs) + u;
@@ -54,7 +54,7 @@ template <int CT> __global__ void __launch_bounds__(256) ntt120_vmp_kernel(VmpAr
 #pragma unroll
         for (int c = 0; c < CT; c++) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) acc[c][i] = red64k(acc[c][i], k);
+            for (int i = 0; i < 4; i++) acc[c][i] = pr.reduce(acc[c][i]);
         }
     }
 #pragma unroll
@@ -93,8 +93,8 @@ __device__ __forceinline__ uint32_t negq(uint32_t x, uint32_t q) { return x == 0
 template <int OP> __global__ void __launch_bounds__(256) ntt120_ew_kernel(EwArgs p) {
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= 4 * p.n4) return;
-    const int k = u / p.n4;
-    const uint32_t q = qk(k);
+    const PrimeRt pr(u / p.n4);
+    const uint32_t q = pr.q;
     const uint32_t j = blockIdx.y, b = blockIdx.z;
     uint4 *dst = reinterpret_cast<uint4 *>(p.dst.base + (size_t)b * p.dst.batch_stride + (size_t)j * p.dst.limb_stride) + u;
     uint4 r = make_uint4(0, 0, 0, 0);
@@ -107,8 +107,8 @@ template <int OP> __global__ void __launch_bounds__(256) ntt120_ew_kernel(EwArgs
             if (OP == EW_ADD) r = make_uint4(addq(x.x, y.x, q), addq(x.y, y.y, q), addq(x.z, y.z, q), addq(x.w, y.w, q));
             else if (OP == EW_SUB) r = make_uint4(subq(x.x, y.x, q), subq(x.y, y.y, q), subq(x.z, y.z, q), subq(x.w, y.w, q));
             else { // EW_MUL
-                r = make_uint4(red64k((unsigned long long)x.x * y.x, k), red64k((unsigned long long)x.y * y.y, k),
-                               red64k((unsigned long long)x.z * y.z, k), red64k((unsigned long long)x.w * y.w, k));
+                r = make_uint4(pr.reduce((unsigned long long)x.x * y.x), pr.reduce((unsigned long long)x.y * y.y),
+                               pr.reduce((unsigned long long)x.z * y.z), pr.reduce((unsigned long long)x.w * y.w));
             }
         }
     }
