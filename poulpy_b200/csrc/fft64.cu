@@ -80,19 +80,20 @@ struct FftJobs {
 };
 
 template <int L, int L0> struct FFwdMid {
-    static __device__ __forceinline__ void run(double2 *sm, double *gout, const double2 *tw, int t, bool active) {
+    static __device__ __forceinline__ void run(double2 *sm, double *gout, const double2 *tw, int t, bool active, uint32_t root = 1u,
+                                               int m_plane = FGeo<L>::M) {
         typedef FGeo<L> G;
         constexpr int SL = L - L0 - 3;
         const int a = t >> SL, b = t & ((1 << SL) - 1);
         const int base = (a << (SL + 3)) | b;
-        const uint32_t hi = (1u << L0) | (uint32_t)a;
+        const uint32_t hi = (root << L0) | (uint32_t)a;
         double2 x[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) x[j] = sm[FPAD(base + (j << SL))];
         fct_radix8<3>(x, tw, hi);
         if (SL == 0) {
             if (active) {
-                double2 *ore = reinterpret_cast<double2 *>(gout + base), *oim = reinterpret_cast<double2 *>(gout + G::M + base);
+                double2 *ore = reinterpret_cast<double2 *>(gout + base), *oim = reinterpret_cast<double2 *>(gout + m_plane + base);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     ore[j] = make_double2(x[2 * j].x, x[2 * j + 1].x);
@@ -104,11 +105,11 @@ template <int L, int L0> struct FFwdMid {
             for (int j = 0; j < 8; j++) sm[FPAD(base + (j << SL))] = x[j];
             __syncthreads();
         }
-        FFwdMid<L, (L0 + 3 < L) ? L0 + 3 : L>::run(sm, gout, tw, t, active);
+        FFwdMid<L, (L0 + 3 < L) ? L0 + 3 : L>::run(sm, gout, tw, t, active, root, m_plane);
     }
 };
 template <int L> struct FFwdMid<L, L> {
-    static __device__ __forceinline__ void run(double2 *, double *, const double2 *, int, bool) {}
+    static __device__ __forceinline__ void run(double2 *, double *, const double2 *, int, bool, uint32_t = 1u, int = 0) {}
 };
 
 template <int L, int LPC> __global__ void __launch_bounds__(FGeo<L>::T *LPC) fft64_fwd_kernel(FftJobs jb, const double2 *__restrict__ tw) {
@@ -145,12 +146,12 @@ template <int L, int LPC> __global__ void __launch_bounds__(FGeo<L>::T *LPC) fft
 }
 
 template <int L, int L0> struct FInvMid {
-    static __device__ __forceinline__ void run(double2 *sm, const double2 *tw, int t) {
+    static __device__ __forceinline__ void run(double2 *sm, const double2 *tw, int t, uint32_t root = 1u) {
         typedef FGeo<L> G;
         constexpr int SL = L - L0 - 3;
         const int a = t >> SL, b = t & ((1 << SL) - 1);
         const int base = (a << (SL + 3)) | b;
-        const uint32_t hi = (1u << L0) | (uint32_t)a;
+        const uint32_t hi = (root << L0) | (uint32_t)a;
         double2 x[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) x[j] = sm[FPAD(base + (j << SL))];
@@ -158,11 +159,11 @@ template <int L, int L0> struct FInvMid {
 #pragma unroll
         for (int j = 0; j < 8; j++) sm[FPAD(base + (j << SL))] = x[j];
         __syncthreads();
-        FInvMid<L, (L0 - 3 >= G::R0) ? L0 - 3 : -1>::run(sm, tw, t);
+        FInvMid<L, (L0 - 3 >= G::R0) ? L0 - 3 : -1>::run(sm, tw, t, root);
     }
 };
 template <int L> struct FInvMid<L, -1> {
-    static __device__ __forceinline__ void run(double2 *, const double2 *, int) {}
+    static __device__ __forceinline__ void run(double2 *, const double2 *, int, uint32_t = 1u) {}
 };
 
 template <int L, int LPC> __global__ void __launch_bounds__(FGeo<L>::T *LPC) fft64_inv_kernel(FftJobs jb, const double2 *__restrict__ tw, double inv_m) {
@@ -274,6 +275,150 @@ template <int L> static int flaunch_inv(pgb_module *m, const FftJobs &jb) {
     return PGB_OK;
 }
 
+// ---- m > 8192: global radix-8 top pass + eight size-m/8 sub-transforms (block twiddles rooted at 8 + sub-block) -----------
+struct FTopJobs {
+    LimbSet in, out;
+    int jobs_per_batch, total_jobs, m;
+};
+__global__ void __launch_bounds__(256) fft64_fwd_top8_kernel(FTopJobs jb, const double2 *__restrict__ tw) {
+    const int m = jb.m, s = m >> 3;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s) return;
+    const int job = blockIdx.y, b = job / jb.jobs_per_batch, j = job % jb.jobs_per_batch;
+    const long long *gin = reinterpret_cast<const long long *>(jb.in.base + (size_t)b * jb.in.batch_stride + (size_t)j * jb.in.limb_stride);
+    double *gout = reinterpret_cast<double *>(jb.out.base + (size_t)b * jb.out.batch_stride + (size_t)j * jb.out.limb_stride);
+    double2 x[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) x[jj] = make_double2((double)__ldg(gin + i + jj * s), (double)__ldg(gin + m + i + jj * s));
+    fct_radix8<3>(x, tw, 1u);
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+        gout[i + jj * s] = x[jj].x;
+        gout[m + i + jj * s] = x[jj].y;
+    }
+}
+template <int L> __global__ void __launch_bounds__(FGeo<L>::T) fft64_fwd_sub_kernel(LimbSet out, int jobs_per_batch, int m_total,
+                                                                                  const double2 *__restrict__ tw) {
+    typedef FGeo<L> G;
+    extern __shared__ __align__(16) double2 fsm[];
+    const int t = threadIdx.x;
+    const int sb = blockIdx.x & 7, limb = blockIdx.x >> 3;
+    const int b = limb / jobs_per_batch, j = limb % jobs_per_batch;
+    double *g = reinterpret_cast<double *>(out.base + (size_t)b * out.batch_stride + (size_t)j * out.limb_stride) + (size_t)sb * G::M;
+    const uint32_t root = 8u | (uint32_t)sb;
+    double2 x[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) x[jj] = make_double2(g[t + jj * G::T], g[m_total + t + jj * G::T]);
+    fct_radix8<G::R0>(x, tw, root);
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) fsm[FPAD(t + jj * G::T)] = x[jj];
+    __syncthreads();
+    FFwdMid<L, G::R0>::run(fsm, g, tw, t, true, root, m_total);
+}
+template <int L> __global__ void __launch_bounds__(FGeo<L>::T) fft64_inv_sub_kernel(LimbSet in, LimbSet out, int jobs_per_batch, int m_total,
+                                                                                  const double2 *__restrict__ tw) {
+    typedef FGeo<L> G;
+    extern __shared__ __align__(16) double2 fsm[];
+    const int t = threadIdx.x;
+    const int sb = blockIdx.x & 7, limb = blockIdx.x >> 3;
+    const int b = limb / jobs_per_batch, j = limb % jobs_per_batch;
+    const double *gi = reinterpret_cast<const double *>(in.base + (size_t)b * in.batch_stride + (size_t)j * in.limb_stride) + (size_t)sb * G::M;
+    double *go = reinterpret_cast<double *>(out.base + (size_t)b * out.batch_stride + (size_t)j * out.limb_stride) + (size_t)sb * G::M;
+    const uint32_t root = 8u | (uint32_t)sb;
+    double2 x[8];
+    {
+        const double2 *pre = reinterpret_cast<const double2 *>(gi + 8 * t), *pim = reinterpret_cast<const double2 *>(gi + m_total + 8 * t);
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+            double2 r = pre[jj], i = pim[jj];
+            x[2 * jj] = make_double2(r.x, i.x);
+            x[2 * jj + 1] = make_double2(r.y, i.y);
+        }
+    }
+    fgs_radix8<3>(x, tw, (root << (L - 3)) | (uint32_t)t);
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) fsm[FPAD(8 * t + jj)] = x[jj];
+    __syncthreads();
+    FInvMid<L, (L - 6 >= G::R0) ? L - 6 : -1>::run(fsm, tw, t, root);
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) x[jj] = fsm[FPAD(t + jj * G::T)];
+    fgs_radix8<G::R0>(x, tw, root);
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+        go[t + jj * G::T] = x[jj].x;
+        go[m_total + t + jj * G::T] = x[jj].y;
+    }
+}
+// in place on the f64 limb left by the sub-transforms: top three levels, scale by 1/m, round, reinterpret as i64
+__global__ void __launch_bounds__(256) fft64_inv_top8_kernel(LimbSet io, int jobs_per_batch, int m, const double2 *__restrict__ tw, double inv_m) {
+    const int s = m >> 3;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s) return;
+    const int job = blockIdx.y, b = job / jobs_per_batch, j = job % jobs_per_batch;
+    double *g = reinterpret_cast<double *>(io.base + (size_t)b * io.batch_stride + (size_t)j * io.limb_stride);
+    double2 x[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) x[jj] = make_double2(g[i + jj * s], g[m + i + jj * s]);
+    fgs_radix8<3>(x, tw, 1u);
+    long long *o = reinterpret_cast<long long *>(g);
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+        o[i + jj * s] = (long long)round(x[jj].x * inv_m);
+        o[m + i + jj * s] = (long long)round(x[jj].y * inv_m);
+    }
+}
+
+template <int L> static int flaunch_fwd_sub(pgb_module *m, LimbSet out, int jobs_per_batch, int total) {
+    typedef FGeo<L> G;
+    size_t smem = (size_t)G::PLANE * sizeof(double2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(fft64_fwd_sub_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    { ProfScope _ps(m, PROF_DFT_FWD);
+    fft64_fwd_sub_kernel<L><<<total * 8, G::T, smem, m->stream>>>(out, jobs_per_batch, (int)(m->n / 2), m->fft_fwd);
+    }
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+template <int L> static int flaunch_inv_sub(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int total) {
+    typedef FGeo<L> G;
+    size_t smem = (size_t)G::PLANE * sizeof(double2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(fft64_inv_sub_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    { ProfScope _ps(m, PROF_DFT_INV);
+    fft64_inv_sub_kernel<L><<<total * 8, G::T, smem, m->stream>>>(in, out, jobs_per_batch, (int)(m->n / 2), m->fft_inv);
+    }
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+static int fft64_forward_large(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch) {
+    const int total = jobs_per_batch * batch, mm = (int)(m->n / 2);
+    PGB_REQUIRE(total <= 65535, "FFT64 large-n path: more than 65535 limbs per call (split the batch)");
+    FTopJobs tj = {in, out, jobs_per_batch, total, mm};
+    dim3 grid(((unsigned)(mm >> 3) + 255) / 256, total);
+    { ProfScope _ps(m, PROF_DFT_FWD);
+    fft64_fwd_top8_kernel<<<grid, 256, 0, m->stream>>>(tj, m->fft_fwd);
+    }
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return m->log_n == 15 ? flaunch_fwd_sub<11>(m, out, jobs_per_batch, total) : flaunch_fwd_sub<12>(m, out, jobs_per_batch, total);
+}
+static int fft64_inverse_large(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch) {
+    const int total = jobs_per_batch * batch, mm = (int)(m->n / 2);
+    PGB_REQUIRE(total <= 65535, "FFT64 large-n path: more than 65535 limbs per call (split the batch)");
+    PGB_TRY(m->log_n == 15 ? flaunch_inv_sub<11>(m, in, out, jobs_per_batch, total) : flaunch_inv_sub<12>(m, in, out, jobs_per_batch, total));
+    dim3 grid(((unsigned)(mm >> 3) + 255) / 256, total);
+    { ProfScope _ps(m, PROF_DFT_INV);
+    fft64_inv_top8_kernel<<<grid, 256, 0, m->stream>>>(out, jobs_per_batch, mm, m->fft_inv, 1.0 / (double)mm);
+    }
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+
 #define FFT_DISPATCH(fn)                           \
     switch (m->log_n - 1) {                        \
     case 3: return fn<3>(m, jb);                   \
@@ -295,11 +440,13 @@ template <int L> static int flaunch_inv(pgb_module *m, const FftJobs &jb) {
 int fft64_forward(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch) {
     FftJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch};
     if (jb.total_jobs == 0) return PGB_OK;
+    if (m->log_n >= 15) return fft64_forward_large(m, in, out, jobs_per_batch, batch);
     FFT_DISPATCH(flaunch_fwd)
 }
 int fft64_inverse_big(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch) {
     FftJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch};
     if (jb.total_jobs == 0) return PGB_OK;
+    if (m->log_n >= 15) return fft64_inverse_large(m, in, out, jobs_per_batch, batch);
     FFT_DISPATCH(flaunch_inv)
 }
 

@@ -102,12 +102,12 @@ template <int K, int L> __device__ __forceinline__ void fwd_prime(const long lon
 }
 
 template <int K, int L, int L0> __device__ __forceinline__ void fwd_mid(uint32_t *__restrict__ plane, uint32_t *__restrict__ gout,
-                                                                       const uint2 *__restrict__ tw, int t, bool active) {
+                                                                       const uint2 *__restrict__ tw, int t, bool active, uint32_t root) {
     constexpr uint32_t q = Prime<K>::q;
     constexpr int SL = L - L0 - 3; // log2 of the in-group stride
     const int a = t >> SL, b = t & ((1 << SL) - 1);
     const int base = (a << (SL + 3)) | b;
-    const uint32_t hi = (1u << L0) | (uint32_t)a;
+    const uint32_t hi = (root << L0) | (uint32_t)a;
     uint32_t x[8];
     if (SL == 0) {
         const uint4 *p = reinterpret_cast<const uint4 *>(plane + PAD(base));
@@ -134,18 +134,19 @@ template <int K, int L, int L0> __device__ __forceinline__ void fwd_mid(uint32_t
 }
 
 template <int L, int L0> struct FwdMid {
-    static __device__ __forceinline__ void run(uint32_t *sm, uint32_t *gout, const uint2 *tw, int n, int t, bool active) {
+    static __device__ __forceinline__ void run(uint32_t *sm, uint32_t *gout, const uint2 *tw, int n, int t, bool active,
+                                               uint32_t root = 1u) {
         typedef Geo<L> G;
-        fwd_mid<0, L, L0>(sm + 0 * G::PLANE, gout + 0 * n, tw + 0 * n, t, active);
-        fwd_mid<1, L, L0>(sm + 1 * G::PLANE, gout + 1 * n, tw + 1 * n, t, active);
-        fwd_mid<2, L, L0>(sm + 2 * G::PLANE, gout + 2 * n, tw + 2 * n, t, active);
-        fwd_mid<3, L, L0>(sm + 3 * G::PLANE, gout + 3 * n, tw + 3 * n, t, active);
+        fwd_mid<0, L, L0>(sm + 0 * G::PLANE, gout + 0 * n, tw + 0 * n, t, active, root);
+        fwd_mid<1, L, L0>(sm + 1 * G::PLANE, gout + 1 * n, tw + 1 * n, t, active, root);
+        fwd_mid<2, L, L0>(sm + 2 * G::PLANE, gout + 2 * n, tw + 2 * n, t, active, root);
+        fwd_mid<3, L, L0>(sm + 3 * G::PLANE, gout + 3 * n, tw + 3 * n, t, active, root);
         if (L0 + 3 < L) __syncthreads();
-        FwdMid<L, (L0 + 3 < L) ? L0 + 3 : L>::run(sm, gout, tw, n, t, active);
+        FwdMid<L, (L0 + 3 < L) ? L0 + 3 : L>::run(sm, gout, tw, n, t, active, root);
     }
 };
 template <int L> struct FwdMid<L, L> {
-    static __device__ __forceinline__ void run(uint32_t *, uint32_t *, const uint2 *, int, int, bool) {}
+    static __device__ __forceinline__ void run(uint32_t *, uint32_t *, const uint2 *, int, int, bool, uint32_t = 1u) {}
 };
 
 template <int L, int LPC> __global__ void __launch_bounds__(Geo<L>::T *LPC) ntt120_fwd_kernel(NttJobs jb, const uint2 *__restrict__ tw) {
@@ -176,9 +177,9 @@ template <int L, int LPC> __global__ void __launch_bounds__(Geo<L>::T *LPC) ntt1
 // ---------------------------------------------------------------------------------------------- inverse
 // bottom pass: levels L-3..L-1 on 8 consecutive residues per thread, results to shared memory
 template <int K, int L> __device__ __forceinline__ void inv_bottom_core(uint32_t (&x)[8], uint32_t *__restrict__ plane,
-                                                                       const uint2 *__restrict__ tw, int t) {
+                                                                       const uint2 *__restrict__ tw, int t, uint32_t root = 1u) {
     constexpr int L0 = L - 3;
-    const uint32_t hi = (1u << L0) | (uint32_t)t;
+    const uint32_t hi = (root << L0) | (uint32_t)t;
     gs_radix8<K, 3>(x, tw, hi);
     uint4 *o = reinterpret_cast<uint4 *>(plane + PAD(8 * t));
     o[0] = make_uint4(x[0], x[1], x[2], x[3]);
@@ -186,7 +187,7 @@ template <int K, int L> __device__ __forceinline__ void inv_bottom_core(uint32_t
 }
 // inputs read from global planes
 template <int K, int L> __device__ __forceinline__ void inv_bottom(uint32_t *__restrict__ plane, const uint32_t *__restrict__ gin,
-                                                                  const uint2 *__restrict__ tw, int t, bool active) {
+                                                                  const uint2 *__restrict__ tw, int t, bool active, uint32_t root = 1u) {
     uint32_t x[8];
     uint4 u0 = make_uint4(0, 0, 0, 0), u1 = u0;
     if (active) {
@@ -196,13 +197,14 @@ template <int K, int L> __device__ __forceinline__ void inv_bottom(uint32_t *__r
     }
     x[0] = u0.x; x[1] = u0.y; x[2] = u0.z; x[3] = u0.w;
     x[4] = u1.x; x[5] = u1.y; x[6] = u1.z; x[7] = u1.w;
-    inv_bottom_core<K, L>(x, plane, tw, t);
+    inv_bottom_core<K, L>(x, plane, tw, t, root);
 }
-template <int K, int L, int L0> __device__ __forceinline__ void inv_mid(uint32_t *__restrict__ plane, const uint2 *__restrict__ tw, int t) {
+template <int K, int L, int L0> __device__ __forceinline__ void inv_mid(uint32_t *__restrict__ plane, const uint2 *__restrict__ tw, int t,
+                                                                       uint32_t root) {
     constexpr int SL = L - L0 - 3;
     const int a = t >> SL, b = t & ((1 << SL) - 1);
     const int base = (a << (SL + 3)) | b;
-    const uint32_t hi = (1u << L0) | (uint32_t)a;
+    const uint32_t hi = (root << L0) | (uint32_t)a;
     uint32_t x[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) x[j] = plane[PAD(base + (j << SL))];
@@ -212,18 +214,18 @@ template <int K, int L, int L0> __device__ __forceinline__ void inv_mid(uint32_t
 }
 // passes from l0 = L-6 down to R0 (exclusive of the top pass)
 template <int L, int L0> struct InvMid {
-    static __device__ __forceinline__ void run(uint32_t *sm, const uint2 *tw, int n, int t) {
+    static __device__ __forceinline__ void run(uint32_t *sm, const uint2 *tw, int n, int t, uint32_t root = 1u) {
         typedef Geo<L> G;
-        inv_mid<0, L, L0>(sm + 0 * G::PLANE, tw + 0 * n, t);
-        inv_mid<1, L, L0>(sm + 1 * G::PLANE, tw + 1 * n, t);
-        inv_mid<2, L, L0>(sm + 2 * G::PLANE, tw + 2 * n, t);
-        inv_mid<3, L, L0>(sm + 3 * G::PLANE, tw + 3 * n, t);
+        inv_mid<0, L, L0>(sm + 0 * G::PLANE, tw + 0 * n, t, root);
+        inv_mid<1, L, L0>(sm + 1 * G::PLANE, tw + 1 * n, t, root);
+        inv_mid<2, L, L0>(sm + 2 * G::PLANE, tw + 2 * n, t, root);
+        inv_mid<3, L, L0>(sm + 3 * G::PLANE, tw + 3 * n, t, root);
         __syncthreads();
-        InvMid<L, (L0 - 3 >= G::R0) ? L0 - 3 : -1>::run(sm, tw, n, t);
+        InvMid<L, (L0 - 3 >= G::R0) ? L0 - 3 : -1>::run(sm, tw, n, t, root);
     }
 };
 template <int L> struct InvMid<L, -1> {
-    static __device__ __forceinline__ void run(uint32_t *, const uint2 *, int, int) {}
+    static __device__ __forceinline__ void run(uint32_t *, const uint2 *, int, int, uint32_t = 1u) {}
 };
 
 // top pass for one prime: R0 levels, then t_k = x * CRT_k / n and accumulation of t_k * (Q / Q_k)
@@ -293,6 +295,112 @@ template <int L, int LPC> __global__ void __launch_bounds__(Geo<L>::T *LPC) ntt1
 #pragma unroll
         for (int jj = 0; jj < 8; jj++) gout[t + jj * G::T] = crt_finish(acc[jj]);
     }
+}
+
+// ---------------------------------------------------------------------------------------------- n > 8192 (two kernels)
+// n = 8 * NB: the three top levels run as a global radix-8 pass (stride n/8, fully coalesced), the remaining log2(NB) levels as
+// eight independent size-NB sub-transforms in shared memory whose block twiddles start at root = 8 + sub-block index.
+struct TopJobs {
+    LimbSet in, out;
+    int jobs_per_batch, total_jobs, n;
+};
+__global__ void __launch_bounds__(256) ntt120_fwd_top8_kernel(TopJobs jb, const uint2 *__restrict__ tw) {
+    const int n = jb.n, s = n >> 3;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s) return;
+    const int job = blockIdx.y, b = job / jb.jobs_per_batch, j = job % jb.jobs_per_batch;
+    const long long *gin = reinterpret_cast<const long long *>(jb.in.base + (size_t)b * jb.in.batch_stride + (size_t)j * jb.in.limb_stride);
+    uint32_t *gout = reinterpret_cast<uint32_t *>(jb.out.base + (size_t)b * jb.out.batch_stride + (size_t)j * jb.out.limb_stride);
+    long long v[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) v[jj] = __ldg(gin + i + jj * s);
+    uint32_t x[8];
+#define TOP_FWD(K)                                                   \
+    _Pragma("unroll") for (int jj = 0; jj < 8; jj++) x[jj] = from_i64<K>(v[jj]); \
+    ct_radix8<K, 3>(x, tw + (size_t)K * n, 1u);                      \
+    _Pragma("unroll") for (int jj = 0; jj < 8; jj++) gout[(size_t)K * n + i + jj * s] = x[jj];
+    TOP_FWD(0) TOP_FWD(1) TOP_FWD(2) TOP_FWD(3)
+#undef TOP_FWD
+}
+
+// sub-transform, forward: in place on the lazy residues left by the top pass; job = limb * 8 + sub-block
+template <int L> __global__ void __launch_bounds__(Geo<L>::T) ntt120_fwd_sub_kernel(LimbSet out, int jobs_per_batch, int n_total,
+                                                                                   const uint2 *__restrict__ tw) {
+    typedef Geo<L> G;
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int t = threadIdx.x;
+    const int sb = blockIdx.x & 7, limb = blockIdx.x >> 3;
+    const int b = limb / jobs_per_batch, j = limb % jobs_per_batch;
+    uint32_t *g = reinterpret_cast<uint32_t *>(out.base + (size_t)b * out.batch_stride + (size_t)j * out.limb_stride) + (size_t)sb * G::NB;
+    const uint32_t root = 8u | (uint32_t)sb;
+#define SUB_FWD(K)                                                                                   \
+    {                                                                                                \
+        uint32_t x[8];                                                                               \
+        _Pragma("unroll") for (int jj = 0; jj < 8; jj++) x[jj] = g[(size_t)K * n_total + t + jj * G::T]; \
+        ct_radix8<K, G::R0>(x, tw + (size_t)K * n_total, root);                                      \
+        _Pragma("unroll") for (int jj = 0; jj < 8; jj++) smem[K * G::PLANE + PAD(t + jj * G::T)] = x[jj]; \
+    }
+    SUB_FWD(0) SUB_FWD(1) SUB_FWD(2) SUB_FWD(3)
+#undef SUB_FWD
+    __syncthreads();
+    FwdMid<L, G::R0>::run(smem, g, tw, n_total, t, true, root);
+}
+
+// sub-transform, inverse: reads canonical residues, writes lazy [0, 2q) residues to `out` (scratch), same plane layout
+template <int L> __global__ void __launch_bounds__(Geo<L>::T) ntt120_inv_sub_kernel(LimbSet in, LimbSet out, int jobs_per_batch, int n_total,
+                                                                                   const uint2 *__restrict__ tw) {
+    typedef Geo<L> G;
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int t = threadIdx.x;
+    const int sb = blockIdx.x & 7, limb = blockIdx.x >> 3;
+    const int b = limb / jobs_per_batch, j = limb % jobs_per_batch;
+    const uint32_t *gi = reinterpret_cast<const uint32_t *>(in.base + (size_t)b * in.batch_stride + (size_t)j * in.limb_stride) + (size_t)sb * G::NB;
+    uint32_t *go = reinterpret_cast<uint32_t *>(out.base + (size_t)b * out.batch_stride + (size_t)j * out.limb_stride) + (size_t)sb * G::NB;
+    const uint32_t root = 8u | (uint32_t)sb;
+    inv_bottom<0, L>(smem + 0 * G::PLANE, gi + (size_t)0 * n_total, tw + (size_t)0 * n_total, t, true, root);
+    inv_bottom<1, L>(smem + 1 * G::PLANE, gi + (size_t)1 * n_total, tw + (size_t)1 * n_total, t, true, root);
+    inv_bottom<2, L>(smem + 2 * G::PLANE, gi + (size_t)2 * n_total, tw + (size_t)2 * n_total, t, true, root);
+    inv_bottom<3, L>(smem + 3 * G::PLANE, gi + (size_t)3 * n_total, tw + (size_t)3 * n_total, t, true, root);
+    __syncthreads();
+    InvMid<L, (L - 6 >= G::R0) ? L - 6 : -1>::run(smem, tw, n_total, t, root);
+#define SUB_INV(K)                                                                                   \
+    {                                                                                                \
+        uint32_t x[8];                                                                               \
+        _Pragma("unroll") for (int jj = 0; jj < 8; jj++) x[jj] = smem[K * G::PLANE + PAD(t + jj * G::T)]; \
+        gs_radix8<K, G::R0>(x, tw + (size_t)K * n_total, root);                                      \
+        _Pragma("unroll") for (int jj = 0; jj < 8; jj++) go[(size_t)K * n_total + t + jj * G::T] = x[jj]; \
+    }
+    SUB_INV(0) SUB_INV(1) SUB_INV(2) SUB_INV(3)
+#undef SUB_INV
+}
+
+// top three inverse levels + CRT, out of place (scratch planes -> i128 limb)
+__global__ void __launch_bounds__(256) ntt120_inv_top8_kernel(TopJobs jb, const uint2 *__restrict__ tw, Ntt120Consts nc) {
+    const int n = jb.n, s = n >> 3;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s) return;
+    const int job = blockIdx.y, b = job / jb.jobs_per_batch, j = job % jb.jobs_per_batch;
+    const uint32_t *gin = reinterpret_cast<const uint32_t *>(jb.in.base + (size_t)b * jb.in.batch_stride + (size_t)j * jb.in.limb_stride);
+    i128 *gout = reinterpret_cast<i128 *>(jb.out.base + (size_t)b * jb.out.batch_stride + (size_t)j * jb.out.limb_stride);
+    u128 acc[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) acc[jj] = 0;
+#define TOP_INV(K)                                                                                    \
+    {                                                                                                 \
+        constexpr uint32_t q = Prime<K>::q;                                                           \
+        uint32_t x[8];                                                                                \
+        _Pragma("unroll") for (int jj = 0; jj < 8; jj++) x[jj] = __ldg(gin + (size_t)K * n + i + jj * s); \
+        gs_radix8<K, 3>(x, tw + (size_t)K * n, 1u);                                                   \
+        const unsigned long long mlo = c_crt.m_lo[K], mhi = c_crt.m_hi[K];                            \
+        _Pragma("unroll") for (int jj = 0; jj < 8; jj++) {                                            \
+            uint32_t tk = csub(mul_shoup(x[jj], nc.crt_ninv[K], nc.crt_ninv_sh[K], q), q);            \
+            acc[jj] += (u128)tk * mlo + ((u128)((unsigned long long)tk * mhi) << 64);                 \
+        }                                                                                             \
+    }
+    TOP_INV(0) TOP_INV(1) TOP_INV(2) TOP_INV(3)
+#undef TOP_INV
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) gout[i + jj * s] = crt_finish(acc[jj]);
 }
 
 // ---------------------------------------------------------------------------------------------- fused back end
@@ -592,20 +700,116 @@ template <int L> static int launch_inv(pgb_module *m, const NttJobs &jb) {
     case 12: return fn<12>(m, jb);               \
     case 13: return fn<13>(m, jb);               \
     default:                                     \
-        pgb_set_error("NTT120: n = 2^%d not supported by the single-CTA path (8 <= n <= 8192)", m->log_n); \
+        pgb_set_error("NTT120: n = 2^%d not supported by the single-CTA path (16 <= n <= 65536)", m->log_n); \
         return PGB_ERR_UNSUPPORTED;              \
     }
+
+template <int L> static int launch_fwd_sub(pgb_module *m, LimbSet out, int jobs_per_batch, int total_jobs) {
+    typedef Geo<L> G;
+    size_t smem = (size_t)4 * G::PLANE * sizeof(uint32_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_fwd_sub_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    { ProfScope _ps(m, PROF_DFT_FWD);
+    ntt120_fwd_sub_kernel<L><<<total_jobs * 8, G::T, smem, m->stream>>>(out, jobs_per_batch, (int)m->n, m->ntt_fwd);
+    }
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+template <int L> static int launch_inv_sub(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int total_jobs) {
+    typedef Geo<L> G;
+    size_t smem = (size_t)4 * G::PLANE * sizeof(uint32_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_inv_sub_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    { ProfScope _ps(m, PROF_DFT_INV);
+    ntt120_inv_sub_kernel<L><<<total_jobs * 8, G::T, smem, m->stream>>>(in, out, jobs_per_batch, (int)m->n, m->ntt_inv);
+    }
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+
+static int ntt120_forward_large(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch) {
+    const int total = jobs_per_batch * batch;
+    for (int j0 = 0; j0 < total; j0 += 32768) { // gridDim.y limit
+        // jobs are (batch, limb) pairs in batch-major order: split on whole batches when there are many, else on limbs
+        const int cnt = total - j0 < 32768 ? total - j0 : 32768;
+        PGB_REQUIRE(j0 == 0 && cnt == total, "NTT120 large-n path: more than 32768 limbs per call (split the batch)");
+        TopJobs tj = {in, out, jobs_per_batch, total, (int)m->n};
+        dim3 grid(((unsigned)(m->n >> 3) + 255) / 256, cnt);
+        { ProfScope _ps(m, PROF_DFT_FWD);
+        ntt120_fwd_top8_kernel<<<grid, 256, 0, m->stream>>>(tj, m->ntt_fwd);
+        }
+        PGB_CHECK_CUDA(cudaGetLastError());
+    }
+    switch (m->log_n) {
+    case 14: return launch_fwd_sub<11>(m, out, jobs_per_batch, total);
+    case 15: return launch_fwd_sub<12>(m, out, jobs_per_batch, total);
+    default: return launch_fwd_sub<13>(m, out, jobs_per_batch, total);
+    }
+}
+
+// scratch for the out-of-place inverse of the large-n path: lazy residue planes of the limbs in flight
+static int ensure_carry_ws(pgb_module *m, size_t need) {
+    if (m->carry_len >= need) return PGB_OK;
+    if (m->carry_ws) {
+        PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+        cudaFree(m->carry_ws);
+    }
+    m->carry_ws = nullptr;
+    m->carry_len = 0;
+    PGB_CHECK_CUDA(cudaMalloc(&m->carry_ws, need));
+    m->carry_len = need;
+    return PGB_OK;
+}
+
+static int ntt120_inverse_large(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch) {
+    const size_t limb_bytes = (size_t)16 * m->n;
+    // process whole batch items per chunk so that the (batch, limb) addressing of the LimbSets stays valid
+    const size_t max_ws = (size_t)512 << 20;
+    int chunk_b = (int)(max_ws / (limb_bytes * jobs_per_batch));
+    if (chunk_b < 1) chunk_b = 1;
+    if (chunk_b > batch) chunk_b = batch;
+    PGB_TRY(ensure_carry_ws(m, (size_t)chunk_b * jobs_per_batch * limb_bytes));
+    for (int b0 = 0; b0 < batch; b0 += chunk_b) {
+        const int nb = batch - b0 < chunk_b ? batch - b0 : chunk_b;
+        const int total = nb * jobs_per_batch;
+        PGB_REQUIRE(total <= 32768, "NTT120 large-n path: more than 32768 limbs per chunk");
+        LimbSet cin = in, cout = out;
+        cin.base += (size_t)b0 * in.batch_stride;
+        cout.base += (size_t)b0 * out.batch_stride;
+        LimbSet ws = {(char *)m->carry_ws, limb_bytes, limb_bytes * jobs_per_batch};
+        switch (m->log_n) {
+        case 14: PGB_TRY(launch_inv_sub<11>(m, cin, ws, jobs_per_batch, total)); break;
+        case 15: PGB_TRY(launch_inv_sub<12>(m, cin, ws, jobs_per_batch, total)); break;
+        default: PGB_TRY(launch_inv_sub<13>(m, cin, ws, jobs_per_batch, total)); break;
+        }
+        TopJobs tj = {ws, cout, jobs_per_batch, total, (int)m->n};
+        dim3 grid(((unsigned)(m->n >> 3) + 255) / 256, total);
+        { ProfScope _ps(m, PROF_DFT_INV);
+        ntt120_inv_top8_kernel<<<grid, 256, 0, m->stream>>>(tj, m->ntt_inv, m->nc);
+        }
+        PGB_CHECK_CUDA(cudaGetLastError());
+    }
+    return PGB_OK;
+}
 
 // in: i64 limbs, out: 16 B/coef DFT limbs
 int ntt120_forward(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch) {
     NttJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch};
     if (jb.total_jobs == 0) return PGB_OK;
+    if (m->log_n >= 14) return ntt120_forward_large(m, in, out, jobs_per_batch, batch);
     NTT_DISPATCH(launch_fwd)
 }
 // in: DFT limbs, out: i128 limbs (may alias `in` limb for limb: in-place consume)
 int ntt120_inverse_big(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch) {
     NttJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch};
     if (jb.total_jobs == 0) return PGB_OK;
+    if (m->log_n >= 14) return ntt120_inverse_large(m, in, out, jobs_per_batch, batch);
     NTT_DISPATCH(launch_inv)
 }
 

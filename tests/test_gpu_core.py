@@ -157,3 +157,20 @@ def test_keyswitch_linearity_full_size():
     diff = np.minimum(diff, (1 << (3 * k)) - diff)
     # each side drops the 4th key limb after rounding: the two sides differ by at most 2 units of the last digit
     assert int(diff.max()) <= 2
+
+
+@pytest.mark.parametrize("fl", FLAVOURS)
+@pytest.mark.parametrize("n", [16384, 65536])
+def test_keyswitch_large_n(fl, n):
+    """Ring degrees above the single-CTA transforms (global radix-8 top pass + sub-transforms), CKKS-like base2k for NTT120."""
+    g, o = pb.Module(n, fl), O.OracleModule(n, fl)
+    rng = np.random.default_rng(900 + n + fl)
+    k = 52 if fl == pb.NTT120 else 14
+    pg, po = _key(g, o, rng, 2, 1, 2, 3, k)
+    a = fill_uniform(rng, (2, 2, 2, n), k)
+    want = np.zeros((2, 2, 2, n), dtype=np.int64)
+    res_g = g.vec_znx_alloc(2, 2, 2)
+    g.glwe_keyswitch(res_g, k, g.vec_znx_from_numpy(a), k, pg, k)
+    g.sync()
+    o.glwe_keyswitch_batch(want, k, a, k, po, k)
+    assert np.array_equal(g.vec_znx_to_numpy(res_g), want)

@@ -47,7 +47,7 @@ def big_equal(fl, g_big_np, o_big_np):
 
 
 @pytest.mark.parametrize("fl", FLAVOURS)
-@pytest.mark.parametrize("n", [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("n", [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536])
 def test_dft_idft_roundtrip_all_sizes(fl, n):
     g, o = mods(n, fl)
     rng = np.random.default_rng(n + fl)
@@ -66,9 +66,13 @@ def test_dft_idft_roundtrip_all_sizes(fl, n):
     big_equal(fl, g.vec_znx_big_to_numpy(bg), bo)
     # the round trip is the identity on small inputs
     if fl == pb.NTT120:
-        assert np.array_equal(O.i128_to_int(g.vec_znx_big_to_numpy(bg)).astype(np.int64), a)
+        big = g.vec_znx_big_to_numpy(bg)
+        assert np.array_equal(big[..., 0].view(np.int64), a) and np.array_equal(big[..., 1].view(np.int64), a >> 63)
     else:
         assert np.array_equal(g.vec_znx_big_to_numpy(bg), a)
+    # consume (in place) gives the same big values
+    cons = g.vec_znx_idft_apply_consume(dg)
+    big_equal(fl, g.vec_znx_big_to_numpy(cons), bo)
 
 
 @pytest.mark.parametrize("n", [64, 1024])
