@@ -1,6 +1,13 @@
 // cggi.cu -- CGGI blind rotation (block-binary), batched and device resident (C3).
 // Restates poulpy-bin-fhe/src/blind_rotation/algorithms/cggi/algorithm.rs:275-368 over the batched HAL kernels.
+#include <stdlib.h>
+
 #include "internal.h"
+
+static inline bool R_ok(uint64_t cols, uint64_t dnum) {
+    const uint64_t R = cols * dnum;
+    return R == 1 || R == 2 || R == 3 || R == 4 || R == 6 || R == 8;
+}
 
 static const uint64_t ALIGN = 256;
 static inline uint64_t align_up(uint64_t x) { return (x + ALIGN - 1) / ALIGN * ALIGN; }
@@ -131,6 +138,12 @@ int cggi_blind_rotate_impl(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2
         LimbSet R = {(char *)res->data, res->cols * n * 8, bt->stride_res};
         LimbSet L = {(char *)lut->data, lut->cols * n * 8, 0};
         PGB_TRY(znx_rotate(m, R, L, 0, (const long long *)lwe_2n, (uint32_t)lwe_stride, (uint32_t)mn, (uint32_t)B));
+    }
+    if (cggi_fused_supported(m, cols, dnum, bsize) && (R_ok(cols, dnum)) && !getenv("PGB_NO_FUSION")) {
+        PGB_REQUIRE(bt->stride_res % 8 == 0, "cggi_blind_rotate: res stride must be a multiple of 8 bytes");
+        return cggi_fused_fft64(m, (long long *)res->data, bt->stride_res / 8, (const long long *)lwe_2n, lwe_stride, (const double *)brk->data,
+                                brk_bytes / 8, (const double *)x_pow_a->data, (int)n_lwe, (int)block_size, (int)base2k, (int)cols, (int)dnum,
+                                (int)bsize, (int)res->size, (int)B);
     }
     for (uint64_t blk = 0; blk + block_size <= n_lwe; blk += block_size) { // chunks_exact
         pgb_batch btd = {B, acc_bs, bt->stride_res, 0};

@@ -288,7 +288,8 @@ static int host_pipeline(pgb_module *m, bool ext, int64_t *res_host, uint64_t re
     if (count == 0) return PGB_OK;
     const uint64_t n = m->n;
     const uint64_t a_bytes = n * a_cols * a_size * 8, r_bytes = n * res_cols * res_size * 8;
-    const uint64_t chunk = umin64(count, 2048);
+    // small chunks keep the three stages overlapped; 64 MB of staging per slot is plenty to reach PCIe line rate
+    const uint64_t chunk = umin64(count, umin64(2048, (a_bytes > r_bytes ? ((uint64_t)64 << 20) / a_bytes : ((uint64_t)64 << 20) / r_bytes) + 1));
     const size_t tmp = ext ? pgb_glwe_external_product_tmp_bytes(m, res_size, a_size, a_base2k, key, key_base2k, dsize, chunk)
                            : pgb_glwe_keyswitch_tmp_bytes(m, res_size, a_size, a_base2k, key, key_base2k, dsize, chunk);
     const size_t in_dev = align_up(chunk * a_bytes), out_dev = align_up(chunk * r_bytes);

@@ -12,66 +12,7 @@
 #include <math.h>
 
 #include "internal.h"
-
-__device__ __forceinline__ int FPAD(int idx) { return idx + (idx >> 3); }
-template <int L> struct FGeo {
-    static constexpr int M = 1 << L;
-    static constexpr int T = M >= 8 ? M / 8 : 1;
-    static constexpr int R0 = (L % 3 == 0) ? 3 : (L % 3);
-    static constexpr int PLANE = M + (M >> 3) + 2; // padded double2 elements
-};
-
-__device__ __forceinline__ void fct_bf(double2 &x, double2 &y, double2 w) { // (x + w*y, x - w*y)
-    double dr = y.x * w.x - y.y * w.y;
-    double di = y.x * w.y + y.y * w.x;
-    y = make_double2(x.x - dr, x.y - di);
-    x = make_double2(x.x + dr, x.y + di);
-}
-__device__ __forceinline__ void fgs_bf(double2 &x, double2 &y, double2 w) { // (x + y, (x - y)*w)
-    double rd = x.x - y.x, id = x.y - y.y;
-    x = make_double2(x.x + y.x, x.y + y.y);
-    y = make_double2(rd * w.x - id * w.y, rd * w.y + id * w.x);
-}
-__device__ __forceinline__ double2 ldw(const double2 *p) {
-    return make_double2(__ldg(&p->x), __ldg(&p->y));
-}
-
-template <int NLEV> __device__ __forceinline__ void fct_radix8(double2 (&x)[8], const double2 *__restrict__ tw, uint32_t hi) {
-    {
-        double2 w = ldw(tw + hi);
-#pragma unroll
-        for (int j = 0; j < 4; j++) fct_bf(x[j], x[j + 4], w);
-    }
-    if (NLEV >= 2) {
-        double2 w0 = ldw(tw + 2 * hi), w1 = ldw(tw + 2 * hi + 1);
-        fct_bf(x[0], x[2], w0);
-        fct_bf(x[1], x[3], w0);
-        fct_bf(x[4], x[6], w1);
-        fct_bf(x[5], x[7], w1);
-    }
-    if (NLEV >= 3) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) fct_bf(x[2 * j], x[2 * j + 1], ldw(tw + 4 * hi + j));
-    }
-}
-template <int NLEV> __device__ __forceinline__ void fgs_radix8(double2 (&x)[8], const double2 *__restrict__ tw, uint32_t hi) {
-    if (NLEV >= 3) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) fgs_bf(x[2 * j], x[2 * j + 1], ldw(tw + 4 * hi + j));
-    }
-    if (NLEV >= 2) {
-        double2 w0 = ldw(tw + 2 * hi), w1 = ldw(tw + 2 * hi + 1);
-        fgs_bf(x[0], x[2], w0);
-        fgs_bf(x[1], x[3], w0);
-        fgs_bf(x[4], x[6], w1);
-        fgs_bf(x[5], x[7], w1);
-    }
-    {
-        double2 w = ldw(tw + hi);
-#pragma unroll
-        for (int j = 0; j < 4; j++) fgs_bf(x[j], x[j + 4], w);
-    }
-}
+#include "fft64.cuh"
 
 struct FftJobs {
     LimbSet in, out;

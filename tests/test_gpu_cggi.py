@@ -35,9 +35,12 @@ def _setup(n, fl, rank, dnum, brk_size, n_lwe, k, rng, trivial_secret=None):
 
 
 @pytest.mark.parametrize("fl", [pb.NTT120, pb.FFT64])
-@pytest.mark.parametrize("rank,dnum,size,brk_size", [(1, 1, 1, 2), (2, 2, 2, 3), (3, 1, 1, 2)])
-def test_blind_rotate_matches_oracle(fl, rank, dnum, size, brk_size):
-    n, k, n_lwe, block, batch = 128, 12, 12, 3, 5
+@pytest.mark.parametrize("n", [128, 256, 512, 1024])
+@pytest.mark.parametrize("rank,dnum,size,brk_size", [(1, 1, 1, 2), (2, 2, 2, 3), (3, 1, 1, 2), (1, 2, 2, 2), (1, 1, 3, 4)])
+def test_blind_rotate_matches_oracle(fl, n, rank, dnum, size, brk_size):
+    """n >= 256 with cols*dnum <= 8 and cols*brk_size <= 8 takes the single-kernel fused path in the FFT64 flavour; the other
+    shapes (and NTT120) run the batched HAL sequence.  batch = 5 leaves a partially filled CTA in the fused kernel."""
+    k, n_lwe, block, batch = 12, 12, 3, 5
     rng = np.random.default_rng(100 * rank + dnum + fl)
     g, o, gbrk, obrk = _setup(n, fl, rank, dnum, brk_size, n_lwe, k, rng)
     xg, xo = g.cggi_x_pow_a(), o.cggi_x_pow_a()
