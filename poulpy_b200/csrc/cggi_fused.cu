@@ -72,22 +72,28 @@ __device__ __forceinline__ void vmp_xai_chunk(const double2 *acc_dft, double2 *a
             br[r][q] = __ldg(pp);
             bi[r][q] = __ldg(pp + M);
         }
-    for (int g = 0; g < G; g++) {
-        double2 a[RT];
+    double wr[G], wi[G];
 #pragma unroll
-        for (int r = 0; r < RT; r++) a[r] = acc_dft[(g * RT + r) * PL + FPAD(f)];
+    for (int g = 0; g < G; g++) { // the G table look-ups are independent: issue them together
         const double *w = xpa + (size_t)s_pos[g] * N + f;
-        const double wr = __ldg(w), wi = __ldg(w + M);
+        wr[g] = __ldg(w);
+        wi[g] = __ldg(w + M);
+    }
+#pragma unroll
+    for (int g = 0; g < G; g++) {
 #pragma unroll
         for (int q = 0; q < PC; q++) {
             if (q < npoly) {
                 double vr = 0.0, vi = 0.0;
 #pragma unroll
-                for (int r = 0; r < RT; r++) { // reim4_add_mul order (reim4/arithmetic_ref.rs:223-232)
-                    vr += a[r].x * br[r][q] - a[r].y * bi[r][q];
-                    vi += a[r].x * bi[r][q] + a[r].y * br[r][q];
+                for (int r = 0; r < RT; r++) { // row order of reim4_add_mul (reim4/arithmetic_ref.rs:223-232), FMA-contracted
+                    const double2 a = acc_dft[(g * RT + r) * PL + FPAD(f)];
+                    vr = fma(a.x, br[r][q], vr);
+                    vr = fma(-a.y, bi[r][q], vr);
+                    vi = fma(a.x, bi[r][q], vi);
+                    vi = fma(a.y, br[r][q], vi);
                 }
-                const double pr = wr * vr - wi * vi, pi = wr * vi + wi * vr; // svp: reim_mul(ppol, v)
+                const double pr = fma(wr[g], vr, -(wi[g] * vi)), pi = fma(wr[g], vi, wi[g] * vr); // svp: reim_mul(ppol, v)
                 double2 *ap = acc_add + (g * C + p0 + q) * PL + FPAD(f);
                 double2 acc = *ap;
                 acc.x = (acc.x + pr) - vr; // dft_add_assign then dft_sub_assign
@@ -150,7 +156,7 @@ template <int LM, int G, int RT> __global__ void __launch_bounds__(G << LM) cggi
             __syncthreads();
             const double *bk = p.brk + (size_t)(blk + tt) * p.brk_doubles;
             const int f = tid % M, pg = tid / M;
-            constexpr int PC = RT <= 4 ? 2 : 1;
+            constexpr int PC = 1;
             for (int p0 = pg * PC; p0 < C; p0 += PC * G)
                 vmp_xai_chunk<RT, PC, G, M, PL>(acc_dft, acc_add, bk, p.xpa, s_pos, C, p0, f, min(PC, C - p0));
             __syncthreads();
