@@ -7,6 +7,8 @@
 //          exact for 16 rows at a time, one Barrett-style reduction per 16 rows)
 //   svp : res[j][k][f] = ppol[k][f] * b[j][k][f] mod Q[k]      (svp.rs:87-180)
 //   add/sub/neg/copy/zero on canonical residues                   (vec_znx_dft.rs:418-652, ntt120/prim.rs:64-165)
+#include <stdlib.h>
+
 #include "internal.h"
 #include "ntt120.cuh"
 
@@ -37,18 +39,19 @@ template <int CT> __global__ void __launch_bounds__(256) ntt120_vmp_kernel(VmpAr
 
     for (uint32_t r0 = 0; r0 < p.row_max; r0 += 16) {
         const uint32_t r1 = min(r0 + 16, p.row_max);
+#pragma unroll 2
         for (uint32_t r = r0; r < r1; r++) {
             const uint4 av = __ldg(a + (size_t)r * poly_words);
             const uint4 *mrow = pm + (size_t)r * p.C * poly_words;
+            uint4 mv[CT];
+#pragma unroll
+            for (int c = 0; c < CT; c++) mv[c] = c < nc ? __ldcs(mrow + (size_t)c * poly_words) : make_uint4(0, 0, 0, 0); // streamed once
 #pragma unroll
             for (int c = 0; c < CT; c++) {
-                if (c < nc) {
-                    const uint4 mv = __ldg(mrow + (size_t)c * poly_words);
-                    acc[c][0] += (unsigned long long)av.x * mv.x;
-                    acc[c][1] += (unsigned long long)av.y * mv.y;
-                    acc[c][2] += (unsigned long long)av.z * mv.z;
-                    acc[c][3] += (unsigned long long)av.w * mv.w;
-                }
+                acc[c][0] += (unsigned long long)av.x * mv[c].x;
+                acc[c][1] += (unsigned long long)av.y * mv[c].y;
+                acc[c][2] += (unsigned long long)av.z * mv[c].z;
+                acc[c][3] += (unsigned long long)av.w * mv[c].w;
             }
         }
 #pragma unroll
@@ -69,10 +72,18 @@ int ntt120_vmp(pgb_module *m, const char *a, uint64_t a_bs, char *res, uint64_t 
     VmpArgs p = {a, a_bs, res, res_bs, pm, pm_bs, (uint32_t)(m->n / 4), row_max, C, col0, ncols_out};
     const uint32_t words = (uint32_t)m->n; // uint4 words per poly
     dim3 block(256);
-    constexpr int CT = 4;
-    dim3 grid((words + 255) / 256, (ncols_out + CT - 1) / CT, batch);
+    static int ct_sel = getenv("PGB_VMP_CT") ? atoi(getenv("PGB_VMP_CT")) : 4;
     { ProfScope _ps(m, PROF_VMP);
-    ntt120_vmp_kernel<CT><<<grid, block, 0, m->stream>>>(p);
+    if (ct_sel == 2 || ncols_out <= 2) {
+        dim3 grid((words + 255) / 256, (ncols_out + 1) / 2, batch);
+        ntt120_vmp_kernel<2><<<grid, block, 0, m->stream>>>(p);
+    } else if (ct_sel == 8 && ncols_out >= 8) {
+        dim3 grid((words + 255) / 256, (ncols_out + 7) / 8, batch);
+        ntt120_vmp_kernel<8><<<grid, block, 0, m->stream>>>(p);
+    } else {
+        dim3 grid((words + 255) / 256, (ncols_out + 3) / 4, batch);
+        ntt120_vmp_kernel<4><<<grid, block, 0, m->stream>>>(p);
+    }
     }
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;
