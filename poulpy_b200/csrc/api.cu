@@ -129,6 +129,7 @@ extern "C" void pgb_module_destroy(pgb_module *m) {
     cudaFree(m->fft_inv);
     cudaFree(m->ws);
     cudaFree(m->carry_ws);
+    cudaFree(m->aux_ws);
     if (m->prof) {
         for (cudaEvent_t e : m->prof->pool) cudaEventDestroy(e);
         delete m->prof;

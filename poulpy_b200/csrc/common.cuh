@@ -71,6 +71,9 @@ struct pgb_module {
     // L2-resident carry scratch of the fused normalising kernels (16 B per coefficient per resident CTA)
     void *carry_ws;
     size_t carry_len;
+    // collapsed key, key coefficient scratch and per-ciphertext guard flags of the collapsed-key fast path
+    void *aux_ws;
+    size_t aux_len;
 };
 
 // kernel categories of the profiler

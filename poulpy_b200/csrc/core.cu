@@ -123,7 +123,8 @@ extern "C" int pgb_glwe_keyswitch_batched(pgb_module *m, pgb_vec_znx *res, uint6
         const uint64_t R = umin64(key->rows * key->cols_in, rank_in * ain.size);
         return ntt120_fused_back(m, (const char *)a_dft.data, a_dft_bs, (const char *)key->data, (int)R, (int)(cols_out * key->size),
                                  (int)cols_out, (const char *)ain.data, ain_bs, ain.cols * n * 8, (int)umin64(ain.size, key->size),
-                                 (char *)res->data, bt->stride_res, res->cols * n * 8, (int)res->size, (int)key_base2k, 0, (int)B);
+                                 (char *)res->data, bt->stride_res, res->cols * n * 8, (int)res->size, (int)key_base2k, 0, (int)B,
+                                 (const char *)ain.data, ain_bs, n * ain.cols * ain.size);
     }
     pgb_vec_znx_dft ai = a_dft, tmp = res_dft;
     uint64_t ai_bs = 0, tmp_bs = 0;
@@ -205,7 +206,7 @@ extern "C" int pgb_glwe_external_product_batched(pgb_module *m, pgb_vec_znx *res
             const uint64_t R = umin64(ggsw->rows * ggsw->cols_in, cols * a_size);
             return ntt120_fused_back(m, (const char *)a_dft.data, a_dft_bs, (const char *)ggsw->data, (int)R, (int)(cols * ggsw->size),
                                      (int)cols, nullptr, 0, 0, 0, (char *)res->data, bt->stride_res, res->cols * n * 8, (int)res->size,
-                                     (int)ggsw_base2k, 0, (int)B);
+                                     (int)ggsw_base2k, 0, (int)B, (const char *)ain.data, ain_bs, n * ain.cols * ain.size);
         }
         PGB_CHECK_CUDA(cudaMemsetAsync(res_dft.data, 0, B * res_dft_bs, m->stream)); // res_dft.zero() (:123)
         pgb_batch btv = {B, res_dft_bs, a_dft_bs, 0};

@@ -15,7 +15,7 @@ int ntt120_inverse_big(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batc
 bool ntt120_fused_supported(const pgb_module *m);
 int ntt120_fused_back(pgb_module *m, const char *a_dft, uint64_t a_bs, const char *pmat, int R, int C, int cols_out, const char *small,
                       uint64_t small_bs, uint64_t small_limb_stride, int small_size, char *res, uint64_t res_bs, uint64_t res_limb_stride,
-                      int res_size, int base2k, int64_t res_offset, int batch);
+                      int res_size, int base2k, int64_t res_offset, int batch, const char *glwe, uint64_t glwe_bs, uint64_t glwe_words);
 // ntt120_ops.cu
 int ntt120_vmp(pgb_module *m, const char *a, uint64_t a_bs, char *res, uint64_t res_bs, const char *pm, uint64_t pm_bs,
                uint32_t row_max, uint32_t C, uint32_t col0, uint32_t ncols_out, uint32_t batch);

@@ -502,7 +502,8 @@ template <int K, int L> __device__ __forceinline__ void fused_top(uint32_t *__re
 // normalisation live in a small L2-resident scratch indexed by CTA (16 B per coefficient), so the kernel fits in 64 registers.
 template <int L> __global__ void __launch_bounds__(Geo<L>::T, 2) ntt120_fused_back_kernel(FusedArgs p, const uint2 *__restrict__ tw,
                                                                                          Ntt120Consts nc, int total_work,
-                                                                                         i128 *__restrict__ carry_scratch) {
+                                                                                         i128 *__restrict__ carry_scratch,
+                                                                                         const int *__restrict__ skip) {
     typedef Geo<L> G;
     static_assert(L > G::R0, "fused path needs at least two passes");
     extern __shared__ __align__(16) uint32_t smem[];
@@ -520,6 +521,7 @@ template <int L> __global__ void __launch_bounds__(Geo<L>::T, 2) ntt120_fused_ba
     for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
         const int col = work % p.cols_out;
         const size_t b = work / p.cols_out;
+        if (skip && skip[b]) continue; // handled by the collapsed-key kernel
         const uint32_t *a = reinterpret_cast<const uint32_t *>(p.a_dft + b * p.a_bs);
         long long *res = reinterpret_cast<long long *>(p.res + b * p.res_bs) + (size_t)col * n;
         const long long *small = (p.small && col == 0) ? reinterpret_cast<const long long *>(p.small + b * p.small_bs) : nullptr;
@@ -589,6 +591,139 @@ template <int L> __global__ void __launch_bounds__(Geo<L>::T, 2) ntt120_fused_ba
                 carry[idx] = nd_get_carry(K, c, out);
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- collapsed-key fast path
+// The S output limbs of a gadget product are the base-2^K digits of ONE integer polynomial
+//     V = sum_j 2^((S-1-j)K) * v_j ,  v_j = sum_r a_r (*) M[r][j]   (negacyclic convolutions over Z)
+// because vec_znx_big_normalize (same base2k, offset 0) is exactly the balanced base-2^K expansion of V
+// (reference/ntt120/vec_znx_big.rs:367-446: out_j = digit(v_j + c_{j+1}), c_j = (v_j + c_{j+1} - out_j) >> K).  By linearity of the
+// NTT, V = sum_r a_r (*) M'[r] with the "collapsed" key M'[r] = sum_j 2^((S-1-j)K) M[r][j] (mod Q, computed in the DFT domain), so
+// ONE inverse transform per output column replaces S of them.  This is bit-identical to the per-limb route iff every v_j and V
+// stay inside (-Q/2, Q/2); that is decided per ciphertext on the device from max|a| and max|key coefficient| (both measured, not
+// assumed), and ciphertexts that fail the bound take the per-limb kernel instead.
+struct CollapseArgs {
+    const char *pmat;
+    char *out;
+    int n4, R, C, cols_out, S;
+    uint32_t c[32][4]; // 2^((S-1-j)K) mod Q[k]
+};
+__global__ void __launch_bounds__(256) ntt120_collapse_key_kernel(CollapseArgs p) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= 4u * p.n4) return;
+    const int k = u / p.n4;
+    const PrimeRt pr(k);
+    const int r = blockIdx.y / p.cols_out, col = blockIdx.y % p.cols_out;
+    const size_t poly = (size_t)4 * p.n4;
+    const uint4 *src = reinterpret_cast<const uint4 *>(p.pmat) + ((size_t)r * p.C + col) * poly + u;
+    unsigned long long acc[4] = {0, 0, 0, 0};
+    for (int j0 = 0; j0 < p.S; j0 += 16) {
+        const int j1 = min(j0 + 16, p.S);
+        for (int j = j0; j < j1; j++) {
+            const uint4 v = __ldg(src + (size_t)j * p.cols_out * poly);
+            const unsigned long long cj = p.c[j][k];
+            acc[0] += v.x * cj; acc[1] += v.y * cj; acc[2] += v.z * cj; acc[3] += v.w * cj;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[i] = pr.reduce(acc[i]);
+    }
+    reinterpret_cast<uint4 *>(p.out)[((size_t)r * p.cols_out + col) * poly + u] =
+        make_uint4((uint32_t)acc[0], (uint32_t)acc[1], (uint32_t)acc[2], (uint32_t)acc[3]);
+}
+
+__device__ __forceinline__ int bitlen_u128(u128 x) {
+    const unsigned long long hi = (unsigned long long)(x >> 64), lo = (unsigned long long)x;
+    return hi ? 128 - __clzll((long long)hi) : (lo ? 64 - __clzll((long long)lo) : 0);
+}
+// bits[0] = max bit length of |x| over `count` i128 values
+__global__ void __launch_bounds__(256) max_bits_i128_kernel(const i128 *__restrict__ x, size_t count, int *__restrict__ bits) {
+    int mx = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        const i128 v = x[i];
+        mx = max(mx, bitlen_u128(v < 0 ? (u128)0 - (u128)v : (u128)v));
+    }
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(bits, mx);
+}
+// per ciphertext: ok[b] = 1 iff the integers behind the collapsed product provably stay below 2^118 in magnitude
+struct GuardArgs {
+    const char *a; uint64_t a_bs; uint64_t words; // i64 words per ciphertext (all columns and limbs of the GLWE)
+    const int *key_bits;
+    int base_bits; // ceil(log2(R * n)) + (S - 1) * K + 3
+    int *ok;
+};
+__global__ void __launch_bounds__(256) ntt120_collapse_guard_kernel(GuardArgs p) {
+    const long long *a = reinterpret_cast<const long long *>(p.a + (size_t)blockIdx.x * p.a_bs);
+    int mx = 0;
+    for (uint64_t i = threadIdx.x; i < p.words; i += blockDim.x) {
+        const long long v = a[i];
+        const unsigned long long m = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+        mx = max(mx, m ? 64 - __clzll((long long)m) : 0);
+    }
+    __shared__ int smx;
+    if (threadIdx.x == 0) smx = 0;
+    __syncthreads();
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(&smx, mx);
+    __syncthreads();
+    if (threadIdx.x == 0) p.ok[blockIdx.x] = (smx + *p.key_bits + p.base_bits <= 118) ? 1 : 0;
+}
+
+template <int L> __global__ void __launch_bounds__(Geo<L>::T, 2) ntt120_collapsed_back_kernel(FusedArgs p, const uint2 *__restrict__ tw,
+                                                                                            Ntt120Consts nc, int total_work,
+                                                                                            const int *__restrict__ ok) {
+    typedef Geo<L> G;
+    extern __shared__ __align__(16) uint32_t smem[];
+    constexpr int n = G::NB;
+    const int t = threadIdx.x;
+    const uint32_t *pm = reinterpret_cast<const uint32_t *>(p.pmat); // collapsed key: [R][cols_out] polys
+    const size_t poly = (size_t)4 * n;
+    const size_t res_ls = p.res_limb_stride / 8, small_ls = p.small_limb_stride / 8;
+    const int K = p.K, S = p.a_size;
+    const size_t m_stride = (size_t)p.cols_out * poly;
+    const u128 M0 = ((u128)c_crt.m_hi[0] << 64) | c_crt.m_lo[0], M1 = ((u128)c_crt.m_hi[1] << 64) | c_crt.m_lo[1];
+    const u128 M2 = ((u128)c_crt.m_hi[2] << 64) | c_crt.m_lo[2], M3 = ((u128)c_crt.m_hi[3] << 64) | c_crt.m_lo[3];
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        const int col = work % p.cols_out;
+        const size_t b = work / p.cols_out;
+        if (!ok[b]) continue; // uniform per CTA: this ciphertext is handled by the per-limb kernel
+        const uint32_t *a = reinterpret_cast<const uint32_t *>(p.a_dft + b * p.a_bs);
+        long long *res = reinterpret_cast<long long *>(p.res + b * p.res_bs) + (size_t)col * n;
+        const long long *small = (p.small && col == 0) ? reinterpret_cast<const long long *>(p.small + b * p.small_bs) : nullptr;
+        const uint32_t *mc = pm + (size_t)col * poly;
+        fused_bottom<0, L>(smem + 0 * G::PLANE, a + 0 * n, poly, mc + 0 * n, m_stride, p.R, tw + 0 * n, t);
+        fused_bottom<1, L>(smem + 1 * G::PLANE, a + 1 * n, poly, mc + 1 * n, m_stride, p.R, tw + 1 * n, t);
+        fused_bottom<2, L>(smem + 2 * G::PLANE, a + 2 * n, poly, mc + 2 * n, m_stride, p.R, tw + 2 * n, t);
+        fused_bottom<3, L>(smem + 3 * G::PLANE, a + 3 * n, poly, mc + 3 * n, m_stride, p.R, tw + 3 * n, t);
+        __syncthreads();
+        InvMid<L, (L - 6 >= G::R0) ? L - 6 : -1>::run(smem, tw, n, t);
+        fused_top<0, L>(smem + 0 * G::PLANE, tw + 0 * n, t, nc);
+        fused_top<1, L>(smem + 1 * G::PLANE, tw + 1 * n, t, nc);
+        fused_top<2, L>(smem + 2 * G::PLANE, tw + 2 * n, t, nc);
+        fused_top<3, L>(smem + 3 * G::PLANE, tw + 3 * n, t, nc);
+#pragma unroll 2
+        for (int jj = 0; jj < 8; jj++) {
+            const int idx = t + jj * G::T;
+            const int pi = PAD(idx);
+            const u128 acc = (u128)smem[pi] * M0 + (u128)smem[G::PLANE + pi] * M1 + (u128)smem[2 * G::PLANE + pi] * M2 +
+                             (u128)smem[3 * G::PLANE + pi] * M3;
+            i128 v = crt_finish(acc);
+            if (small) {
+                for (int j = 0; j < p.small_size; j++)
+                    v = (i128)((u128)v + ((u128)(i128)small[(size_t)j * small_ls + idx] << ((S - 1 - j) * K)));
+            }
+            for (int j = S - 1; j >= 0; j--) { // balanced base-2^K digits, least significant limb first
+                const long long out = ((long long)(unsigned long long)v << (64 - K)) >> (64 - K);
+                v = (i128)((u128)v + ((u128)1 << (K - 1))) >> K;
+                if (j < p.a_start) res[(size_t)(j - p.a_start + p.res_start) * res_ls + idx] = out;
+            }
+        }
+        for (int j = p.res_start; j < p.res_size; j++) {
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) res[(size_t)j * res_ls + t + jj * G::T] = 0;
+        }
+        __syncthreads();
     }
 }
 
@@ -813,7 +948,7 @@ int ntt120_inverse_big(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batc
     NTT_DISPATCH(launch_inv)
 }
 
-template <int L> static int launch_fused(pgb_module *m, const FusedArgs &p, int batch) {
+template <int L> static int launch_fused(pgb_module *m, const FusedArgs &p, int batch, const int *skip) {
     typedef Geo<L> G;
     size_t smem = (size_t)4 * G::PLANE * sizeof(uint32_t);
     static int ctas_per_sm = 0, sms = 0;
@@ -821,25 +956,33 @@ template <int L> static int launch_fused(pgb_module *m, const FusedArgs &p, int 
         PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_fused_back_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_fused_back_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         PGB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, ntt120_fused_back_kernel<L>, G::T, smem));
-        if (getenv("PGB_DEBUG")) fprintf(stderr, "[pgb] fused_back<%d>: %d CTAs/SM, smem %zu\n", L, ctas_per_sm, smem);
         PGB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
     const int total = p.cols_out * batch;
     const int grid = total < sms * ctas_per_sm ? total : sms * ctas_per_sm;
-    const size_t need = (size_t)grid * G::NB * sizeof(i128);
-    if (m->carry_len < need) {
-        if (m->carry_ws) {
-            PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
-            cudaFree(m->carry_ws);
-        }
-        m->carry_ws = nullptr;
-        m->carry_len = 0;
-        PGB_CHECK_CUDA(cudaMalloc(&m->carry_ws, need));
-        m->carry_len = need;
-    }
+    PGB_TRY(ensure_carry_ws(m, (size_t)grid * G::NB * sizeof(i128)));
     { ProfScope _ps(m, PROF_DFT_INV);
-    ntt120_fused_back_kernel<L><<<grid, G::T, smem, m->stream>>>(p, m->ntt_inv, m->nc, total, (i128 *)m->carry_ws);
+    ntt120_fused_back_kernel<L><<<grid, G::T, smem, m->stream>>>(p, m->ntt_inv, m->nc, total, (i128 *)m->carry_ws, skip);
+    }
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+template <int L> static int launch_collapsed(pgb_module *m, const FusedArgs &p, int batch, const int *ok) {
+    typedef Geo<L> G;
+    size_t smem = (size_t)4 * G::PLANE * sizeof(uint32_t);
+    static int ctas_per_sm = 0, sms = 0;
+    if (!ctas_per_sm) {
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_collapsed_back_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_collapsed_back_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        PGB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, ntt120_collapsed_back_kernel<L>, G::T, smem));
+        PGB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    const int total = p.cols_out * batch;
+    const int grid = total < sms * ctas_per_sm ? total : sms * ctas_per_sm;
+    { ProfScope _ps(m, PROF_DFT_INV);
+    ntt120_collapsed_back_kernel<L><<<grid, G::T, smem, m->stream>>>(p, m->ntt_inv, m->nc, total, ok);
     }
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;
@@ -847,10 +990,21 @@ template <int L> static int launch_fused(pgb_module *m, const FusedArgs &p, int 
 
 bool ntt120_fused_supported(const pgb_module *m) { return m->flavour == PGB_NTT120 && m->log_n >= 9 && m->log_n <= 13; }
 
-// res(cols_out, res_size) <- normalize( idft( a_dft(R polys) x pmat[R][C] ) + small on column 0 ), same base2k, offset res_offset
+static uint32_t pow2_mod_q(uint64_t e, uint32_t q) {
+    uint64_t r = 1, b = 2;
+    while (e) {
+        if (e & 1) r = r * b % q;
+        b = b * b % q;
+        e >>= 1;
+    }
+    return (uint32_t)r;
+}
+
+// res(cols_out, res_size) <- normalize( idft( a_dft(R polys) x pmat[R][C] ) + small on column 0 ), same base2k, offset res_offset.
+// `glwe` / `glwe_bs` / `glwe_words`: the i64 input ciphertexts (all columns), used only to bound the integers for the collapsed path.
 int ntt120_fused_back(pgb_module *m, const char *a_dft, uint64_t a_bs, const char *pmat, int R, int C, int cols_out, const char *small,
                       uint64_t small_bs, uint64_t small_limb_stride, int small_size, char *res, uint64_t res_bs, uint64_t res_limb_stride,
-                      int res_size, int base2k, int64_t res_offset, int batch) {
+                      int res_size, int base2k, int64_t res_offset, int batch, const char *glwe, uint64_t glwe_bs, uint64_t glwe_words) {
     FusedArgs p;
     memset(&p, 0, sizeof p);
     p.a_dft = a_dft; p.a_bs = a_bs; p.pmat = pmat; p.small = small; p.small_bs = small_bs; p.small_limb_stride = small_limb_stride;
@@ -868,12 +1022,72 @@ int ntt120_fused_back(pgb_module *m, const char *a_dft, uint64_t a_bs, const cha
     p.res_start = (int)clampi((int64_t)p.a_size - lo, 0, res_size);
     p.a_end = (int)clampi(lo, 0, p.a_size);
     p.a_start = (int)clampi((int64_t)res_size + lo, 0, p.a_size);
+
+    // ---- collapsed-key fast path (see the comment above ntt120_collapse_key_kernel) -------------------------------------------
+    const uint64_t n = m->n, poly_bytes = 16 * n;
+    const int S = p.a_size;
+    const uint64_t key_bytes = (uint64_t)R * C * poly_bytes;
+    const int *ok = nullptr;
+    const bool try_collapse = glwe && res_offset == 0 && S >= 2 && S <= 32 && (int64_t)batch * cols_out >= 64 && key_bytes <= ((uint64_t)64 << 20) &&
+                              (S - 1) * base2k + 3 < 118 && !getenv("PGB_NO_COLLAPSE");
+    if (try_collapse) {
+        // workspace: [collapsed key | key coefficients (i128) | key_bits | ok flags]
+        const uint64_t ck_bytes = (uint64_t)R * cols_out * poly_bytes;
+        const uint64_t need = ck_bytes + key_bytes + 256 + (uint64_t)batch * sizeof(int);
+        if (m->aux_len < need) {
+            if (m->aux_ws) {
+                PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+                cudaFree(m->aux_ws);
+            }
+            m->aux_ws = nullptr;
+            m->aux_len = 0;
+            PGB_CHECK_CUDA(cudaMalloc(&m->aux_ws, need));
+            m->aux_len = need;
+        }
+        char *ck = (char *)m->aux_ws, *kcoef = ck + ck_bytes;
+        int *key_bits = (int *)(kcoef + key_bytes), *okf = key_bits + 64;
+        CollapseArgs ca;
+        memset(&ca, 0, sizeof ca);
+        ca.pmat = pmat; ca.out = ck; ca.n4 = (int)(n / 4); ca.R = R; ca.C = C; ca.cols_out = cols_out; ca.S = S;
+        for (int j = 0; j < S; j++)
+            for (int k = 0; k < 4; k++) ca.c[j][k] = pow2_mod_q((uint64_t)(S - 1 - j) * base2k, qk(k));
+        { ProfScope _ps(m, PROF_OTHER);
+        ntt120_collapse_key_kernel<<<dim3(((unsigned)n + 255) / 256, R * cols_out), 256, 0, m->stream>>>(ca);
+        }
+        PGB_CHECK_CUDA(cudaGetLastError());
+        // exact integer coefficients of every key polynomial (|.| < Q/2), then their largest bit length
+        LimbSet kin = {(char *)pmat, poly_bytes, 0}, kout = {kcoef, poly_bytes, 0};
+        PGB_TRY(ntt120_inverse_big(m, kin, kout, R * C, 1));
+        PGB_CHECK_CUDA(cudaMemsetAsync(key_bits, 0, sizeof(int), m->stream));
+        { ProfScope _ps(m, PROF_OTHER);
+        max_bits_i128_kernel<<<296, 256, 0, m->stream>>>((const i128 *)kcoef, (size_t)R * C * n, key_bits);
+        }
+        PGB_CHECK_CUDA(cudaGetLastError());
+        int rn_bits = 0;
+        while (((uint64_t)1 << rn_bits) < (uint64_t)R * n) rn_bits++;
+        GuardArgs ga = {glwe, glwe_bs, glwe_words, key_bits, rn_bits + (S - 1) * base2k + 3, okf};
+        { ProfScope _ps(m, PROF_OTHER);
+        ntt120_collapse_guard_kernel<<<batch, 256, 0, m->stream>>>(ga);
+        }
+        PGB_CHECK_CUDA(cudaGetLastError());
+        FusedArgs pc = p;
+        pc.pmat = ck;
+        switch (m->log_n) {
+        case 9: PGB_TRY(launch_collapsed<9>(m, pc, batch, okf)); break;
+        case 10: PGB_TRY(launch_collapsed<10>(m, pc, batch, okf)); break;
+        case 11: PGB_TRY(launch_collapsed<11>(m, pc, batch, okf)); break;
+        case 12: PGB_TRY(launch_collapsed<12>(m, pc, batch, okf)); break;
+        case 13: PGB_TRY(launch_collapsed<13>(m, pc, batch, okf)); break;
+        default: pgb_set_error("fused back end: unsupported n"); return PGB_ERR_UNSUPPORTED;
+        }
+        ok = okf; // the per-limb kernel below only processes the ciphertexts that failed the bound
+    }
     switch (m->log_n) {
-    case 9: return launch_fused<9>(m, p, batch);
-    case 10: return launch_fused<10>(m, p, batch);
-    case 11: return launch_fused<11>(m, p, batch);
-    case 12: return launch_fused<12>(m, p, batch);
-    case 13: return launch_fused<13>(m, p, batch);
+    case 9: return launch_fused<9>(m, p, batch, ok);
+    case 10: return launch_fused<10>(m, p, batch, ok);
+    case 11: return launch_fused<11>(m, p, batch, ok);
+    case 12: return launch_fused<12>(m, p, batch, ok);
+    case 13: return launch_fused<13>(m, p, batch, ok);
     default: pgb_set_error("fused back end: unsupported n"); return PGB_ERR_UNSUPPORTED;
     }
 }

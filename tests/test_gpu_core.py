@@ -174,3 +174,52 @@ def test_keyswitch_large_n(fl, n):
     g.sync()
     o.glwe_keyswitch_batch(want, k, a, k, po, k)
     assert np.array_equal(g.vec_znx_to_numpy(res_g), want)
+
+
+@pytest.mark.parametrize("n", [512, 2048])
+def test_collapsed_key_fast_path_and_guard(n):
+    """Batches large enough for the collapsed-key path (one inverse transform per column).  Ciphertexts whose integers could leave
+    (-Q/2, Q/2) -- here: a few with 60-bit 'digits' -- must be routed to the per-limb kernel by the on-device bound, and the whole
+    batch must still equal the oracle bit for bit."""
+    g, o = pb.Module(n, pb.NTT120), O.OracleModule(n, pb.NTT120)
+    rng = np.random.default_rng(1000 + n)
+    k, batch = 18, 48
+    for rank_in, rank_out, a_size, key_size, res_size in ((1, 1, 3, 4, 3), (2, 1, 3, 4, 4), (1, 2, 2, 3, 2), (1, 1, 3, 5, 6)):
+        pg, po = _key(g, o, rng, a_size, rank_in, rank_out + 1, key_size, k)
+        a = fill_uniform(rng, (batch, a_size, rank_in + 1, n), k)
+        a[5] = fill_uniform(rng, a[5].shape, 61)      # fails the bound: per-limb kernel
+        a[17, 0, 0, 3] = -(1 << 62)                   # a single huge body coefficient is enough
+        a[30] = 0                                      # all-zero ciphertext
+        want = fill_uniform(rng, (batch, res_size, rank_out + 1, n), k)
+        res_g = g.vec_znx_from_numpy(want)
+        g.glwe_keyswitch(res_g, k, g.vec_znx_from_numpy(a), k, pg, k)
+        g.sync()
+        o.glwe_keyswitch_batch(want, k, a, k, po, k)
+        got = g.vec_znx_to_numpy(res_g)
+        bad = [b for b in range(batch) if not np.array_equal(got[b], want[b])]
+        assert not bad, (rank_in, rank_out, a_size, key_size, res_size, bad)
+    # external product, and a key with huge entries (bound fails for every ciphertext)
+    for kbits in (k, 62):
+        pg, po = _key(g, o, rng, 3, 2, 2, 3, kbits)
+        a = fill_uniform(rng, (batch, 3, 2, n), k)
+        want = np.zeros((batch, 3, 2, n), dtype=np.int64)
+        res_g = g.vec_znx_alloc(2, 3, batch)
+        g.glwe_external_product(res_g, k, g.vec_znx_from_numpy(a), k, pg, k)
+        g.sync()
+        o.glwe_external_product_batch(want, k, a, k, po, k)
+        assert np.array_equal(g.vec_znx_to_numpy(res_g), want), kbits
+
+
+def test_collapsed_key_wide_base2k():
+    """base2k = 52 (CKKS): the collapsed integer would need > 118 bits, every ciphertext takes the per-limb kernel."""
+    n, k, batch = 1024, 52, 40
+    g, o = pb.Module(n, pb.NTT120), O.OracleModule(n, pb.NTT120)
+    rng = np.random.default_rng(1100)
+    pg, po = _key(g, o, rng, 2, 1, 2, 3, k)
+    a = fill_uniform(rng, (batch, 2, 2, n), k)
+    want = np.zeros((batch, 2, 2, n), dtype=np.int64)
+    res_g = g.vec_znx_alloc(2, 2, batch)
+    g.glwe_keyswitch(res_g, k, g.vec_znx_from_numpy(a), k, pg, k)
+    g.sync()
+    o.glwe_keyswitch_batch(want, k, a, k, po, k)
+    assert np.array_equal(g.vec_znx_to_numpy(res_g), want)
