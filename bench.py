@@ -26,6 +26,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+NCAT = 7  # PGB_PROFILE_NCAT (include/poulpy_b200.h)
 WORK = dict(n=4096, base2k=18, a_size=3, key_size=4, rank=1, dnum=3, dsize=1)
 
 
@@ -229,8 +230,8 @@ def main():
             ev1.record(stream)
         torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
-    prof_ms = (C.c_double * 6)()
-    prof_n = (C.c_uint64 * 6)()
+    prof_ms = (C.c_double * NCAT)()
+    prof_n = (C.c_uint64 * NCAT)()
     lib.pgb_profile_read(m._h, prof_ms, prof_n, 1)
     lib.pgb_profile_enable(m._h, 0)
     launches = m.launch_count - launches0
@@ -274,7 +275,7 @@ def main():
     }
     kernel_names = {"dft_forward": "ntt120_fwd_kernel<12,1>", "dft_inverse": "ntt120_fused_back_kernel<12> (vmp+intt+crt+add_small+normalize)"}
     lib.pgb_profile_category_name.restype = C.c_char_p
-    names = [lib.pgb_profile_category_name(i).decode() for i in range(6)]
+    names = [lib.pgb_profile_category_name(i).decode() for i in range(NCAT)]
     peak, peak_src = peaks()
     kernels = {}
     for i, nm in enumerate(names):

@@ -84,8 +84,9 @@ uint64_t pgb_module_launch_count(const pgb_module *m);
 
 /* Optional per-kernel timing: when enabled every kernel launch is bracketed by CUDA events on the module's stream and the
  * elapsed device time is accumulated per category (0 dft_forward, 1 dft_inverse, 2 vmp_apply, 3 normalize, 4 elementwise,
- * 5 other).  pgb_profile_read synchronises the stream and fills ms[6] / launches[6]. */
-#define PGB_PROFILE_NCAT 6
+ * 5 other, 6 gadget_fused = the single-kernel key-switch / external product).  pgb_profile_read synchronises the stream and
+ * fills ms[PGB_PROFILE_NCAT] / launches[PGB_PROFILE_NCAT]. */
+#define PGB_PROFILE_NCAT 7
 int pgb_profile_enable(pgb_module *m, int on);
 int pgb_profile_read(pgb_module *m, double *ms, uint64_t *launches, int reset);
 const char *pgb_profile_category_name(int category);

@@ -81,7 +81,7 @@ extern "C" int pgb_profile_read(pgb_module *m, double *ms, uint64_t *launches, i
     return PGB_OK;
 }
 extern "C" const char *pgb_profile_category_name(int c) {
-    static const char *names[PROF_NCAT] = {"dft_forward", "dft_inverse", "vmp_apply", "normalize", "elementwise", "other"};
+    static const char *names[PROF_NCAT] = {"dft_forward", "dft_inverse", "vmp_apply", "normalize", "elementwise", "other", "gadget_fused"};
     return (c >= 0 && c < PROF_NCAT) ? names[c] : "?";
 }
 

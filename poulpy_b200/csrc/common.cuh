@@ -61,6 +61,7 @@ struct pgb_module {
     // NTT120: twiddles (w, floor(w*2^32/q)) in block-twiddle (bit-reversed) order, [4][n] each direction
     uint2 *ntt_fwd, *ntt_inv;
     Ntt120Consts nc;
+    uint2 tw_top_f[4][16], tw_top_i[4][16]; // host copy of block twiddles 1..15 per prime (kernel-parameter twiddles of the gadget kernel)
     // FFT64: complex twiddles in block-twiddle order, [m] each direction
     double2 *fft_fwd, *fft_inv;
     // lazily grown device workspace for host front ends
@@ -77,7 +78,7 @@ struct pgb_module {
 };
 
 // kernel categories of the profiler
-enum { PROF_DFT_FWD = 0, PROF_DFT_INV = 1, PROF_VMP = 2, PROF_NORMALIZE = 3, PROF_ELEMENTWISE = 4, PROF_OTHER = 5, PROF_NCAT = 6 };
+enum { PROF_DFT_FWD = 0, PROF_DFT_INV = 1, PROF_VMP = 2, PROF_NORMALIZE = 3, PROF_ELEMENTWISE = 4, PROF_OTHER = 5, PROF_GADGET = 6, PROF_NCAT = 7 };
 void prof_begin(pgb_module *m, int cat);
 void prof_end(pgb_module *m);
 struct ProfScope {

@@ -78,6 +78,7 @@ struct NttJobs {
     LimbSet in, out;
     int jobs_per_batch;
     int total_jobs;
+    const int *skip; // optional, per batch item: non-zero = leave this item alone (forward kernel only)
 };
 
 // ---------------------------------------------------------------------------------------------- forward
@@ -154,8 +155,15 @@ template <int L, int LPC> __global__ void __launch_bounds__(Geo<L>::T *LPC) ntt1
     extern __shared__ __align__(16) uint32_t smem[];
     const int slot = threadIdx.x / G::T, t = threadIdx.x % G::T;
     const int job = blockIdx.x * LPC + slot;
-    const bool active = job < jb.total_jobs;
+    bool active = job < jb.total_jobs;
     const int b = active ? job / jb.jobs_per_batch : 0, j = active ? job % jb.jobs_per_batch : 0;
+    if (jb.skip) {
+        if (LPC == 1) {
+            if (__ldg(jb.skip + b)) return; // CTA-uniform
+        } else {
+            active = active && !__ldg(jb.skip + b);
+        }
+    }
     const long long *gin = reinterpret_cast<const long long *>(jb.in.base + (size_t)b * jb.in.batch_stride + (size_t)j * jb.in.limb_stride);
     uint32_t *gout = reinterpret_cast<uint32_t *>(jb.out.base + (size_t)b * jb.out.batch_stride + (size_t)j * jb.out.limb_stride);
     uint32_t *sm = smem + slot * 4 * G::PLANE;
@@ -756,6 +764,10 @@ int ntt120_module_init(pgb_module *m) {
             uint32_t wi = modpow(psi, 2 * n - E[i], q);
             hf[k * n + i] = make_uint2(w, (uint32_t)(((uint64_t)w << 32) / q));
             hi[k * n + i] = make_uint2(wi, (uint32_t)(((uint64_t)wi << 32) / q));
+            if (i < 16) {
+                m->tw_top_f[k][i] = hf[k * n + i];
+                m->tw_top_i[k][i] = hi[k * n + i];
+            }
         }
         uint32_t ninv = modpow((uint32_t)(n % q), q - 2, q);
         uint32_t c = (uint32_t)((uint64_t)CRT_CST[k] * ninv % q);
@@ -935,14 +947,20 @@ static int ntt120_inverse_large(pgb_module *m, LimbSet in, LimbSet out, int jobs
 
 // in: i64 limbs, out: 16 B/coef DFT limbs
 int ntt120_forward(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch) {
-    NttJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch};
+    NttJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch, nullptr};
     if (jb.total_jobs == 0) return PGB_OK;
     if (m->log_n >= 14) return ntt120_forward_large(m, in, out, jobs_per_batch, batch);
     NTT_DISPATCH(launch_fwd)
 }
+int ntt120_forward_skip(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch, const int *skip) {
+    NttJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch, skip};
+    if (jb.total_jobs == 0) return PGB_OK;
+    PGB_REQUIRE(m->log_n < 14, "ntt120_forward_skip: single-CTA sizes only");
+    NTT_DISPATCH(launch_fwd)
+}
 // in: DFT limbs, out: i128 limbs (may alias `in` limb for limb: in-place consume)
 int ntt120_inverse_big(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch) {
-    NttJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch};
+    NttJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch, nullptr};
     if (jb.total_jobs == 0) return PGB_OK;
     if (m->log_n >= 14) return ntt120_inverse_large(m, in, out, jobs_per_batch, batch);
     NTT_DISPATCH(launch_inv)
@@ -990,6 +1008,19 @@ template <int L> static int launch_collapsed(pgb_module *m, const FusedArgs &p, 
 
 bool ntt120_fused_supported(const pgb_module *m) { return m->flavour == PGB_NTT120 && m->log_n >= 9 && m->log_n <= 13; }
 
+// exact integer coefficients of every key polynomial (|.| < Q/2, inverse NTT + CRT), then their largest bit length
+int ntt120_key_max_bits(pgb_module *m, const char *pmat, int polys, char *coef_ws, int *bits_dev) {
+    const uint64_t poly_bytes = 16 * m->n;
+    LimbSet kin = {(char *)pmat, poly_bytes, 0}, kout = {coef_ws, poly_bytes, 0};
+    PGB_TRY(ntt120_inverse_big(m, kin, kout, polys, 1));
+    PGB_CHECK_CUDA(cudaMemsetAsync(bits_dev, 0, sizeof(int), m->stream));
+    { ProfScope _ps(m, PROF_OTHER);
+    max_bits_i128_kernel<<<296, 256, 0, m->stream>>>((const i128 *)coef_ws, (size_t)polys * m->n, bits_dev);
+    }
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+
 static uint32_t pow2_mod_q(uint64_t e, uint32_t q) {
     uint64_t r = 1, b = 2;
     while (e) {
@@ -1004,7 +1035,8 @@ static uint32_t pow2_mod_q(uint64_t e, uint32_t q) {
 // `glwe` / `glwe_bs` / `glwe_words`: the i64 input ciphertexts (all columns), used only to bound the integers for the collapsed path.
 int ntt120_fused_back(pgb_module *m, const char *a_dft, uint64_t a_bs, const char *pmat, int R, int C, int cols_out, const char *small,
                       uint64_t small_bs, uint64_t small_limb_stride, int small_size, char *res, uint64_t res_bs, uint64_t res_limb_stride,
-                      int res_size, int base2k, int64_t res_offset, int batch, const char *glwe, uint64_t glwe_bs, uint64_t glwe_words) {
+                      int res_size, int base2k, int64_t res_offset, int batch, const char *glwe, uint64_t glwe_bs, uint64_t glwe_words,
+                      const int *skip) {
     FusedArgs p;
     memset(&p, 0, sizeof p);
     p.a_dft = a_dft; p.a_bs = a_bs; p.pmat = pmat; p.small = small; p.small_bs = small_bs; p.small_limb_stride = small_limb_stride;
@@ -1027,8 +1059,8 @@ int ntt120_fused_back(pgb_module *m, const char *a_dft, uint64_t a_bs, const cha
     const uint64_t n = m->n, poly_bytes = 16 * n;
     const int S = p.a_size;
     const uint64_t key_bytes = (uint64_t)R * C * poly_bytes;
-    const int *ok = nullptr;
-    const bool try_collapse = glwe && res_offset == 0 && S >= 2 && S <= 32 && (int64_t)batch * cols_out >= 64 && key_bytes <= ((uint64_t)64 << 20) &&
+    const int *ok = skip;
+    const bool try_collapse = glwe && !skip && res_offset == 0 && S >= 2 && S <= 32 && (int64_t)batch * cols_out >= 64 && key_bytes <= ((uint64_t)64 << 20) &&
                               (S - 1) * base2k + 3 < 118 && !getenv("PGB_NO_COLLAPSE");
     if (try_collapse) {
         // workspace: [collapsed key | key coefficients (i128) | key_bits | ok flags]
@@ -1055,14 +1087,7 @@ int ntt120_fused_back(pgb_module *m, const char *a_dft, uint64_t a_bs, const cha
         ntt120_collapse_key_kernel<<<dim3(((unsigned)n + 255) / 256, R * cols_out), 256, 0, m->stream>>>(ca);
         }
         PGB_CHECK_CUDA(cudaGetLastError());
-        // exact integer coefficients of every key polynomial (|.| < Q/2), then their largest bit length
-        LimbSet kin = {(char *)pmat, poly_bytes, 0}, kout = {kcoef, poly_bytes, 0};
-        PGB_TRY(ntt120_inverse_big(m, kin, kout, R * C, 1));
-        PGB_CHECK_CUDA(cudaMemsetAsync(key_bits, 0, sizeof(int), m->stream));
-        { ProfScope _ps(m, PROF_OTHER);
-        max_bits_i128_kernel<<<296, 256, 0, m->stream>>>((const i128 *)kcoef, (size_t)R * C * n, key_bits);
-        }
-        PGB_CHECK_CUDA(cudaGetLastError());
+        PGB_TRY(ntt120_key_max_bits(m, pmat, R * C, kcoef, key_bits));
         int rn_bits = 0;
         while (((uint64_t)1 << rn_bits) < (uint64_t)R * n) rn_bits++;
         GuardArgs ga = {glwe, glwe_bs, glwe_words, key_bits, rn_bits + (S - 1) * base2k + 3, okf};

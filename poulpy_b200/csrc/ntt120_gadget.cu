@@ -1,0 +1,690 @@
+// ntt120_gadget.cu -- the whole gadget product (GLWE key-switch / GGSW x GLWE external product, dsize = 1, same base2k) of the
+// NTT120 flavour as ONE persistent kernel: i64 GLWE in -> i64 GLWE out, nothing else touches HBM.
+//
+// Restates, per ciphertext, the HAL sequence of poulpy-core/src/keyswitching/glwe.rs:207-239,106-108 and
+// external_product/glwe.rs:197-271,138-140:
+//     vec_znx_dft_apply (R limbs) -> vmp_apply_dft_to_dft -> vec_znx_idft_apply_consume -> vec_znx_big_add_small_assign
+//     -> vec_znx_big_normalize (same base2k, offset 0)
+// using the collapsed key of ntt120_dft.cu (one inverse transform per output column; bit-identical to the per-limb route whenever
+// the integers stay below 2^118, which is decided per ciphertext on the device -- the others are flagged for the per-limb kernels).
+//
+// B200 mapping: a thread-block CLUSTER of four CTAs owns one ciphertext, CTA k works modulo Q[k] (primes.rs:80-90):
+//   * max(R, cols_out) polynomials live in swizzled (unpadded) shared memory, 16 coefficients per thread;
+//   * radix-16 register passes (four butterfly levels per shared-memory round trip), Shoup multiplication, Harvey lazy ranges;
+//   * the R forward transforms run in lock step so that the per-thread twiddles are fetched once per pass;
+//   * the first pass' 15 twiddles are CTA-uniform and come from the kernel parameter bank;
+//   * products with the collapsed key accumulate in u64 and are reduced once;
+//   * CRT needs all four residues of a coefficient: CTA k reconstructs the k-th quarter of the coefficients and reads the other
+//     three residues from its peers through distributed shared memory (ld.shared::cluster), then emits the base-2^K digits.
+// Four independent CTAs (of different clusters) share an SM, so global loads, barriers and the CRT tail of one ciphertext overlap
+// with the butterflies of another.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
+#include "internal.h"
+#include "ntt120.cuh"
+
+namespace cg = cooperative_groups;
+using namespace n120;
+
+namespace {
+
+struct TopTw {
+    uint2 f[16], i[16]; // block twiddles 1..15 of one prime, forward / inverse (index 0 unused)
+};
+
+struct GadgetArgs {
+    const char *in;  unsigned long long in_bs;      // GLWE inputs (i64), limb (j, col) at ((j * in_cols + col) * n) words
+    char *res;       unsigned long long res_bs;     // GLWE outputs (i64), limb (j, col) at ((j * cols_out + col) * n) words
+    const uint32_t *ckey;                           // collapsed key [r][col][k][chunk 0..3][t][4 words]
+    const int *key_bits;                            // device: max bit length of the key's integer coefficients
+    int *ok;                                        // out, per ciphertext: 1 = done here, 0 = needs the per-limb route
+    int in_cols, row_cols, row_col0, R, cols_out;
+    int small_size;                                 // limbs of input column 0 added to output column 0 (key-switch), 0 = none
+    int K, S, res_size;                             // base2k, key size (digits of the collapsed integer), output limbs
+    int base_bits;                                  // ceil(log2(R * n)) + (S - 1) * K + 3
+    int batch;
+    uint32_t zero;                                  // always 0 (see ct_bfz)
+    uint32_t m_w[4][4];                             // M_k = Q / Q[k], four 32-bit words each (arithmetic.rs:119-140)
+    uint32_t nq_w[4];                               // 2^128 - Q
+    unsigned long long half_lo, half_hi;            // sum_j 2^(K-1) 2^(jK), j < S (mod 2^128)
+    uint32_t inv60[4];                              // floor(2^60 / Q[k]) (31 bits)
+    uint32_t crt_ninv[4], crt_ninv_sh[4];           // CRT_CST[k] / n mod Q[k] and its Shoup companion
+    TopTw top[4];
+    struct { uint32_t q, c32, c32s, neg64; } prime[4];
+};
+
+template <int L> struct GGeo {
+    static constexpr int N = 1 << L;
+    static constexpr int T = N / 16;
+    // pass p covers butterfly levels [LV + 4 - NLEV, LV + 4); in-group stride 2^SG
+    static constexpr int LV2 = (L >= 12) ? 4 : (L == 11 ? 4 : 3);
+    static constexpr int NL2 = (L >= 11) ? 4 : 3;
+    static constexpr int LV3 = L - 4;
+    static constexpr int NL3 = L - (LV2 + 4) ;  // levels left for the last pass
+    static constexpr int SG2 = L - LV2 - 4;     // log2 stride of pass 2
+    static constexpr bool SIG3 = SG2 == 3;
+    static constexpr int MINB = 768 / T; // resident CTAs per SM the register budget is sized for (<= 85 registers)
+};
+
+// conflict-free XOR swizzle of a word index for the three access patterns (stride T scalar, stride 2^SG2 scalar, 16 consecutive
+// words as four 128-bit accesses); only bits >= 2 change, so aligned quads stay contiguous
+template <int L> __device__ __forceinline__ int swz(int i) {
+    int r = i ^ (((i >> 5) & 3) << 2);
+    if (GGeo<L>::SIG3) r ^= ((i >> 7) & 3) << 3;
+    else r ^= ((i >> 8) & 1) << 4;
+    return r;
+}
+
+// Butterflies as in ntt120.cuh, with one twist: `z` is a kernel parameter that is always 0 but unknown to the compiler.  ptxas turns
+// two-input integer adds into IMAD.IADD on the FMA-heavy pipe, which the three IMADs of the Shoup product already saturate inside the
+// butterfly sections; a three-input add can only be an IADD3 on the ALU pipe.
+__device__ __forceinline__ void ct_bfz(uint32_t &x, uint32_t &y, uint2 w, uint32_t q, uint32_t z) {
+    const uint32_t xr = csub(x, 2 * q);
+    const uint32_t t = mul_shoup(y, w.x, w.y, q);
+    x = xr + t + z;
+    y = xr - t + 2 * q;
+}
+__device__ __forceinline__ void gs_bfz(uint32_t &x, uint32_t &y, uint2 w, uint32_t q, uint32_t z) {
+    const uint32_t s = csub(x + y + z, 2 * q);
+    const uint32_t d = x - y + 2 * q;
+    x = s;
+    y = mul_shoup(d, w.x, w.y, q);
+}
+
+// ---- 16-point butterfly networks; level j of the network has distance 8 >> j; NLEV < 4 skips the first 4 - NLEV levels ------------
+template <int NLEV, class TW> __device__ __forceinline__ void ct16(uint32_t (&x)[16], const TW &tw, const uint32_t q, const uint32_t z) {
+    if (NLEV >= 4) {
+        const uint2 w = tw.get1();
+#pragma unroll
+        for (int j = 0; j < 8; j++) ct_bfz(x[j], x[j + 8], w, q, z);
+    }
+    if (NLEV >= 3) {
+        uint2 w[2];
+        tw.get2(w);
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) ct_bfz(x[8 * b + j], x[8 * b + j + 4], w[b], q, z);
+    }
+    if (NLEV >= 2) {
+        uint2 w[4];
+        tw.get4(w);
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) ct_bfz(x[4 * b + j], x[4 * b + j + 2], w[b], q, z);
+    }
+    {
+        uint2 w[8];
+        tw.get8(w);
+#pragma unroll
+        for (int b = 0; b < 8; b++) ct_bfz(x[2 * b], x[2 * b + 1], w[b], q, z);
+    }
+}
+template <int NLEV, class TW> __device__ __forceinline__ void gs16(uint32_t (&x)[16], const TW &tw, const uint32_t q, const uint32_t z) {
+    {
+        uint2 w[8];
+        tw.get8(w);
+#pragma unroll
+        for (int b = 0; b < 8; b++) gs_bfz(x[2 * b], x[2 * b + 1], w[b], q, z);
+    }
+    if (NLEV >= 2) {
+        uint2 w[4];
+        tw.get4(w);
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) gs_bfz(x[4 * b + j], x[4 * b + j + 2], w[b], q, z);
+    }
+    if (NLEV >= 3) {
+        uint2 w[2];
+        tw.get2(w);
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) gs_bfz(x[8 * b + j], x[8 * b + j + 4], w[b], q, z);
+    }
+    if (NLEV >= 4) {
+        const uint2 w = tw.get1();
+#pragma unroll
+        for (int j = 0; j < 8; j++) gs_bfz(x[j], x[j + 8], w, q, z);
+    }
+}
+
+// twiddles of tree node `hi` and its descendants from the [n] table of one prime (block-twiddle order, ntt120_dft.cu)
+struct TwGlobal {
+    const uint2 *tw;
+    uint32_t hi;
+    __device__ __forceinline__ uint2 get1() const { return __ldg(tw + hi); }
+    __device__ __forceinline__ void get2(uint2 (&w)[2]) const {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(tw + 2 * hi));
+        w[0] = make_uint2(a.x, a.y); w[1] = make_uint2(a.z, a.w);
+    }
+    __device__ __forceinline__ void get4(uint2 (&w)[4]) const {
+        const uint4 *p = reinterpret_cast<const uint4 *>(tw + 4 * hi);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const uint4 a = __ldg(p + i);
+            w[2 * i] = make_uint2(a.x, a.y); w[2 * i + 1] = make_uint2(a.z, a.w);
+        }
+    }
+    __device__ __forceinline__ void get8(uint2 (&w)[8]) const {
+        const uint4 *p = reinterpret_cast<const uint4 *>(tw + 8 * hi);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint4 a = __ldg(p + i);
+            w[2 * i] = make_uint2(a.x, a.y); w[2 * i + 1] = make_uint2(a.z, a.w);
+        }
+    }
+};
+// the 15 CTA-uniform twiddles of the top pass, straight from the kernel parameter bank
+struct TwTopConst {
+    const uint2 *w; // 16 entries, node indices 1..15
+    __device__ __forceinline__ uint2 get1() const { return w[1]; }
+    __device__ __forceinline__ void get2(uint2 (&o)[2]) const { o[0] = w[2]; o[1] = w[3]; }
+    __device__ __forceinline__ void get4(uint2 (&o)[4]) const {
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = w[4 + i];
+    }
+    __device__ __forceinline__ void get8(uint2 (&o)[8]) const {
+#pragma unroll
+        for (int i = 0; i < 8; i++) o[i] = w[8 + i];
+    }
+};
+
+// L2 prefetch of a contiguous global range by one thread (TMA bulk prefetch; bytes must be a multiple of 16)
+__device__ __forceinline__ void prefetch_l2_bulk(const void *gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+// Cluster barrier halves.  Only shared memory is exchanged between the CTAs of a cluster (ld.shared::cluster), never global data, so
+// the default release/acquire forms -- which ptxas implements as MEMBAR.ALL.GPU + an L1 invalidation (CCTL.IVALL) that also throws
+// away the cached twiddles -- are replaced by a CTA-scope fence (orders this thread's st.shared) followed by the relaxed arrive.
+#ifdef PGB_CLUSTER_BARRIER_DEFAULT
+__device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
+#else
+__device__ __forceinline__ void cl_arrive() {
+    asm volatile("fence.acq_rel.cta;" ::: "memory");
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cl_wait() {
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
+#endif
+
+__device__ __forceinline__ uint32_t ld_cluster(uint32_t cluster_smem_addr) {
+    uint32_t v;
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(cluster_smem_addr));
+    return v;
+}
+
+// one pass over a plane: element j of thread t sits at word (a << (SG + 4)) | b + (j << SG), a = t >> SG, b = t & (2^SG - 1)
+template <int L, int SG> __device__ __forceinline__ int pass_base(int t) {
+    const int a = t >> SG, b = t & ((1 << SG) - 1);
+    return (a << (SG + 4)) | b;
+}
+
+// i64 -> residue in [0, 3q) for a run-time prime (same steps as n120::from_i64<K>)
+struct PrimeCtx {
+    uint32_t q, c32, c32s, neg64; // q, 2^32 mod q, its Shoup companion, q - (2^64 mod q)
+};
+__device__ __forceinline__ uint32_t from_i64_rt(long long v, const PrimeCtx &pc) {
+    const uint32_t uh = (uint32_t)((unsigned long long)v >> 32), ul = (uint32_t)v;
+    uint32_t r = csub(mul_shoup(uh, pc.c32, pc.c32s, pc.q) + (ul - (ul >> 30) * pc.q), 2 * pc.q);
+    if (v < 0) r += pc.neg64;
+    return r;
+}
+
+// compile-time part of the swizzle of a word offset whose bits do not overlap the thread's own index bits
+template <int L> __host__ __device__ constexpr int fmask(int i) {
+    return (((i >> 5) & 3) << 2) ^ (GGeo<L>::SIG3 ? (((i >> 7) & 3) << 3) : (((i >> 8) & 1) << 4));
+}
+
+template <int L> __device__ __forceinline__ void gadget_body(const GadgetArgs &p, uint32_t *__restrict__ sm, const uint2 *__restrict__ twf,
+                                                             const uint2 *__restrict__ twi, const int K) {
+    typedef GGeo<L> G;
+    constexpr int n = G::N, T = G::T;
+    const PrimeCtx pc = {p.prime[K].q, p.prime[K].c32, p.prime[K].c32s, p.prime[K].neg64};
+    const uint32_t q = pc.q, z = p.zero;
+    const int t = threadIdx.x;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int nclusters = gridDim.x / 4, cid = blockIdx.x / 4;
+    const TwGlobal top_f = {twf, 1u}, top_i = {twi, 1u}; // CTA-uniform addresses: one L1 broadcast per load
+    const int R = p.R, cols_out = p.cols_out;
+    const int amax_allowed = 118 - p.base_bits - __ldg(p.key_bits) - 1; // see ntt120_dft.cu (collapsed-key bound), one spare bit
+    const uint32_t sm_base = (uint32_t)__cvta_generic_to_shared(sm);
+    uint32_t rb[4]; // shared::cluster addresses of the four CTAs' plane 0
+#pragma unroll
+    for (int k = 0; k < 4; k++) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb[k]) : "r"(sm_base), "r"(k));
+    // swizzled word addresses: stride-T pattern = (st ^ const) + j*T, 16-consecutive pattern = qa[c], stride-2^SG2 pattern = sb ^ const
+    const int st = swz<L>(t);
+    const int sb = swz<L>(pass_base<L, G::SG2>(t));
+    int qa[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) qa[c] = swz<L>(16 * t + 4 * c);
+#define P1_ADDR(j) ((st ^ fmask<L>((j) * T)) + (j) * T)
+#define P2_ADDR(j) (sb ^ swz<L>((j) << G::SG2))
+
+    for (int ct = cid; ct < p.batch; ct += nclusters) {
+        const long long *in = reinterpret_cast<const long long *>(p.in + (size_t)ct * p.in_bs);
+        // L2 prefetch (one thread per 8n-byte limb, spread over the four CTAs): the body limbs this ciphertext needs in its CRT phase and
+        // the mask limbs of the cluster's next ciphertext
+        if ((t & 3) == K && (t >> 2) < R + p.small_size) {
+            const int u = t >> 2;
+            if (u < p.small_size) {
+                prefetch_l2_bulk(in + (size_t)u * p.in_cols * n, n * 8);
+            } else if (ct + nclusters < p.batch) {
+                const int r = u - p.small_size, limb = r / p.row_cols, col = r % p.row_cols + p.row_col0;
+                prefetch_l2_bulk(in + (size_t)nclusters * (p.in_bs / 8) + ((size_t)limb * p.in_cols + col) * n, n * 8);
+            }
+        }
+        // ---- forward pass 1 (levels 0..3, stride T) fused with the i64 load and the magnitude scan -------------------------------
+        uint32_t mag = 0;       // OR of |v|-like patterns of the values that fit 32 bits
+        bool too_big = false;
+        for (int r = 0; r < R; r++) {
+            const int limb = r / p.row_cols, col = r % p.row_cols + p.row_col0;
+            const long long *src = in + ((size_t)limb * p.in_cols + col) * n + t;
+            long long v[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[j] = __ldg(src + j * T);
+            uint32_t x[16];
+            uint32_t wide = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int lo = (int)v[j], hi = (int)(v[j] >> 32), sg = lo >> 31;
+                wide |= (uint32_t)(hi ^ sg);
+                mag |= (uint32_t)(lo ^ sg);
+                x[j] = (uint32_t)lo + ((uint32_t)sg & (3u * q)); // [0, 3q) when v fits 32 bits (3q > 2^31)
+            }
+            if (__any_sync(0xffffffffu, wide != 0)) { // rare: digits beyond 32 bits, full-range conversion and magnitude
+                unsigned long long m64 = 0;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    m64 |= (unsigned long long)(v[j] ^ (v[j] >> 63));
+                    x[j] = from_i64_rt(v[j], pc);
+                }
+                too_big |= amax_allowed < 0 || (m64 >> (amax_allowed > 63 ? 63 : amax_allowed)) != 0;
+            }
+            ct16<4>(x, top_f, q, z);
+            if (r == 0) cl_wait(); // peers have finished reading my planes (CRT of the previous ciphertext)
+            uint32_t *pl = sm + r * n;
+#pragma unroll
+            for (int j = 0; j < 16; j++) pl[P1_ADDR(j)] = x[j];
+        }
+        too_big |= amax_allowed < 0 || (amax_allowed < 32 && (mag >> amax_allowed) != 0);
+        const int bad = __syncthreads_or(too_big);
+        if (bad) { // identical decision in all four CTAs (same inputs): this ciphertext takes the per-limb kernels
+            if (t == 0 && K == 0) p.ok[ct] = 0;
+            cl_arrive();
+            continue;
+        }
+        // ---- forward pass 2 ---------------------------------------------------------------------------------------------------
+        {
+            const TwGlobal tw = {twf, (1u << G::LV2) | (uint32_t)(t >> G::SG2)};
+            for (int r = 0; r < R; r++) {
+                uint32_t *pl = sm + r * n;
+                uint32_t x[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) x[j] = pl[P2_ADDR(j)];
+                ct16<G::NL2>(x, tw, q, z);
+#pragma unroll
+                for (int j = 0; j < 16; j++) pl[P2_ADDR(j)] = x[j];
+            }
+        }
+        __syncthreads();
+        // ---- forward pass 3 (16 consecutive words per thread), results reduced to [0, 2q) ------------------------------------------
+        {
+            const TwGlobal tw = {twf, (1u << G::LV3) | (uint32_t)t};
+            for (int r = 0; r < R; r++) {
+                uint32_t *pl = sm + r * n;
+                uint32_t x[16];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(pl + qa[c]);
+                    x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+                }
+                ct16<G::NL3>(x, tw, q, z);
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    *reinterpret_cast<uint4 *>(pl + qa[c]) = make_uint4(csub(x[4 * c], 2 * q), csub(x[4 * c + 1], 2 * q),
+                                                                        csub(x[4 * c + 2], 2 * q), csub(x[4 * c + 3], 2 * q));
+            }
+        }
+        // ---- products with the collapsed key (thread-private words: no barrier) ---------------------------------------------------
+        {
+            const uint32_t c32 = pc.c32, c32s = pc.c32s;
+            const uint4 *ck = reinterpret_cast<const uint4 *>(p.ckey) + (size_t)K * (n / 4) + t;
+            const size_t col_stride = (size_t)4 * (n / 4), row_stride = col_stride * cols_out; // in uint4
+#define MAC_CHUNKS(RLOOP)                                                                                                   \
+    _Pragma("unroll 1") for (int c = 0; c < 4; c++) {                                                                       \
+        unsigned long long acc[4][4]; /* up to four output columns */                                                       \
+        _Pragma("unroll") for (int o = 0; o < 4; o++) _Pragma("unroll") for (int i = 0; i < 4; i++) acc[o][i] = 0;          \
+        RLOOP {                                                                                                             \
+            const uint4 a = *reinterpret_cast<const uint4 *>(sm + r * n + qa[c]);                                           \
+            _Pragma("unroll") for (int o = 0; o < 4; o++) {                                                                 \
+                if (o < cols_out) {                                                                                         \
+                    const uint4 m = __ldg(ck + (size_t)r * row_stride + (size_t)o * col_stride + (size_t)c * T);            \
+                    acc[o][0] += (unsigned long long)a.x * m.x; acc[o][1] += (unsigned long long)a.y * m.y;                 \
+                    acc[o][2] += (unsigned long long)a.z * m.z; acc[o][3] += (unsigned long long)a.w * m.w;                 \
+                }                                                                                                           \
+            }                                                                                                               \
+        }                                                                                                                   \
+        _Pragma("unroll") for (int o = 0; o < 4; o++) {                                                                     \
+            if (o < cols_out) {                                                                                             \
+                uint32_t y[4];                                                                                              \
+                _Pragma("unroll") for (int i = 0; i < 4; i++) {                                                             \
+                    const uint32_t hi = (uint32_t)(acc[o][i] >> 32), lo = (uint32_t)acc[o][i];                              \
+                    y[i] = csub(mul_shoup(hi, c32, c32s, q) + (lo - (lo >> 30) * q), 2 * q);                                \
+                }                                                                                                           \
+                *reinterpret_cast<uint4 *>(sm + o * n + qa[c]) = make_uint4(y[0], y[1], y[2], y[3]);                        \
+            }                                                                                                               \
+        }                                                                                                                   \
+    }
+            if (R == 3) { // the bench shapes get all their loads in flight before the first multiply
+                MAC_CHUNKS(_Pragma("unroll") for (int r = 0; r < 3; r++))
+            } else if (R == 6) {
+                MAC_CHUNKS(_Pragma("unroll") for (int r = 0; r < 6; r++))
+            } else {
+                MAC_CHUNKS(for (int r = 0; r < R; r++))
+            }
+#undef MAC_CHUNKS
+        }
+        // ---- inverse pass 1 (levels L-1 .. L-NL3, 16 consecutive words) --------------------------------------------------------------
+        {
+            const TwGlobal tw = {twi, (1u << G::LV3) | (uint32_t)t};
+            for (int o = 0; o < cols_out; o++) {
+                uint32_t *pl = sm + o * n;
+                uint32_t x[16];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(pl + qa[c]);
+                    x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+                }
+                gs16<G::NL3>(x, tw, q, z);
+#pragma unroll
+                for (int c = 0; c < 4; c++) *reinterpret_cast<uint4 *>(pl + qa[c]) = make_uint4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+            }
+        }
+        __syncthreads();
+        // ---- inverse pass 2 ---------------------------------------------------------------------------------------------------
+        {
+            const TwGlobal tw = {twi, (1u << G::LV2) | (uint32_t)(t >> G::SG2)};
+            for (int o = 0; o < cols_out; o++) {
+                uint32_t *pl = sm + o * n;
+                uint32_t x[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) x[j] = pl[P2_ADDR(j)];
+                gs16<G::NL2>(x, tw, q, z);
+#pragma unroll
+                for (int j = 0; j < 16; j++) pl[P2_ADDR(j)] = x[j];
+            }
+        }
+        __syncthreads();
+        // ---- inverse pass 3 (levels 3..0, stride T), scale by CRT_k / n, canonical residues back to the plane ----------------------
+        {
+            const uint32_t cn = p.crt_ninv[K], cns = p.crt_ninv_sh[K];
+            for (int o = 0; o < cols_out; o++) {
+                uint32_t *pl = sm + o * n;
+                uint32_t x[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) x[j] = pl[P1_ADDR(j)];
+                gs16<4>(x, top_i, q, z);
+#pragma unroll
+                for (int j = 0; j < 16; j++) pl[P1_ADDR(j)] = csub(mul_shoup(x[j], cn, cns, q), q);
+            }
+        }
+        cl_arrive();
+        cl_wait(); // all four residues of every coefficient are in place
+        // ---- CRT + digits for coefficient quarter K ----------------------------------------------------------------------------
+        {
+            const int Kb = p.K, S = p.S;
+            const int a_start = p.res_size < S ? p.res_size : S; // digits j >= a_start are discarded (carry only)
+            const size_t res_ls = (size_t)cols_out * n, in_ls = (size_t)p.in_cols * n;
+            const bool four_words = S * Kb > 96;
+            const unsigned long long kmask = (1ull << Kb) - 1, khalf = 1ull << (Kb - 1);
+            for (int o = 0; o < cols_out; o++) {
+                const bool with_small = o == 0 && p.small_size > 0;
+#pragma unroll 1
+                for (int i = 0; i < 4; i++) {
+                    const int idx = K * (n / 4) + i * T + t;
+                    // body limbs that join column 0 (vec_znx_big_add_small_assign), most significant processed last: sm4[s] belongs
+                    // to digit step s (limb S-1-s); issued first so that their latency hides behind the CRT arithmetic
+                    long long sm4[4] = {0, 0, 0, 0};
+                    if (with_small) {
+#pragma unroll
+                        for (int s4 = 0; s4 < 4; s4++)
+                            if (S - 1 - s4 >= 0 && S - 1 - s4 < p.small_size) sm4[s4] = __ldg(in + (size_t)(S - 1 - s4) * in_ls + idx);
+                    }
+                    const uint32_t off = (uint32_t)(o * n + (swz<L>(K * (n / 4) + i * T) ^ st)) * 4u;
+                    const uint32_t t0 = ld_cluster(rb[0] + off), t1 = ld_cluster(rb[1] + off), t2 = ld_cluster(rb[2] + off), t3 = ld_cluster(rb[3] + off);
+                    // v = sum t_k M_k - e Q with e = round(sum t_k / Q[k]); |v| < 2^118 < Q/4 here, so a 2^-28-accurate estimate of
+                    // the fraction (60 fractional bits, truncated constants) always rounds to the right integer.  Only the low
+                    // S*K <= 128 bits of v matter for the digits: column sums of 32-bit words, -e Q folded in as + e (2^128 - Q).
+                    const unsigned long long fr = (unsigned long long)t0 * p.inv60[0] + (unsigned long long)t1 * p.inv60[1] +
+                                                  (unsigned long long)t2 * p.inv60[2] + (unsigned long long)t3 * p.inv60[3];
+                    const uint32_t e = (uint32_t)((fr + (1ull << 59)) >> 60);
+                    const unsigned long long a0 = (unsigned long long)t0 * p.m_w[0][0] + (unsigned long long)t1 * p.m_w[1][0] +
+                                                  (unsigned long long)t2 * p.m_w[2][0] + (unsigned long long)t3 * p.m_w[3][0] + (unsigned long long)e * p.nq_w[0];
+                    const unsigned long long a1 = (a0 >> 32) + (unsigned long long)t0 * p.m_w[0][1] + (unsigned long long)t1 * p.m_w[1][1] +
+                                                  (unsigned long long)t2 * p.m_w[2][1] + (unsigned long long)t3 * p.m_w[3][1] + (unsigned long long)e * p.nq_w[1];
+                    const unsigned long long a2 = (a1 >> 32) + (unsigned long long)t0 * p.m_w[0][2] + (unsigned long long)t1 * p.m_w[1][2] +
+                                                  (unsigned long long)t2 * p.m_w[2][2] + (unsigned long long)t3 * p.m_w[3][2] + (unsigned long long)e * p.nq_w[2];
+                    unsigned long long lo64 = (a0 & 0xffffffffull) | (a1 << 32), hi64 = a2 & 0xffffffffull;
+                    if (four_words) {
+                        const unsigned long long a3 = (a2 >> 32) + (unsigned long long)t0 * p.m_w[0][3] + (unsigned long long)t1 * p.m_w[1][3] +
+                                                      (unsigned long long)t2 * p.m_w[2][3] + (unsigned long long)t3 * p.m_w[3][3] +
+                                                      (unsigned long long)e * p.nq_w[3];
+                        hi64 |= a3 << 32;
+                    }
+                    // balanced digits of v = unsigned K-bit fields of u = v + sum_j 2^(K-1) 2^(jK), each minus 2^(K-1)
+                    lo64 += p.half_lo;
+                    hi64 += p.half_hi + (lo64 < p.half_lo ? 1ull : 0ull);
+                    long long *out_p = reinterpret_cast<long long *>(p.res + (size_t)ct * p.res_bs) + (size_t)(S - 1) * res_ls + (size_t)o * n + idx;
+                    long long carry = 0;
+                    // one digit step: limb j = S - 1 - s; the value is shifted right by K afterwards (K in [2, 62])
+#define DIGIT_STEP(SMALL_EXPR)                                                                                             \
+    {                                                                                                                      \
+        const long long d = (long long)(lo64 & kmask) - (long long)khalf;                                                  \
+        long long outv = d;                                                                                                \
+        if (with_small) {                                                                                                  \
+            /* small = sh 2^K + sl; r = sl + d + carry cannot overflow; carry' = sh + ((r - out) >> K) */                  \
+            const long long sv = (SMALL_EXPR);                                                                             \
+            const long long r = (long long)((unsigned long long)sv & kmask) + d + carry;                                   \
+            outv = (long long)((unsigned long long)r << (64 - Kb)) >> (64 - Kb);                                           \
+            carry = (sv >> Kb) + ((r - outv) >> Kb);                                                                       \
+        }                                                                                                                  \
+        if (j < a_start) *out_p = outv;                                                                                    \
+        out_p -= res_ls;                                                                                                   \
+        lo64 = (lo64 >> Kb) | (hi64 << (64 - Kb));                                                                         \
+        hi64 >>= Kb;                                                                                                       \
+    }
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; s4++) {
+                        const int j = S - 1 - s4;
+                        if (j >= 0) DIGIT_STEP(sm4[s4])
+                    }
+                    for (int j = S - 5; j >= 0; j--) DIGIT_STEP(j < p.small_size ? __ldg(in + (size_t)j * in_ls + idx) : 0ll)
+#undef DIGIT_STEP
+                    long long *zp = reinterpret_cast<long long *>(p.res + (size_t)ct * p.res_bs) + (size_t)o * n + idx;
+                    for (int j = a_start; j < p.res_size; j++) zp[(size_t)j * res_ls] = 0;
+                }
+            }
+        }
+        if (t == 0 && K == 0) p.ok[ct] = 1;
+        cl_arrive();
+    }
+    cl_wait();
+#undef P1_ADDR
+#undef P2_ADDR
+}
+
+template <int L, int MB> __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(GGeo<L>::T, MB * 256 / GGeo<L>::T) ntt120_gadget_kernel(const __grid_constant__ GadgetArgs p,
+                                                                                                            const uint2 *__restrict__ twf,
+                                                                                                            const uint2 *__restrict__ twi) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    constexpr int n = GGeo<L>::N;
+    cl_arrive(); // primes the arrive/wait pairing used by the per-ciphertext loop
+    const int k = blockIdx.x & 3; // = rank in the cluster; one code body for all four primes (instruction-cache footprint)
+    gadget_body<L>(p, smem, twf + (size_t)k * n, twi + (size_t)k * n, k);
+}
+
+// collapsed key in the gadget kernel's layout: out[r][col][k][chunk][t][4] = sum_j 2^((S-1-j)K) * pmat[r][j * cols_out + col][k][16t + 4 chunk + w]
+struct CollapseArgs2 {
+    const char *pmat;
+    uint32_t *out;
+    int n, R, C, cols_out, S;
+    uint32_t c[32][4];
+};
+__global__ void __launch_bounds__(256) gadget_collapse_key_kernel(CollapseArgs2 p) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x; // quad index inside one prime plane
+    const int n4 = p.n / 4;
+    if (u >= n4) return;
+    const int k = blockIdx.z;
+    const PrimeRt pr(k);
+    const int r = blockIdx.y / p.cols_out, col = blockIdx.y % p.cols_out;
+    const size_t poly4 = (size_t)4 * n4; // uint4 per poly
+    const uint4 *src = reinterpret_cast<const uint4 *>(p.pmat) + ((size_t)r * p.C + col) * poly4 + (size_t)k * n4 + u;
+    unsigned long long acc[4] = {0, 0, 0, 0};
+    for (int j0 = 0; j0 < p.S; j0 += 16) {
+        const int j1 = min(j0 + 16, p.S);
+        for (int j = j0; j < j1; j++) {
+            const uint4 v = __ldg(src + (size_t)j * p.cols_out * poly4);
+            const unsigned long long cj = p.c[j][k];
+            acc[0] += v.x * cj; acc[1] += v.y * cj; acc[2] += v.z * cj; acc[3] += v.w * cj;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[i] = pr.reduce(acc[i]);
+    }
+    const int T = p.n / 16, t = u >> 2, c = u & 3;
+    uint4 *dst = reinterpret_cast<uint4 *>(p.out) + ((size_t)r * p.cols_out + col) * poly4 + (size_t)k * n4 + (size_t)c * T + t;
+    *dst = make_uint4((uint32_t)acc[0], (uint32_t)acc[1], (uint32_t)acc[2], (uint32_t)acc[3]);
+}
+
+static uint32_t pow2_mod(uint64_t e, uint32_t q) {
+    uint64_t r = 1, b = 2;
+    while (e) {
+        if (e & 1) r = r * b % q;
+        b = b * b % q;
+        e >>= 1;
+    }
+    return (uint32_t)r;
+}
+
+template <int L, int MB> int launch_gadget_mb(pgb_module *m, const GadgetArgs &p, size_t smem);
+template <int L> int launch_gadget(pgb_module *m, const GadgetArgs &p, size_t smem) {
+    const char *e = getenv("PGB_GADGET_MB");
+    if (e && atoi(e) == 4) return launch_gadget_mb<L, 4>(m, p, smem);
+    return launch_gadget_mb<L, 3>(m, p, smem);
+}
+template <int L, int MB> int launch_gadget_mb(pgb_module *m, const GadgetArgs &p, size_t smem) {
+    typedef GGeo<L> G;
+    static int max_clusters = 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(G::T);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = m->stream;
+    if (!max_clusters) {
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_gadget_kernel<L, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 << 10)));
+        const char *cv = getenv("PGB_GADGET_CARVEOUT");
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_gadget_kernel<L, MB>, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : 100));
+    }
+    // resident clusters for this shared-memory footprint (depends on R through smem)
+    cfg.gridDim = dim3(4 * 148);
+    int nc = 0;
+    PGB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&nc, ntt120_gadget_kernel<L, MB>, &cfg));
+    if (nc < 1) {
+        pgb_set_error("gadget kernel: no resident cluster fits (smem %zu)", smem);
+        return PGB_ERR_UNSUPPORTED;
+    }
+    max_clusters = nc;
+    const int clusters = p.batch < nc ? p.batch : nc;
+    cfg.gridDim = dim3(4 * clusters);
+    { ProfScope _ps(m, PROF_GADGET);
+    PGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ntt120_gadget_kernel<L, MB>, p, (const uint2 *)m->ntt_fwd, (const uint2 *)m->ntt_inv));
+    }
+    return PGB_OK;
+}
+
+} // namespace
+
+bool ntt120_gadget_supported(const pgb_module *m, int R, int cols_out, int S, int base2k, int batch) {
+    if (m->flavour != PGB_NTT120 || m->log_n < 10 || m->log_n > 12) return false;
+    if (getenv("PGB_NO_GADGET")) return false;
+    const int planes = R > cols_out ? R : cols_out;
+    if ((size_t)planes * m->n * 4 > (size_t)(96 << 10)) return false;
+    if (cols_out < 1 || cols_out > 4 || R < 1 || R > 8) return false;
+    if (S < 1 || S > 8 || base2k < 2 || base2k > 62) return false;
+    if ((int64_t)S * base2k > 128 || (S - 1) * base2k + 3 >= 118) return false; // digits must come from the low 128 bits
+    return batch >= 1;
+}
+
+// ok_out (device, batch ints, caller scratch): 1 where the ciphertext was finished here, 0 where the per-limb route is needed
+int ntt120_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_cols, int row_cols, int row_col0, int R, const char *pmat,
+                        int C, int cols_out, int small_size, char *res, uint64_t res_bs, int res_size, int base2k, int batch, int *ok_out) {
+    const uint64_t n = m->n, poly_bytes = 16 * n;
+    const int S = C / cols_out;
+    // workspace: [collapsed key | key coefficients (i128) | key_bits]
+    const uint64_t ck_bytes = (uint64_t)R * cols_out * poly_bytes, key_bytes = (uint64_t)R * C * poly_bytes;
+    const uint64_t need = ck_bytes + key_bytes + 256;
+    if (m->aux_len < need) {
+        if (m->aux_ws) {
+            PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+            cudaFree(m->aux_ws);
+        }
+        m->aux_ws = nullptr;
+        m->aux_len = 0;
+        PGB_CHECK_CUDA(cudaMalloc(&m->aux_ws, need));
+        m->aux_len = need;
+    }
+    char *ck = (char *)m->aux_ws, *kcoef = ck + ck_bytes;
+    int *key_bits = (int *)(kcoef + key_bytes);
+    CollapseArgs2 ca;
+    memset(&ca, 0, sizeof ca);
+    ca.pmat = pmat; ca.out = (uint32_t *)ck; ca.n = (int)n; ca.R = R; ca.C = C; ca.cols_out = cols_out; ca.S = S;
+    for (int j = 0; j < S; j++)
+        for (int k = 0; k < 4; k++) ca.c[j][k] = pow2_mod((uint64_t)(S - 1 - j) * base2k, qk(k));
+    { ProfScope _ps(m, PROF_OTHER);
+    gadget_collapse_key_kernel<<<dim3(((unsigned)(n / 4) + 255) / 256, R * cols_out, 4), 256, 0, m->stream>>>(ca);
+    }
+    PGB_CHECK_CUDA(cudaGetLastError());
+    PGB_TRY(ntt120_key_max_bits(m, pmat, R * C, kcoef, key_bits));
+
+    GadgetArgs p;
+    memset(&p, 0, sizeof p);
+    p.in = in; p.in_bs = in_bs; p.res = res; p.res_bs = res_bs; p.ckey = (const uint32_t *)ck; p.key_bits = key_bits; p.ok = ok_out;
+    p.in_cols = in_cols; p.row_cols = row_cols; p.row_col0 = row_col0; p.R = R; p.cols_out = cols_out; p.small_size = small_size;
+    p.K = base2k; p.S = S; p.res_size = res_size; p.batch = batch;
+    u128 half = 0;
+    for (int j = 0; j < S; j++) half += (u128)1 << (j * base2k + base2k - 1);
+    p.half_lo = (unsigned long long)half;
+    p.half_hi = (unsigned long long)(half >> 64);
+    int rn_bits = 0;
+    while (((uint64_t)1 << rn_bits) < (uint64_t)R * n) rn_bits++;
+    p.base_bits = rn_bits + (S - 1) * base2k + 3;
+    u128 Q = 1;
+    for (int k = 0; k < 4; k++) Q *= qk(k);
+    for (int k = 0; k < 4; k++) {
+        const u128 mk = Q / qk(k);
+        for (int w = 0; w < 4; w++) p.m_w[k][w] = (uint32_t)(mk >> (32 * w));
+        p.nq_w[k] = (uint32_t)(((u128)0 - Q) >> (32 * k));
+        p.inv60[k] = (uint32_t)(((unsigned long long)1 << 60) / qk(k));
+        p.crt_ninv[k] = m->nc.crt_ninv[k];
+        p.crt_ninv_sh[k] = m->nc.crt_ninv_sh[k];
+        memcpy(p.top[k].f, m->tw_top_f[k], sizeof p.top[k].f);
+        memcpy(p.top[k].i, m->tw_top_i[k], sizeof p.top[k].i);
+        const uint32_t q = qk(k), c32 = (uint32_t)((1ull << 32) % q);
+        p.prime[k].q = q;
+        p.prime[k].c32 = c32;
+        p.prime[k].c32s = (uint32_t)(((unsigned long long)c32 << 32) / q);
+        p.prime[k].neg64 = q - (uint32_t)(((unsigned long long)c32 * c32) % q);
+    }
+    const int planes = R > cols_out ? R : cols_out;
+    const size_t smem = (size_t)planes * n * 4;
+    switch (m->log_n) {
+    case 10: return launch_gadget<10>(m, p, smem);
+    case 11: return launch_gadget<11>(m, p, smem);
+    case 12: return launch_gadget<12>(m, p, smem);
+    default: pgb_set_error("gadget kernel: unsupported n"); return PGB_ERR_UNSUPPORTED;
+    }
+}

@@ -223,3 +223,51 @@ def test_collapsed_key_wide_base2k():
     g.sync()
     o.glwe_keyswitch_batch(want, k, a, k, po, k)
     assert np.array_equal(g.vec_znx_to_numpy(res_g), want)
+
+
+@pytest.mark.parametrize("n", [1024, 2048, 4096])
+def test_gadget_single_kernel(n):
+    """The cluster kernel of ntt120_gadget.cu (whole key-switch / external product in one launch, n = 2^10..2^12): shape sweep, more
+    ciphertexts than resident clusters (persistent loop), ciphertexts that must be flagged for the per-limb route, all bit for bit."""
+    g, o = pb.Module(n, pb.NTT120), O.OracleModule(n, pb.NTT120)
+    rng = np.random.default_rng(1200 + n)
+    k = 18
+    batch = 700 if n == 1024 else 40
+    shapes = ((1, 1, 3, 4, 3), (2, 1, 3, 4, 4), (1, 2, 2, 3, 2), (1, 1, 3, 5, 6), (1, 1, 1, 2, 1))
+    for rank_in, rank_out, a_size, key_size, res_size in shapes:
+        pg, po = _key(g, o, rng, a_size, rank_in, rank_out + 1, key_size, k)
+        a = fill_uniform(rng, (batch, a_size, rank_in + 1, n), k)
+        a[5] = fill_uniform(rng, a[5].shape, 61)      # fails the bound: per-limb kernels
+        a[17, 0, 1, 3] = -(1 << 62)                   # one huge mask coefficient is enough
+        a[18, 0, 0, 3] = -(1 << 62)                   # a huge body coefficient is harmless (added after the CRT)
+        a[30] = 0
+        want = fill_uniform(rng, (batch, res_size, rank_out + 1, n), k)
+        res_g = g.vec_znx_from_numpy(want)
+        g.glwe_keyswitch(res_g, k, g.vec_znx_from_numpy(a), k, pg, k)
+        g.sync()
+        o.glwe_keyswitch_batch(want, k, a, k, po, k)
+        got = g.vec_znx_to_numpy(res_g)
+        bad = [b for b in range(batch) if not np.array_equal(got[b], want[b])]
+        assert not bad, ("ks", rank_in, rank_out, a_size, key_size, res_size, bad[:10], len(bad))
+    for kbits, rank in ((k, 1), (62, 1), (k, 2)):
+        if (rank + 1) * 3 * n * 4 > 96 * 1024:
+            continue
+        pg, po = _key(g, o, rng, 3, rank + 1, rank + 1, 3, kbits)
+        a = fill_uniform(rng, (batch, 3, rank + 1, n), k)
+        want = np.zeros((batch, 3, rank + 1, n), dtype=np.int64)
+        res_g = g.vec_znx_alloc(rank + 1, 3, batch)
+        g.glwe_external_product(res_g, k, g.vec_znx_from_numpy(a), k, pg, k)
+        g.sync()
+        o.glwe_external_product_batch(want, k, a, k, po, k)
+        got = g.vec_znx_to_numpy(res_g)
+        bad = [b for b in range(batch) if not np.array_equal(got[b], want[b])]
+        assert not bad, ("ep", kbits, rank, bad[:10], len(bad))
+    # base2k = 25, two digits: S * K = 75 <= 128 and a narrower carry chain
+    pg, po = _key(g, o, rng, 2, 1, 2, 3, 25)
+    a = fill_uniform(rng, (batch, 2, 2, n), 25)
+    want = np.zeros((batch, 3, 2, n), dtype=np.int64)
+    res_g = g.vec_znx_alloc(2, 3, batch)
+    g.glwe_keyswitch(res_g, 25, g.vec_znx_from_numpy(a), 25, pg, 25)
+    g.sync()
+    o.glwe_keyswitch_batch(want, 25, a, 25, po, 25)
+    assert np.array_equal(g.vec_znx_to_numpy(res_g), want)
