@@ -265,15 +265,18 @@ def main():
     n = w["n"]
     cols_out, R, Cc = w["rank"] + 1, w["dnum"] * w["rank"], (w["rank"] + 1) * w["key_size"]
     key_bytes = R * Cc * 16 * n
+    glwe_bytes = (w["rank"] + 1) * w["a_size"] * 8 * n
     bytes_per_launch = {
-        "dft_forward": B * w["a_size"] * (8 * n + 16 * n),                # i64 limb in, 16 B/coef DFT limb out
-        # fused back end (vmp + idft + CRT + add_small + normalize in one kernel): a_dft in, body column in, GLWE out, key once
+        # single-kernel gadget product: GLWE in (mask limbs + body limbs) + GLWE out, collapsed key once (fused minimum)
+        "gadget_fused": B * 2 * glwe_bytes + R * cols_out * 16 * n,
+        "dft_forward": B * w["a_size"] * (8 * n + 16 * n),                # i64 limb in, 16 B/coef DFT limb out (per-limb route only)
         "dft_inverse": B * (R * 16 * n + w["a_size"] * 8 * n + cols_out * w["a_size"] * 8 * n) + key_bytes,
         "vmp_apply": B * (R + Cc) * 16 * n + key_bytes,                   # only on the unfused path
         "normalize": B * (w["key_size"] * 16 * n + w["a_size"] * 8 * n),  # only on the unfused path
         "elementwise": B * (2 * 16 * n + 8 * n),                          # only on the unfused path
     }
-    kernel_names = {"dft_forward": "ntt120_fwd_kernel<12,1>", "dft_inverse": "ntt120_fused_back_kernel<12> (vmp+intt+crt+add_small+normalize)"}
+    kernel_names = {"gadget_fused": "ntt120_gadget_kernel<12> (dft + vmp + idft + CRT + add_small + normalize, one launch per batch)",
+                    "dft_forward": "ntt120_fwd_kernel<12,1>", "dft_inverse": "ntt120_fused_back_kernel<12> (vmp+intt+crt+add_small+normalize)"}
     lib.pgb_profile_category_name.restype = C.c_char_p
     names = [lib.pgb_profile_category_name(i).decode() for i in range(NCAT)]
     peak, peak_src = peaks()
@@ -283,19 +286,43 @@ def main():
             continue
         avg_ms = prof_ms[i] / prof_n[i]
         d = {"launches": int(prof_n[i]), "avg_ms": avg_ms, "share_of_step": prof_ms[i] / ms}
-        if nm in bytes_per_launch:
+        if nm in bytes_per_launch and d["share_of_step"] > 0.05:
             d["algorithmic_bytes_per_launch"] = bytes_per_launch[nm]
             d["achieved_gbs"] = bytes_per_launch[nm] / (avg_ms * 1e-3) / 1e9
             d["frac_of_hbm_peak"] = d["achieved_gbs"] / peak
         kernels[nm] = d
     dom = max((k_ for k_ in kernels if "achieved_gbs" in kernels[k_]), key=lambda k_: kernels[k_]["launches"] * kernels[k_]["avg_ms"])
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/r1_traffic.json, bytes per key-switch)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if dom in tj:
+            traffic = tj[dom]["dram_bytes_per_keyswitch"] * B
+    # the kernel is bound by integer issue, not by HBM: butterflies per second against the in-register butterfly rate measured by
+    # scripts/pipe_peaks.cu on this GPU model (profiles/r1_pipe_peaks.json), scaled to the SM clock observed during the timed region
+    log_n = n.bit_length() - 1
+    bf_per_ks = (R + cols_out) * 4 * (n // 2) * log_n
+    int_pipe = None
+    pp = os.path.join(ROOT, "profiles", "r1_pipe_peaks.json")
+    clocks = cs.summary()
+    if os.path.exists(pp) and dom == "gadget_fused":
+        pk = json.load(open(pp))
+        bf_peak = pk["ct_butterfly(harvey,shoup)"]["chip_per_s"]
+        bf_ach = bf_per_ks * B / (kernels[dom]["avg_ms"] * 1e-3)
+        int_pipe = {"unit": "Shoup/Harvey butterflies/s", "achieved": bf_ach, "peak": bf_peak, "frac": bf_ach / bf_peak,
+                    "peak_source": "scripts/pipe_peaks.cu on B200: in-register butterfly loop on all SMs, chip-wide rate from CUDA events "
+                                   "(profiles/r1_pipe_peaks.json)",
+                    "butterflies_per_keyswitch": bf_per_ks}
     roofline = {"kernel": kernel_names.get(dom, dom), "category": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
-                "note": "algorithmic bytes per launch / CUDA-event duration on the launching stream (DESIGN.md section 3). The kernel is "
-                        "bound by the INT32 pipes (8 inverse NTT limbs of 4 primes per key-switch), not by HBM: a low HBM fraction is expected"}
-    # whole-pipeline view: bytes the fused pipeline must move per key-switch (GLWE in + a_dft out/in + GLWE out) vs what the
-    # unfused HAL sequence moves in this backend's 16 B layout
-    fused_bytes = (bytes_per_launch["dft_forward"] + bytes_per_launch["dft_inverse"]) / B
+                "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": traffic, "peak_source": peak_src, "int_pipe": int_pipe,
+                "note": "algorithmic bytes per launch (fused minimum: GLWE in + GLWE out + key once) / CUDA-event duration on the launching "
+                        "stream (DESIGN.md section 3).  HBM is the only roof MEASURED_PEAKS.json offers, but the kernel is bound by integer "
+                        "issue (five NTTs of four primes per key-switch, FMA-heavy pipe: IMAD / IMAD.HI): int_pipe gives the fraction of the "
+                        "measured in-register butterfly rate"}
+    # whole-pipeline view: bytes the fused pipeline must move per key-switch vs what the unfused HAL sequence moves in this backend's
+    # 16 B layout
+    fused_bytes = bytes_per_launch[dom] / B if dom == "gadget_fused" else (bytes_per_launch["dft_forward"] + bytes_per_launch["dft_inverse"]) / B
     unfused_bytes = 2949504.0
     step_gbs = fused_bytes * B / (ms / args.steps * 1e-3) / 1e9
     out = {
@@ -304,7 +331,7 @@ def main():
         "dtype": "u32 (canonical residues mod four 30-bit primes; i128 big)", "data": "synthetic", "config": config_dict(B, world),
         "e2e": {"value": e2e_value, "unit": "keyswitch/s", "h2d_bytes_per_step": int(a_np.nbytes), "d2h_bytes_per_step": int(a_np.nbytes),
                 "steps": e2e_steps, "api": "pgb_glwe_keyswitch_host (pinned host buffers)"},
-        "gpu_launches": int(launches), "clocks": cs.summary(), "roofline": roofline, "kernels": kernels,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
         "pipeline": {"fused_bytes_per_keyswitch": fused_bytes, "unfused_bytes_per_keyswitch": unfused_bytes, "achieved_gbs": step_gbs,
                      "frac_of_hbm_peak": step_gbs / peak},
     }
