@@ -258,6 +258,18 @@ int pgb_cggi_blind_rotate_batched(pgb_module *m, pgb_vec_znx *res, const int64_t
                                   const pgb_vmp_pmat *brk, const pgb_svp_ppol *x_pow_a, uint64_t block_size, uint64_t base2k,
                                   const pgb_batch *bt, void *scratch, size_t scratch_len);
 
+/* mod_switch_2n (algorithms/mod.rs:136-181) on the device: `lwe` = `count` one-column VecZnx of n_lwe + 1 coefficients (b, a_0, ...),
+ * stride bt->stride_a; res = device int64 [count][n_lwe + 1]; two_n_domain = 2 * lut.domain_size(); rot_left = LookUpTableRotationDirection::Left. */
+int pgb_cggi_mod_switch_2n_batched(pgb_module *m, int64_t *res, const pgb_vec_znx *lwe, uint64_t lwe_base2k, uint64_t two_n_domain,
+                                   int rot_left, const pgb_batch *bt);
+/* execute_standard (algorithm.rs:370-443, block_size == 1 keys): per LWE coefficient one GGSW x GLWE external product, X^{a_i} - 1, add;
+ * one glwe_normalize_assign at the end.  Same argument conventions as pgb_cggi_blind_rotate_batched. */
+size_t pgb_cggi_blind_rotate_standard_tmp_bytes(const pgb_module *m, uint64_t rank, uint64_t res_size, uint64_t res_base2k,
+                                                const pgb_vmp_pmat *brk, uint64_t brk_base2k, uint64_t batch);
+int pgb_cggi_blind_rotate_standard_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, const int64_t *lwe_2n, uint64_t n_lwe,
+                                           const pgb_vec_znx *lut, const pgb_vmp_pmat *brk, uint64_t brk_base2k, const pgb_batch *bt,
+                                           void *scratch, size_t scratch_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,3 +129,22 @@ void orc_cggi_blind_rotate_block_binary(int flavour, const void *mod, orc_vec_zn
     free(vmp_xai.data);
     free(acc_big.data);
 }
+
+/* algorithm.rs:370-443 (execute_standard, block_size == 1): acc = X^b LUT; for every LWE coefficient
+ *   acc_tmp = acc (x) BRK_i (glwe_external_product); acc_tmp *= X^{a_i} - 1; acc += acc_tmp;   then one glwe_normalize_assign.
+ * acc and acc_tmp share layout and base2k with `res` (take_glwe(&out_mut), :423). */
+void orc_cggi_blind_rotate_standard(int flavour, const void *mod, orc_vec_znx *res, size_t res_base2k, const int64_t *lwe_2n,
+                                    size_t n_lwe, const orc_vec_znx *lut, const orc_vmp_pmat *brk, size_t brk_base2k) {
+    size_t n = res->n, cols = res->cols;
+    const int64_t *a = lwe_2n + 1;
+    memset(res->data, 0, 8 * n * cols * res->size);
+    orc_vec_znx_rotate(lwe_2n[0], res, 0, lut, 0);
+    orc_vec_znx tmp = {(int64_t *)calloc(n * cols * res->size, 8), n, cols, res->size};
+    for (size_t i = 0; i < n_lwe; i++) {
+        orc_glwe_external_product(flavour, mod, &tmp, res_base2k, res, res_base2k, &brk[i], brk_base2k, 1);
+        for (size_t c = 0; c < cols; c++) orc_vec_znx_mul_xp_minus_one_assign(a[i], &tmp, c); /* operations/glwe.rs:1051-1062 */
+        for (size_t c = 0; c < cols; c++) orc_vec_znx_add_assign(res, c, &tmp, c);             /* api/operations.rs:273-289 */
+    }
+    for (size_t c = 0; c < cols; c++) orc_vec_znx_normalize_assign(res_base2k, res, c);         /* operations/glwe.rs:1312-1327 */
+    free(tmp.data);
+}

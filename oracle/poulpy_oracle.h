@@ -156,6 +156,10 @@ void orc_vec_znx_normalize(orc_vec_znx *res, size_t res_base2k, int64_t res_offs
                            const orc_vec_znx *a, size_t a_base2k, size_t a_col, int op);
 /* reference/vec_znx/rotate.rs, znx/rotate.rs:3-26 */
 void orc_vec_znx_rotate(int64_t p, orc_vec_znx *res, size_t res_col, const orc_vec_znx *a, size_t a_col);
+/* reference/vec_znx/add.rs:60-82, mul_xp_minus_one.rs:24-38, normalize.rs:403-425 */
+void orc_vec_znx_add_assign(orc_vec_znx *res, size_t res_col, const orc_vec_znx *a, size_t a_col);
+void orc_vec_znx_mul_xp_minus_one_assign(int64_t p, orc_vec_znx *res, size_t res_col);
+void orc_vec_znx_normalize_assign(size_t base2k, orc_vec_znx *res, size_t res_col);
 void orc_znx_rotate(int64_t p, int64_t *res, const int64_t *a, size_t n);
 
 /* ------------------------------------------------------------ compositions */
@@ -182,6 +186,9 @@ void orc_cggi_x_pow_a(int flavour, const void *mod, orc_svp_ppol *res);
 void orc_cggi_blind_rotate_block_binary(int flavour, const void *mod, orc_vec_znx *res, const int64_t *lwe_2n,
                                         size_t n_lwe, const orc_vec_znx *lut, const orc_vmp_pmat *brk,
                                         const orc_svp_ppol *x_pow_a, size_t block_size, size_t base2k);
+/* algorithm.rs:370-443 (execute_standard): brk = n_lwe prepared GGSWs (block_size == 1 keys) */
+void orc_cggi_blind_rotate_standard(int flavour, const void *mod, orc_vec_znx *res, size_t res_base2k, const int64_t *lwe_2n,
+                                    size_t n_lwe, const orc_vec_znx *lut, const orc_vmp_pmat *brk, size_t brk_base2k);
 
 /* ------------------------------------------------------------ batched drivers */
 /* CPU-baseline helpers: run `batch` independent key-switches / external products with OpenMP over

@@ -307,6 +307,16 @@ class OracleModule:
                                                  C.byref(lv), arr, C.byref(xp), _sz(block_size), _sz(base2k))
 
 
+    def cggi_blind_rotate_standard(self, res, res_base2k, lwe_2n, lut, brk, brk_base2k):
+        """execute_standard (block_size == 1); brk: list of VmpPMat (one GGSW per LWE coefficient)."""
+        n_lwe = len(brk)
+        arr = (_PM * n_lwe)(*[b.struct() for b in brk])
+        r, lv = _vz(res), _vz(lut)
+        lwe_2n = np.ascontiguousarray(lwe_2n, dtype=np.int64)
+        lib().orc_cggi_blind_rotate_standard(C.c_int(self.flavour), self._h, C.byref(r), _sz(res_base2k), _p(lwe_2n), _sz(n_lwe),
+                                             C.byref(lv), arr, _sz(brk_base2k))
+
+
 # --- free functions --------------------------------------------------------------------------------
 def vec_znx_normalize(res, res_base2k, res_offset, res_col, a, a_base2k, a_col):
     r, av = _vz(res), _vz(a)
@@ -317,6 +327,16 @@ def vec_znx_normalize(res, res_base2k, res_offset, res_col, a, a_base2k, a_col):
 def vec_znx_rotate(p, res, res_col, a, a_col):
     r, av = _vz(res), _vz(a)
     lib().orc_vec_znx_rotate(C.c_int64(p), C.byref(r), _sz(res_col), C.byref(av), _sz(a_col))
+
+
+def vec_znx_normalize_assign(base2k, res, res_col):
+    r = _vz(res)
+    lib().orc_vec_znx_normalize_assign(_sz(base2k), C.byref(r), _sz(res_col))
+
+
+def vec_znx_mul_xp_minus_one_assign(p, res, res_col):
+    r = _vz(res)
+    lib().orc_vec_znx_mul_xp_minus_one_assign(C.c_int64(p), C.byref(r), _sz(res_col))
 
 
 def mod_switch_2n(two_n_domain, lwe, base2k, rot_left=True):

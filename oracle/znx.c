@@ -63,3 +63,56 @@ void orc_vec_znx_rotate(int64_t p, orc_vec_znx *res, size_t res_col, const orc_v
     for (size_t j = 0; j < mn; j++) orc_znx_rotate(p, znx_at(res, res_col, j), znx_at(a, a_col, j), res->n);
     for (size_t j = mn; j < res->size; j++) memset(znx_at(res, res_col, j), 0, 8 * res->n);
 }
+
+/* reference/vec_znx/add.rs:60-82 */
+void orc_vec_znx_add_assign(orc_vec_znx *res, size_t res_col, const orc_vec_znx *a, size_t a_col) {
+    size_t mn = res->size < a->size ? res->size : a->size;
+    for (size_t j = 0; j < mn; j++) {
+        int64_t *r = znx_at(res, res_col, j);
+        const int64_t *x = znx_at(a, a_col, j);
+        for (size_t i = 0; i < res->n; i++) r[i] = (int64_t)((uint64_t)r[i] + (uint64_t)x[i]);
+    }
+}
+
+/* reference/vec_znx/mul_xp_minus_one.rs:24-38: per limb tmp = rotate(p, x); x = tmp - x (znx/sub.rs:26-36) */
+void orc_vec_znx_mul_xp_minus_one_assign(int64_t p, orc_vec_znx *res, size_t res_col) {
+    int64_t *tmp = (int64_t *)malloc(8 * res->n);
+    for (size_t j = 0; j < res->size; j++) {
+        int64_t *x = znx_at(res, res_col, j);
+        orc_znx_rotate(p, tmp, x, res->n);
+        for (size_t i = 0; i < res->n; i++) x[i] = (int64_t)((uint64_t)tmp[i] - (uint64_t)x[i]);
+    }
+    free(tmp);
+}
+
+/* reference/znx/normalization.rs:4-11 */
+static inline int64_t get_digit64(size_t k, int64_t x) { return (int64_t)((uint64_t)x << (64 - k)) >> (64 - k); }
+static inline int64_t get_carry64(size_t k, int64_t x, int64_t d) { return (int64_t)((uint64_t)x - (uint64_t)d) >> k; }
+
+/* reference/vec_znx/normalize.rs:403-425 with the lsh = 0 steps of reference/znx/normalization.rs:44-56, :132-146, :254-264 */
+void orc_vec_znx_normalize_assign(size_t base2k, orc_vec_znx *res, size_t res_col) {
+    size_t n = res->n, size = res->size;
+    int64_t *carry = (int64_t *)calloc(n, 8);
+    for (size_t jj = 0; jj < size; jj++) {
+        size_t j = size - 1 - jj;
+        int64_t *x = znx_at(res, res_col, j);
+        if (j == size - 1) {
+            for (size_t i = 0; i < n; i++) {
+                int64_t d = get_digit64(base2k, x[i]);
+                carry[i] = get_carry64(base2k, x[i], d);
+                x[i] = d;
+            }
+        } else if (j == 0) {
+            for (size_t i = 0; i < n; i++) x[i] = get_digit64(base2k, (int64_t)((uint64_t)get_digit64(base2k, x[i]) + (uint64_t)carry[i]));
+        } else {
+            for (size_t i = 0; i < n; i++) {
+                int64_t d = get_digit64(base2k, x[i]);
+                int64_t c = get_carry64(base2k, x[i], d);
+                int64_t dc = (int64_t)((uint64_t)d + (uint64_t)carry[i]);
+                x[i] = get_digit64(base2k, dc);
+                carry[i] = (int64_t)((uint64_t)c + (uint64_t)get_carry64(base2k, dc, x[i]));
+            }
+        }
+    }
+    free(carry);
+}

@@ -183,3 +183,120 @@ extern "C" int pgb_cggi_blind_rotate_batched(pgb_module *m, pgb_vec_znx *res, co
     return cggi_blind_rotate_impl(m, res, lwe_2n, n_lwe, lut, brk, x_pow_a, block_size, base2k, bt, scratch, scratch_len);
 }
 
+
+// ---- mod_switch_2n on the device (algorithms/mod.rs:136-181) ---------------------------------------------------------
+struct ModSwitchArgs {
+    const char *lwe; uint64_t lwe_bs, limb_stride; // VecZnx(n = n_lwe + 1, cols = 1, size): limb j at + j * limb_stride bytes
+    long long *res;                                 // [batch][len]
+    uint32_t len, base2k, log2n, size;
+    int rot_left;
+};
+__global__ void __launch_bounds__(256) cggi_mod_switch_kernel(ModSwitchArgs p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.len) return;
+    const char *src = p.lwe + (size_t)blockIdx.y * p.lwe_bs;
+    long long x = reinterpret_cast<const long long *>(src)[i];
+    if (p.rot_left) x = (long long)(0ull - (unsigned long long)x);
+    if (p.base2k > p.log2n) {
+        const uint32_t diff = p.base2k - (p.log2n - 1);
+        x = (long long)((unsigned long long)x + (1ull << (diff - 1))) >> diff; // div_round_by_pow2 (:179-181)
+    } else {
+        const uint32_t rem = p.base2k - (p.log2n % p.base2k);
+        const uint32_t size = (p.log2n + p.base2k - 1) / p.base2k;
+        for (uint32_t j = 1; j < size; j++) {
+            const long long y = reinterpret_cast<const long long *>(src + (size_t)j * p.limb_stride)[i];
+            if (j == size - 1 && rem != p.base2k) x = (long long)(((unsigned long long)x << (p.base2k - rem)) + (unsigned long long)(y >> rem));
+            else x = (long long)(((unsigned long long)x << p.base2k) + (unsigned long long)y);
+        }
+    }
+    p.res[(size_t)blockIdx.y * p.len + i] = x;
+}
+extern "C" int pgb_cggi_mod_switch_2n_batched(pgb_module *m, int64_t *res, const pgb_vec_znx *lwe, uint64_t lwe_base2k, uint64_t two_n_domain,
+                                              int rot_left, const pgb_batch *bt) {
+    PGB_REQUIRE(bt && bt->count >= 1 && bt->count <= 65535, "cggi_mod_switch_2n: batch count must be in [1, 65535]");
+    PGB_REQUIRE(lwe->cols == 1 && lwe->size >= 1 && lwe->n >= 2, "cggi_mod_switch_2n: lwe must be a one-column VecZnx of n_lwe + 1 coefficients");
+    PGB_REQUIRE(lwe_base2k >= 1 && lwe_base2k <= 62 && two_n_domain >= 2, "cggi_mod_switch_2n: bad base2k / domain");
+    uint32_t log2n = 0;
+    while (((uint64_t)1 << log2n) < two_n_domain) log2n++; // usize::BITS - (n - 1).leading_zeros()
+    log2n += 1;
+    const uint32_t size_needed = lwe_base2k > log2n ? 1 : (uint32_t)((log2n + lwe_base2k - 1) / lwe_base2k);
+    PGB_REQUIRE(lwe->size >= size_needed, "cggi_mod_switch_2n: lwe has %llu limbs, %u needed", (unsigned long long)lwe->size, size_needed);
+    ModSwitchArgs p = {(const char *)lwe->data, bt->stride_a, lwe->n * 8, (long long *)res, (uint32_t)lwe->n, (uint32_t)lwe_base2k, log2n,
+                       (uint32_t)lwe->size, rot_left};
+    { ProfScope _ps(m, PROF_OTHER);
+    cggi_mod_switch_kernel<<<dim3(((uint32_t)lwe->n + 255) / 256, (uint32_t)bt->count), 256, 0, m->stream>>>(p);
+    }
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+
+// ---- execute_standard (algorithm.rs:370-443): block_size == 1 keys ------------------------------------------------------
+// out += (X^{a} - 1) * tmp for every limb of every column: glwe_mul_xp_minus_one_assign (operations/glwe.rs:1051-1062:
+// tmp' = rotate(a, tmp) - tmp, reference/vec_znx/mul_xp_minus_one.rs:24-38) followed by glwe_add_assign (api/operations.rs:273-289)
+struct XpAddArgs {
+    char *out; uint64_t out_bs;
+    const char *tmp; uint64_t tmp_bs;
+    const long long *lwe; uint64_t lwe_stride;
+    uint32_t n, limbs;
+};
+__global__ void __launch_bounds__(256) cggi_xpm1_add_kernel(XpAddArgs p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const uint32_t b = blockIdx.z, limb = blockIdx.y;
+    const long long a = p.lwe[(size_t)b * p.lwe_stride];
+    const uint32_t mp = (uint32_t)(a & (long long)(2 * p.n - 1));
+    const long long *t = reinterpret_cast<const long long *>(p.tmp + (size_t)b * p.tmp_bs) + (size_t)limb * p.n;
+    long long *o = reinterpret_cast<long long *>(p.out + (size_t)b * p.out_bs) + (size_t)limb * p.n;
+    const uint32_t s = (i - mp) & (2 * p.n - 1); // coefficient s of tmp lands on i (negated when it wrapped once)
+    const unsigned long long r = s < p.n ? (unsigned long long)t[s] : 0ull - (unsigned long long)t[s - p.n];
+    o[i] = (long long)((unsigned long long)o[i] + (r - (unsigned long long)t[i]));
+}
+
+extern "C" size_t pgb_cggi_blind_rotate_standard_tmp_bytes(const pgb_module *m, uint64_t rank, uint64_t res_size, uint64_t res_base2k,
+                                                           const pgb_vmp_pmat *brk, uint64_t brk_base2k, uint64_t batch) {
+    const uint64_t acc = align_up(batch * m->n * (rank + 1) * res_size * 8);
+    return acc + pgb_glwe_external_product_tmp_bytes(m, res_size, res_size, res_base2k, brk, brk_base2k, 1, batch) + ALIGN;
+}
+extern "C" int pgb_cggi_blind_rotate_standard_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, const int64_t *lwe_2n,
+                                                      uint64_t n_lwe, const pgb_vec_znx *lut, const pgb_vmp_pmat *brk, uint64_t brk_base2k,
+                                                      const pgb_batch *bt, void *scratch, size_t scratch_len) {
+    PGB_REQUIRE(bt && bt->count >= 1 && bt->count <= 65535, "cggi_blind_rotate_standard: batch count must be in [1, 65535]");
+    PGB_REQUIRE(res->n == m->n && lut->n == m->n && brk->n == m->n, "cggi_blind_rotate_standard: ring degree mismatch");
+    PGB_REQUIRE(brk->cols_in == res->cols && brk->cols_out == res->cols, "cggi_blind_rotate_standard: brk rank does not match res");
+    const uint64_t n = m->n, B = bt->count, cols = res->cols;
+    const size_t need = pgb_cggi_blind_rotate_standard_tmp_bytes(m, cols - 1, res->size, res_base2k, brk, brk_base2k, B);
+    if (scratch_len < need) {
+        pgb_set_error("cggi_blind_rotate_standard: scratch of %zu bytes < required %zu", scratch_len, need);
+        return PGB_ERR_SCRATCH;
+    }
+    const uint64_t tmp_bs = n * cols * res->size * 8;
+    pgb_vec_znx tmp = mkv(scratch, n, cols, res->size);
+    char *ep_scratch = (char *)scratch + align_up(B * tmp_bs);
+    const size_t ep_len = scratch_len - (size_t)align_up(B * tmp_bs);
+    const uint64_t brk_bytes = pgb_bytes_of_vmp_pmat(m, brk->rows, brk->cols_in, brk->cols_out, brk->size);
+    const uint64_t lwe_stride = n_lwe + 1;
+    // out.zero(); out[0] = X^b * LUT (:412-415)
+    PGB_CHECK_CUDA(cudaMemset2DAsync(res->data, bt->stride_res, 0, n * cols * res->size * 8, B, m->stream));
+    {
+        const uint64_t mn = umin64(res->size, lut->size);
+        LimbSet R = {(char *)res->data, res->cols * n * 8, bt->stride_res};
+        LimbSet L = {(char *)lut->data, lut->cols * n * 8, 0};
+        PGB_TRY(znx_rotate(m, R, L, 0, (const long long *)lwe_2n, (uint32_t)lwe_stride, (uint32_t)mn, (uint32_t)B));
+    }
+    for (uint64_t i = 0; i < n_lwe; i++) {
+        pgb_vmp_pmat ski = *brk;
+        ski.data = (char *)brk->data + i * brk_bytes;
+        pgb_batch bte = {B, tmp_bs, bt->stride_res, 0};
+        PGB_TRY(pgb_glwe_external_product_batched(m, &tmp, res_base2k, res, res_base2k, &ski, brk_base2k, 1, &bte, ep_scratch, ep_len)); // :429
+        XpAddArgs xa = {(char *)res->data, bt->stride_res, (const char *)tmp.data, tmp_bs, (const long long *)lwe_2n + 1 + i, lwe_stride,
+                        (uint32_t)n, (uint32_t)(cols * res->size)};
+        { ProfScope _ps(m, PROF_ELEMENTWISE);
+        cggi_xpm1_add_kernel<<<dim3(((uint32_t)n + 255) / 256, xa.limbs, (uint32_t)B), 256, 0, m->stream>>>(xa); // :432-435
+        }
+        PGB_CHECK_CUDA(cudaGetLastError());
+    }
+    pgb_batch btn = {B, bt->stride_res, bt->stride_res, 0};
+    for (uint64_t c = 0; c < cols; c++) // glwe_normalize_assign (:440): in place, one thread owns a coefficient across limbs
+        PGB_TRY(big_normalize_impl(m, res, res_base2k, 0, c, res, res_base2k, c, 0, false, &btn));
+    return PGB_OK;
+}

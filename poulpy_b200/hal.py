@@ -72,6 +72,7 @@ def lib():
         _lib.pgb_profile_enable.argtypes = [C.c_void_p, C.c_int]
         _lib.pgb_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
         for name in ("pgb_glwe_keyswitch_tmp_bytes", "pgb_glwe_external_product_tmp_bytes", "pgb_cggi_blind_rotate_tmp_bytes",
+                     "pgb_cggi_blind_rotate_standard_tmp_bytes",
                      "pgb_bytes_of_vmp_pmat", "pgb_size_of_scalar_prep", "pgb_size_of_scalar_big"):
             getattr(_lib, name).restype = C.c_size_t
     return _lib
@@ -490,6 +491,31 @@ class Module:
         _check(lib().pgb_cggi_blind_rotate_batched(self._h, C.byref(r), C.c_void_p(lwe_2n.ptr), _u64(n_lwe), C.byref(lv), C.byref(bs),
                                                    C.byref(xp), _u64(block_size), _u64(base2k), C.byref(bt), C.c_void_p(scratch.ptr),
                                                    C.c_size_t(scratch.nbytes)))
+        return scratch
+
+
+    def cggi_mod_switch_2n(self, lwe_dev: DevBuf, batch, n_lwe, size, lwe_base2k, two_n_domain, rot_left=True) -> DevBuf:
+        """mod_switch_2n of `batch` LWEs stored as (batch, size, 1, n_lwe + 1) int64 on the device -> DevBuf int64 [batch][n_lwe + 1]."""
+        out = DevBuf(batch * (n_lwe + 1) * 8)
+        lv = _VZ(lwe_dev.ptr, n_lwe + 1, 1, size, size)
+        bt = _BT(batch, 0, size * (n_lwe + 1) * 8, 0)
+        _check(lib().pgb_cggi_mod_switch_2n_batched(self._h, C.c_void_p(out.ptr), C.byref(lv), _u64(lwe_base2k), _u64(two_n_domain),
+                                                    C.c_int(1 if rot_left else 0), C.byref(bt)))
+        return out
+
+    def cggi_blind_rotate_standard(self, res: VecZnx, res_base2k, lwe_2n: DevBuf, n_lwe, lut: VecZnx, brk: VmpPMat, brk_base2k,
+                                   scratch: DevBuf = None):
+        """execute_standard (block_size == 1 keys); brk: the n_lwe prepared GGSWs stored consecutively."""
+        bs = brk.struct()
+        need = lib().pgb_cggi_blind_rotate_standard_tmp_bytes(self._h, _u64(res.cols - 1), _u64(res.size), _u64(res_base2k), C.byref(bs),
+                                                              _u64(brk_base2k), _u64(res.batch))
+        if scratch is None or scratch.nbytes < need:
+            scratch = DevBuf(need)
+        r, lv = res.struct(), lut.struct()
+        bt = _BT(res.batch, res.batch_stride, 0, 0)
+        _check(lib().pgb_cggi_blind_rotate_standard_batched(self._h, C.byref(r), _u64(res_base2k), C.c_void_p(lwe_2n.ptr), _u64(n_lwe),
+                                                            C.byref(lv), C.byref(bs), _u64(brk_base2k), C.byref(bt),
+                                                            C.c_void_p(scratch.ptr), C.c_size_t(scratch.nbytes)))
         return scratch
 
 

@@ -96,3 +96,67 @@ def test_blind_rotate_bench_shape_semantics(fl):
         want = np.zeros((1, rank + 1, n), dtype=np.int64)
         O.vec_znx_rotate(shift, want, 0, lut, 0)
         assert np.array_equal(got[b], want), b
+
+
+@pytest.mark.parametrize("base2k,size,two_n", [(18, 1, 1024), (5, 3, 1024), (7, 2, 4096), (12, 2, 2048), (11, 1, 1024)])
+@pytest.mark.parametrize("rot_left", [True, False])
+def test_mod_switch_2n_device(base2k, size, two_n, rot_left):
+    """mod_switch_2n (algorithms/mod.rs:136-181) on the device, both branches (rounding when base2k > log2(2N)+1, limb concatenation
+    otherwise), bit-exact against the oracle for a batch."""
+    n_lwe, batch = 37, 6
+    rng = np.random.default_rng(base2k * 100 + size)
+    g = pb.Module(64, pb.FFT64)
+    lwe = fill_uniform(rng, (batch, size, 1, n_lwe + 1), base2k)
+    dev = pb.DevBuf(lwe.nbytes)
+    dev.upload(lwe)
+    out = g.cggi_mod_switch_2n(dev, batch, n_lwe, size, base2k, two_n, rot_left)
+    g.sync()
+    got = out.download(np.int64, (batch, n_lwe + 1))
+    for b in range(batch):
+        assert np.array_equal(got[b], O.mod_switch_2n(two_n, lwe[b], base2k, rot_left)), b
+
+
+@pytest.mark.parametrize("fl", [pb.NTT120, pb.FFT64])
+@pytest.mark.parametrize("n,rank,dnum,size,brk_size", [(256, 1, 2, 2, 2), (512, 2, 1, 1, 2), (1024, 1, 3, 3, 3), (128, 1, 2, 2, 3)])
+def test_blind_rotate_standard_matches_oracle(fl, n, rank, dnum, size, brk_size):
+    """execute_standard (algorithm.rs:370-443): external product + (X^a - 1) + add per LWE coefficient, one normalize at the end;
+    random (non-cryptographic) GGSWs, bit-exact against the oracle.  n = 1024 routes the external product through the
+    single-kernel gadget path in the NTT120 flavour."""
+    k, n_lwe, batch = 12, 7, 4
+    rng = np.random.default_rng(300 * rank + dnum + fl + n)
+    g, o, gbrk, obrk = _setup(n, fl, rank, dnum, brk_size, n_lwe, k, rng)
+    lut = fill_uniform(rng, (size, 1, n), k)
+    lwe = rng.integers(-n, n, size=(batch, n_lwe + 1), dtype=np.int64)
+    want = np.zeros((batch, size, rank + 1, n), dtype=np.int64)
+    for b in range(batch):
+        o.cggi_blind_rotate_standard(want[b], k, lwe[b], lut, obrk, k)
+    res = g.vec_znx_from_numpy(fill_uniform(rng, want.shape, k))  # garbage pre-fill
+    lwe_dev = pb.DevBuf(lwe.nbytes)
+    lwe_dev.upload(lwe)
+    g.cggi_blind_rotate_standard(res, k, lwe_dev, n_lwe, g.vec_znx_from_numpy(lut), gbrk, k)
+    g.sync()
+    assert np.array_equal(g.vec_znx_to_numpy(res), want)
+
+
+@pytest.mark.parametrize("fl", [pb.NTT120, pb.FFT64])
+def test_blind_rotate_standard_semantics(fl):
+    """Noiseless binary keys: execute_standard on mod-switched LWEs (device mod_switch_2n) gives X^(b + <a, s>) * LUT exactly."""
+    n, k, n_lwe, batch, rank = 512, 18, 16, 5, 1
+    rng = np.random.default_rng(177 + fl)
+    s = rng.integers(0, 2, size=n_lwe, dtype=np.int64)
+    g, o, gbrk, obrk = _setup(n, fl, rank, 2, 2, n_lwe, k, rng, trivial_secret=s)
+    lut = fill_uniform(rng, (2, 1, n), k - 1)
+    lwe_raw = fill_uniform(rng, (batch, 1, 1, n_lwe + 1), k)
+    dev = pb.DevBuf(lwe_raw.nbytes)
+    dev.upload(lwe_raw)
+    lwe_dev = g.cggi_mod_switch_2n(dev, batch, n_lwe, 1, k, 2 * n, True)
+    res = g.vec_znx_alloc(rank + 1, 2, batch)
+    g.cggi_blind_rotate_standard(res, k, lwe_dev, n_lwe, g.vec_znx_from_numpy(lut), gbrk, k)
+    g.sync()
+    got = g.vec_znx_to_numpy(res)
+    for b in range(batch):
+        l2 = O.mod_switch_2n(2 * n, lwe_raw[b], k, True)
+        shift = int(l2[0] + np.dot(l2[1:], s))
+        want = np.zeros((2, rank + 1, n), dtype=np.int64)
+        O.vec_znx_rotate(shift, want, 0, lut, 0)
+        assert np.array_equal(got[b], want), b

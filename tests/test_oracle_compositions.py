@@ -144,3 +144,50 @@ def test_mod_switch_2n():
     want2 = ((lwe2[0, 0] << 5) + lwe2[1, 0])
     want2 = (want2 << 1) + (lwe2[2, 0] >> 4)
     assert np.array_equal(got2, want2)
+
+
+@pytest.mark.parametrize("flavour", [O.NTT120, O.FFT64])
+@pytest.mark.parametrize("rank", [1, 2])
+def test_blind_rotation_standard_semantics_trivial_keys(flavour, rank):
+    """execute_standard (algorithm.rs:370-443, block_size = 1: external product, X^a - 1, add, one final normalize) with noiseless
+    binary keys must give X^(b + <a, s>) * LUT exactly, like the block-binary variant."""
+    n, k, n_lwe = 64, 12, 9
+    size, dnum, brk_size = 2, 2, 2
+    rng = np.random.default_rng(15 + rank)
+    m = O.OracleModule(n, flavour)
+    s = rng.integers(0, 2, size=n_lwe, dtype=np.int64)
+    brk = []
+    for i in range(n_lwe):
+        pm = m.vmp_pmat_alloc(dnum, rank + 1, rank + 1, brk_size)
+        m.vmp_prepare(pm, _trivial_ggsw(n, rank, dnum, brk_size, int(s[i])))
+        brk.append(pm)
+    lut = fill_uniform(rng, (size, 1, n), k - 1)
+    lwe_2n = rng.integers(-n, n, size=n_lwe + 1, dtype=np.int64)
+    res = fill_uniform(rng, (size, rank + 1, n), k)
+    m.cggi_blind_rotate_standard(res, k, lwe_2n, lut, brk, k)
+    shift = int(lwe_2n[0] + np.dot(lwe_2n[1:], s))
+    want = np.zeros_like(res)
+    O.vec_znx_rotate(shift, want, 0, lut, 0)
+    assert np.array_equal(res, want)
+
+
+def test_normalize_assign_and_mul_xp_minus_one():
+    """vec_znx_normalize_assign (normalize.rs:403-425) agrees with the out-of-place normalize at equal base2k / offset 0, and
+    mul_xp_minus_one_assign (mul_xp_minus_one.rs:24-38) is rotate(p, x) - x."""
+    rng = np.random.default_rng(31)
+    n, k = 32, 11
+    for size in (1, 2, 4):
+        a = rng.integers(-(1 << 40), 1 << 40, size=(size, 2, n), dtype=np.int64)
+        want = np.zeros_like(a)
+        got = a.copy()
+        for c in range(2):
+            O.vec_znx_normalize(want, k, 0, c, a, k, c)
+            O.vec_znx_normalize_assign(k, got, c)
+        assert np.array_equal(got, want), size
+    x = rng.integers(-1000, 1000, size=(3, 1, n), dtype=np.int64)
+    for p in (0, 1, n - 1, n, n + 5, -3, 2 * n + 2):
+        r = np.zeros_like(x)
+        O.vec_znx_rotate(p, r, 0, x, 0)
+        y = x.copy()
+        O.vec_znx_mul_xp_minus_one_assign(p, y, 0)
+        assert np.array_equal(y, r - x), p
