@@ -155,6 +155,9 @@ int pgb_vec_znx_dft_zero_batched(pgb_module *m, pgb_vec_znx_dft *res, uint64_t r
 /* ---- svp (oep/hal_impl.rs:595-616; R11, F6) ------------------------------------------------------ */
 /* HalImpl::svp_prepare :595 (ntt120/svp.rs:52-70, fft64/svp.rs:9-20) */
 int pgb_svp_prepare(pgb_module *m, pgb_svp_ppol *res, uint64_t res_col, const pgb_scalar_znx *a, uint64_t a_col);
+/* HalImpl::svp_apply_dft :600 (fft64/svp.rs:21-55; NTT120 default poulpy-cpu-ref/src/hal_defaults/svp_ppol.rs:93-107): b is a VecZnx */
+int pgb_svp_apply_dft(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_svp_ppol *a, uint64_t a_col,
+                      const pgb_vec_znx *b, uint64_t b_col);
 /* HalImpl::svp_apply_dft_to_dft :606 (ntt120/svp.rs:87-133, fft64/svp.rs:57-79) */
 int pgb_svp_apply_dft_to_dft(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_svp_ppol *a, uint64_t a_col,
                              const pgb_vec_znx_dft *b, uint64_t b_col);
@@ -170,6 +173,12 @@ int pgb_svp_apply_dft_to_dft_assign(pgb_module *m, pgb_vec_znx_dft *res, uint64_
 size_t pgb_vmp_prepare_tmp_bytes(const pgb_module *m, uint64_t rows, uint64_t cols_in, uint64_t cols_out, uint64_t size);
 size_t pgb_vmp_apply_dft_to_dft_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t a_size, uint64_t rows,
                                           uint64_t cols_in, uint64_t cols_out, uint64_t size);
+/* HalImpl::vmp_apply_dft_tmp_bytes :626 / vmp_apply_dft :636 (poulpy-cpu-ref/src/hal_impl/family_common.rs:3-58): `a` is a VecZnx; the
+ * library transforms its last min(a.cols, cols_in) columns into `scratch` (device memory) and applies the matrix. */
+size_t pgb_vmp_apply_dft_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t a_size, uint64_t rows, uint64_t cols_in,
+                                   uint64_t cols_out, uint64_t size);
+int pgb_vmp_apply_dft(pgb_module *m, pgb_vec_znx_dft *res, const pgb_vec_znx *a, const pgb_vmp_pmat *pmat, void *scratch,
+                      size_t scratch_len);
 /* HalImpl::vmp_prepare :620 (ntt120/vmp.rs:64-119, fft64/vmp.rs:52-93); `a` is a MatZnx of i64. */
 int pgb_vmp_prepare(pgb_module *m, pgb_vmp_pmat *res, const pgb_mat_znx *a);
 /* HalImpl::vmp_apply_dft_to_dft :653 (ntt120/vmp.rs:301-341 + core :169-288; fft64/vmp.rs:144-264).

@@ -492,6 +492,27 @@ extern "C" int pgb_svp_apply_dft_to_dft_batched(pgb_module *m, pgb_vec_znx_dft *
                                                 uint64_t a_col, const pgb_vec_znx_dft *b, uint64_t b_col, const pgb_batch *bt) {
     return svp_apply_impl(m, res, res_col, a, a_col, b, b_col, bt);
 }
+// HalImpl::svp_apply_dft (hal_impl.rs:600): res[res_col] = ppol[a_col] * DFT(b[b_col]) for min(res.size, b.size) limbs, zero the rest
+// (fft64/svp.rs:21-55; NTT120: hal_defaults/svp_ppol.rs:93-107 = vec_znx_dft_apply into a temporary + svp_apply_dft_to_dft).  The
+// forward transforms land directly in res, then the product is taken in place: same values, no temporary.
+extern "C" int pgb_svp_apply_dft(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_svp_ppol *a, uint64_t a_col,
+                                 const pgb_vec_znx *b, uint64_t b_col) {
+    CHECK_N(res, "svp_apply_dft(res)");
+    CHECK_N(a, "svp_apply_dft(a)");
+    CHECK_N(b, "svp_apply_dft(b)");
+    CHECK_COL(res, res_col, "svp_apply_dft(res)");
+    CHECK_COL(a, a_col, "svp_apply_dft(a)");
+    CHECK_COL(b, b_col, "svp_apply_dft(b)");
+    const uint64_t n = m->n, pb = prep_bytes(m), min_size = umin64(res->size, b->size);
+    LimbSet in = {(char *)b->data + limb_off(n, b->cols, b_col, 0, 8), b->cols * n * 8, 0};
+    LimbSet R = dft_col(m, res, res_col, 0, 0);
+    if (m->flavour == PGB_NTT120) PGB_TRY(ntt120_forward(m, in, R, (int)min_size, 1));
+    else PGB_TRY(fft64_forward(m, in, R, (int)min_size, 1));
+    LimbSet P = {(char *)a->data + a_col * n * pb, 0, 0};
+    PGB_TRY(dft_ew(m, EW_MUL, R, P, R, min_size, 1));
+    PGB_TRY(dft_ew(m, EW_ZERO, shift(R, min_size), shift(R, min_size), shift(R, min_size), res->size - min_size, 1));
+    return sync_if(m, true);
+}
 extern "C" int pgb_svp_apply_dft_to_dft_assign(pgb_module *m, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_svp_ppol *a,
                                                uint64_t a_col) {
     CHECK_N(res, "svp_apply_dft_to_dft_assign(res)");
@@ -561,6 +582,37 @@ extern "C" int pgb_vmp_apply_dft_to_dft(pgb_module *m, pgb_vec_znx_dft *res, con
 extern "C" int pgb_vmp_apply_dft_to_dft_batched(pgb_module *m, pgb_vec_znx_dft *res, const pgb_vec_znx_dft *a, const pgb_vmp_pmat *pmat,
                                                 uint64_t limb_offset, const pgb_batch *bt) {
     return vmp_apply_impl(m, res, a, pmat, limb_offset, bt);
+}
+// HalImpl::vmp_apply_dft_tmp_bytes / vmp_apply_dft (hal_impl.rs:626-640; poulpy-cpu-ref/src/hal_impl/family_common.rs:3-58): forward
+// transform of the last min(a.cols, cols_in) columns of `a` into a scratch VecZnxDft(cols_in, min(a.size, rows)) whose leading
+// columns are zero, then vmp_apply_dft_to_dft with limb_offset 0.
+extern "C" size_t pgb_vmp_apply_dft_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t a_size, uint64_t b_rows, uint64_t b_cols_in,
+                                              uint64_t b_cols_out, uint64_t b_size) {
+    (void)res_size; (void)b_cols_out; (void)b_size;
+    return m->n * b_cols_in * umin64(a_size, b_rows) * prep_bytes(m) + 256;
+}
+extern "C" int pgb_vmp_apply_dft(pgb_module *m, pgb_vec_znx_dft *res, const pgb_vec_znx *a, const pgb_vmp_pmat *pmat, void *scratch,
+                                 size_t scratch_len) {
+    CHECK_N(res, "vmp_apply_dft(res)");
+    CHECK_N(a, "vmp_apply_dft(a)");
+    CHECK_N(pmat, "vmp_apply_dft(pmat)");
+    const uint64_t n = m->n, pb = prep_bytes(m);
+    const uint64_t cols_to_copy = umin64(a->cols, pmat->cols_in), a_start_col = a->cols - cols_to_copy;
+    const uint64_t a_dft_size = umin64(a->size, pmat->rows), offset = pmat->cols_in - cols_to_copy;
+    const size_t need = pgb_vmp_apply_dft_tmp_bytes(m, res->size, a->size, pmat->rows, pmat->cols_in, pmat->cols_out, pmat->size);
+    if (scratch_len < need) {
+        pgb_set_error("vmp_apply_dft: scratch of %zu bytes < required %zu", scratch_len, need);
+        return PGB_ERR_SCRATCH;
+    }
+    char *sp = (char *)(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+    pgb_vec_znx_dft a_dft = {sp, n, pmat->cols_in, a_dft_size, a_dft_size};
+    if (a_dft_size) {
+        for (uint64_t j = 0; j < offset; j++) PGB_TRY(dft_zero_impl(m, &a_dft, j, &ONE));
+        for (uint64_t j = 0; j < cols_to_copy; j++) PGB_TRY(dft_apply_impl(m, 1, 0, &a_dft, offset + j, a, a_start_col + j, &ONE));
+    }
+    (void)pb;
+    PGB_TRY(vmp_apply_impl(m, res, &a_dft, pmat, 0, &ONE));
+    return sync_if(m, true);
 }
 extern "C" int pgb_vmp_zero(pgb_module *m, pgb_vmp_pmat *res) {
     CHECK_N(res, "vmp_zero(res)");

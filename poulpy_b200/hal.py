@@ -72,7 +72,7 @@ def lib():
         _lib.pgb_profile_enable.argtypes = [C.c_void_p, C.c_int]
         _lib.pgb_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
         for name in ("pgb_glwe_keyswitch_tmp_bytes", "pgb_glwe_external_product_tmp_bytes", "pgb_cggi_blind_rotate_tmp_bytes",
-                     "pgb_cggi_blind_rotate_standard_tmp_bytes",
+                     "pgb_cggi_blind_rotate_standard_tmp_bytes", "pgb_vmp_apply_dft_tmp_bytes",
                      "pgb_bytes_of_vmp_pmat", "pgb_size_of_scalar_prep", "pgb_size_of_scalar_big"):
             getattr(_lib, name).restype = C.c_size_t
     return _lib
@@ -373,6 +373,11 @@ class Module:
         else:
             _check(lib().pgb_svp_apply_dft_to_dft(self._h, C.byref(r), _u64(res_col), C.byref(pv), _u64(a_col), C.byref(bv), _u64(b_col)))
 
+    def svp_apply_dft(self, res, res_col, a: SvpPPol, a_col, b, b_col):
+        """HalImpl::svp_apply_dft: b is a VecZnx (coefficient domain)."""
+        r, pv, bv = res.struct(), a.struct(), b.struct()
+        _check(lib().pgb_svp_apply_dft(self._h, C.byref(r), _u64(res_col), C.byref(pv), _u64(a_col), C.byref(bv), _u64(b_col)))
+
     def svp_apply_dft_to_dft_assign(self, res, res_col, a: SvpPPol, a_col):
         r, pv = res.struct(), a.struct()
         _check(lib().pgb_svp_apply_dft_to_dft_assign(self._h, C.byref(r), _u64(res_col), C.byref(pv), _u64(a_col)))
@@ -389,6 +394,14 @@ class Module:
             _check(lib().pgb_vmp_apply_dft_to_dft_batched(self._h, C.byref(r), C.byref(av), C.byref(ps), _u64(limb_offset), C.byref(bt)))
         else:
             _check(lib().pgb_vmp_apply_dft_to_dft(self._h, C.byref(r), C.byref(av), C.byref(ps), _u64(limb_offset)))
+
+    def vmp_apply_dft(self, res, a, pmat: VmpPMat):
+        """HalImpl::vmp_apply_dft: a is a VecZnx; scratch is taken from a temporary device buffer of vmp_apply_dft_tmp_bytes."""
+        r, av, ps = res.struct(), a.struct(), pmat.struct()
+        need = lib().pgb_vmp_apply_dft_tmp_bytes(self._h, _u64(res.size), _u64(a.size), _u64(pmat.rows), _u64(pmat.cols_in),
+                                                 _u64(pmat.cols_out), _u64(pmat.size))
+        scratch = DevBuf(need)
+        _check(lib().pgb_vmp_apply_dft(self._h, C.byref(r), C.byref(av), C.byref(ps), C.c_void_p(scratch.ptr), C.c_size_t(need)))
 
     # --- vec_znx_big (poulpy-hal/src/api/vec_znx_big.rs) ---------------------------------------------------------------------
     def vec_znx_big_add_small_assign(self, res, res_col, a, a_col):

@@ -417,3 +417,52 @@ def test_error_model():
         other.vec_znx_dft_apply(1, 0, d, 0, a, 0)  # ring degree mismatch
     with pytest.raises(pb.PoulpyError):
         pb.Module(48, pb.NTT120)  # not a power of two
+
+
+@pytest.mark.parametrize("fl", FLAVOURS)
+def test_svp_apply_dft_and_vmp_apply_dft_from_coefficients(fl):
+    """HalImpl::svp_apply_dft (hal_impl.rs:600) and vmp_apply_dft (:636): the coefficient-domain front ends.  The oracle side spells
+    out the reference bodies: fft64/svp.rs:21-55 / hal_defaults/svp_ppol.rs:93-107 (dft_apply, then svp_apply_dft_to_dft) and
+    hal_impl/family_common.rs:17-58 (last min(a.cols, cols_in) columns transformed into a zero-padded VecZnxDft, then
+    vmp_apply_dft_to_dft); outputs compared after idft + normalize, bit for bit."""
+    n = 128
+    g, o = mods(n, fl)
+    rng = np.random.default_rng(19)
+    k = base2k_for(fl)
+    s = fill_uniform(rng, (1, n), k)
+    pg, po = g.svp_ppol_alloc(1), o.svp_ppol_alloc(1)
+    g.svp_prepare(pg, 0, g.scalar_znx_from_numpy(s), 0)
+    o.svp_prepare(po, 0, s, 0)
+    for b_size, res_size in ((1, 1), (3, 2), (2, 4)):
+        b = fill_uniform(rng, (b_size, 2, n), k)
+        rg, ro = g.vec_znx_dft_alloc(1, res_size), o.vec_znx_dft_alloc(1, res_size)
+        rg.buf.upload(rng.integers(0, 255, rg.buf.nbytes, dtype=np.uint8))
+        g.svp_apply_dft(rg, 0, pg, 0, g.vec_znx_from_numpy(b), 1)
+        bdo = o.vec_znx_dft_alloc(1, b_size)
+        o.vec_znx_dft_apply(1, 0, bdo, 0, b, 1)
+        o.svp_apply_dft_to_dft(ro, 0, po, 0, bdo, 0)
+        big_g, big_o = g.vec_znx_idft_apply_consume(rg), o.vec_znx_idft_apply_consume(ro)
+        out_g, out_o = g.vec_znx_alloc(1, res_size), o.vec_znx_alloc(1, res_size)
+        g.vec_znx_big_normalize(out_g, k, 0, 0, big_g, k, 0)
+        o.vec_znx_big_normalize(out_o, k, 0, 0, big_o, k, 0)
+        assert np.array_equal(g.vec_znx_to_numpy(out_g), out_o), (b_size, res_size)
+    for a_cols, cols_in, cols_out, a_size, rows, size_out in ((1, 1, 2, 3, 3, 4), (2, 1, 1, 2, 4, 2), (1, 2, 2, 4, 2, 3), (3, 2, 1, 2, 2, 2)):
+        a = fill_uniform(rng, (a_size, a_cols, n), k)
+        mat = fill_uniform(rng, (rows, cols_in, size_out, cols_out, n), k)
+        pmg, pmo = g.vmp_pmat_alloc(rows, cols_in, cols_out, size_out), o.vmp_pmat_alloc(rows, cols_in, cols_out, size_out)
+        g.vmp_prepare(pmg, g.mat_znx_from_numpy(mat))
+        o.vmp_prepare(pmo, mat)
+        rg, ro = g.vec_znx_dft_alloc(cols_out, size_out), o.vec_znx_dft_alloc(cols_out, size_out)
+        g.vmp_apply_dft(rg, g.vec_znx_from_numpy(a), pmg)
+        copy = min(a_cols, cols_in)
+        a_dft_size = min(a_size, rows)
+        ado = o.vec_znx_dft_alloc(cols_in, a_dft_size)  # allocated zeroed: the leading `offset` columns stay zero
+        for j in range(copy):
+            o.vec_znx_dft_apply(1, 0, ado, cols_in - copy + j, a, a_cols - copy + j)
+        o.vmp_apply_dft_to_dft(ro, ado, pmo, 0)
+        big_g, big_o = g.vec_znx_idft_apply_consume(rg), o.vec_znx_idft_apply_consume(ro)
+        out_g, out_o = g.vec_znx_alloc(cols_out, size_out), o.vec_znx_alloc(cols_out, size_out)
+        for c in range(cols_out):
+            g.vec_znx_big_normalize(out_g, k, 0, c, big_g, k, c)
+            o.vec_znx_big_normalize(out_o, k, 0, c, big_o, k, c)
+        assert np.array_equal(g.vec_znx_to_numpy(out_g), out_o), (a_cols, cols_in, cols_out, a_size, rows, size_out)
