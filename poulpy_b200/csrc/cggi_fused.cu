@@ -6,6 +6,8 @@
 //   acc     = normalize(round(IFFT(acc_add)) + acc)      (vec_znx_idft_apply + big_add_small_assign + big_normalize)
 // Nothing but the final accumulator, the LWE coefficients and the key stream touches global memory: the unfused HAL sequence
 // moves ~1.2 MB per block and ciphertext through HBM, this kernel moves 32 KB (the i64 accumulator, L2 resident).
+#include <stdlib.h>
+
 #include "internal.h"
 #include "fft64.cuh"
 
@@ -213,6 +215,479 @@ template <int LM, int G, int RT> __global__ void __launch_bounds__(G << LM) cggi
     }
 }
 
+// ---- version 2: register-blocked key products ----------------------------------------------------------------------
+// ncu on the kernel above (profiles/r1_ncu_fused_v2.md): mio_throttle / long_scoreboard stalls, FP64 pipe 22 % busy.  Per key and
+// frequency it re-reads the 16 accumulator values and read-modify-writes the 32 partial sums through shared memory (288 complex
+// LDS/STS per frequency and block) -- at 128 B/clk of shared-memory bandwidth that, not FP64, is the limit.  Here one thread owns a
+// (ciphertext, frequency) pair for the whole block: its RT accumulator values and its C partial sums stay in registers across the
+// block_size keys (48 complex shared-memory accesses per frequency and block), the lanes of a warp cover 32/G consecutive
+// frequencies x G ciphertexts so that a key value is fetched once per warp and broadcast, and the products are written over the
+// transform buffers they were read from (out[g][p] aliases acc_dft[g][p]; every thread touches only its own frequency).
+template <int LM, int G, int RT, int CT> __global__ void __launch_bounds__(512, 1)
+cggi_fused2_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf, const double2 *__restrict__ twi, double inv_m) {
+    typedef FGeo<LM> FG;
+    constexpr int M = 1 << LM, N = 2 * M, T = FG::T, NT = 512, PL = FG::PLANE, NSLOT = NT / T;
+    constexpr int PMAX = RT > CT ? RT : CT; // polys per ciphertext held in shared memory
+    static_assert(G * M == 1024 && LM > FG::R0, "geometry");
+    extern __shared__ __align__(16) double2 csm[];
+    __shared__ int s_pos[G * 8];
+    const int cols = p.cols, C = cols * p.brk_size, K = p.base2k, bs = p.block_size;
+    const int tid = threadIdx.x, slot = tid / T, t = tid % T;
+    const int ct0 = blockIdx.x * G;
+    const int mn_small = min(p.brk_size, p.out_size);
+    const int a_start = min(p.out_size, p.brk_size);
+
+    for (int blk = 0; blk + bs <= p.n_lwe; blk += bs) {
+        // rotation amounts of the block (at most 8 keys per block, checked on the host)
+        if (tid < G * bs) {
+            const int g = tid / bs, tt = tid % bs, ct = ct0 + g;
+            const long long ai = ct < p.batch ? p.lwe[(size_t)ct * p.lwe_stride + 1 + blk + tt] : 0;
+            s_pos[g * 8 + tt] = (int)((ai + (long long)(2 * N)) & (long long)(2 * N - 1));
+        }
+        // ---- acc_dft = FFT(acc): G * RT transforms, NSLOT at a time -------------------------------------------------------
+        for (int base = 0; base < G * RT; base += NSLOT) {
+            const int job = base + slot;
+            const bool valid = job < G * RT;
+            const int g = valid ? job / RT : 0, r = valid ? job % RT : 0, limb = r / cols, col = r % cols;
+            double2 *buf = csm + (g * PMAX + r) * PL;
+            if (valid) {
+                const int ct = ct0 + g;
+                const bool live = ct < p.batch && limb < p.out_size;
+                const long long *src = p.res + (size_t)(live ? ct : 0) * p.res_stride + (size_t)(limb * cols + col) * N;
+                double2 x[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) {
+                    const int idx = t + jj * T;
+                    x[jj] = live ? make_double2((double)src[idx], (double)src[idx + M]) : make_double2(0.0, 0.0);
+                }
+                fct_radix8<FG::R0>(x, twf, 1u);
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) buf[FPAD(t + jj * T)] = x[jj];
+            }
+            __syncthreads();
+            SmFwd<LM, FG::R0>::run(buf, twf, t, valid);
+        }
+        // ---- out[g][p] = sum_t (X^{a_t} - 1) * (acc_dft[g] x BRK_t)[p], one (g, f) pair per thread and round ------------------
+#pragma unroll 1
+        for (int it = tid; it < G * M; it += NT) {
+            const int g = it % G, f = it / G;
+            double2 *mine = csm + (size_t)g * PMAX * PL + FPAD(f);
+            double ar[RT], ai[RT];
+#pragma unroll
+            for (int r = 0; r < RT; r++) {
+                const double2 a = mine[r * PL];
+                ar[r] = a.x;
+                ai[r] = a.y;
+            }
+            double sr[CT], si[CT];
+#pragma unroll
+            for (int q = 0; q < CT; q++) sr[q] = si[q] = 0.0;
+#pragma unroll 1
+            for (int tt = 0; tt < bs; tt++) {
+                const double *bk = p.brk + (size_t)(blk + tt) * p.brk_doubles + f;
+                const double *w = p.xpa + (size_t)s_pos[g * 8 + tt] * N + f;
+                const double wr = __ldg(w), wi = __ldg(w + M);
+#pragma unroll
+                for (int q = 0; q < CT; q++) {
+                    if (q < C) {
+                        double vr = 0.0, vi = 0.0;
+#pragma unroll
+                        for (int r = 0; r < RT; r++) { // row order of reim4_add_mul (reim4/arithmetic_ref.rs:223-232), FMA-contracted
+                            const double *pp = bk + ((size_t)r * C + q) * N;
+                            const double br = __ldg(pp), bi = __ldg(pp + M);
+                            vr = fma(ar[r], br, vr);
+                            vr = fma(-ai[r], bi, vr);
+                            vi = fma(ar[r], bi, vi);
+                            vi = fma(ai[r], br, vi);
+                        }
+                        const double pr = fma(wr, vr, -(wi * vi)), pi = fma(wr, vi, wi * vr); // svp: reim_mul(ppol, v)
+                        sr[q] = (sr[q] + pr) - vr; // dft_add_assign then dft_sub_assign
+                        si[q] = (si[q] + pi) - vi;
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < CT; q++)
+                if (q < C) mine[q * PL] = make_double2(sr[q], si[q]);
+        }
+        __syncthreads();
+        // ---- acc = normalize(round(IFFT(out) / m) + acc): G * C transforms, NSLOT at a time --------------------------------
+        for (int base = 0; base < G * C; base += NSLOT) {
+            const int job = base + slot;
+            const bool valid = job < G * C;
+            const int g = valid ? job / C : 0, q = valid ? job % C : 0;
+            double2 *buf = csm + (g * PMAX + q) * PL;
+            if (valid) {
+                double2 x[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) x[jj] = buf[FPAD(8 * t + jj)];
+                fgs_radix8<3>(x, twi, (1u << (LM - 3)) | (uint32_t)t);
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) buf[FPAD(8 * t + jj)] = x[jj];
+            }
+            __syncthreads();
+            SmInv<LM, (LM - 6 >= FG::R0) ? LM - 6 : -1>::run(buf, twi, t, valid);
+            double2 x[8];
+            if (valid) {
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) x[jj] = buf[FPAD(t + jj * T)];
+                fgs_radix8<FG::R0>(x, twi, 1u);
+            }
+            __syncthreads(); // the transform has read its inputs: the buffer is reused for the rounded i64 coefficients
+            if (valid) {
+                long long *big = reinterpret_cast<long long *>(buf);
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) {
+                    const int idx = t + jj * T;
+                    big[idx] = (long long)round(x[jj].x * inv_m); // reim_to_znx_i64 (conversion.rs:43-52)
+                    big[idx + M] = (long long)round(x[jj].y * inv_m);
+                }
+            }
+        }
+        __syncthreads();
+        for (int item = tid; item < G * cols * N; item += NT) {
+            const int g = item / (cols * N), col = (item / N) % cols, i = item % N;
+            const int ct = ct0 + g;
+            if (ct >= p.batch) continue;
+            long long *acc = p.res + (size_t)ct * p.res_stride + (size_t)col * N + i; // limb j at + j*cols*N
+            long long c = 0;
+            for (int j = p.brk_size - 1; j >= 0; j--) {
+                long long v = reinterpret_cast<const long long *>(csm + (g * PMAX + j * cols + col) * PL)[i];
+                if (j < mn_small) v = (long long)((unsigned long long)v + (unsigned long long)acc[(size_t)j * cols * N]);
+                const long long tsum = (long long)((unsigned long long)v + (unsigned long long)c);
+                const long long out = (long long)((unsigned long long)tsum << (64 - K)) >> (64 - K);
+                c = (long long)((unsigned long long)tsum - (unsigned long long)out) >> K;
+                if (j < a_start) acc[(size_t)j * cols * N] = out;
+            }
+            for (int j = a_start; j < p.out_size; j++) acc[(size_t)j * cols * N] = 0;
+        }
+        __syncthreads();
+    }
+}
+
+// Synchronisation among the T = m/8 threads that own one transform: a warp (or less) needs no CTA barrier at all, larger groups
+// use one named barrier per transform slot.  The CTA-wide __syncthreads of versions 1/2 made every radix-8 pass wait for all warps.
+template <int T> __device__ __forceinline__ void poly_sync(int slot) {
+    if (T <= 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(T) : "memory");
+}
+template <int L, int L0> struct SmFwdP {
+    static __device__ __forceinline__ void run(double2 *buf, const double2 *tw, int t, int slot, bool valid) {
+        constexpr int SL = L - L0 - 3;
+        if (valid) {
+            const int a = t >> SL, b = t & ((1 << SL) - 1), base = (a << (SL + 3)) | b;
+            double2 x[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) x[j] = buf[FPAD(base + (j << SL))];
+            fct_radix8<3, true>(x, tw, (1u << L0) | (uint32_t)a);
+#pragma unroll
+            for (int j = 0; j < 8; j++) buf[FPAD(base + (j << SL))] = x[j];
+        }
+        poly_sync<FGeo<L>::T>(slot);
+        SmFwdP<L, (L0 + 3 < L) ? L0 + 3 : L>::run(buf, tw, t, slot, valid);
+    }
+};
+template <int L> struct SmFwdP<L, L> {
+    static __device__ __forceinline__ void run(double2 *, const double2 *, int, int, bool) {}
+};
+template <int L, int L0> struct SmInvP {
+    static __device__ __forceinline__ void run(double2 *buf, const double2 *tw, int t, int slot, bool valid) {
+        typedef FGeo<L> G;
+        constexpr int SL = L - L0 - 3;
+        if (valid) {
+            const int a = t >> SL, b = t & ((1 << SL) - 1), base = (a << (SL + 3)) | b;
+            double2 x[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) x[j] = buf[FPAD(base + (j << SL))];
+            fgs_radix8<3, true>(x, tw, (1u << L0) | (uint32_t)a);
+#pragma unroll
+            for (int j = 0; j < 8; j++) buf[FPAD(base + (j << SL))] = x[j];
+        }
+        poly_sync<G::T>(slot);
+        SmInvP<L, (L0 - 3 >= G::R0) ? L0 - 3 : -1>::run(buf, tw, t, slot, valid);
+    }
+};
+template <int L> struct SmInvP<L, -1> {
+    static __device__ __forceinline__ void run(double2 *, const double2 *, int, int, bool) {}
+};
+
+// ---- version 3: key stream through TMA bulk copies -------------------------------------------------------------------
+// Version 2 stalls on the L2 latency of the key values (long_scoreboard 7.8 warps per issue, FP64 pipe 15 %).  The key stream is
+// perfectly predictable, so here thread 0 keeps a ring of NSTAGE shared-memory tiles filled with cp.async.bulk (one tile = the RT
+// rows of one output poly of one key = RT contiguous chunks of 8n bytes, completion on an mbarrier), running ahead of the compute
+// threads across the transform phases.  A thread owns one frequency of TWO ciphertexts (g and g + G/2): a key value read from the
+// tile feeds both, and the 2 x (RT + C) complex values it needs stay in registers for the whole block.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+
+template <int LM, int G, int RT, int CT, int NSTAGE> __global__ void __launch_bounds__(512, 1)
+cggi_fused3_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, const double2 *__restrict__ twi_g, double inv_m) {
+    typedef FGeo<LM> FG;
+    constexpr int M = 1 << LM, N = 2 * M, T = FG::T, NT = 512, PL = FG::PLANE, NSLOT = NT / T, GH = G / 2;
+    constexpr int PMAX = RT > CT ? RT : CT;
+    constexpr uint32_t CHUNK = N * 8, TILE = RT * CHUNK; // bytes
+    static_assert(GH * M == NT && GH >= 1 && LM > FG::R0, "geometry");
+    extern __shared__ __align__(128) double2 csm[];
+    __shared__ int s_pos[G * 8];
+    __shared__ __align__(8) unsigned long long s_bar[NSTAGE], s_empty[NSTAGE]; // tile filled / tile consumed by all threads
+    double *ring = reinterpret_cast<double *>(csm + (size_t)G * PMAX * PL); // [NSTAGE][RT][N]
+    // both twiddle tables (m complex values each) live in shared memory: with ~210 KB of it in use the L1 is too small to keep them
+    double2 *twf = reinterpret_cast<double2 *>(ring + (size_t)NSTAGE * RT * N), *twi = twf + M;
+    for (int i = threadIdx.x; i < M; i += 512) {
+        twf[i] = twf_g[i];
+        twi[i] = twi_g[i];
+    }
+    const int cols = p.cols, C = cols * p.brk_size, K = p.base2k, bs = p.block_size;
+    const int tid = threadIdx.x, slot = tid / T, t = tid % T;
+    const int ct0 = blockIdx.x * G;
+    const int mn_small = min(p.brk_size, p.out_size);
+    const int a_start = min(p.out_size, p.brk_size);
+    const int nblk = p.n_lwe / bs, tiles_per_blk = bs * C, total_tiles = nblk * tiles_per_blk;
+    const uint32_t ring_s = smem_u32(ring), bar_s = smem_u32(s_bar), empty_s = smem_u32(s_empty);
+
+    // tile gk -> key (gk / C), output poly gk % C: rows r at brk + key * brk_doubles + (r * C + q) * N
+    auto issue = [&](int gk) {
+        const int st = gk % NSTAGE, key = gk / C, q = gk % C;
+        const uint32_t bar = bar_s + st * 8;
+        mbar_expect_tx(bar, TILE);
+        const double *src = p.brk + (size_t)key * p.brk_doubles + (size_t)q * N;
+#pragma unroll
+        for (int r = 0; r < RT; r++) bulk_g2s(ring_s + (uint32_t)(st * RT + r) * CHUNK, src + (size_t)r * C * N, CHUNK, bar);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; s++) {
+            mbar_init(bar_s + s * 8, 1);
+            mbar_init(empty_s + s * 8, NT);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int gk = 0; gk < NSTAGE && gk < total_tiles; gk++) issue(gk);
+
+    const int gp = tid % GH, f = tid / GH; // this thread's frequency and its two ciphertexts gp, gp + GH
+    double2 *mine0 = csm + (size_t)gp * PMAX * PL + FPAD(f), *mine1 = csm + (size_t)(gp + GH) * PMAX * PL + FPAD(f);
+    int gk = 0;
+
+    for (int blk = 0; blk + bs <= p.n_lwe; blk += bs) {
+        if (tid < G * bs) {
+            const int g = tid / bs, tt = tid % bs, ct = ct0 + g;
+            const long long ai = ct < p.batch ? p.lwe[(size_t)ct * p.lwe_stride + 1 + blk + tt] : 0;
+            s_pos[g * 8 + tt] = (int)((ai + (long long)(2 * N)) & (long long)(2 * N - 1));
+        }
+        // ---- acc_dft = FFT(acc) ------------------------------------------------------------------------------------------
+        for (int base = 0; base < G * RT; base += NSLOT) {
+            const int job = base + slot;
+            const bool valid = job < G * RT;
+            const int g = valid ? job / RT : 0, r = valid ? job % RT : 0, limb = r / cols, col = r % cols;
+            double2 *buf = csm + (g * PMAX + r) * PL;
+            if (valid) {
+                const int ct = ct0 + g;
+                const bool live = ct < p.batch && limb < p.out_size;
+                const long long *src = p.res + (size_t)(live ? ct : 0) * p.res_stride + (size_t)(limb * cols + col) * N;
+                double2 x[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) {
+                    const int idx = t + jj * T;
+                    x[jj] = live ? make_double2((double)src[idx], (double)src[idx + M]) : make_double2(0.0, 0.0);
+                }
+                fct_radix8<FG::R0, true>(x, twf, 1u);
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) buf[FPAD(t + jj * T)] = x[jj];
+            }
+            poly_sync<T>(slot);
+            SmFwdP<LM, FG::R0>::run(buf, twf, t, slot, valid);
+        }
+        __syncthreads(); // every transform of the block is complete before the key products read across them
+        // ---- key products: tiles in (key, poly) order -----------------------------------------------------------------------
+        {
+            double a0r[RT], a0i[RT], a1r[RT], a1i[RT];
+#pragma unroll
+            for (int r = 0; r < RT; r++) {
+                const double2 u = mine0[r * PL], v = mine1[r * PL];
+                a0r[r] = u.x; a0i[r] = u.y; a1r[r] = v.x; a1i[r] = v.y;
+            }
+            double s0r[CT], s0i[CT], s1r[CT], s1i[CT];
+#pragma unroll
+            for (int q = 0; q < CT; q++) s0r[q] = s0i[q] = s1r[q] = s1i[q] = 0.0;
+#pragma unroll 1
+            for (int tt = 0; tt < bs; tt++) {
+                const double *w0 = p.xpa + (size_t)s_pos[gp * 8 + tt] * N + f, *w1 = p.xpa + (size_t)s_pos[(gp + GH) * 8 + tt] * N + f;
+                const double w0r = __ldg(w0), w0i = __ldg(w0 + M), w1r = __ldg(w1), w1i = __ldg(w1 + M);
+#pragma unroll
+                for (int q = 0; q < CT; q++) {
+                    if (q < C) { // uniform
+                        const int st = gk % NSTAGE;
+                        mbar_wait(bar_s + st * 8, (uint32_t)((gk / NSTAGE) & 1));
+                        const double *tile = ring + (size_t)st * RT * N + f;
+                        double v0r = 0.0, v0i = 0.0, v1r = 0.0, v1i = 0.0;
+#pragma unroll
+                        for (int r = 0; r < RT; r++) { // row order of reim4_add_mul (reim4/arithmetic_ref.rs:223-232), FMA-contracted
+                            const double br = tile[r * N], bi = tile[r * N + M];
+                            v0r = fma(a0r[r], br, v0r); v0r = fma(-a0i[r], bi, v0r);
+                            v0i = fma(a0r[r], bi, v0i); v0i = fma(a0i[r], br, v0i);
+                            v1r = fma(a1r[r], br, v1r); v1r = fma(-a1i[r], bi, v1r);
+                            v1i = fma(a1r[r], bi, v1i); v1i = fma(a1i[r], br, v1i);
+                        }
+                        const double p0r = fma(w0r, v0r, -(w0i * v0i)), p0i = fma(w0r, v0i, w0i * v0r); // svp: reim_mul(ppol, v)
+                        const double p1r = fma(w1r, v1r, -(w1i * v1i)), p1i = fma(w1r, v1i, w1i * v1r);
+                        s0r[q] = (s0r[q] + p0r) - v0r; s0i[q] = (s0i[q] + p0i) - v0i; // dft_add_assign then dft_sub_assign
+                        s1r[q] = (s1r[q] + p1r) - v1r; s1i[q] = (s1i[q] + p1i) - v1i;
+                        // consumer release; thread 0 refills the stage once all 512 threads have released it (only its warp waits)
+                        mbar_arrive(empty_s + st * 8);
+                        if (tid == 0 && gk + NSTAGE < total_tiles) {
+                            mbar_wait(empty_s + st * 8, (uint32_t)((gk / NSTAGE) & 1));
+                            issue(gk + NSTAGE);
+                        }
+                        gk++;
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < CT; q++)
+                if (q < C) {
+                    mine0[q * PL] = make_double2(s0r[q], s0i[q]);
+                    mine1[q * PL] = make_double2(s1r[q], s1i[q]);
+                }
+        }
+        __syncthreads();
+        // ---- acc = normalize(round(IFFT(out) / m) + acc) -----------------------------------------------------------------------
+        for (int base = 0; base < G * C; base += NSLOT) {
+            const int job = base + slot;
+            const bool valid = job < G * C;
+            const int g = valid ? job / C : 0, q = valid ? job % C : 0;
+            double2 *buf = csm + (g * PMAX + q) * PL;
+            if (valid) {
+                double2 x[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) x[jj] = buf[FPAD(8 * t + jj)];
+                fgs_radix8<3, true>(x, twi, (1u << (LM - 3)) | (uint32_t)t);
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) buf[FPAD(8 * t + jj)] = x[jj];
+            }
+            poly_sync<T>(slot);
+            SmInvP<LM, (LM - 6 >= FG::R0) ? LM - 6 : -1>::run(buf, twi, t, slot, valid);
+            double2 x[8];
+            if (valid) {
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) x[jj] = buf[FPAD(t + jj * T)];
+                fgs_radix8<FG::R0, true>(x, twi, 1u);
+            }
+            poly_sync<T>(slot); // the transform has read its inputs: the buffer is reused for the rounded i64 coefficients
+            if (valid) {
+                long long *big = reinterpret_cast<long long *>(buf);
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) {
+                    const int idx = t + jj * T;
+                    big[idx] = (long long)round(x[jj].x * inv_m); // reim_to_znx_i64 (conversion.rs:43-52)
+                    big[idx + M] = (long long)round(x[jj].y * inv_m);
+                }
+            }
+        }
+        __syncthreads();
+        // brk_size <= 4 here (checked on the host): all loads of a coefficient are issued before its carry chain; 32-bit offsets
+        {
+            const int limb_w = cols * N, bsz = p.brk_size;
+            for (int g = 0; g < G; g++) {
+                if (ct0 + g >= p.batch) break;
+                long long *acc_g = p.res + (size_t)(ct0 + g) * p.res_stride;
+                const long long *big_g = reinterpret_cast<const long long *>(csm + (size_t)g * PMAX * PL);
+                for (int col = 0; col < cols; col++) {
+#pragma unroll
+                    for (int i = tid; i < N; i += NT) {
+                        const int o = col * N + i;
+                        long long vv[4], aa[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            vv[j] = j < bsz ? big_g[(j * cols + col) * (2 * PL) + i] : 0;
+                            aa[j] = j < mn_small ? acc_g[o + j * limb_w] : 0;
+                        }
+                        long long c = 0;
+#pragma unroll
+                        for (int j = 3; j >= 0; j--) {
+                            if (j < bsz) {
+                                const long long tsum = (long long)((unsigned long long)vv[j] + (unsigned long long)aa[j] + (unsigned long long)c);
+                                const long long out = (long long)((unsigned long long)tsum << (64 - K)) >> (64 - K);
+                                c = (long long)((unsigned long long)tsum - (unsigned long long)out) >> K;
+                                if (j < a_start) acc_g[o + j * limb_w] = out;
+                            }
+                        }
+                        for (int j = a_start; j < p.out_size; j++) acc_g[o + j * limb_w] = 0;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int LM, int G, int RT, int CT, int NSTAGE> static int launch_cggi3(pgb_module *m, const CggiFusedArgs &p) {
+    typedef FGeo<LM> FG;
+    constexpr int PMAX = RT > CT ? RT : CT;
+    const size_t smem = (size_t)G * PMAX * FG::PLANE * sizeof(double2) + (size_t)NSTAGE * RT * (2 << LM) * 8 + (size_t)2 * (1 << LM) * sizeof(double2);
+    PGB_CHECK_CUDA(cudaFuncSetAttribute(cggi_fused3_fft64_kernel<LM, G, RT, CT, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (p.batch + G - 1) / G;
+    { ProfScope _ps(m, PROF_OTHER);
+    cggi_fused3_fft64_kernel<LM, G, RT, CT, NSTAGE><<<grid, 512, smem, m->stream>>>(p, m->fft_fwd, m->fft_inv, 1.0 / (double)(1 << LM));
+    }
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+template <int LM, int G, int NSTAGE> static int launch_cggi3_shape(pgb_module *m, const CggiFusedArgs &p, int R, int C, bool *handled) {
+    *handled = true;
+    if (R == 4 && C > 4 && C <= 8) return launch_cggi3<LM, G, 4, 8, NSTAGE>(m, p);
+    if (R == 4 && C <= 4) return launch_cggi3<LM, G, 4, 4, NSTAGE>(m, p);
+    if (R == 2 && C > 4 && C <= 8) return launch_cggi3<LM, G, 2, 8, NSTAGE>(m, p);
+    if (R == 2 && C <= 4) return launch_cggi3<LM, G, 2, 4, NSTAGE>(m, p);
+    *handled = false;
+    return PGB_OK;
+}
+
+template <int LM, int G, int RT, int CT> static int launch_cggi2(pgb_module *m, const CggiFusedArgs &p) {
+    typedef FGeo<LM> FG;
+    constexpr int PMAX = RT > CT ? RT : CT;
+    const size_t smem = (size_t)G * PMAX * FG::PLANE * sizeof(double2);
+    PGB_CHECK_CUDA(cudaFuncSetAttribute(cggi_fused2_fft64_kernel<LM, G, RT, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (p.batch + G - 1) / G;
+    { ProfScope _ps(m, PROF_OTHER);
+    cggi_fused2_fft64_kernel<LM, G, RT, CT><<<grid, 512, smem, m->stream>>>(p, m->fft_fwd, m->fft_inv, 1.0 / (double)(1 << LM));
+    }
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+// shapes the register-blocked kernel is instantiated for: rows in {2, 4}, at most 8 output polys, at most 8 keys per block
+template <int LM, int G> static int launch_cggi2_shape(pgb_module *m, const CggiFusedArgs &p, int R, int C, bool *handled) {
+    *handled = true;
+    if (R == 4 && C > 4 && C <= 8) return launch_cggi2<LM, G, 4, 8>(m, p);
+    if (R == 4 && C <= 4) return launch_cggi2<LM, G, 4, 4>(m, p);
+    if (R == 2 && C > 4 && C <= 8) return launch_cggi2<LM, G, 2, 8>(m, p);
+    if (R == 2 && C <= 4) return launch_cggi2<LM, G, 2, 4>(m, p);
+    *handled = false;
+    return PGB_OK;
+}
+
 template <int LM, int G, int RT> static int launch_cggi(pgb_module *m, const CggiFusedArgs &p, int C) {
     typedef FGeo<LM> FG;
     const size_t smem = (size_t)G * (RT + C) * FG::PLANE * sizeof(double2);
@@ -251,6 +726,30 @@ int cggi_fused_fft64(pgb_module *m, long long *res, uint64_t res_stride_words, c
                      int out_size, int batch) {
     CggiFusedArgs p = {res, res_stride_words, lwe, lwe_stride, brk, brk_doubles, xpa, n_lwe, block_size, base2k, cols, dnum, brk_size, out_size, batch};
     const int R = cols * dnum, C = cols * brk_size;
+    if (block_size <= 8 && !getenv("PGB_CGGI_V1") && !getenv("PGB_CGGI_V2") && (brk_doubles % 2) == 0 && brk_size <= 4) {
+        // TMA key stream (tiles must be 16-byte aligned: brk is a cudaMalloc'd / 64-byte aligned buffer of whole polys)
+        bool handled = false;
+        int s = PGB_OK;
+        switch (m->log_n) {
+        case 8: s = launch_cggi3_shape<7, 8, 4>(m, p, R, C, &handled); break;
+        case 9: s = launch_cggi3_shape<8, 4, 4>(m, p, R, C, &handled); break;
+        case 10: s = launch_cggi3_shape<9, 2, 2>(m, p, R, C, &handled); break;
+        default: break;
+        }
+        if (handled) return s;
+    }
+    if (block_size <= 8 && !getenv("PGB_CGGI_V1")) {
+        bool handled = false;
+        int s = PGB_OK;
+        switch (m->log_n) {
+        case 8: s = launch_cggi2_shape<7, 8>(m, p, R, C, &handled); break;
+        case 9: s = launch_cggi2_shape<8, 4>(m, p, R, C, &handled); break;
+        case 10: s = launch_cggi2_shape<9, 2>(m, p, R, C, &handled); break;
+        case 11: s = launch_cggi2_shape<10, 1>(m, p, R, C, &handled); break;
+        default: break;
+        }
+        if (handled) return s;
+    }
     switch (m->log_n) {
     case 8: return launch_cggi_rt<7, 8>(m, p, R, C);
     case 9: return launch_cggi_rt<8, 4>(m, p, R, C);

@@ -21,18 +21,21 @@ __device__ __forceinline__ void fgs_bf(double2 &x, double2 &y, double2 w) { // (
     x = make_double2(x.x + y.x, x.y + y.y);
     y = make_double2(rd * w.x - id * w.y, rd * w.y + id * w.x);
 }
-__device__ __forceinline__ double2 ldw(const double2 *p) {
+// twiddle load: read-only global tables go through the non-coherent path (TWS = false), shared-memory copies (fused CGGI
+// kernel, TWS = true) through plain loads
+template <bool TWS = false> __device__ __forceinline__ double2 ldw(const double2 *p) {
+    if (TWS) return *p;
     return make_double2(__ldg(&p->x), __ldg(&p->y));
 }
 
-template <int NLEV> __device__ __forceinline__ void fct_radix8(double2 (&x)[8], const double2 *__restrict__ tw, uint32_t hi) {
+template <int NLEV, bool TWS = false> __device__ __forceinline__ void fct_radix8(double2 (&x)[8], const double2 *__restrict__ tw, uint32_t hi) {
     {
-        double2 w = ldw(tw + hi);
+        double2 w = ldw<TWS>(tw + hi);
 #pragma unroll
         for (int j = 0; j < 4; j++) fct_bf(x[j], x[j + 4], w);
     }
     if (NLEV >= 2) {
-        double2 w0 = ldw(tw + 2 * hi), w1 = ldw(tw + 2 * hi + 1);
+        double2 w0 = ldw<TWS>(tw + 2 * hi), w1 = ldw<TWS>(tw + 2 * hi + 1);
         fct_bf(x[0], x[2], w0);
         fct_bf(x[1], x[3], w0);
         fct_bf(x[4], x[6], w1);
@@ -40,23 +43,23 @@ template <int NLEV> __device__ __forceinline__ void fct_radix8(double2 (&x)[8], 
     }
     if (NLEV >= 3) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) fct_bf(x[2 * j], x[2 * j + 1], ldw(tw + 4 * hi + j));
+        for (int j = 0; j < 4; j++) fct_bf(x[2 * j], x[2 * j + 1], ldw<TWS>(tw + 4 * hi + j));
     }
 }
-template <int NLEV> __device__ __forceinline__ void fgs_radix8(double2 (&x)[8], const double2 *__restrict__ tw, uint32_t hi) {
+template <int NLEV, bool TWS = false> __device__ __forceinline__ void fgs_radix8(double2 (&x)[8], const double2 *__restrict__ tw, uint32_t hi) {
     if (NLEV >= 3) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) fgs_bf(x[2 * j], x[2 * j + 1], ldw(tw + 4 * hi + j));
+        for (int j = 0; j < 4; j++) fgs_bf(x[2 * j], x[2 * j + 1], ldw<TWS>(tw + 4 * hi + j));
     }
     if (NLEV >= 2) {
-        double2 w0 = ldw(tw + 2 * hi), w1 = ldw(tw + 2 * hi + 1);
+        double2 w0 = ldw<TWS>(tw + 2 * hi), w1 = ldw<TWS>(tw + 2 * hi + 1);
         fgs_bf(x[0], x[2], w0);
         fgs_bf(x[1], x[3], w0);
         fgs_bf(x[4], x[6], w1);
         fgs_bf(x[5], x[7], w1);
     }
     {
-        double2 w = ldw(tw + hi);
+        double2 w = ldw<TWS>(tw + hi);
 #pragma unroll
         for (int j = 0; j < 4; j++) fgs_bf(x[j], x[j + 4], w);
     }
