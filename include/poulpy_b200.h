@@ -252,6 +252,17 @@ int pgb_glwe_external_product_host(pgb_module *m, int64_t *res_host, uint64_t re
                                    const int64_t *a_host, uint64_t a_size, uint64_t a_base2k, uint64_t rank,
                                    const pgb_vmp_pmat *ggsw, uint64_t ggsw_base2k, uint64_t dsize, uint64_t count);
 
+/* ---- coefficient-domain helpers of execute_standard ---- */
+/* vec_znx_add_assign / sub_assign (poulpy-cpu-ref/src/reference/vec_znx/add.rs:60-82, sub.rs:60-82) */
+int pgb_vec_znx_add_assign(pgb_module *m, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col);
+int pgb_vec_znx_add_assign_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col,
+                                   const pgb_batch *bt);
+int pgb_vec_znx_sub_assign(pgb_module *m, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col);
+/* vec_znx_mul_xp_minus_one (reference/vec_znx/mul_xp_minus_one.rs:13-22): res = X^p * a - a; res and a must not alias */
+int pgb_vec_znx_mul_xp_minus_one(pgb_module *m, int64_t p, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col);
+/* vec_znx_normalize_assign (reference/vec_znx/normalize.rs:403-425) */
+int pgb_vec_znx_normalize_assign(pgb_module *m, uint64_t base2k, pgb_vec_znx *res, uint64_t res_col);
+
 /* ---- CGGI blind rotation (poulpy-bin-fhe/src/blind_rotation/algorithms/cggi/algorithm.rs:275-368; C3) ---- */
 /* x_pow_a table of the prepared key (cggi/key_prepared.rs:66-75): SvpPPol with 2n columns, col i = X^i. */
 int pgb_cggi_x_pow_a(pgb_module *m, pgb_svp_ppol *res);

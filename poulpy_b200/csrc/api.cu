@@ -716,3 +716,49 @@ extern "C" int pgb_vec_znx_rotate(pgb_module *m, int64_t p, pgb_vec_znx *res, ui
     PGB_TRY(raw_limbs(m, true, shift(R, mn), shift(R, mn), n * 8, (uint32_t)(res->size - mn), 1));
     return sync_if(m, true);
 }
+
+// ---- coefficient-domain helpers used by execute_standard --------------------------------------------------------
+// vec_znx_add_assign / vec_znx_sub_assign (reference/vec_znx/add.rs:60-82, sub.rs:60-82): the first min(res.size, a.size) limbs
+static int znx_assign_impl(pgb_module *m, int op, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col, const pgb_batch *bt) {
+    CHECK_BATCH(bt);
+    CHECK_N(res, "vec_znx_add/sub_assign(res)");
+    CHECK_N(a, "vec_znx_add/sub_assign(a)");
+    CHECK_COL(res, res_col, "vec_znx_add/sub_assign(res)");
+    CHECK_COL(a, a_col, "vec_znx_add/sub_assign(a)");
+    const uint64_t n = m->n;
+    LimbSet R = {(char *)res->data + limb_off(n, res->cols, res_col, 0, 8), res->cols * n * 8, bt->stride_res};
+    LimbSet A = {(char *)a->data + limb_off(n, a->cols, a_col, 0, 8), a->cols * n * 8, bt->stride_a};
+    return znx_ew(m, op, R, A, 0, nullptr, 0, (uint32_t)umin64(res->size, a->size), (uint32_t)bt->count);
+}
+extern "C" int pgb_vec_znx_add_assign(pgb_module *m, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col) {
+    PGB_TRY(znx_assign_impl(m, 0, res, res_col, a, a_col, &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_vec_znx_add_assign_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col,
+                                              const pgb_batch *bt) {
+    return znx_assign_impl(m, 0, res, res_col, a, a_col, bt);
+}
+extern "C" int pgb_vec_znx_sub_assign(pgb_module *m, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col) {
+    PGB_TRY(znx_assign_impl(m, 1, res, res_col, a, a_col, &ONE));
+    return sync_if(m, true);
+}
+// vec_znx_mul_xp_minus_one (reference/vec_znx/mul_xp_minus_one.rs:13-22): res = rotate(p, a) - a on the common limbs, zero the rest
+// (rotate zero-fills, sub_assign only touches the common limbs).  res and a must not alias.
+extern "C" int pgb_vec_znx_mul_xp_minus_one(pgb_module *m, int64_t p, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col) {
+    CHECK_N(res, "vec_znx_mul_xp_minus_one(res)");
+    CHECK_N(a, "vec_znx_mul_xp_minus_one(a)");
+    CHECK_COL(res, res_col, "vec_znx_mul_xp_minus_one(res)");
+    CHECK_COL(a, a_col, "vec_znx_mul_xp_minus_one(a)");
+    PGB_REQUIRE(res->data != a->data, "vec_znx_mul_xp_minus_one: res and a must not alias");
+    const uint64_t n = m->n, mn = umin64(res->size, a->size);
+    LimbSet R = {(char *)res->data + limb_off(n, res->cols, res_col, 0, 8), res->cols * n * 8, 0};
+    LimbSet A = {(char *)a->data + limb_off(n, a->cols, a_col, 0, 8), a->cols * n * 8, 0};
+    PGB_TRY(znx_ew(m, 2, R, A, p, nullptr, 0, (uint32_t)mn, 1));
+    PGB_TRY(raw_limbs(m, true, shift(R, mn), shift(R, mn), n * 8, (uint32_t)(res->size - mn), 1));
+    return sync_if(m, true);
+}
+// vec_znx_normalize_assign (reference/vec_znx/normalize.rs:403-425): in place, equal base2k, offset 0
+extern "C" int pgb_vec_znx_normalize_assign(pgb_module *m, uint64_t base2k, pgb_vec_znx *res, uint64_t res_col) {
+    PGB_TRY(big_normalize_impl(m, res, base2k, 0, res_col, res, base2k, res_col, 0, false, &ONE));
+    return sync_if(m, true);
+}

@@ -337,6 +337,41 @@ int znx_rotate(pgb_module *m, LimbSet dst, LimbSet a, long long p, const long lo
     return PGB_OK;
 }
 
+// i64 element-wise helpers of the coefficient domain: dst (op)= a, and dst = rotate(p, a) - a (vec_znx_mul_xp_minus_one)
+struct ZnxEwArgs {
+    LimbSet dst, a;
+    uint32_t n;
+    int op; // 0 add_assign, 1 sub_assign, 2 mul_xp_minus_one (dst = X^p a - a)
+    const long long *p_dev;
+    long long p;
+    uint32_t p_stride;
+};
+__global__ void __launch_bounds__(256) znx_ew_kernel(ZnxEwArgs q) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q.n) return;
+    const long long *src = reinterpret_cast<const long long *>(q.a.base + (size_t)blockIdx.z * q.a.batch_stride + (size_t)blockIdx.y * q.a.limb_stride);
+    long long *dst = reinterpret_cast<long long *>(q.dst.base + (size_t)blockIdx.z * q.dst.batch_stride + (size_t)blockIdx.y * q.dst.limb_stride);
+    if (q.op == 0) {
+        dst[i] = (long long)((unsigned long long)dst[i] + (unsigned long long)src[i]);
+    } else if (q.op == 1) {
+        dst[i] = (long long)((unsigned long long)dst[i] - (unsigned long long)src[i]);
+    } else {
+        const long long p = q.p_dev ? q.p_dev[(size_t)blockIdx.z * q.p_stride] : q.p;
+        const uint32_t n = q.n, mp = (uint32_t)(p & (long long)(2 * n - 1));
+        const uint32_t s = (i - mp) & (2 * n - 1); // coefficient s of a lands on i (negated when it wrapped once)
+        const unsigned long long r = s < n ? (unsigned long long)src[s] : 0ull - (unsigned long long)src[s - n];
+        dst[i] = (long long)(r - (unsigned long long)src[i]);
+    }
+}
+int znx_ew(pgb_module *m, int op, LimbSet dst, LimbSet a, long long p, const long long *p_dev, uint32_t p_stride, uint32_t jobs, uint32_t batch) {
+    if (jobs == 0 || batch == 0) return PGB_OK;
+    ProfScope _ps(m, PROF_ELEMENTWISE);
+    ZnxEwArgs q = {dst, a, (uint32_t)m->n, op, p_dev, p, p_stride};
+    znx_ew_kernel<<<dim3(((uint32_t)m->n + 255) / 256, jobs, batch), 256, 0, m->stream>>>(q);
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+
 // raw byte-wise zero / copy over limb sets (both flavours)
 struct RawArgs {
     LimbSet dst, a;

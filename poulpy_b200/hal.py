@@ -486,6 +486,22 @@ class Module:
                                                     C.c_void_p(a.ctypes.data), _u64(a_size), _u64(a_base2k), _u64(a_cols - 1),
                                                     C.byref(ks), _u64(ggsw_base2k), _u64(dsize), _u64(B)))
 
+    def vec_znx_add_assign(self, res, res_col, a, a_col):
+        r, av = res.struct(), a.struct()
+        _check(lib().pgb_vec_znx_add_assign(self._h, C.byref(r), _u64(res_col), C.byref(av), _u64(a_col)))
+
+    def vec_znx_sub_assign(self, res, res_col, a, a_col):
+        r, av = res.struct(), a.struct()
+        _check(lib().pgb_vec_znx_sub_assign(self._h, C.byref(r), _u64(res_col), C.byref(av), _u64(a_col)))
+
+    def vec_znx_mul_xp_minus_one(self, p, res, res_col, a, a_col):
+        r, av = res.struct(), a.struct()
+        _check(lib().pgb_vec_znx_mul_xp_minus_one(self._h, C.c_int64(p), C.byref(r), _u64(res_col), C.byref(av), _u64(a_col)))
+
+    def vec_znx_normalize_assign(self, base2k, res, res_col):
+        r = res.struct()
+        _check(lib().pgb_vec_znx_normalize_assign(self._h, _u64(base2k), C.byref(r), _u64(res_col)))
+
     def cggi_x_pow_a(self) -> SvpPPol:
         res = self.svp_ppol_alloc(2 * self.n)
         r = res.struct()

@@ -466,3 +466,39 @@ def test_svp_apply_dft_and_vmp_apply_dft_from_coefficients(fl):
             g.vec_znx_big_normalize(out_g, k, 0, c, big_g, k, c)
             o.vec_znx_big_normalize(out_o, k, 0, c, big_o, k, c)
         assert np.array_equal(g.vec_znx_to_numpy(out_g), out_o), (a_cols, cols_in, cols_out, a_size, rows, size_out)
+
+
+def test_coefficient_domain_helpers():
+    """vec_znx_add_assign / sub_assign / mul_xp_minus_one / normalize_assign (the helpers of execute_standard) against
+    the oracle / numpy, including size mismatches and rotations across the negacyclic wrap."""
+    n = 64
+    g = pb.Module(n, pb.FFT64)
+    rng = np.random.default_rng(23)
+    for res_size, a_size in ((3, 3), (2, 4), (4, 2)):
+        r0 = rng.integers(-(1 << 40), 1 << 40, size=(res_size, 2, n), dtype=np.int64)
+        a = rng.integers(-(1 << 40), 1 << 40, size=(a_size, 2, n), dtype=np.int64)
+        mn = min(res_size, a_size)
+        rg, ag = g.vec_znx_from_numpy(r0), g.vec_znx_from_numpy(a)
+        g.vec_znx_add_assign(rg, 1, ag, 0)
+        want = r0.copy()
+        want[:mn, 1] += a[:mn, 0]
+        assert np.array_equal(g.vec_znx_to_numpy(rg), want)
+        g.vec_znx_sub_assign(rg, 1, ag, 0)
+        assert np.array_equal(g.vec_znx_to_numpy(rg), r0)
+        for p in (0, 1, n - 1, n, n + 7, -5, 3 * n + 1):
+            rg = g.vec_znx_from_numpy(r0)
+            g.vec_znx_mul_xp_minus_one(p, rg, 0, ag, 1)
+            rot = np.zeros((res_size, 1, n), dtype=np.int64)
+            O.vec_znx_rotate(p, rot, 0, np.ascontiguousarray(a[:, 1:2]), 0)
+            want = r0.copy()
+            want[:, 0] = rot[:, 0]
+            want[:mn, 0] -= a[:mn, 1]
+            assert np.array_equal(g.vec_znx_to_numpy(rg), want), (res_size, a_size, p)
+    for size in (1, 2, 4):
+        x = rng.integers(-(1 << 50), 1 << 50, size=(size, 2, n), dtype=np.int64)
+        xg = g.vec_znx_from_numpy(x)
+        want = x.copy()
+        for c in range(2):
+            g.vec_znx_normalize_assign(13, xg, c)
+            O.vec_znx_normalize_assign(13, want, c)
+        assert np.array_equal(g.vec_znx_to_numpy(xg), want), size
