@@ -168,3 +168,130 @@ void orc_glwe_external_product(int flavour, const void *mod, orc_vec_znx *res, s
     free(res_dft.data);
     free(a_conv.data);
 }
+
+/* ------------------------------------------------------------------ GLWE tensoring / relinearisation (CKKS multiplication) */
+static void be_cnv_prepare(const be_t *b, orc_vec_znx_dft *r, const orc_vec_znx *a, int64_t mask) {
+    if (b->flavour == 0) orc_ntt120_cnv_prepare((const orc_ntt120_module *)b->mod, r, a, mask);
+    else orc_fft64_cnv_prepare((const orc_fft64_module *)b->mod, r, a, mask);
+}
+static void be_cnv_pairwise(const be_t *b, size_t off, orc_vec_znx_dft *r, const orc_vec_znx_dft *x, const orc_vec_znx_dft *y, size_t i, size_t j) {
+    if (b->flavour == 0) orc_ntt120_cnv_pairwise_apply_dft((const orc_ntt120_module *)b->mod, off, r, 0, x, y, i, j);
+    else orc_fft64_cnv_pairwise_apply_dft(off, r, 0, x, y, i, j);
+}
+/* operations/glwe.rs:921-926 */
+static int64_t msb_mask_bottom_limb(size_t base2k, size_t k) {
+    size_t r = k % base2k;
+    return r == 0 ? ~(int64_t)0 : (int64_t)(~(uint64_t)0 << (base2k - r));
+}
+/* operations/glwe.rs:928-957 */
+static size_t normalize_input_limb_bound_with_offset(size_t full, size_t res_size, size_t res_base2k, size_t in_base2k, int64_t res_offset) {
+    int64_t ob = res_offset % (int64_t)in_base2k;
+    if (res_offset < 0 && ob != 0) ob += (int64_t)in_base2k;
+    return zmin(full, div_ceil(res_size * res_base2k + (size_t)ob, in_base2k));
+}
+static void znx_limbwise(orc_vec_znx *r, size_t rc, const orc_vec_znx *a, size_t ac, int op) { /* sizes are equal here */
+    size_t mn = zmin(r->size, a->size);
+    for (size_t j = 0; j < mn; j++) {
+        int64_t *x = r->data + r->n * (j * r->cols + rc);
+        const int64_t *y = a->data + a->n * (j * a->cols + ac);
+        for (size_t i = 0; i < r->n; i++) {
+            uint64_t u = (uint64_t)x[i], v = (uint64_t)y[i];
+            x[i] = (int64_t)(op == 0 ? v : op == 1 ? u + v : op == 2 ? u - v : 0 - v); /* copy, add_assign, sub_assign, negate */
+        }
+    }
+    if (op == 0 || op == 3)
+        for (size_t j = mn; j < r->size; j++) memset(r->data + r->n * (j * r->cols + rc), 0, 8 * r->n);
+}
+
+/* operations/glwe.rs:699-818 (glwe_tensor_apply).  res = GLWETensor VecZnx with (rank+1)(rank+2)/2 columns. */
+void orc_glwe_tensor_apply(int flavour, const void *mod, size_t cnv_offset, orc_vec_znx *res, size_t res_base2k,
+                           const orc_vec_znx *a, size_t a_effective_k, const orc_vec_znx *bb, size_t b_effective_k, size_t ab_base2k) {
+    be_t b = make_be(flavour, mod);
+    size_t n = res->n, cols = a->cols;
+    assert(bb->cols == cols && res->cols == cols * (cols + 1) / 2);
+    assert(div_ceil(a_effective_k, ab_base2k) == a->size && div_ceil(b_effective_k, ab_base2k) == bb->size);
+    orc_vec_znx_dft a_prep = dft_alloc(&b, n, cols, a->size), b_prep = dft_alloc(&b, n, cols, bb->size);
+    be_cnv_prepare(&b, &a_prep, a, msb_mask_bottom_limb(ab_base2k, a_effective_k));
+    be_cnv_prepare(&b, &b_prep, bb, msb_mask_bottom_limb(ab_base2k, b_effective_k));
+    size_t off_hi;
+    int64_t off_lo;
+    if (cnv_offset < ab_base2k) {
+        off_hi = 0;
+        off_lo = -(int64_t)(ab_base2k - (cnv_offset % ab_base2k));
+    } else {
+        off_hi = cnv_offset / ab_base2k - 1; /* saturating_sub(1): cnv_offset >= ab_base2k here */
+        off_lo = (int64_t)(cnv_offset % ab_base2k);
+    }
+    size_t dft_size = normalize_input_limb_bound_with_offset(a->size + bb->size - off_hi, res->size, res_base2k, ab_base2k, off_lo);
+    orc_vec_znx tmp = {(int64_t *)calloc(n * res->size, 8), n, 1, res->size};
+    for (size_t i = 0; i < cols; i++) {
+        size_t col_i = i * cols - (i * (i + 1) / 2);
+        orc_vec_znx_dft res_dft = dft_alloc(&b, n, 1, dft_size);
+        be_cnv_pairwise(&b, off_hi, &res_dft, &a_prep, &b_prep, i, i); /* cnv_apply_dft(a_prep col i, b_prep col i) */
+        be_idft_consume(&b, &res_dft);
+        orc_vec_znx_big res_big = {res_dft.data, n, 1, res_dft.size};
+        be_big_normalize(&b, &tmp, res_base2k, off_lo, 0, &res_big, ab_base2k, 0);
+        znx_limbwise(res, col_i + i, &tmp, 0, 0);
+        for (size_t j = 0; j < cols; j++) {
+            if (j == i) continue;
+            if (j < i) {
+                size_t col_j = j * cols - (j * (j + 1) / 2);
+                znx_limbwise(res, col_j + i, &tmp, 0, 2);
+            } else {
+                znx_limbwise(res, col_i + j, &tmp, 0, 3);
+            }
+        }
+        free(res_dft.data);
+    }
+    for (size_t i = 0; i < cols; i++) {
+        size_t col_i = i * cols - (i * (i + 1) / 2);
+        for (size_t j = i + 1; j < cols; j++) {
+            orc_vec_znx_dft res_dft = dft_alloc(&b, n, 1, dft_size);
+            be_cnv_pairwise(&b, off_hi, &res_dft, &a_prep, &b_prep, i, j);
+            be_idft_consume(&b, &res_dft);
+            orc_vec_znx_big res_big = {res_dft.data, n, 1, res_dft.size};
+            be_big_normalize(&b, &tmp, res_base2k, off_lo, 0, &res_big, ab_base2k, 0);
+            znx_limbwise(res, col_i + j, &tmp, 0, 1);
+            free(res_dft.data);
+        }
+    }
+    free(tmp.data);
+    free(a_prep.data);
+    free(b_prep.data);
+}
+
+/* operations/glwe.rs:545-610 (glwe_tensor_relinearize): a = GLWETensor (base2k a_base2k), tsk = prepared GGLWE with
+ * rank_in = rank(rank+1)/2 rows-columns and rank_out + 1 output columns; `tsk_size` = tsk.size() */
+void orc_glwe_tensor_relinearize(int flavour, const void *mod, orc_vec_znx *res, size_t res_base2k, const orc_vec_znx *a,
+                                 size_t a_base2k, const orc_vmp_pmat *tsk, size_t key_base2k, size_t dsize) {
+    be_t b = make_be(flavour, mod);
+    size_t n = res->n, cols = tsk->cols_out, pairs = tsk->cols_in;
+    assert(res->cols == cols && a->cols == cols + pairs);
+    size_t a_dft_size = div_ceil(a->size * a_base2k, key_base2k);
+    orc_vec_znx_dft a_dft = dft_alloc(&b, n, pairs, a_dft_size);
+    orc_vec_znx a_conv = {(int64_t *)calloc(n * a_dft_size, 8), n, 1, a_dft_size};
+    for (size_t i = 0; i < pairs; i++) {
+        if (a_base2k != key_base2k) {
+            orc_vec_znx_normalize(&a_conv, key_base2k, 0, 0, a, a_base2k, cols + i, 0);
+            be_dft_apply(&b, 1, 0, &a_dft, i, &a_conv, 0);
+        } else {
+            be_dft_apply(&b, 1, 0, &a_dft, i, a, cols + i);
+        }
+    }
+    orc_vec_znx_dft res_dft = dft_alloc(&b, n, cols, tsk->size);
+    gglwe_product_dft(&b, &res_dft, &a_dft, tsk, dsize);
+    be_idft_consume(&b, &res_dft);
+    orc_vec_znx_big res_big = {res_dft.data, n, res_dft.cols, res_dft.size};
+    for (size_t i = 0; i < cols; i++) {
+        if (res_base2k == key_base2k) { /* sic: the reference tests res_base2k, not a_base2k (:595) */
+            be_big_add_small_assign(&b, &res_big, i, a, i);
+        } else {
+            orc_vec_znx_normalize(&a_conv, key_base2k, 0, 0, a, a_base2k, i, 0);
+            be_big_add_small_assign(&b, &res_big, i, &a_conv, 0);
+        }
+    }
+    for (size_t i = 0; i < res->cols; i++) be_big_normalize(&b, res, res_base2k, 0, i, &res_big, key_base2k, i);
+    free(a_conv.data);
+    free(a_dft.data);
+    free(res_dft.data);
+}

@@ -847,3 +847,83 @@ void orc_fft64_vec_znx_big_normalize(orc_vec_znx *res, size_t res_base2k, int64_
     orc_vec_znx av = {(int64_t *)a->data, a->n, a->cols, a->size};
     orc_vec_znx_normalize(res, res_base2k, res_offset, res_col, &av, a_base2k, a_col, op);
 }
+
+/* ---- reference/fft64/convolution.rs (bivariate convolution, FFT64) -----------------------------------------------------
+ * CnvPVecL / CnvPVecR are opaque prepared layouts (the reference interleaves reim4 blocks, convolution.rs:61-70); this
+ * restatement keeps them in the VecZnxDft layout.  Per frequency the arithmetic and its order are the reference's:
+ * reim4_convolution_1coeff_ref (reim4/arithmetic_ref.rs:235-247) = sum over j ascending of reim4_add_mul. */
+static void reim_from_znx_masked(size_t n, double *r, const int64_t *a, int64_t mask) {
+    for (size_t i = 0; i < n; i++) r[i] = (double)(a[i] & mask);
+}
+/* convolution.rs:33-73 */
+void orc_fft64_cnv_prepare(const orc_fft64_module *m, orc_vec_znx_dft *res, const orc_vec_znx *a, int64_t mask) {
+    size_t n = res->n, min_size = zmin(res->size, a->size);
+    for (size_t col = 0; col < res->cols; col++) {
+        for (size_t j = 0; j < min_size; j++) {
+            double *r = dlimb(res, col, j);
+            if (j + 1 == min_size) reim_from_znx_masked(n, r, zlimb(a, col, j), mask);
+            else reim_from_znx(n, r, zlimb(a, col, j));
+            orc_fft64_fft(m, r);
+        }
+        for (size_t j = min_size; j < res->size; j++) memset(dlimb(res, col, j), 0, 8 * n);
+    }
+}
+/* convolution.rs:199-249 (apply_dft), :256-334 (pairwise: operands summed first with reim_add) */
+static void fcnv_apply_core(size_t cnv_offset, orc_vec_znx_dft *res, size_t res_col, const orc_vec_znx_dft *a, size_t a_i, size_t a_j,
+                            const orc_vec_znx_dft *b, size_t b_i, size_t b_j) {
+    size_t n = res->n, mh = n / 2, res_size = res->size, a_size = a->size, b_size = b->size;
+    if (a_size == 0 || b_size == 0) {
+        for (size_t j = 0; j < res_size; j++) memset(dlimb(res, res_col, j), 0, 8 * n);
+        return;
+    }
+    size_t bound = a_size + b_size - 1, min_size = zmin(res_size, bound), offset = zmin(cnv_offset, bound);
+    double *as = (double *)malloc(8 * n * a_size), *bs = (double *)malloc(8 * n * b_size);
+    for (size_t j = 0; j < a_size; j++)
+        for (size_t i = 0; i < n; i++) as[j * n + i] = a_i == a_j ? dlimb(a, a_i, j)[i] : dlimb(a, a_i, j)[i] + dlimb(a, a_j, j)[i];
+    for (size_t j = 0; j < b_size; j++)
+        for (size_t i = 0; i < n; i++) bs[j * n + i] = b_i == b_j ? dlimb(b, b_i, j)[i] : dlimb(b, b_i, j)[i] + dlimb(b, b_j, j)[i];
+    for (size_t k = 0; k < min_size; k++) {
+        size_t k_abs = k + offset;
+        double *r = dlimb(res, res_col, k);
+        memset(r, 0, 8 * n);
+        if (k_abs >= a_size + b_size) continue;
+        size_t j_min = k_abs > a_size - 1 ? k_abs - (a_size - 1) : 0, j_max = zmin(k_abs + 1, b_size);
+        for (size_t j = j_min; j < j_max; j++) {
+            const double *x = as + (k_abs - j) * n, *y = bs + j * n;
+            for (size_t f = 0; f < mh; f++) { /* reim4_add_mul, reim4/arithmetic_ref.rs:223-232 */
+                double ar = x[f], ai = x[f + mh], br = y[f], bi = y[f + mh];
+                r[f] += ar * br - ai * bi;
+                r[f + mh] += ar * bi + ai * br;
+            }
+        }
+    }
+    free(as);
+    free(bs);
+    for (size_t j = min_size; j < res_size; j++) memset(dlimb(res, res_col, j), 0, 8 * n);
+}
+void orc_fft64_cnv_apply_dft(size_t cnv_offset, orc_vec_znx_dft *res, size_t res_col, const orc_vec_znx_dft *a, size_t a_col,
+                             const orc_vec_znx_dft *b, size_t b_col) {
+    fcnv_apply_core(cnv_offset, res, res_col, a, a_col, a_col, b, b_col, b_col);
+}
+void orc_fft64_cnv_pairwise_apply_dft(size_t cnv_offset, orc_vec_znx_dft *res, size_t res_col, const orc_vec_znx_dft *a,
+                                      const orc_vec_znx_dft *b, size_t col_i, size_t col_j) {
+    fcnv_apply_core(cnv_offset, res, res_col, a, col_i, col_j, b, col_i, col_j);
+}
+/* convolution.rs:144-191 with i64_convolution_by_const_1coeff_ref (:401-426): wrapping i64 */
+void orc_fft64_cnv_by_const_apply(size_t cnv_offset, orc_vec_znx_big *res, size_t res_col, const orc_vec_znx *a, size_t a_col,
+                                  const int64_t *b, size_t b_size) {
+    size_t n = res->n, res_size = res->size, a_size = a->size;
+    size_t bound = a_size + b_size - 1, min_size = zmin(res_size, bound), offset = zmin(cnv_offset, bound);
+    for (size_t k = 0; k < min_size; k++) {
+        size_t k_abs = k + offset;
+        int64_t *r = blimb(res, res_col, k);
+        memset(r, 0, 8 * n);
+        if (k_abs >= a_size + b_size) continue;
+        size_t j_min = k_abs > a_size - 1 ? k_abs - (a_size - 1) : 0, j_max = zmin(k_abs + 1, b_size);
+        for (size_t j = j_min; j < j_max; j++) {
+            const int64_t *x = zlimb(a, a_col, k_abs - j);
+            for (size_t i = 0; i < n; i++) r[i] = (int64_t)((uint64_t)r[i] + (uint64_t)x[i] * (uint64_t)b[j]);
+        }
+    }
+    for (size_t j = min_size; j < res_size; j++) memset(blimb(res, res_col, j), 0, 8 * n);
+}

@@ -926,3 +926,123 @@ void orc_ntt120_vec_znx_big_normalize(orc_vec_znx *res, size_t res_base2k, int64
         normalize_cross_i128(res, res_base2k, res_offset, res_col, a, a_base2k, a_col, scratch, op);
     free(scratch);
 }
+
+/* ---- convolution.rs (bivariate convolution, NTT120) ------------------------------------------------------------------
+ * CnvPVecL / CnvPVecR are opaque prepared layouts; this restatement stores both as q120b limbs in the VecZnxDft layout
+ * (limb-major, column-minor) and forms the q120c view of the right operand on the fly (c_from_b), which is what
+ * prepare_right stores (convolution.rs:120-157).  Products go through the same bbc kernel (mat1col_x2_bbc). */
+
+/* arithmetic.rs:64-86 (b_from_znx64_masked_ref): the i64 is ANDed with the mask, then mapped like b_from_znx64 */
+static void b_from_znx64_masked(size_t nn, uint64_t *res, const int64_t *x, int64_t mask) {
+    int64_t *t = (int64_t *)malloc(8 * nn);
+    for (size_t i = 0; i < nn; i++) t[i] = x[i] & mask;
+    orc_ntt120_b_from_znx64(nn, res, t);
+    free(t);
+}
+
+/* convolution.rs:66-100 (prepare_left), :120-157 (prepare_right), :177-236 (prepare_self): all columns of res, limbs
+ * [0, min(res.size, a.size)), the last active limb masked, the remaining limbs zero */
+void orc_ntt120_cnv_prepare(const orc_ntt120_module *m, orc_vec_znx_dft *res, const orc_vec_znx *a, int64_t mask) {
+    size_t n = res->n, min_size = zmin(res->size, a->size);
+    for (size_t col = 0; col < res->cols; col++) {
+        for (size_t j = 0; j < min_size; j++) {
+            uint64_t *r = dft_limb(res, col, j);
+            if (j + 1 == min_size) b_from_znx64_masked(n, r, znx_limb(a, col, j), mask);
+            else orc_ntt120_b_from_znx64(n, r, znx_limb(a, col, j));
+            orc_ntt120_ntt(m, r);
+        }
+        for (size_t j = min_size; j < res->size; j++) memset(dft_limb(res, col, j), 0, 32 * n);
+    }
+}
+
+/* pack one x2 block (two NTT coefficients) of every limb: left = canonical residues with a zero high half
+ * (poulpy-cpu-ref/src/ntt120/prim.rs:223-240, pairwise :259-280), right = q120c in REVERSED limb order (:245-254, :285-299) */
+static void cnv_pack_left(uint32_t *dst, const orc_vec_znx_dft *a, size_t col_i, size_t col_j, size_t blk) {
+    for (size_t row = 0; row < a->size; row++) {
+        const uint64_t *x = dft_limb(a, col_i, row) + 8 * blk, *y = col_j == col_i ? NULL : dft_limb(a, col_j, row) + 8 * blk;
+        for (int c = 0; c < 2; c++)
+            for (int k = 0; k < 4; k++) {
+                uint64_t q = ORC_Q[k], s = x[4 * c + k] % q;
+                if (y) {
+                    s += y[4 * c + k] % q;
+                    if (s >= q) s -= q;
+                }
+                dst[16 * row + 8 * c + 2 * k] = (uint32_t)s;
+                dst[16 * row + 8 * c + 2 * k + 1] = 0;
+            }
+    }
+}
+static void cnv_pack_right(uint32_t *dst, const orc_vec_znx_dft *b, size_t col_i, size_t col_j, size_t blk) {
+    for (size_t row = 0; row < b->size; row++) {
+        size_t src = b->size - 1 - row;
+        uint32_t ci[16], cj[16];
+        orc_ntt120_c_from_b(2, ci, dft_limb(b, col_i, src) + 8 * blk);
+        if (col_j != col_i) {
+            orc_ntt120_c_from_b(2, cj, dft_limb(b, col_j, src) + 8 * blk);
+            for (int t = 0; t < 16; t++) ci[t] += cj[t];
+        }
+        memcpy(dst + 16 * row, ci, 64);
+    }
+}
+/* convolution.rs:256-335 (apply_dft) and :441-557 (pairwise; col_i == col_j falls back to apply_dft with both columns equal):
+ * res[res_col, k] = sum_j a[k_abs - j] (.) b[j], k_abs = k + min(cnv_offset, bound) */
+static void cnv_apply_core(const orc_ntt120_module *m, size_t cnv_offset, orc_vec_znx_dft *res, size_t res_col,
+                           const orc_vec_znx_dft *a, size_t a_i, size_t a_j, const orc_vec_znx_dft *b, size_t b_i, size_t b_j) {
+    size_t n = res->n, res_size = res->size, a_size = a->size, b_size = b->size;
+    if (res_size == 0 || a_size == 0 || b_size == 0) {
+        for (size_t j = 0; j < res_size; j++) memset(dft_limb(res, res_col, j), 0, 32 * n);
+        return;
+    }
+    size_t bound = a_size + b_size - 1, offset = zmin(cnv_offset, bound);
+    size_t min_size = zmin(res_size, bound + 1 > offset ? bound + 1 - offset : 0);
+    uint32_t *a_tmp = (uint32_t *)malloc(64 * a_size), *b_tmp = (uint32_t *)malloc(64 * b_size);
+    for (size_t blk = 0; blk < n / 2; blk++) {
+        cnv_pack_left(a_tmp, a, a_i, a_j, blk);
+        cnv_pack_right(b_tmp, b, b_i, b_j, blk);
+        for (size_t k = 0; k < min_size; k++) {
+            size_t k_abs = k + offset;
+            size_t j_min = k_abs > a_size - 1 ? k_abs - (a_size - 1) : 0;
+            size_t j_max = zmin(k_abs + 1, b_size);
+            uint64_t *r = dft_limb(res, res_col, k) + 8 * blk;
+            if (j_max <= j_min) { /* ell == 0: the bbc kernel writes the reduction of an empty sum */
+                memset(r, 0, 64);
+                continue;
+            }
+            size_t ell = j_max - j_min, a_start = k_abs + 1 - j_max, b_start = b_size - j_max;
+            mat1col_x2_bbc(&m->bbc, ell, r, a_tmp + 16 * a_start, b_tmp + 16 * b_start);
+        }
+    }
+    free(a_tmp);
+    free(b_tmp);
+    for (size_t j = min_size; j < res_size; j++) memset(dft_limb(res, res_col, j), 0, 32 * n);
+}
+void orc_ntt120_cnv_apply_dft(const orc_ntt120_module *m, size_t cnv_offset, orc_vec_znx_dft *res, size_t res_col,
+                              const orc_vec_znx_dft *a, size_t a_col, const orc_vec_znx_dft *b, size_t b_col) {
+    cnv_apply_core(m, cnv_offset, res, res_col, a, a_col, a_col, b, b_col, b_col);
+}
+void orc_ntt120_cnv_pairwise_apply_dft(const orc_ntt120_module *m, size_t cnv_offset, orc_vec_znx_dft *res, size_t res_col,
+                                       const orc_vec_znx_dft *a, const orc_vec_znx_dft *b, size_t col_i, size_t col_j) {
+    cnv_apply_core(m, cnv_offset, res, res_col, a, col_i, col_j, b, col_i, col_j);
+}
+/* convolution.rs:361-410: coefficient-domain product with a constant limb vector, i128 accumulators */
+void orc_ntt120_cnv_by_const_apply(size_t cnv_offset, orc_vec_znx_big *res, size_t res_col, const orc_vec_znx *a, size_t a_col,
+                                   const int64_t *b, size_t b_size) {
+    size_t n = res->n, res_size = res->size, a_size = a->size;
+    if (res_size == 0 || a_size == 0 || b_size == 0) {
+        for (size_t j = 0; j < res_size; j++) memset(big_limb(res, res_col, j), 0, 16 * n);
+        return;
+    }
+    size_t bound = a_size + b_size - 1, offset = zmin(cnv_offset, bound);
+    size_t min_size = zmin(res_size, bound + 1 > offset ? bound + 1 - offset : 0);
+    for (size_t k = 0; k < min_size; k++) {
+        size_t k_abs = k + offset;
+        size_t j_min = k_abs > a_size - 1 ? k_abs - (a_size - 1) : 0, j_max = zmin(k_abs + 1, b_size);
+        i128 *r = big_limb(res, res_col, k);
+        for (size_t i = 0; i < n; i++) {
+            i128 acc = 0;
+            for (size_t j = j_min; j < j_max; j++) acc = wadd(acc, (i128)znx_limb(a, a_col, k_abs - j)[i] * (i128)b[j]);
+            r[i] = acc;
+        }
+    }
+    for (size_t j = min_size; j < res_size; j++) memset(big_limb(res, res_col, j), 0, 16 * n);
+}

@@ -173,6 +173,32 @@ void orc_glwe_external_product(int flavour, const void *mod, orc_vec_znx *res, s
                                const orc_vec_znx *a, size_t a_base2k, const orc_vmp_pmat *ggsw, size_t ggsw_base2k,
                                size_t dsize);
 
+/* ------------------------------------------------------------ bivariate convolution (HalImpl::cnv_*, hal_impl.rs:670-754) */
+/* CnvPVecL / CnvPVecR are opaque prepared layouts: this restatement keeps both in the VecZnxDft layout.
+ * reference/ntt120/convolution.rs:66-236 (prepare_left / right / self), :256-335 (apply_dft), :441-557 (pairwise), :361-410 (by_const);
+ * reference/fft64/convolution.rs:13-137, :199-249, :256-334, :144-191 */
+void orc_ntt120_cnv_prepare(const orc_ntt120_module *m, orc_vec_znx_dft *res, const orc_vec_znx *a, int64_t mask);
+void orc_ntt120_cnv_apply_dft(const orc_ntt120_module *m, size_t cnv_offset, orc_vec_znx_dft *res, size_t res_col,
+                              const orc_vec_znx_dft *a, size_t a_col, const orc_vec_znx_dft *b, size_t b_col);
+void orc_ntt120_cnv_pairwise_apply_dft(const orc_ntt120_module *m, size_t cnv_offset, orc_vec_znx_dft *res, size_t res_col,
+                                       const orc_vec_znx_dft *a, const orc_vec_znx_dft *b, size_t col_i, size_t col_j);
+void orc_ntt120_cnv_by_const_apply(size_t cnv_offset, orc_vec_znx_big *res, size_t res_col, const orc_vec_znx *a, size_t a_col,
+                                   const int64_t *b, size_t b_size);
+void orc_fft64_cnv_prepare(const orc_fft64_module *m, orc_vec_znx_dft *res, const orc_vec_znx *a, int64_t mask);
+void orc_fft64_cnv_apply_dft(size_t cnv_offset, orc_vec_znx_dft *res, size_t res_col, const orc_vec_znx_dft *a, size_t a_col,
+                             const orc_vec_znx_dft *b, size_t b_col);
+void orc_fft64_cnv_pairwise_apply_dft(size_t cnv_offset, orc_vec_znx_dft *res, size_t res_col, const orc_vec_znx_dft *a,
+                                      const orc_vec_znx_dft *b, size_t col_i, size_t col_j);
+void orc_fft64_cnv_by_const_apply(size_t cnv_offset, orc_vec_znx_big *res, size_t res_col, const orc_vec_znx *a, size_t a_col,
+                                  const int64_t *b, size_t b_size);
+/* poulpy-core/src/operations/glwe.rs:699-818 (glwe_tensor_apply) and :545-610 (glwe_tensor_relinearize): the two halves of
+ * poulpy-ckks ckks_mul_into (poulpy-ckks/src/leveled/default/mul.rs:49-86).  res of tensor_apply / a of relinearize is the
+ * GLWETensor VecZnx with (rank+1)(rank+2)/2 columns. */
+void orc_glwe_tensor_apply(int flavour, const void *mod, size_t cnv_offset, orc_vec_znx *res, size_t res_base2k,
+                           const orc_vec_znx *a, size_t a_effective_k, const orc_vec_znx *b, size_t b_effective_k, size_t ab_base2k);
+void orc_glwe_tensor_relinearize(int flavour, const void *mod, orc_vec_znx *res, size_t res_base2k, const orc_vec_znx *a,
+                                 size_t a_base2k, const orc_vmp_pmat *tsk, size_t key_base2k, size_t dsize);
+
 /* ------------------------------------------------------- CGGI blind rotation */
 /* poulpy-bin-fhe/src/blind_rotation/algorithms/mod.rs:136-176 ; rot_left != 0 negates (LookUpTableRotationDirection::Left).
  * lwe = VecZnx(n = n_lwe + 1, cols = 1, size); res has n_lwe + 1 entries (b, a_0, ...). */

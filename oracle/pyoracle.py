@@ -291,6 +291,41 @@ class OracleModule:
                                               _p(a), _sz(a_size), _sz(a_base2k), _sz(n), _sz(a_cols - 1), C.byref(ks),
                                               _sz(ggsw_base2k), _sz(dsize), _sz(B), C.c_int(threads))
 
+    # --- bivariate convolution (poulpy-hal/src/api/convolution.rs; CnvPVecL/R kept in the VecZnxDft layout) ---------------------
+    def cnv_prepare(self, res, a, mask=-1):
+        """cnv_prepare_left / cnv_prepare_right / cnv_prepare_self: res = VecZnxDft-shaped array (size, cols, n[, 4])."""
+        r, av = _vz(res), _vz(a)
+        self._f("cnv_prepare")(self._h, C.byref(r), C.byref(av), C.c_int64(mask))
+
+    def cnv_apply_dft(self, cnv_offset, res, res_col, a, a_col, b, b_col):
+        r, av, bv = _vz(res), _vz(a), _vz(b)
+        if self.flavour == NTT120:
+            lib().orc_ntt120_cnv_apply_dft(self._h, _sz(cnv_offset), C.byref(r), _sz(res_col), C.byref(av), _sz(a_col), C.byref(bv), _sz(b_col))
+        else:
+            lib().orc_fft64_cnv_apply_dft(_sz(cnv_offset), C.byref(r), _sz(res_col), C.byref(av), _sz(a_col), C.byref(bv), _sz(b_col))
+
+    def cnv_pairwise_apply_dft(self, cnv_offset, res, res_col, a, b, col_i, col_j):
+        r, av, bv = _vz(res), _vz(a), _vz(b)
+        if self.flavour == NTT120:
+            lib().orc_ntt120_cnv_pairwise_apply_dft(self._h, _sz(cnv_offset), C.byref(r), _sz(res_col), C.byref(av), C.byref(bv), _sz(col_i), _sz(col_j))
+        else:
+            lib().orc_fft64_cnv_pairwise_apply_dft(_sz(cnv_offset), C.byref(r), _sz(res_col), C.byref(av), C.byref(bv), _sz(col_i), _sz(col_j))
+
+    def cnv_by_const_apply(self, cnv_offset, res, res_col, a, a_col, b):
+        r, av = _vz(res), _vz(a)
+        b = np.ascontiguousarray(b, dtype=np.int64)
+        self._f("cnv_by_const_apply")(_sz(cnv_offset), C.byref(r), _sz(res_col), C.byref(av), _sz(a_col), _p(b), _sz(len(b)))
+
+    def glwe_tensor_apply(self, cnv_offset, res, res_base2k, a, a_effective_k, b, b_effective_k, ab_base2k):
+        r, av, bv = _vz(res), _vz(a), _vz(b)
+        lib().orc_glwe_tensor_apply(C.c_int(self.flavour), self._h, _sz(cnv_offset), C.byref(r), _sz(res_base2k), C.byref(av),
+                                    _sz(a_effective_k), C.byref(bv), _sz(b_effective_k), _sz(ab_base2k))
+
+    def glwe_tensor_relinearize(self, res, res_base2k, a, a_base2k, tsk: VmpPMat, key_base2k, dsize=1):
+        r, av, ks = _vz(res), _vz(a), tsk.struct()
+        lib().orc_glwe_tensor_relinearize(C.c_int(self.flavour), self._h, C.byref(r), _sz(res_base2k), C.byref(av), _sz(a_base2k),
+                                          C.byref(ks), _sz(key_base2k), _sz(dsize))
+
     def cggi_x_pow_a(self):
         res = self.svp_ppol_alloc(2 * self.n)
         r = _pp(res)
