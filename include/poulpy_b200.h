@@ -252,6 +252,37 @@ int pgb_glwe_external_product_host(pgb_module *m, int64_t *res_host, uint64_t re
                                    const int64_t *a_host, uint64_t a_size, uint64_t a_base2k, uint64_t rank,
                                    const pgb_vmp_pmat *ggsw, uint64_t ggsw_base2k, uint64_t dsize, uint64_t count);
 
+/* ---- bivariate convolution (oep/hal_impl.rs:670-754) ---------------------------------------------------
+ * CnvPVecL / CnvPVecR (poulpy-hal/src/layouts/cnv_pvec.rs) are backend-owned prepared layouts; here both are DFT limbs in the
+ * VecZnxDft layout, described by the same POD struct.  All *_tmp_bytes are 0. */
+typedef pgb_vec_znx pgb_cnv_pvec;
+size_t pgb_bytes_of_cnv_pvec_left(const pgb_module *m, uint64_t cols, uint64_t size);
+size_t pgb_bytes_of_cnv_pvec_right(const pgb_module *m, uint64_t cols, uint64_t size);
+size_t pgb_cnv_prepare_left_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t a_size);
+size_t pgb_cnv_prepare_right_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t a_size);
+size_t pgb_cnv_prepare_self_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t a_size);
+size_t pgb_cnv_apply_dft_tmp_bytes(const pgb_module *m, uint64_t cnv_offset, uint64_t res_size, uint64_t a_size, uint64_t b_size);
+size_t pgb_cnv_pairwise_apply_dft_tmp_bytes(const pgb_module *m, uint64_t cnv_offset, uint64_t res_size, uint64_t a_size, uint64_t b_size);
+size_t pgb_cnv_by_const_apply_tmp_bytes(const pgb_module *m, uint64_t cnv_offset, uint64_t res_size, uint64_t a_size, uint64_t b_size);
+/* HalImpl::cnv_prepare_left :672 / cnv_prepare_right :679 / cnv_prepare_self :750 (reference/ntt120/convolution.rs:66-236):
+ * forward transform of every column of `a`, the last active limb ANDed with `mask` first */
+int pgb_cnv_prepare_left(pgb_module *m, pgb_cnv_pvec *res, const pgb_vec_znx *a, int64_t mask);
+int pgb_cnv_prepare_right(pgb_module *m, pgb_cnv_pvec *res, const pgb_vec_znx *a, int64_t mask);
+int pgb_cnv_prepare_self(pgb_module *m, pgb_cnv_pvec *left, pgb_cnv_pvec *right, const pgb_vec_znx *a, int64_t mask);
+/* HalImpl::cnv_apply_dft :709 (convolution.rs:256-335): res[res_col, k] = sum_j a[a_col, k + off - j] (.) b[b_col, j] */
+int pgb_cnv_apply_dft(pgb_module *m, uint64_t cnv_offset, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_cnv_pvec *a, uint64_t a_col,
+                      const pgb_cnv_pvec *b, uint64_t b_col);
+int pgb_cnv_apply_dft_batched(pgb_module *m, uint64_t cnv_offset, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_cnv_pvec *a,
+                              uint64_t a_col, const pgb_cnv_pvec *b, uint64_t b_col, const pgb_batch *bt);
+/* HalImpl::cnv_pairwise_apply_dft :733 (convolution.rs:441-557): (a[:, i] + a[:, j]) x (b[:, i] + b[:, j]) */
+int pgb_cnv_pairwise_apply_dft(pgb_module *m, uint64_t cnv_offset, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_cnv_pvec *a,
+                               const pgb_cnv_pvec *b, uint64_t col_i, uint64_t col_j);
+int pgb_cnv_pairwise_apply_dft_batched(pgb_module *m, uint64_t cnv_offset, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_cnv_pvec *a,
+                                       const pgb_cnv_pvec *b, uint64_t col_i, uint64_t col_j, const pgb_batch *bt);
+/* HalImpl::cnv_by_const_apply :695 (convolution.rs:361-410): coefficient-domain product with b_size HOST constants into the big type */
+int pgb_cnv_by_const_apply(pgb_module *m, uint64_t cnv_offset, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col,
+                           const int64_t *b, uint64_t b_size);
+
 /* ---- coefficient-domain helpers of execute_standard ---- */
 /* vec_znx_add_assign / sub_assign (poulpy-cpu-ref/src/reference/vec_znx/add.rs:60-82, sub.rs:60-82) */
 int pgb_vec_znx_add_assign(pgb_module *m, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col);
@@ -262,6 +293,21 @@ int pgb_vec_znx_sub_assign(pgb_module *m, pgb_vec_znx *res, uint64_t res_col, co
 int pgb_vec_znx_mul_xp_minus_one(pgb_module *m, int64_t p, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col);
 /* vec_znx_normalize_assign (reference/vec_znx/normalize.rs:403-425) */
 int pgb_vec_znx_normalize_assign(pgb_module *m, uint64_t base2k, pgb_vec_znx *res, uint64_t res_col);
+
+/* ---- GLWE tensoring / relinearisation = CKKS multiplication (poulpy-core/src/operations/glwe.rs:699-818, :545-610;
+ * poulpy-ckks/src/leveled/default/mul.rs:49-86), batched and device resident ---- */
+size_t pgb_glwe_tensor_apply_tmp_bytes(const pgb_module *m, uint64_t rank, uint64_t res_size, uint64_t res_base2k, uint64_t a_size,
+                                       uint64_t b_size, uint64_t ab_base2k, uint64_t cnv_offset, uint64_t batch);
+/* res: GLWETensor VecZnx with (rank+1)(rank+2)/2 columns; a, b: GLWE VecZnx of base2k `ab_base2k`, a.size == ceil(a_effective_k / ab_base2k) */
+int pgb_glwe_tensor_apply_batched(pgb_module *m, uint64_t cnv_offset, pgb_vec_znx *res, uint64_t res_base2k, const pgb_vec_znx *a,
+                                  uint64_t a_effective_k, const pgb_vec_znx *b, uint64_t b_effective_k, uint64_t ab_base2k,
+                                  const pgb_batch *bt, void *scratch, size_t scratch_len);
+size_t pgb_glwe_tensor_relinearize_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t a_size, uint64_t a_base2k,
+                                             const pgb_vmp_pmat *tsk, uint64_t key_base2k, uint64_t dsize, uint64_t batch);
+/* a: GLWETensor VecZnx; tsk: prepared tensor key = VmpPMat(dnum, rank(rank+1)/2, rank+1, size) */
+int pgb_glwe_tensor_relinearize_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, const pgb_vec_znx *a, uint64_t a_base2k,
+                                        const pgb_vmp_pmat *tsk, uint64_t key_base2k, uint64_t dsize, const pgb_batch *bt, void *scratch,
+                                        size_t scratch_len);
 
 /* ---- CGGI blind rotation (poulpy-bin-fhe/src/blind_rotation/algorithms/cggi/algorithm.rs:275-368; C3) ---- */
 /* x_pow_a table of the prepared key (cggi/key_prepared.rs:66-75): SvpPPol with 2n columns, col i = X^i. */

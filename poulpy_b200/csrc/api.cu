@@ -762,3 +762,113 @@ extern "C" int pgb_vec_znx_normalize_assign(pgb_module *m, uint64_t base2k, pgb_
     PGB_TRY(big_normalize_impl(m, res, base2k, 0, res_col, res, base2k, res_col, 0, false, &ONE));
     return sync_if(m, true);
 }
+
+// ---- bivariate convolution (HalImpl::cnv_*, hal_impl.rs:670-754; kernels in cnv.cu) --------------------------------------------
+extern "C" size_t pgb_bytes_of_cnv_pvec_left(const pgb_module *m, uint64_t cols, uint64_t size) { return m->n * cols * size * prep_bytes(m); }
+extern "C" size_t pgb_bytes_of_cnv_pvec_right(const pgb_module *m, uint64_t cols, uint64_t size) { return m->n * cols * size * prep_bytes(m); }
+extern "C" size_t pgb_cnv_prepare_left_tmp_bytes(const pgb_module *, uint64_t, uint64_t) { return 0; }
+extern "C" size_t pgb_cnv_prepare_right_tmp_bytes(const pgb_module *, uint64_t, uint64_t) { return 0; }
+extern "C" size_t pgb_cnv_prepare_self_tmp_bytes(const pgb_module *, uint64_t, uint64_t) { return 0; }
+extern "C" size_t pgb_cnv_apply_dft_tmp_bytes(const pgb_module *, uint64_t, uint64_t, uint64_t, uint64_t) { return 0; }
+extern "C" size_t pgb_cnv_pairwise_apply_dft_tmp_bytes(const pgb_module *, uint64_t, uint64_t, uint64_t, uint64_t) { return 0; }
+extern "C" size_t pgb_cnv_by_const_apply_tmp_bytes(const pgb_module *, uint64_t, uint64_t, uint64_t, uint64_t) { return 0; }
+
+// cnv_prepare_left / right (ntt120/convolution.rs:66-157, fft64/convolution.rs:13-73): every column of res; limbs [0, min(res.size,
+// a.size)) transformed, the last active one ANDed with `mask` first, the remaining limbs zero
+int cnv_prepare_impl(pgb_module *m, pgb_vec_znx_dft *res, const pgb_vec_znx *a, int64_t mask, const pgb_batch *bt) {
+    CHECK_BATCH(bt);
+    CHECK_N(res, "cnv_prepare(res)");
+    CHECK_N(a, "cnv_prepare(a)");
+    PGB_REQUIRE(a->cols >= res->cols, "cnv_prepare: a has %llu columns, res %llu", (unsigned long long)a->cols, (unsigned long long)res->cols);
+    const uint64_t n = m->n, pb = prep_bytes(m), min_size = umin64(res->size, a->size);
+    for (uint64_t col = 0; col < res->cols; col++) {
+        LimbSet in = {(char *)a->data + limb_off(n, a->cols, col, 0, 8), a->cols * n * 8, bt->stride_a};
+        LimbSet out = dft_col(m, res, col, 0, bt->stride_res);
+        if (min_size > 1) {
+            if (m->flavour == PGB_NTT120) PGB_TRY(ntt120_forward(m, in, out, (int)(min_size - 1), (int)bt->count));
+            else PGB_TRY(fft64_forward(m, in, out, (int)(min_size - 1), (int)bt->count));
+        }
+        if (min_size > 0) {
+            LimbSet il = in, ol = out;
+            il.base += (min_size - 1) * in.limb_stride;
+            ol.base += (min_size - 1) * out.limb_stride;
+            if (m->flavour == PGB_NTT120) PGB_TRY(ntt120_forward(m, il, ol, 1, (int)bt->count, mask));
+            else PGB_TRY(fft64_forward(m, il, ol, 1, (int)bt->count, mask));
+        }
+        PGB_TRY(raw_limbs(m, true, shift(out, min_size), shift(out, min_size), n * pb, (uint32_t)(res->size - min_size), (uint32_t)bt->count));
+    }
+    return PGB_OK;
+}
+extern "C" int pgb_cnv_prepare_left(pgb_module *m, pgb_vec_znx_dft *res, const pgb_vec_znx *a, int64_t mask) {
+    PGB_TRY(cnv_prepare_impl(m, res, a, mask, &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_cnv_prepare_right(pgb_module *m, pgb_vec_znx_dft *res, const pgb_vec_znx *a, int64_t mask) {
+    PGB_TRY(cnv_prepare_impl(m, res, a, mask, &ONE));
+    return sync_if(m, true);
+}
+// cnv_prepare_self (ntt120/convolution.rs:177-236): both operands from one input; here both layouts coincide
+extern "C" int pgb_cnv_prepare_self(pgb_module *m, pgb_vec_znx_dft *left, pgb_vec_znx_dft *right, const pgb_vec_znx *a, int64_t mask) {
+    PGB_REQUIRE(left->cols == right->cols && left->size == right->size, "cnv_prepare_self: left and right must have the same shape");
+    PGB_TRY(cnv_prepare_impl(m, left, a, mask, &ONE));
+    PGB_CHECK_CUDA(cudaMemcpyAsync(right->data, left->data, m->n * left->cols * left->size * prep_bytes(m), cudaMemcpyDeviceToDevice, m->stream));
+    return sync_if(m, true);
+}
+static int cnv_apply_impl(pgb_module *m, uint64_t cnv_offset, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a, uint64_t a_i,
+                          uint64_t a_j, const pgb_vec_znx_dft *b, uint64_t b_i, uint64_t b_j, const pgb_batch *bt) {
+    CHECK_BATCH(bt);
+    CHECK_N(res, "cnv_apply_dft(res)");
+    CHECK_N(a, "cnv_apply_dft(a)");
+    CHECK_N(b, "cnv_apply_dft(b)");
+    CHECK_COL(res, res_col, "cnv_apply_dft(res)");
+    CHECK_COL(a, a_i, "cnv_apply_dft(a)");
+    CHECK_COL(a, a_j, "cnv_apply_dft(a)");
+    CHECK_COL(b, b_i, "cnv_apply_dft(b)");
+    CHECK_COL(b, b_j, "cnv_apply_dft(b)");
+    LimbSet none = {nullptr, 0, 0};
+    const bool pair = a_i != a_j;
+    return cnv_apply(m, dft_col(m, res, res_col, 0, bt->stride_res), (int)res->size, dft_col(m, a, a_i, 0, bt->stride_a),
+                     pair ? dft_col(m, a, a_j, 0, bt->stride_a) : none, (int)a->size, dft_col(m, b, b_i, 0, bt->stride_b),
+                     pair ? dft_col(m, b, b_j, 0, bt->stride_b) : none, (int)b->size, cnv_offset, (uint32_t)bt->count);
+}
+extern "C" int pgb_cnv_apply_dft(pgb_module *m, uint64_t cnv_offset, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a,
+                                 uint64_t a_col, const pgb_vec_znx_dft *b, uint64_t b_col) {
+    PGB_TRY(cnv_apply_impl(m, cnv_offset, res, res_col, a, a_col, a_col, b, b_col, b_col, &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_cnv_apply_dft_batched(pgb_module *m, uint64_t cnv_offset, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a,
+                                         uint64_t a_col, const pgb_vec_znx_dft *b, uint64_t b_col, const pgb_batch *bt) {
+    return cnv_apply_impl(m, cnv_offset, res, res_col, a, a_col, a_col, b, b_col, b_col, bt);
+}
+// cnv_pairwise_apply_dft (ntt120/convolution.rs:441-557): (a[:, i] + a[:, j]) x (b[:, i] + b[:, j]); i == j is the plain product
+extern "C" int pgb_cnv_pairwise_apply_dft(pgb_module *m, uint64_t cnv_offset, pgb_vec_znx_dft *res, uint64_t res_col, const pgb_vec_znx_dft *a,
+                                          const pgb_vec_znx_dft *b, uint64_t col_i, uint64_t col_j) {
+    PGB_TRY(cnv_apply_impl(m, cnv_offset, res, res_col, a, col_i, col_j, b, col_i, col_j, &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_cnv_pairwise_apply_dft_batched(pgb_module *m, uint64_t cnv_offset, pgb_vec_znx_dft *res, uint64_t res_col,
+                                                  const pgb_vec_znx_dft *a, const pgb_vec_znx_dft *b, uint64_t col_i, uint64_t col_j,
+                                                  const pgb_batch *bt) {
+    return cnv_apply_impl(m, cnv_offset, res, res_col, a, col_i, col_j, b, col_i, col_j, bt);
+}
+// cnv_by_const_apply (ntt120/convolution.rs:361-410, fft64/convolution.rs:144-191): `b` is a HOST array of b_size limb constants
+extern "C" int pgb_cnv_by_const_apply(pgb_module *m, uint64_t cnv_offset, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx *a,
+                                      uint64_t a_col, const int64_t *b, uint64_t b_size) {
+    CHECK_N(res, "cnv_by_const_apply(res)");
+    CHECK_N(a, "cnv_by_const_apply(a)");
+    CHECK_COL(res, res_col, "cnv_by_const_apply(res)");
+    CHECK_COL(a, a_col, "cnv_by_const_apply(a)");
+    PGB_REQUIRE(b_size <= 4096, "cnv_by_const_apply: b_size too large");
+    const uint64_t n = m->n, bb = big_bytes(m);
+    long long *b_dev = nullptr;
+    if (b_size) {
+        PGB_CHECK_CUDA(cudaMallocAsync(&b_dev, b_size * 8, m->stream));
+        PGB_CHECK_CUDA(cudaMemcpyAsync(b_dev, b, b_size * 8, cudaMemcpyHostToDevice, m->stream));
+    }
+    LimbSet R = {(char *)res->data + limb_off(n, res->cols, res_col, 0, bb), res->cols * n * bb, 0};
+    LimbSet A = {(char *)a->data + limb_off(n, a->cols, a_col, 0, 8), a->cols * n * 8, 0};
+    int s = cnv_by_const(m, R, (int)res->size, A, (int)a->size, b_dev, (int)b_size, cnv_offset, 1);
+    if (b_dev) cudaFreeAsync(b_dev, m->stream);
+    PGB_TRY(s);
+    return sync_if(m, true);
+}

@@ -341,7 +341,7 @@ int znx_rotate(pgb_module *m, LimbSet dst, LimbSet a, long long p, const long lo
 struct ZnxEwArgs {
     LimbSet dst, a;
     uint32_t n;
-    int op; // 0 add_assign, 1 sub_assign, 2 mul_xp_minus_one (dst = X^p a - a)
+    int op; // 0 add_assign, 1 sub_assign, 2 mul_xp_minus_one (dst = X^p a - a), 3 copy, 4 negate (dst = -a)
     const long long *p_dev;
     long long p;
     uint32_t p_stride;
@@ -355,6 +355,10 @@ __global__ void __launch_bounds__(256) znx_ew_kernel(ZnxEwArgs q) {
         dst[i] = (long long)((unsigned long long)dst[i] + (unsigned long long)src[i]);
     } else if (q.op == 1) {
         dst[i] = (long long)((unsigned long long)dst[i] - (unsigned long long)src[i]);
+    } else if (q.op == 3) {
+        dst[i] = src[i];
+    } else if (q.op == 4) {
+        dst[i] = (long long)(0ull - (unsigned long long)src[i]);
     } else {
         const long long p = q.p_dev ? q.p_dev[(size_t)blockIdx.z * q.p_stride] : q.p;
         const uint32_t n = q.n, mp = (uint32_t)(p & (long long)(2 * n - 1));

@@ -281,6 +281,174 @@ extern "C" int pgb_glwe_external_product_batched(pgb_module *m, pgb_vec_znx *res
     return PGB_OK;
 }
 
+// ---- GLWE tensoring and relinearisation: the two halves of CKKS multiplication -------------------------------------
+// poulpy-core/src/operations/glwe.rs:699-818 (glwe_tensor_apply), :545-610 (glwe_tensor_relinearize);
+// poulpy-ckks/src/leveled/default/mul.rs:49-86 (ckks_mul_into = tensor_apply + relinearize).
+static int64_t msb_mask_bottom_limb(uint64_t base2k, uint64_t k) { // operations/glwe.rs:921-926
+    const uint64_t r = k % base2k;
+    return r == 0 ? ~(int64_t)0 : (int64_t)(~(uint64_t)0 << (base2k - r));
+}
+static uint64_t normalize_input_limb_bound_with_offset(uint64_t full, uint64_t res_size, uint64_t res_base2k, uint64_t in_base2k, int64_t off) {
+    int64_t ob = off % (int64_t)in_base2k; // operations/glwe.rs:928-957
+    if (off < 0 && ob != 0) ob += (int64_t)in_base2k;
+    return umin64(full, div_ceil64(res_size * res_base2k + (uint64_t)ob, in_base2k));
+}
+struct TensorPlan {
+    uint64_t off_hi, dft_size;
+    int64_t off_lo;
+};
+static TensorPlan tensor_plan(uint64_t cnv_offset, uint64_t ab_base2k, uint64_t a_size, uint64_t b_size, uint64_t res_size, uint64_t res_base2k) {
+    TensorPlan t;
+    if (cnv_offset < ab_base2k) { // operations/glwe.rs:753-757
+        t.off_hi = 0;
+        t.off_lo = -(int64_t)(ab_base2k - (cnv_offset % ab_base2k));
+    } else {
+        t.off_hi = cnv_offset / ab_base2k - 1;
+        t.off_lo = (int64_t)(cnv_offset % ab_base2k);
+    }
+    t.dft_size = normalize_input_limb_bound_with_offset(a_size + b_size - t.off_hi, res_size, res_base2k, ab_base2k, t.off_lo);
+    return t;
+}
+extern "C" size_t pgb_glwe_tensor_apply_tmp_bytes(const pgb_module *m, uint64_t rank, uint64_t res_size, uint64_t res_base2k, uint64_t a_size,
+                                                  uint64_t b_size, uint64_t ab_base2k, uint64_t cnv_offset, uint64_t batch) {
+    const uint64_t n = m->n, pb = prep_bytes(m), cols = rank + 1;
+    const TensorPlan t = tensor_plan(cnv_offset, ab_base2k, a_size, b_size, res_size, res_base2k);
+    return align_up(batch * n * cols * a_size * pb) + align_up(batch * n * cols * b_size * pb) + align_up(batch * n * t.dft_size * pb) +
+           align_up(batch * n * res_size * 8) + ALIGN;
+}
+// res: `count` GLWETensor VecZnx with (rank+1)(rank+2)/2 columns (stride bt->stride_res); a / b: GLWE VecZnx (strides stride_a / stride_b)
+extern "C" int pgb_glwe_tensor_apply_batched(pgb_module *m, uint64_t cnv_offset, pgb_vec_znx *res, uint64_t res_base2k, const pgb_vec_znx *a,
+                                             uint64_t a_effective_k, const pgb_vec_znx *b, uint64_t b_effective_k, uint64_t ab_base2k,
+                                             const pgb_batch *bt, void *scratch, size_t scratch_len) {
+    PGB_REQUIRE(bt && bt->count >= 1 && bt->count <= 65535, "glwe_tensor_apply: batch count must be in [1, 65535]");
+    PGB_REQUIRE(res->n == m->n && a->n == m->n && b->n == m->n, "glwe_tensor_apply: ring degree mismatch");
+    const uint64_t n = m->n, pb = prep_bytes(m), B = bt->count, cols = a->cols;
+    PGB_REQUIRE(b->cols == cols && res->cols == cols * (cols + 1) / 2, "glwe_tensor_apply: res must have (rank+1)(rank+2)/2 columns");
+    PGB_REQUIRE(div_ceil64(a_effective_k, ab_base2k) == a->size && div_ceil64(b_effective_k, ab_base2k) == b->size,
+                "glwe_tensor_apply: effective_k does not match the operand sizes"); // operations/glwe.rs:727-728
+    const size_t need = pgb_glwe_tensor_apply_tmp_bytes(m, cols - 1, res->size, res_base2k, a->size, b->size, ab_base2k, cnv_offset, B);
+    if (scratch_len < need) {
+        pgb_set_error("glwe_tensor_apply: scratch of %zu bytes < required %zu", scratch_len, need);
+        return PGB_ERR_SCRATCH;
+    }
+    const TensorPlan t = tensor_plan(cnv_offset, ab_base2k, a->size, b->size, res->size, res_base2k);
+    Arena ar = {(char *)scratch, scratch_len, 0};
+    const uint64_t ap_bs = n * cols * a->size * pb, bp_bs = n * cols * b->size * pb, rd_bs = n * t.dft_size * pb, tmp_bs = n * res->size * 8;
+    pgb_vec_znx_dft a_prep = mk(ar.take(B * ap_bs), n, cols, a->size), b_prep = mk(ar.take(B * bp_bs), n, cols, b->size);
+    pgb_vec_znx_dft res_dft = mk(ar.take(B * rd_bs), n, 1, t.dft_size);
+    pgb_vec_znx tmp = mk(ar.take(B * tmp_bs), n, 1, res->size);
+    pgb_batch bta = {B, ap_bs, bt->stride_a, 0}, btb = {B, bp_bs, bt->stride_b, 0};
+    PGB_TRY(cnv_prepare_impl(m, &a_prep, a, msb_mask_bottom_limb(ab_base2k, a_effective_k), &bta)); // :736-740
+    PGB_TRY(cnv_prepare_impl(m, &b_prep, b, msb_mask_bottom_limb(ab_base2k, b_effective_k), &btb));
+    const uint64_t res_ls = res->cols * n * 8;
+    auto tensor_col = [&](uint64_t c) { LimbSet s = {(char *)res->data + c * n * 8, res_ls, bt->stride_res}; return s; };
+    const LimbSet T = {(char *)tmp.data, n * 8, tmp_bs};
+    auto product = [&](uint64_t i, uint64_t j) -> int { // tmp <- normalize(idft(cnv(a_prep, b_prep; i, j)))
+        pgb_batch btc = {B, rd_bs, ap_bs, bp_bs};
+        PGB_TRY(pgb_cnv_pairwise_apply_dft_batched(m, t.off_hi, &res_dft, 0, &a_prep, &b_prep, i, j, &btc));
+        pgb_batch bti = {B, rd_bs, 0, 0};
+        PGB_TRY(pgb_vec_znx_idft_apply_consume_batched(m, &res_dft, &bti));
+        pgb_batch btn = {B, tmp_bs, rd_bs, 0};
+        return big_normalize_impl(m, &tmp, res_base2k, t.off_lo, 0, &res_dft, ab_base2k, 0, 0, true, &btn);
+    };
+    const uint32_t rs = (uint32_t)res->size;
+    for (uint64_t i = 0; i < cols; i++) { // :773-797
+        const uint64_t col_i = i * cols - (i * (i + 1) / 2);
+        PGB_TRY(product(i, i));
+        PGB_TRY(znx_ew(m, 3, tensor_col(col_i + i), T, 0, nullptr, 0, rs, (uint32_t)B)); // vec_znx_copy
+        for (uint64_t j = 0; j < cols; j++) {
+            if (j == i) continue;
+            if (j < i) {
+                const uint64_t col_j = j * cols - (j * (j + 1) / 2);
+                PGB_TRY(znx_ew(m, 1, tensor_col(col_j + i), T, 0, nullptr, 0, rs, (uint32_t)B)); // vec_znx_sub_assign
+            } else {
+                PGB_TRY(znx_ew(m, 4, tensor_col(col_i + j), T, 0, nullptr, 0, rs, (uint32_t)B)); // vec_znx_negate
+            }
+        }
+    }
+    for (uint64_t i = 0; i < cols; i++) { // :799-816
+        const uint64_t col_i = i * cols - (i * (i + 1) / 2);
+        for (uint64_t j = i + 1; j < cols; j++) {
+            PGB_TRY(product(i, j));
+            PGB_TRY(znx_ew(m, 0, tensor_col(col_i + j), T, 0, nullptr, 0, rs, (uint32_t)B)); // vec_znx_add_assign
+        }
+    }
+    return PGB_OK;
+}
+
+extern "C" size_t pgb_glwe_tensor_relinearize_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t a_size, uint64_t a_base2k,
+                                                        const pgb_vmp_pmat *tsk, uint64_t key_base2k, uint64_t dsize, uint64_t batch) {
+    (void)res_size;
+    const uint64_t n = m->n, pb = prep_bytes(m), cols = tsk->cols_out, pairs = tsk->cols_in;
+    const uint64_t a_dft_size = div_ceil64(a_size * a_base2k, key_base2k);
+    uint64_t t = align_up(batch * n * pairs * a_dft_size * pb) + align_up(batch * n * a_dft_size * 8) + align_up(batch * n * cols * tsk->size * pb);
+    if (dsize > 1) t += align_up(batch * n * pairs * div_ceil64(a_dft_size, dsize) * pb) + align_up(batch * n * cols * tsk->size * pb);
+    return t + ALIGN;
+}
+// a: `count` GLWETensor VecZnx (cols + pairs columns, stride bt->stride_a); tsk: prepared tensor key VmpPMat(dnum, pairs, cols, size)
+extern "C" int pgb_glwe_tensor_relinearize_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, const pgb_vec_znx *a, uint64_t a_base2k,
+                                                   const pgb_vmp_pmat *tsk, uint64_t key_base2k, uint64_t dsize, const pgb_batch *bt,
+                                                   void *scratch, size_t scratch_len) {
+    PGB_REQUIRE(bt && bt->count >= 1 && bt->count <= 65535, "glwe_tensor_relinearize: batch count must be in [1, 65535]");
+    PGB_REQUIRE(res->n == m->n && a->n == m->n && tsk->n == m->n, "glwe_tensor_relinearize: ring degree mismatch");
+    const uint64_t n = m->n, pb = prep_bytes(m), B = bt->count, cols = tsk->cols_out, pairs = tsk->cols_in;
+    PGB_REQUIRE(res->cols == cols && a->cols == cols + pairs, "glwe_tensor_relinearize: rank mismatch"); // :571-572
+    PGB_REQUIRE(dsize >= 1, "glwe_tensor_relinearize: dsize must be >= 1");
+    const size_t need = pgb_glwe_tensor_relinearize_tmp_bytes(m, res->size, a->size, a_base2k, tsk, key_base2k, dsize, B);
+    if (scratch_len < need) {
+        pgb_set_error("glwe_tensor_relinearize: scratch of %zu bytes < required %zu", scratch_len, need);
+        return PGB_ERR_SCRATCH;
+    }
+    Arena ar = {(char *)scratch, scratch_len, 0};
+    const uint64_t a_dft_size = div_ceil64(a->size * a_base2k, key_base2k);
+    const uint64_t a_dft_bs = n * pairs * a_dft_size * pb, conv_bs = n * a_dft_size * 8, res_dft_bs = n * cols * tsk->size * pb;
+    pgb_vec_znx_dft a_dft = mk(ar.take(B * a_dft_bs), n, pairs, a_dft_size);
+    pgb_vec_znx a_conv = mk(ar.take(B * conv_bs), n, 1, a_dft_size);
+    pgb_vec_znx_dft res_dft = mk(ar.take(B * res_dft_bs), n, cols, tsk->size);
+    for (uint64_t i = 0; i < pairs; i++) { // :579-589
+        pgb_batch btd = {B, a_dft_bs, bt->stride_a, 0};
+        if (a_base2k != key_base2k) {
+            pgb_batch btn = {B, conv_bs, bt->stride_a, 0};
+            PGB_TRY(big_normalize_impl(m, &a_conv, key_base2k, 0, 0, a, a_base2k, cols + i, 0, false, &btn));
+            btd.stride_a = conv_bs;
+            PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &a_dft, i, &a_conv, 0, &btd));
+        } else {
+            PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &a_dft, i, a, cols + i, &btd));
+        }
+    }
+    pgb_vec_znx_dft ai = a_dft, tmp = res_dft;
+    uint64_t ai_bs = 0, tmp_bs = 0;
+    if (dsize > 1) {
+        const uint64_t ai_max = umin64(div_ceil64(a_dft_size, dsize), tsk->rows);
+        ai_bs = n * pairs * ai_max * pb;
+        ai = mk(ar.take(B * ai_bs), n, pairs, ai_max);
+        tmp_bs = res_dft_bs;
+        tmp = mk(ar.take(B * tmp_bs), n, cols, tsk->size);
+        PGB_REQUIRE(ai.data && tmp.data, "glwe_tensor_relinearize: scratch exhausted");
+        PGB_CHECK_CUDA(cudaMemsetAsync(ai.data, 0, B * ai_bs, m->stream));
+        PGB_CHECK_CUDA(cudaMemsetAsync(tmp.data, 0, B * tmp_bs, m->stream));
+    }
+    PGB_CHECK_CUDA(cudaMemsetAsync(res_dft.data, 0, B * res_dft_bs, m->stream));
+    PGB_TRY(gadget_product(m, &res_dft, &a_dft, tsk, dsize, true, &ai, &tmp, res_dft_bs, a_dft_bs, ai_bs, tmp_bs, B)); // :593
+    pgb_batch btc = {B, res_dft_bs, 0, 0};
+    PGB_TRY(pgb_vec_znx_idft_apply_consume_batched(m, &res_dft, &btc));
+    pgb_vec_znx_big res_big = res_dft;
+    for (uint64_t i = 0; i < cols; i++) { // :596-606 (sic: the reference tests res_base2k == key_base2k)
+        if (res_base2k == key_base2k) {
+            pgb_batch bts = {B, res_dft_bs, bt->stride_a, 0};
+            PGB_TRY(big_add_small_impl(m, &res_big, i, a, i, &bts));
+        } else {
+            pgb_batch btn = {B, conv_bs, bt->stride_a, 0};
+            PGB_TRY(big_normalize_impl(m, &a_conv, key_base2k, 0, 0, a, a_base2k, i, 0, false, &btn));
+            pgb_batch bts = {B, res_dft_bs, conv_bs, 0};
+            PGB_TRY(big_add_small_impl(m, &res_big, i, &a_conv, 0, &bts));
+        }
+    }
+    pgb_batch btn = {B, bt->stride_res, res_dft_bs, 0};
+    for (uint64_t i = 0; i < res->cols; i++) PGB_TRY(big_normalize_impl(m, res, res_base2k, 0, i, &res_big, key_base2k, i, 0, true, &btn));
+    return PGB_OK;
+}
+
 // ---- host-buffer front ends ---------------------------------------------------------------------------------------------------
 // Chunked three-stage pipeline (H2D on aux stream 0, compute on the module stream, D2H on aux stream 1), double buffered.
 static int ensure_ws(pgb_module *m, size_t len) {

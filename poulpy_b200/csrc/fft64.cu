@@ -18,6 +18,7 @@ struct FftJobs {
     LimbSet in, out;
     int jobs_per_batch;
     int total_jobs;
+    long long and_mask; // i64 inputs are ANDed with this before conversion (cnv_prepare's masked last limb); -1 = none
 };
 
 template <int L, int L0> struct FFwdMid {
@@ -67,7 +68,7 @@ template <int L, int LPC> __global__ void __launch_bounds__(FGeo<L>::T *LPC) fft
 #pragma unroll
     for (int jj = 0; jj < 8; jj++) {
         const int idx = t + jj * G::T;
-        x[jj] = active ? make_double2((double)__ldg(gin + idx), (double)__ldg(gin + G::M + idx)) : make_double2(0.0, 0.0);
+        x[jj] = active ? make_double2((double)(__ldg(gin + idx) & jb.and_mask), (double)(__ldg(gin + G::M + idx) & jb.and_mask)) : make_double2(0.0, 0.0);
     }
     fct_radix8<G::R0>(x, tw, 1u);
     if (L == G::R0) {
@@ -220,6 +221,7 @@ template <int L> static int flaunch_inv(pgb_module *m, const FftJobs &jb) {
 struct FTopJobs {
     LimbSet in, out;
     int jobs_per_batch, total_jobs, m;
+    long long and_mask;
 };
 __global__ void __launch_bounds__(256) fft64_fwd_top8_kernel(FTopJobs jb, const double2 *__restrict__ tw) {
     const int m = jb.m, s = m >> 3;
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(256) fft64_fwd_top8_kernel(FTopJobs jb, const 
     double *gout = reinterpret_cast<double *>(jb.out.base + (size_t)b * jb.out.batch_stride + (size_t)j * jb.out.limb_stride);
     double2 x[8];
 #pragma unroll
-    for (int jj = 0; jj < 8; jj++) x[jj] = make_double2((double)__ldg(gin + i + jj * s), (double)__ldg(gin + m + i + jj * s));
+    for (int jj = 0; jj < 8; jj++) x[jj] = make_double2((double)(__ldg(gin + i + jj * s) & jb.and_mask), (double)(__ldg(gin + m + i + jj * s) & jb.and_mask));
     fct_radix8<3>(x, tw, 1u);
 #pragma unroll
     for (int jj = 0; jj < 8; jj++) {
@@ -337,10 +339,10 @@ template <int L> static int flaunch_inv_sub(pgb_module *m, LimbSet in, LimbSet o
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;
 }
-static int fft64_forward_large(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch) {
+static int fft64_forward_large(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch, long long and_mask) {
     const int total = jobs_per_batch * batch, mm = (int)(m->n / 2);
     PGB_REQUIRE(total <= 65535, "FFT64 large-n path: more than 65535 limbs per call (split the batch)");
-    FTopJobs tj = {in, out, jobs_per_batch, total, mm};
+    FTopJobs tj = {in, out, jobs_per_batch, total, mm, and_mask};
     dim3 grid(((unsigned)(mm >> 3) + 255) / 256, total);
     { ProfScope _ps(m, PROF_DFT_FWD);
     fft64_fwd_top8_kernel<<<grid, 256, 0, m->stream>>>(tj, m->fft_fwd);
@@ -378,14 +380,14 @@ static int fft64_inverse_large(pgb_module *m, LimbSet in, LimbSet out, int jobs_
         return PGB_ERR_UNSUPPORTED;                \
     }
 
-int fft64_forward(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch) {
-    FftJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch};
+int fft64_forward(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch, long long and_mask) {
+    FftJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch, and_mask};
     if (jb.total_jobs == 0) return PGB_OK;
-    if (m->log_n >= 15) return fft64_forward_large(m, in, out, jobs_per_batch, batch);
+    if (m->log_n >= 15) return fft64_forward_large(m, in, out, jobs_per_batch, batch, and_mask);
     FFT_DISPATCH(flaunch_fwd)
 }
 int fft64_inverse_big(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch) {
-    FftJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch};
+    FftJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch, -1};
     if (jb.total_jobs == 0) return PGB_OK;
     if (m->log_n >= 15) return fft64_inverse_large(m, in, out, jobs_per_batch, batch);
     FFT_DISPATCH(flaunch_inv)

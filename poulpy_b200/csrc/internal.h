@@ -10,7 +10,7 @@ enum { BIG_ADD_SMALL = 0, BIG_FROM_SMALL = 1, BIG_ZERO = 2 };
 
 // ntt120_dft.cu
 int ntt120_module_init(pgb_module *m);
-int ntt120_forward(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch);
+int ntt120_forward(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch, long long and_mask = -1);
 // same, skipping the batch items b with skip[b] != 0 (device array); single-CTA sizes only
 int ntt120_forward_skip(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch, const int *skip);
 int ntt120_inverse_big(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch);
@@ -31,7 +31,7 @@ int ntt120_vmp(pgb_module *m, const char *a, uint64_t a_bs, char *res, uint64_t 
 int ntt120_ew(pgb_module *m, int op, LimbSet dst, LimbSet a, LimbSet b, uint32_t jobs, uint32_t batch);
 // fft64.cu
 int fft64_module_init(pgb_module *m);
-int fft64_forward(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch);
+int fft64_forward(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch, long long and_mask = -1);
 int fft64_inverse_big(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch);
 int fft64_vmp(pgb_module *m, const char *a, uint64_t a_bs, char *res, uint64_t res_bs, const char *pm, uint64_t pm_bs,
               uint32_t row_max, uint32_t C, uint32_t col0, uint32_t ncols_out, uint32_t batch);
@@ -48,6 +48,12 @@ int big_ew(pgb_module *m, bool big_is_i128, int op, LimbSet dst, LimbSet a, uint
 int znx_rotate(pgb_module *m, LimbSet dst, LimbSet a, long long p, const long long *p_dev, uint32_t p_stride, uint32_t jobs, uint32_t batch);
 int znx_ew(pgb_module *m, int op, LimbSet dst, LimbSet a, long long p, const long long *p_dev, uint32_t p_stride, uint32_t jobs, uint32_t batch);
 int raw_limbs(pgb_module *m, bool zero, LimbSet dst, LimbSet a, uint64_t limb_bytes, uint32_t jobs, uint32_t batch);
+// cnv.cu
+int cnv_apply(pgb_module *m, LimbSet res, int res_size, LimbSet a, LimbSet a2, int a_size, LimbSet b, LimbSet b2, int b_size, uint64_t cnv_offset,
+              uint32_t batch);
+int cnv_by_const(pgb_module *m, LimbSet res, int res_size, LimbSet a, int a_size, const long long *b_dev, int b_size, uint64_t cnv_offset,
+                 uint32_t batch);
+int cnv_prepare_impl(pgb_module *m, pgb_vec_znx_dft *res, const pgb_vec_znx *a, int64_t mask, const pgb_batch *bt);
 // api.cu (used by core.cu)
 int vmp_apply_impl(pgb_module *m, pgb_vec_znx_dft *res, const pgb_vec_znx_dft *a, const pgb_vmp_pmat *pmat, uint64_t limb_offset,
                    const pgb_batch *bt);

@@ -79,6 +79,7 @@ struct NttJobs {
     int jobs_per_batch;
     int total_jobs;
     const int *skip; // optional, per batch item: non-zero = leave this item alone (forward kernel only)
+    long long and_mask; // i64 inputs are ANDed with this before the residue map (cnv_prepare's masked last limb); -1 = none
 };
 
 // ---------------------------------------------------------------------------------------------- forward
@@ -171,7 +172,7 @@ template <int L, int LPC> __global__ void __launch_bounds__(Geo<L>::T *LPC) ntt1
 
     long long v[8];
 #pragma unroll
-    for (int jj = 0; jj < 8; jj++) v[jj] = active ? __ldg(gin + t + jj * G::T) : 0;
+    for (int jj = 0; jj < 8; jj++) v[jj] = active ? (__ldg(gin + t + jj * G::T) & jb.and_mask) : 0;
     fwd_prime<0, L>(v, sm + 0 * G::PLANE, gout + 0 * n, tw + 0 * n, t, active);
     fwd_prime<1, L>(v, sm + 1 * G::PLANE, gout + 1 * n, tw + 1 * n, t, active);
     fwd_prime<2, L>(v, sm + 2 * G::PLANE, gout + 2 * n, tw + 2 * n, t, active);
@@ -311,6 +312,7 @@ template <int L, int LPC> __global__ void __launch_bounds__(Geo<L>::T *LPC) ntt1
 struct TopJobs {
     LimbSet in, out;
     int jobs_per_batch, total_jobs, n;
+    long long and_mask;
 };
 __global__ void __launch_bounds__(256) ntt120_fwd_top8_kernel(TopJobs jb, const uint2 *__restrict__ tw) {
     const int n = jb.n, s = n >> 3;
@@ -321,7 +323,7 @@ __global__ void __launch_bounds__(256) ntt120_fwd_top8_kernel(TopJobs jb, const 
     uint32_t *gout = reinterpret_cast<uint32_t *>(jb.out.base + (size_t)b * jb.out.batch_stride + (size_t)j * jb.out.limb_stride);
     long long v[8];
 #pragma unroll
-    for (int jj = 0; jj < 8; jj++) v[jj] = __ldg(gin + i + jj * s);
+    for (int jj = 0; jj < 8; jj++) v[jj] = __ldg(gin + i + jj * s) & jb.and_mask;
     uint32_t x[8];
 #define TOP_FWD(K)                                                   \
     _Pragma("unroll") for (int jj = 0; jj < 8; jj++) x[jj] = from_i64<K>(v[jj]); \
@@ -880,13 +882,13 @@ template <int L> static int launch_inv_sub(pgb_module *m, LimbSet in, LimbSet ou
     return PGB_OK;
 }
 
-static int ntt120_forward_large(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch) {
+static int ntt120_forward_large(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch, long long and_mask) {
     const int total = jobs_per_batch * batch;
     for (int j0 = 0; j0 < total; j0 += 32768) { // gridDim.y limit
         // jobs are (batch, limb) pairs in batch-major order: split on whole batches when there are many, else on limbs
         const int cnt = total - j0 < 32768 ? total - j0 : 32768;
         PGB_REQUIRE(j0 == 0 && cnt == total, "NTT120 large-n path: more than 32768 limbs per call (split the batch)");
-        TopJobs tj = {in, out, jobs_per_batch, total, (int)m->n};
+        TopJobs tj = {in, out, jobs_per_batch, total, (int)m->n, and_mask};
         dim3 grid(((unsigned)(m->n >> 3) + 255) / 256, cnt);
         { ProfScope _ps(m, PROF_DFT_FWD);
         ntt120_fwd_top8_kernel<<<grid, 256, 0, m->stream>>>(tj, m->ntt_fwd);
@@ -935,7 +937,7 @@ static int ntt120_inverse_large(pgb_module *m, LimbSet in, LimbSet out, int jobs
         case 15: PGB_TRY(launch_inv_sub<12>(m, cin, ws, jobs_per_batch, total)); break;
         default: PGB_TRY(launch_inv_sub<13>(m, cin, ws, jobs_per_batch, total)); break;
         }
-        TopJobs tj = {ws, cout, jobs_per_batch, total, (int)m->n};
+        TopJobs tj = {ws, cout, jobs_per_batch, total, (int)m->n, -1};
         dim3 grid(((unsigned)(m->n >> 3) + 255) / 256, total);
         { ProfScope _ps(m, PROF_DFT_INV);
         ntt120_inv_top8_kernel<<<grid, 256, 0, m->stream>>>(tj, m->ntt_inv, m->nc);
@@ -946,21 +948,21 @@ static int ntt120_inverse_large(pgb_module *m, LimbSet in, LimbSet out, int jobs
 }
 
 // in: i64 limbs, out: 16 B/coef DFT limbs
-int ntt120_forward(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch) {
-    NttJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch, nullptr};
+int ntt120_forward(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch, long long and_mask) {
+    NttJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch, nullptr, and_mask};
     if (jb.total_jobs == 0) return PGB_OK;
-    if (m->log_n >= 14) return ntt120_forward_large(m, in, out, jobs_per_batch, batch);
+    if (m->log_n >= 14) return ntt120_forward_large(m, in, out, jobs_per_batch, batch, and_mask);
     NTT_DISPATCH(launch_fwd)
 }
 int ntt120_forward_skip(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch, const int *skip) {
-    NttJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch, skip};
+    NttJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch, skip, -1};
     if (jb.total_jobs == 0) return PGB_OK;
     PGB_REQUIRE(m->log_n < 14, "ntt120_forward_skip: single-CTA sizes only");
     NTT_DISPATCH(launch_fwd)
 }
 // in: DFT limbs, out: i128 limbs (may alias `in` limb for limb: in-place consume)
 int ntt120_inverse_big(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch) {
-    NttJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch, nullptr};
+    NttJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch, nullptr, -1};
     if (jb.total_jobs == 0) return PGB_OK;
     if (m->log_n >= 14) return ntt120_inverse_large(m, in, out, jobs_per_batch, batch);
     NTT_DISPATCH(launch_inv)

@@ -72,7 +72,8 @@ def lib():
         _lib.pgb_profile_enable.argtypes = [C.c_void_p, C.c_int]
         _lib.pgb_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
         for name in ("pgb_glwe_keyswitch_tmp_bytes", "pgb_glwe_external_product_tmp_bytes", "pgb_cggi_blind_rotate_tmp_bytes",
-                     "pgb_cggi_blind_rotate_standard_tmp_bytes", "pgb_vmp_apply_dft_tmp_bytes",
+                     "pgb_cggi_blind_rotate_standard_tmp_bytes", "pgb_vmp_apply_dft_tmp_bytes", "pgb_glwe_tensor_apply_tmp_bytes",
+                     "pgb_glwe_tensor_relinearize_tmp_bytes",
                      "pgb_bytes_of_vmp_pmat", "pgb_size_of_scalar_prep", "pgb_size_of_scalar_big"):
             getattr(_lib, name).restype = C.c_size_t
     return _lib
@@ -501,6 +502,64 @@ class Module:
     def vec_znx_normalize_assign(self, base2k, res, res_col):
         r = res.struct()
         _check(lib().pgb_vec_znx_normalize_assign(self._h, _u64(base2k), C.byref(r), _u64(res_col)))
+
+    # --- bivariate convolution (poulpy-hal/src/api/convolution.rs); CnvPVecL/R share the VecZnxDft layout ---------------------
+    def cnv_pvec_alloc(self, cols, size, batch=1) -> VecZnxDft:
+        return self.vec_znx_dft_alloc(cols, size, batch)
+
+    def cnv_prepare_left(self, res: VecZnxDft, a: VecZnx, mask=-1):
+        r, av = res.struct(), a.struct()
+        _check(lib().pgb_cnv_prepare_left(self._h, C.byref(r), C.byref(av), C.c_int64(mask)))
+
+    def cnv_prepare_right(self, res: VecZnxDft, a: VecZnx, mask=-1):
+        r, av = res.struct(), a.struct()
+        _check(lib().pgb_cnv_prepare_right(self._h, C.byref(r), C.byref(av), C.c_int64(mask)))
+
+    def cnv_prepare_self(self, left: VecZnxDft, right: VecZnxDft, a: VecZnx, mask=-1):
+        l, r, av = left.struct(), right.struct(), a.struct()
+        _check(lib().pgb_cnv_prepare_self(self._h, C.byref(l), C.byref(r), C.byref(av), C.c_int64(mask)))
+
+    def cnv_apply_dft(self, cnv_offset, res, res_col, a, a_col, b, b_col):
+        r, av, bv = res.struct(), a.struct(), b.struct()
+        _check(lib().pgb_cnv_apply_dft(self._h, _u64(cnv_offset), C.byref(r), _u64(res_col), C.byref(av), _u64(a_col), C.byref(bv), _u64(b_col)))
+
+    def cnv_pairwise_apply_dft(self, cnv_offset, res, res_col, a, b, col_i, col_j):
+        r, av, bv = res.struct(), a.struct(), b.struct()
+        _check(lib().pgb_cnv_pairwise_apply_dft(self._h, _u64(cnv_offset), C.byref(r), _u64(res_col), C.byref(av), C.byref(bv), _u64(col_i),
+                                                _u64(col_j)))
+
+    def cnv_by_const_apply(self, cnv_offset, res: VecZnxBig, res_col, a: VecZnx, a_col, b):
+        r, av = res.struct(), a.struct()
+        b = np.ascontiguousarray(b, dtype=np.int64)
+        _check(lib().pgb_cnv_by_const_apply(self._h, _u64(cnv_offset), C.byref(r), _u64(res_col), C.byref(av), _u64(a_col),
+                                            C.c_void_p(b.ctypes.data), _u64(len(b))))
+
+    # --- CKKS multiplication halves (poulpy-core/src/operations/glwe.rs:699-818, :545-610) -------------------------------------
+    def glwe_tensor_apply(self, cnv_offset, res: VecZnx, res_base2k, a: VecZnx, a_effective_k, b: VecZnx, b_effective_k, ab_base2k,
+                          scratch: DevBuf = None):
+        need = lib().pgb_glwe_tensor_apply_tmp_bytes(self._h, _u64(a.cols - 1), _u64(res.size), _u64(res_base2k), _u64(a.size), _u64(b.size),
+                                                     _u64(ab_base2k), _u64(cnv_offset), _u64(res.batch))
+        if scratch is None or scratch.nbytes < need:
+            scratch = DevBuf(need)
+        r, av, bv = res.struct(), a.struct(), b.struct()
+        bt = _BT(res.batch, res.batch_stride, a.batch_stride if a.batch > 1 else 0, b.batch_stride if b.batch > 1 else 0)
+        _check(lib().pgb_glwe_tensor_apply_batched(self._h, _u64(cnv_offset), C.byref(r), _u64(res_base2k), C.byref(av), _u64(a_effective_k),
+                                                   C.byref(bv), _u64(b_effective_k), _u64(ab_base2k), C.byref(bt), C.c_void_p(scratch.ptr),
+                                                   C.c_size_t(scratch.nbytes)))
+        return scratch
+
+    def glwe_tensor_relinearize(self, res: VecZnx, res_base2k, a: VecZnx, a_base2k, tsk: VmpPMat, key_base2k, dsize=1, scratch: DevBuf = None):
+        ks = tsk.struct()
+        need = lib().pgb_glwe_tensor_relinearize_tmp_bytes(self._h, _u64(res.size), _u64(a.size), _u64(a_base2k), C.byref(ks), _u64(key_base2k),
+                                                           _u64(dsize), _u64(res.batch))
+        if scratch is None or scratch.nbytes < need:
+            scratch = DevBuf(need)
+        r, av = res.struct(), a.struct()
+        bt = _BT(res.batch, res.batch_stride, a.batch_stride if a.batch > 1 else 0, 0)
+        _check(lib().pgb_glwe_tensor_relinearize_batched(self._h, C.byref(r), _u64(res_base2k), C.byref(av), _u64(a_base2k), C.byref(ks),
+                                                         _u64(key_base2k), _u64(dsize), C.byref(bt), C.c_void_p(scratch.ptr),
+                                                         C.c_size_t(scratch.nbytes)))
+        return scratch
 
     def cggi_x_pow_a(self) -> SvpPPol:
         res = self.svp_ppol_alloc(2 * self.n)
