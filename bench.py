@@ -180,6 +180,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner must not precede the JSON line on stdout
     import torch
     import torch.distributed as dist
 
@@ -468,6 +469,32 @@ def aux_measurements(pb, torch, local, peak):
     ms = _time_ms(torch, stream, f4, 5)
     aux["ckks_relinearize_keyswitch_per_s_ntt120_n32768_b32"] = {"value": B / (ms * 1e-3), "ms_per_batch": ms}
     del m, a, r, pm, sc
+
+    # CKKS ciphertext x ciphertext multiplication (BASELINE config 4): glwe_tensor_apply + glwe_tensor_relinearize
+    # (poulpy-ckks/src/leveled/default/mul.rs:49-86) at the reference's bench parameters (poulpy-bench/src/bench_suite/ckks.rs:31-37:
+    # base2k = 52, K = 728 = 14 limbs, rank 1, dsize 1, tensor key 15 limbs); N = 2^15 as in the reference bench and 2^16 as BASELINE asks
+    ck = {}
+    for log_n, B in ((15, 8), (16, 4)):
+        n, k, size = 1 << log_n, 52, 14
+        m = pb.Module(n, pb.NTT120, device=local)
+        m.set_stream(stream.cuda_stream)
+        tsk = m.vmp_pmat_alloc(size, 1, 2, size + 1)
+        mat = rng.integers(-(1 << 51), 1 << 51, size=(1, 1, size + 1, 2, n), dtype=np.int64)
+        m.vmp_prepare(pb.hal.VmpPMat(tsk.buf, n, 1, 1, 2, size + 1), m.mat_znx_from_numpy(mat))  # first row random, rest zero (timing only)
+        a = m.vec_znx_from_numpy(rng.integers(-(1 << 51), 1 << 51, size=(B, size, 2, n), dtype=np.int64))
+        b2 = m.vec_znx_from_numpy(rng.integers(-(1 << 51), 1 << 51, size=(B, size, 2, n), dtype=np.int64))
+        tensor = m.vec_znx_alloc(3, size, B)
+        r = m.vec_znx_alloc(2, size, B)
+        sc = [None, None]
+
+        def f5():
+            sc[0] = m.glwe_tensor_apply(size * k, tensor, k, a, size * k, b2, size * k, k, sc[0])
+            sc[1] = m.glwe_tensor_relinearize(r, k, tensor, k, tsk, k, 1, sc[1])
+
+        ms = _time_ms(torch, stream, f5, 5)
+        ck[f"log_n={log_n}"] = {"value": B / (ms * 1e-3), "unit": "ct x ct multiplications/s", "ms_per_batch": ms, "batch": B}
+        del m, a, b2, tensor, r, tsk, sc
+    aux["ckks_mul_ntt120_base2k52_k728"] = ck
 
     # batched DFT sweep (BASELINE config 1): forward then inverse over VecZnx(cols=2, size) at log_n 10..16, >= 256 MB of limbs
     sweep = {}

@@ -86,6 +86,20 @@ def main():
     res = np.zeros((1, cols, n), dtype=np.int64)
     t = timeit(lambda: m.cggi_blind_rotate_block_binary(res, lwe, lut, brk, xpa, 3, k), 2.0)
     out["M4_cggi_fft64_n512_nlwe687"] = {"bootstraps_per_s_1T": 1 / t, "bootstraps_per_s_all_cores_extrapolated": threads / t}
+    # M6: CKKS ct x ct multiplication (glwe_tensor_apply + glwe_tensor_relinearize), N = 2^15, base2k = 52, 14 limbs, single thread
+    n, k, size = 1 << 15, 52, 14
+    m = O.OracleModule(n, O.NTT120)
+    tsk = m.vmp_pmat_alloc(size, 1, 2, size + 1)
+    m.vmp_prepare(tsk, u((size, 1, size + 1, 2, n), 52))
+    a, b = u((size, 2, n), 52), u((size, 2, n), 52)
+    tensor, res = np.zeros((size, 3, n), dtype=np.int64), np.zeros((size, 2, n), dtype=np.int64)
+
+    def mul():
+        m.glwe_tensor_apply(size * k, tensor, k, a, size * k, b, size * k, k)
+        m.glwe_tensor_relinearize(res, k, tensor, k, tsk, k, 1)
+
+    t = timeit(mul, 2.0)
+    out["M6_ckks_mul_ntt120_n32768"] = {"mul_per_s_1T": 1 / t, "mul_per_s_all_cores_extrapolated": threads / t}
     print(json.dumps(out, indent=1))
 
 
