@@ -331,7 +331,8 @@ def main():
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32 (canonical residues mod four 30-bit primes; i128 big)", "data": "synthetic", "config": config_dict(B, world),
         "e2e": {"value": e2e_value, "unit": "keyswitch/s", "h2d_bytes_per_step": int(a_np.nbytes), "d2h_bytes_per_step": int(a_np.nbytes),
-                "steps": e2e_steps, "api": "pgb_glwe_keyswitch_host (pinned host buffers)"},
+                "steps": e2e_steps, "api": "pgb_glwe_keyswitch_host (pinned host buffers)",
+                "note": "PCIe bound: 393 KB cross the bus per key-switch; scripts/e2e_probe.py measured 49 GB/s pinned H2D on this box = 250 k key-switches/s ceiling"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
         "pipeline": {"fused_bytes_per_keyswitch": fused_bytes, "unfused_bytes_per_keyswitch": unfused_bytes, "achieved_gbs": step_gbs,
                      "frac_of_hbm_peak": step_gbs / peak},

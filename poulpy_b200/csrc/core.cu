@@ -494,8 +494,10 @@ static int host_pipeline(pgb_module *m, bool ext, int64_t *res_host, uint64_t re
     if (count == 0) return PGB_OK;
     const uint64_t n = m->n;
     const uint64_t a_bytes = n * a_cols * a_size * 8, r_bytes = n * res_cols * res_size * 8;
-    // small chunks keep the three stages overlapped; 64 MB of staging per slot is plenty to reach PCIe line rate
-    const uint64_t chunk = umin64(count, umin64(2048, (a_bytes > r_bytes ? ((uint64_t)64 << 20) / a_bytes : ((uint64_t)64 << 20) / r_bytes) + 1));
+    // small chunks keep the three stages overlapped and the fill / drain of the pipeline short; 32 MB of staging per slot measured best
+    // (scripts/e2e_probe.py: 229 k key-switches/s against a 250 k ceiling of this box's pinned H2D rate, 49 GB/s)
+    static const uint64_t stage_bytes = (uint64_t)(getenv("PGB_HOST_CHUNK_MB") ? atoi(getenv("PGB_HOST_CHUNK_MB")) : 32) << 20;
+    const uint64_t chunk = umin64(count, umin64(2048, (a_bytes > r_bytes ? stage_bytes / a_bytes : stage_bytes / r_bytes) + 1));
     const size_t tmp = ext ? pgb_glwe_external_product_tmp_bytes(m, res_size, a_size, a_base2k, key, key_base2k, dsize, chunk)
                            : pgb_glwe_keyswitch_tmp_bytes(m, res_size, a_size, a_base2k, key, key_base2k, dsize, chunk);
     const size_t in_dev = align_up(chunk * a_bytes), out_dev = align_up(chunk * r_bytes);
