@@ -309,6 +309,19 @@ int pgb_glwe_tensor_relinearize_batched(pgb_module *m, pgb_vec_znx *res, uint64_
                                         const pgb_vmp_pmat *tsk, uint64_t key_base2k, uint64_t dsize, const pgb_batch *bt, void *scratch,
                                         size_t scratch_len);
 
+/* ---- automorphisms ---- */
+/* vec_znx_automorphism (poulpy-cpu-ref/src/reference/vec_znx/automorphism.rs:9-38): res = a(X^p), p odd; res and a must not alias */
+int pgb_vec_znx_automorphism(pgb_module *m, int64_t p, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col);
+int pgb_vec_znx_automorphism_batched(pgb_module *m, int64_t p, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col,
+                                     const pgb_batch *bt);
+/* glwe_automorphism (poulpy-core/src/automorphism/glwe_ct.rs:51-72): glwe_keyswitch with the automorphism key of Galois element p, then
+ * X -> X^p on every column (what CKKS rotations / conjugation and the trace are made of) */
+size_t pgb_glwe_automorphism_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t a_size, uint64_t a_base2k, const pgb_vmp_pmat *key,
+                                       uint64_t key_base2k, uint64_t dsize, uint64_t batch);
+int pgb_glwe_automorphism_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, const pgb_vec_znx *a, uint64_t a_base2k,
+                                  const pgb_vmp_pmat *key, uint64_t key_base2k, int64_t p, uint64_t dsize, const pgb_batch *bt, void *scratch,
+                                  size_t scratch_len);
+
 /* ---- CGGI blind rotation (poulpy-bin-fhe/src/blind_rotation/algorithms/cggi/algorithm.rs:275-368; C3) ---- */
 /* x_pow_a table of the prepared key (cggi/key_prepared.rs:66-75): SvpPPol with 2n columns, col i = X^i. */
 int pgb_cggi_x_pow_a(pgb_module *m, pgb_svp_ppol *res);

@@ -295,3 +295,14 @@ void orc_glwe_tensor_relinearize(int flavour, const void *mod, orc_vec_znx *res,
     free(a_dft.data);
     free(res_dft.data);
 }
+
+/* poulpy-core/src/automorphism/glwe_ct.rs:51-72 (glwe_automorphism_default): key-switch with the automorphism key, then
+ * vec_znx_automorphism_assign(key.p()) on every column */
+void orc_glwe_automorphism(int flavour, const void *mod, orc_vec_znx *res, size_t res_base2k, const orc_vec_znx *a, size_t a_base2k,
+                           const orc_vmp_pmat *key, size_t key_base2k, int64_t p, size_t dsize) {
+    orc_glwe_keyswitch(flavour, mod, res, res_base2k, a, a_base2k, key, key_base2k, dsize);
+    orc_vec_znx tmp = {(int64_t *)malloc(8 * res->n * res->cols * res->size), res->n, res->cols, res->size};
+    memcpy(tmp.data, res->data, 8 * res->n * res->cols * res->size);
+    for (size_t i = 0; i < res->cols; i++) orc_vec_znx_automorphism(p, res, i, &tmp, i);
+    free(tmp.data);
+}

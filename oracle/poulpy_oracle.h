@@ -160,6 +160,9 @@ void orc_vec_znx_rotate(int64_t p, orc_vec_znx *res, size_t res_col, const orc_v
 void orc_vec_znx_add_assign(orc_vec_znx *res, size_t res_col, const orc_vec_znx *a, size_t a_col);
 void orc_vec_znx_mul_xp_minus_one_assign(int64_t p, orc_vec_znx *res, size_t res_col);
 void orc_vec_znx_normalize_assign(size_t base2k, orc_vec_znx *res, size_t res_col);
+/* reference/znx/automorphism.rs:1-17, reference/vec_znx/automorphism.rs:9-38 */
+void orc_znx_automorphism(int64_t p, int64_t *res, const int64_t *a, size_t n);
+void orc_vec_znx_automorphism(int64_t p, orc_vec_znx *res, size_t res_col, const orc_vec_znx *a, size_t a_col);
 void orc_znx_rotate(int64_t p, int64_t *res, const int64_t *a, size_t n);
 
 /* ------------------------------------------------------------ compositions */
@@ -172,6 +175,10 @@ void orc_glwe_keyswitch(int flavour, const void *mod, orc_vec_znx *res, size_t r
 void orc_glwe_external_product(int flavour, const void *mod, orc_vec_znx *res, size_t res_base2k,
                                const orc_vec_znx *a, size_t a_base2k, const orc_vmp_pmat *ggsw, size_t ggsw_base2k,
                                size_t dsize);
+
+/* poulpy-core/src/automorphism/glwe_ct.rs:51-72 */
+void orc_glwe_automorphism(int flavour, const void *mod, orc_vec_znx *res, size_t res_base2k, const orc_vec_znx *a, size_t a_base2k,
+                           const orc_vmp_pmat *key, size_t key_base2k, int64_t p, size_t dsize);
 
 /* ------------------------------------------------------------ bivariate convolution (HalImpl::cnv_*, hal_impl.rs:670-754) */
 /* CnvPVecL / CnvPVecR are opaque prepared layouts: this restatement keeps both in the VecZnxDft layout.

@@ -326,6 +326,11 @@ class OracleModule:
         lib().orc_glwe_tensor_relinearize(C.c_int(self.flavour), self._h, C.byref(r), _sz(res_base2k), C.byref(av), _sz(a_base2k),
                                           C.byref(ks), _sz(key_base2k), _sz(dsize))
 
+    def glwe_automorphism(self, res, res_base2k, a, a_base2k, key: VmpPMat, key_base2k, p, dsize=1):
+        r, av, ks = _vz(res), _vz(a), key.struct()
+        lib().orc_glwe_automorphism(C.c_int(self.flavour), self._h, C.byref(r), _sz(res_base2k), C.byref(av), _sz(a_base2k), C.byref(ks),
+                                    _sz(key_base2k), C.c_int64(p), _sz(dsize))
+
     def cggi_x_pow_a(self):
         res = self.svp_ppol_alloc(2 * self.n)
         r = _pp(res)
@@ -362,6 +367,11 @@ def vec_znx_normalize(res, res_base2k, res_offset, res_col, a, a_base2k, a_col):
 def vec_znx_rotate(p, res, res_col, a, a_col):
     r, av = _vz(res), _vz(a)
     lib().orc_vec_znx_rotate(C.c_int64(p), C.byref(r), _sz(res_col), C.byref(av), _sz(a_col))
+
+
+def vec_znx_automorphism(p, res, res_col, a, a_col):
+    r, av = _vz(res), _vz(a)
+    lib().orc_vec_znx_automorphism(C.c_int64(p), C.byref(r), _sz(res_col), C.byref(av), _sz(a_col))
 
 
 def vec_znx_normalize_assign(base2k, res, res_col):

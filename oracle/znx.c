@@ -116,3 +116,20 @@ void orc_vec_znx_normalize_assign(size_t base2k, orc_vec_znx *res, size_t res_co
     }
     free(carry);
 }
+
+/* reference/znx/automorphism.rs:1-17: a(X) -> a(X^p); coefficient i lands on i*p mod 2n, negated in the upper half */
+void orc_znx_automorphism(int64_t p, int64_t *res, const int64_t *a, size_t n) {
+    size_t k = 0, mask = 2 * n - 1, p_2n = (size_t)(p & (int64_t)mask);
+    res[0] = a[0];
+    for (size_t i = 1; i < n; i++) {
+        k = (k + p_2n) & mask;
+        if (k < n) res[k] = a[i];
+        else res[k - n] = (int64_t)(0 - (uint64_t)a[i]);
+    }
+}
+/* reference/vec_znx/automorphism.rs:9-38 */
+void orc_vec_znx_automorphism(int64_t p, orc_vec_znx *res, size_t res_col, const orc_vec_znx *a, size_t a_col) {
+    size_t mn = res->size < a->size ? res->size : a->size;
+    for (size_t j = 0; j < mn; j++) orc_znx_automorphism(p, znx_at(res, res_col, j), znx_at(a, a_col, j), res->n);
+    for (size_t j = mn; j < res->size; j++) memset(znx_at(res, res_col, j), 0, 8 * res->n);
+}

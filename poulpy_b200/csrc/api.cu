@@ -872,3 +872,27 @@ extern "C" int pgb_cnv_by_const_apply(pgb_module *m, uint64_t cnv_offset, pgb_ve
     PGB_TRY(s);
     return sync_if(m, true);
 }
+
+// ---- vec_znx_automorphism (reference/vec_znx/automorphism.rs:9-38) ---------------------------------------------------
+static int automorphism_impl(pgb_module *m, int64_t p, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col, const pgb_batch *bt) {
+    CHECK_BATCH(bt);
+    CHECK_N(res, "vec_znx_automorphism(res)");
+    CHECK_N(a, "vec_znx_automorphism(a)");
+    CHECK_COL(res, res_col, "vec_znx_automorphism(res)");
+    CHECK_COL(a, a_col, "vec_znx_automorphism(a)");
+    PGB_REQUIRE(res->data != a->data, "vec_znx_automorphism: res and a must not alias");
+    PGB_REQUIRE((p & 1) != 0, "vec_znx_automorphism: the Galois element must be odd");
+    const uint64_t n = m->n, mn = umin64(res->size, a->size);
+    LimbSet R = {(char *)res->data + limb_off(n, res->cols, res_col, 0, 8), res->cols * n * 8, bt->stride_res};
+    LimbSet A = {(char *)a->data + limb_off(n, a->cols, a_col, 0, 8), a->cols * n * 8, bt->stride_a};
+    PGB_TRY(znx_automorphism(m, R, A, p, (uint32_t)mn, (uint32_t)bt->count));
+    return raw_limbs(m, true, shift(R, mn), shift(R, mn), n * 8, (uint32_t)(res->size - mn), (uint32_t)bt->count);
+}
+extern "C" int pgb_vec_znx_automorphism(pgb_module *m, int64_t p, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col) {
+    PGB_TRY(automorphism_impl(m, p, res, res_col, a, a_col, &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_vec_znx_automorphism_batched(pgb_module *m, int64_t p, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col,
+                                                const pgb_batch *bt) {
+    return automorphism_impl(m, p, res, res_col, a, a_col, bt);
+}

@@ -376,6 +376,33 @@ int znx_ew(pgb_module *m, int op, LimbSet dst, LimbSet a, long long p, const lon
     return PGB_OK;
 }
 
+// vec_znx_automorphism (reference/znx/automorphism.rs:1-17): a(X) -> a(X^p); thread i scatters coefficient i to i*p mod 2n with the
+// negacyclic sign (a permutation: race-free)
+struct AutoArgs {
+    LimbSet dst, a;
+    uint32_t n;
+    long long p;
+};
+__global__ void __launch_bounds__(256) znx_automorphism_kernel(AutoArgs q) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q.n) return;
+    const long long *src = reinterpret_cast<const long long *>(q.a.base + (size_t)blockIdx.z * q.a.batch_stride + (size_t)blockIdx.y * q.a.limb_stride);
+    long long *dst = reinterpret_cast<long long *>(q.dst.base + (size_t)blockIdx.z * q.dst.batch_stride + (size_t)blockIdx.y * q.dst.limb_stride);
+    const uint32_t mask = 2 * q.n - 1, p2n = (uint32_t)(q.p & (long long)mask);
+    const uint32_t k = (uint32_t)(((unsigned long long)i * p2n) & mask);
+    const long long v = src[i];
+    if (k < q.n) dst[k] = v;
+    else dst[k - q.n] = (long long)(0ull - (unsigned long long)v);
+}
+int znx_automorphism(pgb_module *m, LimbSet dst, LimbSet a, long long p, uint32_t jobs, uint32_t batch) {
+    if (jobs == 0 || batch == 0) return PGB_OK;
+    ProfScope _ps(m, PROF_ELEMENTWISE);
+    AutoArgs q = {dst, a, (uint32_t)m->n, p};
+    znx_automorphism_kernel<<<dim3(((uint32_t)m->n + 255) / 256, jobs, batch), 256, 0, m->stream>>>(q);
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+
 // raw byte-wise zero / copy over limb sets (both flavours)
 struct RawArgs {
     LimbSet dst, a;

@@ -449,6 +449,34 @@ extern "C" int pgb_glwe_tensor_relinearize_batched(pgb_module *m, pgb_vec_znx *r
     return PGB_OK;
 }
 
+// ---- glwe_automorphism (poulpy-core/src/automorphism/glwe_ct.rs:51-72): key-switch with the automorphism key, then
+// X -> X^p on every column.  The key-switch lands in scratch so that the permutation is out of place.
+extern "C" size_t pgb_glwe_automorphism_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t a_size, uint64_t a_base2k,
+                                                  const pgb_vmp_pmat *key, uint64_t key_base2k, uint64_t dsize, uint64_t batch) {
+    return align_up(batch * m->n * key->cols_out * res_size * 8) + pgb_glwe_keyswitch_tmp_bytes(m, res_size, a_size, a_base2k, key, key_base2k, dsize, batch) +
+           ALIGN;
+}
+extern "C" int pgb_glwe_automorphism_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, const pgb_vec_znx *a, uint64_t a_base2k,
+                                             const pgb_vmp_pmat *key, uint64_t key_base2k, int64_t p, uint64_t dsize, const pgb_batch *bt,
+                                             void *scratch, size_t scratch_len) {
+    PGB_REQUIRE(bt && bt->count >= 1 && bt->count <= 65535, "glwe_automorphism: batch count must be in [1, 65535]");
+    PGB_REQUIRE(res->n == m->n && res->cols == key->cols_out, "glwe_automorphism: res does not match the key");
+    const size_t need = pgb_glwe_automorphism_tmp_bytes(m, res->size, a->size, a_base2k, key, key_base2k, dsize, bt->count);
+    if (scratch_len < need) {
+        pgb_set_error("glwe_automorphism: scratch of %zu bytes < required %zu", scratch_len, need);
+        return PGB_ERR_SCRATCH;
+    }
+    const uint64_t n = m->n, B = bt->count, tmp_bs = n * res->cols * res->size * 8;
+    pgb_vec_znx tmp = mk(scratch, n, res->cols, res->size);
+    char *ks_scratch = (char *)scratch + align_up(B * tmp_bs);
+    pgb_batch btk = {B, tmp_bs, bt->stride_a, 0};
+    PGB_TRY(pgb_glwe_keyswitch_batched(m, &tmp, res_base2k, a, a_base2k, key, key_base2k, dsize, &btk, ks_scratch,
+                                       scratch_len - (size_t)align_up(B * tmp_bs)));
+    pgb_batch bta = {B, bt->stride_res, tmp_bs, 0};
+    for (uint64_t i = 0; i < res->cols; i++) PGB_TRY(pgb_vec_znx_automorphism_batched(m, p, res, i, &tmp, i, &bta));
+    return PGB_OK;
+}
+
 // ---- host-buffer front ends ---------------------------------------------------------------------------------------------------
 // Chunked three-stage pipeline (H2D on aux stream 0, compute on the module stream, D2H on aux stream 1), double buffered.
 static int ensure_ws(pgb_module *m, size_t len) {

@@ -73,7 +73,7 @@ def lib():
         _lib.pgb_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
         for name in ("pgb_glwe_keyswitch_tmp_bytes", "pgb_glwe_external_product_tmp_bytes", "pgb_cggi_blind_rotate_tmp_bytes",
                      "pgb_cggi_blind_rotate_standard_tmp_bytes", "pgb_vmp_apply_dft_tmp_bytes", "pgb_glwe_tensor_apply_tmp_bytes",
-                     "pgb_glwe_tensor_relinearize_tmp_bytes",
+                     "pgb_glwe_tensor_relinearize_tmp_bytes", "pgb_glwe_automorphism_tmp_bytes",
                      "pgb_bytes_of_vmp_pmat", "pgb_size_of_scalar_prep", "pgb_size_of_scalar_big"):
             getattr(_lib, name).restype = C.c_size_t
     return _lib
@@ -559,6 +559,23 @@ class Module:
         _check(lib().pgb_glwe_tensor_relinearize_batched(self._h, C.byref(r), _u64(res_base2k), C.byref(av), _u64(a_base2k), C.byref(ks),
                                                          _u64(key_base2k), _u64(dsize), C.byref(bt), C.c_void_p(scratch.ptr),
                                                          C.c_size_t(scratch.nbytes)))
+        return scratch
+
+    def vec_znx_automorphism(self, p, res, res_col, a, a_col):
+        r, av = res.struct(), a.struct()
+        _check(lib().pgb_vec_znx_automorphism(self._h, C.c_int64(p), C.byref(r), _u64(res_col), C.byref(av), _u64(a_col)))
+
+    def glwe_automorphism(self, res: VecZnx, res_base2k, a: VecZnx, a_base2k, key: VmpPMat, key_base2k, p, dsize=1, scratch: DevBuf = None):
+        ks = key.struct()
+        need = lib().pgb_glwe_automorphism_tmp_bytes(self._h, _u64(res.size), _u64(a.size), _u64(a_base2k), C.byref(ks), _u64(key_base2k),
+                                                     _u64(dsize), _u64(res.batch))
+        if scratch is None or scratch.nbytes < need:
+            scratch = DevBuf(need)
+        r, av = res.struct(), a.struct()
+        bt = _BT(res.batch, res.batch_stride, a.batch_stride if a.batch > 1 else 0, 0)
+        _check(lib().pgb_glwe_automorphism_batched(self._h, C.byref(r), _u64(res_base2k), C.byref(av), _u64(a_base2k), C.byref(ks),
+                                                   _u64(key_base2k), C.c_int64(p), _u64(dsize), C.byref(bt), C.c_void_p(scratch.ptr),
+                                                   C.c_size_t(scratch.nbytes)))
         return scratch
 
     def cggi_x_pow_a(self) -> SvpPPol:

@@ -271,3 +271,29 @@ def test_gadget_single_kernel(n):
     g.sync()
     o.glwe_keyswitch_batch(want, 25, a, 25, po, 25)
     assert np.array_equal(g.vec_znx_to_numpy(res_g), want)
+
+
+@pytest.mark.parametrize("fl", FLAVOURS)
+@pytest.mark.parametrize("n", [256, 2048])
+def test_glwe_automorphism(fl, n):
+    """glwe_automorphism (poulpy-core/src/automorphism/glwe_ct.rs:51-72) = key-switch + X -> X^p, and the bare vec_znx_automorphism,
+    against the oracle for several Galois elements (n = 2048 takes the single-kernel key-switch in the NTT120 flavour)."""
+    g, o = pb.Module(n, fl), O.OracleModule(n, fl)
+    rng = np.random.default_rng(1300 + n + fl)
+    k, batch = (12 if fl == pb.FFT64 else 18), 5
+    pg, po = _key(g, o, rng, 3, 1, 2, 4, k)
+    a = fill_uniform(rng, (batch, 3, 2, n), k)
+    for p in (3, 5, -1, 2 * n - 1, 2 * 5 ** 3 + 1):
+        want = np.zeros((batch, 3, 2, n), dtype=np.int64)
+        res_g = g.vec_znx_alloc(2, 3, batch)
+        g.glwe_automorphism(res_g, k, g.vec_znx_from_numpy(a), k, pg, k, p)
+        g.sync()
+        for b in range(batch):
+            o.glwe_automorphism(want[b], k, a[b], k, po, k, p)
+        assert np.array_equal(g.vec_znx_to_numpy(res_g), want), p
+        x = g.vec_znx_from_numpy(a[0])
+        y = g.vec_znx_alloc(2, 4)
+        g.vec_znx_automorphism(p, y, 1, x, 0)
+        wy = np.zeros((4, 2, n), dtype=np.int64)
+        O.vec_znx_automorphism(p, wy, 1, a[0], 0)
+        assert np.array_equal(g.vec_znx_to_numpy(y)[:, 1], wy[:, 1]), p

@@ -191,3 +191,38 @@ def test_normalize_assign_and_mul_xp_minus_one():
         y = x.copy()
         O.vec_znx_mul_xp_minus_one_assign(p, y, 0)
         assert np.array_equal(y, r - x), p
+
+
+def test_automorphism_is_substitution():
+    """znx_automorphism (reference/znx/automorphism.rs:1-17) is a(X) -> a(X^p) mod X^n + 1: check against direct substitution, the
+    group law phi_p(phi_q(a)) = phi_{pq}(a) and phi_p(a * b) = phi_p(a) * phi_p(b) on a negacyclic product."""
+    n = 32
+    rng = np.random.default_rng(71)
+    a = rng.integers(-1000, 1000, size=(1, 1, n), dtype=np.int64)
+    b = rng.integers(-1000, 1000, size=(1, 1, n), dtype=np.int64)
+
+    def phi(p, x):
+        r = np.zeros_like(x)
+        O.vec_znx_automorphism(p, r, 0, x, 0)
+        return r
+
+    def direct(p, x):
+        r = np.zeros(n, dtype=np.int64)
+        for i in range(n):
+            k = (i * p) % (2 * n)
+            if k < n:
+                r[k] += x[i]
+            else:
+                r[k - n] -= x[i]
+        return r
+
+    def negacyclic(x, y):
+        full = np.convolve(x, y)
+        r = full[:n].copy()
+        r[: n - 1] -= full[n:]
+        return r
+
+    for p in (1, 3, 5, -1, 2 * n - 1, 7, -3):
+        assert np.array_equal(phi(p, a)[0, 0], direct(p, a[0, 0])), p
+    assert np.array_equal(phi(3, phi(5, a)), phi(15, a))
+    assert np.array_equal(negacyclic(phi(5, a)[0, 0], phi(5, b)[0, 0]), direct(5, negacyclic(a[0, 0], b[0, 0])))
