@@ -7,7 +7,11 @@
 // (limb-major, column-minor, 16 B / 8 B per coefficient), so "prepare" is a forward transform with the last active limb masked.
 //   res[k] = sum_{j = j_min}^{j_max - 1} a[k_abs - j] (.) b[j],   k_abs = k + min(cnv_offset, a.size + b.size - 1)
 // per frequency (and prime).  The NTT120 kernel accumulates u32 x u32 products in u64 and reduces once per 16 terms; results
-// are canonical residues, which is all the reference's CRT sees (arithmetic.rs:132).
+// are canonical residues, which is all the reference's CRT sees (arithmetic.rs:132).  (A register-tiled variant that loads every
+// limb once per thread measured no faster at the CKKS shape -- the kernel is bound by streaming the operands, which L2 already
+// de-duplicates across the output limbs of one ciphertext -- and was dropped.)
+#include <stdlib.h>
+
 #include "internal.h"
 #include "ntt120.cuh"
 

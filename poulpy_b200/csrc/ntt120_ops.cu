@@ -66,6 +66,57 @@ template <int CT> __global__ void __launch_bounds__(256) ntt120_vmp_kernel(VmpAr
     }
 }
 
+// Batch-tiled variant for matrices that do not fit in L2 (CKKS relinearisation key: 220-440 MB): one thread applies a loaded matrix
+// word to BT batch items, so the matrix crosses HBM once per BT ciphertexts instead of once per ciphertext.
+template <int CT, int BT> __global__ void __launch_bounds__(256) ntt120_vmp_bt_kernel(VmpArgs p, uint32_t batch) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= 4 * p.n4) return;
+    const PrimeRt pr(u / p.n4);
+    const uint32_t c0 = blockIdx.y * CT, b0 = blockIdx.z * BT;
+    const size_t poly_words = (size_t)4 * p.n4;
+    const uint4 *pm = reinterpret_cast<const uint4 *>(p.pm) + u + (size_t)(p.col0 + c0) * poly_words;
+    const int nc = min((uint32_t)CT, p.ncols_out - c0), nb = min((uint32_t)BT, batch - b0);
+    unsigned long long acc[BT][CT][4];
+#pragma unroll
+    for (int b = 0; b < BT; b++)
+#pragma unroll
+        for (int c = 0; c < CT; c++) acc[b][c][0] = acc[b][c][1] = acc[b][c][2] = acc[b][c][3] = 0;
+    for (uint32_t r0 = 0; r0 < p.row_max; r0 += 16) {
+        const uint32_t r1 = min(r0 + 16, p.row_max);
+        for (uint32_t r = r0; r < r1; r++) {
+            const uint4 *mrow = pm + (size_t)r * p.C * poly_words;
+            uint4 mv[CT], av[BT];
+#pragma unroll
+            for (int c = 0; c < CT; c++) mv[c] = c < nc ? __ldcs(mrow + (size_t)c * poly_words) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int b = 0; b < BT; b++)
+                av[b] = b < nb ? __ldg(reinterpret_cast<const uint4 *>(p.a + (size_t)(b0 + b) * p.a_bs) + u + (size_t)r * poly_words) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int b = 0; b < BT; b++)
+#pragma unroll
+                for (int c = 0; c < CT; c++) {
+                    acc[b][c][0] += (unsigned long long)av[b].x * mv[c].x;
+                    acc[b][c][1] += (unsigned long long)av[b].y * mv[c].y;
+                    acc[b][c][2] += (unsigned long long)av[b].z * mv[c].z;
+                    acc[b][c][3] += (unsigned long long)av[b].w * mv[c].w;
+                }
+        }
+#pragma unroll
+        for (int b = 0; b < BT; b++)
+#pragma unroll
+            for (int c = 0; c < CT; c++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc[b][c][i] = pr.reduce(acc[b][c][i]);
+    }
+#pragma unroll
+    for (int b = 0; b < BT; b++)
+#pragma unroll
+        for (int c = 0; c < CT; c++)
+            if (b < nb && c < nc)
+                (reinterpret_cast<uint4 *>(p.res + (size_t)(b0 + b) * p.res_bs) + u + (size_t)(c0 + c) * poly_words)[0] =
+                    make_uint4((uint32_t)acc[b][c][0], (uint32_t)acc[b][c][1], (uint32_t)acc[b][c][2], (uint32_t)acc[b][c][3]);
+}
+
 int ntt120_vmp(pgb_module *m, const char *a, uint64_t a_bs, char *res, uint64_t res_bs, const char *pm, uint64_t pm_bs,
                uint32_t row_max, uint32_t C, uint32_t col0, uint32_t ncols_out, uint32_t batch) {
     if (ncols_out == 0 || batch == 0) return PGB_OK;
@@ -73,6 +124,14 @@ int ntt120_vmp(pgb_module *m, const char *a, uint64_t a_bs, char *res, uint64_t 
     const uint32_t words = (uint32_t)m->n; // uint4 words per poly
     dim3 block(256);
     static int ct_sel = getenv("PGB_VMP_CT") ? atoi(getenv("PGB_VMP_CT")) : 4;
+    const uint64_t key_bytes = (uint64_t)row_max * C * 16 * m->n;
+    if (pm_bs == 0 && batch >= 4 && key_bytes >= ((uint64_t)48 << 20) && !getenv("PGB_VMP_NO_BT")) {
+        ProfScope _ps(m, PROF_VMP);
+        dim3 grid((words + 255) / 256, (ncols_out + 1) / 2, (batch + 3) / 4);
+        ntt120_vmp_bt_kernel<2, 4><<<grid, block, 0, m->stream>>>(p, batch);
+        PGB_CHECK_CUDA(cudaGetLastError());
+        return PGB_OK;
+    }
     { ProfScope _ps(m, PROF_VMP);
     if (ct_sel == 2 || ncols_out <= 2) {
         dim3 grid((words + 255) / 256, (ncols_out + 1) / 2, batch);

@@ -104,3 +104,4 @@ def test_glwe_tensor_apply_and_relinearize(fl, rank, n):
         for bi in range(batch):
             o.glwe_tensor_relinearize(want2[bi], res_k2, tensor[bi], t_k, po, key_k, dsize)
         assert np.array_equal(g.vec_znx_to_numpy(rg), want2), (key_k, res_k2, dsize)
+

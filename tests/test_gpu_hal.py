@@ -502,3 +502,50 @@ def test_coefficient_domain_helpers():
             g.vec_znx_normalize_assign(13, xg, c)
             O.vec_znx_normalize_assign(13, want, c)
         assert np.array_equal(g.vec_znx_to_numpy(xg), want), size
+
+
+def test_vmp_batch_tiled_large_key():
+    """Matrices beyond 48 MB take the batch-tiled vmp kernel (one matrix read per four ciphertexts).  batch = 6 leaves a partial tile;
+    the result must equal the per-item kernel bit for bit, and item 0 must match the oracle after idft + normalize."""
+    import os
+    n, rows, cols_out, size, batch, k = 16384, 13, 2, 8, 6, 30
+    g, o = pb.Module(n, pb.NTT120), O.OracleModule(n, pb.NTT120)
+    rng = np.random.default_rng(29)
+    mat = fill_uniform(rng, (rows, 1, size, cols_out, n), k)
+    pmg, pmo = g.vmp_pmat_alloc(rows, 1, cols_out, size), o.vmp_pmat_alloc(rows, 1, cols_out, size)
+    g.vmp_prepare(pmg, g.mat_znx_from_numpy(mat))
+    a = fill_uniform(rng, (batch, rows, 1, n), k)
+    a_g = g.vec_znx_from_numpy(a)
+    adg = g.vec_znx_dft_alloc(1, rows, batch)
+    g.vec_znx_dft_apply(1, 0, adg, 0, a_g, 0)
+    outs = []
+    for no_bt in (False, True):
+        if no_bt:
+            os.environ["PGB_VMP_NO_BT"] = "1"
+        try:
+            rg = g.vec_znx_dft_alloc(cols_out, size, batch)
+            rg.buf.upload(rng.integers(0, 255, rg.buf.nbytes, dtype=np.uint8))
+            g.vmp_apply_dft_to_dft(rg, adg, pmg, 0)
+            g.sync()
+            outs.append(rg.buf.download(np.uint32, (rg.buf.nbytes // 4,)).copy())
+        finally:
+            os.environ.pop("PGB_VMP_NO_BT", None)
+    assert np.array_equal(outs[0], outs[1])
+    o.vmp_prepare(pmo, mat)
+    ado, ro = o.vec_znx_dft_alloc(1, rows), o.vec_znx_dft_alloc(cols_out, size)
+    o.vec_znx_dft_apply(1, 0, ado, 0, a[0], 0)
+    o.vmp_apply_dft_to_dft(ro, ado, pmo, 0)
+    big_o = o.vec_znx_idft_apply_consume(ro)
+    r0 = g.vec_znx_dft_alloc(cols_out, size)
+    g.vmp_apply_dft_to_dft(r0, _first_item(g, adg), pmg, 0)
+    big_g = g.vec_znx_idft_apply_consume(r0)
+    out_g, out_o = g.vec_znx_alloc(cols_out, size), o.vec_znx_alloc(cols_out, size)
+    for c in range(cols_out):
+        g.vec_znx_big_normalize(out_g, k, 0, c, big_g, k, c)
+        o.vec_znx_big_normalize(out_o, k, 0, c, big_o, k, c)
+    assert np.array_equal(g.vec_znx_to_numpy(out_g), out_o)
+
+
+def _first_item(g, v):
+    """View of batch item 0 of a batched device container."""
+    return type(v)(v.buf, v.n, v.cols, v.size, v.offset, 1, v.batch_stride)
