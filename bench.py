@@ -499,6 +499,8 @@ def aux_measurements(pb, torch, local, peak):
 
     # batched DFT sweep (BASELINE config 1): forward then inverse over VecZnx(cols=2, size) at log_n 10..16, >= 256 MB of limbs
     sweep = {}
+    pp = os.path.join(ROOT, "profiles", "r1_pipe_peaks.json")
+    bf_peak = json.load(open(pp))["ct_butterfly(harvey,shoup)"]["chip_per_s"] if os.path.exists(pp) else None
     for fl, nm, k in ((pb.NTT120, "ntt120", 18), (pb.FFT64, "fft64", 18)):
         for log_n, size in ((10, 2), (11, 4), (12, 8), (13, 16), (14, 32), (15, 8), (16, 8)):
             n = 1 << log_n
@@ -522,9 +524,13 @@ def aux_measurements(pb, torch, local, peak):
             t_f = _time_ms(torch, stream, fwd, 5)
             t_i = _time_ms(torch, stream, inv, 5)
             pbytes = m.prep_bytes
-            sweep[f"{nm}_log_n={log_n}_size={size}"] = {
-                "limbs": limbs, "fwd_ms": t_f, "inv_ms": t_i, "fwd_limbs_per_s": limbs / (t_f * 1e-3), "inv_limbs_per_s": limbs / (t_i * 1e-3),
-                "fwd_gbs": limbs * n * (8 + pbytes) / (t_f * 1e-3) / 1e9, "inv_gbs": limbs * n * (pbytes + m.big_bytes) / (t_i * 1e-3) / 1e9}
+            e = {"limbs": limbs, "fwd_ms": t_f, "inv_ms": t_i, "fwd_limbs_per_s": limbs / (t_f * 1e-3), "inv_limbs_per_s": limbs / (t_i * 1e-3),
+                 "fwd_gbs": limbs * n * (8 + pbytes) / (t_f * 1e-3) / 1e9, "inv_gbs": limbs * n * (pbytes + m.big_bytes) / (t_i * 1e-3) / 1e9}
+            if fl == pb.NTT120 and bf_peak:  # the transforms are integer-issue bound: fraction of the measured in-register butterfly rate
+                bf = 4 * (n // 2) * log_n
+                e["fwd_butterfly_frac"] = limbs * bf / (t_f * 1e-3) / bf_peak
+                e["inv_butterfly_frac"] = limbs * bf / (t_i * 1e-3) / bf_peak
+            sweep[f"{nm}_log_n={log_n}_size={size}"] = e
             del m, a, d, big
     aux["dft_sweep"] = sweep
 
