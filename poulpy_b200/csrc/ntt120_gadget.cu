@@ -443,6 +443,8 @@ template <int L> __device__ __forceinline__ void gadget_body(const GadgetArgs &p
             const size_t res_ls = (size_t)cols_out * n, in_ls = (size_t)p.in_cols * n;
             const bool four_words = S * Kb > 96;
             const unsigned long long kmask = (1ull << Kb) - 1, khalf = 1ull << (Kb - 1);
+            long long *res_ct = reinterpret_cast<long long *>(p.res + (size_t)ct * p.res_bs) + K * (n / 4) + t;
+            const long long *in_kt = in + K * (n / 4) + t;
             for (int o = 0; o < cols_out; o++) {
                 const bool with_small = o == 0 && p.small_size > 0;
 #pragma unroll 1
@@ -454,7 +456,7 @@ template <int L> __device__ __forceinline__ void gadget_body(const GadgetArgs &p
                     if (with_small) {
 #pragma unroll
                         for (int s4 = 0; s4 < 4; s4++)
-                            if (S - 1 - s4 >= 0 && S - 1 - s4 < p.small_size) sm4[s4] = __ldg(in + (size_t)(S - 1 - s4) * in_ls + idx);
+                            if (S - 1 - s4 >= 0 && S - 1 - s4 < p.small_size) sm4[s4] = __ldg(in_kt + (size_t)(S - 1 - s4) * in_ls + i * T);
                     }
                     const uint32_t off = (uint32_t)(o * n + (swz<L>(K * (n / 4) + i * T) ^ st)) * 4u;
                     const uint32_t t0 = ld_cluster(rb[0] + off), t1 = ld_cluster(rb[1] + off), t2 = ld_cluster(rb[2] + off), t3 = ld_cluster(rb[3] + off);
@@ -480,7 +482,7 @@ template <int L> __device__ __forceinline__ void gadget_body(const GadgetArgs &p
                     // balanced digits of v = unsigned K-bit fields of u = v + sum_j 2^(K-1) 2^(jK), each minus 2^(K-1)
                     lo64 += p.half_lo;
                     hi64 += p.half_hi + (lo64 < p.half_lo ? 1ull : 0ull);
-                    long long *out_p = reinterpret_cast<long long *>(p.res + (size_t)ct * p.res_bs) + (size_t)(S - 1) * res_ls + (size_t)o * n + idx;
+                    long long *out_p = res_ct + (size_t)(S - 1) * res_ls + (size_t)o * n + i * T;
                     long long carry = 0;
                     // one digit step: limb j = S - 1 - s; the value is shifted right by K afterwards (K in [2, 62])
 #define DIGIT_STEP(SMALL_EXPR)                                                                                             \
@@ -506,7 +508,7 @@ template <int L> __device__ __forceinline__ void gadget_body(const GadgetArgs &p
                     }
                     for (int j = S - 5; j >= 0; j--) DIGIT_STEP(j < p.small_size ? __ldg(in + (size_t)j * in_ls + idx) : 0ll)
 #undef DIGIT_STEP
-                    long long *zp = reinterpret_cast<long long *>(p.res + (size_t)ct * p.res_bs) + (size_t)o * n + idx;
+                    long long *zp = res_ct + (size_t)o * n + i * T;
                     for (int j = a_start; j < p.res_size; j++) zp[(size_t)j * res_ls] = 0;
                 }
             }
