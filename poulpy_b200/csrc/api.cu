@@ -174,7 +174,10 @@ extern "C" void *pgb_alloc_bytes(size_t len) {
 extern "C" void *pgb_alloc_device_bytes(size_t len) {
     void *p = nullptr;
     if (cudaMalloc(&p, len ? len : 1) != cudaSuccess) return nullptr;
+    // the memset runs on the legacy stream, the modules' streams are non-blocking: without the synchronisation a kernel launched right
+    // after the allocation could be overtaken by the zero fill
     cudaMemset(p, 0, len);
+    cudaStreamSynchronize(0);
     return p;
 }
 extern "C" void *pgb_alloc_pinned_bytes(size_t len) {
@@ -184,16 +187,24 @@ extern "C" void *pgb_alloc_pinned_bytes(size_t len) {
 }
 extern "C" void pgb_free(void *p) { cudaFree(p); }
 extern "C" void pgb_free_pinned(void *p) { cudaFreeHost(p); }
+// Setup / test helpers, not on the hot path.  They run on the legacy stream while the modules' streams are non-blocking, and a pageable
+// host-to-device cudaMemcpy may return before its last DMA chunk has landed: a full device synchronisation on both sides makes them
+// ordered against every module stream.
 extern "C" int pgb_memcpy_h2d(void *dst, const void *src, size_t len) {
+    PGB_CHECK_CUDA(cudaDeviceSynchronize());
     PGB_CHECK_CUDA(cudaMemcpy(dst, src, len, cudaMemcpyHostToDevice));
+    PGB_CHECK_CUDA(cudaDeviceSynchronize());
     return PGB_OK;
 }
 extern "C" int pgb_memcpy_d2h(void *dst, const void *src, size_t len) {
+    PGB_CHECK_CUDA(cudaDeviceSynchronize());
     PGB_CHECK_CUDA(cudaMemcpy(dst, src, len, cudaMemcpyDeviceToHost));
     return PGB_OK;
 }
 extern "C" int pgb_memcpy_d2d(void *dst, const void *src, size_t len) {
+    PGB_CHECK_CUDA(cudaDeviceSynchronize());
     PGB_CHECK_CUDA(cudaMemcpy(dst, src, len, cudaMemcpyDeviceToDevice));
+    PGB_CHECK_CUDA(cudaDeviceSynchronize());
     return PGB_OK;
 }
 extern "C" int pgb_memset(void *dst, int byte, size_t len) {

@@ -297,3 +297,38 @@ def test_glwe_automorphism(fl, n):
         wy = np.zeros((4, 2, n), dtype=np.int64)
         O.vec_znx_automorphism(p, wy, 1, a[0], 0)
         assert np.array_equal(g.vec_znx_to_numpy(y)[:, 1], wy[:, 1]), p
+
+
+def test_gadget_kernel_random_shapes():
+    """Randomised shape sweep through the single-kernel gadget product (n = 1024): ranks 1..3, 1..4 input limbs, 1..5 key limbs,
+    output sizes below / equal / above the key size, base2k from 4 to 62 (S * K <= 128 selects the kernel, the rest falls back to the
+    limb-wise kernels), batch 1..9 -- all bit for bit against the oracle."""
+    n = 1024
+    g, o = pb.Module(n, pb.NTT120), O.OracleModule(n, pb.NTT120)
+    rng = np.random.default_rng(4242)
+    for trial in range(28):
+        k = int(rng.choice([4, 8, 13, 18, 25, 31, 40, 52, 62]))
+        rank_in, rank_out = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        a_size, key_size, res_size = int(rng.integers(1, 5)), int(rng.integers(1, 6)), int(rng.integers(1, 7))
+        batch = int(rng.integers(1, 10))
+        ext = trial % 3 == 2
+        digits = min(k, 50)  # keep |a|, |key| small enough that most ciphertexts stay on the collapsed path
+        if ext:
+            cols = rank_in + 1
+            pg, po = _key(g, o, rng, a_size, cols, cols, key_size, digits)
+            a = fill_uniform(rng, (batch, a_size, cols, n), digits)
+            want = fill_uniform(rng, (batch, res_size, cols, n), 8)
+            res_g = g.vec_znx_from_numpy(want)
+            g.glwe_external_product(res_g, k, g.vec_znx_from_numpy(a), k, pg, k)
+            g.sync()
+            o.glwe_external_product_batch(want, k, a, k, po, k)
+        else:
+            pg, po = _key(g, o, rng, a_size, rank_in, rank_out + 1, key_size, digits)
+            a = fill_uniform(rng, (batch, a_size, rank_in + 1, n), digits)
+            want = fill_uniform(rng, (batch, res_size, rank_out + 1, n), 8)
+            res_g = g.vec_znx_from_numpy(want)
+            g.glwe_keyswitch(res_g, k, g.vec_znx_from_numpy(a), k, pg, k)
+            g.sync()
+            o.glwe_keyswitch_batch(want, k, a, k, po, k)
+        got = g.vec_znx_to_numpy(res_g).reshape(want.shape)  # batch 1 comes back without the batch axis
+        assert np.array_equal(got, want), (trial, ext, k, rank_in, rank_out, a_size, key_size, res_size, batch)
