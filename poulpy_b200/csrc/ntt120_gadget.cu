@@ -442,21 +442,26 @@ template <int L> __device__ __forceinline__ void gadget_body(const GadgetArgs &p
             const int a_start = p.res_size < S ? p.res_size : S; // digits j >= a_start are discarded (carry only)
             const size_t res_ls = (size_t)cols_out * n, in_ls = (size_t)p.in_cols * n;
             const bool four_words = S * Kb > 96;
+            const bool narrow = Kb < 32; // digit fields inside one 32-bit word: funnel shifts over four words
             const unsigned long long kmask = (1ull << Kb) - 1, khalf = 1ull << (Kb - 1);
+            const uint32_t kmask32 = (uint32_t)kmask, khalf32 = (uint32_t)khalf;
+            const uint32_t hw0 = (uint32_t)p.half_lo, hw1 = (uint32_t)(p.half_lo >> 32), hw2 = (uint32_t)p.half_hi, hw3 = (uint32_t)(p.half_hi >> 32);
             long long *res_ct = reinterpret_cast<long long *>(p.res + (size_t)ct * p.res_bs) + K * (n / 4) + t;
-            const long long *in_kt = in + K * (n / 4) + t;
+            const long long *in_kt = in + K * (n / 4) + t + (size_t)(S - 1) * in_ls; // body limb S - 1 (column 0)
             for (int o = 0; o < cols_out; o++) {
                 const bool with_small = o == 0 && p.small_size > 0;
 #pragma unroll 1
                 for (int i = 0; i < 4; i++) {
-                    const int idx = K * (n / 4) + i * T + t;
-                    // body limbs that join column 0 (vec_znx_big_add_small_assign), most significant processed last: sm4[s] belongs
-                    // to digit step s (limb S-1-s); issued first so that their latency hides behind the CRT arithmetic
+                    // body limbs that join column 0 (vec_znx_big_add_small_assign), least significant digit first: sm4[s] belongs to
+                    // digit step s (limb S-1-s); issued first so that their latency hides behind the CRT arithmetic
                     long long sm4[4] = {0, 0, 0, 0};
+                    const long long *sp = in_kt + i * T;
                     if (with_small) {
 #pragma unroll
-                        for (int s4 = 0; s4 < 4; s4++)
-                            if (S - 1 - s4 >= 0 && S - 1 - s4 < p.small_size) sm4[s4] = __ldg(in_kt + (size_t)(S - 1 - s4) * in_ls + i * T);
+                        for (int s4 = 0; s4 < 4; s4++) {
+                            if (S - 1 - s4 >= 0 && S - 1 - s4 < p.small_size) sm4[s4] = __ldg(sp);
+                            sp -= in_ls;
+                        }
                     }
                     const uint32_t off = (uint32_t)(o * n + (swz<L>(K * (n / 4) + i * T) ^ st)) * 4u;
                     const uint32_t t0 = ld_cluster(rb[0] + off), t1 = ld_cluster(rb[1] + off), t2 = ld_cluster(rb[2] + off), t3 = ld_cluster(rb[3] + off);
@@ -472,42 +477,74 @@ template <int L> __device__ __forceinline__ void gadget_body(const GadgetArgs &p
                                                   (unsigned long long)t2 * p.m_w[2][1] + (unsigned long long)t3 * p.m_w[3][1] + (unsigned long long)e * p.nq_w[1];
                     const unsigned long long a2 = (a1 >> 32) + (unsigned long long)t0 * p.m_w[0][2] + (unsigned long long)t1 * p.m_w[1][2] +
                                                   (unsigned long long)t2 * p.m_w[2][2] + (unsigned long long)t3 * p.m_w[3][2] + (unsigned long long)e * p.nq_w[2];
-                    unsigned long long lo64 = (a0 & 0xffffffffull) | (a1 << 32), hi64 = a2 & 0xffffffffull;
+                    uint32_t w0 = (uint32_t)a0, w1 = (uint32_t)a1, w2 = (uint32_t)a2, w3 = 0;
                     if (four_words) {
                         const unsigned long long a3 = (a2 >> 32) + (unsigned long long)t0 * p.m_w[0][3] + (unsigned long long)t1 * p.m_w[1][3] +
                                                       (unsigned long long)t2 * p.m_w[2][3] + (unsigned long long)t3 * p.m_w[3][3] +
                                                       (unsigned long long)e * p.nq_w[3];
-                        hi64 |= a3 << 32;
+                        w3 = (uint32_t)a3;
                     }
-                    // balanced digits of v = unsigned K-bit fields of u = v + sum_j 2^(K-1) 2^(jK), each minus 2^(K-1)
-                    lo64 += p.half_lo;
-                    hi64 += p.half_hi + (lo64 < p.half_lo ? 1ull : 0ull);
+                    // Balanced digits of W = v + sum_j body_j 2^((S-1-j)K): the unsigned K-bit fields of u = W + sum_j 2^(K-1) 2^(jK), each
+                    // minus 2^(K-1).  u is kept modulo 2^128 and shifted right by K per digit; body limb j joins at bit 0 just before its
+                    // own digit is read (same as adding it at bit (S-1-j)K up front; the carry out of the top digit is dropped as in
+                    // vec_znx_big_normalize).
+                    asm("add.cc.u32 %0, %0, %4; addc.cc.u32 %1, %1, %5; addc.cc.u32 %2, %2, %6; addc.u32 %3, %3, %7;"
+                        : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(w3) : "r"(hw0), "r"(hw1), "r"(hw2), "r"(hw3));
                     long long *out_p = res_ct + (size_t)(S - 1) * res_ls + (size_t)o * n + i * T;
-                    long long carry = 0;
-                    // one digit step: limb j = S - 1 - s; the value is shifted right by K afterwards (K in [2, 62])
-#define DIGIT_STEP(SMALL_EXPR)                                                                                             \
+#define ADD_BODY(SV)                                                                                                       \
     {                                                                                                                      \
-        const long long d = (long long)(lo64 & kmask) - (long long)khalf;                                                  \
-        long long outv = d;                                                                                                \
-        if (with_small) {                                                                                                  \
-            /* small = sh 2^K + sl; r = sl + d + carry cannot overflow; carry' = sh + ((r - out) >> K) */                  \
-            const long long sv = (SMALL_EXPR);                                                                             \
-            const long long r = (long long)((unsigned long long)sv & kmask) + d + carry;                                   \
-            outv = (long long)((unsigned long long)r << (64 - Kb)) >> (64 - Kb);                                           \
-            carry = (sv >> Kb) + ((r - outv) >> Kb);                                                                       \
-        }                                                                                                                  \
-        if (j < a_start) *out_p = outv;                                                                                    \
+        const long long sv_ = (SV);                                                                                        \
+        const uint32_t sx_ = (uint32_t)(sv_ >> 63);                                                                        \
+        asm("add.cc.u32 %0, %0, %4; addc.cc.u32 %1, %1, %5; addc.cc.u32 %2, %2, %6; addc.u32 %3, %3, %6;"                  \
+            : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(w3) : "r"((uint32_t)sv_), "r"((uint32_t)((unsigned long long)sv_ >> 32)), "r"(sx_)); \
+    }
+                    if (narrow) {
+#define DIGIT_STEP32                                                                                                       \
+    {                                                                                                                      \
+        if (j < a_start) *out_p = (long long)((int)(w0 & kmask32) - (int)khalf32);                                         \
         out_p -= res_ls;                                                                                                   \
-        lo64 = (lo64 >> Kb) | (hi64 << (64 - Kb));                                                                         \
-        hi64 >>= Kb;                                                                                                       \
+        w0 = __funnelshift_r(w0, w1, Kb); w1 = __funnelshift_r(w1, w2, Kb); w2 = __funnelshift_r(w2, w3, Kb); w3 >>= Kb;   \
     }
 #pragma unroll
-                    for (int s4 = 0; s4 < 4; s4++) {
-                        const int j = S - 1 - s4;
-                        if (j >= 0) DIGIT_STEP(sm4[s4])
+                        for (int s4 = 0; s4 < 4; s4++) {
+                            const int j = S - 1 - s4;
+                            if (j >= 0) {
+                                if (with_small && j < p.small_size) ADD_BODY(sm4[s4])
+                                DIGIT_STEP32
+                            }
+                        }
+                        for (int j = S - 5; j >= 0; j--) {
+                            if (with_small && j < p.small_size) ADD_BODY(__ldg(sp))
+                            sp -= in_ls;
+                            DIGIT_STEP32
+                        }
+#undef DIGIT_STEP32
+                    } else {
+#define DIGIT_STEP64                                                                                                       \
+    {                                                                                                                      \
+        unsigned long long lo_ = ((unsigned long long)w1 << 32) | w0, hi_ = ((unsigned long long)w3 << 32) | w2;           \
+        if (j < a_start) *out_p = (long long)(lo_ & kmask) - (long long)khalf;                                             \
+        out_p -= res_ls;                                                                                                   \
+        lo_ = (lo_ >> Kb) | (hi_ << (64 - Kb));                                                                            \
+        hi_ >>= Kb;                                                                                                        \
+        w0 = (uint32_t)lo_; w1 = (uint32_t)(lo_ >> 32); w2 = (uint32_t)hi_; w3 = (uint32_t)(hi_ >> 32);                    \
+    }
+#pragma unroll
+                        for (int s4 = 0; s4 < 4; s4++) {
+                            const int j = S - 1 - s4;
+                            if (j >= 0) {
+                                if (with_small && j < p.small_size) ADD_BODY(sm4[s4])
+                                DIGIT_STEP64
+                            }
+                        }
+                        for (int j = S - 5; j >= 0; j--) {
+                            if (with_small && j < p.small_size) ADD_BODY(__ldg(sp))
+                            sp -= in_ls;
+                            DIGIT_STEP64
+                        }
+#undef DIGIT_STEP64
                     }
-                    for (int j = S - 5; j >= 0; j--) DIGIT_STEP(j < p.small_size ? __ldg(in + (size_t)j * in_ls + idx) : 0ll)
-#undef DIGIT_STEP
+#undef ADD_BODY
                     long long *zp = res_ct + (size_t)o * n + i * T;
                     for (int j = a_start; j < p.res_size; j++) zp[(size_t)j * res_ls] = 0;
                 }
