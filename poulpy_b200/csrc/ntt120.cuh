@@ -24,8 +24,21 @@ static constexpr uint32_t OMEGA[4] = {1070907127u, 315046632u, 309185662u, 84646
 static constexpr uint32_t CRT_CST[4] = {43599465u, 292938863u, 594011630u, 140177212u};
 
 // x * w mod q in [0, 2q) for any x < 2^32, w < q, wp = floor(w * 2^32 / q)   (Shoup)
+// -DPGB_SHOUP_WIDE takes the high word from a full 32x32->64 product (IMAD.WIDE, full IMAD rate in isolation) instead of __umulhi
+// (IMAD.HI, half rate: profiles/r1_pipe_peaks.json); ptxas keeps the wide form when it is spelled as mul.wide + unpack.  Measured on the
+// key-switch kernel: no gain (1.564 vs 1.541 ms per 4096), so the default stays __umulhi.
+__device__ __forceinline__ uint32_t umulhi_wide(uint32_t a, uint32_t b) {
+#ifndef PGB_SHOUP_WIDE
+    return __umulhi(a, b);
+#else
+    uint32_t lo, hi;
+    asm("{ .reg .u64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t; }" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+    (void)lo;
+    return hi;
+#endif
+}
 __device__ __forceinline__ uint32_t mul_shoup(uint32_t x, uint32_t w, uint32_t wp, uint32_t q) {
-    uint32_t h = __umulhi(x, wp);
+    uint32_t h = umulhi_wide(x, wp);
     return x * w - h * q;
 }
 __device__ __forceinline__ uint32_t csub(uint32_t x, uint32_t m) { return min(x, x - m); } // x in [0, 2m) -> [0, m)
