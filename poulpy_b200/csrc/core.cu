@@ -118,6 +118,13 @@ extern "C" int pgb_glwe_keyswitch_batched(pgb_module *m, pgb_vec_znx *res, uint6
     const uint64_t a_dft_bs = n * rank_in * ain.size * pb;
     pgb_vec_znx_dft a_dft = mk(ar.take(B * a_dft_bs), n, rank_in, ain.size);
     pgb_batch btd = {B, a_dft_bs, ain_bs, 0};
+    if (dsize == 1 && res_base2k == key_base2k && m->flavour == PGB_FFT64 && !getenv("PGB_NO_FUSION")) {
+        const uint64_t R = umin64(key->rows * key->cols_in, rank_in * ain.size);
+        if (fft64_gadget_supported(m, (int)R, (int)cols_out, (int)key->size, (int)key_base2k, (int)B)) // one kernel per batch (fft64_gadget.cu)
+            return fft64_gadget_fused(m, (const char *)ain.data, ain_bs, (int)ain.cols, (int)rank_in, 1, (int)R, (const char *)key->data,
+                                      (int)(cols_out * key->size), (int)cols_out, (int)umin64(ain.size, key->size), (char *)res->data,
+                                      bt->stride_res, (int)res->size, (int)key_base2k, (int)B);
+    }
     if (dsize == 1 && res_base2k == key_base2k && ntt120_fused_supported(m) && !getenv("PGB_NO_FUSION")) {
         const uint64_t R = umin64(key->rows * key->cols_in, rank_in * ain.size);
         const int small_size = (int)umin64(ain.size, key->size);
@@ -222,6 +229,13 @@ extern "C" int pgb_glwe_external_product_batched(pgb_module *m, pgb_vec_znx *res
     pgb_vec_znx_dft a_dft = mk(ar.take(B * a_dft_bs), n, cols, a_dft_max);
     if (dsize == 1) {
         pgb_batch btd = {B, a_dft_bs, ain_bs, 0};
+        if (res_base2k == ggsw_base2k && m->flavour == PGB_FFT64 && !getenv("PGB_NO_FUSION")) {
+            const uint64_t R = umin64(ggsw->rows * ggsw->cols_in, cols * a_size);
+            if (fft64_gadget_supported(m, (int)R, (int)cols, (int)ggsw->size, (int)ggsw_base2k, (int)B)) // fft64_gadget.cu
+                return fft64_gadget_fused(m, (const char *)ain.data, ain_bs, (int)ain.cols, (int)cols, 0, (int)R, (const char *)ggsw->data,
+                                          (int)(cols * ggsw->size), (int)cols, 0, (char *)res->data, bt->stride_res, (int)res->size,
+                                          (int)ggsw_base2k, (int)B);
+        }
         if (res_base2k == ggsw_base2k && ntt120_fused_supported(m) && !getenv("PGB_NO_FUSION")) {
             const uint64_t R = umin64(ggsw->rows * ggsw->cols_in, cols * a_size);
             if (ntt120_gadget_supported(m, (int)R, (int)cols, (int)ggsw->size, (int)ggsw_base2k, (int)B)) {

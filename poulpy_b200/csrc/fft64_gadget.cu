@@ -1,0 +1,333 @@
+// fft64_gadget.cu -- the whole gadget product (GLWE key-switch / GGSW x GLWE external product, dsize = 1, same base2k) of the FFT64
+// flavour as ONE persistent kernel: i64 GLWE in -> i64 GLWE out, nothing else touches HBM (the prepared key streams from L2).
+//
+// Restates, per ciphertext, the HAL sequence of poulpy-core/src/keyswitching/glwe.rs:207-239,106-108 and
+// external_product/glwe.rs:197-271,138-140 on the FFT64 backend:
+//     vec_znx_dft_apply (R limbs; reference/fft64/vec_znx_dft.rs:160-200)
+//  -> vmp_apply_dft_to_dft (fft64/vmp.rs:144-264, rows accumulated in row order)
+//  -> vec_znx_idft_apply_consume (vec_znx_dft.rs:264-288: x 1/m, round half away from zero)
+//  -> vec_znx_big_add_small_assign (fft64/vec_znx_big.rs, wrapping i64)
+//  -> vec_znx_big_normalize, same base2k, offset 0 (reference/vec_znx/normalize.rs:52-148 with the i64 steps of
+//     reference/znx/normalization.rs:24-323)
+// Unlike the NTT120 kernel there is no collapsed key: f64 cannot hold the 2^((S-1)K) spread, so every output limb gets its own
+// inverse transform and the rounded limbs are chained by the carry exactly like the unfused sequence.
+//
+// Mapping: one CTA owns one ciphertext at a time (persistent loop).  A transform of m = n/2 complex points is run by a "slot" of
+// T = m/8 threads (radix-8 passes through padded shared memory, FMA butterflies, as in fft64.cu); the CTA holds NS = cols_out * LPR
+// slots.  The R forward transforms stay resident in R shared-memory planes.  In the last forward pass and the first inverse pass a
+// thread owns the same eight frequencies, so the key products need no barrier: thread t of a slot multiplies rows x key for
+// frequencies 8t..8t+7 in registers and walks straight into the inverse passes.  Slot s serves output column s % cols_out; the LPR
+// slots of a column take LPR consecutive limbs per round and hand their rounded i64 coefficients to the column's carry chain
+// (registers when LPR == 1, the slot's own plane + a named barrier otherwise).
+#include <stdlib.h>
+
+#include "internal.h"
+#include "fft64.cuh"
+
+namespace {
+
+struct FGadgetArgs {
+    const char *in;  unsigned long long in_bs;   // GLWE inputs (i64), limb (j, col) at ((j * in_cols + col) * n) words
+    char *res;       unsigned long long res_bs;  // GLWE outputs (i64), limb (j, col) at ((j * cols_out + col) * n) words
+    const double *pmat;                          // prepared matrix [row][C][re(m) | im(m)]
+    int in_cols, row_cols, row_col0, R, C, cols_out;
+    int small_size;                              // limbs of input column 0 added to output column 0 (key-switch), 0 = none
+    int K, S, res_size, batch;
+    double inv_m;
+};
+
+template <int T> __device__ __forceinline__ void slot_sync(int slot) {
+    if (T <= 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(T) : "memory");
+}
+__device__ __forceinline__ void group_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+template <int L, int L0, bool TWS> struct GFwd {
+    static __device__ __forceinline__ void run(double2 *buf, const double2 *tw, int t, int slot) {
+        constexpr int SL = L - L0 - 3;
+        const int a = t >> SL, b = t & ((1 << SL) - 1), base = (a << (SL + 3)) | b;
+        double2 x[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) x[j] = buf[FPAD(base + (j << SL))];
+        fct_radix8<3, TWS>(x, tw, (1u << L0) | (uint32_t)a);
+#pragma unroll
+        for (int j = 0; j < 8; j++) buf[FPAD(base + (j << SL))] = x[j];
+        if (SL > 0) slot_sync<FGeo<L>::T>(slot); // after the last pass every thread only re-reads its own eight values
+        GFwd<L, (L0 + 3 < L) ? L0 + 3 : L, TWS>::run(buf, tw, t, slot);
+    }
+};
+template <int L, bool TWS> struct GFwd<L, L, TWS> {
+    static __device__ __forceinline__ void run(double2 *, const double2 *, int, int) {}
+};
+template <int L, int L0, bool TWS> struct GInv {
+    static __device__ __forceinline__ void run(double2 *buf, const double2 *tw, int t, int slot) {
+        typedef FGeo<L> G;
+        constexpr int SL = L - L0 - 3;
+        const int a = t >> SL, b = t & ((1 << SL) - 1), base = (a << (SL + 3)) | b;
+        double2 x[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) x[j] = buf[FPAD(base + (j << SL))];
+        fgs_radix8<3, TWS>(x, tw, (1u << L0) | (uint32_t)a);
+#pragma unroll
+        for (int j = 0; j < 8; j++) buf[FPAD(base + (j << SL))] = x[j];
+        slot_sync<G::T>(slot);
+        GInv<L, (L0 - 3 >= G::R0) ? L0 - 3 : -1, TWS>::run(buf, tw, t, slot);
+    }
+};
+template <int L, bool TWS> struct GInv<L, -1, TWS> {
+    static __device__ __forceinline__ void run(double2 *, const double2 *, int, int) {}
+};
+
+// one step of the same-base2k carry chain on i64 (znx_normalize_{first,middle}_step with lsh = 0, normalization.rs:24-323): the digit
+// of x and the digit of (digit + carry_in) are taken separately, exactly like the reference, so wrap-around cases agree too
+__device__ __forceinline__ long long norm_step(long long x, long long &c, int K) {
+    const long long d = (long long)((unsigned long long)x << (64 - K)) >> (64 - K);
+    const long long co = (long long)((unsigned long long)x - (unsigned long long)d) >> K;
+    const long long s = (long long)((unsigned long long)d + (unsigned long long)c);
+    const long long out = (long long)((unsigned long long)s << (64 - K)) >> (64 - K);
+    c = (long long)((unsigned long long)co + (unsigned long long)((long long)((unsigned long long)s - (unsigned long long)out) >> K));
+    return out;
+}
+
+template <int LM, int LPR, bool TWS> __global__ void __launch_bounds__(512, 1)
+fft64_gadget_kernel(const __grid_constant__ FGadgetArgs p, const double2 *__restrict__ twf_g, const double2 *__restrict__ twi_g) {
+    typedef FGeo<LM> G;
+    constexpr int M = 1 << LM, N = 2 * M, T = G::T, PL = G::PLANE;
+    constexpr int CPT = 16 / LPR; // coefficients of a column per thread of its slot group
+    static_assert(LM > G::R0 && T >= 32 && (16 % LPR) == 0, "geometry");
+    extern __shared__ __align__(16) double2 gsm[];
+    const int cols_out = p.cols_out, NS = cols_out * LPR, R = p.R, S = p.S, K = p.K;
+    const int slot = threadIdx.x / T, t = threadIdx.x % T;
+    const int c = slot % cols_out, g = slot / cols_out; // output column and position inside the column's slot group
+    double2 *planes = gsm;                               // R resident forward transforms
+    double2 *work = gsm + (size_t)(R + slot) * PL;       // this slot's inverse-transform plane
+    const double2 *twf = twf_g, *twi = twi_g;
+    if (TWS) {
+        double2 *tws = gsm + (size_t)(R + NS) * PL;
+        for (int i = threadIdx.x; i < M; i += blockDim.x) {
+            tws[i] = twf_g[i];
+            tws[M + i] = twi_g[i];
+        }
+        twf = tws;
+        twi = tws + M;
+        __syncthreads();
+    }
+    const int a_start = p.res_size < S ? p.res_size : S; // limbs j >= a_start are carry-only
+    const size_t res_ls = (size_t)cols_out * N, in_ls = (size_t)p.in_cols * N;
+    const int nrounds = (S + LPR - 1) / LPR;
+    const int gt = g * T + t, GT = LPR * T;
+
+    for (int ct = blockIdx.x; ct < p.batch; ct += gridDim.x) {
+        const long long *in = reinterpret_cast<const long long *>(p.in + (size_t)ct * p.in_bs);
+        long long *res = reinterpret_cast<long long *>(p.res + (size_t)ct * p.res_bs);
+        // ---- forward transforms of the R input limbs ------------------------------------------------------------------------------
+        for (int r = slot; r < R; r += NS) {
+            const int limb = r / p.row_cols, col = r % p.row_cols + p.row_col0;
+            const long long *src = in + ((size_t)limb * p.in_cols + col) * N;
+            double2 *buf = planes + (size_t)r * PL;
+            double2 x[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) {
+                const int idx = t + jj * T;
+                x[jj] = make_double2((double)__ldg(src + idx), (double)__ldg(src + idx + M)); // reim_from_znx_i64 (conversion.rs:19-28)
+            }
+            fct_radix8<G::R0, TWS>(x, twf, 1u);
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) buf[FPAD(t + jj * T)] = x[jj];
+            slot_sync<T>(slot);
+            GFwd<LM, G::R0, TWS>::run(buf, twf, t, slot);
+        }
+        __syncthreads(); // the products read every plane
+        // ---- output limbs, least significant first: products -> inverse transform -> round -> carry chain ------------------------------
+        long long carry[CPT];
+#pragma unroll
+        for (int i = 0; i < CPT; i++) carry[i] = 0;
+        for (int k = 0; k < nrounds; k++) {
+            const int jl = k * LPR + g, j = S - 1 - jl;
+            const bool valid = jl < S;
+            double2 x[8];
+            if (valid) {
+                const int poly = j * cols_out + c;
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) x[jj] = make_double2(0.0, 0.0);
+                const double *kp = p.pmat + (size_t)poly * N + 8 * t;
+                for (int r = 0; r < R; r++) { // row order of reim4_add_mul (reim4/arithmetic_ref.rs:223-232), FMA-contracted
+                    const double2 *kr = reinterpret_cast<const double2 *>(kp + (size_t)r * p.C * N);
+                    const double2 *ki = reinterpret_cast<const double2 *>(kp + (size_t)r * p.C * N + M);
+                    double br[8], bi[8];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const double2 u = __ldg(kr + q), v = __ldg(ki + q);
+                        br[2 * q] = u.x; br[2 * q + 1] = u.y; bi[2 * q] = v.x; bi[2 * q + 1] = v.y;
+                    }
+                    const double2 *ap = planes + (size_t)r * PL;
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj++) {
+                        const double2 a = ap[FPAD(8 * t + jj)];
+                        x[jj].x = fma(a.x, br[jj], x[jj].x); x[jj].x = fma(-a.y, bi[jj], x[jj].x);
+                        x[jj].y = fma(a.x, bi[jj], x[jj].y); x[jj].y = fma(a.y, br[jj], x[jj].y);
+                    }
+                }
+                fgs_radix8<3, TWS>(x, twi, (1u << (LM - 3)) | (uint32_t)t);
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) work[FPAD(8 * t + jj)] = x[jj];
+                slot_sync<T>(slot);
+                GInv<LM, (LM - 6 >= G::R0) ? LM - 6 : -1, TWS>::run(work, twi, t, slot);
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) x[jj] = work[FPAD(t + jj * T)];
+                fgs_radix8<G::R0, TWS>(x, twi, 1u);
+            }
+            if (LPR == 1) {
+                // the thread that produced a coefficient also owns its carry: no shared-memory round trip
+                if (valid) {
+                    const bool with_small = c == 0 && j < p.small_size;
+                    const long long *sp = in + (size_t)j * in_ls + t; // input column 0 (the body)
+                    long long *op = res + (size_t)j * res_ls + (size_t)c * N + t;
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj++) {
+                        long long v0 = (long long)round(x[jj].x * p.inv_m), v1 = (long long)round(x[jj].y * p.inv_m); // conversion.rs:43-52
+                        if (with_small) {
+                            v0 = (long long)((unsigned long long)v0 + (unsigned long long)__ldg(sp + jj * T));
+                            v1 = (long long)((unsigned long long)v1 + (unsigned long long)__ldg(sp + jj * T + M));
+                        }
+                        const long long o0 = norm_step(v0, carry[2 * jj], K), o1 = norm_step(v1, carry[2 * jj + 1], K);
+                        if (j < a_start) {
+                            op[jj * T] = o0;
+                            op[jj * T + M] = o1;
+                        }
+                    }
+                }
+            } else {
+                if (valid) {
+                    slot_sync<T>(slot); // the last pass has read its inputs: the plane now takes the rounded i64 coefficients
+                    long long *big = reinterpret_cast<long long *>(work);
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj++) {
+                        big[t + jj * T] = (long long)round(x[jj].x * p.inv_m);
+                        big[t + jj * T + M] = (long long)round(x[jj].y * p.inv_m);
+                    }
+                }
+                group_sync(8 + c, GT);
+                // the LPR * T threads of the column's group split its n coefficients and walk this round's limbs in order
+                for (int l = 0; l < LPR; l++) {
+                    const int j2 = S - 1 - (k * LPR + l);
+                    if (j2 < 0) break;
+                    const long long *big = reinterpret_cast<const long long *>(gsm + (size_t)(R + c + l * cols_out) * PL);
+                    const bool with_small = c == 0 && j2 < p.small_size;
+                    const long long *sp = in + (size_t)j2 * in_ls + gt;
+                    long long *op = res + (size_t)j2 * res_ls + (size_t)c * N + gt;
+#pragma unroll
+                    for (int i = 0; i < CPT; i++) {
+                        long long v = big[gt + i * GT];
+                        if (with_small) v = (long long)((unsigned long long)v + (unsigned long long)__ldg(sp + i * GT));
+                        const long long o = norm_step(v, carry[i], K);
+                        if (j2 < a_start) op[i * GT] = o;
+                    }
+                }
+                group_sync(8 + c, GT); // the planes are rewritten by the next round
+            }
+        }
+        // limbs beyond the key size are zero (normalize.rs:60-66)
+        if (p.res_size > a_start) {
+            if (LPR == 1) {
+                for (int j = a_start; j < p.res_size; j++) {
+                    long long *op = res + (size_t)j * res_ls + (size_t)c * N + t;
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj++) {
+                        op[jj * T] = 0;
+                        op[jj * T + M] = 0;
+                    }
+                }
+            } else {
+                for (int j = a_start; j < p.res_size; j++) {
+                    long long *op = res + (size_t)j * res_ls + (size_t)c * N + gt;
+#pragma unroll
+                    for (int i = 0; i < CPT; i++) op[i * GT] = 0;
+                }
+            }
+        }
+        __syncthreads(); // the next ciphertext's forward transforms overwrite the planes
+    }
+}
+
+template <int LM, int LPR, bool TWS> int launch(pgb_module *m, const FGadgetArgs &p, size_t smem) {
+    static int sms = 0;
+    if (!sms) {
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(fft64_gadget_kernel<LM, LPR, TWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 << 10)));
+        PGB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device));
+    }
+    const int threads = p.cols_out * LPR * FGeo<LM>::T;
+    const int grid = p.batch < sms ? p.batch : sms;
+    { ProfScope _ps(m, PROF_GADGET);
+    fft64_gadget_kernel<LM, LPR, TWS><<<grid, threads, smem, m->stream>>>(p, m->fft_fwd, m->fft_inv);
+    }
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+template <int LM> int launch_lm(pgb_module *m, const FGadgetArgs &p, int lpr, bool tws, size_t smem) {
+    if (tws) {
+        switch (lpr) {
+        case 1: return launch<LM, 1, true>(m, p, smem);
+        case 2: return launch<LM, 2, true>(m, p, smem);
+        default: return launch<LM, 4, true>(m, p, smem);
+        }
+    }
+    switch (lpr) {
+    case 1: return launch<LM, 1, false>(m, p, smem);
+    case 2: return launch<LM, 2, false>(m, p, smem);
+    default: return launch<LM, 4, false>(m, p, smem);
+    }
+}
+
+// slots per column (limbs in flight per round), whether the twiddles fit in shared memory next to the planes, bytes of shared memory
+bool plan(const pgb_module *m, int R, int cols_out, int S, int *lpr_out, bool *tws_out, size_t *smem_out) {
+    const size_t M = m->n / 2, T = M / 8, PL = M + (M >> 3) + 2;
+    const size_t cap = (size_t)227 << 10, tw_bytes = 2 * M * sizeof(double2);
+    for (int lpr = 4; lpr >= 1; lpr >>= 1) {
+        if ((size_t)cols_out * lpr * T > 512 || (lpr > 1 && lpr > 2 * S)) continue;
+        if (cols_out * lpr > 7) continue; // named barriers 1..7 are the slots', 8..11 the column groups'
+        const size_t planes = (size_t)(R + cols_out * lpr) * PL * sizeof(double2);
+        if (planes > cap) continue;
+        *lpr_out = lpr;
+        *tws_out = planes + tw_bytes <= cap;
+        *smem_out = planes + (*tws_out ? tw_bytes : 0);
+        return true;
+    }
+    return false;
+}
+
+} // namespace
+
+bool fft64_gadget_supported(const pgb_module *m, int R, int cols_out, int S, int base2k, int batch) {
+    if (m->flavour != PGB_FFT64 || m->log_n < 9 || m->log_n > 12) return false;
+    if (getenv("PGB_NO_GADGET")) return false;
+    if (cols_out < 1 || cols_out > 4 || R < 1 || S < 1 || base2k < 1 || base2k > 63 || batch < 1) return false;
+    int lpr;
+    bool tws;
+    size_t smem;
+    return plan(m, R, cols_out, S, &lpr, &tws, &smem);
+}
+
+int fft64_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_cols, int row_cols, int row_col0, int R, const char *pmat, int C,
+                       int cols_out, int small_size, char *res, uint64_t res_bs, int res_size, int base2k, int batch) {
+    FGadgetArgs p;
+    memset(&p, 0, sizeof p);
+    p.in = in; p.in_bs = in_bs; p.res = res; p.res_bs = res_bs; p.pmat = (const double *)pmat;
+    p.in_cols = in_cols; p.row_cols = row_cols; p.row_col0 = row_col0; p.R = R; p.C = C; p.cols_out = cols_out; p.small_size = small_size;
+    p.K = base2k; p.S = C / cols_out; p.res_size = res_size; p.batch = batch;
+    p.inv_m = 1.0 / (double)(m->n / 2);
+    int lpr;
+    bool tws;
+    size_t smem;
+    if (!plan(m, R, cols_out, p.S, &lpr, &tws, &smem)) {
+        pgb_set_error("fft64 gadget kernel: shape does not fit");
+        return PGB_ERR_UNSUPPORTED;
+    }
+    switch (m->log_n) {
+    case 9: return launch_lm<8>(m, p, lpr, tws, smem);
+    case 10: return launch_lm<9>(m, p, lpr, tws, smem);
+    case 11: return launch_lm<10>(m, p, lpr, tws, smem);
+    case 12: return launch_lm<11>(m, p, lpr, tws, smem);
+    default: pgb_set_error("fft64 gadget kernel: unsupported n"); return PGB_ERR_UNSUPPORTED;
+    }
+}

@@ -25,6 +25,10 @@ int ntt120_key_max_bits(pgb_module *m, const char *pmat, int polys, char *coef_w
 bool ntt120_gadget_supported(const pgb_module *m, int R, int cols_out, int S, int base2k, int batch);
 int ntt120_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_cols, int row_cols, int row_col0, int R, const char *pmat,
                         int C, int cols_out, int small_size, char *res, uint64_t res_bs, int res_size, int base2k, int batch, int *ok_out);
+// fft64_gadget.cu
+bool fft64_gadget_supported(const pgb_module *m, int R, int cols_out, int S, int base2k, int batch);
+int fft64_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_cols, int row_cols, int row_col0, int R, const char *pmat, int C,
+                       int cols_out, int small_size, char *res, uint64_t res_bs, int res_size, int base2k, int batch);
 // ntt120_ops.cu
 int ntt120_vmp(pgb_module *m, const char *a, uint64_t a_bs, char *res, uint64_t res_bs, const char *pm, uint64_t pm_bs,
                uint32_t row_max, uint32_t C, uint32_t col0, uint32_t ncols_out, uint32_t batch);

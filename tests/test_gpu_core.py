@@ -332,3 +332,64 @@ def test_gadget_kernel_random_shapes():
             o.glwe_keyswitch_batch(want, k, a, k, po, k)
         got = g.vec_znx_to_numpy(res_g).reshape(want.shape)  # batch 1 comes back without the batch axis
         assert np.array_equal(got, want), (trial, ext, k, rank_in, rank_out, a_size, key_size, res_size, batch)
+
+
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096])
+def test_fft64_gadget_kernel(n):
+    """The single-kernel FFT64 gadget product (fft64_gadget.cu: forward FFTs, key products, inverse FFTs, rounding, add_small and the
+    carry chain in one launch): key-switch and external product over ranks 1..3, output sizes below / equal / above the key size,
+    one / two / four limbs in flight per column (LPR), more ciphertexts than CTAs, one unnormalised body -- bit for bit against the
+    oracle's FFT64 restatement."""
+    g, o = pb.Module(n, pb.FFT64), O.OracleModule(n, pb.FFT64)
+    rng = np.random.default_rng(1300 + n)
+    k = 14
+    batch = 310 if n == 512 else 37
+    #        rank_in rank_out a_size key_size res_size
+    shapes = ((1, 1, 3, 4, 3), (2, 1, 3, 4, 5), (1, 2, 2, 3, 2), (1, 1, 2, 5, 6), (1, 1, 1, 2, 1), (1, 0, 2, 3, 3), (2, 3, 2, 2, 2), (1, 1, 4, 1, 2))
+    for rank_in, rank_out, a_size, key_size, res_size in shapes:
+        pg, po = _key(g, o, rng, a_size, rank_in, rank_out + 1, key_size, k)
+        a = fill_uniform(rng, (batch, a_size, rank_in + 1, n), k)
+        a[3, :, 0] = fill_uniform(rng, a[3, :, 0].shape, 40)  # an unnormalised body only passes through add_small + normalize
+        a[7] = 0
+        want = fill_uniform(rng, (batch, res_size, rank_out + 1, n), k)
+        res_g = g.vec_znx_from_numpy(want)
+        g.glwe_keyswitch(res_g, k, g.vec_znx_from_numpy(a), k, pg, k)
+        g.sync()
+        o.glwe_keyswitch_batch(want, k, a, k, po, k)
+        got = g.vec_znx_to_numpy(res_g)
+        bad = [b for b in range(batch) if not np.array_equal(got[b], want[b])]
+        assert not bad, ("ks", rank_in, rank_out, a_size, key_size, res_size, bad[:10], len(bad))
+    for rank, a_size, g_size, res_size in ((1, 3, 3, 3), (2, 2, 3, 2), (1, 2, 4, 5), (3, 1, 2, 2)):
+        pg, po = _key(g, o, rng, a_size, rank + 1, rank + 1, g_size, k)
+        a = fill_uniform(rng, (batch, a_size, rank + 1, n), k)
+        want = fill_uniform(rng, (batch, res_size, rank + 1, n), k)
+        res_g = g.vec_znx_from_numpy(want)
+        g.glwe_external_product(res_g, k, g.vec_znx_from_numpy(a), k, pg, k)
+        g.sync()
+        o.glwe_external_product_batch(want, k, a, k, po, k)
+        got = g.vec_znx_to_numpy(res_g)
+        bad = [b for b in range(batch) if not np.array_equal(got[b], want[b])]
+        assert not bad, ("ep", rank, a_size, g_size, res_size, bad[:10], len(bad))
+
+
+def test_fft64_gadget_bench_shape():
+    """FFT64 key-switch at the bench shape (n = 4096, base2k = 18, three input limbs, key of four): fused kernel == unfused HAL sequence
+    == oracle."""
+    import os
+    n, k, batch = 4096, 18, 24
+    g, o = pb.Module(n, pb.FFT64), O.OracleModule(n, pb.FFT64)
+    rng = np.random.default_rng(1400)
+    pg, po = _key(g, o, rng, 3, 1, 2, 4, k)
+    a = fill_uniform(rng, (batch, 3, 2, n), k)
+    want = np.zeros((batch, 3, 2, n), dtype=np.int64)
+    o.glwe_keyswitch_batch(want, k, a, k, po, k)
+    for env in (None, "1"):
+        if env:
+            os.environ["PGB_NO_FUSION"] = env
+        try:
+            res_g = g.vec_znx_alloc(2, 3, batch)
+            g.glwe_keyswitch(res_g, k, g.vec_znx_from_numpy(a), k, pg, k)
+            g.sync()
+        finally:
+            os.environ.pop("PGB_NO_FUSION", None)
+        assert np.array_equal(g.vec_znx_to_numpy(res_g), want), env
