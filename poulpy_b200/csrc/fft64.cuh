@@ -25,7 +25,7 @@ __device__ __forceinline__ void fgs_bf(double2 &x, double2 &y, double2 w) { // (
 // kernel, TWS = true) through plain loads
 template <bool TWS = false> __device__ __forceinline__ double2 ldw(const double2 *p) {
     if (TWS) return *p;
-    return make_double2(__ldg(&p->x), __ldg(&p->y));
+    return __ldg(p); // one 128-bit load
 }
 
 template <int NLEV, bool TWS = false> __device__ __forceinline__ void fct_radix8(double2 (&x)[8], const double2 *__restrict__ tw, uint32_t hi) {

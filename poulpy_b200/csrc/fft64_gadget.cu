@@ -40,6 +40,9 @@ template <int T> __device__ __forceinline__ void slot_sync(int slot) {
     if (T <= 32) __syncwarp();
     else asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(T) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2_bulk(const void *gptr, uint32_t bytes) { // bytes: multiple of 16
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void group_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 template <int L, int L0, bool TWS> struct GFwd {
@@ -120,6 +123,17 @@ fft64_gadget_kernel(const __grid_constant__ FGadgetArgs p, const double2 *__rest
     for (int ct = blockIdx.x; ct < p.batch; ct += gridDim.x) {
         const long long *in = reinterpret_cast<const long long *>(p.in + (size_t)ct * p.in_bs);
         long long *res = reinterpret_cast<long long *>(p.res + (size_t)ct * p.res_bs);
+        // L2 prefetch (TMA bulk prefetch, one thread per 8n-byte limb): the mask limbs of this CTA's next ciphertext and the body limbs
+        // this one needs in its carry chain
+        if ((int)threadIdx.x < R + p.small_size) {
+            const int u = threadIdx.x;
+            if (u < p.small_size) {
+                prefetch_l2_bulk(in + (size_t)u * in_ls, N * 8);
+            } else if (ct + (int)gridDim.x < p.batch) {
+                const int r = u - p.small_size, limb = r / p.row_cols, col = r % p.row_cols + p.row_col0;
+                prefetch_l2_bulk(in + (size_t)gridDim.x * (p.in_bs / 8) + ((size_t)limb * p.in_cols + col) * N, N * 8);
+            }
+        }
         // ---- forward transforms of the R input limbs ------------------------------------------------------------------------------
         for (int r = slot; r < R; r += NS) {
             const int limb = r / p.row_cols, col = r % p.row_cols + p.row_col0;
@@ -151,9 +165,12 @@ fft64_gadget_kernel(const __grid_constant__ FGadgetArgs p, const double2 *__rest
 #pragma unroll
                 for (int jj = 0; jj < 8; jj++) x[jj] = make_double2(0.0, 0.0);
                 const double *kp = p.pmat + (size_t)poly * N + 8 * t;
-                for (int r = 0; r < R; r++) { // row order of reim4_add_mul (reim4/arithmetic_ref.rs:223-232), FMA-contracted
-                    const double2 *kr = reinterpret_cast<const double2 *>(kp + (size_t)r * p.C * N);
-                    const double2 *ki = reinterpret_cast<const double2 *>(kp + (size_t)r * p.C * N + M);
+                const size_t krow = (size_t)p.C * N;
+                // rows accumulate in row order (reim4_add_mul, reim4/arithmetic_ref.rs:223-232), FMA-contracted; the key values come from L2.
+                // (Requesting three rows x four frequencies together was measured: no gain, the phase is not bound by this latency.)
+                for (int r = 0; r < R; r++) {
+                    const double2 *kr = reinterpret_cast<const double2 *>(kp + (size_t)r * krow);
+                    const double2 *ki = reinterpret_cast<const double2 *>(kp + (size_t)r * krow + M);
                     double br[8], bi[8];
 #pragma unroll
                     for (int q = 0; q < 4; q++) {

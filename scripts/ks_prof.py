@@ -1,4 +1,4 @@
-"""Profiling driver: a few batched key-switches at the bench shape (n=4096, NTT120).  Usage under ncu:
+"""Profiling driver: a few batched key-switches at the bench shape (n=4096, NTT120; KS_FLAVOUR=fft64 for the FFT64 kernel).  Usage under ncu:
 ncu --set full --clock-control none --import-source on -k regex:gadget_kernel -s 2 -c 1 -o gpurun_out/prof_gadget python scripts/ks_prof.py"""
 import os
 import sys
@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import poulpy_b200 as pb
 
 n, k, B = 4096, 18, int(os.environ.get("KS_BATCH", "2048"))
-m = pb.Module(n, pb.NTT120)
+m = pb.Module(n, pb.FFT64 if os.environ.get("KS_FLAVOUR") == "fft64" else pb.NTT120)
 rng = np.random.default_rng(1)
 mat = rng.integers(-(1 << 17), 1 << 17, size=(3, 1, 4, 2, n), dtype=np.int64)
 pm = m.vmp_pmat_alloc(3, 1, 2, 4)
