@@ -497,6 +497,30 @@ def aux_measurements(pb, torch, local, peak):
         del m, a, b2, tensor, r, tsk, sc
     aux["ckks_mul_ntt120_base2k52_k728"] = ck
 
+    # prepare paths: vmp_prepare (MatZnx i64 -> prepared VmpPMat) and svp_prepare at the key-switch, CGGI and CKKS key shapes;
+    # algorithmic bytes per poly = 8n in + prep_bytes * n out
+    prep = {}
+    for fl, nm, log_n, shape, k in ((pb.NTT120, "ntt120", 12, (3, 1, 2, 4), 18), (pb.FFT64, "fft64", 12, (3, 1, 2, 4), 18),
+                                    (pb.FFT64, "fft64", 9, (1, 4, 4, 2), 18), (pb.NTT120, "ntt120", 15, (14, 1, 2, 15), 52)):
+        n = 1 << log_n
+        m = pb.Module(n, fl, device=local)
+        m.set_stream(stream.cuda_stream)
+        rows, cols_in, cols_out, size = shape
+        polys = rows * cols_in * cols_out * size
+        matd = m.mat_znx_from_numpy(np.broadcast_to(rng.integers(-(1 << (k - 1)), 1 << (k - 1), size=(1, 1, 1, 1, n), dtype=np.int64),
+                                                    (rows, cols_in, size, cols_out, n)))
+        pm = m.vmp_pmat_alloc(rows, cols_in, cols_out, size)
+        ms = _time_ms(torch, stream, lambda: m.vmp_prepare(pm, matd), 5)
+        byts = polys * n * (8 + m.prep_bytes)
+        prep[f"vmp_prepare_{nm}_log_n={log_n}_shape={rows}x{cols_in}x{cols_out}x{size}"] = {
+            "ms": ms, "polys_per_s": polys / (ms * 1e-3), "achieved_gbs": byts / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": byts / (ms * 1e-3) / 1e9 / peak,
+            "note": "one synchronous call (host launch + stream sync inside the timed region)"}
+        sp, sz = m.svp_ppol_alloc(1), m.scalar_znx_from_numpy(rng.integers(-1, 2, size=(1, n), dtype=np.int64))
+        ms = _time_ms(torch, stream, lambda: m.svp_prepare(sp, 0, sz, 0), 20)
+        prep[f"svp_prepare_{nm}_log_n={log_n}"] = {"ms": ms, "note": "single polynomial, launch-latency bound"}
+        del m, matd, pm, sp, sz
+    aux["prepare_paths"] = prep
+
     # batched DFT sweep (BASELINE config 1): forward then inverse over VecZnx(cols=2, size) at log_n 10..16, >= 256 MB of limbs
     sweep = {}
     pp = os.path.join(ROOT, "profiles", "r1_pipe_peaks.json")

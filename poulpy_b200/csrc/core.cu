@@ -79,7 +79,7 @@ extern "C" size_t pgb_glwe_keyswitch_tmp_bytes(const pgb_module *m, uint64_t res
         t += align_up(batch * n * rank_in * div_ceil64(in_size, dsize) * pb);   // ai_dft
         t += align_up(batch * n * cols_out * key->size * pb);                   // res_dft_tmp
     }
-    t += align_up(batch * sizeof(int));                                         // per-ciphertext route flags of the fused kernel
+    t += align_up((2 * batch + 1) * sizeof(int));                               // per-ciphertext route flags of the fused kernel + fail list
     return t + ALIGN;
 }
 
@@ -131,7 +131,7 @@ extern "C" int pgb_glwe_keyswitch_batched(pgb_module *m, pgb_vec_znx *res, uint6
         if (ntt120_gadget_supported(m, (int)R, (int)cols_out, (int)key->size, (int)key_base2k, (int)B)) {
             // one kernel per batch: i64 in -> i64 out (ntt120_gadget.cu); ciphertexts whose integers could leave the collapsed-key
             // bound are flagged in `ok` and redone by the per-limb kernels below (normally none)
-            int *ok = (int *)ar.take(B * sizeof(int));
+            int *ok = (int *)ar.take((2 * B + 1) * sizeof(int)); // flags | count of flagged | their indices
             PGB_REQUIRE(ok != nullptr, "glwe_keyswitch: scratch exhausted");
             PGB_TRY(ntt120_gadget_fused(m, (const char *)ain.data, ain_bs, (int)ain.cols, (int)rank_in, 1, (int)R, (const char *)key->data,
                                         (int)(cols_out * key->size), (int)cols_out, small_size, (char *)res->data, bt->stride_res,
@@ -139,11 +139,11 @@ extern "C" int pgb_glwe_keyswitch_batched(pgb_module *m, pgb_vec_znx *res, uint6
             for (uint64_t c = 0; c < rank_in; c++) {
                 LimbSet in = {(char *)ain.data + limb_off(n, ain.cols, c + 1, 0, 8), ain.cols * n * 8, ain_bs};
                 LimbSet out = {(char *)a_dft.data + limb_off(n, rank_in, c, 0, pb), rank_in * n * pb, a_dft_bs};
-                PGB_TRY(ntt120_forward_skip(m, in, out, (int)ain.size, (int)B, ok));
+                PGB_TRY(ntt120_forward_skip(m, in, out, (int)ain.size, (int)B, ok, true));
             }
             return ntt120_fused_back(m, (const char *)a_dft.data, a_dft_bs, (const char *)key->data, (int)R, (int)(cols_out * key->size),
                                      (int)cols_out, (const char *)ain.data, ain_bs, ain.cols * n * 8, small_size, (char *)res->data,
-                                     bt->stride_res, res->cols * n * 8, (int)res->size, (int)key_base2k, 0, (int)B, nullptr, 0, 0, ok);
+                                     bt->stride_res, res->cols * n * 8, (int)res->size, (int)key_base2k, 0, (int)B, nullptr, 0, 0, ok, true);
         }
         // fused back end: vmp -> idft -> CRT -> add_small -> normalize per (ciphertext, column), nothing but a_dft touches HBM
         for (uint64_t c = 0; c < rank_in; c++) PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &a_dft, c, &ain, c + 1, &btd));
@@ -191,7 +191,7 @@ extern "C" size_t pgb_glwe_external_product_tmp_bytes(const pgb_module *m, uint6
     t += align_up(batch * n * cols * in_size * pb); // a_dft (dsize == 1 uses a_size limbs, dsize > 1 uses <= a_size)
     if (a_base2k != ggsw_base2k) t += align_up(batch * n * cols * in_size * 8);
     if (dsize > 1) t += align_up(batch * n * cols * ggsw->size * pb);
-    t += align_up(batch * sizeof(int)); // per-ciphertext route flags of the fused kernel
+    t += align_up((2 * batch + 1) * sizeof(int)); // per-ciphertext route flags of the fused kernel + fail list
     return t + ALIGN;
 }
 
@@ -239,7 +239,7 @@ extern "C" int pgb_glwe_external_product_batched(pgb_module *m, pgb_vec_znx *res
         if (res_base2k == ggsw_base2k && ntt120_fused_supported(m) && !getenv("PGB_NO_FUSION")) {
             const uint64_t R = umin64(ggsw->rows * ggsw->cols_in, cols * a_size);
             if (ntt120_gadget_supported(m, (int)R, (int)cols, (int)ggsw->size, (int)ggsw_base2k, (int)B)) {
-                int *ok = (int *)ar.take(B * sizeof(int));
+                int *ok = (int *)ar.take((2 * B + 1) * sizeof(int)); // flags | count of flagged | their indices
                 PGB_REQUIRE(ok != nullptr, "glwe_external_product: scratch exhausted");
                 PGB_TRY(ntt120_gadget_fused(m, (const char *)ain.data, ain_bs, (int)ain.cols, (int)cols, 0, (int)R, (const char *)ggsw->data,
                                             (int)(cols * ggsw->size), (int)cols, 0, (char *)res->data, bt->stride_res, (int)res->size,
@@ -247,11 +247,11 @@ extern "C" int pgb_glwe_external_product_batched(pgb_module *m, pgb_vec_znx *res
                 for (uint64_t j = 0; j < cols; j++) {
                     LimbSet in = {(char *)ain.data + limb_off(n, ain.cols, j, 0, 8), ain.cols * n * 8, ain_bs};
                     LimbSet out = {(char *)a_dft.data + limb_off(n, cols, j, 0, pb), cols * n * pb, a_dft_bs};
-                    PGB_TRY(ntt120_forward_skip(m, in, out, (int)a_size, (int)B, ok));
+                    PGB_TRY(ntt120_forward_skip(m, in, out, (int)a_size, (int)B, ok, true));
                 }
                 return ntt120_fused_back(m, (const char *)a_dft.data, a_dft_bs, (const char *)ggsw->data, (int)R, (int)(cols * ggsw->size),
                                          (int)cols, nullptr, 0, 0, 0, (char *)res->data, bt->stride_res, res->cols * n * 8, (int)res->size,
-                                         (int)ggsw_base2k, 0, (int)B, nullptr, 0, 0, ok);
+                                         (int)ggsw_base2k, 0, (int)B, nullptr, 0, 0, ok, true);
             }
             for (uint64_t j = 0; j < cols; j++) PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &a_dft, j, &ain, j, &btd));
             return ntt120_fused_back(m, (const char *)a_dft.data, a_dft_bs, (const char *)ggsw->data, (int)R, (int)(cols * ggsw->size),

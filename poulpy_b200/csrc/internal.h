@@ -11,14 +11,15 @@ enum { BIG_ADD_SMALL = 0, BIG_FROM_SMALL = 1, BIG_ZERO = 2 };
 // ntt120_dft.cu
 int ntt120_module_init(pgb_module *m);
 int ntt120_forward(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch, long long and_mask = -1);
-// same, skipping the batch items b with skip[b] != 0 (device array); single-CTA sizes only
-int ntt120_forward_skip(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch, const int *skip);
+// same, skipping the batch items b with skip[b] != 0 (device array); single-CTA sizes only.  skip_list: skip[batch] holds the number of
+// items that are NOT skipped and skip[batch + 1 ..] their indices (the gadget kernel's fail list), so a small grid strides over those only
+int ntt120_forward_skip(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch, const int *skip, bool skip_list = false);
 int ntt120_inverse_big(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch);
 bool ntt120_fused_supported(const pgb_module *m);
 int ntt120_fused_back(pgb_module *m, const char *a_dft, uint64_t a_bs, const char *pmat, int R, int C, int cols_out, const char *small,
                       uint64_t small_bs, uint64_t small_limb_stride, int small_size, char *res, uint64_t res_bs, uint64_t res_limb_stride,
                       int res_size, int base2k, int64_t res_offset, int batch, const char *glwe, uint64_t glwe_bs, uint64_t glwe_words,
-                      const int *skip = nullptr);
+                      const int *skip = nullptr, bool skip_list = false);
 // max bit length of the integer coefficients of `polys` DFT polys -> *bits_dev (coef_ws: polys * 16n bytes of device scratch)
 int ntt120_key_max_bits(pgb_module *m, const char *pmat, int polys, char *coef_ws, int *bits_dev);
 // ntt120_gadget.cu

@@ -79,6 +79,8 @@ struct NttJobs {
     int jobs_per_batch;
     int total_jobs;
     const int *skip; // optional, per batch item: non-zero = leave this item alone (forward kernel only)
+    int skip_list;   // skip[] is followed by a count and a compacted list of the items that are NOT skipped: skip[batch] = count,
+                     // skip[batch + 1 ..] = their indices (written by the gadget kernel); the grid then strides over that list only
     long long and_mask; // i64 inputs are ANDed with this before the residue map (cnv_prepare's masked last limb); -1 = none
 };
 
@@ -151,20 +153,9 @@ template <int L> struct FwdMid<L, L> {
     static __device__ __forceinline__ void run(uint32_t *, uint32_t *, const uint2 *, int, int, bool, uint32_t = 1u) {}
 };
 
-template <int L, int LPC> __global__ void __launch_bounds__(Geo<L>::T *LPC) ntt120_fwd_kernel(NttJobs jb, const uint2 *__restrict__ tw) {
+template <int L, int LPC> __device__ __forceinline__ void ntt120_fwd_job(const NttJobs &jb, const uint2 *__restrict__ tw, uint32_t *smem, int b, int j,
+                                                                         bool active, int slot, int t) {
     typedef Geo<L> G;
-    extern __shared__ __align__(16) uint32_t smem[];
-    const int slot = threadIdx.x / G::T, t = threadIdx.x % G::T;
-    const int job = blockIdx.x * LPC + slot;
-    bool active = job < jb.total_jobs;
-    const int b = active ? job / jb.jobs_per_batch : 0, j = active ? job % jb.jobs_per_batch : 0;
-    if (jb.skip) {
-        if (LPC == 1) {
-            if (__ldg(jb.skip + b)) return; // CTA-uniform
-        } else {
-            active = active && !__ldg(jb.skip + b);
-        }
-    }
     const long long *gin = reinterpret_cast<const long long *>(jb.in.base + (size_t)b * jb.in.batch_stride + (size_t)j * jb.in.limb_stride);
     uint32_t *gout = reinterpret_cast<uint32_t *>(jb.out.base + (size_t)b * jb.out.batch_stride + (size_t)j * jb.out.limb_stride);
     uint32_t *sm = smem + slot * 4 * G::PLANE;
@@ -181,6 +172,35 @@ template <int L, int LPC> __global__ void __launch_bounds__(Geo<L>::T *LPC) ntt1
         __syncthreads();
         FwdMid<L, (L > G::R0) ? G::R0 : L>::run(sm, gout, tw, n, t, active);
     }
+}
+
+template <int L, int LPC> __global__ void __launch_bounds__(Geo<L>::T *LPC) ntt120_fwd_kernel(NttJobs jb, const uint2 *__restrict__ tw) {
+    typedef Geo<L> G;
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int slot = threadIdx.x / G::T, t = threadIdx.x % G::T;
+    if (jb.skip && jb.skip_list) { // the per-limb route of the gadget product: normally an empty list, the few CTAs leave at once
+        const int batch = jb.total_jobs / jb.jobs_per_batch;
+        const int nwork = __ldg(jb.skip + batch) * jb.jobs_per_batch;
+        for (int base = blockIdx.x * LPC; base < nwork; base += gridDim.x * LPC) {
+            const int job = base + slot;
+            const bool active = job < nwork;
+            const int b = active ? __ldg(jb.skip + batch + 1 + job / jb.jobs_per_batch) : 0, j = active ? job % jb.jobs_per_batch : 0;
+            ntt120_fwd_job<L, LPC>(jb, tw, smem, b, j, active, slot, t);
+            __syncthreads(); // the planes are reused by the next job
+        }
+        return;
+    }
+    const int job = blockIdx.x * LPC + slot;
+    bool active = job < jb.total_jobs;
+    const int b = active ? job / jb.jobs_per_batch : 0, j = active ? job % jb.jobs_per_batch : 0;
+    if (jb.skip) {
+        if (LPC == 1) {
+            if (__ldg(jb.skip + b)) return; // CTA-uniform
+        } else {
+            active = active && !__ldg(jb.skip + b);
+        }
+    }
+    ntt120_fwd_job<L, LPC>(jb, tw, smem, b, j, active, slot, t);
 }
 
 // ---------------------------------------------------------------------------------------------- inverse
@@ -513,7 +533,7 @@ template <int K, int L> __device__ __forceinline__ void fused_top(uint32_t *__re
 template <int L> __global__ void __launch_bounds__(Geo<L>::T, 2) ntt120_fused_back_kernel(FusedArgs p, const uint2 *__restrict__ tw,
                                                                                          Ntt120Consts nc, int total_work,
                                                                                          i128 *__restrict__ carry_scratch,
-                                                                                         const int *__restrict__ skip) {
+                                                                                         const int *__restrict__ skip, int skip_list) {
     typedef Geo<L> G;
     static_assert(L > G::R0, "fused path needs at least two passes");
     extern __shared__ __align__(16) uint32_t smem[];
@@ -524,6 +544,7 @@ template <int L> __global__ void __launch_bounds__(Geo<L>::T, 2) ntt120_fused_ba
     const size_t res_ls = p.res_limb_stride / 8, small_ls = p.small_limb_stride / 8;
     const int K = p.K, lsh = p.lsh, w = lsh == 0 ? K : K - lsh;
     i128 *carry = carry_scratch + (size_t)blockIdx.x * n;
+    if (skip && skip_list && __ldg(skip + total_work / p.cols_out) == 0) return; // the gadget kernel flagged nothing (see NttJobs::skip_list)
     const size_t m_stride = (size_t)p.C * poly;
     const u128 M0 = ((u128)c_crt.m_hi[0] << 64) | c_crt.m_lo[0], M1 = ((u128)c_crt.m_hi[1] << 64) | c_crt.m_lo[1];
     const u128 M2 = ((u128)c_crt.m_hi[2] << 64) | c_crt.m_lo[2], M3 = ((u128)c_crt.m_hi[3] << 64) | c_crt.m_lo[3];
@@ -812,6 +833,7 @@ template <int L> static int launch_fwd(pgb_module *m, const NttJobs &jb) {
         attr_set = true;
     }
     int grid = (jb.total_jobs + LPC - 1) / LPC;
+    if (jb.skip && jb.skip_list && grid > 296) grid = 296;
     { ProfScope _ps(m, PROF_DFT_FWD);
     ntt120_fwd_kernel<L, LPC><<<grid, G::T * LPC, smem, m->stream>>>(jb, m->ntt_fwd);
     }
@@ -949,26 +971,26 @@ static int ntt120_inverse_large(pgb_module *m, LimbSet in, LimbSet out, int jobs
 
 // in: i64 limbs, out: 16 B/coef DFT limbs
 int ntt120_forward(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch, long long and_mask) {
-    NttJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch, nullptr, and_mask};
+    NttJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch, nullptr, 0, and_mask};
     if (jb.total_jobs == 0) return PGB_OK;
     if (m->log_n >= 14) return ntt120_forward_large(m, in, out, jobs_per_batch, batch, and_mask);
     NTT_DISPATCH(launch_fwd)
 }
-int ntt120_forward_skip(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch, const int *skip) {
-    NttJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch, skip, -1};
+int ntt120_forward_skip(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch, const int *skip, bool skip_list) {
+    NttJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch, skip, skip_list ? 1 : 0, -1};
     if (jb.total_jobs == 0) return PGB_OK;
     PGB_REQUIRE(m->log_n < 14, "ntt120_forward_skip: single-CTA sizes only");
     NTT_DISPATCH(launch_fwd)
 }
 // in: DFT limbs, out: i128 limbs (may alias `in` limb for limb: in-place consume)
 int ntt120_inverse_big(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int batch) {
-    NttJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch, nullptr, -1};
+    NttJobs jb = {in, out, jobs_per_batch, jobs_per_batch * batch, nullptr, 0, -1};
     if (jb.total_jobs == 0) return PGB_OK;
     if (m->log_n >= 14) return ntt120_inverse_large(m, in, out, jobs_per_batch, batch);
     NTT_DISPATCH(launch_inv)
 }
 
-template <int L> static int launch_fused(pgb_module *m, const FusedArgs &p, int batch, const int *skip) {
+template <int L> static int launch_fused(pgb_module *m, const FusedArgs &p, int batch, const int *skip, int skip_list) {
     typedef Geo<L> G;
     size_t smem = (size_t)4 * G::PLANE * sizeof(uint32_t);
     static int ctas_per_sm = 0, sms = 0;
@@ -983,7 +1005,7 @@ template <int L> static int launch_fused(pgb_module *m, const FusedArgs &p, int 
     const int grid = total < sms * ctas_per_sm ? total : sms * ctas_per_sm;
     PGB_TRY(ensure_carry_ws(m, (size_t)grid * G::NB * sizeof(i128)));
     { ProfScope _ps(m, PROF_DFT_INV);
-    ntt120_fused_back_kernel<L><<<grid, G::T, smem, m->stream>>>(p, m->ntt_inv, m->nc, total, (i128 *)m->carry_ws, skip);
+    ntt120_fused_back_kernel<L><<<grid, G::T, smem, m->stream>>>(p, m->ntt_inv, m->nc, total, (i128 *)m->carry_ws, skip, skip_list);
     }
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;
@@ -1038,7 +1060,7 @@ static uint32_t pow2_mod_q(uint64_t e, uint32_t q) {
 int ntt120_fused_back(pgb_module *m, const char *a_dft, uint64_t a_bs, const char *pmat, int R, int C, int cols_out, const char *small,
                       uint64_t small_bs, uint64_t small_limb_stride, int small_size, char *res, uint64_t res_bs, uint64_t res_limb_stride,
                       int res_size, int base2k, int64_t res_offset, int batch, const char *glwe, uint64_t glwe_bs, uint64_t glwe_words,
-                      const int *skip) {
+                      const int *skip, bool skip_list) {
     FusedArgs p;
     memset(&p, 0, sizeof p);
     p.a_dft = a_dft; p.a_bs = a_bs; p.pmat = pmat; p.small = small; p.small_bs = small_bs; p.small_limb_stride = small_limb_stride;
@@ -1110,11 +1132,11 @@ int ntt120_fused_back(pgb_module *m, const char *a_dft, uint64_t a_bs, const cha
         ok = okf; // the per-limb kernel below only processes the ciphertexts that failed the bound
     }
     switch (m->log_n) {
-    case 9: return launch_fused<9>(m, p, batch, ok);
-    case 10: return launch_fused<10>(m, p, batch, ok);
-    case 11: return launch_fused<11>(m, p, batch, ok);
-    case 12: return launch_fused<12>(m, p, batch, ok);
-    case 13: return launch_fused<13>(m, p, batch, ok);
+    case 9: return launch_fused<9>(m, p, batch, ok, (skip && skip_list) ? 1 : 0);
+    case 10: return launch_fused<10>(m, p, batch, ok, (skip && skip_list) ? 1 : 0);
+    case 11: return launch_fused<11>(m, p, batch, ok, (skip && skip_list) ? 1 : 0);
+    case 12: return launch_fused<12>(m, p, batch, ok, (skip && skip_list) ? 1 : 0);
+    case 13: return launch_fused<13>(m, p, batch, ok, (skip && skip_list) ? 1 : 0);
     default: pgb_set_error("fused back end: unsupported n"); return PGB_ERR_UNSUPPORTED;
     }
 }

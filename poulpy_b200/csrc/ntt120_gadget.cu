@@ -315,7 +315,10 @@ template <int L> __device__ __forceinline__ void gadget_body(const GadgetArgs &p
         too_big |= amax_allowed < 0 || (amax_allowed < 32 && (mag >> amax_allowed) != 0);
         const int bad = __syncthreads_or(too_big);
         if (bad) { // identical decision in all four CTAs (same inputs): this ciphertext takes the per-limb kernels
-            if (t == 0 && K == 0) p.ok[ct] = 0;
+            if (t == 0 && K == 0) { // ok[batch] counts the flagged ciphertexts, ok[batch + 1 ..] lists them for the per-limb kernels
+                p.ok[ct] = 0;
+                p.ok[p.batch + 1 + atomicAdd(p.ok + p.batch, 1)] = ct;
+            }
             cl_arrive();
             continue;
         }
@@ -658,7 +661,8 @@ bool ntt120_gadget_supported(const pgb_module *m, int R, int cols_out, int S, in
     return batch >= 1;
 }
 
-// ok_out (device, batch ints, caller scratch): 1 where the ciphertext was finished here, 0 where the per-limb route is needed
+// ok_out (device, 2 * batch + 1 ints, caller scratch): ok[b] = 1 where the ciphertext was finished here, 0 where the per-limb route is
+// needed; ok[batch] = number of the latter, ok[batch + 1 ..] = their indices
 int ntt120_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_cols, int row_cols, int row_col0, int R, const char *pmat,
                         int C, int cols_out, int small_size, char *res, uint64_t res_bs, int res_size, int base2k, int batch, int *ok_out) {
     const uint64_t n = m->n, poly_bytes = 16 * n;
@@ -720,6 +724,7 @@ int ntt120_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_co
     }
     const int planes = R > cols_out ? R : cols_out;
     const size_t smem = (size_t)planes * n * 4;
+    PGB_CHECK_CUDA(cudaMemsetAsync(ok_out + batch, 0, sizeof(int), m->stream));
     switch (m->log_n) {
     case 10: return launch_gadget<10>(m, p, smem);
     case 11: return launch_gadget<11>(m, p, smem);
