@@ -291,6 +291,16 @@ int pgb_vec_znx_add_assign_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res
 int pgb_vec_znx_sub_assign(pgb_module *m, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col);
 /* vec_znx_mul_xp_minus_one (reference/vec_znx/mul_xp_minus_one.rs:13-22): res = X^p * a - a; res and a must not alias */
 int pgb_vec_znx_mul_xp_minus_one(pgb_module *m, int64_t p, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col);
+/* vec_znx_rsh_assign (HalImpl::vec_znx_rsh_assign, hal_impl.rs; reference/vec_znx/shift.rs:186-243): arithmetic right shift by k bits in base
+ * 2^base2k, in place; ceil(k / base2k) must not exceed res.size (the reference panics) */
+int pgb_vec_znx_rsh_assign(pgb_module *m, uint64_t base2k, uint64_t k, pgb_vec_znx *res, uint64_t res_col);
+int pgb_vec_znx_rsh_assign_batched(pgb_module *m, uint64_t base2k, uint64_t k, pgb_vec_znx *res, uint64_t res_col, const pgb_batch *bt);
+/* vec_znx_big_automorphism / _assign (HalImpl, hal_impl.rs; reference/ntt120/vec_znx_big.rs:1462-1529, reference/fft64/vec_znx_big.rs:140-188) */
+int pgb_vec_znx_big_automorphism(pgb_module *m, int64_t p, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx_big *a, uint64_t a_col);
+int pgb_vec_znx_big_automorphism_batched(pgb_module *m, int64_t p, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx_big *a,
+                                         uint64_t a_col, const pgb_batch *bt);
+size_t pgb_vec_znx_big_automorphism_assign_tmp_bytes(const pgb_module *m);
+int pgb_vec_znx_big_automorphism_assign(pgb_module *m, int64_t p, pgb_vec_znx_big *res, uint64_t res_col);
 /* vec_znx_normalize_assign (reference/vec_znx/normalize.rs:403-425) */
 int pgb_vec_znx_normalize_assign(pgb_module *m, uint64_t base2k, pgb_vec_znx *res, uint64_t res_col);
 
@@ -321,6 +331,19 @@ size_t pgb_glwe_automorphism_tmp_bytes(const pgb_module *m, uint64_t res_size, u
 int pgb_glwe_automorphism_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, const pgb_vec_znx *a, uint64_t a_base2k,
                                   const pgb_vmp_pmat *key, uint64_t key_base2k, int64_t p, uint64_t dsize, const pgb_batch *bt, void *scratch,
                                   size_t scratch_len);
+
+/* glwe_automorphism_add_assign (poulpy-core/src/automorphism/glwe_ct.rs:142-183): res += automorphism_p(key-switch(res)), the step the
+ * trace is made of; glwe_trace_assign (poulpy-core/src/glwe_trace.rs:129-175): for i in skip..log_n { glwe_rsh(1); automorphism_add_assign
+ * with the key of trace_galois_elements()[i] } (glwe_trace.rs:34-44).  `keys` is a HOST array of log_n prepared automorphism keys. */
+size_t pgb_glwe_automorphism_add_assign_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t res_base2k, const pgb_vmp_pmat *key,
+                                                  uint64_t key_base2k, uint64_t dsize, uint64_t batch);
+int pgb_glwe_automorphism_add_assign_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, const pgb_vmp_pmat *key, uint64_t key_base2k,
+                                             int64_t p, uint64_t dsize, const pgb_batch *bt, void *scratch, size_t scratch_len);
+int64_t pgb_trace_galois_element(const pgb_module *m, uint64_t i);
+size_t pgb_glwe_trace_assign_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t res_base2k, const pgb_vmp_pmat *key, uint64_t key_base2k,
+                                       uint64_t dsize, uint64_t batch);
+int pgb_glwe_trace_assign_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, uint64_t skip, const pgb_vmp_pmat *keys, uint64_t nkeys,
+                                  uint64_t key_base2k, uint64_t dsize, const pgb_batch *bt, void *scratch, size_t scratch_len);
 
 /* ---- CGGI blind rotation (poulpy-bin-fhe/src/blind_rotation/algorithms/cggi/algorithm.rs:275-368; C3) ---- */
 /* x_pow_a table of the prepared key (cggi/key_prepared.rs:66-75): SvpPPol with 2n columns, col i = X^i. */

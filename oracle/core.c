@@ -306,3 +306,96 @@ void orc_glwe_automorphism(int flavour, const void *mod, orc_vec_znx *res, size_
     for (size_t i = 0; i < res->cols; i++) orc_vec_znx_automorphism(p, res, i, &tmp, i);
     free(tmp.data);
 }
+
+/* ---- automorphism_add_assign and trace --------------------------------------------------------------------------------- */
+/* ntt120/vec_znx_big.rs:1499-1529 (i128) and fft64/vec_znx_big.rs:172-188 (i64, through reference/vec_znx/automorphism.rs):
+ * X -> X^p in place on every limb of column `col` */
+static void be_big_automorphism_assign(const be_t *b, int64_t p, orc_vec_znx_big *r, size_t col) {
+    size_t n = r->n, eb = b->flavour == 0 ? 16 : 8, mask = 2 * n - 1, p_2n = (size_t)(p & (int64_t)mask);
+    char *tmp = (char *)malloc(n * eb);
+    for (size_t limb = 0; limb < r->size; limb++) {
+        char *rj = (char *)r->data + eb * n * (limb * r->cols + col);
+        memcpy(tmp, rj, n * eb);
+        size_t k = 0;
+        for (size_t i = 1; i < n; i++) {
+            k = (k + p_2n) & mask;
+            if (b->flavour == 0) {
+                unsigned __int128 v;
+                memcpy(&v, tmp + 16 * i, 16);
+                if (k >= n) v = (unsigned __int128)0 - v; /* wrapping_neg */
+                memcpy(rj + 16 * (k < n ? k : k - n), &v, 16);
+            } else {
+                uint64_t v;
+                memcpy(&v, tmp + 8 * i, 8);
+                if (k >= n) v = 0 - v;
+                memcpy(rj + 8 * (k < n ? k : k - n), &v, 8);
+            }
+        }
+    }
+    free(tmp);
+}
+
+/* poulpy-core/src/automorphism/glwe_ct.rs:142-183 (glwe_automorphism_add_assign_default):
+ *   res_big = glwe_keyswitch_internal(res_dft(rank+1, key.size), res, key); per column: big_automorphism_assign(p), big_add_small_assign
+ *   (the column of res itself), big_normalize back into res */
+void orc_glwe_automorphism_add_assign(int flavour, const void *mod, orc_vec_znx *res, size_t res_base2k, const orc_vmp_pmat *key,
+                                      size_t key_base2k, int64_t p, size_t dsize) {
+    be_t b = make_be(flavour, mod);
+    size_t n = res->n;
+    assert(res->cols - 1 == key->cols_in && res->cols == key->cols_out);
+    orc_vec_znx_dft res_dft = dft_alloc(&b, n, res->cols, key->size);
+    orc_vec_znx res_conv = {0};
+    const orc_vec_znx *ain = res;
+    if (res_base2k != key_base2k) {
+        res_conv = conv_base2k(res, res_base2k, key_base2k);
+        ain = &res_conv;
+    }
+    /* glwe_keyswitch_internal (keyswitching/glwe.rs:207-239) */
+    orc_vec_znx_dft a_dft = dft_alloc(&b, n, ain->cols - 1, ain->size);
+    for (size_t c = 0; c + 1 < ain->cols; c++) be_dft_apply(&b, 1, 0, &a_dft, c, ain, c + 1);
+    gglwe_product_dft(&b, &res_dft, &a_dft, key, dsize);
+    be_idft_consume(&b, &res_dft);
+    orc_vec_znx_big res_big = {res_dft.data, n, res_dft.cols, res_dft.size};
+    be_big_add_small_assign(&b, &res_big, 0, ain, 0);
+    for (size_t i = 0; i < res->cols; i++) {
+        be_big_automorphism_assign(&b, p, &res_big, i);
+        be_big_add_small_assign(&b, &res_big, i, ain, i);
+        be_big_normalize(&b, res, res_base2k, 0, i, &res_big, key_base2k, i);
+    }
+    free(a_dft.data);
+    free(res_dft.data);
+    free(res_conv.data);
+}
+
+/* GALOISGENERATOR = 5 (poulpy-hal/src/lib.rs); galois_element (layouts/module.rs:214-226) for a positive generator exponent */
+static int64_t galois_element_pos(uint64_t e, size_t cyclotomic_order) {
+    uint64_t r = 1, x = 5;
+    while (e) { /* mod_exp_u64: wrapping square-and-multiply */
+        if (e & 1) r *= x;
+        x *= x;
+        e >>= 1;
+    }
+    return (int64_t)(r & (uint64_t)(cyclotomic_order - 1));
+}
+/* poulpy-core/src/glwe_trace.rs:34-44 */
+int64_t orc_trace_galois_element(size_t i, size_t n) { return i == 0 ? -1 : galois_element_pos((uint64_t)1 << (i - 1), 2 * n); }
+
+/* poulpy-core/src/glwe_trace.rs:129-175 (glwe_trace_assign_default); keys[i] is the prepared automorphism key of
+ * orc_trace_galois_element(i, n), i in [skip, log_n) (entries below `skip` are not read) */
+void orc_glwe_trace_assign(int flavour, const void *mod, orc_vec_znx *res, size_t res_base2k, size_t skip, const orc_vmp_pmat *const *keys,
+                           size_t key_base2k, size_t dsize) {
+    size_t n = res->n, log_n = 0;
+    while (((size_t)1 << log_n) < n) log_n++;
+    assert(skip <= log_n);
+    if (res_base2k != key_base2k) {
+        orc_vec_znx res_conv = conv_base2k(res, res_base2k, key_base2k);
+        orc_glwe_trace_assign(flavour, mod, &res_conv, key_base2k, skip, keys, key_base2k, dsize);
+        for (size_t i = 0; i < res->cols; i++) orc_vec_znx_normalize(res, res_base2k, 0, i, &res_conv, key_base2k, i, 0); /* glwe_normalize */
+        free(res_conv.data);
+        return;
+    }
+    for (size_t i = skip; i < log_n; i++) {
+        for (size_t c = 0; c < res->cols; c++) orc_vec_znx_rsh_assign(res_base2k, 1, res, c); /* glwe_rsh(1) (operations/glwe.rs:1096-1112) */
+        orc_glwe_automorphism_add_assign(flavour, mod, res, res_base2k, keys[i], key_base2k, orc_trace_galois_element(i, n), dsize);
+    }
+}

@@ -164,6 +164,8 @@ void orc_vec_znx_normalize_assign(size_t base2k, orc_vec_znx *res, size_t res_co
 void orc_znx_automorphism(int64_t p, int64_t *res, const int64_t *a, size_t n);
 void orc_vec_znx_automorphism(int64_t p, orc_vec_znx *res, size_t res_col, const orc_vec_znx *a, size_t a_col);
 void orc_znx_rotate(int64_t p, int64_t *res, const int64_t *a, size_t n);
+/* reference/vec_znx/shift.rs:186-243 */
+void orc_vec_znx_rsh_assign(size_t base2k, size_t k, orc_vec_znx *res, size_t res_col);
 
 /* ------------------------------------------------------------ compositions */
 /* flavour: 0 = NTT120, 1 = FFT64.  `mod` is the matching module pointer. */
@@ -179,6 +181,13 @@ void orc_glwe_external_product(int flavour, const void *mod, orc_vec_znx *res, s
 /* poulpy-core/src/automorphism/glwe_ct.rs:51-72 */
 void orc_glwe_automorphism(int flavour, const void *mod, orc_vec_znx *res, size_t res_base2k, const orc_vec_znx *a, size_t a_base2k,
                            const orc_vmp_pmat *key, size_t key_base2k, int64_t p, size_t dsize);
+
+/* poulpy-core/src/automorphism/glwe_ct.rs:142-183; poulpy-core/src/glwe_trace.rs:34-44, :129-175 */
+void orc_glwe_automorphism_add_assign(int flavour, const void *mod, orc_vec_znx *res, size_t res_base2k, const orc_vmp_pmat *key,
+                                      size_t key_base2k, int64_t p, size_t dsize);
+int64_t orc_trace_galois_element(size_t i, size_t n);
+void orc_glwe_trace_assign(int flavour, const void *mod, orc_vec_znx *res, size_t res_base2k, size_t skip, const orc_vmp_pmat *const *keys,
+                           size_t key_base2k, size_t dsize);
 
 /* ------------------------------------------------------------ bivariate convolution (HalImpl::cnv_*, hal_impl.rs:670-754) */
 /* CnvPVecL / CnvPVecR are opaque prepared layouts: this restatement keeps both in the VecZnxDft layout.

@@ -331,6 +331,18 @@ class OracleModule:
         lib().orc_glwe_automorphism(C.c_int(self.flavour), self._h, C.byref(r), _sz(res_base2k), C.byref(av), _sz(a_base2k), C.byref(ks),
                                     _sz(key_base2k), C.c_int64(p), _sz(dsize))
 
+    def glwe_automorphism_add_assign(self, res, res_base2k, key: VmpPMat, key_base2k, p, dsize=1):
+        """res (size, cols, n) += automorphism_p(key-switch(res)) -- automorphism/glwe_ct.rs:142-183."""
+        r, ks = _vz(res), key.struct()
+        lib().orc_glwe_automorphism_add_assign(C.c_int(self.flavour), self._h, C.byref(r), _sz(res_base2k), C.byref(ks), _sz(key_base2k),
+                                               C.c_int64(p), _sz(dsize))
+
+    def glwe_trace_assign(self, res, res_base2k, skip, keys, key_base2k, dsize=1):
+        """keys: list of log_n prepared automorphism keys, keys[i] for trace_galois_element(i, n) (glwe_trace.rs:129-175)."""
+        arr = (C.POINTER(_PM) * len(keys))(*[C.pointer(k.struct()) for k in keys])
+        r = _vz(res)
+        lib().orc_glwe_trace_assign(C.c_int(self.flavour), self._h, C.byref(r), _sz(res_base2k), _sz(skip), arr, _sz(key_base2k), _sz(dsize))
+
     def cggi_x_pow_a(self):
         res = self.svp_ppol_alloc(2 * self.n)
         r = _pp(res)
@@ -409,3 +421,13 @@ def ntt120_b_to_znx128(x):
     res = np.zeros((x.shape[0], 2), dtype=np.uint64)
     lib().orc_ntt120_b_to_znx128(_sz(x.shape[0]), _p(res), _p(x))
     return i128_to_int(res)
+
+
+def vec_znx_rsh_assign(base2k, k, res, res_col):
+    r = _vz(res)
+    lib().orc_vec_znx_rsh_assign(_sz(base2k), _sz(k), C.byref(r), _sz(res_col))
+
+
+def trace_galois_element(i, n):
+    lib().orc_trace_galois_element.restype = C.c_int64
+    return int(lib().orc_trace_galois_element(_sz(i), _sz(n)))

@@ -133,3 +133,30 @@ void orc_vec_znx_automorphism(int64_t p, orc_vec_znx *res, size_t res_col, const
     for (size_t j = 0; j < mn; j++) orc_znx_automorphism(p, znx_at(res, res_col, j), znx_at(a, a_col, j), res->n);
     for (size_t j = mn; j < res->size; j++) memset(znx_at(res, res_col, j), 0, 8 * res->n);
 }
+
+/* reference/vec_znx/shift.rs:186-243 (vec_znx_rsh_assign), restated limb step for limb step with the i64 slice kernels of
+ * reference/znx/normalization.rs (first/middle carry-only, middle_step_assign, final_step_assign); `carry` and `tmp` are the 2n words of
+ * scratch the reference splits.  The third loop is kept verbatim (zero limb j, then step on limb steps-1-j). */
+void orc_vec_znx_rsh_assign(size_t base2k, size_t k, orc_vec_znx *res, size_t res_col) {
+    size_t n = res->n, size = res->size;
+    size_t steps = k / base2k, k_rem = k % base2k;
+    if (k_rem != 0) steps += 1;
+    size_t lsh = (base2k - k_rem) % base2k;
+    if (steps > size) abort(); /* the reference indexes limb size - j - 1: it panics here */
+    int64_t *carry = (int64_t *)calloc(2 * n, sizeof(int64_t)), *tmp = carry + n;
+    for (size_t j = 0; j < steps; j++) {
+        if (j == 0) nfc_first_carry_only_i64(n, base2k, lsh, znx_at(res, res_col, size - j - 1), carry);
+        else nfc_middle_carry_only_i64(n, base2k, lsh, znx_at(res, res_col, size - j - 1), carry);
+    }
+    for (size_t j = 0; j + steps < size; j++) {
+        memcpy(tmp, znx_at(res, res_col, size - steps - j - 1), 8 * n);
+        nfc_middle_step_assign_i64(n, base2k, lsh, tmp, carry);
+        memcpy(znx_at(res, res_col, size - j - 1), tmp, 8 * n);
+    }
+    for (size_t j = 0; j < steps; j++) {
+        memset(znx_at(res, res_col, j), 0, 8 * n);
+        if (j == 0) nfc_final_step_assign_i64(n, base2k, lsh, znx_at(res, res_col, steps - j - 1), carry);
+        else nfc_middle_step_assign_i64(n, base2k, lsh, znx_at(res, res_col, steps - j - 1), carry);
+    }
+    free(carry);
+}

@@ -899,6 +899,71 @@ static int automorphism_impl(pgb_module *m, int64_t p, pgb_vec_znx *res, uint64_
     PGB_TRY(znx_automorphism(m, R, A, p, (uint32_t)mn, (uint32_t)bt->count));
     return raw_limbs(m, true, shift(R, mn), shift(R, mn), n * 8, (uint32_t)(res->size - mn), (uint32_t)bt->count);
 }
+// vec_znx_big_automorphism (ntt120/vec_znx_big.rs:1462-1497, fft64/vec_znx_big.rs:144-170): out of place, limbs of res beyond a.size zeroed
+int big_automorphism_impl(pgb_module *m, int64_t p, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx_big *a, uint64_t a_col,
+                          const pgb_batch *bt) {
+    CHECK_BATCH(bt);
+    CHECK_N(res, "vec_znx_big_automorphism(res)");
+    CHECK_N(a, "vec_znx_big_automorphism(a)");
+    CHECK_COL(res, res_col, "vec_znx_big_automorphism(res)");
+    CHECK_COL(a, a_col, "vec_znx_big_automorphism(a)");
+    PGB_REQUIRE(res->data != a->data, "vec_znx_big_automorphism: res and a must not alias (use the _assign entry)");
+    PGB_REQUIRE((p & 1) != 0, "vec_znx_big_automorphism: the Galois element must be odd");
+    const uint64_t n = m->n, bb = big_bytes(m), mn = umin64(res->size, a->size);
+    LimbSet R = {(char *)res->data + limb_off(n, res->cols, res_col, 0, bb), res->cols * n * bb, bt->stride_res};
+    LimbSet A = {(char *)a->data + limb_off(n, a->cols, a_col, 0, bb), a->cols * n * bb, bt->stride_a};
+    PGB_TRY(znx_automorphism(m, R, A, p, (uint32_t)mn, (uint32_t)bt->count, m->flavour == PGB_NTT120));
+    return raw_limbs(m, true, shift(R, mn), shift(R, mn), n * bb, (uint32_t)(res->size - mn), (uint32_t)bt->count);
+}
+extern "C" int pgb_vec_znx_big_automorphism(pgb_module *m, int64_t p, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx_big *a,
+                                            uint64_t a_col) {
+    PGB_TRY(big_automorphism_impl(m, p, res, res_col, a, a_col, &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_vec_znx_big_automorphism_batched(pgb_module *m, int64_t p, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx_big *a,
+                                                    uint64_t a_col, const pgb_batch *bt) {
+    return big_automorphism_impl(m, p, res, res_col, a, a_col, bt);
+}
+// vec_znx_big_automorphism_assign (ntt120/vec_znx_big.rs:1499-1529): the reference permutes through an n-element tmp; here the column is
+// staged in a stream-ordered temporary and permuted back
+extern "C" size_t pgb_vec_znx_big_automorphism_assign_tmp_bytes(const pgb_module *m) { return m->n * big_bytes(m); }
+extern "C" int pgb_vec_znx_big_automorphism_assign(pgb_module *m, int64_t p, pgb_vec_znx_big *res, uint64_t res_col) {
+    CHECK_N(res, "vec_znx_big_automorphism_assign(res)");
+    CHECK_COL(res, res_col, "vec_znx_big_automorphism_assign(res)");
+    PGB_REQUIRE((p & 1) != 0, "vec_znx_big_automorphism_assign: the Galois element must be odd");
+    const uint64_t n = m->n, bb = big_bytes(m);
+    if (res->size == 0) return PGB_OK;
+    char *tmp = nullptr;
+    PGB_CHECK_CUDA(cudaMallocAsync(&tmp, res->size * n * bb, m->stream));
+    LimbSet R = {(char *)res->data + limb_off(n, res->cols, res_col, 0, bb), res->cols * n * bb, 0};
+    LimbSet Tm = {tmp, n * bb, 0};
+    int s = raw_limbs(m, false, Tm, R, n * bb, (uint32_t)res->size, 1);
+    if (s == PGB_OK) s = znx_automorphism(m, R, Tm, p, (uint32_t)res->size, 1, m->flavour == PGB_NTT120);
+    cudaFreeAsync(tmp, m->stream);
+    PGB_TRY(s);
+    return sync_if(m, true);
+}
+
+// vec_znx_rsh_assign (reference/vec_znx/shift.rs:186-243)
+int rsh_assign_impl(pgb_module *m, uint64_t base2k, uint64_t k, pgb_vec_znx *res, uint64_t res_col, const pgb_batch *bt) {
+    CHECK_BATCH(bt);
+    CHECK_N(res, "vec_znx_rsh_assign(res)");
+    CHECK_COL(res, res_col, "vec_znx_rsh_assign(res)");
+    PGB_REQUIRE(base2k >= 1 && base2k <= 63, "vec_znx_rsh_assign: base2k must be in [1, 63]");
+    PGB_REQUIRE(div_ceil64(k, base2k) <= res->size, "vec_znx_rsh_assign: shift of %llu bits exceeds the %llu limbs of res (the reference panics)",
+                (unsigned long long)k, (unsigned long long)res->size);
+    const uint64_t n = m->n;
+    LimbSet R = {(char *)res->data + limb_off(n, res->cols, res_col, 0, 8), res->cols * n * 8, bt->stride_res};
+    return znx_rsh_assign(m, R, (int)res->size, (int)base2k, (int)k, (uint32_t)bt->count);
+}
+extern "C" int pgb_vec_znx_rsh_assign(pgb_module *m, uint64_t base2k, uint64_t k, pgb_vec_znx *res, uint64_t res_col) {
+    PGB_TRY(rsh_assign_impl(m, base2k, k, res, res_col, &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_vec_znx_rsh_assign_batched(pgb_module *m, uint64_t base2k, uint64_t k, pgb_vec_znx *res, uint64_t res_col, const pgb_batch *bt) {
+    return rsh_assign_impl(m, base2k, k, res, res_col, bt);
+}
+
 extern "C" int pgb_vec_znx_automorphism(pgb_module *m, int64_t p, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col) {
     PGB_TRY(automorphism_impl(m, p, res, res_col, a, a_col, &ONE));
     return sync_if(m, true);

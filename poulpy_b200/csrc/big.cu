@@ -383,22 +383,79 @@ struct AutoArgs {
     uint32_t n;
     long long p;
 };
-__global__ void __launch_bounds__(256) znx_automorphism_kernel(AutoArgs q) {
+template <typename T> __global__ void __launch_bounds__(256) znx_automorphism_kernel(AutoArgs q) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= q.n) return;
-    const long long *src = reinterpret_cast<const long long *>(q.a.base + (size_t)blockIdx.z * q.a.batch_stride + (size_t)blockIdx.y * q.a.limb_stride);
-    long long *dst = reinterpret_cast<long long *>(q.dst.base + (size_t)blockIdx.z * q.dst.batch_stride + (size_t)blockIdx.y * q.dst.limb_stride);
+    const T *src = reinterpret_cast<const T *>(q.a.base + (size_t)blockIdx.z * q.a.batch_stride + (size_t)blockIdx.y * q.a.limb_stride);
+    T *dst = reinterpret_cast<T *>(q.dst.base + (size_t)blockIdx.z * q.dst.batch_stride + (size_t)blockIdx.y * q.dst.limb_stride);
     const uint32_t mask = 2 * q.n - 1, p2n = (uint32_t)(q.p & (long long)mask);
     const uint32_t k = (uint32_t)(((unsigned long long)i * p2n) & mask);
-    const long long v = src[i];
+    const T v = src[i];
     if (k < q.n) dst[k] = v;
-    else dst[k - q.n] = (long long)(0ull - (unsigned long long)v);
+    else dst[k - q.n] = (T)((typename BT<T>::U)0 - (typename BT<T>::U)v); // wrapping_neg
 }
-int znx_automorphism(pgb_module *m, LimbSet dst, LimbSet a, long long p, uint32_t jobs, uint32_t batch) {
+// big_is_i128: the limbs are i128 (NTT120 VecZnxBig, ntt120/vec_znx_big.rs:1462-1497) instead of i64 (VecZnx and the FFT64 VecZnxBig)
+int znx_automorphism(pgb_module *m, LimbSet dst, LimbSet a, long long p, uint32_t jobs, uint32_t batch, bool big_is_i128) {
     if (jobs == 0 || batch == 0) return PGB_OK;
     ProfScope _ps(m, PROF_ELEMENTWISE);
     AutoArgs q = {dst, a, (uint32_t)m->n, p};
-    znx_automorphism_kernel<<<dim3(((uint32_t)m->n + 255) / 256, jobs, batch), 256, 0, m->stream>>>(q);
+    const dim3 grid(((uint32_t)m->n + 255) / 256, jobs, batch);
+    if (big_is_i128) znx_automorphism_kernel<i128><<<grid, 256, 0, m->stream>>>(q);
+    else znx_automorphism_kernel<long long><<<grid, 256, 0, m->stream>>>(q);
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+
+// vec_znx_rsh_assign (reference/vec_znx/shift.rs:186-243): right shift by k bits in base 2^K, in place, one thread per coefficient walking
+// the limbs with the carry in a register.  The three loops follow the reference verbatim, including the order of its last loop (zero
+// limb j, then step on limb steps-1-j), which is only the arithmetic shift for steps <= 1 or k a multiple of K.
+struct RshArgs {
+    LimbSet r;
+    uint32_t n;
+    int size, K, k;
+};
+__global__ void __launch_bounds__(256) znx_rsh_assign_kernel(RshArgs q) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q.n) return;
+    char *rb = q.r.base + (size_t)blockIdx.y * q.r.batch_stride;
+#define R_AT(j) (reinterpret_cast<long long *>(rb + (size_t)(j) * q.r.limb_stride)[i])
+    typedef long long T;
+    const int K = q.K, size = q.size, k_rem = q.k % K;
+    const int steps = q.k / K + (k_rem ? 1 : 0), lsh = (K - k_rem) % K, w = lsh == 0 ? K : K - lsh;
+    T c = 0;
+    for (int j = 0; j < steps; j++) {
+        const T x = R_AT(size - j - 1);
+        const T d = get_digit<T>(w, x), co = get_carry<T>(w, x, d);
+        if (j == 0) c = co;
+        else {
+            const T s = wadd<T>(wshl<T>(d, lsh), c);
+            c = wadd<T>(co, get_carry<T>(K, s, get_digit<T>(K, s)));
+        }
+    }
+    for (int j = 0; j < size - steps; j++) {
+        const T x = R_AT(size - steps - j - 1);
+        const T d = get_digit<T>(w, x), co = get_carry<T>(w, x, d);
+        const T s = wadd<T>(wshl<T>(d, lsh), c);
+        const T out = get_digit<T>(K, s);
+        c = wadd<T>(co, get_carry<T>(K, s, out));
+        R_AT(size - j - 1) = out;
+    }
+    for (int j = 0; j < steps; j++) {
+        R_AT(j) = 0;
+        const T x = R_AT(steps - j - 1);
+        const T d = get_digit<T>(w, x);
+        const T s = wadd<T>(wshl<T>(d, lsh), c);
+        const T out = get_digit<T>(K, s);
+        if (j != 0) c = wadd<T>(get_carry<T>(w, x, d), get_carry<T>(K, s, out));
+        R_AT(steps - j - 1) = out;
+    }
+#undef R_AT
+}
+int znx_rsh_assign(pgb_module *m, LimbSet r, int size, int base2k, int k, uint32_t batch) {
+    if (size == 0 || batch == 0) return PGB_OK;
+    ProfScope _ps(m, PROF_NORMALIZE);
+    RshArgs q = {r, (uint32_t)m->n, size, base2k, k};
+    znx_rsh_assign_kernel<<<dim3(((uint32_t)m->n + 255) / 256, batch), 256, 0, m->stream>>>(q);
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;
 }

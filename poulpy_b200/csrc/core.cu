@@ -491,6 +491,144 @@ extern "C" int pgb_glwe_automorphism_batched(pgb_module *m, pgb_vec_znx *res, ui
     return PGB_OK;
 }
 
+// ---- glwe_automorphism_add_assign (poulpy-core/src/automorphism/glwe_ct.rs:142-183) and glwe_trace_assign
+// (poulpy-core/src/glwe_trace.rs:129-175), batched and device resident.  The limb-wise HAL sequence of the reference:
+//   res_big = glwe_keyswitch_internal(res_dft, res, key); per column: big_automorphism(p), big_add_small_assign(res column),
+//   big_normalize back into res.  The permutation is out of place into a second big buffer instead of through an n-element tmp.
+extern "C" size_t pgb_glwe_automorphism_add_assign_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t res_base2k, const pgb_vmp_pmat *key,
+                                                             uint64_t key_base2k, uint64_t dsize, uint64_t batch) {
+    const uint64_t n = m->n, pb = prep_bytes(m), bb = big_bytes(m);
+    const uint64_t rank_in = key->cols_in, cols = key->cols_out;
+    const uint64_t in_size = res_base2k == key_base2k ? res_size : conv_size(res_size, res_base2k, key_base2k);
+    uint64_t t = 0;
+    t += align_up(batch * n * cols * key->size * pb);                                   // res_dft / res_big
+    t += align_up(batch * n * cols * key->size * bb);                                   // permuted big
+    t += align_up(batch * n * rank_in * in_size * pb);                                  // a_dft
+    if (res_base2k != key_base2k) t += align_up(batch * n * cols * in_size * 8);        // res_conv
+    if (dsize > 1) t += align_up(batch * n * rank_in * div_ceil64(in_size, dsize) * pb) + align_up(batch * n * cols * key->size * pb);
+    return t + ALIGN;
+}
+extern "C" int pgb_glwe_automorphism_add_assign_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, const pgb_vmp_pmat *key,
+                                                        uint64_t key_base2k, int64_t p, uint64_t dsize, const pgb_batch *bt, void *scratch,
+                                                        size_t scratch_len) {
+    PGB_REQUIRE(bt && bt->count >= 1 && bt->count <= 65535, "glwe_automorphism_add_assign: batch count must be in [1, 65535]");
+    PGB_REQUIRE(res->n == m->n && key->n == m->n, "glwe_automorphism_add_assign: ring degree mismatch");
+    PGB_REQUIRE(res->cols == key->cols_in + 1 && res->cols == key->cols_out, "glwe_automorphism_add_assign: res.rank() != key.rank()");
+    PGB_REQUIRE(dsize >= 1, "glwe_automorphism_add_assign: dsize must be >= 1");
+    const size_t need = pgb_glwe_automorphism_add_assign_tmp_bytes(m, res->size, res_base2k, key, key_base2k, dsize, bt->count);
+    if (scratch_len < need) {
+        pgb_set_error("glwe_automorphism_add_assign: scratch of %zu bytes < required %zu", scratch_len, need);
+        return PGB_ERR_SCRATCH;
+    }
+    const uint64_t n = m->n, pb = prep_bytes(m), bb = big_bytes(m), B = bt->count, rank_in = key->cols_in, cols = key->cols_out;
+    Arena ar = {(char *)scratch, scratch_len, 0};
+    const uint64_t res_dft_bs = n * cols * key->size * pb, big2_bs = n * cols * key->size * bb;
+    pgb_vec_znx_dft res_dft = mk(ar.take(B * res_dft_bs), n, cols, key->size);
+    pgb_vec_znx_big big2 = mk(ar.take(B * big2_bs), n, cols, key->size);
+    pgb_vec_znx ain = *res;
+    uint64_t ain_bs = bt->stride_res;
+    if (res_base2k != key_base2k) { // (:161-168) res_conv = glwe_normalize(res) at the key's base2k
+        const uint64_t cs = conv_size(res->size, res_base2k, key_base2k);
+        ain_bs = n * res->cols * cs * 8;
+        ain = mk(ar.take(B * ain_bs), n, res->cols, cs);
+        pgb_batch btn = {B, ain_bs, bt->stride_res, 0};
+        for (uint64_t i = 0; i < res->cols; i++) PGB_TRY(big_normalize_impl(m, &ain, key_base2k, 0, i, res, res_base2k, i, 0, false, &btn));
+    }
+    // glwe_keyswitch_internal (keyswitching/glwe.rs:207-239)
+    const uint64_t a_dft_bs = n * rank_in * ain.size * pb;
+    pgb_vec_znx_dft a_dft = mk(ar.take(B * a_dft_bs), n, rank_in, ain.size);
+    pgb_batch btd = {B, a_dft_bs, ain_bs, 0};
+    for (uint64_t c = 0; c < rank_in; c++) PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &a_dft, c, &ain, c + 1, &btd));
+    pgb_vec_znx_dft ai = a_dft, tmp = res_dft;
+    uint64_t ai_bs = 0, tmp_bs = 0;
+    if (dsize > 1) {
+        const uint64_t ai_max = umin64(div_ceil64(ain.size, dsize), key->rows);
+        ai_bs = n * rank_in * ai_max * pb;
+        ai = mk(ar.take(B * ai_bs), n, rank_in, ai_max);
+        tmp_bs = res_dft_bs;
+        tmp = mk(ar.take(B * tmp_bs), n, cols, key->size);
+        PGB_REQUIRE(ai.data && tmp.data, "glwe_automorphism_add_assign: scratch exhausted");
+        PGB_CHECK_CUDA(cudaMemsetAsync(ai.data, 0, B * ai_bs, m->stream));
+        PGB_CHECK_CUDA(cudaMemsetAsync(tmp.data, 0, B * tmp_bs, m->stream));
+    }
+    PGB_CHECK_CUDA(cudaMemsetAsync(res_dft.data, 0, B * res_dft_bs, m->stream));
+    PGB_TRY(gadget_product(m, &res_dft, &a_dft, key, dsize, true, &ai, &tmp, res_dft_bs, a_dft_bs, ai_bs, tmp_bs, B));
+    pgb_batch btc = {B, res_dft_bs, 0, 0};
+    PGB_TRY(pgb_vec_znx_idft_apply_consume_batched(m, &res_dft, &btc));
+    pgb_vec_znx_big res_big = res_dft;
+    pgb_batch bts = {B, res_dft_bs, ain_bs, 0};
+    PGB_TRY(big_add_small_impl(m, &res_big, 0, &ain, 0, &bts));
+    for (uint64_t i = 0; i < res->cols; i++) { // (:170-181)
+        pgb_batch bta = {B, big2_bs, res_dft_bs, 0};
+        PGB_TRY(big_automorphism_impl(m, p, &big2, i, &res_big, i, &bta));
+        pgb_batch bt2 = {B, big2_bs, ain_bs, 0};
+        PGB_TRY(big_add_small_impl(m, &big2, i, &ain, i, &bt2));
+        pgb_batch btn = {B, bt->stride_res, big2_bs, 0};
+        PGB_TRY(big_normalize_impl(m, res, res_base2k, 0, i, &big2, key_base2k, i, 0, true, &btn));
+    }
+    return PGB_OK;
+}
+
+// trace_galois_elements (glwe_trace.rs:34-44): -1 for i = 0, GALOISGENERATOR^(2^(i-1)) mod 2n otherwise (layouts/module.rs:214-226)
+extern "C" int64_t pgb_trace_galois_element(const pgb_module *m, uint64_t i) {
+    if (i == 0) return -1;
+    uint64_t r = 1, x = 5, e = (uint64_t)1 << (i - 1);
+    while (e) {
+        if (e & 1) r *= x;
+        x *= x;
+        e >>= 1;
+    }
+    return (int64_t)(r & (2 * m->n - 1));
+}
+extern "C" size_t pgb_glwe_trace_assign_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t res_base2k, const pgb_vmp_pmat *key,
+                                                  uint64_t key_base2k, uint64_t dsize, uint64_t batch) {
+    const uint64_t in_size = res_base2k == key_base2k ? res_size : conv_size(res_size, res_base2k, key_base2k);
+    size_t t = pgb_glwe_automorphism_add_assign_tmp_bytes(m, in_size, key_base2k, key, key_base2k, dsize, batch);
+    if (res_base2k != key_base2k) t += align_up(batch * m->n * key->cols_out * in_size * 8);
+    return t + ALIGN;
+}
+// keys: host array of log_n prepared automorphism keys (same shape), keys[i] for pgb_trace_galois_element(i); entries below `skip` unread
+extern "C" int pgb_glwe_trace_assign_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, uint64_t skip, const pgb_vmp_pmat *keys,
+                                             uint64_t nkeys, uint64_t key_base2k, uint64_t dsize, const pgb_batch *bt, void *scratch,
+                                             size_t scratch_len) {
+    PGB_REQUIRE(bt && bt->count >= 1 && bt->count <= 65535, "glwe_trace: batch count must be in [1, 65535]");
+    PGB_REQUIRE(res->n == m->n, "glwe_trace: ring degree mismatch");
+    PGB_REQUIRE(skip <= (uint64_t)m->log_n, "glwe_trace: skip > log_n");                      // glwe_trace.rs:144
+    PGB_REQUIRE(nkeys >= (uint64_t)m->log_n, "glwe_trace: needs log_n automorphism keys");
+    if (skip == (uint64_t)m->log_n) return PGB_OK;
+    const pgb_vmp_pmat *k0 = &keys[skip];
+    const size_t need = pgb_glwe_trace_assign_tmp_bytes(m, res->size, res_base2k, k0, key_base2k, dsize, bt->count);
+    if (scratch_len < need) {
+        pgb_set_error("glwe_trace: scratch of %zu bytes < required %zu", scratch_len, need);
+        return PGB_ERR_SCRATCH;
+    }
+    const uint64_t n = m->n, B = bt->count;
+    pgb_vec_znx cur = *res;
+    uint64_t cur_bs = bt->stride_res;
+    char *sc = (char *)scratch;
+    size_t sc_len = scratch_len;
+    if (res_base2k != key_base2k) { // (:156-165) work on a copy at the key's base2k
+        const uint64_t cs = conv_size(res->size, res_base2k, key_base2k);
+        cur_bs = n * res->cols * cs * 8;
+        cur = mk(sc, n, res->cols, cs);
+        sc += align_up(B * cur_bs);
+        sc_len -= (size_t)align_up(B * cur_bs);
+        pgb_batch btn = {B, cur_bs, bt->stride_res, 0};
+        for (uint64_t i = 0; i < res->cols; i++) PGB_TRY(big_normalize_impl(m, &cur, key_base2k, 0, i, res, res_base2k, i, 0, false, &btn));
+    }
+    pgb_batch btc = {B, cur_bs, 0, 0};
+    for (uint64_t i = skip; i < (uint64_t)m->log_n; i++) { // (:166-177)
+        for (uint64_t c = 0; c < cur.cols; c++) PGB_TRY(rsh_assign_impl(m, key_base2k, 1, &cur, c, &btc)); // glwe_rsh(1)
+        PGB_TRY(pgb_glwe_automorphism_add_assign_batched(m, &cur, key_base2k, &keys[i], key_base2k, pgb_trace_galois_element(m, i), dsize, &btc,
+                                                         sc, sc_len));
+    }
+    if (res_base2k != key_base2k) {
+        pgb_batch btn = {B, bt->stride_res, cur_bs, 0};
+        for (uint64_t i = 0; i < res->cols; i++) PGB_TRY(big_normalize_impl(m, res, res_base2k, 0, i, &cur, key_base2k, i, 0, false, &btn));
+    }
+    return PGB_OK;
+}
+
 // ---- host-buffer front ends ---------------------------------------------------------------------------------------------------
 // Chunked three-stage pipeline (H2D on aux stream 0, compute on the module stream, D2H on aux stream 1), double buffered.
 static int ensure_ws(pgb_module *m, size_t len) {

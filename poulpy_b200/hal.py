@@ -68,12 +68,14 @@ def lib():
         _lib.pgb_module_launch_count.argtypes = [C.c_void_p]
         _lib.pgb_module_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         _lib.pgb_module_sync.argtypes = [C.c_void_p]
+        _lib.pgb_trace_galois_element.restype = C.c_int64
         _lib.pgb_profile_category_name.restype = C.c_char_p
         _lib.pgb_profile_enable.argtypes = [C.c_void_p, C.c_int]
         _lib.pgb_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
         for name in ("pgb_glwe_keyswitch_tmp_bytes", "pgb_glwe_external_product_tmp_bytes", "pgb_cggi_blind_rotate_tmp_bytes",
                      "pgb_cggi_blind_rotate_standard_tmp_bytes", "pgb_vmp_apply_dft_tmp_bytes", "pgb_glwe_tensor_apply_tmp_bytes",
-                     "pgb_glwe_tensor_relinearize_tmp_bytes", "pgb_glwe_automorphism_tmp_bytes",
+                     "pgb_glwe_tensor_relinearize_tmp_bytes", "pgb_glwe_automorphism_tmp_bytes", "pgb_glwe_automorphism_add_assign_tmp_bytes",
+                     "pgb_glwe_trace_assign_tmp_bytes", "pgb_vec_znx_big_automorphism_assign_tmp_bytes",
                      "pgb_bytes_of_vmp_pmat", "pgb_size_of_scalar_prep", "pgb_size_of_scalar_big"):
             getattr(_lib, name).restype = C.c_size_t
     return _lib
@@ -576,6 +578,51 @@ class Module:
         _check(lib().pgb_glwe_automorphism_batched(self._h, C.byref(r), _u64(res_base2k), C.byref(av), _u64(a_base2k), C.byref(ks),
                                                    _u64(key_base2k), C.c_int64(p), _u64(dsize), C.byref(bt), C.c_void_p(scratch.ptr),
                                                    C.c_size_t(scratch.nbytes)))
+        return scratch
+
+    # --- trace (poulpy-core/src/glwe_trace.rs) and its HAL pieces ---------------------------------------------------------------------
+    def vec_znx_rsh_assign(self, base2k, k, res, res_col):
+        r = res.struct()
+        if res.batch > 1:
+            bt = _BT(res.batch, res.batch_stride, 0, 0)
+            _check(lib().pgb_vec_znx_rsh_assign_batched(self._h, _u64(base2k), _u64(k), C.byref(r), _u64(res_col), C.byref(bt)))
+        else:
+            _check(lib().pgb_vec_znx_rsh_assign(self._h, _u64(base2k), _u64(k), C.byref(r), _u64(res_col)))
+
+    def vec_znx_big_automorphism(self, p, res, res_col, a, a_col):
+        r, av = res.struct(), a.struct()
+        _check(lib().pgb_vec_znx_big_automorphism(self._h, C.c_int64(p), C.byref(r), _u64(res_col), C.byref(av), _u64(a_col)))
+
+    def vec_znx_big_automorphism_assign(self, p, res, res_col):
+        r = res.struct()
+        _check(lib().pgb_vec_znx_big_automorphism_assign(self._h, C.c_int64(p), C.byref(r), _u64(res_col)))
+
+    def glwe_automorphism_add_assign(self, res: VecZnx, res_base2k, key: VmpPMat, key_base2k, p, dsize=1, scratch: DevBuf = None):
+        ks = key.struct()
+        need = lib().pgb_glwe_automorphism_add_assign_tmp_bytes(self._h, _u64(res.size), _u64(res_base2k), C.byref(ks), _u64(key_base2k),
+                                                                _u64(dsize), _u64(res.batch))
+        if scratch is None or scratch.nbytes < need:
+            scratch = DevBuf(need)
+        r = res.struct()
+        bt = _BT(res.batch, res.batch_stride, 0, 0)
+        _check(lib().pgb_glwe_automorphism_add_assign_batched(self._h, C.byref(r), _u64(res_base2k), C.byref(ks), _u64(key_base2k), C.c_int64(p),
+                                                              _u64(dsize), C.byref(bt), C.c_void_p(scratch.ptr), C.c_size_t(scratch.nbytes)))
+        return scratch
+
+    def trace_galois_element(self, i):
+        return int(lib().pgb_trace_galois_element(self._h, _u64(i)))
+
+    def glwe_trace_assign(self, res: VecZnx, res_base2k, skip, keys, key_base2k, dsize=1, scratch: DevBuf = None):
+        """keys: list of log_n prepared automorphism keys, keys[i] for trace_galois_element(i)."""
+        arr = (_PM * len(keys))(*[k.struct() for k in keys])
+        need = lib().pgb_glwe_trace_assign_tmp_bytes(self._h, _u64(res.size), _u64(res_base2k), C.byref(arr[min(skip, len(keys) - 1)]),
+                                                     _u64(key_base2k), _u64(dsize), _u64(res.batch))
+        if scratch is None or scratch.nbytes < need:
+            scratch = DevBuf(need)
+        r = res.struct()
+        bt = _BT(res.batch, res.batch_stride, 0, 0)
+        _check(lib().pgb_glwe_trace_assign_batched(self._h, C.byref(r), _u64(res_base2k), _u64(skip), arr, _u64(len(keys)), _u64(key_base2k),
+                                                   _u64(dsize), C.byref(bt), C.c_void_p(scratch.ptr), C.c_size_t(scratch.nbytes)))
         return scratch
 
     def cggi_x_pow_a(self) -> SvpPPol:
