@@ -393,3 +393,32 @@ def test_fft64_gadget_bench_shape():
         finally:
             os.environ.pop("PGB_NO_FUSION", None)
         assert np.array_equal(g.vec_znx_to_numpy(res_g), want), env
+
+
+@pytest.mark.parametrize("fl", FLAVOURS)
+@pytest.mark.parametrize("ext", [False, True])
+def test_full_bench_batch_4096(fl, ext):
+    """BASELINE's full batch (4096 ciphertexts, key-switch at n = 4096 / external product at n = 2048, base2k = 18): 64 distinct
+    ciphertexts replicated 64 times in shuffled order, every one of the 4096 outputs compared bit for bit with the oracle's result for
+    its source -- the persistent loops of the single-kernel paths run their full length (28-37 ciphertexts per cluster / CTA)."""
+    n, k, batch, distinct = (2048 if ext else 4096), 18, 4096, 64
+    g, o = pb.Module(n, fl), O.OracleModule(n, fl)
+    rng = np.random.default_rng(1500 + fl + 2 * ext)
+    if ext:
+        pg, po = _key(g, o, rng, 3, 2, 2, 3, k)
+    else:
+        pg, po = _key(g, o, rng, 3, 1, 2, 4, k)
+    src = fill_uniform(rng, (distinct, 3, 2, n), k)
+    want = np.zeros((distinct, 3, 2, n), dtype=np.int64)
+    if ext:
+        o.glwe_external_product_batch(want, k, src, k, po, k)
+    else:
+        o.glwe_keyswitch_batch(want, k, src, k, po, k)
+    perm = rng.permutation(batch) % distinct
+    a = g.vec_znx_from_numpy(src[perm])
+    res = g.vec_znx_alloc(2, 3, batch)
+    (g.glwe_external_product if ext else g.glwe_keyswitch)(res, k, a, k, pg, k)
+    g.sync()
+    got = g.vec_znx_to_numpy(res)
+    bad = [b for b in range(batch) if not np.array_equal(got[b], want[perm[b]])]
+    assert not bad, (bad[:10], len(bad))
