@@ -188,7 +188,8 @@ template <int L> static int flaunch_fwd(pgb_module *m, const FftJobs &jb) {
     constexpr int LPC = flpc_for<L>();
     typedef FGeo<L> G;
     size_t smem = (size_t)LPC * G::PLANE * sizeof(double2);
-    static bool attr_set = false;
+    static bool attr_set_dev[32] = {}; // per device: function attributes are per device
+    bool &attr_set = attr_set_dev[m->device & 31];
     if (!attr_set) {
         PGB_CHECK_CUDA(cudaFuncSetAttribute(fft64_fwd_kernel<L, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
@@ -204,7 +205,8 @@ template <int L> static int flaunch_inv(pgb_module *m, const FftJobs &jb) {
     constexpr int LPC = flpc_for<L>();
     typedef FGeo<L> G;
     size_t smem = (size_t)LPC * G::PLANE * sizeof(double2);
-    static bool attr_set = false;
+    static bool attr_set_dev[32] = {}; // per device: function attributes are per device
+    bool &attr_set = attr_set_dev[m->device & 31];
     if (!attr_set) {
         PGB_CHECK_CUDA(cudaFuncSetAttribute(fft64_inv_kernel<L, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
@@ -314,7 +316,8 @@ __global__ void __launch_bounds__(256) fft64_inv_top8_kernel(LimbSet io, int job
 template <int L> static int flaunch_fwd_sub(pgb_module *m, LimbSet out, int jobs_per_batch, int total) {
     typedef FGeo<L> G;
     size_t smem = (size_t)G::PLANE * sizeof(double2);
-    static bool attr_set = false;
+    static bool attr_set_dev[32] = {}; // per device: function attributes are per device
+    bool &attr_set = attr_set_dev[m->device & 31];
     if (!attr_set) {
         PGB_CHECK_CUDA(cudaFuncSetAttribute(fft64_fwd_sub_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
@@ -328,7 +331,8 @@ template <int L> static int flaunch_fwd_sub(pgb_module *m, LimbSet out, int jobs
 template <int L> static int flaunch_inv_sub(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int total) {
     typedef FGeo<L> G;
     size_t smem = (size_t)G::PLANE * sizeof(double2);
-    static bool attr_set = false;
+    static bool attr_set_dev[32] = {}; // per device: function attributes are per device
+    bool &attr_set = attr_set_dev[m->device & 31];
     if (!attr_set) {
         PGB_CHECK_CUDA(cudaFuncSetAttribute(fft64_inv_sub_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;

@@ -29,7 +29,8 @@ namespace {
 struct FGadgetArgs {
     const char *in;  unsigned long long in_bs;   // GLWE inputs (i64), limb (j, col) at ((j * in_cols + col) * n) words
     char *res;       unsigned long long res_bs;  // GLWE outputs (i64), limb (j, col) at ((j * cols_out + col) * n) words
-    const double *pmat;                          // prepared matrix [row][C][re(m) | im(m)]
+    const double *pmat;                          // key in the kernel's layout (fft64_gadget_key_kernel): [row][C][re | im][q][t] double2
+    const double2 *twl_f, *twl_i;                // last forward / first inverse pass twiddles, [7][T]: thread t's seven values, coalesced
     int in_cols, row_cols, row_col0, R, C, cols_out;
     int small_size;                              // limbs of input column 0 added to output column 0 (key-switch), 0 = none
     int K, S, res_size, batch;
@@ -45,22 +46,56 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *gptr, uint32_t byte
 }
 __device__ __forceinline__ void group_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
+// The last forward pass and the first inverse pass give thread t the node hi = 2^(L-3) | t: its seven twiddles tw[hi], tw[2hi], tw[2hi+1],
+// tw[4hi..4hi+3] sit 16 / 32 / 64 bytes apart between neighbouring threads, so a warp-wide 128-bit load of them touches 4x the lines it
+// needs (the L1 data pipe was at 80 % with these and the key loads).  `twl` holds the same values as [7][T]: one coalesced load each.
+__device__ __forceinline__ void load_tw7(double2 (&w)[7], const double2 *__restrict__ twl, int T, int t) {
+#pragma unroll
+    for (int j = 0; j < 7; j++) w[j] = __ldg(twl + j * T + t);
+}
+__device__ __forceinline__ void fct_radix8_w(double2 (&x)[8], const double2 (&w)[7]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) fct_bf(x[j], x[j + 4], w[0]);
+    fct_bf(x[0], x[2], w[1]);
+    fct_bf(x[1], x[3], w[1]);
+    fct_bf(x[4], x[6], w[2]);
+    fct_bf(x[5], x[7], w[2]);
+#pragma unroll
+    for (int j = 0; j < 4; j++) fct_bf(x[2 * j], x[2 * j + 1], w[3 + j]);
+}
+__device__ __forceinline__ void fgs_radix8_w(double2 (&x)[8], const double2 (&w)[7]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) fgs_bf(x[2 * j], x[2 * j + 1], w[3 + j]);
+    fgs_bf(x[0], x[2], w[1]);
+    fgs_bf(x[1], x[3], w[1]);
+    fgs_bf(x[4], x[6], w[2]);
+    fgs_bf(x[5], x[7], w[2]);
+#pragma unroll
+    for (int j = 0; j < 4; j++) fgs_bf(x[j], x[j + 4], w[0]);
+}
+
 template <int L, int L0, bool TWS> struct GFwd {
-    static __device__ __forceinline__ void run(double2 *buf, const double2 *tw, int t, int slot) {
+    static __device__ __forceinline__ void run(double2 *buf, const double2 *tw, const double2 *twl, int t, int slot) {
         constexpr int SL = L - L0 - 3;
         const int a = t >> SL, b = t & ((1 << SL) - 1), base = (a << (SL + 3)) | b;
         double2 x[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) x[j] = buf[FPAD(base + (j << SL))];
-        fct_radix8<3, TWS>(x, tw, (1u << L0) | (uint32_t)a);
+        if (SL == 0) {
+            double2 w[7];
+            load_tw7(w, twl, FGeo<L>::T, t);
+            fct_radix8_w(x, w);
+        } else {
+            fct_radix8<3, TWS>(x, tw, (1u << L0) | (uint32_t)a);
+        }
 #pragma unroll
         for (int j = 0; j < 8; j++) buf[FPAD(base + (j << SL))] = x[j];
         if (SL > 0) slot_sync<FGeo<L>::T>(slot); // after the last pass every thread only re-reads its own eight values
-        GFwd<L, (L0 + 3 < L) ? L0 + 3 : L, TWS>::run(buf, tw, t, slot);
+        GFwd<L, (L0 + 3 < L) ? L0 + 3 : L, TWS>::run(buf, tw, twl, t, slot);
     }
 };
 template <int L, bool TWS> struct GFwd<L, L, TWS> {
-    static __device__ __forceinline__ void run(double2 *, const double2 *, int, int) {}
+    static __device__ __forceinline__ void run(double2 *, const double2 *, const double2 *, int, int) {}
 };
 template <int L, int L0, bool TWS> struct GInv {
     static __device__ __forceinline__ void run(double2 *buf, const double2 *tw, int t, int slot) {
@@ -149,7 +184,7 @@ fft64_gadget_kernel(const __grid_constant__ FGadgetArgs p, const double2 *__rest
 #pragma unroll
             for (int jj = 0; jj < 8; jj++) buf[FPAD(t + jj * T)] = x[jj];
             slot_sync<T>(slot);
-            GFwd<LM, G::R0, TWS>::run(buf, twf, t, slot);
+            GFwd<LM, G::R0, TWS>::run(buf, twf, p.twl_f, t, slot);
         }
         __syncthreads(); // the products read every plane
         // ---- output limbs, least significant first: products -> inverse transform -> round -> carry chain ------------------------------
@@ -164,17 +199,16 @@ fft64_gadget_kernel(const __grid_constant__ FGadgetArgs p, const double2 *__rest
                 const int poly = j * cols_out + c;
 #pragma unroll
                 for (int jj = 0; jj < 8; jj++) x[jj] = make_double2(0.0, 0.0);
-                const double *kp = p.pmat + (size_t)poly * N + 8 * t;
-                const size_t krow = (size_t)p.C * N;
-                // rows accumulate in row order (reim4_add_mul, reim4/arithmetic_ref.rs:223-232), FMA-contracted; the key values come from L2.
-                // (Requesting three rows x four frequencies together was measured: no gain, the phase is not bound by this latency.)
+                const double2 *kp = reinterpret_cast<const double2 *>(p.pmat + (size_t)poly * N) + t;
+                const size_t krow = (size_t)p.C * M; // double2 per key row
+                // rows accumulate in row order (reim4_add_mul, reim4/arithmetic_ref.rs:223-232), FMA-contracted; the key values come from L2
+                // in the kernel's own layout: load q of a warp covers 512 contiguous bytes
                 for (int r = 0; r < R; r++) {
-                    const double2 *kr = reinterpret_cast<const double2 *>(kp + (size_t)r * krow);
-                    const double2 *ki = reinterpret_cast<const double2 *>(kp + (size_t)r * krow + M);
+                    const double2 *kr = kp + (size_t)r * krow, *ki = kr + M / 2;
                     double br[8], bi[8];
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        const double2 u = __ldg(kr + q), v = __ldg(ki + q);
+                        const double2 u = __ldg(kr + q * T), v = __ldg(ki + q * T);
                         br[2 * q] = u.x; br[2 * q + 1] = u.y; bi[2 * q] = v.x; bi[2 * q + 1] = v.y;
                     }
                     const double2 *ap = planes + (size_t)r * PL;
@@ -185,7 +219,11 @@ fft64_gadget_kernel(const __grid_constant__ FGadgetArgs p, const double2 *__rest
                         x[jj].y = fma(a.x, bi[jj], x[jj].y); x[jj].y = fma(a.y, br[jj], x[jj].y);
                     }
                 }
-                fgs_radix8<3, TWS>(x, twi, (1u << (LM - 3)) | (uint32_t)t);
+                {
+                    double2 w[7];
+                    load_tw7(w, p.twl_i, T, t);
+                    fgs_radix8_w(x, w);
+                }
 #pragma unroll
                 for (int jj = 0; jj < 8; jj++) work[FPAD(8 * t + jj)] = x[jj];
                 slot_sync<T>(slot);
@@ -267,8 +305,32 @@ fft64_gadget_kernel(const __grid_constant__ FGadgetArgs p, const double2 *__rest
     }
 }
 
+// key re-layout: out[(r * C + p)][part][q][t] (double2) = in[(r * C + p)][part][8t + 2q, 8t + 2q + 1], part = re / im
+__global__ void __launch_bounds__(256) fft64_gadget_key_kernel(const double *__restrict__ in, double2 *__restrict__ out, int M, int polys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x; // output double2 index inside one half poly: q * T + t
+    const int T = M / 8;
+    if (i >= M / 2) return;
+    const int q = i / T, t = i % T;
+    const size_t poly = blockIdx.y;
+    const double *src = in + poly * 2 * (size_t)M + (size_t)blockIdx.z * M + 8 * t + 2 * q;
+    out[poly * (size_t)M + (size_t)blockIdx.z * (M / 2) + i] = make_double2(src[0], src[1]);
+    (void)polys;
+}
+// last-pass twiddles of thread t (node hi = M/8 + t): out[j][t], j = 0..6 <- tw[hi], tw[2hi], tw[2hi+1], tw[4hi .. 4hi+3]
+__global__ void __launch_bounds__(256) fft64_gadget_tw_kernel(const double2 *__restrict__ tw, double2 *__restrict__ out, int T) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int hi = T + t;
+    out[0 * T + t] = tw[hi];
+    out[1 * T + t] = tw[2 * hi];
+    out[2 * T + t] = tw[2 * hi + 1];
+#pragma unroll
+    for (int j = 0; j < 4; j++) out[(3 + j) * T + t] = tw[4 * hi + j];
+}
+
 template <int LM, int LPR, bool TWS> int launch(pgb_module *m, const FGadgetArgs &p, size_t smem) {
-    static int sms = 0;
+    static int sms_dev[32] = {};
+    int &sms = sms_dev[m->device & 31];
     if (!sms) {
         PGB_CHECK_CUDA(cudaFuncSetAttribute(fft64_gadget_kernel<LM, LPR, TWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 << 10)));
         PGB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device));
@@ -333,6 +395,31 @@ int fft64_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_col
     p.in_cols = in_cols; p.row_cols = row_cols; p.row_col0 = row_col0; p.R = R; p.C = C; p.cols_out = cols_out; p.small_size = small_size;
     p.K = base2k; p.S = C / cols_out; p.res_size = res_size; p.batch = batch;
     p.inv_m = 1.0 / (double)(m->n / 2);
+    // workspace: [key in the kernel's layout | last-pass twiddles, forward and inverse]
+    const uint64_t M = m->n / 2, T = M / 8;
+    const uint64_t key_bytes = (uint64_t)R * C * m->n * 8, tw_bytes = 2 * 7 * T * sizeof(double2), need = key_bytes + tw_bytes + 256;
+    if (m->aux_len < need) {
+        if (m->aux_ws) {
+            PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+            cudaFree(m->aux_ws);
+        }
+        m->aux_ws = nullptr;
+        m->aux_len = 0;
+        PGB_CHECK_CUDA(cudaMalloc(&m->aux_ws, need));
+        m->aux_len = need;
+    }
+    double2 *kperm = (double2 *)m->aux_ws, *twl = (double2 *)((char *)m->aux_ws + ((key_bytes + 255) / 256) * 256);
+    { ProfScope _ps(m, PROF_OTHER);
+    fft64_gadget_key_kernel<<<dim3(((unsigned)(M / 2) + 255) / 256, R * C, 2), 256, 0, m->stream>>>((const double *)pmat, kperm, (int)M, R * C);
+    }
+    { ProfScope _ps(m, PROF_OTHER);
+    fft64_gadget_tw_kernel<<<dim3(((unsigned)T + 255) / 256, 1, 1), 256, 0, m->stream>>>(m->fft_fwd, twl, (int)T);
+    fft64_gadget_tw_kernel<<<dim3(((unsigned)T + 255) / 256, 1, 1), 256, 0, m->stream>>>(m->fft_inv, twl + 7 * T, (int)T);
+    }
+    PGB_CHECK_CUDA(cudaGetLastError());
+    p.pmat = (const double *)kperm;
+    p.twl_f = twl;
+    p.twl_i = twl + 7 * T;
     int lpr;
     bool tws;
     size_t smem;

@@ -827,7 +827,8 @@ template <int L> static int launch_fwd(pgb_module *m, const NttJobs &jb) {
     constexpr int LPC = lpc_for<L>();
     typedef Geo<L> G;
     size_t smem = (size_t)LPC * 4 * G::PLANE * sizeof(uint32_t);
-    static bool attr_set = false;
+    static bool attr_set_dev[32] = {}; // per device: function attributes are per device
+    bool &attr_set = attr_set_dev[m->device & 31];
     if (!attr_set) {
         PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_fwd_kernel<L, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
@@ -844,7 +845,8 @@ template <int L> static int launch_inv(pgb_module *m, const NttJobs &jb) {
     constexpr int LPC = lpc_for<L>();
     typedef Geo<L> G;
     size_t smem = (size_t)LPC * 4 * G::PLANE * sizeof(uint32_t);
-    static bool attr_set = false;
+    static bool attr_set_dev[32] = {}; // per device: function attributes are per device
+    bool &attr_set = attr_set_dev[m->device & 31];
     if (!attr_set) {
         PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_inv_kernel<L, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
@@ -878,7 +880,8 @@ template <int L> static int launch_inv(pgb_module *m, const NttJobs &jb) {
 template <int L> static int launch_fwd_sub(pgb_module *m, LimbSet out, int jobs_per_batch, int total_jobs) {
     typedef Geo<L> G;
     size_t smem = (size_t)4 * G::PLANE * sizeof(uint32_t);
-    static bool attr_set = false;
+    static bool attr_set_dev[32] = {}; // per device: function attributes are per device
+    bool &attr_set = attr_set_dev[m->device & 31];
     if (!attr_set) {
         PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_fwd_sub_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
@@ -892,7 +895,8 @@ template <int L> static int launch_fwd_sub(pgb_module *m, LimbSet out, int jobs_
 template <int L> static int launch_inv_sub(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batch, int total_jobs) {
     typedef Geo<L> G;
     size_t smem = (size_t)4 * G::PLANE * sizeof(uint32_t);
-    static bool attr_set = false;
+    static bool attr_set_dev[32] = {}; // per device: function attributes are per device
+    bool &attr_set = attr_set_dev[m->device & 31];
     if (!attr_set) {
         PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_inv_sub_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
@@ -993,7 +997,8 @@ int ntt120_inverse_big(pgb_module *m, LimbSet in, LimbSet out, int jobs_per_batc
 template <int L> static int launch_fused(pgb_module *m, const FusedArgs &p, int batch, const int *skip, int skip_list) {
     typedef Geo<L> G;
     size_t smem = (size_t)4 * G::PLANE * sizeof(uint32_t);
-    static int ctas_per_sm = 0, sms = 0;
+    static int ctas_per_sm_dev[32] = {}, sms_dev[32] = {};
+    int &ctas_per_sm = ctas_per_sm_dev[m->device & 31], &sms = sms_dev[m->device & 31];
     if (!ctas_per_sm) {
         PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_fused_back_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_fused_back_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -1013,7 +1018,8 @@ template <int L> static int launch_fused(pgb_module *m, const FusedArgs &p, int 
 template <int L> static int launch_collapsed(pgb_module *m, const FusedArgs &p, int batch, const int *ok) {
     typedef Geo<L> G;
     size_t smem = (size_t)4 * G::PLANE * sizeof(uint32_t);
-    static int ctas_per_sm = 0, sms = 0;
+    static int ctas_per_sm_dev[32] = {}, sms_dev[32] = {};
+    int &ctas_per_sm = ctas_per_sm_dev[m->device & 31], &sms = sms_dev[m->device & 31];
     if (!ctas_per_sm) {
         PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_collapsed_back_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_collapsed_back_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));

@@ -621,7 +621,8 @@ template <int L> int launch_gadget(pgb_module *m, const GadgetArgs &p, size_t sm
 }
 template <int L, int MB> int launch_gadget_mb(pgb_module *m, const GadgetArgs &p, size_t smem) {
     typedef GGeo<L> G;
-    static int max_clusters = 0;
+    static int max_clusters_dev[32] = {};
+    int &max_clusters = max_clusters_dev[m->device & 31];
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(G::T);
     cfg.dynamicSmemBytes = smem;
