@@ -127,6 +127,8 @@ extern "C" void pgb_module_destroy(pgb_module *m) {
     cudaFree(m->ntt_inv);
     cudaFree(m->fft_fwd);
     cudaFree(m->fft_inv);
+    cudaFree(m->fft_last_f);
+    cudaFree(m->fft_last_i);
     cudaFree(m->ws);
     cudaFree(m->carry_ws);
     cudaFree(m->aux_ws);

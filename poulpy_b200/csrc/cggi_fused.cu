@@ -371,24 +371,32 @@ template <int T> __device__ __forceinline__ void poly_sync(int slot) {
     if (T <= 32) __syncwarp();
     else asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(T) : "memory");
 }
+// tw: shared-memory copy of the first T = m/8 block twiddles (all a pass other than the last one touches); twl: shared-memory copy of
+// the last-pass table [7][T] (fft64.cuh: load_tw7) -- conflict-free where the strided reads of tw[4 hi + j] were 4-way conflicted
 template <int L, int L0> struct SmFwdP {
-    static __device__ __forceinline__ void run(double2 *buf, const double2 *tw, int t, int slot, bool valid) {
+    static __device__ __forceinline__ void run(double2 *buf, const double2 *tw, const double2 *twl, int t, int slot, bool valid) {
         constexpr int SL = L - L0 - 3;
         if (valid) {
             const int a = t >> SL, b = t & ((1 << SL) - 1), base = (a << (SL + 3)) | b;
             double2 x[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) x[j] = buf[FPAD(base + (j << SL))];
-            fct_radix8<3, true>(x, tw, (1u << L0) | (uint32_t)a);
+            if (SL == 0) {
+                double2 w[7];
+                load_tw7<true>(w, twl, FGeo<L>::T, t);
+                fct_radix8_w(x, w);
+            } else {
+                fct_radix8<3, true>(x, tw, (1u << L0) | (uint32_t)a);
+            }
 #pragma unroll
             for (int j = 0; j < 8; j++) buf[FPAD(base + (j << SL))] = x[j];
         }
         poly_sync<FGeo<L>::T>(slot);
-        SmFwdP<L, (L0 + 3 < L) ? L0 + 3 : L>::run(buf, tw, t, slot, valid);
+        SmFwdP<L, (L0 + 3 < L) ? L0 + 3 : L>::run(buf, tw, twl, t, slot, valid);
     }
 };
 template <int L> struct SmFwdP<L, L> {
-    static __device__ __forceinline__ void run(double2 *, const double2 *, int, int, bool) {}
+    static __device__ __forceinline__ void run(double2 *, const double2 *, const double2 *, int, int, bool) {}
 };
 template <int L, int L0> struct SmInvP {
     static __device__ __forceinline__ void run(double2 *buf, const double2 *tw, int t, int slot, bool valid) {
@@ -443,7 +451,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 }
 
 template <int LM, int G, int RT, int CT, int NSTAGE> __global__ void __launch_bounds__(512, 1)
-cggi_fused3_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, const double2 *__restrict__ twi_g, double inv_m) {
+cggi_fused3_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, const double2 *__restrict__ twi_g, const double2 *__restrict__ twlf_g,
+                         const double2 *__restrict__ twli_g, double inv_m) {
     typedef FGeo<LM> FG;
     constexpr int M = 1 << LM, N = 2 * M, T = FG::T, NT = 512, PL = FG::PLANE, NSLOT = NT / T, GH = G / 2;
     constexpr int PMAX = RT > CT ? RT : CT;
@@ -454,10 +463,15 @@ cggi_fused3_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
     __shared__ __align__(8) unsigned long long s_bar[NSTAGE], s_empty[NSTAGE]; // tile filled / tile consumed by all threads
     double *ring = reinterpret_cast<double *>(csm + (size_t)G * PMAX * PL); // [NSTAGE][RT][N]
     // both twiddle tables (m complex values each) live in shared memory: with ~210 KB of it in use the L1 is too small to keep them
-    double2 *twf = reinterpret_cast<double2 *>(ring + (size_t)NSTAGE * RT * N), *twi = twf + M;
-    for (int i = threadIdx.x; i < M; i += 512) {
+    // M entries per direction as before, split into the first T block twiddles and the [7][T] last-pass table
+    double2 *twf = reinterpret_cast<double2 *>(ring + (size_t)NSTAGE * RT * N), *twlf = twf + T, *twi = twf + M, *twli = twi + T;
+    for (int i = threadIdx.x; i < T; i += 512) {
         twf[i] = twf_g[i];
         twi[i] = twi_g[i];
+    }
+    for (int i = threadIdx.x; i < 7 * T; i += 512) {
+        twlf[i] = twlf_g[i];
+        twli[i] = twli_g[i];
     }
     const int cols = p.cols, C = cols * p.brk_size, K = p.base2k, bs = p.block_size;
     const int tid = threadIdx.x, slot = tid / T, t = tid % T;
@@ -518,7 +532,7 @@ cggi_fused3_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
                 for (int jj = 0; jj < 8; jj++) buf[FPAD(t + jj * T)] = x[jj];
             }
             poly_sync<T>(slot);
-            SmFwdP<LM, FG::R0>::run(buf, twf, t, slot, valid);
+            SmFwdP<LM, FG::R0>::run(buf, twf, twlf, t, slot, valid);
         }
         __syncthreads(); // every transform of the block is complete before the key products read across them
         // ---- key products: tiles in (key, poly) order -----------------------------------------------------------------------
@@ -583,7 +597,9 @@ cggi_fused3_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
                 double2 x[8];
 #pragma unroll
                 for (int jj = 0; jj < 8; jj++) x[jj] = buf[FPAD(8 * t + jj)];
-                fgs_radix8<3, true>(x, twi, (1u << (LM - 3)) | (uint32_t)t);
+                double2 w[7];
+                load_tw7<true>(w, twli, T, t);
+                fgs_radix8_w(x, w);
 #pragma unroll
                 for (int jj = 0; jj < 8; jj++) buf[FPAD(8 * t + jj)] = x[jj];
             }
@@ -650,7 +666,8 @@ template <int LM, int G, int RT, int CT, int NSTAGE> static int launch_cggi3(pgb
     PGB_CHECK_CUDA(cudaFuncSetAttribute(cggi_fused3_fft64_kernel<LM, G, RT, CT, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (p.batch + G - 1) / G;
     { ProfScope _ps(m, PROF_OTHER);
-    cggi_fused3_fft64_kernel<LM, G, RT, CT, NSTAGE><<<grid, 512, smem, m->stream>>>(p, m->fft_fwd, m->fft_inv, 1.0 / (double)(1 << LM));
+    cggi_fused3_fft64_kernel<LM, G, RT, CT, NSTAGE><<<grid, 512, smem, m->stream>>>(p, m->fft_fwd, m->fft_inv, m->fft_last_f, m->fft_last_i,
+                                                                                   1.0 / (double)(1 << LM));
     }
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;

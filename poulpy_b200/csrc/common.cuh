@@ -64,6 +64,7 @@ struct pgb_module {
     uint2 tw_top_f[4][16], tw_top_i[4][16]; // host copy of block twiddles 1..15 per prime (kernel-parameter twiddles of the gadget kernel)
     // FFT64: complex twiddles in block-twiddle order, [m] each direction
     double2 *fft_fwd, *fft_inv;
+    double2 *fft_last_f, *fft_last_i; // last-pass twiddles per thread, [7][m/8] (fft64.cuh: load_tw7); null for m < 8
     // lazily grown device workspace for host front ends
     void *ws;
     size_t ws_len;

@@ -23,7 +23,7 @@ struct FftJobs {
 
 template <int L, int L0> struct FFwdMid {
     static __device__ __forceinline__ void run(double2 *sm, double *gout, const double2 *tw, int t, bool active, uint32_t root = 1u,
-                                               int m_plane = FGeo<L>::M) {
+                                               int m_plane = FGeo<L>::M, const double2 *twl = nullptr) {
         typedef FGeo<L> G;
         constexpr int SL = L - L0 - 3;
         const int a = t >> SL, b = t & ((1 << SL) - 1);
@@ -32,7 +32,13 @@ template <int L, int L0> struct FFwdMid {
         double2 x[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) x[j] = sm[FPAD(base + (j << SL))];
-        fct_radix8<3>(x, tw, hi);
+        if (SL == 0 && twl) { // whole-transform last pass (root == 1): coalesced per-thread twiddles
+            double2 w[7];
+            load_tw7(w, twl, G::T, t);
+            fct_radix8_w(x, w);
+        } else {
+            fct_radix8<3>(x, tw, hi);
+        }
         if (SL == 0) {
             if (active) {
                 double2 *ore = reinterpret_cast<double2 *>(gout + base), *oim = reinterpret_cast<double2 *>(gout + m_plane + base);
@@ -47,14 +53,15 @@ template <int L, int L0> struct FFwdMid {
             for (int j = 0; j < 8; j++) sm[FPAD(base + (j << SL))] = x[j];
             __syncthreads();
         }
-        FFwdMid<L, (L0 + 3 < L) ? L0 + 3 : L>::run(sm, gout, tw, t, active, root, m_plane);
+        FFwdMid<L, (L0 + 3 < L) ? L0 + 3 : L>::run(sm, gout, tw, t, active, root, m_plane, twl);
     }
 };
 template <int L> struct FFwdMid<L, L> {
-    static __device__ __forceinline__ void run(double2 *, double *, const double2 *, int, bool, uint32_t = 1u, int = 0) {}
+    static __device__ __forceinline__ void run(double2 *, double *, const double2 *, int, bool, uint32_t = 1u, int = 0, const double2 * = nullptr) {}
 };
 
-template <int L, int LPC> __global__ void __launch_bounds__(FGeo<L>::T *LPC) fft64_fwd_kernel(FftJobs jb, const double2 *__restrict__ tw) {
+template <int L, int LPC> __global__ void __launch_bounds__(FGeo<L>::T *LPC) fft64_fwd_kernel(FftJobs jb, const double2 *__restrict__ tw,
+                                                                                         const double2 *__restrict__ twl) {
     typedef FGeo<L> G;
     extern __shared__ __align__(16) double2 fsm[];
     const int slot = threadIdx.x / G::T, t = threadIdx.x % G::T;
@@ -84,7 +91,7 @@ template <int L, int LPC> __global__ void __launch_bounds__(FGeo<L>::T *LPC) fft
 #pragma unroll
     for (int jj = 0; jj < 8; jj++) sm[FPAD(t + jj * G::T)] = x[jj];
     __syncthreads();
-    FFwdMid<L, (L > G::R0) ? G::R0 : L>::run(sm, gout, tw, t, active);
+    FFwdMid<L, (L > G::R0) ? G::R0 : L>::run(sm, gout, tw, t, active, 1u, G::M, twl);
 }
 
 template <int L, int L0> struct FInvMid {
@@ -108,7 +115,8 @@ template <int L> struct FInvMid<L, -1> {
     static __device__ __forceinline__ void run(double2 *, const double2 *, int, uint32_t = 1u) {}
 };
 
-template <int L, int LPC> __global__ void __launch_bounds__(FGeo<L>::T *LPC) fft64_inv_kernel(FftJobs jb, const double2 *__restrict__ tw, double inv_m) {
+template <int L, int LPC> __global__ void __launch_bounds__(FGeo<L>::T *LPC) fft64_inv_kernel(FftJobs jb, const double2 *__restrict__ tw, double inv_m,
+                                                                                         const double2 *__restrict__ twl) {
     typedef FGeo<L> G;
     extern __shared__ __align__(16) double2 fsm[];
     const int slot = threadIdx.x / G::T, t = threadIdx.x % G::T;
@@ -133,7 +141,11 @@ template <int L, int LPC> __global__ void __launch_bounds__(FGeo<L>::T *LPC) fft
 #pragma unroll
             for (int jj = 0; jj < 8; jj++) x[jj] = make_double2(0.0, 0.0);
         }
-        fgs_radix8<3>(x, tw, (1u << L0) | (uint32_t)t);
+        {
+            double2 w[7];
+            load_tw7(w, twl, G::T, t);
+            fgs_radix8_w(x, w);
+        }
 #pragma unroll
         for (int jj = 0; jj < 8; jj++) sm[FPAD(8 * t + jj)] = x[jj];
         __syncthreads();
@@ -177,6 +189,24 @@ int fft64_module_init(pgb_module *m) {
     PGB_CHECK_CUDA(cudaMalloc(&m->fft_inv, mm * sizeof(double2)));
     PGB_CHECK_CUDA(cudaMemcpy(m->fft_fwd, hf, mm * sizeof(double2), cudaMemcpyHostToDevice));
     PGB_CHECK_CUDA(cudaMemcpy(m->fft_inv, hi, mm * sizeof(double2), cudaMemcpyHostToDevice));
+    m->fft_last_f = m->fft_last_i = nullptr;
+    if (mm >= 8) { // last-pass tables (fft64.cuh: load_tw7): thread t of T = m/8 owns node hi = T + t
+        const uint64_t T = mm / 8;
+        double2 *lf = (double2 *)malloc(7 * T * sizeof(double2)), *li = (double2 *)malloc(7 * T * sizeof(double2));
+        for (uint64_t t = 0; t < T; t++) {
+            const uint64_t node = T + t, idx[7] = {node, 2 * node, 2 * node + 1, 4 * node, 4 * node + 1, 4 * node + 2, 4 * node + 3};
+            for (int j = 0; j < 7; j++) {
+                lf[j * T + t] = hf[idx[j]];
+                li[j * T + t] = hi[idx[j]];
+            }
+        }
+        PGB_CHECK_CUDA(cudaMalloc(&m->fft_last_f, 7 * T * sizeof(double2)));
+        PGB_CHECK_CUDA(cudaMalloc(&m->fft_last_i, 7 * T * sizeof(double2)));
+        PGB_CHECK_CUDA(cudaMemcpy(m->fft_last_f, lf, 7 * T * sizeof(double2), cudaMemcpyHostToDevice));
+        PGB_CHECK_CUDA(cudaMemcpy(m->fft_last_i, li, 7 * T * sizeof(double2), cudaMemcpyHostToDevice));
+        free(lf);
+        free(li);
+    }
     free(hf);
     free(hi);
     return PGB_OK;
@@ -196,7 +226,7 @@ template <int L> static int flaunch_fwd(pgb_module *m, const FftJobs &jb) {
     }
     int grid = (jb.total_jobs + LPC - 1) / LPC;
     { ProfScope _ps(m, PROF_DFT_FWD);
-    fft64_fwd_kernel<L, LPC><<<grid, G::T * LPC, smem, m->stream>>>(jb, m->fft_fwd);
+    fft64_fwd_kernel<L, LPC><<<grid, G::T * LPC, smem, m->stream>>>(jb, m->fft_fwd, m->fft_last_f);
     }
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;
@@ -213,7 +243,7 @@ template <int L> static int flaunch_inv(pgb_module *m, const FftJobs &jb) {
     }
     int grid = (jb.total_jobs + LPC - 1) / LPC;
     { ProfScope _ps(m, PROF_DFT_INV);
-    fft64_inv_kernel<L, LPC><<<grid, G::T * LPC, smem, m->stream>>>(jb, m->fft_inv, 1.0 / (double)(m->n / 2));
+    fft64_inv_kernel<L, LPC><<<grid, G::T * LPC, smem, m->stream>>>(jb, m->fft_inv, 1.0 / (double)(m->n / 2), m->fft_last_i);
     }
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;

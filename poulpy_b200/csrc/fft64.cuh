@@ -65,3 +65,32 @@ template <int NLEV, bool TWS = false> __device__ __forceinline__ void fgs_radix8
     }
 }
 
+
+// The last forward pass and the first inverse pass give thread t the node hi = T | t (T = m/8): its seven twiddles tw[hi], tw[2hi],
+// tw[2hi+1], tw[4hi..4hi+3] sit 16 / 32 / 64 bytes apart between neighbouring threads, so a warp-wide 128-bit load of them touches up to
+// 4x the lines (or shared-memory banks) it needs.  The module keeps the same values a second time as [7][T] ("last-pass tables",
+// fft64_module_init): one coalesced / conflict-free load each.
+template <bool TWS = false> __device__ __forceinline__ void load_tw7(double2 (&w)[7], const double2 *__restrict__ twl, int T, int t) {
+#pragma unroll
+    for (int j = 0; j < 7; j++) w[j] = ldw<TWS>(twl + j * T + t);
+}
+__device__ __forceinline__ void fct_radix8_w(double2 (&x)[8], const double2 (&w)[7]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) fct_bf(x[j], x[j + 4], w[0]);
+    fct_bf(x[0], x[2], w[1]);
+    fct_bf(x[1], x[3], w[1]);
+    fct_bf(x[4], x[6], w[2]);
+    fct_bf(x[5], x[7], w[2]);
+#pragma unroll
+    for (int j = 0; j < 4; j++) fct_bf(x[2 * j], x[2 * j + 1], w[3 + j]);
+}
+__device__ __forceinline__ void fgs_radix8_w(double2 (&x)[8], const double2 (&w)[7]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) fgs_bf(x[2 * j], x[2 * j + 1], w[3 + j]);
+    fgs_bf(x[0], x[2], w[1]);
+    fgs_bf(x[1], x[3], w[1]);
+    fgs_bf(x[4], x[6], w[2]);
+    fgs_bf(x[5], x[7], w[2]);
+#pragma unroll
+    for (int j = 0; j < 4; j++) fgs_bf(x[j], x[j + 4], w[0]);
+}

@@ -46,34 +46,6 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *gptr, uint32_t byte
 }
 __device__ __forceinline__ void group_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
-// The last forward pass and the first inverse pass give thread t the node hi = 2^(L-3) | t: its seven twiddles tw[hi], tw[2hi], tw[2hi+1],
-// tw[4hi..4hi+3] sit 16 / 32 / 64 bytes apart between neighbouring threads, so a warp-wide 128-bit load of them touches 4x the lines it
-// needs (the L1 data pipe was at 80 % with these and the key loads).  `twl` holds the same values as [7][T]: one coalesced load each.
-__device__ __forceinline__ void load_tw7(double2 (&w)[7], const double2 *__restrict__ twl, int T, int t) {
-#pragma unroll
-    for (int j = 0; j < 7; j++) w[j] = __ldg(twl + j * T + t);
-}
-__device__ __forceinline__ void fct_radix8_w(double2 (&x)[8], const double2 (&w)[7]) {
-#pragma unroll
-    for (int j = 0; j < 4; j++) fct_bf(x[j], x[j + 4], w[0]);
-    fct_bf(x[0], x[2], w[1]);
-    fct_bf(x[1], x[3], w[1]);
-    fct_bf(x[4], x[6], w[2]);
-    fct_bf(x[5], x[7], w[2]);
-#pragma unroll
-    for (int j = 0; j < 4; j++) fct_bf(x[2 * j], x[2 * j + 1], w[3 + j]);
-}
-__device__ __forceinline__ void fgs_radix8_w(double2 (&x)[8], const double2 (&w)[7]) {
-#pragma unroll
-    for (int j = 0; j < 4; j++) fgs_bf(x[2 * j], x[2 * j + 1], w[3 + j]);
-    fgs_bf(x[0], x[2], w[1]);
-    fgs_bf(x[1], x[3], w[1]);
-    fgs_bf(x[4], x[6], w[2]);
-    fgs_bf(x[5], x[7], w[2]);
-#pragma unroll
-    for (int j = 0; j < 4; j++) fgs_bf(x[j], x[j + 4], w[0]);
-}
-
 template <int L, int L0, bool TWS> struct GFwd {
     static __device__ __forceinline__ void run(double2 *buf, const double2 *tw, const double2 *twl, int t, int slot) {
         constexpr int SL = L - L0 - 3;
@@ -316,18 +288,6 @@ __global__ void __launch_bounds__(256) fft64_gadget_key_kernel(const double *__r
     out[poly * (size_t)M + (size_t)blockIdx.z * (M / 2) + i] = make_double2(src[0], src[1]);
     (void)polys;
 }
-// last-pass twiddles of thread t (node hi = M/8 + t): out[j][t], j = 0..6 <- tw[hi], tw[2hi], tw[2hi+1], tw[4hi .. 4hi+3]
-__global__ void __launch_bounds__(256) fft64_gadget_tw_kernel(const double2 *__restrict__ tw, double2 *__restrict__ out, int T) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
-    const int hi = T + t;
-    out[0 * T + t] = tw[hi];
-    out[1 * T + t] = tw[2 * hi];
-    out[2 * T + t] = tw[2 * hi + 1];
-#pragma unroll
-    for (int j = 0; j < 4; j++) out[(3 + j) * T + t] = tw[4 * hi + j];
-}
-
 template <int LM, int LPR, bool TWS> int launch(pgb_module *m, const FGadgetArgs &p, size_t smem) {
     static int sms_dev[32] = {};
     int &sms = sms_dev[m->device & 31];
@@ -395,9 +355,9 @@ int fft64_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_col
     p.in_cols = in_cols; p.row_cols = row_cols; p.row_col0 = row_col0; p.R = R; p.C = C; p.cols_out = cols_out; p.small_size = small_size;
     p.K = base2k; p.S = C / cols_out; p.res_size = res_size; p.batch = batch;
     p.inv_m = 1.0 / (double)(m->n / 2);
-    // workspace: [key in the kernel's layout | last-pass twiddles, forward and inverse]
-    const uint64_t M = m->n / 2, T = M / 8;
-    const uint64_t key_bytes = (uint64_t)R * C * m->n * 8, tw_bytes = 2 * 7 * T * sizeof(double2), need = key_bytes + tw_bytes + 256;
+    // workspace: the key in the kernel's layout
+    const uint64_t M = m->n / 2;
+    const uint64_t key_bytes = (uint64_t)R * C * m->n * 8, need = key_bytes + 256;
     if (m->aux_len < need) {
         if (m->aux_ws) {
             PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
@@ -408,18 +368,14 @@ int fft64_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_col
         PGB_CHECK_CUDA(cudaMalloc(&m->aux_ws, need));
         m->aux_len = need;
     }
-    double2 *kperm = (double2 *)m->aux_ws, *twl = (double2 *)((char *)m->aux_ws + ((key_bytes + 255) / 256) * 256);
+    double2 *kperm = (double2 *)m->aux_ws;
     { ProfScope _ps(m, PROF_OTHER);
     fft64_gadget_key_kernel<<<dim3(((unsigned)(M / 2) + 255) / 256, R * C, 2), 256, 0, m->stream>>>((const double *)pmat, kperm, (int)M, R * C);
     }
-    { ProfScope _ps(m, PROF_OTHER);
-    fft64_gadget_tw_kernel<<<dim3(((unsigned)T + 255) / 256, 1, 1), 256, 0, m->stream>>>(m->fft_fwd, twl, (int)T);
-    fft64_gadget_tw_kernel<<<dim3(((unsigned)T + 255) / 256, 1, 1), 256, 0, m->stream>>>(m->fft_inv, twl + 7 * T, (int)T);
-    }
     PGB_CHECK_CUDA(cudaGetLastError());
     p.pmat = (const double *)kperm;
-    p.twl_f = twl;
-    p.twl_i = twl + 7 * T;
+    p.twl_f = m->fft_last_f;
+    p.twl_i = m->fft_last_i;
     int lpr;
     bool tws;
     size_t smem;
