@@ -125,6 +125,8 @@ extern "C" void pgb_module_destroy(pgb_module *m) {
     cudaDeviceSynchronize();
     cudaFree(m->ntt_fwd);
     cudaFree(m->ntt_inv);
+    cudaFree(m->ntt_last16_f);
+    cudaFree(m->ntt_last16_i);
     cudaFree(m->fft_fwd);
     cudaFree(m->fft_inv);
     cudaFree(m->fft_last_f);

@@ -60,6 +60,9 @@ struct pgb_module {
     struct ProfState *prof;
     // NTT120: twiddles (w, floor(w*2^32/q)) in block-twiddle (bit-reversed) order, [4][n] each direction
     uint2 *ntt_fwd, *ntt_inv;
+    // the 15 twiddles of tree node n/16 + t and its descendants, per prime and thread, as [4][8][n/16] uint4 (slot 0: node, 1: children,
+    // 2-3: grandchildren, 4-7: great-grandchildren): the last radix-16 pass of the gadget kernel loads them coalesced (null for n < 32)
+    uint4 *ntt_last16_f, *ntt_last16_i;
     Ntt120Consts nc;
     uint2 tw_top_f[4][16], tw_top_i[4][16]; // host copy of block twiddles 1..15 per prime (kernel-parameter twiddles of the gadget kernel)
     // FFT64: complex twiddles in block-twiddle order, [m] each direction

@@ -802,6 +802,31 @@ int ntt120_module_init(pgb_module *m) {
     PGB_CHECK_CUDA(cudaMalloc(&m->ntt_inv, 4 * n * sizeof(uint2)));
     PGB_CHECK_CUDA(cudaMemcpy(m->ntt_fwd, hf, 4 * n * sizeof(uint2), cudaMemcpyHostToDevice));
     PGB_CHECK_CUDA(cudaMemcpy(m->ntt_inv, hi, 4 * n * sizeof(uint2), cudaMemcpyHostToDevice));
+    m->ntt_last16_f = m->ntt_last16_i = nullptr;
+    if (n >= 32) { // per-thread tables of the last radix-16 pass (common.cuh)
+        const uint64_t T = n / 16;
+        uint4 *lf = (uint4 *)calloc(4 * 8 * T, sizeof(uint4)), *li = (uint4 *)calloc(4 * 8 * T, sizeof(uint4));
+        for (int k = 0; k < 4; k++)
+            for (uint64_t t = 0; t < T; t++) {
+                const uint64_t node = T + t;
+                for (int dir = 0; dir < 2; dir++) {
+                    const uint2 *src = (dir ? hi : hf) + (size_t)k * n;
+                    uint4 *dst = (dir ? li : lf) + (size_t)k * 8 * T + t;
+                    dst[0 * T] = make_uint4(src[node].x, src[node].y, 0u, 0u);
+                    dst[1 * T] = make_uint4(src[2 * node].x, src[2 * node].y, src[2 * node + 1].x, src[2 * node + 1].y);
+                    for (int j = 0; j < 2; j++)
+                        dst[(2 + j) * T] = make_uint4(src[4 * node + 2 * j].x, src[4 * node + 2 * j].y, src[4 * node + 2 * j + 1].x, src[4 * node + 2 * j + 1].y);
+                    for (int j = 0; j < 4; j++)
+                        dst[(4 + j) * T] = make_uint4(src[8 * node + 2 * j].x, src[8 * node + 2 * j].y, src[8 * node + 2 * j + 1].x, src[8 * node + 2 * j + 1].y);
+                }
+            }
+        PGB_CHECK_CUDA(cudaMalloc(&m->ntt_last16_f, 4 * 8 * T * sizeof(uint4)));
+        PGB_CHECK_CUDA(cudaMalloc(&m->ntt_last16_i, 4 * 8 * T * sizeof(uint4)));
+        PGB_CHECK_CUDA(cudaMemcpy(m->ntt_last16_f, lf, 4 * 8 * T * sizeof(uint4), cudaMemcpyHostToDevice));
+        PGB_CHECK_CUDA(cudaMemcpy(m->ntt_last16_i, li, 4 * 8 * T * sizeof(uint4), cudaMemcpyHostToDevice));
+        free(lf);
+        free(li);
+    }
     free(hf);
     free(hi);
     CrtConsts cc;

@@ -178,6 +178,34 @@ struct TwGlobal {
         }
     }
 };
+// the same 15 twiddles from the per-thread table [8][T] uint4 (common.cuh: ntt_last16_*): every load of a warp is one contiguous 512 bytes,
+// where the 64-byte-strided get8 / get4 of TwGlobal touch four / two times the lines they need
+struct TwLast {
+    const uint4 *p; // table of this prime + t
+    int T;
+    __device__ __forceinline__ uint2 get1() const {
+        const uint4 a = __ldg(p);
+        return make_uint2(a.x, a.y);
+    }
+    __device__ __forceinline__ void get2(uint2 (&w)[2]) const {
+        const uint4 a = __ldg(p + T);
+        w[0] = make_uint2(a.x, a.y); w[1] = make_uint2(a.z, a.w);
+    }
+    __device__ __forceinline__ void get4(uint2 (&w)[4]) const {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const uint4 a = __ldg(p + (2 + i) * T);
+            w[2 * i] = make_uint2(a.x, a.y); w[2 * i + 1] = make_uint2(a.z, a.w);
+        }
+    }
+    __device__ __forceinline__ void get8(uint2 (&w)[8]) const {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint4 a = __ldg(p + (4 + i) * T);
+            w[2 * i] = make_uint2(a.x, a.y); w[2 * i + 1] = make_uint2(a.z, a.w);
+        }
+    }
+};
 // the 15 CTA-uniform twiddles of the top pass, straight from the kernel parameter bank
 struct TwTopConst {
     const uint2 *w; // 16 entries, node indices 1..15
@@ -242,7 +270,8 @@ template <int L> __host__ __device__ constexpr int fmask(int i) {
 }
 
 template <int L> __device__ __forceinline__ void gadget_body(const GadgetArgs &p, uint32_t *__restrict__ sm, const uint2 *__restrict__ twf,
-                                                             const uint2 *__restrict__ twi, const int K) {
+                                                             const uint2 *__restrict__ twi, const uint4 *__restrict__ lastf,
+                                                             const uint4 *__restrict__ lasti, const int K) {
     typedef GGeo<L> G;
     constexpr int n = G::N, T = G::T;
     const PrimeCtx pc = {p.prime[K].q, p.prime[K].c32, p.prime[K].c32s, p.prime[K].neg64};
@@ -338,7 +367,7 @@ template <int L> __device__ __forceinline__ void gadget_body(const GadgetArgs &p
         __syncthreads();
         // ---- forward pass 3 (16 consecutive words per thread), results reduced to [0, 2q) ------------------------------------------
         {
-            const TwGlobal tw = {twf, (1u << G::LV3) | (uint32_t)t};
+            const TwLast tw = {lastf + t, T};
             for (int r = 0; r < R; r++) {
                 uint32_t *pl = sm + r * n;
                 uint32_t x[16];
@@ -395,7 +424,7 @@ template <int L> __device__ __forceinline__ void gadget_body(const GadgetArgs &p
         }
         // ---- inverse pass 1 (levels L-1 .. L-NL3, 16 consecutive words) --------------------------------------------------------------
         {
-            const TwGlobal tw = {twi, (1u << G::LV3) | (uint32_t)t};
+            const TwLast tw = {lasti + t, T};
             for (int o = 0; o < cols_out; o++) {
                 uint32_t *pl = sm + o * n;
                 uint32_t x[16];
@@ -563,12 +592,14 @@ template <int L> __device__ __forceinline__ void gadget_body(const GadgetArgs &p
 
 template <int L, int MB> __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(GGeo<L>::T, MB * 256 / GGeo<L>::T) ntt120_gadget_kernel(const __grid_constant__ GadgetArgs p,
                                                                                                             const uint2 *__restrict__ twf,
-                                                                                                            const uint2 *__restrict__ twi) {
+                                                                                                            const uint2 *__restrict__ twi,
+                                                                                                            const uint4 *__restrict__ lastf,
+                                                                                                            const uint4 *__restrict__ lasti) {
     extern __shared__ __align__(16) uint32_t smem[];
     constexpr int n = GGeo<L>::N;
     cl_arrive(); // primes the arrive/wait pairing used by the per-ciphertext loop
     const int k = blockIdx.x & 3; // = rank in the cluster; one code body for all four primes (instruction-cache footprint)
-    gadget_body<L>(p, smem, twf + (size_t)k * n, twi + (size_t)k * n, k);
+    gadget_body<L>(p, smem, twf + (size_t)k * n, twi + (size_t)k * n, lastf + (size_t)k * (n / 2), lasti + (size_t)k * (n / 2), k);
 }
 
 // collapsed key in the gadget kernel's layout: out[r][col][k][chunk][t][4] = sum_j 2^((S-1-j)K) * pmat[r][j * cols_out + col][k][16t + 4 chunk + w]
@@ -644,7 +675,8 @@ template <int L, int MB> int launch_gadget_mb(pgb_module *m, const GadgetArgs &p
     const int clusters = p.batch < nc ? p.batch : nc;
     cfg.gridDim = dim3(4 * clusters);
     { ProfScope _ps(m, PROF_GADGET);
-    PGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ntt120_gadget_kernel<L, MB>, p, (const uint2 *)m->ntt_fwd, (const uint2 *)m->ntt_inv));
+    PGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ntt120_gadget_kernel<L, MB>, p, (const uint2 *)m->ntt_fwd, (const uint2 *)m->ntt_inv,
+                                      (const uint4 *)m->ntt_last16_f, (const uint4 *)m->ntt_last16_i));
     }
     return PGB_OK;
 }
