@@ -456,12 +456,15 @@ cggi_fused3_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
     typedef FGeo<LM> FG;
     constexpr int M = 1 << LM, N = 2 * M, T = FG::T, NT = 512, PL = FG::PLANE, NSLOT = NT / T, GH = G / 2;
     constexpr int PMAX = RT > CT ? RT : CT;
+    // planes of consecutive ciphertexts start 64 bytes (mod 128) apart: in the key products neighbouring threads hold the same frequency of
+    // two different ciphertexts, and a plane stride that is a multiple of 128 bytes put both on the same banks (2-way conflicts)
+    constexpr int GS = PMAX * PL + 4;
     constexpr uint32_t CHUNK = N * 8, TILE = RT * CHUNK; // bytes
     static_assert(GH * M == NT && GH >= 1 && LM > FG::R0, "geometry");
     extern __shared__ __align__(128) double2 csm[];
     __shared__ int s_pos[G * 8];
     __shared__ __align__(8) unsigned long long s_bar[NSTAGE], s_empty[NSTAGE]; // tile filled / tile consumed by all threads
-    double *ring = reinterpret_cast<double *>(csm + (size_t)G * PMAX * PL); // [NSTAGE][RT][N]
+    double *ring = reinterpret_cast<double *>(csm + (size_t)G * GS); // [NSTAGE][RT][N]
     // both twiddle tables (m complex values each) live in shared memory: with ~210 KB of it in use the L1 is too small to keep them
     // M entries per direction as before, split into the first T block twiddles and the [7][T] last-pass table
     double2 *twf = reinterpret_cast<double2 *>(ring + (size_t)NSTAGE * RT * N), *twlf = twf + T, *twi = twf + M, *twli = twi + T;
@@ -502,7 +505,7 @@ cggi_fused3_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
         for (int gk = 0; gk < NSTAGE && gk < total_tiles; gk++) issue(gk);
 
     const int gp = tid % GH, f = tid / GH; // this thread's frequency and its two ciphertexts gp, gp + GH
-    double2 *mine0 = csm + (size_t)gp * PMAX * PL + FPAD(f), *mine1 = csm + (size_t)(gp + GH) * PMAX * PL + FPAD(f);
+    double2 *mine0 = csm + (size_t)gp * GS + FPAD(f), *mine1 = csm + (size_t)(gp + GH) * GS + FPAD(f);
     int gk = 0;
 
     for (int blk = 0; blk + bs <= p.n_lwe; blk += bs) {
@@ -516,7 +519,7 @@ cggi_fused3_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
             const int job = base + slot;
             const bool valid = job < G * RT;
             const int g = valid ? job / RT : 0, r = valid ? job % RT : 0, limb = r / cols, col = r % cols;
-            double2 *buf = csm + (g * PMAX + r) * PL;
+            double2 *buf = csm + g * GS + r * PL;
             if (valid) {
                 const int ct = ct0 + g;
                 const bool live = ct < p.batch && limb < p.out_size;
@@ -592,7 +595,7 @@ cggi_fused3_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
             const int job = base + slot;
             const bool valid = job < G * C;
             const int g = valid ? job / C : 0, q = valid ? job % C : 0;
-            double2 *buf = csm + (g * PMAX + q) * PL;
+            double2 *buf = csm + g * GS + q * PL;
             if (valid) {
                 double2 x[8];
 #pragma unroll
@@ -629,7 +632,7 @@ cggi_fused3_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
             for (int g = 0; g < G; g++) {
                 if (ct0 + g >= p.batch) break;
                 long long *acc_g = p.res + (size_t)(ct0 + g) * p.res_stride;
-                const long long *big_g = reinterpret_cast<const long long *>(csm + (size_t)g * PMAX * PL);
+                const long long *big_g = reinterpret_cast<const long long *>(csm + (size_t)g * GS);
                 for (int col = 0; col < cols; col++) {
 #pragma unroll
                     for (int i = tid; i < N; i += NT) {
@@ -662,7 +665,7 @@ cggi_fused3_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
 template <int LM, int G, int RT, int CT, int NSTAGE> static int launch_cggi3(pgb_module *m, const CggiFusedArgs &p) {
     typedef FGeo<LM> FG;
     constexpr int PMAX = RT > CT ? RT : CT;
-    const size_t smem = (size_t)G * PMAX * FG::PLANE * sizeof(double2) + (size_t)NSTAGE * RT * (2 << LM) * 8 + (size_t)2 * (1 << LM) * sizeof(double2);
+    const size_t smem = (size_t)G * (PMAX * FG::PLANE + 4) * sizeof(double2) + (size_t)NSTAGE * RT * (2 << LM) * 8 + (size_t)2 * (1 << LM) * sizeof(double2);
     PGB_CHECK_CUDA(cudaFuncSetAttribute(cggi_fused3_fft64_kernel<LM, G, RT, CT, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (p.batch + G - 1) / G;
     { ProfScope _ps(m, PROF_OTHER);
