@@ -629,10 +629,26 @@ cggi_fused3_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
         // brk_size <= 4 here (checked on the host): all loads of a coefficient are issued before its carry chain; 32-bit offsets
         {
             const int limb_w = cols * N, bsz = p.brk_size;
+            const bool two_to_one = bsz == 2 && p.out_size == 1; // the bench shape (k_brk = 2 limbs, k_glwe = 1 limb): no predicated loads
             for (int g = 0; g < G; g++) {
                 if (ct0 + g >= p.batch) break;
                 long long *acc_g = p.res + (size_t)(ct0 + g) * p.res_stride;
                 const long long *big_g = reinterpret_cast<const long long *>(csm + (size_t)g * GS);
+                if (two_to_one) {
+                    for (int col = 0; col < cols; col++) {
+#pragma unroll
+                        for (int i = tid; i < N; i += NT) {
+                            const long long v0 = big_g[col * (2 * PL) + i], v1 = big_g[(cols + col) * (2 * PL) + i];
+                            long long *ap = acc_g + col * N + i;
+                            const long long a0 = *ap;
+                            const long long o1 = (long long)((unsigned long long)v1 << (64 - K)) >> (64 - K);
+                            const long long c = (long long)((unsigned long long)v1 - (unsigned long long)o1) >> K;
+                            const long long tsum = (long long)((unsigned long long)v0 + (unsigned long long)a0 + (unsigned long long)c);
+                            *ap = (long long)((unsigned long long)tsum << (64 - K)) >> (64 - K);
+                        }
+                    }
+                    continue;
+                }
                 for (int col = 0; col < cols; col++) {
 #pragma unroll
                     for (int i = tid; i < N; i += NT) {
