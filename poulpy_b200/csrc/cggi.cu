@@ -80,6 +80,107 @@ __global__ void __launch_bounds__(256) cggi_xai_ntt120_kernel(XaiArgs p) {
     };
     *ap = make_uint4(f(a.x, w.x, v.x), f(a.y, w.y, v.y), f(a.z, w.z, v.z), f(a.w, w.w, v.w));
 }
+// One launch per block of `bs` LWE coefficients (NTT120): acc_add[c] = sum_t ( x_pow_a[a_t] * v_t[c] - v_t[c] ),  v_t[c] = sum_r acc_dft[r] * BRK_t[r][c],
+// i.e. the bs x (vmp_apply_dft_to_dft + svp_apply_dft_to_dft + dft_add_assign + dft_sub_assign) of algorithm.rs:338-357 with the C partial sums
+// in registers: the limb-wise sequence moves 864 KB per ciphertext and block through HBM at the bench shape, this kernel 96 KB.  Every
+// intermediate is canonical, so the result is bit-identical to the per-key kernels (ntt120_vmp_kernel + cggi_xai_ntt120_kernel).
+struct BlockArgs {
+    const char *acc_dft; uint64_t acc_bs;   // R polys per ciphertext
+    char *acc_add;       uint64_t add_bs;   // C polys per ciphertext (written, not accumulated)
+    const char *brk;     uint64_t brk_bytes; // key of LWE coefficient i at brk + i * brk_bytes, layout [r][c] polys
+    const char *xpa;
+    const long long *lwe; uint64_t lwe_stride; // a_{blk + t} of item b at lwe[b * lwe_stride + t]
+    uint32_t n, R, C, bs;
+};
+// BT ciphertexts per thread: a key word loaded from L2 serves all of them (with one ciphertext per thread every CTA re-read the block's
+// 786 KB of key: 6.6 TB/s of L2 traffic at the bench shape, the limiter of the first version)
+// SM = 1: the block's inputs a[i][r] and the table values w[i][t] sit in thread-private shared-memory slots instead of registers
+// (162 registers allowed one CTA of eight warps per SM: latency bound); SM = 0: registers / L2 (shapes whose staging does not fit)
+template <int RMAX, int BT, int SM> __global__ void __launch_bounds__(256, SM ? 2 : 1) cggi_block_ntt120_kernel(BlockArgs p, uint32_t batch) {
+    extern __shared__ __align__(16) uint4 bsm[];
+    uint4 *asm_ = bsm + threadIdx.x;                                 // a slot (i * RMAX + r) at asm_[(i * RMAX + r) * 256]
+    uint4 *wsm = bsm + (size_t)BT * RMAX * 256;                      // w slot [(i * bs + t) * 256 + tid]
+    constexpr int w_in_smem = SM;
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; // uint4 index inside a poly
+    if (u >= p.n) return;
+    const n120::PrimeRt pr(u / (p.n / 4));
+    const uint32_t q = pr.q, b0 = blockIdx.z * BT;
+    const size_t poly = (size_t)p.n; // uint4 per poly
+    uint4 a[SM ? 1 : BT][SM ? 1 : RMAX]; // SM = 0: the block's inputs stay in registers for all bs x C products
+    uint32_t pos[BT];
+#pragma unroll
+    for (int i = 0; i < BT; i++) {
+        const uint32_t b = b0 + i < batch ? b0 + i : batch - 1; // the tail repeats the last ciphertext (its stores are skipped)
+        const uint4 *ap = reinterpret_cast<const uint4 *>(p.acc_dft + (size_t)b * p.acc_bs) + u;
+#pragma unroll
+        for (int r = 0; r < RMAX; r++) {
+            const uint4 v = r < (int)p.R ? __ldg(ap + (size_t)r * poly) : make_uint4(0, 0, 0, 0);
+            if (SM) asm_[(i * RMAX + r) * 256] = v;
+            else a[SM ? 0 : i][SM ? 0 : r] = v;
+        }
+    }
+    if (w_in_smem) { // the table values do not depend on the output poly: without this every one of the C passes re-read them from L2
+        for (uint32_t t = 0; t < p.bs; t++)
+#pragma unroll
+            for (int i = 0; i < BT; i++) {
+                const uint32_t b = b0 + i < batch ? b0 + i : batch - 1;
+                const long long ai = p.lwe[(size_t)b * p.lwe_stride + t];
+                const uint32_t ps = (uint32_t)((ai + (long long)(2 * p.n)) & (long long)(2 * p.n - 1));
+                const uint4 w = __ldg(reinterpret_cast<const uint4 *>(p.xpa + (size_t)ps * p.n * 16) + u);
+                wsm[(i * p.bs + t) * 256 + threadIdx.x] =
+                    make_uint4(w.x ? w.x - 1 : q - 1, w.y ? w.y - 1 : q - 1, w.z ? w.z - 1 : q - 1, w.w ? w.w - 1 : q - 1); // w - 1 mod q
+            }
+    }
+    // (s + w v) - v = s + (w - 1) v (mod q): the bs updates of one output poly accumulate as u64 products of (w - 1) in [0, q) and a lazy
+    // v in [0, 2q) (each < 2^61, bs <= 8), reduced once -- same canonical result as the per-key kernels, half the instructions
+    auto lazy = [&](unsigned long long x) { // any u64 -> [0, 2q)
+        const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
+        return n120::csub(n120::mul_shoup(hi, pr.c32, pr.c32s, q) + (lo - (lo >> 30) * q), 2 * q);
+    };
+    for (uint32_t c = 0; c < p.C; c++) {
+        unsigned long long acc[BT][4];
+#pragma unroll
+        for (int i = 0; i < BT; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0;
+        for (uint32_t t = 0; t < p.bs; t++) {
+            const uint4 *key = reinterpret_cast<const uint4 *>(p.brk + (size_t)t * p.brk_bytes) + u + (size_t)c * poly;
+            uint4 mv[RMAX];
+#pragma unroll
+            for (int r = 0; r < RMAX; r++) mv[r] = r < (int)p.R ? __ldg(key + (size_t)r * p.C * poly) : make_uint4(0, 0, 0, 0);
+            if (!w_in_smem) {
+#pragma unroll
+                for (int i = 0; i < BT; i++) {
+                    const uint32_t b = b0 + i < batch ? b0 + i : batch - 1;
+                    const long long ai = p.lwe[(size_t)b * p.lwe_stride + t];
+                    pos[i] = (uint32_t)((ai + (long long)(2 * p.n)) & (long long)(2 * p.n - 1));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < BT; i++) {
+                uint4 w;
+                if (w_in_smem) {
+                    w = wsm[(i * p.bs + t) * 256 + threadIdx.x];
+                } else {
+                    w = __ldg(reinterpret_cast<const uint4 *>(p.xpa + (size_t)pos[i] * p.n * 16) + u);
+                    w = make_uint4(w.x ? w.x - 1 : q - 1, w.y ? w.y - 1 : q - 1, w.z ? w.z - 1 : q - 1, w.w ? w.w - 1 : q - 1); // w - 1 mod q
+                }
+                unsigned long long s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+                for (int r = 0; r < RMAX; r++) { // R <= 16: the u64 sums cannot overflow (ntt120_vmp_kernel reduces every 16 rows)
+                    const uint4 av = SM ? asm_[(i * RMAX + r) * 256] : a[SM ? 0 : i][SM ? 0 : r];
+                    s0 += (unsigned long long)av.x * mv[r].x; s1 += (unsigned long long)av.y * mv[r].y;
+                    s2 += (unsigned long long)av.z * mv[r].z; s3 += (unsigned long long)av.w * mv[r].w;
+                }
+                acc[i][0] += (unsigned long long)w.x * lazy(s0); acc[i][1] += (unsigned long long)w.y * lazy(s1);
+                acc[i][2] += (unsigned long long)w.z * lazy(s2); acc[i][3] += (unsigned long long)w.w * lazy(s3);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < BT; i++)
+            if (b0 + i < batch)
+                (reinterpret_cast<uint4 *>(p.acc_add + (size_t)(b0 + i) * p.add_bs) + u)[(size_t)c * poly] =
+                    make_uint4(pr.reduce(acc[i][0]), pr.reduce(acc[i][1]), pr.reduce(acc[i][2]), pr.reduce(acc[i][3]));
+    }
+}
 __global__ void __launch_bounds__(256) cggi_xai_fft64_kernel(XaiArgs p) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; // complex index
     const uint32_t m = p.n / 2;
@@ -148,6 +249,34 @@ int cggi_blind_rotate_impl(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2
     for (uint64_t blk = 0; blk + block_size <= n_lwe; blk += block_size) { // chunks_exact
         pgb_batch btd = {B, acc_bs, bt->stride_res, 0};
         for (uint64_t j = 0; j < cols; j++) PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &acc_dft, j, res, j, &btd));
+        if (m->flavour == PGB_NTT120 && cols * dnum <= 16 && block_size <= 8 && !getenv("PGB_NO_FUSION")) {
+            // the block's key products and X^{a_t} - 1 updates in one launch (cggi_block_ntt120_kernel)
+            BlockArgs ba = {(const char *)acc_dft.data, acc_bs, (char *)acc_add.data, vres_bs, (const char *)brk->data + blk * brk_bytes, brk_bytes,
+                            (const char *)x_pow_a->data, (const long long *)lwe_2n + 1 + blk, lwe_stride, (uint32_t)n, (uint32_t)(cols * dnum),
+                            (uint32_t)(cols * bsize), (uint32_t)block_size};
+            ProfScope _ps(m, PROF_VMP);
+            // staging per CTA: (BT * RMAX + BT * block_size) slots of 256 x 16 bytes; two CTAs per SM need <= 113 KB each
+            #define BLOCK_LAUNCH(RM, BTV)                                                                                         \
+                {                                                                                                                 \
+                    const dim3 grid(((uint32_t)n + 255) / 256, 1, (uint32_t)((B + (BTV) - 1) / (BTV)));                           \
+                    const size_t sb = (size_t)((BTV) * (RM) + (BTV) * block_size) * 256 * 16;                                     \
+                    if (sb <= (size_t)(113 << 10)) {                                                                              \
+                        static bool attr_dev[32] = {};                                                                            \
+                        if (!attr_dev[m->device & 31]) {                                                                          \
+                            PGB_CHECK_CUDA(cudaFuncSetAttribute(cggi_block_ntt120_kernel<RM, BTV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 << 10)); \
+                            attr_dev[m->device & 31] = true;                                                                      \
+                        }                                                                                                         \
+                        cggi_block_ntt120_kernel<RM, BTV, 1><<<grid, 256, sb, m->stream>>>(ba, (uint32_t)B);                      \
+                    } else {                                                                                                      \
+                        cggi_block_ntt120_kernel<RM, BTV, 0><<<grid, 256, 0, m->stream>>>(ba, (uint32_t)B);                       \
+                    }                                                                                                             \
+                }
+            if (cols * dnum <= 4) BLOCK_LAUNCH(4, 4)
+            else if (cols * dnum <= 8) BLOCK_LAUNCH(8, 2)
+            else BLOCK_LAUNCH(16, 1)
+            #undef BLOCK_LAUNCH
+            PGB_CHECK_CUDA(cudaGetLastError());
+        } else {
         PGB_CHECK_CUDA(cudaMemsetAsync(acc_add.data, 0, B * vres_bs, m->stream)); // vec_znx_dft_zero on every column
         for (uint64_t t = 0; t < block_size; t++) {
             pgb_vmp_pmat ski = *brk;
@@ -165,6 +294,7 @@ int cggi_blind_rotate_impl(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2
                 cggi_xai_fft64_kernel<<<grid, 256, 0, m->stream>>>(xa);
             }
             PGB_CHECK_CUDA(cudaGetLastError());
+        }
         }
         for (uint64_t i = 0; i < cols; i++) { // algorithm.rs:361-365
             pgb_batch bti = {B, big_bs, vres_bs, 0};
