@@ -296,6 +296,14 @@ int cggi_blind_rotate_impl(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2
             PGB_CHECK_CUDA(cudaGetLastError());
         }
         }
+        if (m->flavour == PGB_NTT120 && ntt120_fused_supported(m) && !getenv("PGB_NO_FUSION")) {
+            // algorithm.rs:361-365 for all columns in one launch: inverse transform + CRT + add_small (the accumulator column itself) +
+            // normalize, nothing but acc_add and the accumulator touches HBM
+            PGB_TRY(ntt120_fused_back(m, (const char *)acc_add.data, vres_bs, nullptr, 0, (int)(cols * bsize), (int)cols, (const char *)res->data,
+                                      bt->stride_res, res->cols * n * 8, (int)umin64(bsize, res->size), (char *)res->data, bt->stride_res,
+                                      res->cols * n * 8, (int)res->size, (int)base2k, 0, (int)B, nullptr, 0, 0, nullptr, false, true, true));
+            continue;
+        }
         for (uint64_t i = 0; i < cols; i++) { // algorithm.rs:361-365
             pgb_batch bti = {B, big_bs, vres_bs, 0};
             PGB_TRY(pgb_vec_znx_idft_apply_batched(m, &acc_big, 0, &acc_add, i, &bti));

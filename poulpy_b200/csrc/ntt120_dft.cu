@@ -447,6 +447,8 @@ struct FusedArgs {
     const char *small;  uint64_t small_bs;  uint64_t small_limb_stride; int small_size; // i64 limbs added to column 0 (or null)
     char *res;          uint64_t res_bs;    uint64_t res_limb_stride;                    // i64 output, column c at + c*n*8
     int R, C, cols_out;
+    int direct;         // 1: a_dft already holds the C product polys (limb-major, column-minor): no matrix, straight to the inverse transform
+    int small_all_cols; // 1: `small` is added on every output column (column c at + c*n words), not only on column 0
     // same-base2k normalisation plan (big = C / cols_out limbs)
     int K, lsh, res_size, a_size, a_start, a_end, res_start, res_end;
 };
@@ -507,6 +509,14 @@ template <int K> __device__ __forceinline__ void vmp_rows8(uint32_t (&x)[8], con
     for (int i = 0; i < 8; i++) x[i] = (uint32_t)acc[i];
 }
 
+// direct mode: the residues of one product poly come straight from global memory
+template <int K, int L> __device__ __forceinline__ void fused_bottom_direct(uint32_t *__restrict__ plane, const uint32_t *__restrict__ src,
+                                                                           const uint2 *__restrict__ tw, int t) {
+    const uint4 *p4 = reinterpret_cast<const uint4 *>(src + 8 * t);
+    const uint4 u0 = __ldg(p4), u1 = __ldg(p4 + 1);
+    uint32_t x[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+    inv_bottom_core<K, L>(x, plane, tw, t);
+}
 template <int K, int L> __device__ __forceinline__ void fused_bottom(uint32_t *__restrict__ plane, const uint32_t *__restrict__ a,
                                                                     size_t a_stride, const uint32_t *__restrict__ mm, size_t m_stride,
                                                                     int R, const uint2 *__restrict__ tw, int t) {
@@ -555,18 +565,28 @@ template <int L> __global__ void __launch_bounds__(Geo<L>::T, 2) ntt120_fused_ba
         if (skip && skip[b]) continue; // handled by the collapsed-key kernel
         const uint32_t *a = reinterpret_cast<const uint32_t *>(p.a_dft + b * p.a_bs);
         long long *res = reinterpret_cast<long long *>(p.res + b * p.res_bs) + (size_t)col * n;
-        const long long *small = (p.small && col == 0) ? reinterpret_cast<const long long *>(p.small + b * p.small_bs) : nullptr;
+        const long long *small = (p.small && (col == 0 || p.small_all_cols))
+                                     ? reinterpret_cast<const long long *>(p.small + b * p.small_bs) + (p.small_all_cols ? (size_t)col * n : 0)
+                                     : nullptr;
 
         for (int j = p.res_start; j < p.res_size; j++) {
 #pragma unroll
             for (int jj = 0; jj < 8; jj++) res[(size_t)j * res_ls + t + jj * G::T] = 0;
         }
         for (int j = p.a_size - 1; j >= p.a_end; j--) {
-            const uint32_t *mc = pm + ((size_t)j * p.cols_out + col) * poly;
-            fused_bottom<0, L>(smem + 0 * G::PLANE, a + 0 * n, poly, mc + 0 * n, m_stride, p.R, tw + 0 * n, t);
-            fused_bottom<1, L>(smem + 1 * G::PLANE, a + 1 * n, poly, mc + 1 * n, m_stride, p.R, tw + 1 * n, t);
-            fused_bottom<2, L>(smem + 2 * G::PLANE, a + 2 * n, poly, mc + 2 * n, m_stride, p.R, tw + 2 * n, t);
-            fused_bottom<3, L>(smem + 3 * G::PLANE, a + 3 * n, poly, mc + 3 * n, m_stride, p.R, tw + 3 * n, t);
+            if (p.direct) {
+                const uint32_t *src = a + ((size_t)j * p.cols_out + col) * poly;
+                fused_bottom_direct<0, L>(smem + 0 * G::PLANE, src + 0 * n, tw + 0 * n, t);
+                fused_bottom_direct<1, L>(smem + 1 * G::PLANE, src + 1 * n, tw + 1 * n, t);
+                fused_bottom_direct<2, L>(smem + 2 * G::PLANE, src + 2 * n, tw + 2 * n, t);
+                fused_bottom_direct<3, L>(smem + 3 * G::PLANE, src + 3 * n, tw + 3 * n, t);
+            } else {
+                const uint32_t *mc = pm + ((size_t)j * p.cols_out + col) * poly;
+                fused_bottom<0, L>(smem + 0 * G::PLANE, a + 0 * n, poly, mc + 0 * n, m_stride, p.R, tw + 0 * n, t);
+                fused_bottom<1, L>(smem + 1 * G::PLANE, a + 1 * n, poly, mc + 1 * n, m_stride, p.R, tw + 1 * n, t);
+                fused_bottom<2, L>(smem + 2 * G::PLANE, a + 2 * n, poly, mc + 2 * n, m_stride, p.R, tw + 2 * n, t);
+                fused_bottom<3, L>(smem + 3 * G::PLANE, a + 3 * n, poly, mc + 3 * n, m_stride, p.R, tw + 3 * n, t);
+            }
             __syncthreads();
             InvMid<L, (L - 6 >= G::R0) ? L - 6 : -1>::run(smem, tw, n, t);
             fused_top<0, L>(smem + 0 * G::PLANE, tw + 0 * n, t, nc);
@@ -1091,12 +1111,13 @@ static uint32_t pow2_mod_q(uint64_t e, uint32_t q) {
 int ntt120_fused_back(pgb_module *m, const char *a_dft, uint64_t a_bs, const char *pmat, int R, int C, int cols_out, const char *small,
                       uint64_t small_bs, uint64_t small_limb_stride, int small_size, char *res, uint64_t res_bs, uint64_t res_limb_stride,
                       int res_size, int base2k, int64_t res_offset, int batch, const char *glwe, uint64_t glwe_bs, uint64_t glwe_words,
-                      const int *skip, bool skip_list) {
+                      const int *skip, bool skip_list, bool direct, bool small_all_cols) {
     FusedArgs p;
     memset(&p, 0, sizeof p);
     p.a_dft = a_dft; p.a_bs = a_bs; p.pmat = pmat; p.small = small; p.small_bs = small_bs; p.small_limb_stride = small_limb_stride;
     p.small_size = small_size; p.res = res; p.res_bs = res_bs; p.res_limb_stride = res_limb_stride;
     p.R = R; p.C = C; p.cols_out = cols_out;
+    p.direct = direct ? 1 : 0; p.small_all_cols = small_all_cols ? 1 : 0;
     p.K = base2k; p.res_size = res_size; p.a_size = C / cols_out;
     int64_t lsh = res_offset % base2k, lo = res_offset / base2k;
     if (res_offset < 0 && lsh != 0) {
@@ -1115,7 +1136,7 @@ int ntt120_fused_back(pgb_module *m, const char *a_dft, uint64_t a_bs, const cha
     const int S = p.a_size;
     const uint64_t key_bytes = (uint64_t)R * C * poly_bytes;
     const int *ok = skip;
-    const bool try_collapse = glwe && !skip && res_offset == 0 && S >= 2 && S <= 32 && (int64_t)batch * cols_out >= 64 && key_bytes <= ((uint64_t)64 << 20) &&
+    const bool try_collapse = glwe && !skip && !direct && res_offset == 0 && S >= 2 && S <= 32 && (int64_t)batch * cols_out >= 64 && key_bytes <= ((uint64_t)64 << 20) &&
                               (S - 1) * base2k + 3 < 118 && !getenv("PGB_NO_COLLAPSE");
     if (try_collapse) {
         // workspace: [collapsed key | key coefficients (i128) | key_bits | ok flags]
