@@ -64,6 +64,15 @@ static int gadget_product(pgb_module *m, pgb_vec_znx_dft *res, const pgb_vec_znx
     return PGB_OK;
 }
 
+// The collapsed key needs |V| < 2^118: bits(a) + bits(key) + ceil(log2(R n)) + (S - 1) K + 3 <= 118 (decided exactly on the device).  With
+// dsize > 1 a flagged ciphertext costs a redo of the whole batch, so the single-kernel route is only tried when normalised operands
+// (K-bit digits on both sides) would pass; long keys (S K beyond ~85 bits) go straight to the limb-wise sequence.
+static bool gadget_likely_fits(uint64_t n, uint64_t R, uint64_t S, uint64_t K) {
+    uint64_t rn = 0;
+    while (((uint64_t)1 << rn) < R * n) rn++;
+    return rn + (S - 1) * K + 3 + 2 * K <= 118;
+}
+
 // ---- key-switch --------------------------------------------------------------------------------------------------------
 extern "C" size_t pgb_glwe_keyswitch_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t a_size, uint64_t a_base2k,
                                                const pgb_vmp_pmat *key, uint64_t key_base2k, uint64_t dsize, uint64_t batch) {
@@ -151,6 +160,24 @@ extern "C" int pgb_glwe_keyswitch_batched(pgb_module *m, pgb_vec_znx *res, uint6
                                  (int)cols_out, (const char *)ain.data, ain_bs, ain.cols * n * 8, small_size,
                                  (char *)res->data, bt->stride_res, res->cols * n * 8, (int)res->size, (int)key_base2k, 0, (int)B,
                                  (const char *)ain.data, ain_bs, n * ain.cols * ain.size);
+    }
+    if (dsize > 1 && res_base2k == key_base2k && m->flavour == PGB_NTT120 && !getenv("PGB_NO_FUSION") &&
+        ntt120_gadget_supported(m, (int)(rank_in * ain.size), (int)cols_out, (int)key->size, (int)key_base2k, (int)B) &&
+        gadget_likely_fits(n, rank_in * ain.size, key->size, key_base2k)) {
+        // digit groups folded into the collapsed key (ntt120_gadget_fused): same single kernel as dsize == 1.  The per-limb fallback for
+        // flagged ciphertexts is the generic sequence below, so the count of flagged ones is read back (one 4-byte copy + sync).
+        const size_t mark = ar.used;
+        int *ok = (int *)ar.take((2 * B + 1) * sizeof(int));
+        PGB_REQUIRE(ok != nullptr, "glwe_keyswitch: scratch exhausted");
+        PGB_TRY(ntt120_gadget_fused(m, (const char *)ain.data, ain_bs, (int)ain.cols, (int)rank_in, 1, (int)(rank_in * ain.size), (const char *)key->data,
+                                    (int)(cols_out * key->size), (int)cols_out, (int)umin64(ain.size, key->size), (char *)res->data, bt->stride_res,
+                                    (int)res->size, (int)key_base2k, (int)B, ok, (int)dsize, (int)ain.size, (int)(key->rows * key->cols_in),
+                                    (int)key->rows));
+        int nfail = 0;
+        PGB_CHECK_CUDA(cudaMemcpyAsync(&nfail, ok + B, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+        PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+        if (nfail == 0) return PGB_OK;
+        ar.used = mark; // some integers could leave the collapsed-key bound: redo the batch limb by limb
     }
     for (uint64_t c = 0; c < rank_in; c++) PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &a_dft, c, &ain, c + 1, &btd));
     pgb_vec_znx_dft ai = a_dft, tmp = res_dft;
@@ -263,6 +290,22 @@ extern "C" int pgb_glwe_external_product_batched(pgb_module *m, pgb_vec_znx *res
         pgb_batch btv = {B, res_dft_bs, a_dft_bs, 0};
         PGB_TRY(vmp_apply_impl(m, &res_dft, &a_dft, ggsw, 0, &btv));
     } else {
+        if (res_base2k == ggsw_base2k && m->flavour == PGB_NTT120 && !getenv("PGB_NO_FUSION") &&
+            ntt120_gadget_supported(m, (int)(cols * a_size), (int)cols, (int)ggsw->size, (int)ggsw_base2k, (int)B) &&
+            gadget_likely_fits(n, cols * a_size, ggsw->size, ggsw_base2k)) {
+            // digit groups folded into the collapsed key, as in the key-switch; no bound on the limbs of a group here (:233)
+            const size_t mark = ar.used;
+            int *ok = (int *)ar.take((2 * B + 1) * sizeof(int));
+            PGB_REQUIRE(ok != nullptr, "glwe_external_product: scratch exhausted");
+            PGB_TRY(ntt120_gadget_fused(m, (const char *)ain.data, ain_bs, (int)ain.cols, (int)cols, 0, (int)(cols * a_size), (const char *)ggsw->data,
+                                        (int)(cols * ggsw->size), (int)cols, 0, (char *)res->data, bt->stride_res, (int)res->size, (int)ggsw_base2k,
+                                        (int)B, ok, (int)dsize, (int)a_size, (int)(ggsw->rows * ggsw->cols_in), 0));
+            int nfail = 0;
+            PGB_CHECK_CUDA(cudaMemcpyAsync(&nfail, ok + B, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+            PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+            if (nfail == 0) return PGB_OK;
+            ar.used = mark; // redo the batch limb by limb
+        }
         PGB_CHECK_CUDA(cudaMemsetAsync(res_dft.data, 0, B * res_dft_bs, m->stream)); // res_dft.zero() (:123)
         pgb_vec_znx_dft tmp = mk(ar.take(B * res_dft_bs), n, cols, ggsw->size);
         PGB_REQUIRE(tmp.data, "glwe_external_product: scratch exhausted");

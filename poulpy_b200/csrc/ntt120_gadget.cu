@@ -607,6 +607,9 @@ struct CollapseArgs2 {
     const char *pmat;
     uint32_t *out;
     int n, R, C, cols_out, S;
+    // output row r (the r-th input poly of the gadget kernel) <- key row src_row[r], key limbs shifted by di[r], limbs j < jmax[r] only
+    // (dsize == 1: src_row = r, di = 0, jmax = S; dsize > 1: the digit groups of keyswitching/glwe.rs:332-379, see ntt120_gadget_fused)
+    signed char src_row[8], di[8], jmax[8];
     uint32_t c[32][4];
 };
 __global__ void __launch_bounds__(256) gadget_collapse_key_kernel(CollapseArgs2 p) {
@@ -617,10 +620,11 @@ __global__ void __launch_bounds__(256) gadget_collapse_key_kernel(CollapseArgs2 
     const PrimeRt pr(k);
     const int r = blockIdx.y / p.cols_out, col = blockIdx.y % p.cols_out;
     const size_t poly4 = (size_t)4 * n4; // uint4 per poly
-    const uint4 *src = reinterpret_cast<const uint4 *>(p.pmat) + ((size_t)r * p.C + col) * poly4 + (size_t)k * n4 + u;
+    const int jm = p.jmax[r], di = p.di[r];
+    const uint4 *src = reinterpret_cast<const uint4 *>(p.pmat) + ((size_t)p.src_row[r] * p.C + (size_t)di * p.cols_out + col) * poly4 + (size_t)k * n4 + u;
     unsigned long long acc[4] = {0, 0, 0, 0};
-    for (int j0 = 0; j0 < p.S; j0 += 16) {
-        const int j1 = min(j0 + 16, p.S);
+    for (int j0 = 0; j0 < jm; j0 += 16) {
+        const int j1 = min(j0 + 16, jm);
         for (int j = j0; j < j1; j++) {
             const uint4 v = __ldg(src + (size_t)j * p.cols_out * poly4);
             const unsigned long long cj = p.c[j][k];
@@ -696,12 +700,22 @@ bool ntt120_gadget_supported(const pgb_module *m, int R, int cols_out, int S, in
 
 // ok_out (device, 2 * batch + 1 ints, caller scratch): ok[b] = 1 where the ciphertext was finished here, 0 where the per-limb route is
 // needed; ok[batch] = number of the latter, ok[batch + 1 ..] = their indices
+//
+// dsize > 1 (keyswitching/glwe.rs:332-379, external_product/glwe.rs:225-270): input limb l belongs to digit group di = dsize-1 - l % dsize
+// and is the (l / dsize)-th limb of that group; the group is multiplied by the key with its limbs shifted by di (vmp limb_offset) into
+// the first size_di = S - max(dsize-di-2, 0) output limbs.  By linearity the collapsed key of input poly (l, ci) is therefore
+//     sum_{j < min(S - di, size_di)} 2^((S-1-j)K) key[(l / dsize) * row_cols + ci][(j + di) * cols_out + col]
+// and the kernel itself is unchanged: R = a_size * row_cols input polys in their natural order.  `key_rows` = rows * cols_in of the key,
+// `group_limit` = the reference's bound on the limbs of a digit group (dnum for the key-switch, none = 0 for the external product).
 int ntt120_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_cols, int row_cols, int row_col0, int R, const char *pmat,
-                        int C, int cols_out, int small_size, char *res, uint64_t res_bs, int res_size, int base2k, int batch, int *ok_out) {
+                        int C, int cols_out, int small_size, char *res, uint64_t res_bs, int res_size, int base2k, int batch, int *ok_out,
+                        int dsize, int a_size, int key_rows, int group_limit) {
     const uint64_t n = m->n, poly_bytes = 16 * n;
     const int S = C / cols_out;
+    if (dsize < 1) dsize = 1;
+    if (dsize == 1) key_rows = R;
     // workspace: [collapsed key | key coefficients (i128) | key_bits]
-    const uint64_t ck_bytes = (uint64_t)R * cols_out * poly_bytes, key_bytes = (uint64_t)R * C * poly_bytes;
+    const uint64_t ck_bytes = (uint64_t)R * cols_out * poly_bytes, key_bytes = (uint64_t)key_rows * C * poly_bytes;
     const uint64_t need = ck_bytes + key_bytes + 256;
     if (m->aux_len < need) {
         if (m->aux_ws) {
@@ -720,11 +734,25 @@ int ntt120_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_co
     ca.pmat = pmat; ca.out = (uint32_t *)ck; ca.n = (int)n; ca.R = R; ca.C = C; ca.cols_out = cols_out; ca.S = S;
     for (int j = 0; j < S; j++)
         for (int k = 0; k < 4; k++) ca.c[j][k] = pow2_mod((uint64_t)(S - 1 - j) * base2k, qk(k));
+    for (int r = 0; r < R; r++) {
+        if (dsize == 1) {
+            ca.src_row[r] = (signed char)r; ca.di[r] = 0; ca.jmax[r] = (signed char)S;
+            continue;
+        }
+        const int l = r / row_cols, ci = r % row_cols, di = dsize - 1 - l % dsize, jl = l / dsize;
+        int group = (a_size + di) / dsize; // limbs of digit group di
+        if (group_limit > 0 && group > group_limit) group = group_limit;
+        const int src = jl * row_cols + ci;
+        const int cut = dsize - di - 2, size_di = S - (cut > 0 ? cut : 0);
+        int jm = S - di < size_di ? S - di : size_di;
+        if (jl >= group || src >= key_rows || jm < 0) jm = 0; // this limb takes no part: its collapsed key is zero
+        ca.src_row[r] = (signed char)(jm ? src : 0); ca.di[r] = (signed char)(jm ? di : 0); ca.jmax[r] = (signed char)jm;
+    }
     { ProfScope _ps(m, PROF_OTHER);
     gadget_collapse_key_kernel<<<dim3(((unsigned)(n / 4) + 255) / 256, R * cols_out, 4), 256, 0, m->stream>>>(ca);
     }
     PGB_CHECK_CUDA(cudaGetLastError());
-    PGB_TRY(ntt120_key_max_bits(m, pmat, R * C, kcoef, key_bits));
+    PGB_TRY(ntt120_key_max_bits(m, pmat, key_rows * C, kcoef, key_bits));
 
     GadgetArgs p;
     memset(&p, 0, sizeof p);

@@ -422,3 +422,50 @@ def test_full_bench_batch_4096(fl, ext):
     got = g.vec_znx_to_numpy(res)
     bad = [b for b in range(batch) if not np.array_equal(got[b], want[perm[b]])]
     assert not bad, (bad[:10], len(bad))
+
+
+@pytest.mark.parametrize("dsize", [2, 3])
+@pytest.mark.parametrize("n", [1024, 4096])
+def test_gadget_kernel_dsize(dsize, n):
+    """dsize > 1 through the single-kernel NTT120 path (the digit groups of keyswitching/glwe.rs:332-379 folded into the collapsed key):
+    key-switch and external product, ranks 1..2, input sizes that are / are not multiples of dsize, fewer key rows than digit groups,
+    a flagged ciphertext (whole batch redone limb by limb) -- bit for bit against the oracle."""
+    g, o = pb.Module(n, pb.NTT120), O.OracleModule(n, pb.NTT120)
+    rng = np.random.default_rng(1600 + dsize + n)
+    k, batch = 18, 9
+    #        rank_in rank_out a_size dnum key_size res_size
+    shapes = ((1, 1, 4, -1, 5, 4), (1, 1, 3, -1, 4, 3), (2, 1, 4, -1, 5, 3), (1, 2, 5, -1, 4, 6), (1, 1, 6, 1, 4, 4), (1, 1, 2, -1, 3, 3))
+    for rank_in, rank_out, a_size, dnum, key_size, res_size in shapes:
+        dnum = -(-a_size // dsize) if dnum < 0 else dnum
+        pg, po = _key(g, o, rng, dnum, rank_in, rank_out + 1, key_size, k)
+        for flagged in (False, True):
+            a = fill_uniform(rng, (batch, a_size, rank_in + 1, n), k)
+            if flagged:
+                a[4, 0, 1, 7] = 1 << 61
+            want = fill_uniform(rng, (batch, res_size, rank_out + 1, n), k)
+            res_g = g.vec_znx_from_numpy(want)
+            a_g = g.vec_znx_from_numpy(a)
+            l0 = g.launch_count
+            g.glwe_keyswitch(res_g, k, a_g, k, pg, k, dsize)
+            g.sync()
+            launches = g.launch_count - l0
+            o.glwe_keyswitch_batch(want, k, a, k, po, k, dsize)
+            got = g.vec_znx_to_numpy(res_g)
+            bad = [b for b in range(batch) if not np.array_equal(got[b], want[b])]
+            assert not bad, ("ks", rank_in, rank_out, a_size, dnum, key_size, res_size, flagged, bad)
+            if key_size <= 4 and not flagged:  # short keys fit the collapsed form: one product kernel + its three key pre-passes
+                assert launches <= 5, (launches, rank_in, rank_out, a_size, key_size)
+            elif key_size <= 4:
+                assert launches > 8, launches  # the flagged batch was redone by the limb-wise sequence
+    for rank, a_size, g_size, res_size in ((1, 4, 5, 4), (1, 3, 3, 3), (2, 2, 3, 2), (1, 4, 2, 5)):
+        dnum = -(-a_size // dsize)
+        pg, po = _key(g, o, rng, dnum, rank + 1, rank + 1, g_size, k)
+        a = fill_uniform(rng, (batch, a_size, rank + 1, n), k)
+        want = fill_uniform(rng, (batch, res_size, rank + 1, n), k)
+        res_g = g.vec_znx_from_numpy(want)
+        g.glwe_external_product(res_g, k, g.vec_znx_from_numpy(a), k, pg, k, dsize)
+        g.sync()
+        o.glwe_external_product_batch(want, k, a, k, po, k, dsize)
+        got = g.vec_znx_to_numpy(res_g)
+        bad = [b for b in range(batch) if not np.array_equal(got[b], want[b])]
+        assert not bad, ("ep", rank, a_size, g_size, res_size, bad)
