@@ -161,6 +161,11 @@ extern "C" int pgb_glwe_keyswitch_batched(pgb_module *m, pgb_vec_znx *res, uint6
                                  (char *)res->data, bt->stride_res, res->cols * n * 8, (int)res->size, (int)key_base2k, 0, (int)B,
                                  (const char *)ain.data, ain_bs, n * ain.cols * ain.size);
     }
+    if (dsize == 2 && res_base2k == key_base2k && m->flavour == PGB_FFT64 && !getenv("PGB_NO_FUSION") && rank_in * ain.size <= 16 &&
+        fft64_gadget_supported(m, (int)(rank_in * ain.size), (int)cols_out, (int)key->size, (int)key_base2k, (int)B))
+        return fft64_gadget_fused(m, (const char *)ain.data, ain_bs, (int)ain.cols, (int)rank_in, 1, (int)(rank_in * ain.size), (const char *)key->data,
+                                  (int)(cols_out * key->size), (int)cols_out, (int)umin64(ain.size, key->size), (char *)res->data, bt->stride_res,
+                                  (int)res->size, (int)key_base2k, (int)B, 2, (int)ain.size, (int)(key->rows * key->cols_in), (int)key->rows);
     if (dsize > 1 && res_base2k == key_base2k && m->flavour == PGB_NTT120 && !getenv("PGB_NO_FUSION") &&
         ntt120_gadget_supported(m, (int)(rank_in * ain.size), (int)cols_out, (int)key->size, (int)key_base2k, (int)B) &&
         gadget_likely_fits(n, rank_in * ain.size, key->size, key_base2k)) {
@@ -290,6 +295,11 @@ extern "C" int pgb_glwe_external_product_batched(pgb_module *m, pgb_vec_znx *res
         pgb_batch btv = {B, res_dft_bs, a_dft_bs, 0};
         PGB_TRY(vmp_apply_impl(m, &res_dft, &a_dft, ggsw, 0, &btv));
     } else {
+        if (dsize == 2 && res_base2k == ggsw_base2k && m->flavour == PGB_FFT64 && !getenv("PGB_NO_FUSION") && cols * a_size <= 16 &&
+            fft64_gadget_supported(m, (int)(cols * a_size), (int)cols, (int)ggsw->size, (int)ggsw_base2k, (int)B))
+            return fft64_gadget_fused(m, (const char *)ain.data, ain_bs, (int)ain.cols, (int)cols, 0, (int)(cols * a_size), (const char *)ggsw->data,
+                                      (int)(cols * ggsw->size), (int)cols, 0, (char *)res->data, bt->stride_res, (int)res->size, (int)ggsw_base2k,
+                                      (int)B, 2, (int)a_size, (int)(ggsw->rows * ggsw->cols_in), 0);
         if (res_base2k == ggsw_base2k && m->flavour == PGB_NTT120 && !getenv("PGB_NO_FUSION") &&
             ntt120_gadget_supported(m, (int)(cols * a_size), (int)cols, (int)ggsw->size, (int)ggsw_base2k, (int)B) &&
             gadget_likely_fits(n, cols * a_size, ggsw->size, ggsw_base2k)) {

@@ -34,6 +34,9 @@ struct FGadgetArgs {
     int in_cols, row_cols, row_col0, R, C, cols_out;
     int small_size;                              // limbs of input column 0 added to output column 0 (key-switch), 0 = none
     int K, S, res_size, batch;
+    // input poly r (limb r / row_cols) multiplies key row src_row[r] with its limbs shifted by di[r], into output limbs j < jmax[r] only
+    // (dsize == 1: src_row = r, di = 0, jmax = S; dsize == 2: the digit groups of keyswitching/glwe.rs:332-379, see fft64_gadget_fused)
+    signed char src_row[16], di[16], jmax[16];
     double inv_m;
 };
 
@@ -168,15 +171,14 @@ fft64_gadget_kernel(const __grid_constant__ FGadgetArgs p, const double2 *__rest
             const bool valid = jl < S;
             double2 x[8];
             if (valid) {
-                const int poly = j * cols_out + c;
 #pragma unroll
                 for (int jj = 0; jj < 8; jj++) x[jj] = make_double2(0.0, 0.0);
-                const double2 *kp = reinterpret_cast<const double2 *>(p.pmat + (size_t)poly * N) + t;
-                const size_t krow = (size_t)p.C * M; // double2 per key row
+                const double2 *kp = reinterpret_cast<const double2 *>(p.pmat) + t; // + key poly index * M
                 // rows accumulate in row order (reim4_add_mul, reim4/arithmetic_ref.rs:223-232), FMA-contracted; the key values come from L2
                 // in the kernel's own layout: load q of a warp covers 512 contiguous bytes
                 for (int r = 0; r < R; r++) {
-                    const double2 *kr = kp + (size_t)r * krow, *ki = kr + M / 2;
+                    if (j >= p.jmax[r]) continue; // CTA-uniform per slot: this input limb does not reach output limb j
+                    const double2 *kr = kp + ((size_t)p.src_row[r] * p.C + (size_t)(j + p.di[r]) * cols_out + c) * M, *ki = kr + M / 2;
                     double br[8], bi[8];
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
@@ -347,17 +349,42 @@ bool fft64_gadget_supported(const pgb_module *m, int R, int cols_out, int S, int
     return plan(m, R, cols_out, S, &lpr, &tws, &smem);
 }
 
+// dsize == 2: R = a_size * row_cols input polys in their natural order, `key_rows` = rows * cols_in of the key, `group_limit` = bound on
+// the limbs of a digit group (dnum for the key-switch, 0 = none for the external product); the row mapping is the one of
+// ntt120_gadget_fused.  (dsize >= 3 is not offered: there the reference's FFT64 vmp leaves stale limbs in its temporary, fft64/vmp.rs:263.)
 int fft64_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_cols, int row_cols, int row_col0, int R, const char *pmat, int C,
-                       int cols_out, int small_size, char *res, uint64_t res_bs, int res_size, int base2k, int batch) {
+                       int cols_out, int small_size, char *res, uint64_t res_bs, int res_size, int base2k, int batch, int dsize, int a_size,
+                       int key_rows, int group_limit) {
     FGadgetArgs p;
     memset(&p, 0, sizeof p);
+    if (dsize < 1) dsize = 1;
+    if (dsize == 1) key_rows = R;
+    if (R > 16) {
+        pgb_set_error("fft64 gadget kernel: more than 16 input polys");
+        return PGB_ERR_UNSUPPORTED;
+    }
+    for (int r = 0; r < R; r++) {
+        const int S = C / cols_out;
+        if (dsize == 1) {
+            p.src_row[r] = (signed char)r; p.di[r] = 0; p.jmax[r] = (signed char)S;
+            continue;
+        }
+        const int l = r / row_cols, ci = r % row_cols, di = dsize - 1 - l % dsize, jl = l / dsize;
+        int group = (a_size + di) / dsize;
+        if (group_limit > 0 && group > group_limit) group = group_limit;
+        const int src = jl * row_cols + ci;
+        const int cut = dsize - di - 2, size_di = S - (cut > 0 ? cut : 0);
+        int jm = S - di < size_di ? S - di : size_di;
+        if (jl >= group || src >= key_rows || jm < 0) jm = 0;
+        p.src_row[r] = (signed char)(jm ? src : 0); p.di[r] = (signed char)(jm ? di : 0); p.jmax[r] = (signed char)jm;
+    }
     p.in = in; p.in_bs = in_bs; p.res = res; p.res_bs = res_bs; p.pmat = (const double *)pmat;
     p.in_cols = in_cols; p.row_cols = row_cols; p.row_col0 = row_col0; p.R = R; p.C = C; p.cols_out = cols_out; p.small_size = small_size;
     p.K = base2k; p.S = C / cols_out; p.res_size = res_size; p.batch = batch;
     p.inv_m = 1.0 / (double)(m->n / 2);
     // workspace: the key in the kernel's layout
     const uint64_t M = m->n / 2;
-    const uint64_t key_bytes = (uint64_t)R * C * m->n * 8, need = key_bytes + 256;
+    const uint64_t key_bytes = (uint64_t)key_rows * C * m->n * 8, need = key_bytes + 256;
     if (m->aux_len < need) {
         if (m->aux_ws) {
             PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
@@ -370,7 +397,7 @@ int fft64_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_col
     }
     double2 *kperm = (double2 *)m->aux_ws;
     { ProfScope _ps(m, PROF_OTHER);
-    fft64_gadget_key_kernel<<<dim3(((unsigned)(M / 2) + 255) / 256, R * C, 2), 256, 0, m->stream>>>((const double *)pmat, kperm, (int)M, R * C);
+    fft64_gadget_key_kernel<<<dim3(((unsigned)(M / 2) + 255) / 256, key_rows * C, 2), 256, 0, m->stream>>>((const double *)pmat, kperm, (int)M, key_rows * C);
     }
     PGB_CHECK_CUDA(cudaGetLastError());
     p.pmat = (const double *)kperm;

@@ -6,7 +6,7 @@ import poulpy_b200 as pb
 n, k, B, dsize = 4096, 18, 4096, 2
 stream = torch.cuda.Stream()
 rng = np.random.default_rng(1)
-m = pb.Module(n, pb.NTT120); m.set_stream(stream.cuda_stream)
+m = pb.Module(n, pb.FFT64 if os.environ.get("KS_FLAVOUR") == "fft64" else pb.NTT120); m.set_stream(stream.cuda_stream)
 mat = rng.integers(-(1 << 17), 1 << 17, size=(2, 1, 4, 2, n), dtype=np.int64)
 pm = m.vmp_pmat_alloc(2, 1, 2, 4)
 m.vmp_prepare(pm, m.mat_znx_from_numpy(mat))

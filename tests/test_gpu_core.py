@@ -469,3 +469,46 @@ def test_gadget_kernel_dsize(dsize, n):
         got = g.vec_znx_to_numpy(res_g)
         bad = [b for b in range(batch) if not np.array_equal(got[b], want[b])]
         assert not bad, ("ep", rank, a_size, g_size, res_size, bad)
+
+
+@pytest.mark.parametrize("n", [1024, 4096])
+def test_fft64_gadget_kernel_dsize2(n):
+    """dsize = 2 through the single-kernel FFT64 path (per-row key limb shift instead of limb_offset vmp + dft_add_assign): key-switch and
+    external product against the oracle's FFT64 restatement, with the launch count proving the fused route was taken."""
+    g, o = pb.Module(n, pb.FFT64), O.OracleModule(n, pb.FFT64)
+    rng = np.random.default_rng(1700 + n)
+    k, batch, dsize = 13, 11, 2
+    #        rank_in rank_out a_size dnum key_size res_size
+    shapes = ((1, 1, 4, -1, 5, 4), (1, 1, 3, -1, 4, 3), (1, 2, 4, -1, 3, 5), (1, 1, 4, 1, 4, 4), (1, 1, 2, -1, 3, 3))
+    for rank_in, rank_out, a_size, dnum, key_size, res_size in shapes:
+        dnum = -(-a_size // dsize) if dnum < 0 else dnum
+        pg, po = _key(g, o, rng, dnum, rank_in, rank_out + 1, key_size, k)
+        a = fill_uniform(rng, (batch, a_size, rank_in + 1, n), k)
+        want = fill_uniform(rng, (batch, res_size, rank_out + 1, n), k)
+        res_g, a_g = g.vec_znx_from_numpy(want), g.vec_znx_from_numpy(a)
+        l0 = g.launch_count
+        g.glwe_keyswitch(res_g, k, a_g, k, pg, k, dsize)
+        g.sync()
+        fits = (rank_out + 1) * (n // 16) <= 512 and (rank_in * a_size + rank_out + 1) * (n // 2 + n // 16 + 2) * 16 <= 227 * 1024
+        if fits:  # slots and planes fit one CTA: key re-layout + the product kernel, nothing else
+            assert g.launch_count - l0 <= 2, (g.launch_count - l0, rank_in, rank_out, a_size, key_size)
+        o.glwe_keyswitch_batch(want, k, a, k, po, k, dsize)
+        got = g.vec_znx_to_numpy(res_g)
+        bad = [b for b in range(batch) if not np.array_equal(got[b], want[b])]
+        assert not bad, ("ks", rank_in, rank_out, a_size, dnum, key_size, res_size, bad)
+    for rank, a_size, g_size, res_size in ((1, 2, 3, 2), (1, 3, 3, 4)):
+        if (rank + 1) * a_size > (4 if n == 4096 else 8):
+            continue
+        dnum = -(-a_size // dsize)
+        pg, po = _key(g, o, rng, dnum, rank + 1, rank + 1, g_size, k)
+        a = fill_uniform(rng, (batch, a_size, rank + 1, n), k)
+        want = fill_uniform(rng, (batch, res_size, rank + 1, n), k)
+        res_g, a_g = g.vec_znx_from_numpy(want), g.vec_znx_from_numpy(a)
+        l0 = g.launch_count
+        g.glwe_external_product(res_g, k, a_g, k, pg, k, dsize)
+        g.sync()
+        assert g.launch_count - l0 <= 2, (g.launch_count - l0, rank, a_size, g_size)
+        o.glwe_external_product_batch(want, k, a, k, po, k, dsize)
+        got = g.vec_znx_to_numpy(res_g)
+        bad = [b for b in range(batch) if not np.array_equal(got[b], want[b])]
+        assert not bad, ("ep", rank, a_size, g_size, res_size, bad)
