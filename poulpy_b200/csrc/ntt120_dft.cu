@@ -27,6 +27,11 @@ template <int L> struct Geo {
     static constexpr int PLANE = NB + (NB >> 5) * 4 + 4;   // padded words per prime plane
 };
 
+// resident CTAs the register budget of the stand-alone transforms is sized for: two CTAs of 512 threads at n = 4096 (one CTA of 16 warps per SM
+// at 100 registers left the passes latency bound), unconstrained below
+#ifndef NTT_MINB
+#define NTT_MINB(threads) (((threads) >= 128 && (threads) <= 512) ? 1024 / (threads) : 1)
+#endif
 template <int K, int NLEV> __device__ __forceinline__ void ct_radix8(uint32_t (&x)[8], const uint2 *__restrict__ tw, uint32_t hi) {
     constexpr uint32_t q = Prime<K>::q;
     {
@@ -174,7 +179,7 @@ template <int L, int LPC> __device__ __forceinline__ void ntt120_fwd_job(const N
     }
 }
 
-template <int L, int LPC> __global__ void __launch_bounds__(Geo<L>::T *LPC) ntt120_fwd_kernel(NttJobs jb, const uint2 *__restrict__ tw) {
+template <int L, int LPC> __global__ void __launch_bounds__(Geo<L>::T *LPC, NTT_MINB(Geo<L>::T *LPC)) ntt120_fwd_kernel(NttJobs jb, const uint2 *__restrict__ tw) {
     typedef Geo<L> G;
     extern __shared__ __align__(16) uint32_t smem[];
     const int slot = threadIdx.x / G::T, t = threadIdx.x % G::T;
@@ -291,7 +296,7 @@ __device__ __forceinline__ i128 crt_finish(u128 v) {
 }
 
 // OUT_I128 = true : write centred i128 coefficients (VecZnxBig of the NTT120 flavour)
-template <int L, int LPC> __global__ void __launch_bounds__(Geo<L>::T *LPC) ntt120_inv_kernel(NttJobs jb, const uint2 *__restrict__ tw,
+template <int L, int LPC> __global__ void __launch_bounds__(Geo<L>::T *LPC, NTT_MINB(Geo<L>::T *LPC)) ntt120_inv_kernel(NttJobs jb, const uint2 *__restrict__ tw,
                                                                                              Ntt120Consts nc) {
     typedef Geo<L> G;
     extern __shared__ __align__(16) uint32_t smem[];
