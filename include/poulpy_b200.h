@@ -345,6 +345,13 @@ size_t pgb_glwe_trace_assign_tmp_bytes(const pgb_module *m, uint64_t res_size, u
 int pgb_glwe_trace_assign_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, uint64_t skip, const pgb_vmp_pmat *keys, uint64_t nkeys,
                                   uint64_t key_base2k, uint64_t dsize, const pgb_batch *bt, void *scratch, size_t scratch_len);
 
+/* ggsw_expand_row (poulpy-core/src/conversion/gglwe_to_ggsw.rs:116-268; CoreImpl `ggsw_expand_row`): columns 1..rank of a GGSW from its
+ * column-0 GLWEs and the tensor keys GGLWE(s[c] * s); `tsk` is a HOST array of rank prepared keys of identical shape */
+size_t pgb_ggsw_expand_row_tmp_bytes(const pgb_module *m, uint64_t rank, uint64_t size, uint64_t res_base2k, const pgb_vmp_pmat *tsk,
+                                     uint64_t tsk_base2k, uint64_t dsize, uint64_t batch);
+int pgb_ggsw_expand_row_batched(pgb_module *m, pgb_mat_znx *ggsw, uint64_t res_base2k, const pgb_vmp_pmat *tsk, uint64_t ntsk, uint64_t tsk_base2k,
+                                uint64_t dsize, const pgb_batch *bt, void *scratch, size_t scratch_len);
+
 /* ---- CGGI blind rotation (poulpy-bin-fhe/src/blind_rotation/algorithms/cggi/algorithm.rs:275-368; C3) ---- */
 /* x_pow_a table of the prepared key (cggi/key_prepared.rs:66-75): SvpPPol with 2n columns, col i = X^i. */
 int pgb_cggi_x_pow_a(pgb_module *m, pgb_svp_ppol *res);

@@ -399,3 +399,42 @@ void orc_glwe_trace_assign(int flavour, const void *mod, orc_vec_znx *res, size_
         orc_glwe_automorphism_add_assign(flavour, mod, res, res_base2k, keys[i], key_base2k, orc_trace_galois_element(i, n), dsize);
     }
 }
+
+/* ---- ggsw_expand_row (poulpy-core/src/conversion/gglwe_to_ggsw.rs:116-268; SURVEY 8f N4: the last step of circuit bootstrapping) ---------- */
+/* ggsw: MatZnx(dnum, rank+1, rank+1, size) whose column-0 GLWEs are filled; writes the GLWEs of columns 1..rank.  tsk[c] is the prepared
+ * GGLWE of s[c] * s (VmpPMat(dnum_tsk, rank, rank+1, size_tsk)), c < rank. */
+void orc_ggsw_expand_row(int flavour, const void *mod, int64_t *ggsw, size_t n, size_t dnum, size_t rank, size_t size, size_t res_base2k,
+                         const orc_vmp_pmat *const *tsk, size_t tsk_base2k, size_t dsize) {
+    be_t b = make_be(flavour, mod);
+    size_t cols = rank + 1, glwe_words = size * cols * n;
+    size_t conv = div_ceil(size * res_base2k, tsk_base2k); /* res.max_k().div_ceil(tsk_base2k) */
+    for (size_t row = 0; row < dnum; row++) {
+        orc_vec_znx mi = {ggsw + (row * cols + 0) * glwe_words, n, cols, size};
+        orc_vec_znx_dft a_dft = dft_alloc(&b, n, cols - 1, conv);
+        orc_vec_znx a_0 = {(int64_t *)calloc(n * conv, 8), n, 1, conv};
+        if (res_base2k == tsk_base2k) {
+            for (size_t c = 0; c + 1 < cols; c++) be_dft_apply(&b, 1, 0, &a_dft, c, &mi, c + 1);
+            for (size_t j = 0; j < size; j++) memcpy(a_0.data + j * n, mi.data + n * (j * cols + 0), 8 * n); /* vec_znx_copy */
+        } else {
+            for (size_t c = 0; c + 1 < cols; c++) {
+                orc_vec_znx_normalize(&a_0, tsk_base2k, 0, 0, &mi, res_base2k, c + 1, 0);
+                be_dft_apply(&b, 1, 0, &a_dft, c, &a_0, 0);
+            }
+            orc_vec_znx_normalize(&a_0, tsk_base2k, 0, 0, &mi, res_base2k, 0, 0);
+        }
+        /* ggsw_expand_rows_internal (:182-268) */
+        for (size_t col = 1; col < cols; col++) {
+            const orc_vmp_pmat *key = tsk[col - 1];
+            orc_vec_znx_dft res_dft = dft_alloc(&b, n, cols, key->size); /* zeroed */
+            gglwe_product_dft(&b, &res_dft, &a_dft, key, dsize);
+            be_idft_consume(&b, &res_dft);
+            orc_vec_znx_big res_big = {res_dft.data, n, res_dft.cols, res_dft.size};
+            be_big_add_small_assign(&b, &res_big, col, &a_0, 0);
+            orc_vec_znx out = {ggsw + (row * cols + col) * glwe_words, n, cols, size};
+            for (size_t j = 0; j < cols; j++) be_big_normalize(&b, &out, res_base2k, 0, j, &res_big, tsk_base2k, j);
+            free(res_dft.data);
+        }
+        free(a_dft.data);
+        free(a_0.data);
+    }
+}

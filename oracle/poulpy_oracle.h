@@ -189,6 +189,10 @@ int64_t orc_trace_galois_element(size_t i, size_t n);
 void orc_glwe_trace_assign(int flavour, const void *mod, orc_vec_znx *res, size_t res_base2k, size_t skip, const orc_vmp_pmat *const *keys,
                            size_t key_base2k, size_t dsize);
 
+/* poulpy-core/src/conversion/gglwe_to_ggsw.rs:116-268 */
+void orc_ggsw_expand_row(int flavour, const void *mod, int64_t *ggsw, size_t n, size_t dnum, size_t rank, size_t size, size_t res_base2k,
+                         const orc_vmp_pmat *const *tsk, size_t tsk_base2k, size_t dsize);
+
 /* ------------------------------------------------------------ bivariate convolution (HalImpl::cnv_*, hal_impl.rs:670-754) */
 /* CnvPVecL / CnvPVecR are opaque prepared layouts: this restatement keeps both in the VecZnxDft layout.
  * reference/ntt120/convolution.rs:66-236 (prepare_left / right / self), :256-335 (apply_dft), :441-557 (pairwise), :361-410 (by_const);

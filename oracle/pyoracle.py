@@ -343,6 +343,15 @@ class OracleModule:
         r = _vz(res)
         lib().orc_glwe_trace_assign(C.c_int(self.flavour), self._h, C.byref(r), _sz(res_base2k), _sz(skip), arr, _sz(key_base2k), _sz(dsize))
 
+    def ggsw_expand_row(self, ggsw, res_base2k, tsk, tsk_base2k, dsize=1):
+        """ggsw: int64 (dnum, rank+1, size, rank+1, n) with the column-0 GLWEs filled; tsk: list of rank prepared keys
+        (conversion/gglwe_to_ggsw.rs:116-268)."""
+        dnum, cols, size, cols2, n = ggsw.shape
+        assert cols == cols2 and len(tsk) == cols - 1
+        arr = (C.POINTER(_PM) * len(tsk))(*[C.pointer(k.struct()) for k in tsk])
+        lib().orc_ggsw_expand_row(C.c_int(self.flavour), self._h, _p(ggsw), _sz(n), _sz(dnum), _sz(cols - 1), _sz(size), _sz(res_base2k), arr,
+                                  _sz(tsk_base2k), _sz(dsize))
+
     def cggi_x_pow_a(self):
         res = self.svp_ppol_alloc(2 * self.n)
         r = _pp(res)

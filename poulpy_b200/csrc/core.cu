@@ -682,6 +682,89 @@ extern "C" int pgb_glwe_trace_assign_batched(pgb_module *m, pgb_vec_znx *res, ui
     return PGB_OK;
 }
 
+// ---- ggsw_expand_row (poulpy-core/src/conversion/gglwe_to_ggsw.rs:116-268): the GLWEs of columns 1..rank of a GGSW from
+// its column-0 GLWEs and the tensor keys GGLWE(s[c] * s) -- the last step of circuit bootstrapping.  Per row: the mask of the column-0
+// GLWE goes to the DFT domain once, then every column is a gadget product with tsk[col-1], the column-0 body added on output column `col`
+// (vec_znx_big_add_small_assign) and the normalisation of all output columns.
+extern "C" size_t pgb_ggsw_expand_row_tmp_bytes(const pgb_module *m, uint64_t rank, uint64_t size, uint64_t res_base2k, const pgb_vmp_pmat *tsk,
+                                                uint64_t tsk_base2k, uint64_t dsize, uint64_t batch) {
+    const uint64_t n = m->n, pb = prep_bytes(m), cols = rank + 1;
+    const uint64_t conv = res_base2k == tsk_base2k ? size : conv_size(size, res_base2k, tsk_base2k);
+    uint64_t t = align_up(batch * n * rank * conv * pb) + align_up(batch * n * conv * 8) + align_up(batch * n * cols * tsk->size * pb);
+    if (dsize > 1) t += align_up(batch * n * rank * div_ceil64(conv, dsize) * pb) + align_up(batch * n * cols * tsk->size * pb);
+    return t + ALIGN;
+}
+// ggsw: `count` MatZnx(dnum, rank+1, rank+1, size) (stride bt->stride_res bytes) with the column-0 GLWEs filled; tsk: HOST array of `rank`
+// prepared keys VmpPMat(dnum_tsk, rank, rank+1, size_tsk)
+extern "C" int pgb_ggsw_expand_row_batched(pgb_module *m, pgb_mat_znx *ggsw, uint64_t res_base2k, const pgb_vmp_pmat *tsk, uint64_t ntsk,
+                                           uint64_t tsk_base2k, uint64_t dsize, const pgb_batch *bt, void *scratch, size_t scratch_len) {
+    PGB_REQUIRE(bt && bt->count >= 1 && bt->count <= 65535, "ggsw_expand_row: batch count must be in [1, 65535]");
+    PGB_REQUIRE(ggsw->n == m->n && ggsw->cols_in == ggsw->cols_out && ggsw->cols_in >= 1, "ggsw_expand_row: not a GGSW of this ring");
+    const uint64_t n = m->n, pb = prep_bytes(m), B = bt->count, cols = ggsw->cols_in, rank = cols - 1, size = ggsw->size, dnum = ggsw->rows;
+    if (rank == 0) return PGB_OK;
+    PGB_REQUIRE(ntsk >= rank, "ggsw_expand_row: needs one tensor key per mask column");
+    for (uint64_t c = 0; c < rank; c++)
+        PGB_REQUIRE(tsk[c].n == n && tsk[c].cols_in == rank && tsk[c].cols_out == cols && tsk[c].size == tsk[0].size && tsk[c].rows == tsk[0].rows,
+                    "ggsw_expand_row: tensor key %llu has the wrong shape", (unsigned long long)c);
+    PGB_REQUIRE(dsize >= 1, "ggsw_expand_row: dsize must be >= 1");
+    const size_t need = pgb_ggsw_expand_row_tmp_bytes(m, rank, size, res_base2k, &tsk[0], tsk_base2k, dsize, B);
+    if (scratch_len < need) {
+        pgb_set_error("ggsw_expand_row: scratch of %zu bytes < required %zu", scratch_len, need);
+        return PGB_ERR_SCRATCH;
+    }
+    Arena ar = {(char *)scratch, scratch_len, 0};
+    const uint64_t conv = res_base2k == tsk_base2k ? size : conv_size(size, res_base2k, tsk_base2k);
+    const uint64_t a_dft_bs = n * rank * conv * pb, a0_bs = n * conv * 8, res_dft_bs = n * cols * tsk[0].size * pb, glwe_bytes = n * cols * size * 8;
+    pgb_vec_znx_dft a_dft = mk(ar.take(B * a_dft_bs), n, rank, conv);
+    pgb_vec_znx a_0 = mk(ar.take(B * a0_bs), n, 1, conv);
+    pgb_vec_znx_dft res_dft = mk(ar.take(B * res_dft_bs), n, cols, tsk[0].size);
+    pgb_vec_znx_dft ai = a_dft, tmp = res_dft;
+    uint64_t ai_bs = 0, tmp_bs = 0;
+    if (dsize > 1) {
+        const uint64_t ai_max = umin64(div_ceil64(conv, dsize), tsk[0].rows);
+        ai_bs = n * rank * ai_max * pb;
+        ai = mk(ar.take(B * ai_bs), n, rank, ai_max);
+        tmp_bs = res_dft_bs;
+        tmp = mk(ar.take(B * tmp_bs), n, cols, tsk[0].size);
+        PGB_REQUIRE(ai.data && tmp.data, "ggsw_expand_row: scratch exhausted");
+    }
+    for (uint64_t row = 0; row < dnum; row++) {
+        pgb_vec_znx mi = mk((char *)ggsw->data + (row * cols + 0) * glwe_bytes, n, cols, size); // res.at(row, 0)
+        const pgb_vec_znx *small = &mi; // column 0 of the row's GLWE joins output column `col`
+        uint64_t small_bs = bt->stride_res;
+        if (res_base2k == tsk_base2k) { // (:145-149)
+            pgb_batch btd = {B, a_dft_bs, bt->stride_res, 0};
+            for (uint64_t c = 0; c < rank; c++) PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &a_dft, c, &mi, c + 1, &btd));
+        } else { // (:150-156)
+            pgb_batch btn = {B, a0_bs, bt->stride_res, 0}, btd = {B, a_dft_bs, a0_bs, 0};
+            for (uint64_t c = 0; c < rank; c++) {
+                PGB_TRY(big_normalize_impl(m, &a_0, tsk_base2k, 0, 0, &mi, res_base2k, c + 1, 0, false, &btn));
+                PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &a_dft, c, &a_0, 0, &btd));
+            }
+            PGB_TRY(big_normalize_impl(m, &a_0, tsk_base2k, 0, 0, &mi, res_base2k, 0, 0, false, &btn));
+            small = &a_0;
+            small_bs = a0_bs;
+        }
+        for (uint64_t col = 1; col < cols; col++) { // ggsw_expand_rows_internal (:182-268)
+            if (dsize > 1) {
+                PGB_CHECK_CUDA(cudaMemsetAsync(ai.data, 0, B * ai_bs, m->stream));
+                PGB_CHECK_CUDA(cudaMemsetAsync(tmp.data, 0, B * tmp_bs, m->stream));
+            }
+            PGB_CHECK_CUDA(cudaMemsetAsync(res_dft.data, 0, B * res_dft_bs, m->stream));
+            PGB_TRY(gadget_product(m, &res_dft, &a_dft, &tsk[col - 1], dsize, true, &ai, &tmp, res_dft_bs, a_dft_bs, ai_bs, tmp_bs, B));
+            pgb_batch btc = {B, res_dft_bs, 0, 0};
+            PGB_TRY(pgb_vec_znx_idft_apply_consume_batched(m, &res_dft, &btc));
+            pgb_vec_znx_big res_big = res_dft;
+            pgb_batch bts = {B, res_dft_bs, small_bs, 0};
+            PGB_TRY(big_add_small_impl(m, &res_big, col, small, 0, &bts));
+            pgb_vec_znx out = mk((char *)ggsw->data + (row * cols + col) * glwe_bytes, n, cols, size); // res.at(row, col)
+            pgb_batch btn = {B, bt->stride_res, res_dft_bs, 0};
+            for (uint64_t j = 0; j < cols; j++) PGB_TRY(big_normalize_impl(m, &out, res_base2k, 0, j, &res_big, tsk_base2k, j, 0, true, &btn));
+        }
+    }
+    return PGB_OK;
+}
+
 // ---- host-buffer front ends ---------------------------------------------------------------------------------------------------
 // Chunked three-stage pipeline (H2D on aux stream 0, compute on the module stream, D2H on aux stream 1), double buffered.
 static int ensure_ws(pgb_module *m, size_t len) {

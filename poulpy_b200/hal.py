@@ -75,7 +75,7 @@ def lib():
         for name in ("pgb_glwe_keyswitch_tmp_bytes", "pgb_glwe_external_product_tmp_bytes", "pgb_cggi_blind_rotate_tmp_bytes",
                      "pgb_cggi_blind_rotate_standard_tmp_bytes", "pgb_vmp_apply_dft_tmp_bytes", "pgb_glwe_tensor_apply_tmp_bytes",
                      "pgb_glwe_tensor_relinearize_tmp_bytes", "pgb_glwe_automorphism_tmp_bytes", "pgb_glwe_automorphism_add_assign_tmp_bytes",
-                     "pgb_glwe_trace_assign_tmp_bytes", "pgb_vec_znx_big_automorphism_assign_tmp_bytes",
+                     "pgb_glwe_trace_assign_tmp_bytes", "pgb_vec_znx_big_automorphism_assign_tmp_bytes", "pgb_ggsw_expand_row_tmp_bytes",
                      "pgb_bytes_of_vmp_pmat", "pgb_size_of_scalar_prep", "pgb_size_of_scalar_big"):
             getattr(_lib, name).restype = C.c_size_t
     return _lib
@@ -623,6 +623,21 @@ class Module:
         bt = _BT(res.batch, res.batch_stride, 0, 0)
         _check(lib().pgb_glwe_trace_assign_batched(self._h, C.byref(r), _u64(res_base2k), _u64(skip), arr, _u64(len(keys)), _u64(key_base2k),
                                                    _u64(dsize), C.byref(bt), C.c_void_p(scratch.ptr), C.c_size_t(scratch.nbytes)))
+        return scratch
+
+    def ggsw_expand_row(self, ggsw_buf: DevBuf, batch, dnum, rank, size, res_base2k, tsk, tsk_base2k, dsize=1, scratch: DevBuf = None):
+        """ggsw_buf: `batch` MatZnx(dnum, rank+1, rank+1, size) back to back, column-0 GLWEs filled; tsk: list of rank prepared keys
+        (poulpy-core/src/conversion/gglwe_to_ggsw.rs:116-268)."""
+        arr = (_PM * len(tsk))(*[k.struct() for k in tsk])
+        need = lib().pgb_ggsw_expand_row_tmp_bytes(self._h, _u64(rank), _u64(size), _u64(res_base2k), C.byref(arr[0]), _u64(tsk_base2k),
+                                                   _u64(dsize), _u64(batch))
+        if scratch is None or scratch.nbytes < need:
+            scratch = DevBuf(need)
+        g = _PM(ggsw_buf.ptr, self.n, size, dnum, rank + 1, rank + 1)
+        stride = self.n * dnum * (rank + 1) * (rank + 1) * size * 8
+        bt = _BT(batch, stride, 0, 0)
+        _check(lib().pgb_ggsw_expand_row_batched(self._h, C.byref(g), _u64(res_base2k), arr, _u64(len(tsk)), _u64(tsk_base2k), _u64(dsize),
+                                                 C.byref(bt), C.c_void_p(scratch.ptr), C.c_size_t(scratch.nbytes)))
         return scratch
 
     def cggi_x_pow_a(self) -> SvpPPol:

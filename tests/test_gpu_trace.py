@@ -111,3 +111,30 @@ def test_glwe_trace_assign(fl):
             for bi in range(batch):
                 o.glwe_trace_assign(want[bi], res_k, skip, [k[1] for k in keys], b, dsize)
             assert np.array_equal(g.vec_znx_to_numpy(res_g), want), (rank, dsize, res_k, skip)
+
+
+@pytest.mark.parametrize("fl", FLAVOURS)
+@pytest.mark.parametrize("dsize", [1, 2])
+def test_ggsw_expand_row(fl, dsize):
+    """ggsw_expand_row (conversion/gglwe_to_ggsw.rs:116-268): columns 1..rank of a batch of GGSWs from their column-0 GLWEs and the tensor
+    keys, equal and mixed base2k, ranks 1..2 -- every GLWE of the result bit for bit against the oracle, column 0 untouched."""
+    n, batch = 256, 3
+    g, o = pb.Module(n, fl), O.OracleModule(n, fl)
+    rng = np.random.default_rng(500 + dsize + fl)
+    b = 12 if fl == pb.FFT64 else 30
+    for rank in (1, 2):
+        for (res_k, tsk_k) in ((b, b), (b - 2, b)):
+            dnum, size, tsk_size = 3, 3, 4
+            conv = -(-size * res_k // tsk_k)
+            tsk = [_key(g, o, rng, -(-conv // dsize), rank, rank + 1, tsk_size, tsk_k) for _ in range(rank)]
+            want = fill_uniform(rng, (batch, dnum, rank + 1, size, rank + 1, n), res_k)  # garbage in columns >= 1 on both sides
+            buf = pb.DevBuf(want.nbytes)
+            buf.upload(want)
+            g.ggsw_expand_row(buf, batch, dnum, rank, size, res_k, [t[0] for t in tsk], tsk_k, dsize)
+            g.sync()
+            col0 = want[:, :, 0].copy()
+            for bi in range(batch):
+                o.ggsw_expand_row(want[bi], res_k, [t[1] for t in tsk], tsk_k, dsize)
+            got = buf.download(np.int64, want.shape)
+            assert np.array_equal(got[:, :, 0], col0)
+            assert np.array_equal(got, want), (rank, res_k, tsk_k)

@@ -120,3 +120,32 @@ def test_trace_cross_backend():
             o.glwe_trace_assign(r, res_k, skip, keys, K, dsize)
             outs.append(r)
         assert np.array_equal(outs[0], outs[1]), (rank, dsize, res_k, skip)
+
+
+def test_ggsw_expand_row_pins():
+    """conversion/gglwe_to_ggsw.rs:116-268.  Zero mask: the gadget products vanish, so GLWE (row, col) is zero except for its column `col`,
+    which carries the column-0 body (already normalised: unchanged) -- the '+ M[i] on the diagonal' of the reference's comment; and the
+    cross-backend procedure on random inputs."""
+    n, K, dnum, size = 64, 12, 2, 3
+    rng = np.random.default_rng(4)
+    for rank in (1, 2):
+        mats = [fill_uniform(rng, (size, rank, size + 1, rank + 1, n), K) for _ in range(rank)]
+        outs = []
+        for fl in (O.NTT120, O.FFT64):
+            o = O.OracleModule(n, fl)
+            tsk = []
+            for mt in mats:
+                pm = o.vmp_pmat_alloc(size, rank, rank + 1, size + 1)
+                o.vmp_prepare(pm, mt)
+                tsk.append(pm)
+            g = np.zeros((dnum, rank + 1, size, rank + 1, n), dtype=np.int64)
+            body = fill_uniform(np.random.default_rng(5), (dnum, size, n), K)
+            g[:, 0, :, 0] = body
+            o.ggsw_expand_row(g, K, tsk, K)
+            for col in range(1, rank + 1):
+                for j in range(rank + 1):
+                    assert np.array_equal(g[:, col, :, j], body if j == col else np.zeros_like(body)), (fl, col, j)
+            r = fill_uniform(np.random.default_rng(6), (dnum, rank + 1, size, rank + 1, n), K)
+            o.ggsw_expand_row(r, K, tsk, K)
+            outs.append(r)
+        assert np.array_equal(outs[0], outs[1]), rank
