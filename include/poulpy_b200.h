@@ -222,6 +222,10 @@ int pgb_vec_znx_normalize_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_
                                   const pgb_batch *bt);
 /* HalImpl::vec_znx_rotate :225 (reference/vec_znx/rotate.rs:9-38) */
 int pgb_vec_znx_rotate(pgb_module *m, int64_t p, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col);
+int pgb_vec_znx_rotate_batched(pgb_module *m, int64_t p, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col,
+                               const pgb_batch *bt);
+/* strided device-to-device copy on the module's stream (glwe_copy between containers of different batch strides) */
+int pgb_memcpy_d2d_strided(pgb_module *m, void *dst, uint64_t dst_stride, const void *src, uint64_t src_stride, uint64_t width, uint64_t count);
 
 /* ---- CoreImpl tier: fused, device-resident, batched pipelines (poulpy-core/src/oep/core_impl.rs:36-52,114-130) ---- */
 /* Device scratch needed by the batched pipelines below (bytes; pass a pgb_alloc_device_bytes buffer). */

@@ -717,6 +717,28 @@ extern "C" int pgb_vec_znx_big_from_small(pgb_module *m, pgb_vec_znx_big *res, u
     return sync_if(m, true);
 }
 
+// batched twin of pgb_vec_znx_rotate (stream-ordered; one p for the whole batch)
+extern "C" int pgb_vec_znx_rotate_batched(pgb_module *m, int64_t p, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col,
+                                          const pgb_batch *bt) {
+    CHECK_BATCH(bt);
+    CHECK_N(res, "vec_znx_rotate(res)");
+    CHECK_N(a, "vec_znx_rotate(a)");
+    CHECK_COL(res, res_col, "vec_znx_rotate(res)");
+    CHECK_COL(a, a_col, "vec_znx_rotate(a)");
+    PGB_REQUIRE(res->data != a->data, "vec_znx_rotate: res and a must not alias");
+    const uint64_t n = m->n;
+    LimbSet R = {(char *)res->data + limb_off(n, res->cols, res_col, 0, 8), res->cols * n * 8, bt->stride_res};
+    LimbSet A = {(char *)a->data + limb_off(n, a->cols, a_col, 0, 8), a->cols * n * 8, bt->stride_a};
+    const uint64_t mn = umin64(res->size, a->size);
+    PGB_TRY(znx_rotate(m, R, A, p, nullptr, 0, (uint32_t)mn, (uint32_t)bt->count));
+    return raw_limbs(m, true, shift(R, mn), shift(R, mn), n * 8, (uint32_t)(res->size - mn), (uint32_t)bt->count);
+}
+// strided device-to-device copy on the module's stream: `count` rows of `width` bytes (glwe_copy between containers of different strides)
+extern "C" int pgb_memcpy_d2d_strided(pgb_module *m, void *dst, uint64_t dst_stride, const void *src, uint64_t src_stride, uint64_t width,
+                                      uint64_t count) {
+    PGB_CHECK_CUDA(cudaMemcpy2DAsync(dst, dst_stride, src, src_stride, width, count, cudaMemcpyDeviceToDevice, m->stream));
+    return PGB_OK;
+}
 extern "C" int pgb_vec_znx_rotate(pgb_module *m, int64_t p, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col) {
     CHECK_N(res, "vec_znx_rotate(res)");
     CHECK_N(a, "vec_znx_rotate(a)");

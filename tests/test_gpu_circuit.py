@@ -1,0 +1,116 @@
+"""Circuit bootstrapping, constant mode (poulpy-bin-fhe/src/circuit_bootstrapping/circuit.rs:219-380, extension_factor = 1): the device
+orchestration of poulpy_b200/circuit.py against the same sequence restated over the oracle (LUT construction lut.rs:271-338, mod_switch_2n,
+block-binary blind rotation, trace, rotation by the gap, ggsw_expand_row) on identical synthetic keys -- the GGSW must agree bit for bit.
+(The reference's own test decrypts the GGSW and bounds its noise, which needs the key generator; every primitive used here has its own
+semantic pin in tests/test_oracle_*.py.)"""
+import numpy as np
+import pytest
+
+import poulpy_b200 as pb
+from oracle import pyoracle as O
+from poulpy_b200 import circuit
+from util import fill_uniform
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_lut(n, f, k, base2k):
+    limbs = -(-k // base2k)
+    scale = 1 << (base2k - k % base2k) if k % base2k else 1
+    step = (n + len(f) // 2) // len(f)
+    full = np.zeros((limbs, 1, n), dtype=np.int64)
+    for i, fi in enumerate(f):
+        full[limbs - 1, 0, i * step:(i + 1) * step] = fi * scale
+    O.vec_znx_normalize_assign(base2k, full, 0)
+    out = np.zeros_like(full)
+    O.vec_znx_rotate(-(step >> 1), out, 0, full, 0)
+    return out, step >> 1
+
+
+@pytest.mark.parametrize("fl", [pb.FFT64, pb.NTT120])
+def test_circuit_bootstrap_to_constant(fl):
+    n, log_n, n_lwe, block, rank, K = 256, 8, 12, 3, 1, 12 if fl == pb.FFT64 else 18
+    brk_size, dnum_res, res_size, log_domain, batch, lwe_size = 2, 2, 2, 2, 3, 2
+    cols = rank + 1
+    g, o = pb.Module(n, fl), O.OracleModule(n, fl)
+    rng = np.random.default_rng(900 + fl)
+    # synthetic key material (uniform digits), identical on both sides
+    brk_mats = [fill_uniform(rng, (1, cols, brk_size, cols, n), K) for _ in range(n_lwe)]
+    per = n * cols * cols * brk_size * g.prep_bytes
+    brk_buf = pb.DevBuf(per * n_lwe)
+    brk_o = []
+    for i, mt in enumerate(brk_mats):
+        g.vmp_prepare(pb.hal.VmpPMat(brk_buf, n, 1, cols, cols, brk_size, offset=i * per), g.mat_znx_from_numpy(mt))
+        pm = o.vmp_pmat_alloc(1, cols, cols, brk_size)
+        o.vmp_prepare(pm, mt)
+        brk_o.append(pm)
+    brk_g = pb.hal.VmpPMat(brk_buf, n, 1, cols, cols, brk_size)
+    tmp_size = max(brk_size, res_size)
+
+    def keys(count, dnum, size):
+        out_g, out_o = [], []
+        for _ in range(count):
+            mt = fill_uniform(rng, (dnum, rank, size, cols, n), K)
+            pg, po = g.vmp_pmat_alloc(dnum, rank, cols, size), o.vmp_pmat_alloc(dnum, rank, cols, size)
+            g.vmp_prepare(pg, g.mat_znx_from_numpy(mt))
+            o.vmp_prepare(po, mt)
+            out_g.append(pg)
+            out_o.append(po)
+        return out_g, out_o
+
+    atk_g, atk_o = keys(log_n, tmp_size, tmp_size + 1)
+    tsk_g, tsk_o = keys(rank, res_size, res_size + 1)
+    lwe = fill_uniform(rng, (batch, lwe_size, 1, n_lwe + 1), K)
+    lwe_dev = pb.DevBuf(lwe.nbytes)
+    lwe_dev.upload(lwe)
+
+    ggsw = circuit.circuit_bootstrap_to_constant(g, lwe_dev, batch, n_lwe, lwe_size, K, brk_g, g.cggi_x_pow_a(), block, atk_g, tsk_g, K, rank,
+                                                 dnum_res, res_size, log_domain)
+    got = ggsw.download(np.int64, (batch, dnum_res, cols, res_size, cols, n))
+
+    # the same sequence over the oracle
+    alpha = 1 << (dnum_res - 1).bit_length() if dnum_res > 1 else 1
+    f = [0] * ((1 << log_domain) * alpha)
+    for j in range(1 << log_domain):
+        for i in range(dnum_res):
+            f[j * alpha + i] = j * (1 << (K * (dnum_res - 1 - i)))
+    lut, drift = _oracle_lut(n, f, K * dnum_res, K)
+    xpa = o.cggi_x_pow_a()
+    want = np.zeros_like(got)
+    for b in range(batch):
+        lwe_2n = O.mod_switch_2n(2 * n, lwe[b], K, rot_left=True)
+        acc = np.zeros((brk_size, cols, n), dtype=np.int64)
+        o.cggi_blind_rotate_block_binary(acc, lwe_2n, lut, brk_o, xpa, block, K)
+        for i in range(dnum_res):
+            tmp = np.zeros((tmp_size, cols, n), dtype=np.int64)
+            tmp[:brk_size] = acc[:tmp_size]
+            o.glwe_trace_assign(tmp, K, 0, atk_o, K)
+            want[b, i, 0, :min(res_size, tmp_size)] = tmp[:res_size]
+            if i + 1 < dnum_res:
+                nxt = np.zeros_like(acc)
+                for c in range(cols):
+                    O.vec_znx_rotate(-2 * drift, nxt, c, acc, c)
+                acc = nxt
+        o.ggsw_expand_row(want[b], K, tsk_o, K)
+    assert np.array_equal(got, want)
+    assert np.any(got[:, :, 1])  # the expanded columns are populated
+
+
+def test_lookup_table_set():
+    """LookupTable::set, extension_factor 1 (lut.rs:271-338): device construction == the numpy/oracle restatement, and the table's meaning:
+    coefficient c of X^{drift} * LUT carries f[c / step] * 2^{-k} on the torus (k bits of message precision)."""
+    from fractions import Fraction
+    n, K = 256, 12
+    g = pb.Module(n, pb.FFT64)
+    for f, k in (([1, 2, 3, 4], 2 * K), ([5, -7, 11, 0, 3, 9, -1, 2], K + 5), (list(range(-8, 8)), 3 * K)):
+        lut_g, drift_g = circuit.lookup_table_set(g, f, k, K)
+        lut_o, drift_o = _oracle_lut(n, f, k, K)
+        assert drift_g == drift_o and np.array_equal(g.vec_znx_to_numpy(lut_g), lut_o)
+        step, limbs = (n + len(f) // 2) // len(f), -(-k // K)
+        back = np.zeros_like(lut_o)
+        O.vec_znx_rotate(drift_o, back, 0, lut_o, 0)
+        for c in (0, 1, step - 1, step, n // 2, n - 1):
+            val = sum(Fraction(int(back[j, 0, c]), 1 << ((j + 1) * K)) for j in range(limbs))
+            want = Fraction(f[min(c // step, len(f) - 1)], 1 << k)
+            d = val - want
+            assert d - round(d) == 0, (f, k, c)
