@@ -305,6 +305,9 @@ int pgb_vec_znx_big_automorphism_batched(pgb_module *m, int64_t p, pgb_vec_znx_b
                                          uint64_t a_col, const pgb_batch *bt);
 size_t pgb_vec_znx_big_automorphism_assign_tmp_bytes(const pgb_module *m);
 int pgb_vec_znx_big_automorphism_assign(pgb_module *m, int64_t p, pgb_vec_znx_big *res, uint64_t res_col);
+/* vec_znx_big_sub_small_assign / _sub_small_negate_assign (HalImpl; reference/ntt120/vec_znx_big.rs:1285-1318): res -= a ; res = a - res */
+int pgb_vec_znx_big_sub_small_assign(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col);
+int pgb_vec_znx_big_sub_small_negate_assign(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col);
 /* vec_znx_normalize_assign (reference/vec_znx/normalize.rs:403-425) */
 int pgb_vec_znx_normalize_assign(pgb_module *m, uint64_t base2k, pgb_vec_znx *res, uint64_t res_col);
 
@@ -343,6 +346,10 @@ size_t pgb_glwe_automorphism_add_assign_tmp_bytes(const pgb_module *m, uint64_t 
                                                   uint64_t key_base2k, uint64_t dsize, uint64_t batch);
 int pgb_glwe_automorphism_add_assign_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, const pgb_vmp_pmat *key, uint64_t key_base2k,
                                              int64_t p, uint64_t dsize, const pgb_batch *bt, void *scratch, size_t scratch_len);
+/* glwe_automorphism_add / _sub / _sub_negate (automorphism/glwe_ct.rs:95-275), out of place; op = 0: res = aut(ks(a)) + a, 1: aut(ks(a)) - a,
+ * 2: a - aut(ks(a)); res == a gives the _assign forms; scratch as pgb_glwe_automorphism_add_assign_tmp_bytes */
+int pgb_glwe_automorphism_op_batched(pgb_module *m, int op, pgb_vec_znx *res, uint64_t res_base2k, const pgb_vec_znx *a, const pgb_vmp_pmat *key,
+                                     uint64_t key_base2k, int64_t p, uint64_t dsize, const pgb_batch *bt, void *scratch, size_t scratch_len);
 int64_t pgb_trace_galois_element(const pgb_module *m, uint64_t i);
 size_t pgb_glwe_trace_assign_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t res_base2k, const pgb_vmp_pmat *key, uint64_t key_base2k,
                                        uint64_t dsize, uint64_t batch);

@@ -335,20 +335,46 @@ static void be_big_automorphism_assign(const be_t *b, int64_t p, orc_vec_znx_big
     free(tmp);
 }
 
-/* poulpy-core/src/automorphism/glwe_ct.rs:142-183 (glwe_automorphism_add_assign_default):
- *   res_big = glwe_keyswitch_internal(res_dft(rank+1, key.size), res, key); per column: big_automorphism_assign(p), big_add_small_assign
- *   (the column of res itself), big_normalize back into res */
-void orc_glwe_automorphism_add_assign(int flavour, const void *mod, orc_vec_znx *res, size_t res_base2k, const orc_vmp_pmat *key,
-                                      size_t key_base2k, int64_t p, size_t dsize) {
+/* vec_znx_big_sub_small_assign (op 1: res -= a) / _sub_small_negate_assign (op 2: res = a - res, limbs of res beyond a.size negated):
+ * ntt120/vec_znx_big.rs:1285-1318 and the FFT64 twins (i64), wrapping */
+static void be_big_small_op(const be_t *b, int op, orc_vec_znx_big *r, size_t rc, const orc_vec_znx *a, size_t ac) {
+    if (op == 0) {
+        be_big_add_small_assign(b, r, rc, a, ac);
+        return;
+    }
+    size_t n = r->n, mn = zmin(r->size, a->size);
+    for (size_t j = 0; j < r->size; j++) {
+        if (j >= mn && !(op == 2)) break;
+        const int64_t *aj = j < a->size ? a->data + n * (j * a->cols + ac) : NULL;
+        for (size_t i = 0; i < n; i++) {
+            if (b->flavour == 0) {
+                unsigned __int128 *rp = (unsigned __int128 *)r->data + n * (j * r->cols + rc) + i, x = aj ? (unsigned __int128)(__int128)aj[i] : 0;
+                if (op == 1) *rp = *rp - x;
+                else *rp = x - *rp;
+            } else {
+                uint64_t *rp = (uint64_t *)r->data + n * (j * r->cols + rc) + i, x = aj ? (uint64_t)aj[i] : 0;
+                if (op == 1) *rp = *rp - x;
+                else *rp = x - *rp;
+            }
+        }
+    }
+}
+
+/* poulpy-core/src/automorphism/glwe_ct.rs:95-275 (glwe_automorphism_add / _sub / _sub_negate and their _assign forms):
+ *   res_big = glwe_keyswitch_internal(res_dft(rank+1, key.size), a, key); per column: big_automorphism_assign(p), then
+ *   big_add_small_assign (op 0) / big_sub_small_assign (op 1) / big_sub_small_negate_assign (op 2) with the column of a, big_normalize into
+ *   res.  a and res share res_base2k; res may alias a. */
+void orc_glwe_automorphism_op(int flavour, const void *mod, int op, orc_vec_znx *res, size_t res_base2k, const orc_vec_znx *a,
+                              const orc_vmp_pmat *key, size_t key_base2k, int64_t p, size_t dsize) {
     be_t b = make_be(flavour, mod);
     size_t n = res->n;
-    assert(res->cols - 1 == key->cols_in && res->cols == key->cols_out);
+    assert(res->cols - 1 == key->cols_in && res->cols == key->cols_out && a->cols == res->cols);
     orc_vec_znx_dft res_dft = dft_alloc(&b, n, res->cols, key->size);
-    orc_vec_znx res_conv = {0};
-    const orc_vec_znx *ain = res;
+    orc_vec_znx a_conv = {0};
+    const orc_vec_znx *ain = a;
     if (res_base2k != key_base2k) {
-        res_conv = conv_base2k(res, res_base2k, key_base2k);
-        ain = &res_conv;
+        a_conv = conv_base2k(a, res_base2k, key_base2k);
+        ain = &a_conv;
     }
     /* glwe_keyswitch_internal (keyswitching/glwe.rs:207-239) */
     orc_vec_znx_dft a_dft = dft_alloc(&b, n, ain->cols - 1, ain->size);
@@ -359,12 +385,16 @@ void orc_glwe_automorphism_add_assign(int flavour, const void *mod, orc_vec_znx 
     be_big_add_small_assign(&b, &res_big, 0, ain, 0);
     for (size_t i = 0; i < res->cols; i++) {
         be_big_automorphism_assign(&b, p, &res_big, i);
-        be_big_add_small_assign(&b, &res_big, i, ain, i);
+        be_big_small_op(&b, op, &res_big, i, ain, i);
         be_big_normalize(&b, res, res_base2k, 0, i, &res_big, key_base2k, i);
     }
     free(a_dft.data);
     free(res_dft.data);
-    free(res_conv.data);
+    free(a_conv.data);
+}
+void orc_glwe_automorphism_add_assign(int flavour, const void *mod, orc_vec_znx *res, size_t res_base2k, const orc_vmp_pmat *key,
+                                      size_t key_base2k, int64_t p, size_t dsize) {
+    orc_glwe_automorphism_op(flavour, mod, 0, res, res_base2k, res, key, key_base2k, p, dsize);
 }
 
 /* GALOISGENERATOR = 5 (poulpy-hal/src/lib.rs); galois_element (layouts/module.rs:214-226) for a positive generator exponent */

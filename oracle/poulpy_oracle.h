@@ -185,6 +185,9 @@ void orc_glwe_automorphism(int flavour, const void *mod, orc_vec_znx *res, size_
 /* poulpy-core/src/automorphism/glwe_ct.rs:142-183; poulpy-core/src/glwe_trace.rs:34-44, :129-175 */
 void orc_glwe_automorphism_add_assign(int flavour, const void *mod, orc_vec_znx *res, size_t res_base2k, const orc_vmp_pmat *key,
                                       size_t key_base2k, int64_t p, size_t dsize);
+/* automorphism/glwe_ct.rs:95-275: op 0 add, 1 sub, 2 sub_negate; res may alias a */
+void orc_glwe_automorphism_op(int flavour, const void *mod, int op, orc_vec_znx *res, size_t res_base2k, const orc_vec_znx *a,
+                              const orc_vmp_pmat *key, size_t key_base2k, int64_t p, size_t dsize);
 int64_t orc_trace_galois_element(size_t i, size_t n);
 void orc_glwe_trace_assign(int flavour, const void *mod, orc_vec_znx *res, size_t res_base2k, size_t skip, const orc_vmp_pmat *const *keys,
                            size_t key_base2k, size_t dsize);

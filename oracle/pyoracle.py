@@ -337,6 +337,12 @@ class OracleModule:
         lib().orc_glwe_automorphism_add_assign(C.c_int(self.flavour), self._h, C.byref(r), _sz(res_base2k), C.byref(ks), _sz(key_base2k),
                                                C.c_int64(p), _sz(dsize))
 
+    def glwe_automorphism_op(self, op, res, res_base2k, a, key: VmpPMat, key_base2k, p, dsize=1):
+        """op 0: res = aut(ks(a)) + a, 1: aut(ks(a)) - a, 2: a - aut(ks(a)) (automorphism/glwe_ct.rs:95-275); res may be a."""
+        r, av, ks = _vz(res), _vz(a), key.struct()
+        lib().orc_glwe_automorphism_op(C.c_int(self.flavour), self._h, C.c_int(op), C.byref(r), _sz(res_base2k), C.byref(av), C.byref(ks),
+                                       _sz(key_base2k), C.c_int64(p), _sz(dsize))
+
     def glwe_trace_assign(self, res, res_base2k, skip, keys, key_base2k, dsize=1):
         """keys: list of log_n prepared automorphism keys, keys[i] for trace_galois_element(i, n) (glwe_trace.rs:129-175)."""
         arr = (C.POINTER(_PM) * len(keys))(*[C.pointer(k.struct()) for k in keys])

@@ -695,6 +695,30 @@ int big_add_small_impl(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, co
     LimbSet A = {(char *)a->data + limb_off(n, a->cols, a_col, 0, 8), a->cols * n * 8, bt->stride_a};
     return big_ew(m, m->flavour == PGB_NTT120, BIG_ADD_SMALL, R, A, (uint32_t)umin64(res->size, a->size), (uint32_t)bt->count);
 }
+// vec_znx_big_sub_small_assign / _sub_small_negate_assign (ntt120/vec_znx_big.rs:1285-1318 and the FFT64 twins): res -= a ; res = a - res
+int big_small_op_impl(pgb_module *m, int op, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col, const pgb_batch *bt) {
+    if (op == BIG_ADD_SMALL) return big_add_small_impl(m, res, res_col, a, a_col, bt);
+    CHECK_BATCH(bt);
+    CHECK_N(res, "vec_znx_big_sub_small(res)");
+    CHECK_N(a, "vec_znx_big_sub_small(a)");
+    CHECK_COL(res, res_col, "vec_znx_big_sub_small(res)");
+    CHECK_COL(a, a_col, "vec_znx_big_sub_small(a)");
+    const uint64_t n = m->n, bb = big_bytes(m), mn = umin64(res->size, a->size);
+    LimbSet R = {(char *)res->data + limb_off(n, res->cols, res_col, 0, bb), res->cols * n * bb, bt->stride_res};
+    LimbSet A = {(char *)a->data + limb_off(n, a->cols, a_col, 0, 8), a->cols * n * 8, bt->stride_a};
+    PGB_TRY(big_ew(m, m->flavour == PGB_NTT120, op, R, A, (uint32_t)mn, (uint32_t)bt->count));
+    if (op == BIG_SUB_SMALL_NEG && res->size > a->size) // (:1315-1317) the remaining limbs of res are negated
+        PGB_TRY(big_ew(m, m->flavour == PGB_NTT120, BIG_NEG, shift(R, a->size), shift(R, a->size), (uint32_t)(res->size - a->size), (uint32_t)bt->count));
+    return PGB_OK;
+}
+extern "C" int pgb_vec_znx_big_sub_small_assign(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col) {
+    PGB_TRY(big_small_op_impl(m, BIG_SUB_SMALL, res, res_col, a, a_col, &ONE));
+    return sync_if(m, true);
+}
+extern "C" int pgb_vec_znx_big_sub_small_negate_assign(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col) {
+    PGB_TRY(big_small_op_impl(m, BIG_SUB_SMALL_NEG, res, res_col, a, a_col, &ONE));
+    return sync_if(m, true);
+}
 extern "C" int pgb_vec_znx_big_add_small_assign(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col) {
     PGB_TRY(big_add_small_impl(m, res, res_col, a, a_col, &ONE));
     return sync_if(m, true);

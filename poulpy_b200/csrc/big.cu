@@ -273,7 +273,16 @@ template <typename T, int OP> __global__ void __launch_bounds__(256) big_ew_kern
     }
     const long long x = reinterpret_cast<const long long *>(p.a.base + (size_t)blockIdx.z * p.a.batch_stride + (size_t)blockIdx.y * p.a.limb_stride)[i];
     if (OP == BIG_ADD_SMALL) *d = wadd<T>(*d, (T)x);
+    else if (OP == BIG_SUB_SMALL) *d = wsub<T>(*d, (T)x);
+    else if (OP == BIG_SUB_SMALL_NEG) *d = wsub<T>((T)x, *d);
     else *d = (T)x;
+}
+// res = -res (wrapping) over limb sets: the tail of vec_znx_big_sub_small_negate_assign
+template <typename T> __global__ void __launch_bounds__(256) big_neg_kernel(BigEwArgs p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    T *d = reinterpret_cast<T *>(p.dst.base + (size_t)blockIdx.z * p.dst.batch_stride + (size_t)blockIdx.y * p.dst.limb_stride) + i;
+    *d = wsub<T>((T)0, *d);
 }
 
 int big_ew(pgb_module *m, bool big_is_i128, int op, LimbSet dst, LimbSet a, uint32_t jobs, uint32_t batch) {
@@ -285,10 +294,16 @@ int big_ew(pgb_module *m, bool big_is_i128, int op, LimbSet dst, LimbSet a, uint
     if (big_is_i128) {
         if (op == BIG_ADD_SMALL) LAUNCH(i128, BIG_ADD_SMALL);
         else if (op == BIG_FROM_SMALL) LAUNCH(i128, BIG_FROM_SMALL);
+        else if (op == BIG_SUB_SMALL) LAUNCH(i128, BIG_SUB_SMALL);
+        else if (op == BIG_SUB_SMALL_NEG) LAUNCH(i128, BIG_SUB_SMALL_NEG);
+        else if (op == BIG_NEG) big_neg_kernel<i128><<<grid, block, 0, m->stream>>>(p);
         else LAUNCH(i128, BIG_ZERO);
     } else {
         if (op == BIG_ADD_SMALL) LAUNCH(long long, BIG_ADD_SMALL);
         else if (op == BIG_FROM_SMALL) LAUNCH(long long, BIG_FROM_SMALL);
+        else if (op == BIG_SUB_SMALL) LAUNCH(long long, BIG_SUB_SMALL);
+        else if (op == BIG_SUB_SMALL_NEG) LAUNCH(long long, BIG_SUB_SMALL_NEG);
+        else if (op == BIG_NEG) big_neg_kernel<long long><<<grid, block, 0, m->stream>>>(p);
         else LAUNCH(long long, BIG_ZERO);
     }
 #undef LAUNCH

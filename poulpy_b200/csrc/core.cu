@@ -561,16 +561,30 @@ extern "C" size_t pgb_glwe_automorphism_add_assign_tmp_bytes(const pgb_module *m
     if (dsize > 1) t += align_up(batch * n * rank_in * div_ceil64(in_size, dsize) * pb) + align_up(batch * n * cols * key->size * pb);
     return t + ALIGN;
 }
+// glwe_automorphism_add / _sub / _sub_negate (automorphism/glwe_ct.rs:95-275): res = normalize(aut_p(ks(a)) (+|-) a) resp. normalize(a -
+// aut_p(ks(a))), out of place (res == a gives the _assign forms); op = 0 add, 1 sub, 2 sub_negate.  a and res share a_base2k / sizes here
+// (what the trace and the packing use); bt->stride_a is the stride of a.
+extern "C" int pgb_glwe_automorphism_op_batched(pgb_module *m, int op, pgb_vec_znx *res, uint64_t res_base2k, const pgb_vec_znx *a,
+                                                const pgb_vmp_pmat *key, uint64_t key_base2k, int64_t p, uint64_t dsize, const pgb_batch *bt,
+                                                void *scratch, size_t scratch_len);
 extern "C" int pgb_glwe_automorphism_add_assign_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, const pgb_vmp_pmat *key,
                                                         uint64_t key_base2k, int64_t p, uint64_t dsize, const pgb_batch *bt, void *scratch,
                                                         size_t scratch_len) {
-    PGB_REQUIRE(bt && bt->count >= 1 && bt->count <= 65535, "glwe_automorphism_add_assign: batch count must be in [1, 65535]");
-    PGB_REQUIRE(res->n == m->n && key->n == m->n, "glwe_automorphism_add_assign: ring degree mismatch");
-    PGB_REQUIRE(res->cols == key->cols_in + 1 && res->cols == key->cols_out, "glwe_automorphism_add_assign: res.rank() != key.rank()");
-    PGB_REQUIRE(dsize >= 1, "glwe_automorphism_add_assign: dsize must be >= 1");
+    pgb_batch b2 = {bt->count, bt->stride_res, bt->stride_res, 0};
+    return pgb_glwe_automorphism_op_batched(m, 0, res, res_base2k, res, key, key_base2k, p, dsize, &b2, scratch, scratch_len);
+}
+extern "C" int pgb_glwe_automorphism_op_batched(pgb_module *m, int op, pgb_vec_znx *res, uint64_t res_base2k, const pgb_vec_znx *a,
+                                                const pgb_vmp_pmat *key, uint64_t key_base2k, int64_t p, uint64_t dsize, const pgb_batch *bt,
+                                                void *scratch, size_t scratch_len) {
+    PGB_REQUIRE(bt && bt->count >= 1 && bt->count <= 65535, "glwe_automorphism_op: batch count must be in [1, 65535]");
+    PGB_REQUIRE(op >= 0 && op <= 2, "glwe_automorphism_op: op must be 0 (add), 1 (sub) or 2 (sub_negate)");
+    PGB_REQUIRE(res->n == m->n && key->n == m->n && a->n == m->n, "glwe_automorphism_op: ring degree mismatch");
+    PGB_REQUIRE(res->cols == key->cols_in + 1 && res->cols == key->cols_out && a->cols == res->cols, "glwe_automorphism_op: rank mismatch");
+    PGB_REQUIRE(a->size == res->size, "glwe_automorphism_op: a and res must have the same size");
+    PGB_REQUIRE(dsize >= 1, "glwe_automorphism_op: dsize must be >= 1");
     const size_t need = pgb_glwe_automorphism_add_assign_tmp_bytes(m, res->size, res_base2k, key, key_base2k, dsize, bt->count);
     if (scratch_len < need) {
-        pgb_set_error("glwe_automorphism_add_assign: scratch of %zu bytes < required %zu", scratch_len, need);
+        pgb_set_error("glwe_automorphism_op: scratch of %zu bytes < required %zu", scratch_len, need);
         return PGB_ERR_SCRATCH;
     }
     const uint64_t n = m->n, pb = prep_bytes(m), bb = big_bytes(m), B = bt->count, rank_in = key->cols_in, cols = key->cols_out;
@@ -578,14 +592,14 @@ extern "C" int pgb_glwe_automorphism_add_assign_batched(pgb_module *m, pgb_vec_z
     const uint64_t res_dft_bs = n * cols * key->size * pb, big2_bs = n * cols * key->size * bb;
     pgb_vec_znx_dft res_dft = mk(ar.take(B * res_dft_bs), n, cols, key->size);
     pgb_vec_znx_big big2 = mk(ar.take(B * big2_bs), n, cols, key->size);
-    pgb_vec_znx ain = *res;
-    uint64_t ain_bs = bt->stride_res;
+    pgb_vec_znx ain = *a;
+    uint64_t ain_bs = bt->stride_a;
     if (res_base2k != key_base2k) { // (:161-168) res_conv = glwe_normalize(res) at the key's base2k
         const uint64_t cs = conv_size(res->size, res_base2k, key_base2k);
         ain_bs = n * res->cols * cs * 8;
         ain = mk(ar.take(B * ain_bs), n, res->cols, cs);
-        pgb_batch btn = {B, ain_bs, bt->stride_res, 0};
-        for (uint64_t i = 0; i < res->cols; i++) PGB_TRY(big_normalize_impl(m, &ain, key_base2k, 0, i, res, res_base2k, i, 0, false, &btn));
+        pgb_batch btn = {B, ain_bs, bt->stride_a, 0};
+        for (uint64_t i = 0; i < res->cols; i++) PGB_TRY(big_normalize_impl(m, &ain, key_base2k, 0, i, a, res_base2k, i, 0, false, &btn));
     }
     // glwe_keyswitch_internal (keyswitching/glwe.rs:207-239)
     const uint64_t a_dft_bs = n * rank_in * ain.size * pb;
@@ -600,7 +614,7 @@ extern "C" int pgb_glwe_automorphism_add_assign_batched(pgb_module *m, pgb_vec_z
         ai = mk(ar.take(B * ai_bs), n, rank_in, ai_max);
         tmp_bs = res_dft_bs;
         tmp = mk(ar.take(B * tmp_bs), n, cols, key->size);
-        PGB_REQUIRE(ai.data && tmp.data, "glwe_automorphism_add_assign: scratch exhausted");
+        PGB_REQUIRE(ai.data && tmp.data, "glwe_automorphism_op: scratch exhausted");
         PGB_CHECK_CUDA(cudaMemsetAsync(ai.data, 0, B * ai_bs, m->stream));
         PGB_CHECK_CUDA(cudaMemsetAsync(tmp.data, 0, B * tmp_bs, m->stream));
     }
@@ -615,7 +629,7 @@ extern "C" int pgb_glwe_automorphism_add_assign_batched(pgb_module *m, pgb_vec_z
         pgb_batch bta = {B, big2_bs, res_dft_bs, 0};
         PGB_TRY(big_automorphism_impl(m, p, &big2, i, &res_big, i, &bta));
         pgb_batch bt2 = {B, big2_bs, ain_bs, 0};
-        PGB_TRY(big_add_small_impl(m, &big2, i, &ain, i, &bt2));
+        PGB_TRY(big_small_op_impl(m, op == 0 ? BIG_ADD_SMALL : (op == 1 ? BIG_SUB_SMALL : BIG_SUB_SMALL_NEG), &big2, i, &ain, i, &bt2));
         pgb_batch btn = {B, bt->stride_res, big2_bs, 0};
         PGB_TRY(big_normalize_impl(m, res, res_base2k, 0, i, &big2, key_base2k, i, 0, true, &btn));
     }

@@ -609,6 +609,20 @@ class Module:
                                                               _u64(dsize), C.byref(bt), C.c_void_p(scratch.ptr), C.c_size_t(scratch.nbytes)))
         return scratch
 
+    def glwe_automorphism_op(self, op, res: VecZnx, res_base2k, a: VecZnx, key: VmpPMat, key_base2k, p, dsize=1, scratch: DevBuf = None):
+        """op 0: res = aut(ks(a)) + a, 1: aut(ks(a)) - a, 2: a - aut(ks(a)) (automorphism/glwe_ct.rs:95-275); res may be a."""
+        ks = key.struct()
+        need = lib().pgb_glwe_automorphism_add_assign_tmp_bytes(self._h, _u64(res.size), _u64(res_base2k), C.byref(ks), _u64(key_base2k),
+                                                                _u64(dsize), _u64(res.batch))
+        if scratch is None or scratch.nbytes < need:
+            scratch = DevBuf(need)
+        r, av = res.struct(), a.struct()
+        bt = _BT(res.batch, res.batch_stride, a.batch_stride, 0)
+        _check(lib().pgb_glwe_automorphism_op_batched(self._h, C.c_int(op), C.byref(r), _u64(res_base2k), C.byref(av), C.byref(ks),
+                                                      _u64(key_base2k), C.c_int64(p), _u64(dsize), C.byref(bt), C.c_void_p(scratch.ptr),
+                                                      C.c_size_t(scratch.nbytes)))
+        return scratch
+
     def trace_galois_element(self, i):
         return int(lib().pgb_trace_galois_element(self._h, _u64(i)))
 

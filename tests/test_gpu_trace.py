@@ -138,3 +138,31 @@ def test_ggsw_expand_row(fl, dsize):
             got = buf.download(np.int64, want.shape)
             assert np.array_equal(got[:, :, 0], col0)
             assert np.array_equal(got, want), (rank, res_k, tsk_k)
+
+
+@pytest.mark.parametrize("fl", FLAVOURS)
+def test_glwe_automorphism_op_family(fl):
+    """glwe_automorphism_add / _sub / _sub_negate (automorphism/glwe_ct.rs:95-275), out of place and in place, equal and mixed base2k."""
+    n, batch = 256, 3
+    g, o = pb.Module(n, fl), O.OracleModule(n, fl)
+    rng = np.random.default_rng(600 + fl)
+    b = 12 if fl == pb.FFT64 else 40
+    for rank in (1, 2):
+        for (res_k, key_k) in ((b, b), (b - 2, b)):
+            size, key_size = 3, 4
+            pg, po = _key(g, o, rng, size, rank, rank + 1, key_size, key_k)
+            for op in (0, 1, 2):
+                a = fill_uniform(rng, (batch, size, rank + 1, n), res_k)
+                want = fill_uniform(rng, (batch, size, rank + 1, n), res_k)
+                res_g, a_g = g.vec_znx_from_numpy(want), g.vec_znx_from_numpy(a)
+                g.glwe_automorphism_op(op, res_g, res_k, a_g, pg, key_k, 5)
+                g.sync()
+                for bi in range(batch):
+                    o.glwe_automorphism_op(op, want[bi], res_k, a[bi], po, key_k, 5)
+                assert np.array_equal(g.vec_znx_to_numpy(res_g), want), (rank, res_k, key_k, op)
+                # in place
+                g.glwe_automorphism_op(op, a_g, res_k, a_g, pg, key_k, -1)
+                g.sync()
+                for bi in range(batch):
+                    o.glwe_automorphism_op(op, a[bi], res_k, a[bi], po, key_k, -1)
+                assert np.array_equal(g.vec_znx_to_numpy(a_g), a), ("assign", rank, res_k, key_k, op)
