@@ -293,6 +293,8 @@ int pgb_vec_znx_add_assign(pgb_module *m, pgb_vec_znx *res, uint64_t res_col, co
 int pgb_vec_znx_add_assign_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col,
                                    const pgb_batch *bt);
 int pgb_vec_znx_sub_assign(pgb_module *m, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col);
+int pgb_vec_znx_sub_assign_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col,
+                                   const pgb_batch *bt);
 /* vec_znx_mul_xp_minus_one (reference/vec_znx/mul_xp_minus_one.rs:13-22): res = X^p * a - a; res and a must not alias */
 int pgb_vec_znx_mul_xp_minus_one(pgb_module *m, int64_t p, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col);
 /* vec_znx_rsh_assign (HalImpl::vec_znx_rsh_assign, hal_impl.rs; reference/vec_znx/shift.rs:186-243): arithmetic right shift by k bits in base
@@ -310,6 +312,7 @@ int pgb_vec_znx_big_sub_small_assign(pgb_module *m, pgb_vec_znx_big *res, uint64
 int pgb_vec_znx_big_sub_small_negate_assign(pgb_module *m, pgb_vec_znx_big *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col);
 /* vec_znx_normalize_assign (reference/vec_znx/normalize.rs:403-425) */
 int pgb_vec_znx_normalize_assign(pgb_module *m, uint64_t base2k, pgb_vec_znx *res, uint64_t res_col);
+int pgb_vec_znx_normalize_assign_batched(pgb_module *m, uint64_t base2k, pgb_vec_znx *res, uint64_t res_col, const pgb_batch *bt);
 
 /* ---- GLWE tensoring / relinearisation = CKKS multiplication (poulpy-core/src/operations/glwe.rs:699-818, :545-610;
  * poulpy-ckks/src/leveled/default/mul.rs:49-86), batched and device resident ---- */

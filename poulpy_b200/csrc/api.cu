@@ -803,6 +803,10 @@ extern "C" int pgb_vec_znx_sub_assign(pgb_module *m, pgb_vec_znx *res, uint64_t 
     PGB_TRY(znx_assign_impl(m, 1, res, res_col, a, a_col, &ONE));
     return sync_if(m, true);
 }
+extern "C" int pgb_vec_znx_sub_assign_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col,
+                                              const pgb_batch *bt) {
+    return znx_assign_impl(m, 1, res, res_col, a, a_col, bt);
+}
 // vec_znx_mul_xp_minus_one (reference/vec_znx/mul_xp_minus_one.rs:13-22): res = rotate(p, a) - a on the common limbs, zero the rest
 // (rotate zero-fills, sub_assign only touches the common limbs).  res and a must not alias.
 extern "C" int pgb_vec_znx_mul_xp_minus_one(pgb_module *m, int64_t p, pgb_vec_znx *res, uint64_t res_col, const pgb_vec_znx *a, uint64_t a_col) {
@@ -822,6 +826,10 @@ extern "C" int pgb_vec_znx_mul_xp_minus_one(pgb_module *m, int64_t p, pgb_vec_zn
 extern "C" int pgb_vec_znx_normalize_assign(pgb_module *m, uint64_t base2k, pgb_vec_znx *res, uint64_t res_col) {
     PGB_TRY(big_normalize_impl(m, res, base2k, 0, res_col, res, base2k, res_col, 0, false, &ONE));
     return sync_if(m, true);
+}
+extern "C" int pgb_vec_znx_normalize_assign_batched(pgb_module *m, uint64_t base2k, pgb_vec_znx *res, uint64_t res_col, const pgb_batch *bt) {
+    pgb_batch b2 = {bt->count, bt->stride_res, bt->stride_res, 0};
+    return big_normalize_impl(m, res, base2k, 0, res_col, res, base2k, res_col, 0, false, &b2);
 }
 
 // ---- bivariate convolution (HalImpl::cnv_*, hal_impl.rs:670-754; kernels in cnv.cu) --------------------------------------------

@@ -10,6 +10,7 @@ import poulpy_b200 as pb
 from oracle import pyoracle as O
 from poulpy_b200 import circuit
 from util import fill_uniform
+from util_circuit import OracleGlweOps, _Ct
 
 pytestmark = pytest.mark.gpu
 
@@ -114,3 +115,89 @@ def test_lookup_table_set():
             want = Fraction(f[min(c // step, len(f) - 1)], 1 << k)
             d = val - want
             assert d - round(d) == 0, (f, k, c)
+
+
+def _setup(fl, n, n_lwe, rank, K, brk_size, size, batch, lwe_size, seed):
+    cols, log_n = rank + 1, n.bit_length() - 1
+    g, o = pb.Module(n, fl), O.OracleModule(n, fl)
+    rng = np.random.default_rng(seed)
+    per = n * cols * cols * brk_size * g.prep_bytes
+    brk_buf = pb.DevBuf(per * n_lwe)
+    brk_o = []
+    for i in range(n_lwe):
+        mt = fill_uniform(rng, (1, cols, brk_size, cols, n), K)
+        g.vmp_prepare(pb.hal.VmpPMat(brk_buf, n, 1, cols, cols, brk_size, offset=i * per), g.mat_znx_from_numpy(mt))
+        pm = o.vmp_pmat_alloc(1, cols, cols, brk_size)
+        o.vmp_prepare(pm, mt)
+        brk_o.append(pm)
+
+    def keys(count, dnum, ksize):
+        out_g, out_o = [], []
+        for _ in range(count):
+            mt = fill_uniform(rng, (dnum, rank, ksize, cols, n), K)
+            pg, po = g.vmp_pmat_alloc(dnum, rank, cols, ksize), o.vmp_pmat_alloc(dnum, rank, cols, ksize)
+            g.vmp_prepare(pg, g.mat_znx_from_numpy(mt))
+            o.vmp_prepare(po, mt)
+            out_g.append(pg)
+            out_o.append(po)
+        return out_g, out_o
+
+    atk = keys(log_n, size, size + 1)
+    tsk = keys(rank, size, size + 1)
+    lwe = fill_uniform(rng, (batch, lwe_size, 1, n_lwe + 1), K)
+    lwe_dev = pb.DevBuf(lwe.nbytes)
+    lwe_dev.upload(lwe)
+    return g, o, pb.hal.VmpPMat(brk_buf, n, 1, cols, cols, brk_size), brk_o, atk, tsk, lwe, lwe_dev
+
+
+def test_glwe_pack():
+    """glwe_pack (poulpy-core/src/glwe_packing.rs:15-170) with a sparse input map: the same sequencing over the device and the oracle."""
+    n, rank, K, size, batch = 64, 1, 18, 3, 2
+    g, o, _, _, atk, _, _, _ = _setup(pb.NTT120, n, 3, rank, K, 2, size, batch, 1, 950)
+    rng = np.random.default_rng(951)
+    dev, orc = circuit.DeviceGlweOps(g, atk[0], K, rank + 1, size, batch), OracleGlweOps(o, atk[1], K, rank + 1, size, batch, n)
+    for idxs, log_gap_out in (((0, 8, 16, 24), 3), ((0, 4, 12), 2), ((0, 16, 32, 48), 4)):
+        cts_d, cts_o = {}, {}
+        for i in idxs:
+            a = fill_uniform(rng, (batch, size, rank + 1, n), K)
+            cts_d[i], cts_o[i] = g.vec_znx_from_numpy(a), _Ct(a.copy())
+        res_d, res_o = dev.new(), orc.new()
+        circuit.glwe_pack(dev, res_d, cts_d, log_gap_out)
+        circuit.glwe_pack(orc, res_o, cts_o, log_gap_out)
+        g.sync()
+        assert np.array_equal(g.vec_znx_to_numpy(res_d), res_o.arr), (idxs, log_gap_out)
+
+
+@pytest.mark.parametrize("fl", [pb.FFT64, pb.NTT120])
+def test_circuit_bootstrap_to_exponent(fl):
+    """Exponent mode (circuit.rs:219-380 with to_exponent = true: LUT of the gadget powers, rotation direction Right, post_process with the
+    partial trace and glwe_pack per row, ggsw_expand_row): device orchestration == the same sequencing over the oracle."""
+    n, n_lwe, block, rank, K = 128, 6, 3, 1, 12 if fl == pb.FFT64 else 18
+    size, dnum_res, log_domain, log_gap_out, batch, lwe_size = 2, 2, 2, 2, 2, 2
+    cols = rank + 1
+    g, o, brk_g, brk_o, atk, tsk, lwe, lwe_dev = _setup(fl, n, n_lwe, rank, K, size, size, batch, lwe_size, 960 + fl)
+    ggsw = circuit.circuit_bootstrap_to_exponent(g, log_gap_out, lwe_dev, batch, n_lwe, lwe_size, K, brk_g, g.cggi_x_pow_a(), block, atk[0], tsk[0],
+                                                 K, rank, dnum_res, size, log_domain)
+    got = ggsw.download(np.int64, (batch, dnum_res, cols, size, cols, n))
+
+    f, alpha = circuit.exponent_lut(K, dnum_res, log_domain)
+    lut, drift = _oracle_lut(n, f, K * dnum_res, K)
+    gap = 2 * drift
+    log_gap_in = (gap * alpha - 1).bit_length()
+    assert log_gap_in != log_gap_out  # the packing branch of post_process is the one exercised
+    xpa = o.cggi_x_pow_a()
+    acc = _Ct(np.zeros((batch, size, cols, n), dtype=np.int64))
+    for b in range(batch):
+        o.cggi_blind_rotate_block_binary(acc.arr[b], O.mod_switch_2n(2 * n, lwe[b], K, rot_left=False), lut, brk_o, xpa, block, K)
+    ops = OracleGlweOps(o, atk[1], K, cols, size, batch, n)
+    want = np.zeros_like(got)
+    for i in range(dnum_res):
+        row = ops.new()
+        circuit.post_process(ops, row, acc, log_gap_in, log_gap_out, log_domain)
+        want[:, i, 0] = row.arr
+        if i + 1 < dnum_res:
+            ops.rotate_assign(-gap, acc)
+    for b in range(batch):
+        o.ggsw_expand_row(want[b], K, tsk[1], K)
+    assert np.array_equal(got, want)
+    assert np.any(got[:, :, 0]) and np.any(got[:, :, 1])
