@@ -380,6 +380,13 @@ size_t pgb_cggi_blind_rotate_tmp_bytes(const pgb_module *m, uint64_t rank, uint6
 int pgb_cggi_blind_rotate_batched(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2n, uint64_t n_lwe, const pgb_vec_znx *lut,
                                   const pgb_vmp_pmat *brk, const pgb_svp_ppol *x_pow_a, uint64_t block_size, uint64_t base2k,
                                   const pgb_batch *bt, void *scratch, size_t scratch_len);
+/* execute_block_binary_extended (algorithm.rs:121-273): lut = `ext` VecZnx(1 col, lut_size) stored consecutively (LookupTable.data), lwe_2n
+ * mod-switched to 2 * n * ext; res receives ring 0 of the accumulator */
+size_t pgb_cggi_blind_rotate_extended_tmp_bytes(const pgb_module *m, uint64_t rank, uint64_t res_size, uint64_t dnum, uint64_t brk_size,
+                                                uint64_t ext, uint64_t batch);
+int pgb_cggi_blind_rotate_extended_batched(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2n, uint64_t n_lwe, const pgb_vec_znx *lut,
+                                           uint64_t ext, const pgb_vmp_pmat *brk, const pgb_svp_ppol *x_pow_a, uint64_t block_size,
+                                           uint64_t base2k, const pgb_batch *bt, void *scratch, size_t scratch_len);
 
 /* mod_switch_2n (algorithms/mod.rs:136-181) on the device: `lwe` = `count` one-column VecZnx of n_lwe + 1 coefficients (b, a_0, ...),
  * stride bt->stride_a; res = device int64 [count][n_lwe + 1]; two_n_domain = 2 * lut.domain_size(); rot_left = LookUpTableRotationDirection::Left. */

@@ -5,7 +5,8 @@
  * Restates: poulpy-bin-fhe/src/blind_rotation/algorithms/mod.rs:136-181 (mod_switch_2n, div_round_by_pow2),
  *   poulpy-bin-fhe/src/blind_rotation/utils.rs:6-41 (set_xai_plus_y with y = 0),
  *   poulpy-bin-fhe/src/blind_rotation/algorithms/cggi/key_prepared.rs:66-75 (x_pow_a table),
- *   poulpy-bin-fhe/src/blind_rotation/algorithms/cggi/algorithm.rs:275-368 (execute_block_binary).
+ *   poulpy-bin-fhe/src/blind_rotation/algorithms/cggi/algorithm.rs:275-368 (execute_block_binary),
+ *   :121-273 (execute_block_binary_extended).
  */
 #include "poulpy_oracle.h"
 
@@ -147,4 +148,94 @@ void orc_cggi_blind_rotate_standard(int flavour, const void *mod, orc_vec_znx *r
     }
     for (size_t c = 0; c < cols; c++) orc_vec_znx_normalize_assign(res_base2k, res, c);         /* operations/glwe.rs:1312-1327 */
     free(tmp.data);
+}
+
+/* ---- flavour dispatch for the extended variant ------------------------------------------------------------------------------------- */
+#define FL(f0, f1, ...) do { if (flavour == 0) f0(__VA_ARGS__); else f1(__VA_ARGS__); } while (0)
+
+/* algorithm.rs:121-273 (execute_block_binary_extended): the accumulator lives in `ext` interleaved rings of degree n (domain size n * ext);
+ * lwe_2n is mod-switched to 2 * n * ext; lut: `ext` VecZnx(1 col); res receives acc[0] (res.size limbs). */
+void orc_cggi_blind_rotate_block_binary_extended(int flavour, const void *mod, orc_vec_znx *res, const int64_t *lwe_2n, size_t n_lwe,
+                                                 const orc_vec_znx *lut, size_t ext, const orc_vmp_pmat *brk, const orc_svp_ppol *x_pow_a,
+                                                 size_t block_size, size_t base2k) {
+    size_t n = res->n, cols = res->cols, two_n = 2 * n, two_n_ext = 2 * n * ext;
+    size_t dnum = brk[0].rows, bsize = brk[0].size;
+    size_t pb = prep_bytes(flavour), bb = flavour == 0 ? 16u : 8u;
+    const orc_ntt120_module *m0 = (const orc_ntt120_module *)mod;
+    const orc_fft64_module *m1 = (const orc_fft64_module *)mod;
+    orc_vec_znx *acc = (orc_vec_znx *)calloc(ext, sizeof *acc);
+    orc_vec_znx_dft *acc_dft = (orc_vec_znx_dft *)calloc(ext, sizeof *acc_dft), *vmp_res = (orc_vec_znx_dft *)calloc(ext, sizeof *vmp_res),
+                    *acc_add = (orc_vec_znx_dft *)calloc(ext, sizeof *acc_add);
+    for (size_t i = 0; i < ext; i++) {
+        acc[i] = (orc_vec_znx){(int64_t *)calloc(n * cols * res->size, 8), n, cols, res->size};
+        acc_dft[i] = (orc_vec_znx_dft){calloc(n * cols * dnum, pb), n, cols, dnum};
+        vmp_res[i] = (orc_vec_znx_dft){calloc(n * cols * bsize, pb), n, cols, bsize};
+        acc_add[i] = (orc_vec_znx_dft){calloc(n * cols * bsize, pb), n, cols, bsize};
+    }
+    orc_vec_znx_dft vmp_xai = {calloc(n * bsize, pb), n, 1, bsize};
+    orc_vec_znx_big acc_big = {calloc(n * bsize, bb), n, 1, bsize};
+
+    const int64_t *a = lwe_2n + 1;
+    size_t b_pos = (size_t)((lwe_2n[0] + (int64_t)two_n_ext) & (int64_t)(two_n_ext - 1));
+    size_t b_hi = b_pos / ext, b_lo = b_pos & (ext - 1);
+    for (size_t i = 0; i < b_lo; i++) orc_vec_znx_rotate((int64_t)b_hi + 1, &acc[i], 0, &lut[ext - b_lo + i], 0);   /* :185-187 */
+    for (size_t i = b_lo; i < ext; i++) orc_vec_znx_rotate((int64_t)b_hi, &acc[i], 0, &lut[i - b_lo], 0);            /* :188-190 */
+
+    for (size_t blk = 0; blk + block_size <= n_lwe; blk += block_size) {
+        for (size_t i = 0; i < ext; i++)
+            for (size_t j = 0; j < cols; j++) {
+                if (flavour == 0) { orc_ntt120_vec_znx_dft_apply(m0, 1, 0, &acc_dft[i], j, &acc[i], j); orc_ntt120_vec_znx_dft_zero(&acc_add[i], j); }
+                else { orc_fft64_vec_znx_dft_apply(m1, 1, 0, &acc_dft[i], j, &acc[i], j); orc_fft64_vec_znx_dft_zero(&acc_add[i], j); }
+            }
+        for (size_t t = 0; t < block_size; t++) {
+            int64_t aii = a[blk + t];
+            size_t ai_pos = (size_t)((aii + (int64_t)two_n_ext) & (int64_t)(two_n_ext - 1));
+            size_t ai_hi = ai_pos / ext, ai_lo = ai_pos & (ext - 1);
+            const orc_vmp_pmat *sk = &brk[blk + t];
+            for (size_t i = 0; i < ext; i++) {
+                if (flavour == 0) orc_ntt120_vmp_apply_dft_to_dft(m0, &vmp_res[i], &acc_dft[i], sk, 0);
+                else orc_fft64_vmp_apply_dft_to_dft(m1, &vmp_res[i], &acc_dft[i], sk, 0);
+            }
+/* acc_add[I][k] += x_pow_a[IDX] * vmp_res[J][k] - vmp_res[I][k] */
+#define XAI(I, J, IDX)                                                                                                       \
+    for (size_t k = 0; k < cols; k++) {                                                                                      \
+        if (flavour == 0) {                                                                                                  \
+            orc_ntt120_svp_apply_dft_to_dft(m0, &vmp_xai, 0, x_pow_a, (IDX), &vmp_res[(J)], k);                              \
+            orc_ntt120_vec_znx_dft_add_assign(&acc_add[(I)], k, &vmp_xai, 0);                                                \
+            orc_ntt120_vec_znx_dft_sub_assign(&acc_add[(I)], k, &vmp_res[(I)], k);                                           \
+        } else {                                                                                                             \
+            orc_fft64_svp_apply_dft_to_dft(m1, &vmp_xai, 0, x_pow_a, (IDX), &vmp_res[(J)], k);                               \
+            orc_fft64_vec_znx_dft_add_assign(&acc_add[(I)], k, &vmp_xai, 0);                                                 \
+            orc_fft64_vec_znx_dft_sub_assign(&acc_add[(I)], k, &vmp_res[(I)], k);                                            \
+        }                                                                                                                    \
+    }
+            if (ai_lo == 0) { /* :216-228 */
+                if (ai_hi != 0)
+                    for (size_t j = 0; j < ext; j++) XAI(j, j, ai_hi)
+            } else {          /* :235-258 */
+                if (((ai_hi + 1) & (two_n - 1)) != 0)
+                    for (size_t i = 0; i < ai_lo; i++) XAI(i, ext - ai_lo + i, ai_hi + 1)
+                if (ai_hi != 0)
+                    for (size_t i = ai_lo; i < ext; i++) XAI(i, i - ai_lo, ai_hi)
+            }
+#undef XAI
+        }
+        for (size_t j = 0; j < ext; j++)
+            for (size_t i = 0; i < cols; i++) {
+                if (flavour == 0) {
+                    orc_ntt120_vec_znx_idft_apply(m0, &acc_big, 0, &acc_add[j], i);
+                    orc_ntt120_vec_znx_big_add_small_assign(&acc_big, 0, &acc[j], i);
+                    orc_ntt120_vec_znx_big_normalize(&acc[j], base2k, 0, i, &acc_big, base2k, 0, 0);
+                } else {
+                    orc_fft64_vec_znx_idft_apply(m1, &acc_big, 0, &acc_add[j], i);
+                    orc_fft64_vec_znx_big_add_small_assign(&acc_big, 0, &acc[j], i);
+                    orc_fft64_vec_znx_big_normalize(&acc[j], base2k, 0, i, &acc_big, base2k, 0, 0);
+                }
+            }
+    }
+    memcpy(res->data, acc[0].data, 8 * n * cols * res->size); /* vec_znx_copy of every column (:268-270) */
+    for (size_t i = 0; i < ext; i++) {
+        free(acc[i].data); free(acc_dft[i].data); free(vmp_res[i].data); free(acc_add[i].data);
+    }
+    free(acc); free(acc_dft); free(vmp_res); free(acc_add); free(vmp_xai.data); free(acc_big.data);
 }

@@ -235,6 +235,10 @@ void orc_cggi_x_pow_a(int flavour, const void *mod, orc_svp_ppol *res);
 void orc_cggi_blind_rotate_block_binary(int flavour, const void *mod, orc_vec_znx *res, const int64_t *lwe_2n,
                                         size_t n_lwe, const orc_vec_znx *lut, const orc_vmp_pmat *brk,
                                         const orc_svp_ppol *x_pow_a, size_t block_size, size_t base2k);
+/* algorithm.rs:121-273: lut = `ext` VecZnx(1 col) (LookupTable.data), lwe_2n mod-switched to 2 * n * ext */
+void orc_cggi_blind_rotate_block_binary_extended(int flavour, const void *mod, orc_vec_znx *res, const int64_t *lwe_2n, size_t n_lwe,
+                                                 const orc_vec_znx *lut, size_t ext, const orc_vmp_pmat *brk, const orc_svp_ppol *x_pow_a,
+                                                 size_t block_size, size_t base2k);
 /* algorithm.rs:370-443 (execute_standard): brk = n_lwe prepared GGSWs (block_size == 1 keys) */
 void orc_cggi_blind_rotate_standard(int flavour, const void *mod, orc_vec_znx *res, size_t res_base2k, const int64_t *lwe_2n,
                                     size_t n_lwe, const orc_vec_znx *lut, const orc_vmp_pmat *brk, size_t brk_base2k);

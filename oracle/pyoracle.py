@@ -374,6 +374,17 @@ class OracleModule:
                                                  C.byref(lv), arr, C.byref(xp), _sz(block_size), _sz(base2k))
 
 
+    def cggi_blind_rotate_block_binary_extended(self, res, lwe_2n, luts, brk, x_pow_a, block_size, base2k):
+        """execute_block_binary_extended (algorithm.rs:121-273); luts: list of extension_factor arrays (size, 1, n) = LookupTable.data,
+        lwe_2n mod-switched to 2 * n * extension_factor."""
+        n_lwe, ext = len(brk), len(luts)
+        arr = (_PM * n_lwe)(*[b.struct() for b in brk])
+        larr = (_VZ * ext)(*[_vz(l) for l in luts])
+        r, xp = _vz(res), _pp(x_pow_a)
+        lwe_2n = np.ascontiguousarray(lwe_2n, dtype=np.int64)
+        lib().orc_cggi_blind_rotate_block_binary_extended(C.c_int(self.flavour), self._h, C.byref(r), _p(lwe_2n), _sz(n_lwe), larr, _sz(ext),
+                                                          arr, C.byref(xp), _sz(block_size), _sz(base2k))
+
     def cggi_blind_rotate_standard(self, res, res_base2k, lwe_2n, lut, brk, brk_base2k):
         """execute_standard (block_size == 1); brk: list of VmpPMat (one GGSW per LWE coefficient)."""
         n_lwe = len(brk)

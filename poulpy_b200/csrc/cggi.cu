@@ -197,6 +197,87 @@ __global__ void __launch_bounds__(256) cggi_xai_fft64_kernel(XaiArgs p) {
     a[i + m] = (a[i + m] + pi) - vi;
 }
 
+// ---- extended blind rotation (algorithm.rs:121-273): the accumulator is `ext` interleaved rings; items are (ciphertext b, ring i) at
+// index b * ext + i.  Which source ring and which X^a table entry a ring takes depends on the ciphertext's own a_t (and is decided per
+// item on the device); the reference's skip conditions are kept verbatim (see the oracle's note on a_hi = 0 / 2n - 1).
+struct ExtInitArgs {
+    char *acc; uint64_t acc_item;        // acc item stride (bytes); column 0, limb j at + j * cols * n * 8
+    const char *lut; uint64_t lut_item;  // lut[j]: VecZnx(1 col), limb l at + l * n * 8
+    const long long *lwe; uint64_t lwe_stride;
+    uint32_t n, ext, cols;
+};
+__global__ void __launch_bounds__(256) cggi_ext_init_kernel(ExtInitArgs p) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; // destination coefficient
+    if (k >= p.n) return;
+    const uint32_t item = blockIdx.z, b = item / p.ext, i = item % p.ext, n = p.n;
+    const long long two_n_ext = 2ll * n * p.ext;
+    const unsigned long long b_pos = (unsigned long long)((p.lwe[(size_t)b * p.lwe_stride] + two_n_ext) & (two_n_ext - 1));
+    const uint32_t b_hi = (uint32_t)(b_pos / p.ext), b_lo = (uint32_t)(b_pos & (p.ext - 1));
+    const uint32_t j = i < b_lo ? p.ext - b_lo + i : i - b_lo;   // (:185-190)
+    const uint32_t rot = i < b_lo ? b_hi + 1 : b_hi;
+    const uint32_t mp_2n = rot & (2 * n - 1), mp_1n = mp_2n & (n - 1);
+    const bool neg_first = mp_2n < n;
+    const long long *src = reinterpret_cast<const long long *>(p.lut + (size_t)j * p.lut_item + (size_t)blockIdx.y * n * 8);
+    long long *dst = reinterpret_cast<long long *>(p.acc + (size_t)item * p.acc_item + (size_t)blockIdx.y * p.cols * n * 8);
+    long long v;
+    bool neg;
+    if (k < mp_1n) { v = src[n - mp_1n + k]; neg = neg_first; }
+    else { v = src[k - mp_1n]; neg = !neg_first; }
+    dst[k] = neg ? (long long)(0ull - (unsigned long long)v) : v;
+}
+// acc_add[b][i][poly] = (acc_add + x_pow_a[idx] * v[b][j][poly]) - v[b][i][poly] with (j, idx, skip) from a_t of ciphertext b (:216-258)
+struct XaiExtArgs {
+    char *acc;       uint64_t acc_item;
+    const char *v;   uint64_t v_item;
+    const char *xpa;
+    const long long *lwe; uint64_t lwe_stride;
+    uint32_t n, ext;
+};
+__device__ __forceinline__ bool ext_route(long long ai, uint32_t n, uint32_t ext, uint32_t i, uint32_t &j, uint32_t &idx) {
+    const long long two_n_ext = 2ll * n * ext;
+    const unsigned long long pos = (unsigned long long)((ai + two_n_ext) & (two_n_ext - 1));
+    const uint32_t hi = (uint32_t)(pos / ext), lo = (uint32_t)(pos & (ext - 1));
+    if (lo == 0) { j = i; idx = hi; return hi != 0; }
+    if (i < lo) { j = ext - lo + i; idx = hi + 1; return ((hi + 1) & (2 * n - 1)) != 0; }
+    j = i - lo; idx = hi;
+    return hi != 0;
+}
+__global__ void __launch_bounds__(256) cggi_xai_ext_ntt120_kernel(XaiExtArgs p) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= p.n) return;
+    const uint32_t item = blockIdx.z, b = item / p.ext, i = item % p.ext, poly = blockIdx.y;
+    uint32_t j, idx;
+    if (!ext_route(p.lwe[(size_t)b * p.lwe_stride], p.n, p.ext, i, j, idx)) return;
+    const n120::PrimeRt pr(u / (p.n / 4));
+    const uint32_t q = pr.q;
+    const uint4 w = __ldg(reinterpret_cast<const uint4 *>(p.xpa + (size_t)idx * p.n * 16) + u);
+    const uint4 vj = *(reinterpret_cast<const uint4 *>(p.v + (size_t)(b * p.ext + j) * p.v_item + (size_t)poly * p.n * 16) + u);
+    const uint4 vi = *(reinterpret_cast<const uint4 *>(p.v + (size_t)item * p.v_item + (size_t)poly * p.n * 16) + u);
+    uint4 *ap = reinterpret_cast<uint4 *>(p.acc + (size_t)item * p.acc_item + (size_t)poly * p.n * 16) + u;
+    const uint4 a = *ap;
+    auto f = [&](uint32_t acc, uint32_t ww, uint32_t x, uint32_t y) {
+        const uint32_t t = n120::csub(acc + pr.reduce((unsigned long long)ww * x), q);
+        return t >= y ? t - y : t - y + q;
+    };
+    *ap = make_uint4(f(a.x, w.x, vj.x, vi.x), f(a.y, w.y, vj.y, vi.y), f(a.z, w.z, vj.z, vi.z), f(a.w, w.w, vj.w, vi.w));
+}
+__global__ void __launch_bounds__(256) cggi_xai_ext_fft64_kernel(XaiExtArgs p) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; // complex index
+    const uint32_t m = p.n / 2;
+    if (c >= m) return;
+    const uint32_t item = blockIdx.z, b = item / p.ext, i = item % p.ext, poly = blockIdx.y;
+    uint32_t j, idx;
+    if (!ext_route(p.lwe[(size_t)b * p.lwe_stride], p.n, p.ext, i, j, idx)) return;
+    const double *w = reinterpret_cast<const double *>(p.xpa + (size_t)idx * p.n * 8);
+    const double *vj = reinterpret_cast<const double *>(p.v + (size_t)(b * p.ext + j) * p.v_item + (size_t)poly * p.n * 8);
+    const double *vi = reinterpret_cast<const double *>(p.v + (size_t)item * p.v_item + (size_t)poly * p.n * 8);
+    double *a = reinterpret_cast<double *>(p.acc + (size_t)item * p.acc_item + (size_t)poly * p.n * 8);
+    const double wr = __ldg(w + c), wi = __ldg(w + c + m), xr = vj[c], xi = vj[c + m];
+    const double pr = wr * xr - wi * xi, pi = wr * xi + wi * xr; // reim_mul(ppol, v[j])
+    a[c] = (a[c] + pr) - vi[c];
+    a[c + m] = (a[c + m] + pi) - vi[c + m];
+}
+
 static pgb_vec_znx mkv(void *data, uint64_t n, uint64_t cols, uint64_t size) {
     pgb_vec_znx v = {data, n, cols, size, size};
     return v;
@@ -315,6 +396,85 @@ int cggi_blind_rotate_impl(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2
     }
     return PGB_OK;
 }
+// execute_block_binary_extended over a batch (algorithm.rs:121-273): the limb-wise HAL sequence with B * ext accumulator items
+extern "C" size_t pgb_cggi_blind_rotate_extended_tmp_bytes(const pgb_module *m, uint64_t rank, uint64_t res_size, uint64_t dnum, uint64_t brk_size,
+                                                           uint64_t ext, uint64_t batch) {
+    const uint64_t n = m->n, pb = prep_bytes(m), bb = big_bytes(m), cols = rank + 1, items = batch * ext;
+    return align_up(items * n * cols * res_size * 8) + align_up(items * n * cols * dnum * pb) + 2 * align_up(items * n * cols * brk_size * pb) +
+           align_up(items * n * brk_size * bb) + ALIGN;
+}
+extern "C" int pgb_cggi_blind_rotate_extended_batched(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2n, uint64_t n_lwe, const pgb_vec_znx *lut,
+                                                      uint64_t ext, const pgb_vmp_pmat *brk, const pgb_svp_ppol *x_pow_a, uint64_t block_size,
+                                                      uint64_t base2k, const pgb_batch *bt, void *scratch, size_t scratch_len) {
+    PGB_REQUIRE(bt && bt->count >= 1 && bt->count * ext <= 65535, "cggi_blind_rotate_extended: batch * extension_factor must be in [1, 65535]");
+    PGB_REQUIRE(ext >= 1 && (ext & (ext - 1)) == 0, "cggi_blind_rotate_extended: extension_factor must be a power of two");
+    PGB_REQUIRE(res->n == m->n && lut->n == m->n && brk->n == m->n && x_pow_a->n == m->n, "cggi_blind_rotate_extended: ring degree mismatch");
+    PGB_REQUIRE(x_pow_a->cols == 2 * m->n && lut->cols == 1, "cggi_blind_rotate_extended: x_pow_a needs 2n columns, the LUT one");
+    PGB_REQUIRE(brk->cols_in == res->cols && brk->cols_out == res->cols, "cggi_blind_rotate_extended: brk rank does not match res");
+    PGB_REQUIRE(block_size >= 1, "cggi_blind_rotate_extended: block_size must be >= 1");
+    const uint64_t n = m->n, pb = prep_bytes(m), bb = big_bytes(m), B = bt->count, cols = res->cols, items = B * ext;
+    const uint64_t dnum = brk->rows, bsize = brk->size;
+    const size_t need = pgb_cggi_blind_rotate_extended_tmp_bytes(m, cols - 1, res->size, dnum, bsize, ext, B);
+    if (scratch_len < need) {
+        pgb_set_error("cggi_blind_rotate_extended: scratch of %zu bytes < required %zu", scratch_len, need);
+        return PGB_ERR_SCRATCH;
+    }
+    char *sp = (char *)scratch;
+    auto take = [&](uint64_t bytes) {
+        char *q = sp;
+        sp += align_up(bytes);
+        return (void *)q;
+    };
+    const uint64_t acc_item = n * cols * res->size * 8, accd_bs = n * cols * dnum * pb, vres_bs = n * cols * bsize * pb, big_bs = n * bsize * bb;
+    pgb_vec_znx acc = mkv(take(items * acc_item), n, cols, res->size);
+    pgb_vec_znx_dft acc_dft = mkv(take(items * accd_bs), n, cols, dnum);
+    pgb_vec_znx_dft vmp_res = mkv(take(items * vres_bs), n, cols, bsize);
+    pgb_vec_znx_dft acc_add = mkv(take(items * vres_bs), n, cols, bsize);
+    pgb_vec_znx_big acc_big = mkv(take(items * big_bs), n, 1, bsize);
+    const uint64_t brk_bytes = pgb_bytes_of_vmp_pmat(m, brk->rows, brk->cols_in, brk->cols_out, brk->size);
+    const uint64_t lwe_stride = n_lwe + 1;
+    // acc[i].zero(); acc[i][0] = X^{b_hi (+1)} * lut[j] (:159-190)
+    PGB_CHECK_CUDA(cudaMemsetAsync(acc.data, 0, items * acc_item, m->stream));
+    {
+        const uint64_t mn = umin64(res->size, lut->size);
+        ExtInitArgs ia = {(char *)acc.data, acc_item, (const char *)lut->data, n * lut->size * 8, (const long long *)lwe_2n, lwe_stride, (uint32_t)n,
+                          (uint32_t)ext, (uint32_t)cols};
+        ProfScope _ps(m, PROF_OTHER);
+        cggi_ext_init_kernel<<<dim3(((uint32_t)n + 255) / 256, (uint32_t)mn, (uint32_t)items), 256, 0, m->stream>>>(ia);
+        PGB_CHECK_CUDA(cudaGetLastError());
+    }
+    for (uint64_t blk = 0; blk + block_size <= n_lwe; blk += block_size) {
+        pgb_batch btd = {items, accd_bs, acc_item, 0};
+        for (uint64_t j = 0; j < cols; j++) PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &acc_dft, j, &acc, j, &btd));
+        PGB_CHECK_CUDA(cudaMemsetAsync(acc_add.data, 0, items * vres_bs, m->stream));
+        for (uint64_t t = 0; t < block_size; t++) {
+            pgb_vmp_pmat ski = *brk;
+            ski.data = (char *)brk->data + (blk + t) * brk_bytes;
+            pgb_batch btv = {items, vres_bs, accd_bs, 0};
+            PGB_TRY(vmp_apply_impl(m, &vmp_res, &acc_dft, &ski, 0, &btv));
+            XaiExtArgs xa = {(char *)acc_add.data, vres_bs, (const char *)vmp_res.data, vres_bs, (const char *)x_pow_a->data,
+                             (const long long *)lwe_2n + 1 + blk + t, lwe_stride, (uint32_t)n, (uint32_t)ext};
+            ProfScope _ps(m, PROF_ELEMENTWISE);
+            if (m->flavour == PGB_NTT120)
+                cggi_xai_ext_ntt120_kernel<<<dim3(((uint32_t)n + 255) / 256, (uint32_t)(cols * bsize), (uint32_t)items), 256, 0, m->stream>>>(xa);
+            else
+                cggi_xai_ext_fft64_kernel<<<dim3(((uint32_t)(n / 2) + 255) / 256, (uint32_t)(cols * bsize), (uint32_t)items), 256, 0, m->stream>>>(xa);
+            PGB_CHECK_CUDA(cudaGetLastError());
+        }
+        for (uint64_t i = 0; i < cols; i++) { // (:262-268)
+            pgb_batch bti = {items, big_bs, vres_bs, 0};
+            PGB_TRY(pgb_vec_znx_idft_apply_batched(m, &acc_big, 0, &acc_add, i, &bti));
+            pgb_batch bts = {items, big_bs, acc_item, 0};
+            PGB_TRY(big_add_small_impl(m, &acc_big, 0, &acc, i, &bts));
+            pgb_batch btn = {items, acc_item, big_bs, 0};
+            PGB_TRY(big_normalize_impl(m, &acc, base2k, 0, i, &acc_big, base2k, 0, 0, true, &btn));
+        }
+    }
+    // res <- acc[0] of every ciphertext (:270-272)
+    PGB_CHECK_CUDA(cudaMemcpy2DAsync(res->data, bt->stride_res, acc.data, ext * acc_item, acc_item, B, cudaMemcpyDeviceToDevice, m->stream));
+    return PGB_OK;
+}
+
 extern "C" int pgb_cggi_blind_rotate_batched(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2n, uint64_t n_lwe, const pgb_vec_znx *lut,
                                              const pgb_vmp_pmat *brk, const pgb_svp_ppol *x_pow_a, uint64_t block_size, uint64_t base2k,
                                              const pgb_batch *bt, void *scratch, size_t scratch_len) {

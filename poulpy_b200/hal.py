@@ -73,7 +73,7 @@ def lib():
         _lib.pgb_profile_enable.argtypes = [C.c_void_p, C.c_int]
         _lib.pgb_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
         for name in ("pgb_glwe_keyswitch_tmp_bytes", "pgb_glwe_external_product_tmp_bytes", "pgb_cggi_blind_rotate_tmp_bytes",
-                     "pgb_cggi_blind_rotate_standard_tmp_bytes", "pgb_vmp_apply_dft_tmp_bytes", "pgb_glwe_tensor_apply_tmp_bytes",
+                     "pgb_cggi_blind_rotate_standard_tmp_bytes", "pgb_cggi_blind_rotate_extended_tmp_bytes", "pgb_vmp_apply_dft_tmp_bytes", "pgb_glwe_tensor_apply_tmp_bytes",
                      "pgb_glwe_tensor_relinearize_tmp_bytes", "pgb_glwe_automorphism_tmp_bytes", "pgb_glwe_automorphism_add_assign_tmp_bytes",
                      "pgb_glwe_trace_assign_tmp_bytes", "pgb_vec_znx_big_automorphism_assign_tmp_bytes", "pgb_ggsw_expand_row_tmp_bytes",
                      "pgb_bytes_of_vmp_pmat", "pgb_size_of_scalar_prep", "pgb_size_of_scalar_big"):
@@ -674,6 +674,21 @@ class Module:
                                                    C.c_size_t(scratch.nbytes)))
         return scratch
 
+
+    def cggi_blind_rotate_extended(self, res: VecZnx, lwe_2n: DevBuf, n_lwe, luts: VecZnx, ext, brk: VmpPMat, x_pow_a: SvpPPol, block_size,
+                                   base2k, scratch: DevBuf = None):
+        """execute_block_binary_extended (algorithm.rs:121-273); luts: VecZnx(1 col) with `ext` batch items (LookupTable.data), lwe_2n
+        mod-switched to 2 * n * ext."""
+        need = lib().pgb_cggi_blind_rotate_extended_tmp_bytes(self._h, _u64(res.cols - 1), _u64(res.size), _u64(brk.rows), _u64(brk.size),
+                                                              _u64(ext), _u64(res.batch))
+        if scratch is None or scratch.nbytes < need:
+            scratch = DevBuf(need)
+        r, lv, bs, xp = res.struct(), luts.struct(), brk.struct(), x_pow_a.struct()
+        bt = _BT(res.batch, res.batch_stride, 0, 0)
+        _check(lib().pgb_cggi_blind_rotate_extended_batched(self._h, C.byref(r), C.c_void_p(lwe_2n.ptr), _u64(n_lwe), C.byref(lv), _u64(ext),
+                                                            C.byref(bs), C.byref(xp), _u64(block_size), _u64(base2k), C.byref(bt),
+                                                            C.c_void_p(scratch.ptr), C.c_size_t(scratch.nbytes)))
+        return scratch
 
     def cggi_mod_switch_2n(self, lwe_dev: DevBuf, batch, n_lwe, size, lwe_base2k, two_n_domain, rot_left=True) -> DevBuf:
         """mod_switch_2n of `batch` LWEs stored as (batch, size, 1, n_lwe + 1) int64 on the device -> DevBuf int64 [batch][n_lwe + 1]."""

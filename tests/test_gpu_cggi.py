@@ -160,3 +160,40 @@ def test_blind_rotate_standard_semantics(fl):
         want = np.zeros((2, rank + 1, n), dtype=np.int64)
         O.vec_znx_rotate(shift, want, 0, lut, 0)
         assert np.array_equal(got[b], want), b
+
+
+@pytest.mark.parametrize("fl", [pb.NTT120, pb.FFT64])
+@pytest.mark.parametrize("ext", [2, 4])
+def test_blind_rotate_extended_matches_oracle(fl, ext):
+    """execute_block_binary_extended (algorithm.rs:121-273): `ext` interleaved accumulator rings, source ring and X^a table entry chosen per
+    ciphertext on the device; random keys and LWEs (including the positions where the reference skips the cross-ring update), batch 5."""
+    n, n_lwe, block, rank, batch = 128, 9, 3, 1, 5
+    k = 12 if fl == pb.FFT64 else 18
+    dnum, brk_size, size = 1, 2, 2
+    cols = rank + 1
+    g, o = pb.Module(n, fl), O.OracleModule(n, fl)
+    rng = np.random.default_rng(70 + ext + fl)
+    per = n * cols * cols * brk_size * dnum * g.prep_bytes
+    brk_buf = pb.DevBuf(per * n_lwe)
+    brk_o = []
+    for i in range(n_lwe):
+        mt = fill_uniform(rng, (dnum, cols, brk_size, cols, n), k)
+        g.vmp_prepare(pb.hal.VmpPMat(brk_buf, n, dnum, cols, cols, brk_size, offset=i * per), g.mat_znx_from_numpy(mt))
+        pm = o.vmp_pmat_alloc(dnum, cols, cols, brk_size)
+        o.vmp_prepare(pm, mt)
+        brk_o.append(pm)
+    luts = fill_uniform(rng, (ext, size, 1, n), k - 1)
+    N = n * ext
+    lwe_2n = rng.integers(-N, N, size=(batch, n_lwe + 1), dtype=np.int64)
+    lwe_2n[1, 1:4] = [1, 2 * N - 1, ext]  # a_hi = 0 with a_lo != 0, a_hi = 2n - 1, and a pure in-ring rotation
+    lwe_dev = pb.DevBuf(lwe_2n.nbytes)
+    lwe_dev.upload(lwe_2n)
+    want = fill_uniform(rng, (batch, size, cols, n), k)
+    res_g = g.vec_znx_from_numpy(want)
+    g.cggi_blind_rotate_extended(res_g, lwe_dev, n_lwe, g.vec_znx_from_numpy(luts), ext, pb.hal.VmpPMat(brk_buf, n, dnum, cols, cols, brk_size),
+                                 g.cggi_x_pow_a(), block, k)
+    g.sync()
+    xpa = o.cggi_x_pow_a()
+    for b in range(batch):
+        o.cggi_blind_rotate_block_binary_extended(want[b], lwe_2n[b], [luts[j] for j in range(ext)], brk_o, xpa, block, k)
+    assert np.array_equal(g.vec_znx_to_numpy(res_g), want)

@@ -129,6 +129,54 @@ def test_blind_rotation_semantics_trivial_keys(flavour, rank):
     assert np.array_equal(res, want)
 
 
+@pytest.mark.parametrize("flavour", [O.NTT120, O.FFT64])
+@pytest.mark.parametrize("ext", [2, 4])
+def test_blind_rotation_extended_semantics_trivial_keys(flavour, ext):
+    """execute_block_binary_extended (algorithm.rs:121-273): the accumulator is a polynomial of degree n * ext held as `ext` interleaved
+    rings (lut.data[j][k] = L[k * ext + j], lut.rs:318-327).  With noiseless keys the result must be component 0 of
+    Y^(b + <a, s>) * L(Y) in Z[Y]/(Y^(n ext) + 1), for shifts with every residue modulo ext (trivial and cross-ring cases, :216-258)."""
+    n, k, n_lwe, block, rank = 32, 12, 12, 3, 1
+    size, dnum, brk_size = 2, 2, 2
+    rng = np.random.default_rng(25 + ext)
+    m = O.OracleModule(n, flavour)
+    s = np.zeros(n_lwe, dtype=np.int64)
+    for b0 in range(0, n_lwe, block):
+        s[b0 + rng.integers(0, block)] = 1
+    brk = []
+    for i in range(n_lwe):
+        pm = m.vmp_pmat_alloc(dnum, rank + 1, rank + 1, brk_size)
+        m.vmp_prepare(pm, _trivial_ggsw(n, rank, dnum, brk_size, int(s[i])))
+        brk.append(pm)
+    xpa = m.cggi_x_pow_a()
+    big = fill_uniform(rng, (size, n * ext), k - 1)  # L(Y), limb-wise
+    luts = [np.ascontiguousarray(big[:, j::ext].reshape(size, 1, n)) for j in range(ext)]
+    N = n * ext
+    for trial in range(6):
+        lwe_2n = rng.integers(-N, N, size=n_lwe + 1, dtype=np.int64)
+        if trial == 0:
+            lwe_2n[1:] -= lwe_2n[1:] % ext  # every a_i a multiple of ext: the trivial branch only
+        # The reference skips the cross-ring update when the rotation inside a ring is the identity (a_hi = 0, resp. a_hi + 1 = 2n, with
+        # a_lo != 0: `if ai_hi != 0` / `if (ai_hi + 1) & (two_n - 1) != 0`, :237,:248) although the term v[j] - v[i] is not zero there.  The
+        # restatement keeps that behaviour; the semantic property is checked away from those positions.
+        for i in range(1, n_lwe + 1):
+            pos = int(lwe_2n[i]) % (2 * N)
+            if pos % ext and (pos // ext == 0 or pos // ext == 2 * n - 1):
+                lwe_2n[i] += ext
+        res = fill_uniform(rng, (size, rank + 1, n), k)
+        m.cggi_blind_rotate_block_binary_extended(res, lwe_2n, luts, brk, xpa, block, k)
+        shift = int(lwe_2n[0] + np.dot(lwe_2n[1:], s)) % (2 * N)
+        rot = np.zeros_like(big)
+        for i in range(N):
+            p = (i + shift) % (2 * N)
+            if p < N:
+                rot[:, p] = big[:, i]
+            else:
+                rot[:, p - N] = -big[:, i]
+        want = np.zeros_like(res)
+        want[:, 0] = rot[:, 0::ext]
+        assert np.array_equal(res, want), (ext, trial)
+
+
 def test_mod_switch_2n():
     """algorithms/mod.rs:136-181: base2k > log2(2N)+1 path rounds to [-N, N); the multi-limb path concatenates limbs."""
     rng = np.random.default_rng(9)
