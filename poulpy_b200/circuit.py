@@ -1,6 +1,6 @@
 """Circuit bootstrapping, constant mode: host orchestration of
-`circuit_bootstrap_core(to_exponent = false, ...)` (poulpy-bin-fhe/src/circuit_bootstrapping/circuit.rs:219-380) with
-extension_factor = 1 over the device-resident entry points of the C ABI:
+`circuit_bootstrap_core(to_exponent = false, ...)` (poulpy-bin-fhe/src/circuit_bootstrapping/circuit.rs:219-380) over the device-resident
+entry points of the C ABI:
 
     LUT f[j * alpha + i] = j * 2^(res_base2k * (dnum - 1 - i))            circuit.rs:278-299, lut.rs:271-338 (lookup_table_set)
     acc  = blind_rotate(lwe, LUT)                                           pgb_cggi_mod_switch_2n_batched + pgb_cggi_blind_rotate_batched
@@ -8,8 +8,8 @@ extension_factor = 1 over the device-resident entry points of the C ABI:
     GGSW columns 1..rank = ggsw_expand_row(GGSW, tsk)                       pgb_ggsw_expand_row_batched
 
 Everything stays on the device; the host only sequences the launches, as `poulpy-bin-fhe` does above `Module<B>`.  All layouts share one
-base2k here (the reference converts between the BRK / ATK / result layouts with glwe_normalize when they differ); extension_factor > 1
-(extended blind rotation) is not ported.
+base2k here (the reference converts between the BRK / ATK / result layouts with glwe_normalize when they differ); extension_factor > 1 goes
+through the extended blind rotation (`pgb_cggi_blind_rotate_extended_batched`) and the `ext`-component lookup table.
 
 The exponent mode (`to_exponent = true`: circuit.rs:286-290, 352-366 and `post_process` :382-420 with `glwe_pack`,
 poulpy-core/src/glwe_packing.rs:15-170) is written once over a small GLWE-operations interface (`DeviceGlweOps` below): the sequencing is
@@ -22,24 +22,49 @@ import numpy as np
 from . import hal
 
 
-def lookup_table_set(module: "hal.Module", f, k, base2k):
-    """LookupTable::set for extension_factor = 1 (lut.rs:271-338) -> (VecZnx(1 col, ceil(k / base2k) limbs) on the device, drift)."""
-    n = module.n
+def lookup_table_limbs(n, f, k, base2k, ext=1):
+    """The un-normalised LookupTable.data of lut.rs:271-327 as a numpy array (ext, limbs, 1, n): the table over the domain n * ext with
+    f[i] * scale on blocks of `step` coefficients in its last limb, component j = coefficients j, j + ext, ... (vec_znx_switch_ring after j
+    rotations by X^-1).  -> (array, step)"""
     f = [int(x) for x in f]
-    assert 0 < len(f) <= n
+    domain = n * ext
+    assert 0 < len(f) <= domain
     limbs = -(-k // base2k)
     scale = 1 << (base2k - k % base2k) if k % base2k else 1
-    step = (n + len(f) // 2) // len(f)  # usize::div_round (lut.rs:243-247)
-    last = np.zeros(n, dtype=np.int64)
+    step = (domain + len(f) // 2) // len(f)  # usize::div_round (lut.rs:243-247)
+    last = np.zeros(domain, dtype=np.int64)
     for i, fi in enumerate(f):
         last[i * step:(i + 1) * step] = fi * scale
-    full = np.zeros((limbs, 1, n), dtype=np.int64)
-    full[limbs - 1, 0] = last
-    lut = module.vec_znx_from_numpy(full)
-    module.vec_znx_normalize_assign(base2k, lut, 0)
+    out = np.zeros((ext, limbs, 1, n), dtype=np.int64)
+    for j in range(ext):
+        out[j, limbs - 1, 0] = last[j::ext]
+    return out, step
+
+
+def lookup_table_rotation_plan(n, ext, k):
+    """lookup_table_rotate(k) (lut.rs:340-362): component i is rotated by k_hi (+1 for the last k_lo components) and moves to slot
+    (i + k_lo) mod ext.  -> list of (source component, rotation, destination slot)"""
+    two_n_ext = 2 * n * ext
+    k_pos = (k + two_n_ext) % two_n_ext
+    k_hi, k_lo = k_pos // ext, k_pos % ext
+    return [(i, k_hi + (1 if i >= ext - k_lo else 0), (i + k_lo) % ext) for i in range(ext)]
+
+
+def lookup_table_set(module: "hal.Module", f, k, base2k, ext=1):
+    """LookupTable::set (lut.rs:271-338) -> (VecZnx(1 col, ceil(k / base2k) limbs) with `ext` batch items on the device, drift)."""
+    n = module.n
+    raw, step = lookup_table_limbs(n, f, k, base2k, ext)
+    lut = module.vec_znx_from_numpy(raw if ext > 1 else raw[0])
+    r = lut.struct()
+    bt = hal._BT(ext, lut.batch_stride, 0, 0)
+    hal._check(hal.lib().pgb_vec_znx_normalize_assign_batched(module._h, C.c_uint64(base2k), C.byref(r), C.c_uint64(0), C.byref(bt)))
     drift = step >> 1
-    out = module.vec_znx_alloc(1, limbs)
-    module.vec_znx_rotate(-drift, out, 0, lut, 0)  # lookup_table_rotate(-drift): extension_factor = 1 -> one negacyclic rotation
+    out = module.vec_znx_alloc(1, raw.shape[1], ext)
+    item = n * raw.shape[1] * 8
+    for src, rot, dst in lookup_table_rotation_plan(n, ext, -drift):  # res.rotate(-drift) (lut.rs:333)
+        o = hal._VZ(out.buf.ptr + dst * item, n, 1, raw.shape[1], raw.shape[1])
+        a = hal._VZ(lut.buf.ptr + src * item, n, 1, raw.shape[1], raw.shape[1])
+        hal._check(hal.lib().pgb_vec_znx_rotate(module._h, C.c_int64(rot), C.byref(o), C.c_uint64(0), C.byref(a), C.c_uint64(0)))
     return out, drift
 
 
@@ -56,8 +81,18 @@ def _glwe_copy(module, dst_ptr, dst_stride, dst_size, src_ptr, src_stride, src_s
             hal._check(lib.pgb_memset(C.c_void_p(dst_ptr + b * dst_stride + width), 0, C.c_size_t((dst_size - src_size) * cols * n * 8)))
 
 
+def _blind_rotate(module, acc, lwe_dev, batch, n_lwe, lwe_size, lwe_base2k, lut, ext, brk, x_pow_a, block_size, base2k, rot_left):
+    """BlindRotationExecute (cggi/algorithm.rs:88-117): mod switch to 2 * n * ext, then the plain or the extended block-binary rotation."""
+    lwe_2n = module.cggi_mod_switch_2n(lwe_dev, batch, n_lwe, lwe_size, lwe_base2k, 2 * module.n * ext, rot_left=rot_left)
+    if ext == 1:
+        module.cggi_blind_rotate(acc, lwe_2n, n_lwe, lut, brk, x_pow_a, block_size, base2k)
+    else:
+        module.cggi_blind_rotate_extended(acc, lwe_2n, n_lwe, lut, ext, brk, x_pow_a, block_size, base2k)
+
+
 def circuit_bootstrap_to_constant(module: "hal.Module", lwe_dev: "hal.DevBuf", batch, n_lwe, lwe_size, lwe_base2k, brk: "hal.VmpPMat",
-                                  x_pow_a, block_size, atk, tsk, base2k, rank, dnum_res, res_size, log_domain, dsize_atk=1, dsize_tsk=1):
+                                  x_pow_a, block_size, atk, tsk, base2k, rank, dnum_res, res_size, log_domain, dsize_atk=1, dsize_tsk=1,
+                                  extension_factor=1):
     """-> DevBuf holding `batch` GGSW MatZnx(dnum_res, rank+1, rank+1, res_size) (base2k digits).
     lwe_dev: (batch, lwe_size, 1, n_lwe + 1) int64; brk: the n_lwe prepared GGSWs stored consecutively (VmpPMat of the first);
     atk: log_n prepared automorphism keys, atk[i] for Module.trace_galois_element(i); tsk: rank prepared tensor keys."""
@@ -68,13 +103,13 @@ def circuit_bootstrap_to_constant(module: "hal.Module", lwe_dev: "hal.DevBuf", b
     for j in range(1 << log_domain):
         for i in range(dnum_res):
             f[j * alpha + i] = j * (1 << (base2k * (dnum_res - 1 - i)))
-    lut, drift = lookup_table_set(module, f, base2k * dnum_res, base2k)
+    ext = extension_factor
+    lut, drift = lookup_table_set(module, f, base2k * dnum_res, base2k, ext)
     # blind rotation over the BRK layout (k = brk.max_k: brk.size limbs)
-    lwe_2n = module.cggi_mod_switch_2n(lwe_dev, batch, n_lwe, lwe_size, lwe_base2k, 2 * n, rot_left=True)
     acc_size = brk.size
     acc = module.vec_znx_alloc(cols, acc_size, batch)
-    module.cggi_blind_rotate(acc, lwe_2n, n_lwe, lut, brk, x_pow_a, block_size, base2k)
-    gap = 2 * drift
+    _blind_rotate(module, acc, lwe_dev, batch, n_lwe, lwe_size, lwe_base2k, lut, ext, brk, x_pow_a, block_size, base2k, True)
+    gap = 2 * drift // ext  # circuit.rs:336
     assert gap > 0
     ggsw_stride = n * dnum_res * cols * cols * res_size * 8
     ggsw = hal.DevBuf(batch * ggsw_stride)
@@ -245,18 +280,19 @@ def exponent_lut(base2k, dnum_res, log_domain):
 
 
 def circuit_bootstrap_to_exponent(module: "hal.Module", log_gap_out, lwe_dev: "hal.DevBuf", batch, n_lwe, lwe_size, lwe_base2k, brk: "hal.VmpPMat",
-                                  x_pow_a, block_size, atk, tsk, base2k, rank, dnum_res, size, log_domain, dsize_atk=1, dsize_tsk=1):
+                                  x_pow_a, block_size, atk, tsk, base2k, rank, dnum_res, size, log_domain, dsize_atk=1, dsize_tsk=1,
+                                  extension_factor=1):
     """circuit_bootstrap_core(to_exponent = true) (circuit.rs:219-380): -> DevBuf of `batch` GGSW MatZnx(dnum_res, rank+1, rank+1, size).
     One GLWE layout throughout (`size` limbs = the limbs of the blind-rotation key)."""
     n, cols = module.n, rank + 1
     assert brk.size == size
     f, alpha = exponent_lut(base2k, dnum_res, log_domain)
-    lut, drift = lookup_table_set(module, f, base2k * dnum_res, base2k)
-    lwe_2n = module.cggi_mod_switch_2n(lwe_dev, batch, n_lwe, lwe_size, lwe_base2k, 2 * n, rot_left=False)  # rotation direction Right (:305-307)
+    ext = extension_factor
+    lut, drift = lookup_table_set(module, f, base2k * dnum_res, base2k, ext)
     ops = DeviceGlweOps(module, atk, base2k, cols, size, batch, dsize_atk)
     acc = ops.new()
-    module.cggi_blind_rotate(acc, lwe_2n, n_lwe, lut, brk, x_pow_a, block_size, base2k)
-    gap = 2 * drift
+    _blind_rotate(module, acc, lwe_dev, batch, n_lwe, lwe_size, lwe_base2k, lut, ext, brk, x_pow_a, block_size, base2k, False)  # direction Right (:305-307)
+    gap = 2 * drift // ext
     assert gap > 0
     log_gap_in = (gap * alpha - 1).bit_length()
     ggsw_stride = n * dnum_res * cols * cols * size * 8

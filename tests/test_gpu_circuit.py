@@ -15,21 +15,31 @@ from util_circuit import OracleGlweOps, _Ct
 pytestmark = pytest.mark.gpu
 
 
-def _oracle_lut(n, f, k, base2k):
-    limbs = -(-k // base2k)
-    scale = 1 << (base2k - k % base2k) if k % base2k else 1
-    step = (n + len(f) // 2) // len(f)
-    full = np.zeros((limbs, 1, n), dtype=np.int64)
-    for i, fi in enumerate(f):
-        full[limbs - 1, 0, i * step:(i + 1) * step] = fi * scale
-    O.vec_znx_normalize_assign(base2k, full, 0)
-    out = np.zeros_like(full)
-    O.vec_znx_rotate(-(step >> 1), out, 0, full, 0)
-    return out, step >> 1
+def _oracle_lut(n, f, k, base2k, ext=1):
+    """LookupTable::set over the oracle: the shared un-normalised limbs (circuit.lookup_table_limbs), oracle normalisation, then
+    lookup_table_rotate(-drift) (lut.rs:340-362) -> (list of ext arrays (limbs, 1, n), drift)."""
+    raw, step = circuit.lookup_table_limbs(n, f, k, base2k, ext)
+    for j in range(ext):
+        O.vec_znx_normalize_assign(base2k, raw[j], 0)
+    drift = step >> 1
+    out = [None] * ext
+    for src, rot, dst in circuit.lookup_table_rotation_plan(n, ext, -drift):
+        out[dst] = np.zeros_like(raw[src])
+        O.vec_znx_rotate(rot, out[dst], 0, raw[src], 0)
+    return (out if ext > 1 else out[0]), drift
+
+
+def _oracle_blind_rotate(o, acc, lwe, K, n, ext, lut, brk_o, xpa, block, rot_left):
+    lwe_2n = O.mod_switch_2n(2 * n * ext, lwe, K, rot_left=rot_left)
+    if ext == 1:
+        o.cggi_blind_rotate_block_binary(acc, lwe_2n, lut, brk_o, xpa, block, K)
+    else:
+        o.cggi_blind_rotate_block_binary_extended(acc, lwe_2n, lut, brk_o, xpa, block, K)
 
 
 @pytest.mark.parametrize("fl", [pb.FFT64, pb.NTT120])
-def test_circuit_bootstrap_to_constant(fl):
+@pytest.mark.parametrize("ext", [1, 2])
+def test_circuit_bootstrap_to_constant(fl, ext):
     n, log_n, n_lwe, block, rank, K = 256, 8, 12, 3, 1, 12 if fl == pb.FFT64 else 18
     brk_size, dnum_res, res_size, log_domain, batch, lwe_size = 2, 2, 2, 2, 3, 2
     cols = rank + 1
@@ -66,7 +76,7 @@ def test_circuit_bootstrap_to_constant(fl):
     lwe_dev.upload(lwe)
 
     ggsw = circuit.circuit_bootstrap_to_constant(g, lwe_dev, batch, n_lwe, lwe_size, K, brk_g, g.cggi_x_pow_a(), block, atk_g, tsk_g, K, rank,
-                                                 dnum_res, res_size, log_domain)
+                                                 dnum_res, res_size, log_domain, extension_factor=ext)
     got = ggsw.download(np.int64, (batch, dnum_res, cols, res_size, cols, n))
 
     # the same sequence over the oracle
@@ -75,13 +85,12 @@ def test_circuit_bootstrap_to_constant(fl):
     for j in range(1 << log_domain):
         for i in range(dnum_res):
             f[j * alpha + i] = j * (1 << (K * (dnum_res - 1 - i)))
-    lut, drift = _oracle_lut(n, f, K * dnum_res, K)
+    lut, drift = _oracle_lut(n, f, K * dnum_res, K, ext)
     xpa = o.cggi_x_pow_a()
     want = np.zeros_like(got)
     for b in range(batch):
-        lwe_2n = O.mod_switch_2n(2 * n, lwe[b], K, rot_left=True)
         acc = np.zeros((brk_size, cols, n), dtype=np.int64)
-        o.cggi_blind_rotate_block_binary(acc, lwe_2n, lut, brk_o, xpa, block, K)
+        _oracle_blind_rotate(o, acc, lwe[b], K, n, ext, lut, brk_o, xpa, block, True)
         for i in range(dnum_res):
             tmp = np.zeros((tmp_size, cols, n), dtype=np.int64)
             tmp[:brk_size] = acc[:tmp_size]
@@ -90,7 +99,7 @@ def test_circuit_bootstrap_to_constant(fl):
             if i + 1 < dnum_res:
                 nxt = np.zeros_like(acc)
                 for c in range(cols):
-                    O.vec_znx_rotate(-2 * drift, nxt, c, acc, c)
+                    O.vec_znx_rotate(-(2 * drift // ext), nxt, c, acc, c)
                 acc = nxt
         o.ggsw_expand_row(want[b], K, tsk_o, K)
     assert np.array_equal(got, want)
@@ -107,6 +116,25 @@ def test_lookup_table_set():
         lut_g, drift_g = circuit.lookup_table_set(g, f, k, K)
         lut_o, drift_o = _oracle_lut(n, f, k, K)
         assert drift_g == drift_o and np.array_equal(g.vec_znx_to_numpy(lut_g), lut_o)
+        for ext in (2, 4):  # the ext-component table: component j of Y^-drift * L(Y) over the domain n * ext (lut.rs:318-333)
+            le_g, d_g = circuit.lookup_table_set(g, f, k, K, ext)
+            le_o, d_o = _oracle_lut(n, f, k, K, ext)
+            assert d_g == d_o and np.array_equal(g.vec_znx_to_numpy(le_g), np.stack(le_o))
+            raw, step_e = circuit.lookup_table_limbs(n, f, k, K, ext)
+            big = np.zeros((raw.shape[1], n * ext), dtype=np.int64)
+            for j in range(ext):
+                O.vec_znx_normalize_assign(K, raw[j], 0)
+                big[:, j::ext] = raw[j][:, 0]
+            N = n * ext
+            rot = np.zeros_like(big)
+            for i in range(N):
+                p = (i - d_o) % (2 * N)
+                if p < N:
+                    rot[:, p] = big[:, i]
+                else:
+                    rot[:, p - N] = -big[:, i]
+            for j in range(ext):
+                assert np.array_equal(le_o[j][:, 0], rot[:, j::ext]), (ext, j)
         step, limbs = (n + len(f) // 2) // len(f), -(-k // K)
         back = np.zeros_like(lut_o)
         O.vec_znx_rotate(drift_o, back, 0, lut_o, 0)
@@ -169,7 +197,8 @@ def test_glwe_pack():
 
 
 @pytest.mark.parametrize("fl", [pb.FFT64, pb.NTT120])
-def test_circuit_bootstrap_to_exponent(fl):
+@pytest.mark.parametrize("ext", [1, 2])
+def test_circuit_bootstrap_to_exponent(fl, ext):
     """Exponent mode (circuit.rs:219-380 with to_exponent = true: LUT of the gadget powers, rotation direction Right, post_process with the
     partial trace and glwe_pack per row, ggsw_expand_row): device orchestration == the same sequencing over the oracle."""
     n, n_lwe, block, rank, K = 128, 6, 3, 1, 12 if fl == pb.FFT64 else 18
@@ -177,18 +206,18 @@ def test_circuit_bootstrap_to_exponent(fl):
     cols = rank + 1
     g, o, brk_g, brk_o, atk, tsk, lwe, lwe_dev = _setup(fl, n, n_lwe, rank, K, size, size, batch, lwe_size, 960 + fl)
     ggsw = circuit.circuit_bootstrap_to_exponent(g, log_gap_out, lwe_dev, batch, n_lwe, lwe_size, K, brk_g, g.cggi_x_pow_a(), block, atk[0], tsk[0],
-                                                 K, rank, dnum_res, size, log_domain)
+                                                 K, rank, dnum_res, size, log_domain, extension_factor=ext)
     got = ggsw.download(np.int64, (batch, dnum_res, cols, size, cols, n))
 
     f, alpha = circuit.exponent_lut(K, dnum_res, log_domain)
-    lut, drift = _oracle_lut(n, f, K * dnum_res, K)
-    gap = 2 * drift
+    lut, drift = _oracle_lut(n, f, K * dnum_res, K, ext)
+    gap = 2 * drift // ext
     log_gap_in = (gap * alpha - 1).bit_length()
     assert log_gap_in != log_gap_out  # the packing branch of post_process is the one exercised
     xpa = o.cggi_x_pow_a()
     acc = _Ct(np.zeros((batch, size, cols, n), dtype=np.int64))
     for b in range(batch):
-        o.cggi_blind_rotate_block_binary(acc.arr[b], O.mod_switch_2n(2 * n, lwe[b], K, rot_left=False), lut, brk_o, xpa, block, K)
+        _oracle_blind_rotate(o, acc.arr[b], lwe[b], K, n, ext, lut, brk_o, xpa, block, False)
     ops = OracleGlweOps(o, atk[1], K, cols, size, batch, n)
     want = np.zeros_like(got)
     for i in range(dnum_res):
