@@ -588,6 +588,74 @@ def aux_measurements(pb, torch, local, peak):
         aux[f"cggi_bootstraps_per_s_{nm}_n512_nlwe687_b{B}"] = {"value": B / (ms * 1e-3), "ms_per_batch": ms,
                                                                  "launches_per_batch": (m.launch_count - l0) // 3}
         del m, brk_buf, xpa, lut, lwe_dev, res, sc
+    # N4 compositions at the headline key-switch shape (n=4096, base2k=18, rank 1, 3 limbs, key dnum 3 x 4 limbs): automorphism
+    # (key-switch + X -> X^p) and trace (log_n key-switch/automorphism/add rounds), batch of ciphertexts per call
+    try:
+        for fl, nm in ((pb.NTT120, "ntt120"), (pb.FFT64, "fft64")):
+            n, B, k = 4096, 1024, 18
+            m = pb.Module(n, fl, device=local)
+            m.set_stream(stream.cuda_stream)
+            keys = []
+            for _ in range(12):
+                pm = m.vmp_pmat_alloc(3, 1, 2, 4)
+                m.vmp_prepare(pm, m.mat_znx_from_numpy(rng.integers(-(1 << 17), 1 << 17, size=(3, 1, 4, 2, n), dtype=np.int64)))
+                keys.append(pm)
+            a = m.vec_znx_from_numpy(rng.integers(-(1 << 17), 1 << 17, size=(B, 3, 2, n), dtype=np.int64))
+            r = m.vec_znx_alloc(2, 3, B)
+            sc = [None, None]
+
+            def f_aut():
+                sc[0] = m.glwe_automorphism(r, k, a, k, keys[0], k, 5, 1, sc[0])
+
+            def f_tr():
+                sc[1] = m.glwe_trace_assign(r, k, 0, keys, k, 1, sc[1])
+
+            ms = _time_ms(torch, stream, f_aut, 5)
+            aux[f"glwe_automorphism_per_s_{nm}_n4096_b{B}"] = B / (ms * 1e-3)
+            ms = _time_ms(torch, stream, f_tr, 3, warm=1)
+            aux[f"glwe_trace_per_s_{nm}_n4096_b{B}"] = B / (ms * 1e-3)
+            del m, keys, a, r, sc
+    except Exception as e:
+        aux["glwe_trace_per_s"] = {"error": repr(e)}
+    # circuit bootstrapping, constant mode (poulpy-bench circuit_bootstrapping.rs:47-129 "1-bit"): n=1024, n_lwe=574, block 7, rank 2,
+    # base2k 13, BRK/ATK/TSK k=52 dnum=3, result GGSW k=26 dnum=2; synthetic keys; batch of LWEs per call
+    try:
+        from poulpy_b200 import circuit
+        n, log_n, n_lwe, block, rank, K, B = 1024, 10, 574, 7, 2, 13, 128
+        cols, ksz, kd, res_size, dnum_res = rank + 1, 4, 3, 2, 2
+        m = pb.Module(n, pb.FFT64, device=local)
+        m.set_stream(stream.cuda_stream)
+        per = n * cols * cols * kd * ksz * m.prep_bytes
+        brk_buf = pb.DevBuf(per * n_lwe)
+        one = pb.hal.VmpPMat(brk_buf, n, kd, cols, cols, ksz)
+        m.vmp_prepare(one, m.mat_znx_from_numpy(rng.integers(-(1 << 12), 1 << 12, size=(kd, cols, ksz, cols, n), dtype=np.int64)))
+        for i in range(1, n_lwe):
+            lib.pgb_memcpy_d2d(C.c_void_p(brk_buf.ptr + i * per), C.c_void_p(brk_buf.ptr), C.c_size_t(per))
+
+        def mk(count):
+            out = []
+            for _ in range(count):
+                pm = m.vmp_pmat_alloc(kd, rank, cols, ksz)
+                m.vmp_prepare(pm, m.mat_znx_from_numpy(rng.integers(-(1 << 12), 1 << 12, size=(kd, rank, ksz, cols, n), dtype=np.int64)))
+                out.append(pm)
+            return out
+
+        atk, tsk = mk(log_n), mk(rank)
+        lwe = rng.integers(-(1 << 12), 1 << 12, size=(B, 1, 1, n_lwe + 1), dtype=np.int64)
+        lwe_dev = pb.DevBuf(lwe.nbytes)
+        lwe_dev.upload(lwe)
+        xpa = m.cggi_x_pow_a()
+
+        def cbt():
+            circuit.circuit_bootstrap_to_constant(m, lwe_dev, B, n_lwe, 1, K, one, xpa, block, atk, tsk, K, rank, dnum_res, res_size, 1)
+
+        l0 = m.launch_count
+        ms = _time_ms(torch, stream, cbt, 2, warm=1)
+        aux[f"circuit_bootstraps_per_s_fft64_n1024_nlwe574_rank2_b{B}"] = {"value": B / (ms * 1e-3), "ms_per_batch": ms,
+                                                                          "launches_per_batch": (m.launch_count - l0) // 3}
+        del m, brk_buf, atk, tsk, lwe_dev, xpa
+    except Exception as e:
+        aux["circuit_bootstraps_per_s_fft64_n1024_nlwe574_rank2"] = {"error": repr(e)}
     return aux
 
 
