@@ -516,12 +516,52 @@ extern "C" int pgb_glwe_tensor_relinearize_batched(pgb_module *m, pgb_vec_znx *r
     return PGB_OK;
 }
 
+// Single-kernel route of the automorphism family in the NTT120 flavour (ntt120_gadget.cu, automorphism epilogue): key-switch, X -> X^p and
+// the addition / subtraction of the input in one launch per batch.  aut_mode 1..3 = op 0..2 of pgb_glwe_automorphism_op_batched, 4 = plain
+// glwe_automorphism.  Returns 1 when the batch was finished here, 0 when the caller must run the limb-wise sequence (unsupported geometry
+// or a ciphertext flagged by the collapsed-key bound), < 0 on error.  `ar` supplies the flag list and, when res overlaps a, the staging
+// buffer of the outputs (the epilogue gathers column 0 of a at permuted positions, so it cannot run in place).
+static int automorphism_fused(pgb_module *m, int aut_mode, pgb_vec_znx *res, uint64_t res_bs, const pgb_vec_znx *a, uint64_t a_bs,
+                              const pgb_vmp_pmat *key, uint64_t base2k, int64_t p, uint64_t dsize, uint64_t B, Arena &ar) {
+    if (m->flavour != PGB_NTT120 || !ntt120_fused_supported(m) || getenv("PGB_NO_FUSION") || getenv("PGB_NO_AUT_FUSION")) return 0;
+    const uint64_t n = m->n, rank_in = key->cols_in, cols = key->cols_out;
+    const uint64_t Rfull = rank_in * a->size, R = dsize == 1 ? umin64(key->rows * key->cols_in, Rfull) : Rfull;
+    if (!ntt120_gadget_supported(m, (int)R, (int)cols, (int)key->size, (int)base2k, (int)B)) return 0;
+    if (dsize > 1 && !gadget_likely_fits(n, R, key->size, base2k)) return 0;
+    const size_t mark = ar.used;
+    int *ok = (int *)ar.take((2 * B + 1) * sizeof(int));
+    const char *r0 = (const char *)res->data, *r1 = r0 + (B - 1) * res_bs + n * cols * res->size * 8;
+    const char *a0 = (const char *)a->data, *a1 = a0 + (B - 1) * a_bs + n * a->cols * a->size * 8;
+    const bool aliased = r0 < a1 && a0 < r1;
+    char *out = (char *)res->data;
+    uint64_t out_bs = res_bs;
+    if (aliased) {
+        out_bs = n * cols * res->size * 8;
+        out = (char *)ar.take(B * out_bs);
+    }
+    if (!ok || !out) {
+        ar.used = mark;
+        return 0;
+    }
+    const int small = (int)umin64(a->size, key->size);
+    PGB_TRY(ntt120_gadget_fused(m, (const char *)a->data, a_bs, (int)a->cols, (int)rank_in, 1, (int)R, (const char *)key->data,
+                                (int)(cols * key->size), (int)cols, small, out, out_bs, (int)res->size, (int)base2k, (int)B, ok, (int)dsize,
+                                (int)a->size, (int)(key->rows * key->cols_in), (int)key->rows, aut_mode, p, aut_mode == 4 ? 0 : small));
+    int nfail = 0;
+    PGB_CHECK_CUDA(cudaMemcpyAsync(&nfail, ok + B, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+    if (nfail == 0 && aliased)
+        PGB_CHECK_CUDA(cudaMemcpy2DAsync(res->data, res_bs, out, out_bs, out_bs, B, cudaMemcpyDeviceToDevice, m->stream));
+    if (nfail != 0) ar.used = mark;
+    return nfail == 0 ? 1 : 0;
+}
+
 // ---- glwe_automorphism (poulpy-core/src/automorphism/glwe_ct.rs:51-72): key-switch with the automorphism key, then
 // X -> X^p on every column.  The key-switch lands in scratch so that the permutation is out of place.
 extern "C" size_t pgb_glwe_automorphism_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t a_size, uint64_t a_base2k,
                                                   const pgb_vmp_pmat *key, uint64_t key_base2k, uint64_t dsize, uint64_t batch) {
     return align_up(batch * m->n * key->cols_out * res_size * 8) + pgb_glwe_keyswitch_tmp_bytes(m, res_size, a_size, a_base2k, key, key_base2k, dsize, batch) +
-           ALIGN;
+           align_up((2 * batch + 1) * sizeof(int)) + ALIGN;
 }
 extern "C" int pgb_glwe_automorphism_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, const pgb_vec_znx *a, uint64_t a_base2k,
                                              const pgb_vmp_pmat *key, uint64_t key_base2k, int64_t p, uint64_t dsize, const pgb_batch *bt,
@@ -534,6 +574,12 @@ extern "C" int pgb_glwe_automorphism_batched(pgb_module *m, pgb_vec_znx *res, ui
         return PGB_ERR_SCRATCH;
     }
     const uint64_t n = m->n, B = bt->count, tmp_bs = n * res->cols * res->size * 8;
+    if (res_base2k == key_base2k && a_base2k == key_base2k && a->cols == key->cols_in + 1) {
+        Arena ar = {(char *)scratch, scratch_len, 0};
+        const int done = automorphism_fused(m, 4, res, bt->stride_res, a, bt->stride_a, key, key_base2k, p, dsize, B, ar);
+        if (done < 0) return done;
+        if (done) return PGB_OK;
+    }
     pgb_vec_znx tmp = mk(scratch, n, res->cols, res->size);
     char *ks_scratch = (char *)scratch + align_up(B * tmp_bs);
     pgb_batch btk = {B, tmp_bs, bt->stride_a, 0};
@@ -559,7 +605,8 @@ extern "C" size_t pgb_glwe_automorphism_add_assign_tmp_bytes(const pgb_module *m
     t += align_up(batch * n * rank_in * in_size * pb);                                  // a_dft
     if (res_base2k != key_base2k) t += align_up(batch * n * cols * in_size * 8);        // res_conv
     if (dsize > 1) t += align_up(batch * n * rank_in * div_ceil64(in_size, dsize) * pb) + align_up(batch * n * cols * key->size * pb);
-    return t + ALIGN;
+    const uint64_t fused = align_up((2 * batch + 1) * sizeof(int)) + align_up(batch * n * cols * res_size * 8); // flags + in-place staging
+    return (t > fused ? t : fused) + ALIGN;
 }
 // glwe_automorphism_add / _sub / _sub_negate (automorphism/glwe_ct.rs:95-275): res = normalize(aut_p(ks(a)) (+|-) a) resp. normalize(a -
 // aut_p(ks(a))), out of place (res == a gives the _assign forms); op = 0 add, 1 sub, 2 sub_negate.  a and res share a_base2k / sizes here
@@ -589,6 +636,11 @@ extern "C" int pgb_glwe_automorphism_op_batched(pgb_module *m, int op, pgb_vec_z
     }
     const uint64_t n = m->n, pb = prep_bytes(m), bb = big_bytes(m), B = bt->count, rank_in = key->cols_in, cols = key->cols_out;
     Arena ar = {(char *)scratch, scratch_len, 0};
+    if (res_base2k == key_base2k) {
+        const int done = automorphism_fused(m, op + 1, res, bt->stride_res, a, bt->stride_a, key, key_base2k, p, dsize, B, ar);
+        if (done < 0) return done;
+        if (done) return PGB_OK;
+    }
     const uint64_t res_dft_bs = n * cols * key->size * pb, big2_bs = n * cols * key->size * bb;
     pgb_vec_znx_dft res_dft = mk(ar.take(B * res_dft_bs), n, cols, key->size);
     pgb_vec_znx_big big2 = mk(ar.take(B * big2_bs), n, cols, key->size);
@@ -652,6 +704,7 @@ extern "C" size_t pgb_glwe_trace_assign_tmp_bytes(const pgb_module *m, uint64_t 
     const uint64_t in_size = res_base2k == key_base2k ? res_size : conv_size(res_size, res_base2k, key_base2k);
     size_t t = pgb_glwe_automorphism_add_assign_tmp_bytes(m, in_size, key_base2k, key, key_base2k, dsize, batch);
     if (res_base2k != key_base2k) t += align_up(batch * m->n * key->cols_out * in_size * 8);
+    t += align_up(batch * m->n * key->cols_out * in_size * 8); // second GLWE buffer: the rounds alternate between two buffers
     return t + ALIGN;
 }
 // keys: host array of log_n prepared automorphism keys (same shape), keys[i] for pgb_trace_galois_element(i); entries below `skip` unread
@@ -683,11 +736,32 @@ extern "C" int pgb_glwe_trace_assign_batched(pgb_module *m, pgb_vec_znx *res, ui
         pgb_batch btn = {B, cur_bs, bt->stride_res, 0};
         for (uint64_t i = 0; i < res->cols; i++) PGB_TRY(big_normalize_impl(m, &cur, key_base2k, 0, i, res, res_base2k, i, 0, false, &btn));
     }
-    pgb_batch btc = {B, cur_bs, 0, 0};
+    // The rounds run out of place, alternating between `cur` and a second buffer (glwe_automorphism_add_assign is res = aut(ks(res)) +
+    // res; the single-kernel route cannot run in place), and the result is copied back if it ends in the second one.
+    const uint64_t alt_bs = n * cur.cols * cur.size * 8;
+    pgb_vec_znx alt = mk(sc, n, cur.cols, cur.size);
+    sc += align_up(B * alt_bs);
+    sc_len -= (size_t)align_up(B * alt_bs);
+    pgb_vec_znx home = cur;
+    const uint64_t home_bs = cur_bs;
+    uint64_t alt_stride = alt_bs;
     for (uint64_t i = skip; i < (uint64_t)m->log_n; i++) { // (:166-177)
+        pgb_batch btc = {B, cur_bs, 0, 0};
         for (uint64_t c = 0; c < cur.cols; c++) PGB_TRY(rsh_assign_impl(m, key_base2k, 1, &cur, c, &btc)); // glwe_rsh(1)
-        PGB_TRY(pgb_glwe_automorphism_add_assign_batched(m, &cur, key_base2k, &keys[i], key_base2k, pgb_trace_galois_element(m, i), dsize, &btc,
-                                                         sc, sc_len));
+        pgb_batch bto = {B, alt_stride, cur_bs, 0};
+        PGB_TRY(pgb_glwe_automorphism_op_batched(m, 0, &alt, key_base2k, &cur, &keys[i], key_base2k, pgb_trace_galois_element(m, i), dsize, &bto,
+                                                 sc, sc_len));
+        pgb_vec_znx tv = cur;
+        cur = alt;
+        alt = tv;
+        const uint64_t ts = cur_bs;
+        cur_bs = alt_stride;
+        alt_stride = ts;
+    }
+    if (cur.data != home.data) {
+        PGB_CHECK_CUDA(cudaMemcpy2DAsync(home.data, home_bs, cur.data, cur_bs, alt_bs, B, cudaMemcpyDeviceToDevice, m->stream));
+        cur = home;
+        cur_bs = home_bs;
     }
     if (res_base2k != key_base2k) {
         pgb_batch btn = {B, bt->stride_res, cur_bs, 0};

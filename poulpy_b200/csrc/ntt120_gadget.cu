@@ -44,6 +44,13 @@ struct GadgetArgs {
     int K, S, res_size;                             // base2k, key size (digits of the collapsed integer), output limbs
     int base_bits;                                  // ceil(log2(R * n)) + (S - 1) * K + 3
     int batch;
+    // automorphism epilogue (AUT instances only): output coefficient j' takes source coefficient j = j' * aut_pinv mod 2n (sign flipped
+    // when that product lands in [n, 2n)).  x = CRT value + body.  mode 1: res = normalize(aut(x) + a), 2: normalize(aut(x) - a),
+    // 3: normalize(a - aut(x)) with a = limbs of the INPUT ciphertext (all columns, the first post_size limbs) -- the limb-wise
+    // big_automorphism / big_(add|sub)_small / big_normalize sequence of automorphism/glwe_ct.rs:95-275; mode 4: res = aut(normalize(x))
+    // (glwe_automorphism, glwe_ct.rs:51-72: the digits are permuted and negated after the normalisation)
+    int aut_mode, post_size;
+    uint32_t aut_pinv;
     uint32_t zero;                                  // always 0 (see ct_bfz)
     uint32_t m_w[4][4];                             // M_k = Q / Q[k], four 32-bit words each (arithmetic.rs:119-140)
     uint32_t nq_w[4];                               // 2^128 - Q
@@ -269,7 +276,7 @@ template <int L> __host__ __device__ constexpr int fmask(int i) {
     return (((i >> 5) & 3) << 2) ^ (GGeo<L>::SIG3 ? (((i >> 7) & 3) << 3) : (((i >> 8) & 1) << 4));
 }
 
-template <int L> __device__ __forceinline__ void gadget_body(const GadgetArgs &p, uint32_t *__restrict__ sm, const uint2 *__restrict__ twf,
+template <int L, bool AUT> __device__ __forceinline__ void gadget_body(const GadgetArgs &p, uint32_t *__restrict__ sm, const uint2 *__restrict__ twf,
                                                              const uint2 *__restrict__ twi, const uint4 *__restrict__ lastf,
                                                              const uint4 *__restrict__ lasti, const int K) {
     typedef GGeo<L> G;
@@ -480,6 +487,82 @@ template <int L> __device__ __forceinline__ void gadget_body(const GadgetArgs &p
             const uint32_t hw0 = (uint32_t)p.half_lo, hw1 = (uint32_t)(p.half_lo >> 32), hw2 = (uint32_t)p.half_hi, hw3 = (uint32_t)(p.half_hi >> 32);
             long long *res_ct = reinterpret_cast<long long *>(p.res + (size_t)ct * p.res_bs) + K * (n / 4) + t;
             const long long *in_kt = in + K * (n / 4) + t + (size_t)(S - 1) * in_ls; // body limb S - 1 (column 0)
+            if constexpr (AUT) {
+                // Automorphism epilogue (see GadgetArgs): this thread still owns OUTPUT coefficients K n/4 + i T + t (coalesced stores and
+                // reads of `a`); residues and body limbs are gathered at the source coefficient.
+                const int mode = p.aut_mode;
+                for (int o = 0; o < cols_out; o++) {
+                    const bool with_small = o == 0 && p.small_size > 0;
+#pragma unroll 1
+                    for (int i = 0; i < 4; i++) {
+                        const int jo = K * (n / 4) + i * T + t;
+                        const uint32_t j0 = ((uint32_t)jo * p.aut_pinv) & (uint32_t)(2 * n - 1);
+                        const int js = (int)(j0 & (uint32_t)(n - 1));
+                        const bool flip = j0 >= (uint32_t)n;            // sign of the permuted coefficient
+                        const bool negx = mode == 4 ? false : (mode == 3 ? !flip : flip); // sign applied to x before the digits
+                        const uint32_t off = (uint32_t)(o * n + swz<L>(js)) * 4u;
+                        const uint32_t t0 = ld_cluster(rb[0] + off), t1 = ld_cluster(rb[1] + off), t2 = ld_cluster(rb[2] + off), t3 = ld_cluster(rb[3] + off);
+                        const unsigned long long fr = (unsigned long long)t0 * p.inv60[0] + (unsigned long long)t1 * p.inv60[1] +
+                                                      (unsigned long long)t2 * p.inv60[2] + (unsigned long long)t3 * p.inv60[3];
+                        const uint32_t e = (uint32_t)((fr + (1ull << 59)) >> 60);
+                        const unsigned long long a0 = (unsigned long long)t0 * p.m_w[0][0] + (unsigned long long)t1 * p.m_w[1][0] +
+                                                      (unsigned long long)t2 * p.m_w[2][0] + (unsigned long long)t3 * p.m_w[3][0] + (unsigned long long)e * p.nq_w[0];
+                        const unsigned long long a1 = (a0 >> 32) + (unsigned long long)t0 * p.m_w[0][1] + (unsigned long long)t1 * p.m_w[1][1] +
+                                                      (unsigned long long)t2 * p.m_w[2][1] + (unsigned long long)t3 * p.m_w[3][1] + (unsigned long long)e * p.nq_w[1];
+                        const unsigned long long a2 = (a1 >> 32) + (unsigned long long)t0 * p.m_w[0][2] + (unsigned long long)t1 * p.m_w[1][2] +
+                                                      (unsigned long long)t2 * p.m_w[2][2] + (unsigned long long)t3 * p.m_w[3][2] + (unsigned long long)e * p.nq_w[2];
+                        const unsigned long long a3 = (a2 >> 32) + (unsigned long long)t0 * p.m_w[0][3] + (unsigned long long)t1 * p.m_w[1][3] +
+                                                      (unsigned long long)t2 * p.m_w[2][3] + (unsigned long long)t3 * p.m_w[3][3] + (unsigned long long)e * p.nq_w[3];
+                        // u = +-v + half as a 128-bit integer in two 64-bit words (mod 2^128; only the low S K bits are read)
+                        unsigned long long lo = (a0 & 0xffffffffull) | (a1 << 32), hi = (a2 & 0xffffffffull) | (a3 << 32);
+                        if (negx) {
+                            lo = ~lo + 1;
+                            hi = ~hi + (lo == 0);
+                        }
+                        lo += p.half_lo;
+                        hi += p.half_hi + (lo < p.half_lo);
+                        const long long *bp = in + (size_t)(S - 1) * in_ls + js;                     // body (column 0) at the source coefficient
+                        const long long *pp = in + (size_t)(S - 1) * in_ls + (size_t)o * n + jo;     // a, column o, at the output coefficient
+                        long long *out_p = reinterpret_cast<long long *>(p.res + (size_t)ct * p.res_bs) + (size_t)(S - 1) * res_ls + (size_t)o * n + jo;
+                        for (int j = S - 1; j >= 0; j--) {
+                            if (with_small && j < p.small_size) {
+                                const long long sv = __ldg(bp);
+                                const unsigned long long sl = (unsigned long long)sv, sh = (unsigned long long)(sv >> 63);
+                                if (negx) {
+                                    const unsigned long long nl = lo - sl;
+                                    hi = hi - sh - (lo < sl);
+                                    lo = nl;
+                                } else {
+                                    lo += sl;
+                                    hi += sh + (lo < sl);
+                                }
+                            }
+                            if (mode != 4 && j < p.post_size) {
+                                const long long sv = __ldg(pp);
+                                const unsigned long long sl = (unsigned long long)sv, sh = (unsigned long long)(sv >> 63);
+                                if (mode == 2) {
+                                    const unsigned long long nl = lo - sl;
+                                    hi = hi - sh - (lo < sl);
+                                    lo = nl;
+                                } else {
+                                    lo += sl;
+                                    hi += sh + (lo < sl);
+                                }
+                            }
+                            bp -= in_ls;
+                            pp -= in_ls;
+                            long long d = (long long)(lo & kmask) - (long long)khalf;
+                            if (mode == 4 && flip) d = -d;
+                            if (j < a_start) *out_p = d;
+                            out_p -= res_ls;
+                            lo = (lo >> Kb) | (hi << (64 - Kb));
+                            hi >>= Kb;
+                        }
+                        long long *zp = reinterpret_cast<long long *>(p.res + (size_t)ct * p.res_bs) + (size_t)o * n + jo;
+                        for (int j = a_start; j < p.res_size; j++) zp[(size_t)j * res_ls] = 0;
+                    }
+                }
+            } else
             for (int o = 0; o < cols_out; o++) {
                 const bool with_small = o == 0 && p.small_size > 0;
 #pragma unroll 1
@@ -590,7 +673,7 @@ template <int L> __device__ __forceinline__ void gadget_body(const GadgetArgs &p
 #undef P2_ADDR
 }
 
-template <int L, int MB> __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(GGeo<L>::T, MB * 256 / GGeo<L>::T) ntt120_gadget_kernel(const __grid_constant__ GadgetArgs p,
+template <int L, int MB, bool AUT> __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(GGeo<L>::T, MB * 256 / GGeo<L>::T) ntt120_gadget_kernel(const __grid_constant__ GadgetArgs p,
                                                                                                             const uint2 *__restrict__ twf,
                                                                                                             const uint2 *__restrict__ twi,
                                                                                                             const uint4 *__restrict__ lastf,
@@ -599,7 +682,7 @@ template <int L, int MB> __global__ void __cluster_dims__(4, 1, 1) __launch_boun
     constexpr int n = GGeo<L>::N;
     cl_arrive(); // primes the arrive/wait pairing used by the per-ciphertext loop
     const int k = blockIdx.x & 3; // = rank in the cluster; one code body for all four primes (instruction-cache footprint)
-    gadget_body<L>(p, smem, twf + (size_t)k * n, twi + (size_t)k * n, lastf + (size_t)k * (n / 2), lasti + (size_t)k * (n / 2), k);
+    gadget_body<L, AUT>(p, smem, twf + (size_t)k * n, twi + (size_t)k * n, lastf + (size_t)k * (n / 2), lasti + (size_t)k * (n / 2), k);
 }
 
 // collapsed key in the gadget kernel's layout: out[r][col][k][chunk][t][4] = sum_j 2^((S-1-j)K) * pmat[r][j * cols_out + col][k][16t + 4 chunk + w]
@@ -648,13 +731,14 @@ static uint32_t pow2_mod(uint64_t e, uint32_t q) {
     return (uint32_t)r;
 }
 
-template <int L, int MB> int launch_gadget_mb(pgb_module *m, const GadgetArgs &p, size_t smem);
+template <int L, int MB, bool AUT> int launch_gadget_mb(pgb_module *m, const GadgetArgs &p, size_t smem);
 template <int L> int launch_gadget(pgb_module *m, const GadgetArgs &p, size_t smem) {
     const char *e = getenv("PGB_GADGET_MB");
-    if (e && atoi(e) == 4) return launch_gadget_mb<L, 4>(m, p, smem);
-    return launch_gadget_mb<L, 3>(m, p, smem);
+    if (p.aut_mode) return launch_gadget_mb<L, 3, true>(m, p, smem);
+    if (e && atoi(e) == 4) return launch_gadget_mb<L, 4, false>(m, p, smem);
+    return launch_gadget_mb<L, 3, false>(m, p, smem);
 }
-template <int L, int MB> int launch_gadget_mb(pgb_module *m, const GadgetArgs &p, size_t smem) {
+template <int L, int MB, bool AUT> int launch_gadget_mb(pgb_module *m, const GadgetArgs &p, size_t smem) {
     typedef GGeo<L> G;
     static int max_clusters_dev[32] = {};
     int &max_clusters = max_clusters_dev[m->device & 31];
@@ -663,14 +747,14 @@ template <int L, int MB> int launch_gadget_mb(pgb_module *m, const GadgetArgs &p
     cfg.dynamicSmemBytes = smem;
     cfg.stream = m->stream;
     if (!max_clusters) {
-        PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_gadget_kernel<L, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 << 10)));
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_gadget_kernel<L, MB, AUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 << 10)));
         const char *cv = getenv("PGB_GADGET_CARVEOUT");
-        PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_gadget_kernel<L, MB>, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : 100));
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_gadget_kernel<L, MB, AUT>, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : 100));
     }
     // resident clusters for this shared-memory footprint (depends on R through smem)
     cfg.gridDim = dim3(4 * 148);
     int nc = 0;
-    PGB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&nc, ntt120_gadget_kernel<L, MB>, &cfg));
+    PGB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&nc, ntt120_gadget_kernel<L, MB, AUT>, &cfg));
     if (nc < 1) {
         pgb_set_error("gadget kernel: no resident cluster fits (smem %zu)", smem);
         return PGB_ERR_UNSUPPORTED;
@@ -679,7 +763,7 @@ template <int L, int MB> int launch_gadget_mb(pgb_module *m, const GadgetArgs &p
     const int clusters = p.batch < nc ? p.batch : nc;
     cfg.gridDim = dim3(4 * clusters);
     { ProfScope _ps(m, PROF_GADGET);
-    PGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ntt120_gadget_kernel<L, MB>, p, (const uint2 *)m->ntt_fwd, (const uint2 *)m->ntt_inv,
+    PGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ntt120_gadget_kernel<L, MB, AUT>, p, (const uint2 *)m->ntt_fwd, (const uint2 *)m->ntt_inv,
                                       (const uint4 *)m->ntt_last16_f, (const uint4 *)m->ntt_last16_i));
     }
     return PGB_OK;
@@ -709,7 +793,7 @@ bool ntt120_gadget_supported(const pgb_module *m, int R, int cols_out, int S, in
 // `group_limit` = the reference's bound on the limbs of a digit group (dnum for the key-switch, none = 0 for the external product).
 int ntt120_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_cols, int row_cols, int row_col0, int R, const char *pmat,
                         int C, int cols_out, int small_size, char *res, uint64_t res_bs, int res_size, int base2k, int batch, int *ok_out,
-                        int dsize, int a_size, int key_rows, int group_limit) {
+                        int dsize, int a_size, int key_rows, int group_limit, int aut_mode, int64_t aut_p, int post_size) {
     const uint64_t n = m->n, poly_bytes = 16 * n;
     const int S = C / cols_out;
     if (dsize < 1) dsize = 1;
@@ -759,6 +843,17 @@ int ntt120_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_co
     p.in = in; p.in_bs = in_bs; p.res = res; p.res_bs = res_bs; p.ckey = (const uint32_t *)ck; p.key_bits = key_bits; p.ok = ok_out;
     p.in_cols = in_cols; p.row_cols = row_cols; p.row_col0 = row_col0; p.R = R; p.cols_out = cols_out; p.small_size = small_size;
     p.K = base2k; p.S = S; p.res_size = res_size; p.batch = batch;
+    p.aut_mode = aut_mode; p.post_size = post_size;
+    if (aut_mode) { // p^-1 mod 2n (p odd): Newton iterations double the number of correct low bits
+        const uint32_t pm = (uint32_t)(((aut_p % (int64_t)(2 * n)) + (int64_t)(2 * n)) % (int64_t)(2 * n));
+        if (!(pm & 1)) {
+            pgb_set_error("gadget kernel: automorphism index must be odd");
+            return PGB_ERR_SHAPE;
+        }
+        uint32_t x = pm;
+        for (int it = 0; it < 5; it++) x *= 2u - pm * x;
+        p.aut_pinv = x & (uint32_t)(2 * n - 1);
+    }
     u128 half = 0;
     for (int j = 0; j < S; j++) half += (u128)1 << (j * base2k + base2k - 1);
     p.half_lo = (unsigned long long)half;

@@ -166,3 +166,53 @@ def test_glwe_automorphism_op_family(fl):
                 for bi in range(batch):
                     o.glwe_automorphism_op(op, a[bi], res_k, a[bi], po, key_k, -1)
                 assert np.array_equal(g.vec_znx_to_numpy(a_g), a), ("assign", rank, res_k, key_k, op)
+
+
+@pytest.mark.parametrize("n", [1024, 4096])
+def test_automorphism_single_kernel_route(n):
+    """NTT120, log_n in 10..12, one base2k: key-switch + X -> X^p + (add | sub | sub_negate) of the input run as ONE launch of the gadget
+    kernel with the automorphism epilogue (ntt120_gadget.cu); the launch count proves the route, the oracle the bits.  Out of place, in
+    place (staged), dsize 2 (digit groups folded into the collapsed key) and a base2k whose integers leave the collapsed-key bound (every
+    ciphertext flagged on the device -> the limb-wise sequence redoes the batch from the untouched input)."""
+    g, o = pb.Module(n, pb.NTT120), O.OracleModule(n, pb.NTT120)
+    rng = np.random.default_rng(700 + n)
+    batch = 3
+    for rank, k, size, key_size, dsize, fused in ((1, 18, 3, 4, 1, True), (2, 18, 3, 4, 1, True), (1, 18, 4, 4, 2, True), (1, 30, 3, 3, 1, False)):
+        dnum = -(-size // dsize)
+        pg, po = _key(g, o, rng, dnum, rank, rank + 1, key_size, k)
+        for op, p in ((0, 5), (1, -1), (2, 2 * n - 3), (0, 2 * n - 1)):
+            a = fill_uniform(rng, (batch, size, rank + 1, n), k)
+            want = fill_uniform(rng, (batch, size, rank + 1, n), k)
+            res_g, a_g = g.vec_znx_from_numpy(want), g.vec_znx_from_numpy(a)
+            sc = g.glwe_automorphism_op(op, res_g, k, a_g, pg, k, p, dsize)
+            g.sync()
+            l0 = g.launch_count
+            g.glwe_automorphism_op(op, res_g, k, a_g, pg, k, p, dsize, sc)
+            g.sync()
+            launches = g.launch_count - l0
+            assert (launches <= 6) == fused, (rank, k, dsize, launches)
+            for bi in range(batch):
+                o.glwe_automorphism_op(op, want[bi], k, a[bi], po, k, p, dsize)
+            assert np.array_equal(g.vec_znx_to_numpy(res_g), want), (rank, k, dsize, op, p)
+            assert np.array_equal(g.vec_znx_to_numpy(a_g), a)
+            g.glwe_automorphism_op(op, a_g, k, a_g, pg, k, p, dsize, sc)  # in place
+            g.sync()
+            assert np.array_equal(g.vec_znx_to_numpy(a_g), want), ("assign", rank, k, dsize, op, p)
+
+
+def test_glwe_trace_single_kernel_rounds():
+    """Trace at n = 1024 in the NTT120 flavour: ten rounds of rsh + fused automorphism_add alternating between two buffers."""
+    n, batch, log_n, k = 1024, 2, 10, 18
+    g, o = pb.Module(n, pb.NTT120), O.OracleModule(n, pb.NTT120)
+    rng = np.random.default_rng(710)
+    for rank, skip in ((1, 0), (2, 3)):
+        keys = [_key(g, o, rng, 3, rank, rank + 1, 4, k) for _ in range(log_n)]
+        want = fill_uniform(rng, (batch, 3, rank + 1, n), k)
+        res_g = g.vec_znx_from_numpy(want)
+        l0 = g.launch_count
+        g.glwe_trace_assign(res_g, k, skip, [x[0] for x in keys], k, 1)
+        g.sync()
+        assert g.launch_count - l0 <= (log_n - skip) * (6 + rank + 1) + 2
+        for bi in range(batch):
+            o.glwe_trace_assign(want[bi], k, skip, [x[1] for x in keys], k, 1)
+        assert np.array_equal(g.vec_znx_to_numpy(res_g), want), (rank, skip)
