@@ -516,18 +516,23 @@ extern "C" int pgb_glwe_tensor_relinearize_batched(pgb_module *m, pgb_vec_znx *r
     return PGB_OK;
 }
 
-// Single-kernel route of the automorphism family in the NTT120 flavour (ntt120_gadget.cu, automorphism epilogue): key-switch, X -> X^p and
+// Single-kernel route of the automorphism family (ntt120_gadget.cu / fft64_gadget.cu, automorphism epilogue): key-switch, X -> X^p and
 // the addition / subtraction of the input in one launch per batch.  aut_mode 1..3 = op 0..2 of pgb_glwe_automorphism_op_batched, 4 = plain
 // glwe_automorphism.  Returns 1 when the batch was finished here, 0 when the caller must run the limb-wise sequence (unsupported geometry
 // or a ciphertext flagged by the collapsed-key bound), < 0 on error.  `ar` supplies the flag list and, when res overlaps a, the staging
 // buffer of the outputs (the epilogue gathers column 0 of a at permuted positions, so it cannot run in place).
 static int automorphism_fused(pgb_module *m, int aut_mode, pgb_vec_znx *res, uint64_t res_bs, const pgb_vec_znx *a, uint64_t a_bs,
                               const pgb_vmp_pmat *key, uint64_t base2k, int64_t p, uint64_t dsize, uint64_t B, Arena &ar) {
-    if (m->flavour != PGB_NTT120 || !ntt120_fused_supported(m) || getenv("PGB_NO_FUSION") || getenv("PGB_NO_AUT_FUSION")) return 0;
+    if (getenv("PGB_NO_FUSION") || getenv("PGB_NO_AUT_FUSION")) return 0;
     const uint64_t n = m->n, rank_in = key->cols_in, cols = key->cols_out;
     const uint64_t Rfull = rank_in * a->size, R = dsize == 1 ? umin64(key->rows * key->cols_in, Rfull) : Rfull;
-    if (!ntt120_gadget_supported(m, (int)R, (int)cols, (int)key->size, (int)base2k, (int)B)) return 0;
-    if (dsize > 1 && !gadget_likely_fits(n, R, key->size, base2k)) return 0;
+    const bool f64 = m->flavour == PGB_FFT64;
+    if (f64) {
+        if (dsize > 2 || R > 16 || !fft64_gadget_supported(m, (int)R, (int)cols, (int)key->size, (int)base2k, (int)B)) return 0;
+    } else {
+        if (!ntt120_fused_supported(m) || !ntt120_gadget_supported(m, (int)R, (int)cols, (int)key->size, (int)base2k, (int)B)) return 0;
+        if (dsize > 1 && !gadget_likely_fits(n, R, key->size, base2k)) return 0;
+    }
     const size_t mark = ar.used;
     int *ok = (int *)ar.take((2 * B + 1) * sizeof(int));
     const char *r0 = (const char *)res->data, *r1 = r0 + (B - 1) * res_bs + n * cols * res->size * 8;
@@ -544,6 +549,13 @@ static int automorphism_fused(pgb_module *m, int aut_mode, pgb_vec_znx *res, uin
         return 0;
     }
     const int small = (int)umin64(a->size, key->size);
+    if (f64) { // no bound to check in this flavour: the kernel restates the f64 pipeline itself
+        PGB_TRY(fft64_gadget_fused(m, (const char *)a->data, a_bs, (int)a->cols, (int)rank_in, 1, (int)R, (const char *)key->data,
+                                   (int)(cols * key->size), (int)cols, small, out, out_bs, (int)res->size, (int)base2k, (int)B, (int)dsize,
+                                   (int)a->size, (int)(key->rows * key->cols_in), (int)key->rows, aut_mode, p, aut_mode == 4 ? 0 : small));
+        if (aliased) PGB_CHECK_CUDA(cudaMemcpy2DAsync(res->data, res_bs, out, out_bs, out_bs, B, cudaMemcpyDeviceToDevice, m->stream));
+        return 1;
+    }
     PGB_TRY(ntt120_gadget_fused(m, (const char *)a->data, a_bs, (int)a->cols, (int)rank_in, 1, (int)R, (const char *)key->data,
                                 (int)(cols * key->size), (int)cols, small, out, out_bs, (int)res->size, (int)base2k, (int)B, ok, (int)dsize,
                                 (int)a->size, (int)(key->rows * key->cols_in), (int)key->rows, aut_mode, p, aut_mode == 4 ? 0 : small));

@@ -38,7 +38,34 @@ struct FGadgetArgs {
     // (dsize == 1: src_row = r, di = 0, jmax = S; dsize == 2: the digit groups of keyswitching/glwe.rs:332-379, see fft64_gadget_fused)
     signed char src_row[16], di[16], jmax[16];
     double inv_m;
+    // automorphism epilogue (AUT instances only): the coefficient at source position j goes to j * aut_p mod 2n (negated when that lands
+    // in [n, 2n)).  x = rounded product + body.  mode 1: res = normalize(aut(x) + a), 2: normalize(aut(x) - a), 3: normalize(a - aut(x)),
+    // a = the first post_size limbs of the INPUT ciphertext, every column (automorphism/glwe_ct.rs:95-275: big_automorphism,
+    // big_(add|sub)_small, big_normalize); mode 4: res = aut(normalize(x)) (glwe_automorphism, glwe_ct.rs:51-72)
+    int aut_mode, post_size;
+    uint32_t aut_p;
 };
+
+__device__ __forceinline__ long long norm_step(long long x, long long &c, int K);
+// one coefficient of the automorphism epilogue: v = rounded product (+ body already added) at source position js of limb j, column c
+__device__ __forceinline__ void aut_emit(const FGadgetArgs &p, long long v, long long &carry, int K, int N, int js, const long long *post_limb,
+                                         long long *out_limb, bool store) {
+    const uint32_t e = ((uint32_t)js * p.aut_p) & (uint32_t)(2 * N - 1);
+    const int jo = (int)(e & (uint32_t)(N - 1));
+    const bool flip = e >= (uint32_t)N;
+    const int mode = p.aut_mode;
+    unsigned long long x = (unsigned long long)v;
+    if (mode != 4) {
+        if ((mode == 3) != flip) x = 0ull - x;
+        if (post_limb) {
+            const unsigned long long a = (unsigned long long)__ldg(post_limb + jo);
+            x = mode == 2 ? x - a : x + a;
+        }
+    }
+    long long o = norm_step((long long)x, carry, K);
+    if (mode == 4 && flip) o = (long long)(0ull - (unsigned long long)o);
+    if (store) out_limb[jo] = o;
+}
 
 template <int T> __device__ __forceinline__ void slot_sync(int slot) {
     if (T <= 32) __syncwarp();
@@ -102,7 +129,7 @@ __device__ __forceinline__ long long norm_step(long long x, long long &c, int K)
     return out;
 }
 
-template <int LM, int LPR, bool TWS> __global__ void __launch_bounds__(512, 1)
+template <int LM, int LPR, bool TWS, bool AUT> __global__ void __launch_bounds__(512, 1)
 fft64_gadget_kernel(const __grid_constant__ FGadgetArgs p, const double2 *__restrict__ twf_g, const double2 *__restrict__ twi_g) {
     typedef FGeo<LM> G;
     constexpr int M = 1 << LM, N = 2 * M, T = G::T, PL = G::PLANE;
@@ -219,10 +246,17 @@ fft64_gadget_kernel(const __grid_constant__ FGadgetArgs p, const double2 *__rest
                             v0 = (long long)((unsigned long long)v0 + (unsigned long long)__ldg(sp + jj * T));
                             v1 = (long long)((unsigned long long)v1 + (unsigned long long)__ldg(sp + jj * T + M));
                         }
+                        if constexpr (AUT) {
+                            const long long *post = j < p.post_size ? in + (size_t)j * in_ls + (size_t)c * N : nullptr;
+                            long long *ol = res + (size_t)j * res_ls + (size_t)c * N;
+                            aut_emit(p, v0, carry[2 * jj], K, N, t + jj * T, post, ol, j < a_start);
+                            aut_emit(p, v1, carry[2 * jj + 1], K, N, t + jj * T + M, post, ol, j < a_start);
+                        } else {
                         const long long o0 = norm_step(v0, carry[2 * jj], K), o1 = norm_step(v1, carry[2 * jj + 1], K);
                         if (j < a_start) {
                             op[jj * T] = o0;
                             op[jj * T + M] = o1;
+                        }
                         }
                     }
                 }
@@ -249,8 +283,13 @@ fft64_gadget_kernel(const __grid_constant__ FGadgetArgs p, const double2 *__rest
                     for (int i = 0; i < CPT; i++) {
                         long long v = big[gt + i * GT];
                         if (with_small) v = (long long)((unsigned long long)v + (unsigned long long)__ldg(sp + i * GT));
+                        if constexpr (AUT) {
+                            const long long *post = j2 < p.post_size ? in + (size_t)j2 * in_ls + (size_t)c * N : nullptr;
+                            aut_emit(p, v, carry[i], K, N, gt + i * GT, post, res + (size_t)j2 * res_ls + (size_t)c * N, j2 < a_start);
+                        } else {
                         const long long o = norm_step(v, carry[i], K);
                         if (j2 < a_start) op[i * GT] = o;
+                        }
                     }
                 }
                 group_sync(8 + c, GT); // the planes are rewritten by the next round
@@ -290,20 +329,23 @@ __global__ void __launch_bounds__(256) fft64_gadget_key_kernel(const double *__r
     out[poly * (size_t)M + (size_t)blockIdx.z * (M / 2) + i] = make_double2(src[0], src[1]);
     (void)polys;
 }
-template <int LM, int LPR, bool TWS> int launch(pgb_module *m, const FGadgetArgs &p, size_t smem) {
+template <int LM, int LPR, bool TWS, bool AUT> int launch_a(pgb_module *m, const FGadgetArgs &p, size_t smem) {
     static int sms_dev[32] = {};
     int &sms = sms_dev[m->device & 31];
     if (!sms) {
-        PGB_CHECK_CUDA(cudaFuncSetAttribute(fft64_gadget_kernel<LM, LPR, TWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 << 10)));
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(fft64_gadget_kernel<LM, LPR, TWS, AUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 << 10)));
         PGB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device));
     }
     const int threads = p.cols_out * LPR * FGeo<LM>::T;
     const int grid = p.batch < sms ? p.batch : sms;
     { ProfScope _ps(m, PROF_GADGET);
-    fft64_gadget_kernel<LM, LPR, TWS><<<grid, threads, smem, m->stream>>>(p, m->fft_fwd, m->fft_inv);
+    fft64_gadget_kernel<LM, LPR, TWS, AUT><<<grid, threads, smem, m->stream>>>(p, m->fft_fwd, m->fft_inv);
     }
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;
+}
+template <int LM, int LPR, bool TWS> int launch(pgb_module *m, const FGadgetArgs &p, size_t smem) {
+    return p.aut_mode ? launch_a<LM, LPR, TWS, true>(m, p, smem) : launch_a<LM, LPR, TWS, false>(m, p, smem);
 }
 template <int LM> int launch_lm(pgb_module *m, const FGadgetArgs &p, int lpr, bool tws, size_t smem) {
     if (tws) {
@@ -354,9 +396,19 @@ bool fft64_gadget_supported(const pgb_module *m, int R, int cols_out, int S, int
 // ntt120_gadget_fused.  (dsize >= 3 is not offered: there the reference's FFT64 vmp leaves stale limbs in its temporary, fft64/vmp.rs:263.)
 int fft64_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_cols, int row_cols, int row_col0, int R, const char *pmat, int C,
                        int cols_out, int small_size, char *res, uint64_t res_bs, int res_size, int base2k, int batch, int dsize, int a_size,
-                       int key_rows, int group_limit) {
+                       int key_rows, int group_limit, int aut_mode, int64_t aut_p, int post_size) {
     FGadgetArgs p;
     memset(&p, 0, sizeof p);
+    p.aut_mode = aut_mode;
+    p.post_size = post_size;
+    if (aut_mode) {
+        const int64_t two_n = 2 * (int64_t)m->n;
+        p.aut_p = (uint32_t)(((aut_p % two_n) + two_n) % two_n);
+        if (!(p.aut_p & 1)) {
+            pgb_set_error("fft64 gadget kernel: automorphism index must be odd");
+            return PGB_ERR_SHAPE;
+        }
+    }
     if (dsize < 1) dsize = 1;
     if (dsize == 1) key_rows = R;
     if (R > 16) {

@@ -34,7 +34,7 @@ int ntt120_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_co
 bool fft64_gadget_supported(const pgb_module *m, int R, int cols_out, int S, int base2k, int batch);
 int fft64_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_cols, int row_cols, int row_col0, int R, const char *pmat, int C,
                        int cols_out, int small_size, char *res, uint64_t res_bs, int res_size, int base2k, int batch, int dsize = 1, int a_size = 0,
-                       int key_rows = 0, int group_limit = 0);
+                       int key_rows = 0, int group_limit = 0, int aut_mode = 0, int64_t aut_p = 0, int post_size = 0);
 // ntt120_ops.cu
 int ntt120_vmp(pgb_module *m, const char *a, uint64_t a_bs, char *res, uint64_t res_bs, const char *pm, uint64_t pm_bs,
                uint32_t row_max, uint32_t C, uint32_t col0, uint32_t ncols_out, uint32_t batch);
