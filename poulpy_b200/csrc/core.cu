@@ -319,6 +319,9 @@ extern "C" int pgb_glwe_external_product_batched(pgb_module *m, pgb_vec_znx *res
         PGB_CHECK_CUDA(cudaMemsetAsync(res_dft.data, 0, B * res_dft_bs, m->stream)); // res_dft.zero() (:123)
         pgb_vec_znx_dft tmp = mk(ar.take(B * res_dft_bs), n, cols, ggsw->size);
         PGB_REQUIRE(tmp.data, "glwe_external_product: scratch exhausted");
+        // the temporary starts zeroed (a fresh allocation in the oracle's model of the scratch arena): with dsize > 1 the FFT64 vmp leaves
+        // limbs past the shifted key untouched, so the result must not depend on what a reused scratch held before
+        PGB_CHECK_CUDA(cudaMemsetAsync(tmp.data, 0, B * res_dft_bs, m->stream));
         // a_dft.data_mut().fill(0) (:226): FFT64 dft_apply leaves limbs past a.size untouched inside min_steps
         PGB_CHECK_CUDA(cudaMemsetAsync(a_dft.data, 0, B * a_dft_bs, m->stream));
         for (uint64_t di = 0; di < dsize; di++) {

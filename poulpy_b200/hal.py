@@ -220,6 +220,15 @@ class Module:
     def _buf(self, nbytes):
         return DevBuf(nbytes, managed=self.managed)
 
+    def _scratch(self, need):
+        """Grow-only scratch owned by the module, handed to every call that was not given one: the calls of one module are ordered on
+        its stream, so consecutive operations can share it (a fresh cudaMalloc + clear per call costs more than most operations)."""
+        c = getattr(self, "_scratch_cache", None)
+        if c is None or c.nbytes < need:
+            self._scratch_cache = c = None  # cudaFree of the old block synchronises the device
+            self._scratch_cache = c = DevBuf(max(int(need), 1 << 20))
+        return c
+
     def vec_znx_alloc(self, cols, size, batch=1):
         stride = self.n * cols * size * 8
         return VecZnx(self._buf(stride * batch), self.n, cols, size, batch=batch, batch_stride=stride)
@@ -403,7 +412,7 @@ class Module:
         r, av, ps = res.struct(), a.struct(), pmat.struct()
         need = lib().pgb_vmp_apply_dft_tmp_bytes(self._h, _u64(res.size), _u64(a.size), _u64(pmat.rows), _u64(pmat.cols_in),
                                                  _u64(pmat.cols_out), _u64(pmat.size))
-        scratch = DevBuf(need)
+        scratch = self._scratch(need)
         _check(lib().pgb_vmp_apply_dft(self._h, C.byref(r), C.byref(av), C.byref(ps), C.c_void_p(scratch.ptr), C.c_size_t(need)))
 
     # --- vec_znx_big (poulpy-hal/src/api/vec_znx_big.rs) ---------------------------------------------------------------------
@@ -454,7 +463,7 @@ class Module:
         need = lib().pgb_glwe_keyswitch_tmp_bytes(self._h, _u64(res.size), _u64(a.size), _u64(a_base2k), C.byref(ks), _u64(key_base2k),
                                                   _u64(dsize), _u64(res.batch))
         if scratch is None or scratch.nbytes < need:
-            scratch = DevBuf(need)
+            scratch = self._scratch(need)
         r, av = res.struct(), a.struct()
         bt = _BT(res.batch, res.batch_stride, a.batch_stride, 0)
         _check(lib().pgb_glwe_keyswitch_batched(self._h, C.byref(r), _u64(res_base2k), C.byref(av), _u64(a_base2k), C.byref(ks),
@@ -466,7 +475,7 @@ class Module:
         need = lib().pgb_glwe_external_product_tmp_bytes(self._h, _u64(res.size), _u64(a.size), _u64(a_base2k), C.byref(ks),
                                                          _u64(ggsw_base2k), _u64(dsize), _u64(res.batch))
         if scratch is None or scratch.nbytes < need:
-            scratch = DevBuf(need)
+            scratch = self._scratch(need)
         r, av = res.struct(), a.struct()
         bt = _BT(res.batch, res.batch_stride, a.batch_stride, 0)
         _check(lib().pgb_glwe_external_product_batched(self._h, C.byref(r), _u64(res_base2k), C.byref(av), _u64(a_base2k), C.byref(ks),
@@ -542,7 +551,7 @@ class Module:
         need = lib().pgb_glwe_tensor_apply_tmp_bytes(self._h, _u64(a.cols - 1), _u64(res.size), _u64(res_base2k), _u64(a.size), _u64(b.size),
                                                      _u64(ab_base2k), _u64(cnv_offset), _u64(res.batch))
         if scratch is None or scratch.nbytes < need:
-            scratch = DevBuf(need)
+            scratch = self._scratch(need)
         r, av, bv = res.struct(), a.struct(), b.struct()
         bt = _BT(res.batch, res.batch_stride, a.batch_stride if a.batch > 1 else 0, b.batch_stride if b.batch > 1 else 0)
         _check(lib().pgb_glwe_tensor_apply_batched(self._h, _u64(cnv_offset), C.byref(r), _u64(res_base2k), C.byref(av), _u64(a_effective_k),
@@ -555,7 +564,7 @@ class Module:
         need = lib().pgb_glwe_tensor_relinearize_tmp_bytes(self._h, _u64(res.size), _u64(a.size), _u64(a_base2k), C.byref(ks), _u64(key_base2k),
                                                            _u64(dsize), _u64(res.batch))
         if scratch is None or scratch.nbytes < need:
-            scratch = DevBuf(need)
+            scratch = self._scratch(need)
         r, av = res.struct(), a.struct()
         bt = _BT(res.batch, res.batch_stride, a.batch_stride if a.batch > 1 else 0, 0)
         _check(lib().pgb_glwe_tensor_relinearize_batched(self._h, C.byref(r), _u64(res_base2k), C.byref(av), _u64(a_base2k), C.byref(ks),
@@ -572,7 +581,7 @@ class Module:
         need = lib().pgb_glwe_automorphism_tmp_bytes(self._h, _u64(res.size), _u64(a.size), _u64(a_base2k), C.byref(ks), _u64(key_base2k),
                                                      _u64(dsize), _u64(res.batch))
         if scratch is None or scratch.nbytes < need:
-            scratch = DevBuf(need)
+            scratch = self._scratch(need)
         r, av = res.struct(), a.struct()
         bt = _BT(res.batch, res.batch_stride, a.batch_stride if a.batch > 1 else 0, 0)
         _check(lib().pgb_glwe_automorphism_batched(self._h, C.byref(r), _u64(res_base2k), C.byref(av), _u64(a_base2k), C.byref(ks),
@@ -602,7 +611,7 @@ class Module:
         need = lib().pgb_glwe_automorphism_add_assign_tmp_bytes(self._h, _u64(res.size), _u64(res_base2k), C.byref(ks), _u64(key_base2k),
                                                                 _u64(dsize), _u64(res.batch))
         if scratch is None or scratch.nbytes < need:
-            scratch = DevBuf(need)
+            scratch = self._scratch(need)
         r = res.struct()
         bt = _BT(res.batch, res.batch_stride, 0, 0)
         _check(lib().pgb_glwe_automorphism_add_assign_batched(self._h, C.byref(r), _u64(res_base2k), C.byref(ks), _u64(key_base2k), C.c_int64(p),
@@ -615,7 +624,7 @@ class Module:
         need = lib().pgb_glwe_automorphism_add_assign_tmp_bytes(self._h, _u64(res.size), _u64(res_base2k), C.byref(ks), _u64(key_base2k),
                                                                 _u64(dsize), _u64(res.batch))
         if scratch is None or scratch.nbytes < need:
-            scratch = DevBuf(need)
+            scratch = self._scratch(need)
         r, av = res.struct(), a.struct()
         bt = _BT(res.batch, res.batch_stride, a.batch_stride, 0)
         _check(lib().pgb_glwe_automorphism_op_batched(self._h, C.c_int(op), C.byref(r), _u64(res_base2k), C.byref(av), C.byref(ks),
@@ -632,7 +641,7 @@ class Module:
         need = lib().pgb_glwe_trace_assign_tmp_bytes(self._h, _u64(res.size), _u64(res_base2k), C.byref(arr[min(skip, len(keys) - 1)]),
                                                      _u64(key_base2k), _u64(dsize), _u64(res.batch))
         if scratch is None or scratch.nbytes < need:
-            scratch = DevBuf(need)
+            scratch = self._scratch(need)
         r = res.struct()
         bt = _BT(res.batch, res.batch_stride, 0, 0)
         _check(lib().pgb_glwe_trace_assign_batched(self._h, C.byref(r), _u64(res_base2k), _u64(skip), arr, _u64(len(keys)), _u64(key_base2k),
@@ -646,7 +655,7 @@ class Module:
         need = lib().pgb_ggsw_expand_row_tmp_bytes(self._h, _u64(rank), _u64(size), _u64(res_base2k), C.byref(arr[0]), _u64(tsk_base2k),
                                                    _u64(dsize), _u64(batch))
         if scratch is None or scratch.nbytes < need:
-            scratch = DevBuf(need)
+            scratch = self._scratch(need)
         g = _PM(ggsw_buf.ptr, self.n, size, dnum, rank + 1, rank + 1)
         stride = self.n * dnum * (rank + 1) * (rank + 1) * size * 8
         bt = _BT(batch, stride, 0, 0)
@@ -666,7 +675,7 @@ class Module:
         need = lib().pgb_cggi_blind_rotate_tmp_bytes(self._h, _u64(res.cols - 1), _u64(res.size), _u64(brk.rows), _u64(brk.size),
                                                      _u64(res.batch))
         if scratch is None or scratch.nbytes < need:
-            scratch = DevBuf(need)
+            scratch = self._scratch(need)
         r, lv, bs, xp = res.struct(), lut.struct(), brk.struct(), x_pow_a.struct()
         bt = _BT(res.batch, res.batch_stride, 0, 0)
         _check(lib().pgb_cggi_blind_rotate_batched(self._h, C.byref(r), C.c_void_p(lwe_2n.ptr), _u64(n_lwe), C.byref(lv), C.byref(bs),
@@ -682,7 +691,7 @@ class Module:
         need = lib().pgb_cggi_blind_rotate_extended_tmp_bytes(self._h, _u64(res.cols - 1), _u64(res.size), _u64(brk.rows), _u64(brk.size),
                                                               _u64(ext), _u64(res.batch))
         if scratch is None or scratch.nbytes < need:
-            scratch = DevBuf(need)
+            scratch = self._scratch(need)
         r, lv, bs, xp = res.struct(), luts.struct(), brk.struct(), x_pow_a.struct()
         bt = _BT(res.batch, res.batch_stride, 0, 0)
         _check(lib().pgb_cggi_blind_rotate_extended_batched(self._h, C.byref(r), C.c_void_p(lwe_2n.ptr), _u64(n_lwe), C.byref(lv), _u64(ext),
@@ -706,7 +715,7 @@ class Module:
         need = lib().pgb_cggi_blind_rotate_standard_tmp_bytes(self._h, _u64(res.cols - 1), _u64(res.size), _u64(res_base2k), C.byref(bs),
                                                               _u64(brk_base2k), _u64(res.batch))
         if scratch is None or scratch.nbytes < need:
-            scratch = DevBuf(need)
+            scratch = self._scratch(need)
         r, lv = res.struct(), lut.struct()
         bt = _BT(res.batch, res.batch_stride, 0, 0)
         _check(lib().pgb_cggi_blind_rotate_standard_batched(self._h, C.byref(r), _u64(res_base2k), C.c_void_p(lwe_2n.ptr), _u64(n_lwe),
