@@ -101,6 +101,9 @@ int pgb_memcpy_h2d(void *dst, const void *src, size_t len);
 int pgb_memcpy_d2h(void *dst, const void *src, size_t len);
 int pgb_memcpy_d2d(void *dst, const void *src, size_t len);
 int pgb_memset(void *dst, int byte, size_t len);
+/* zero fill of a block a host-side pool hands out again (device-wide synchronisation on both sides) */
+int pgb_recycle_device_bytes(void *p, size_t len);
+int pgb_current_device(void); /* the device pgb_alloc_device_bytes allocates on (-1 on error) */
 
 /* Backend::bytes_of_* (layouts/module.rs:44-70) */
 size_t pgb_size_of_scalar_prep(const pgb_module *m);

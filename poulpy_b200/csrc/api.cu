@@ -215,6 +215,18 @@ extern "C" int pgb_memset(void *dst, int byte, size_t len) {
     PGB_CHECK_CUDA(cudaMemset(dst, byte, len));
     return PGB_OK;
 }
+// Zero fill of a block that is being recycled by a host-side pool: ordered against every module stream on both sides (work that still
+// uses the block's previous life finishes first; nothing launched afterwards can overtake the fill).
+extern "C" int pgb_current_device(void) {
+    int d = -1;
+    return cudaGetDevice(&d) == cudaSuccess ? d : -1;
+}
+extern "C" int pgb_recycle_device_bytes(void *p, size_t len) {
+    PGB_CHECK_CUDA(cudaDeviceSynchronize());
+    PGB_CHECK_CUDA(cudaMemset(p, 0, len));
+    PGB_CHECK_CUDA(cudaStreamSynchronize(0));
+    return PGB_OK;
+}
 
 extern "C" size_t pgb_size_of_scalar_prep(const pgb_module *m) { return prep_bytes(m); }
 extern "C" size_t pgb_size_of_scalar_big(const pgb_module *m) { return big_bytes(m); }

@@ -62,6 +62,7 @@ def lib():
         for name in ("pgb_memcpy_h2d", "pgb_memcpy_d2h", "pgb_memcpy_d2d"):
             getattr(_lib, name).argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         _lib.pgb_memset.argtypes = [C.c_void_p, C.c_int, C.c_size_t]
+        _lib.pgb_recycle_device_bytes.argtypes = [C.c_void_p, C.c_size_t]
         _lib.pgb_module_new.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         _lib.pgb_module_destroy.argtypes = [C.c_void_p]
         _lib.pgb_module_launch_count.restype = C.c_uint64
@@ -90,21 +91,42 @@ def _u64(x):
     return C.c_uint64(int(x))
 
 
+_POOL = {}          # (device, nbytes) -> [device pointers] of released DevBufs (cudaMalloc / cudaFree cost milliseconds once GBs are mapped)
+_POOL_BYTES = [0]
+_POOL_CAP = 8 << 30
+
+
 class DevBuf:
-    """A device (or managed) allocation owned by Python."""
+    """A device (or managed) allocation owned by Python, zero-filled.  Released device blocks go to a size-keyed pool and are handed out
+    again after a device-wide synchronisation and a zero fill (pgb_recycle_device_bytes), so loops that allocate their temporaries per
+    call do not pay cudaMalloc / cudaFree."""
 
     def __init__(self, nbytes, managed=False):
         self.nbytes = int(nbytes)
         self.managed = managed
+        self._key = None if managed else (lib().pgb_current_device(), self.nbytes)
+        free = None if managed else _POOL.get(self._key)
+        if free:
+            self.ptr = free.pop()
+            _POOL_BYTES[0] -= self.nbytes
+            _check(lib().pgb_recycle_device_bytes(C.c_void_p(self.ptr), C.c_size_t(self.nbytes)))
+            return
         f = lib().pgb_alloc_bytes if managed else lib().pgb_alloc_device_bytes
         self.ptr = f(self.nbytes)
+        if not self.ptr and _POOL_BYTES[0]:  # out of memory with blocks parked in the pool: release them and retry
+            pool_trim()
+            self.ptr = f(self.nbytes)
         if not self.ptr:
             raise PoulpyError(f"device allocation of {nbytes} bytes failed")
 
     def __del__(self):
         try:
             if getattr(self, "ptr", None):
-                lib().pgb_free(self.ptr)
+                if not self.managed and self.nbytes >= (1 << 12) and _POOL_BYTES[0] + self.nbytes <= _POOL_CAP:
+                    _POOL.setdefault(self._key, []).append(self.ptr)
+                    _POOL_BYTES[0] += self.nbytes
+                else:
+                    lib().pgb_free(self.ptr)
                 self.ptr = None
         except Exception:
             pass
@@ -722,6 +744,15 @@ class Module:
                                                             C.byref(lv), C.byref(bs), _u64(brk_base2k), C.byref(bt),
                                                             C.c_void_p(scratch.ptr), C.c_size_t(scratch.nbytes)))
         return scratch
+
+
+def pool_trim():
+    """cudaFree every block parked in the DevBuf pool."""
+    for blocks in _POOL.values():
+        while blocks:
+            lib().pgb_free(blocks.pop())
+    _POOL.clear()
+    _POOL_BYTES[0] = 0
 
 
 def pinned_empty(shape, dtype=np.int64):
