@@ -617,11 +617,12 @@ def aux_measurements(pb, torch, local, peak):
             del m, keys, a, r, sc
     except Exception as e:
         aux["glwe_trace_per_s"] = {"error": repr(e)}
+    pb.hal.pool_trim()  # blocks parked by the sections above are of no use below
     # circuit bootstrapping, constant mode (poulpy-bench circuit_bootstrapping.rs:47-129 "1-bit"): n=1024, n_lwe=574, block 7, rank 2,
     # base2k 13, BRK/ATK/TSK k=52 dnum=3, result GGSW k=26 dnum=2; synthetic keys; batch of LWEs per call
     try:
         from poulpy_b200 import circuit
-        n, log_n, n_lwe, block, rank, K, B = 1024, 10, 574, 7, 2, 13, 128
+        n, log_n, n_lwe, block, rank, K, B = 1024, 10, 574, 7, 2, 13, 512
         cols, ksz, kd, res_size, dnum_res = rank + 1, 4, 3, 2, 2
         m = pb.Module(n, pb.FFT64, device=local)
         m.set_stream(stream.cuda_stream)

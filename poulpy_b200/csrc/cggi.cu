@@ -197,6 +197,65 @@ __global__ void __launch_bounds__(256) cggi_xai_fft64_kernel(XaiArgs p) {
     a[i + m] = (a[i + m] + pi) - vi;
 }
 
+// FFT64 counterpart of cggi_block_ntt120_kernel for the shapes the fully fused kernel (cggi_fused.cu) does not take: the key products of
+// one block and their X^{a_t} - 1 updates in one launch, acc_add written once.  Per frequency the operations and their order are those
+// of fft64_vmp_kernel followed by cggi_xai_fft64_kernel (v = sum_r a_r k_r in row order; acc = (acc + w v) - v, acc starting at 0), so
+// the result is the limb-wise sequence's bit for bit; what disappears is vmp_res / acc_add crossing HBM 2 x block_size times.
+// Thread: two consecutive complex frequencies (double2 of re, double2 of im) x CT output polys; grid (m2 / 128, C / CT, batch).
+template <int CT> __global__ void __launch_bounds__(128) cggi_block_fft64_kernel(BlockArgs p) {
+    const uint32_t m2 = p.n / 4; // double2 words per half poly
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= m2) return;
+    const uint32_t b = blockIdx.z, c0 = blockIdx.y * CT;
+    const size_t poly_words = (size_t)2 * m2;
+    const int nc = min((uint32_t)CT, p.C - c0);
+    const double2 *a = reinterpret_cast<const double2 *>(p.acc_dft + (size_t)b * p.acc_bs) + u;
+    double2 sr[CT], si[CT];
+#pragma unroll
+    for (int c = 0; c < CT; c++) sr[c] = si[c] = make_double2(0.0, 0.0);
+    for (uint32_t t = 0; t < p.bs; t++) {
+        const long long ai = p.lwe[(size_t)b * p.lwe_stride + t];
+        const uint32_t pos = (uint32_t)((ai + (long long)(2 * p.n)) & (long long)(2 * p.n - 1));
+        const double2 *w = reinterpret_cast<const double2 *>(p.xpa + (size_t)pos * p.n * 8) + u;
+        const double2 wr = __ldg(w), wi = __ldg(w + m2);
+        const double2 *pm = reinterpret_cast<const double2 *>(p.brk + (size_t)t * p.brk_bytes) + u + (size_t)c0 * poly_words;
+        double2 vr[CT], vi[CT];
+#pragma unroll
+        for (int c = 0; c < CT; c++) vr[c] = vi[c] = make_double2(0.0, 0.0);
+        for (uint32_t r = 0; r < p.R; r++) {
+            const double2 ar = __ldg(a + (size_t)r * poly_words), ai2 = __ldg(a + (size_t)r * poly_words + m2);
+            const double2 *mrow = pm + (size_t)r * p.C * poly_words;
+#pragma unroll
+            for (int c = 0; c < CT; c++) {
+                if (c < nc) {
+                    const double2 br = __ldg(mrow + (size_t)c * poly_words), bi = __ldg(mrow + (size_t)c * poly_words + m2);
+                    vr[c].x += ar.x * br.x - ai2.x * bi.x;
+                    vr[c].y += ar.y * br.y - ai2.y * bi.y;
+                    vi[c].x += ar.x * bi.x + ai2.x * br.x;
+                    vi[c].y += ar.y * bi.y + ai2.y * br.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CT; c++) {
+            const double prx = wr.x * vr[c].x - wi.x * vi[c].x, pix = wr.x * vi[c].x + wi.x * vr[c].x; // reim_mul(ppol, v)
+            const double pry = wr.y * vr[c].y - wi.y * vi[c].y, piy = wr.y * vi[c].y + wi.y * vr[c].y;
+            sr[c].x = (sr[c].x + prx) - vr[c].x;
+            sr[c].y = (sr[c].y + pry) - vr[c].y;
+            si[c].x = (si[c].x + pix) - vi[c].x;
+            si[c].y = (si[c].y + piy) - vi[c].y;
+        }
+    }
+    double2 *res = reinterpret_cast<double2 *>(p.acc_add + (size_t)b * p.add_bs) + u + (size_t)c0 * poly_words;
+#pragma unroll
+    for (int c = 0; c < CT; c++) {
+        if (c < nc) {
+            res[(size_t)c * poly_words] = sr[c];
+            res[(size_t)c * poly_words + m2] = si[c];
+        }
+    }
+}
+
 // ---- extended blind rotation (algorithm.rs:121-273): the accumulator is `ext` interleaved rings; items are (ciphertext b, ring i) at
 // index b * ext + i.  Which source ring and which X^a table entry a ring takes depends on the ciphertext's own a_t (and is decided per
 // item on the device); the reference's skip conditions are kept verbatim (see the oracle's note on a_hi = 0 / 2n - 1).
@@ -356,6 +415,15 @@ int cggi_blind_rotate_impl(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2
             else if (cols * dnum <= 8) BLOCK_LAUNCH(8, 2)
             else BLOCK_LAUNCH(16, 1)
             #undef BLOCK_LAUNCH
+            PGB_CHECK_CUDA(cudaGetLastError());
+        } else if (m->flavour == PGB_FFT64 && n >= 8 && !getenv("PGB_NO_FUSION")) {
+            BlockArgs ba = {(const char *)acc_dft.data, acc_bs, (char *)acc_add.data, vres_bs, (const char *)brk->data + blk * brk_bytes, brk_bytes,
+                            (const char *)x_pow_a->data, (const long long *)lwe_2n + 1 + blk, lwe_stride, (uint32_t)n, (uint32_t)(cols * dnum),
+                            (uint32_t)(cols * bsize), (uint32_t)block_size};
+            ProfScope _ps(m, PROF_VMP);
+            constexpr int CT = 4;
+            const dim3 grid(((uint32_t)(n / 4) + 127) / 128, (uint32_t)((cols * bsize + CT - 1) / CT), (uint32_t)B);
+            cggi_block_fft64_kernel<CT><<<grid, 128, 0, m->stream>>>(ba);
             PGB_CHECK_CUDA(cudaGetLastError());
         } else {
         PGB_CHECK_CUDA(cudaMemsetAsync(acc_add.data, 0, B * vres_bs, m->stream)); // vec_znx_dft_zero on every column

@@ -122,7 +122,9 @@ class DevBuf:
     def __del__(self):
         try:
             if getattr(self, "ptr", None):
-                if not self.managed and self.nbytes >= (1 << 12) and _POOL_BYTES[0] + self.nbytes <= _POOL_CAP:
+                if not self.managed and (1 << 12) <= self.nbytes <= _POOL_CAP:
+                    if _POOL_BYTES[0] + self.nbytes > _POOL_CAP:
+                        pool_trim()  # parked blocks of sizes nobody asks for any more: release them all, then park this one
                     _POOL.setdefault(self._key, []).append(self.ptr)
                     _POOL_BYTES[0] += self.nbytes
                 else:

@@ -18,6 +18,9 @@ a = m.vec_znx_from_numpy(rng.integers(-(1 << 17), 1 << 17, size=(B, 3, 2, n), dt
 r = m.vec_znx_alloc(2, 3, B)
 sc = None
 for _ in range(4):
-    sc = m.glwe_keyswitch(r, k, a, k, pm, k, 1, sc)
+    if os.environ.get("KS_OP") == "aut":  # the automorphism epilogue: res = normalize(aut_5(ks(a)) + a)
+        sc = m.glwe_automorphism_op(0, r, k, a, pm, k, 5, 1, sc)
+    else:
+        sc = m.glwe_keyswitch(r, k, a, k, pm, k, 1, sc)
 m.sync()
 print("done")
