@@ -256,6 +256,95 @@ template <int CT> __global__ void __launch_bounds__(128) cggi_block_fft64_kernel
     }
 }
 
+// BT ciphertexts per thread: a key word loaded from L2 serves all of them, and the block's inputs a[bi][r] are staged once in
+// thread-private shared-memory slots instead of being re-read for every LWE coefficient of the block (the one-ciphertext version moves
+// 6.2 MB of key words + 1.5 MB of inputs per ciphertext and block through L2 at the circuit-bootstrapping shape: its limiter).
+// Same operations and order per (ciphertext, frequency, output poly) as cggi_block_fft64_kernel.
+template <int CT, int BT> __global__ void __launch_bounds__(128) cggi_block_fft64_bt_kernel(BlockArgs p, uint32_t B) {
+    extern __shared__ __align__(16) double2 a_s[]; // [BT][R][re | im][128]
+    const uint32_t m2 = p.n / 4;
+    const uint32_t tid = threadIdx.x, u = blockIdx.x * blockDim.x + tid;
+    if (u >= m2) return; // no block-wide synchronisation below: every shared-memory slot belongs to one thread
+    const uint32_t b0 = blockIdx.z * BT, c0 = blockIdx.y * CT;
+    const int nb = min((uint32_t)BT, B - b0), nc = min((uint32_t)CT, p.C - c0);
+    const size_t poly_words = (size_t)2 * m2;
+#pragma unroll
+    for (int bi = 0; bi < BT; bi++) {
+        const double2 *a = reinterpret_cast<const double2 *>(p.acc_dft + (size_t)(b0 + (bi < nb ? bi : 0)) * p.acc_bs) + u;
+        for (uint32_t r = 0; r < p.R; r++) {
+            a_s[((bi * p.R + r) * 2 + 0) * 128 + tid] = __ldg(a + (size_t)r * poly_words);
+            a_s[((bi * p.R + r) * 2 + 1) * 128 + tid] = __ldg(a + (size_t)r * poly_words + m2);
+        }
+    }
+    double2 sr[BT][CT], si[BT][CT];
+#pragma unroll
+    for (int bi = 0; bi < BT; bi++)
+#pragma unroll
+        for (int c = 0; c < CT; c++) sr[bi][c] = si[bi][c] = make_double2(0.0, 0.0);
+    for (uint32_t t = 0; t < p.bs; t++) {
+        double2 wr[BT], wi[BT];
+#pragma unroll
+        for (int bi = 0; bi < BT; bi++) {
+            const long long ai = p.lwe[(size_t)(b0 + (bi < nb ? bi : 0)) * p.lwe_stride + t];
+            const uint32_t pos = (uint32_t)((ai + (long long)(2 * p.n)) & (long long)(2 * p.n - 1));
+            const double2 *w = reinterpret_cast<const double2 *>(p.xpa + (size_t)pos * p.n * 8) + u;
+            wr[bi] = __ldg(w);
+            wi[bi] = __ldg(w + m2);
+        }
+        const double2 *pm = reinterpret_cast<const double2 *>(p.brk + (size_t)t * p.brk_bytes) + u + (size_t)c0 * poly_words;
+        double2 vr[BT][CT], vi[BT][CT];
+#pragma unroll
+        for (int bi = 0; bi < BT; bi++)
+#pragma unroll
+            for (int c = 0; c < CT; c++) vr[bi][c] = vi[bi][c] = make_double2(0.0, 0.0);
+        for (uint32_t r = 0; r < p.R; r++) {
+            const double2 *mrow = pm + (size_t)r * p.C * poly_words;
+            double2 br[CT], bim[CT];
+#pragma unroll
+            for (int c = 0; c < CT; c++) {
+                const int cc = c < nc ? c : 0;
+                br[c] = __ldg(mrow + (size_t)cc * poly_words);
+                bim[c] = __ldg(mrow + (size_t)cc * poly_words + m2);
+            }
+#pragma unroll
+            for (int bi = 0; bi < BT; bi++) {
+                const double2 ar = a_s[((bi * p.R + r) * 2 + 0) * 128 + tid], ai2 = a_s[((bi * p.R + r) * 2 + 1) * 128 + tid];
+#pragma unroll
+                for (int c = 0; c < CT; c++) {
+                    vr[bi][c].x += ar.x * br[c].x - ai2.x * bim[c].x;
+                    vr[bi][c].y += ar.y * br[c].y - ai2.y * bim[c].y;
+                    vi[bi][c].x += ar.x * bim[c].x + ai2.x * br[c].x;
+                    vi[bi][c].y += ar.y * bim[c].y + ai2.y * br[c].y;
+                }
+            }
+        }
+#pragma unroll
+        for (int bi = 0; bi < BT; bi++)
+#pragma unroll
+            for (int c = 0; c < CT; c++) {
+                const double2 v_r = vr[bi][c], v_i = vi[bi][c];
+                const double prx = wr[bi].x * v_r.x - wi[bi].x * v_i.x, pix = wr[bi].x * v_i.x + wi[bi].x * v_r.x; // reim_mul(ppol, v)
+                const double pry = wr[bi].y * v_r.y - wi[bi].y * v_i.y, piy = wr[bi].y * v_i.y + wi[bi].y * v_r.y;
+                sr[bi][c].x = (sr[bi][c].x + prx) - v_r.x;
+                sr[bi][c].y = (sr[bi][c].y + pry) - v_r.y;
+                si[bi][c].x = (si[bi][c].x + pix) - v_i.x;
+                si[bi][c].y = (si[bi][c].y + piy) - v_i.y;
+            }
+    }
+#pragma unroll
+    for (int bi = 0; bi < BT; bi++) {
+        if (bi >= nb) break;
+        double2 *res = reinterpret_cast<double2 *>(p.acc_add + (size_t)(b0 + bi) * p.add_bs) + u + (size_t)c0 * poly_words;
+#pragma unroll
+        for (int c = 0; c < CT; c++) {
+            if (c < nc) {
+                res[(size_t)c * poly_words] = sr[bi][c];
+                res[(size_t)c * poly_words + m2] = si[bi][c];
+            }
+        }
+    }
+}
+
 // ---- extended blind rotation (algorithm.rs:121-273): the accumulator is `ext` interleaved rings; items are (ciphertext b, ring i) at
 // index b * ext + i.  Which source ring and which X^a table entry a ring takes depends on the ciphertext's own a_t (and is decided per
 // item on the device); the reference's skip conditions are kept verbatim (see the oracle's note on a_hi = 0 / 2n - 1).
@@ -421,9 +510,20 @@ int cggi_blind_rotate_impl(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2
                             (const char *)x_pow_a->data, (const long long *)lwe_2n + 1 + blk, lwe_stride, (uint32_t)n, (uint32_t)(cols * dnum),
                             (uint32_t)(cols * bsize), (uint32_t)block_size};
             ProfScope _ps(m, PROF_VMP);
-            constexpr int CT = 4;
-            const dim3 grid(((uint32_t)(n / 4) + 127) / 128, (uint32_t)((cols * bsize + CT - 1) / CT), (uint32_t)B);
-            cggi_block_fft64_kernel<CT><<<grid, 128, 0, m->stream>>>(ba);
+            constexpr int CT = 4, CT2 = 2, BT = 2;
+            const size_t sb = (size_t)BT * cols * dnum * 2 * 128 * sizeof(double2);
+            if (B >= 2 && sb <= (size_t)(100 << 10) && !getenv("PGB_CGGI_BLOCK_BT1")) { // two ciphertexts per thread share every key word
+                static bool attr_dev[32] = {};
+                if (!attr_dev[m->device & 31]) {
+                    PGB_CHECK_CUDA(cudaFuncSetAttribute(cggi_block_fft64_bt_kernel<CT2, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 << 10));
+                    attr_dev[m->device & 31] = true;
+                }
+                const dim3 grid(((uint32_t)(n / 4) + 127) / 128, (uint32_t)((cols * bsize + CT2 - 1) / CT2), (uint32_t)((B + BT - 1) / BT));
+                cggi_block_fft64_bt_kernel<CT2, BT><<<grid, 128, sb, m->stream>>>(ba, (uint32_t)B);
+            } else {
+                const dim3 grid(((uint32_t)(n / 4) + 127) / 128, (uint32_t)((cols * bsize + CT - 1) / CT), (uint32_t)B);
+                cggi_block_fft64_kernel<CT><<<grid, 128, 0, m->stream>>>(ba);
+            }
             PGB_CHECK_CUDA(cudaGetLastError());
         } else {
         PGB_CHECK_CUDA(cudaMemsetAsync(acc_add.data, 0, B * vres_bs, m->stream)); // vec_znx_dft_zero on every column

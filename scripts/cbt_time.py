@@ -91,3 +91,16 @@ if os.environ.get("CBT_PROFILE"):
     m.sync()
     pr.disable()
     pstats.Stats(pr).sort_stats("cumulative").print_stats(25)
+
+# per-category split of the blind rotation (the module's event profiler around every launch)
+NCAT = 16
+lib.pgb_profile_category_name.restype = C.c_char_p
+lib.pgb_profile_enable(m._h, 1)
+br()
+m.sync()
+pm_, pn_ = (C.c_double * NCAT)(), (C.c_uint64 * NCAT)()
+lib.pgb_profile_read(m._h, pm_, pn_, 1)
+lib.pgb_profile_enable(m._h, 0)
+for i in range(NCAT):
+    if pn_[i]:
+        print(f"  {lib.pgb_profile_category_name(i).decode():16s} {pm_[i]:9.3f} ms  {pn_[i]:5d} launches")
