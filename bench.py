@@ -180,7 +180,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner must not precede the JSON line on stdout
+    # Libraries write to fd 1 behind Python's back (NCCL prints its version banner there): stdout must carry the ONE JSON line only, so
+    # fd 1 is pointed at stderr for the whole run and the line goes to the saved descriptor at the end.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
 
@@ -347,7 +352,8 @@ def main():
         except Exception as e:  # auxiliary numbers must never break the headline line
             out["aux"] = {"error": repr(e)}
     if rank == 0:
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
