@@ -553,6 +553,12 @@ int cggi_blind_rotate_impl(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2
                                       res->cols * n * 8, (int)res->size, (int)base2k, 0, (int)B, nullptr, 0, 0, nullptr, false, true, true));
             continue;
         }
+        if (m->flavour == PGB_FFT64 && base2k >= 1 && base2k <= 63 && fft64_fused_back_supported(m, (int)bsize) && !getenv("PGB_NO_FUSION")) {
+            // algorithm.rs:361-365 for all columns in one launch (fft64_back_kernel): acc_add is read once, the accumulator updated in place
+            PGB_TRY(fft64_fused_back(m, (const char *)acc_add.data, vres_bs, (int)cols, (int)bsize, (char *)res->data, bt->stride_res,
+                                     (int)res->size, (int)base2k, (int)B));
+            continue;
+        }
         for (uint64_t i = 0; i < cols; i++) { // algorithm.rs:361-365
             pgb_batch bti = {B, big_bs, vres_bs, 0};
             PGB_TRY(pgb_vec_znx_idft_apply_batched(m, &acc_big, 0, &acc_add, i, &bti));

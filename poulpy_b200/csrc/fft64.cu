@@ -168,6 +168,107 @@ template <int L, int LPC> __global__ void __launch_bounds__(FGeo<L>::T *LPC) fft
     }
 }
 
+// ---- fused back end of one accumulator column (CGGI outside the fully fused kernel): inverse transform of the S limbs of (ciphertext,
+// column) in one CTA (slot = limb), round (conversion.rs:43-52), + the column's own limbs (vec_znx_big_add_small_assign), same-base2k carry
+// chain from the least significant limb (vec_znx_big_normalize) straight into the column -- what idft / add_small / normalize did in three
+// launches per column with the i64 big crossing HBM three times.  In place on `res` (a thread reads limb j of a coefficient before it
+// writes it; nobody else touches that word).
+struct FBackArgs {
+    const char *in;  unsigned long long in_bs;   // DFT limbs: poly (j * cols + c) at + ((j * cols + c) * n * 8)
+    char *res;       unsigned long long res_bs;  // VecZnx: limb (j, c) at + ((j * cols + c) * n * 8)
+    int cols, S, res_size, small_size, K;
+    double inv_m;
+};
+template <int L> __global__ void __launch_bounds__(1024) fft64_back_kernel(FBackArgs p, const double2 *__restrict__ tw, const double2 *__restrict__ twl) {
+    typedef FGeo<L> G;
+    constexpr int M = G::M, N = 2 * M;
+    extern __shared__ __align__(16) double2 fsm[];
+    const int slot = threadIdx.x / G::T, t = threadIdx.x % G::T; // slot = limb
+    const int b = blockIdx.x / p.cols, c = blockIdx.x % p.cols;
+    const double *gin = reinterpret_cast<const double *>(p.in + (size_t)b * p.in_bs) + ((size_t)slot * p.cols + c) * N;
+    double2 *sm = fsm + slot * G::PLANE;
+    double2 x[8];
+    if (L > G::R0) {
+        const double2 *pre = reinterpret_cast<const double2 *>(gin + 8 * t), *pim = reinterpret_cast<const double2 *>(gin + M + 8 * t);
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+            double2 r = pre[jj], i = pim[jj];
+            x[2 * jj] = make_double2(r.x, i.x);
+            x[2 * jj + 1] = make_double2(r.y, i.y);
+        }
+        {
+            double2 w[7];
+            load_tw7(w, twl, G::T, t);
+            fgs_radix8_w(x, w);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) sm[FPAD(8 * t + jj)] = x[jj];
+        __syncthreads();
+        FInvMid<L, (L - 6 >= G::R0) ? L - 6 : -1>::run(sm, tw, t);
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) x[jj] = sm[FPAD(t + jj * G::T)];
+    } else {
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) x[jj] = make_double2(gin[jj], gin[M + jj]);
+    }
+    fgs_radix8<G::R0>(x, tw, 1u);
+    __syncthreads(); // every thread has taken its last-pass inputs: the planes now hold the rounded i64 coefficients
+    long long *big = reinterpret_cast<long long *>(sm);
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+        const int idx = t + jj * G::T;
+        big[idx] = (long long)round(x[jj].x * p.inv_m);
+        big[M + idx] = (long long)round(x[jj].y * p.inv_m);
+    }
+    __syncthreads();
+    const int a_start = p.res_size < p.S ? p.res_size : p.S; // limbs >= a_start only feed the carry
+    long long *res = reinterpret_cast<long long *>(p.res + (size_t)b * p.res_bs) + (size_t)c * N;
+    const size_t ls = (size_t)p.cols * N;
+    for (int idx = threadIdx.x; idx < N; idx += blockDim.x) {
+        long long carry = 0;
+        for (int j = p.S - 1; j >= 0; j--) {
+            long long v = reinterpret_cast<const long long *>(fsm + j * G::PLANE)[idx];
+            if (j < p.small_size) v = (long long)((unsigned long long)v + (unsigned long long)res[(size_t)j * ls + idx]);
+            const long long o = norm_step(v, carry, p.K);
+            if (j < a_start) res[(size_t)j * ls + idx] = o;
+        }
+        for (int j = a_start; j < p.res_size; j++) res[(size_t)j * ls + idx] = 0; // normalize.rs:60-66
+    }
+}
+template <int L> static int flaunch_back(pgb_module *m, const FBackArgs &p, int batch) {
+    typedef FGeo<L> G;
+    const size_t smem = (size_t)p.S * G::PLANE * sizeof(double2);
+    static bool attr_set_dev[32] = {};
+    bool &attr_set = attr_set_dev[m->device & 31];
+    if (!attr_set) {
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(fft64_back_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 << 10)));
+        attr_set = true;
+    }
+    { ProfScope _ps(m, PROF_DFT_INV);
+    fft64_back_kernel<L><<<batch * p.cols, G::T * p.S, smem, m->stream>>>(p, m->fft_inv, m->fft_last_i);
+    }
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+bool fft64_fused_back_supported(const pgb_module *m, int S) {
+    if (m->flavour != PGB_FFT64 || m->log_n < 7 || m->log_n > 13 || S < 1) return false;
+    const size_t M = m->n / 2, T = M / 8, PL = M + (M >> 3) + 2;
+    return (size_t)S * T <= 1024 && (size_t)S * PL * sizeof(double2) <= (size_t)(227 << 10);
+}
+int fft64_fused_back(pgb_module *m, const char *in, uint64_t in_bs, int cols, int S, char *res, uint64_t res_bs, int res_size, int base2k, int batch) {
+    FBackArgs p = {in, in_bs, res, res_bs, cols, S, res_size, S < res_size ? S : res_size, base2k, 1.0 / (double)(m->n / 2)};
+    switch (m->log_n - 1) {
+    case 6: return flaunch_back<6>(m, p, batch);
+    case 7: return flaunch_back<7>(m, p, batch);
+    case 8: return flaunch_back<8>(m, p, batch);
+    case 9: return flaunch_back<9>(m, p, batch);
+    case 10: return flaunch_back<10>(m, p, batch);
+    case 11: return flaunch_back<11>(m, p, batch);
+    case 12: return flaunch_back<12>(m, p, batch);
+    default: pgb_set_error("fft64 fused back end: unsupported n"); return PGB_ERR_UNSUPPORTED;
+    }
+}
+
 int fft64_module_init(pgb_module *m) {
     const uint64_t mm = m->n / 2;
     uint64_t *E = (uint64_t *)malloc(sizeof(uint64_t) * (mm > 2 ? mm : 2));

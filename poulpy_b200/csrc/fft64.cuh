@@ -94,3 +94,14 @@ __device__ __forceinline__ void fgs_radix8_w(double2 (&x)[8], const double2 (&w)
 #pragma unroll
     for (int j = 0; j < 4; j++) fgs_bf(x[j], x[j + 4], w[0]);
 }
+
+// one step of the same-base2k carry chain on i64 (znx_normalize_{first,middle}_step with lsh = 0, normalization.rs:24-323): the digit
+// of x and the digit of (digit + carry_in) are taken separately, exactly like the reference, so wrap-around cases agree too
+__device__ __forceinline__ long long norm_step(long long x, long long &c, int K) {
+    const long long d = (long long)((unsigned long long)x << (64 - K)) >> (64 - K);
+    const long long co = (long long)((unsigned long long)x - (unsigned long long)d) >> K;
+    const long long s = (long long)((unsigned long long)d + (unsigned long long)c);
+    const long long out = (long long)((unsigned long long)s << (64 - K)) >> (64 - K);
+    c = (long long)((unsigned long long)co + (unsigned long long)((long long)((unsigned long long)s - (unsigned long long)out) >> K));
+    return out;
+}

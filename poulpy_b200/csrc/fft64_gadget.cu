@@ -46,7 +46,6 @@ struct FGadgetArgs {
     uint32_t aut_p;
 };
 
-__device__ __forceinline__ long long norm_step(long long x, long long &c, int K);
 // one coefficient of the automorphism epilogue: v = rounded product (+ body already added) at source position js of limb j, column c
 __device__ __forceinline__ void aut_emit(const FGadgetArgs &p, long long v, long long &carry, int K, int N, int js, const long long *post_limb,
                                          long long *out_limb, bool store) {
@@ -118,16 +117,6 @@ template <int L, bool TWS> struct GInv<L, -1, TWS> {
     static __device__ __forceinline__ void run(double2 *, const double2 *, int, int) {}
 };
 
-// one step of the same-base2k carry chain on i64 (znx_normalize_{first,middle}_step with lsh = 0, normalization.rs:24-323): the digit
-// of x and the digit of (digit + carry_in) are taken separately, exactly like the reference, so wrap-around cases agree too
-__device__ __forceinline__ long long norm_step(long long x, long long &c, int K) {
-    const long long d = (long long)((unsigned long long)x << (64 - K)) >> (64 - K);
-    const long long co = (long long)((unsigned long long)x - (unsigned long long)d) >> K;
-    const long long s = (long long)((unsigned long long)d + (unsigned long long)c);
-    const long long out = (long long)((unsigned long long)s << (64 - K)) >> (64 - K);
-    c = (long long)((unsigned long long)co + (unsigned long long)((long long)((unsigned long long)s - (unsigned long long)out) >> K));
-    return out;
-}
 
 template <int LM, int LPR, bool TWS, bool AUT> __global__ void __launch_bounds__(512, 1)
 fft64_gadget_kernel(const __grid_constant__ FGadgetArgs p, const double2 *__restrict__ twf_g, const double2 *__restrict__ twi_g) {

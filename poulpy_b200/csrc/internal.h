@@ -30,6 +30,9 @@ int ntt120_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_co
                         int C, int cols_out, int small_size, char *res, uint64_t res_bs, int res_size, int base2k, int batch, int *ok_out,
                         int dsize = 1, int a_size = 0, int key_rows = 0, int group_limit = 0, int aut_mode = 0, int64_t aut_p = 0,
                         int post_size = 0);
+// fft64.cu: inverse transform + round + add of the column's own limbs + same-base2k normalisation of every (ciphertext, column), in place
+bool fft64_fused_back_supported(const pgb_module *m, int S);
+int fft64_fused_back(pgb_module *m, const char *in, uint64_t in_bs, int cols, int S, char *res, uint64_t res_bs, int res_size, int base2k, int batch);
 // fft64_gadget.cu
 bool fft64_gadget_supported(const pgb_module *m, int R, int cols_out, int S, int base2k, int batch);
 int fft64_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_cols, int row_cols, int row_col0, int R, const char *pmat, int C,
