@@ -477,7 +477,14 @@ int cggi_blind_rotate_impl(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2
     }
     for (uint64_t blk = 0; blk + block_size <= n_lwe; blk += block_size) { // chunks_exact
         pgb_batch btd = {B, acc_bs, bt->stride_res, 0};
-        for (uint64_t j = 0; j < cols; j++) PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &acc_dft, j, res, j, &btd));
+        if (res->size >= dnum && !getenv("PGB_NO_FUSION")) {
+            // the first dnum limbs of every column are the polys 0 .. cols * dnum - 1 of both layouts: one transform launch per block
+            LimbSet fin = {(char *)res->data, n * 8, bt->stride_res}, fout = {(char *)acc_dft.data, n * pb, acc_bs};
+            if (m->flavour == PGB_NTT120) PGB_TRY(ntt120_forward(m, fin, fout, (int)(cols * dnum), (int)B));
+            else PGB_TRY(fft64_forward(m, fin, fout, (int)(cols * dnum), (int)B, -1));
+        } else {
+            for (uint64_t j = 0; j < cols; j++) PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &acc_dft, j, res, j, &btd));
+        }
         if (m->flavour == PGB_NTT120 && cols * dnum <= 16 && block_size <= 8 && !getenv("PGB_NO_FUSION")) {
             // the block's key products and X^{a_t} - 1 updates in one launch (cggi_block_ntt120_kernel)
             BlockArgs ba = {(const char *)acc_dft.data, acc_bs, (char *)acc_add.data, vres_bs, (const char *)brk->data + blk * brk_bytes, brk_bytes,
