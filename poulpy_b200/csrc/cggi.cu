@@ -297,6 +297,7 @@ template <int CT, int BT> __global__ void __launch_bounds__(128) cggi_block_fft6
         for (int bi = 0; bi < BT; bi++)
 #pragma unroll
             for (int c = 0; c < CT; c++) vr[bi][c] = vi[bi][c] = make_double2(0.0, 0.0);
+#pragma unroll 3
         for (uint32_t r = 0; r < p.R; r++) {
             const double2 *mrow = pm + (size_t)r * p.C * poly_words;
             double2 br[CT], bim[CT];
