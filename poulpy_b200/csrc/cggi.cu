@@ -297,7 +297,6 @@ template <int CT, int BT> __global__ void __launch_bounds__(128) cggi_block_fft6
         for (int bi = 0; bi < BT; bi++)
 #pragma unroll
             for (int c = 0; c < CT; c++) vr[bi][c] = vi[bi][c] = make_double2(0.0, 0.0);
-#pragma unroll 3
         for (uint32_t r = 0; r < p.R; r++) {
             const double2 *mrow = pm + (size_t)r * p.C * poly_words;
             double2 br[CT], bim[CT];
@@ -627,7 +626,14 @@ extern "C" int pgb_cggi_blind_rotate_extended_batched(pgb_module *m, pgb_vec_znx
     }
     for (uint64_t blk = 0; blk + block_size <= n_lwe; blk += block_size) {
         pgb_batch btd = {items, accd_bs, acc_item, 0};
-        for (uint64_t j = 0; j < cols; j++) PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &acc_dft, j, &acc, j, &btd));
+        const bool fuse = !getenv("PGB_NO_FUSION");
+        if (acc.size >= dnum && fuse) { // one transform launch for all columns (see cggi_blind_rotate_impl)
+            LimbSet fin = {(char *)acc.data, n * 8, acc_item}, fout = {(char *)acc_dft.data, n * pb, accd_bs};
+            if (m->flavour == PGB_NTT120) PGB_TRY(ntt120_forward(m, fin, fout, (int)(cols * dnum), (int)items));
+            else PGB_TRY(fft64_forward(m, fin, fout, (int)(cols * dnum), (int)items, -1));
+        } else {
+            for (uint64_t j = 0; j < cols; j++) PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &acc_dft, j, &acc, j, &btd));
+        }
         PGB_CHECK_CUDA(cudaMemsetAsync(acc_add.data, 0, items * vres_bs, m->stream));
         for (uint64_t t = 0; t < block_size; t++) {
             pgb_vmp_pmat ski = *brk;
@@ -643,7 +649,19 @@ extern "C" int pgb_cggi_blind_rotate_extended_batched(pgb_module *m, pgb_vec_znx
                 cggi_xai_ext_fft64_kernel<<<dim3(((uint32_t)(n / 2) + 255) / 256, (uint32_t)(cols * bsize), (uint32_t)items), 256, 0, m->stream>>>(xa);
             PGB_CHECK_CUDA(cudaGetLastError());
         }
-        for (uint64_t i = 0; i < cols; i++) { // (:262-268)
+        // (:262-268) inverse transform + add_small + normalize of every column of every item: one launch where the fused back ends apply
+        if (fuse && m->flavour == PGB_NTT120 && ntt120_fused_supported(m)) {
+            PGB_TRY(ntt120_fused_back(m, (const char *)acc_add.data, vres_bs, nullptr, 0, (int)(cols * bsize), (int)cols, (const char *)acc.data,
+                                      acc_item, cols * n * 8, (int)umin64(bsize, acc.size), (char *)acc.data, acc_item, cols * n * 8, (int)acc.size,
+                                      (int)base2k, 0, (int)items, nullptr, 0, 0, nullptr, false, true, true));
+            continue;
+        }
+        if (fuse && m->flavour == PGB_FFT64 && base2k >= 1 && base2k <= 63 && fft64_fused_back_supported(m, (int)bsize)) {
+            PGB_TRY(fft64_fused_back(m, (const char *)acc_add.data, vres_bs, (int)cols, (int)bsize, (char *)acc.data, acc_item, (int)acc.size,
+                                     (int)base2k, (int)items));
+            continue;
+        }
+        for (uint64_t i = 0; i < cols; i++) {
             pgb_batch bti = {items, big_bs, vres_bs, 0};
             PGB_TRY(pgb_vec_znx_idft_apply_batched(m, &acc_big, 0, &acc_add, i, &bti));
             pgb_batch bts = {items, big_bs, acc_item, 0};
