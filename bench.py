@@ -624,45 +624,51 @@ def aux_measurements(pb, torch, local, peak):
     except Exception as e:
         aux["glwe_trace_per_s"] = {"error": repr(e)}
     pb.hal.pool_trim()  # blocks parked by the sections above are of no use below
-    # circuit bootstrapping, constant mode (poulpy-bench circuit_bootstrapping.rs:47-129 "1-bit"): n=1024, n_lwe=574, block 7, rank 2,
-    # base2k 13, BRK/ATK/TSK k=52 dnum=3, result GGSW k=26 dnum=2; synthetic keys; batch of LWEs per call
-    try:
-        from poulpy_b200 import circuit
-        n, log_n, n_lwe, block, rank, K, B = 1024, 10, 574, 7, 2, 13, 512
-        cols, ksz, kd, res_size, dnum_res = rank + 1, 4, 3, 2, 2
-        m = pb.Module(n, pb.FFT64, device=local)
-        m.set_stream(stream.cuda_stream)
-        per = n * cols * cols * kd * ksz * m.prep_bytes
-        brk_buf = pb.DevBuf(per * n_lwe)
-        one = pb.hal.VmpPMat(brk_buf, n, kd, cols, cols, ksz)
-        m.vmp_prepare(one, m.mat_znx_from_numpy(rng.integers(-(1 << 12), 1 << 12, size=(kd, cols, ksz, cols, n), dtype=np.int64)))
-        for i in range(1, n_lwe):
-            lib.pgb_memcpy_d2d(C.c_void_p(brk_buf.ptr + i * per), C.c_void_p(brk_buf.ptr), C.c_size_t(per))
+    # circuit bootstrapping (poulpy-bench circuit_bootstrapping.rs:47-129 "1-bit"): n=1024, n_lwe=574, block 7, rank 2, base2k 13,
+    # BRK/ATK/TSK k=52 dnum=3, result GGSW dnum=2 (constant mode: k=26, 2 limbs; exponent mode keeps the 4-limb layout); synthetic keys;
+    # a batch of LWEs per call.  Both flavours for the constant mode (the reference benches FFT64), exponent mode in FFT64.
+    from poulpy_b200 import circuit
+    for fl, nm, mode in ((pb.FFT64, "fft64", "constant"), (pb.NTT120, "ntt120", "constant"), (pb.FFT64, "fft64", "exponent")):
+        key = f"circuit_bootstraps_per_s_{nm}_n1024_nlwe574_rank2" + ("" if mode == "constant" else "_to_exponent")
+        try:
+            n, log_n, n_lwe, block, rank, K, B = 1024, 10, 574, 7, 2, 13, 512
+            cols, ksz, kd, res_size, dnum_res = rank + 1, 4, 3, 2, 2
+            m = pb.Module(n, fl, device=local)
+            m.set_stream(stream.cuda_stream)
+            per = n * cols * cols * kd * ksz * m.prep_bytes
+            brk_buf = pb.DevBuf(per * n_lwe)
+            one = pb.hal.VmpPMat(brk_buf, n, kd, cols, cols, ksz)
+            m.vmp_prepare(one, m.mat_znx_from_numpy(rng.integers(-(1 << 12), 1 << 12, size=(kd, cols, ksz, cols, n), dtype=np.int64)))
+            for i in range(1, n_lwe):
+                lib.pgb_memcpy_d2d(C.c_void_p(brk_buf.ptr + i * per), C.c_void_p(brk_buf.ptr), C.c_size_t(per))
 
-        def mk(count):
-            out = []
-            for _ in range(count):
-                pm = m.vmp_pmat_alloc(kd, rank, cols, ksz)
-                m.vmp_prepare(pm, m.mat_znx_from_numpy(rng.integers(-(1 << 12), 1 << 12, size=(kd, rank, ksz, cols, n), dtype=np.int64)))
-                out.append(pm)
-            return out
+            def mk(count):
+                out = []
+                for _ in range(count):
+                    pm = m.vmp_pmat_alloc(kd, rank, cols, ksz)
+                    m.vmp_prepare(pm, m.mat_znx_from_numpy(rng.integers(-(1 << 12), 1 << 12, size=(kd, rank, ksz, cols, n), dtype=np.int64)))
+                    out.append(pm)
+                return out
 
-        atk, tsk = mk(log_n), mk(rank)
-        lwe = rng.integers(-(1 << 12), 1 << 12, size=(B, 1, 1, n_lwe + 1), dtype=np.int64)
-        lwe_dev = pb.DevBuf(lwe.nbytes)
-        lwe_dev.upload(lwe)
-        xpa = m.cggi_x_pow_a()
+            atk, tsk = mk(log_n), mk(rank)
+            lwe = rng.integers(-(1 << 12), 1 << 12, size=(B, 1, 1, n_lwe + 1), dtype=np.int64)
+            lwe_dev = pb.DevBuf(lwe.nbytes)
+            lwe_dev.upload(lwe)
+            xpa = m.cggi_x_pow_a()
 
-        def cbt():
-            circuit.circuit_bootstrap_to_constant(m, lwe_dev, B, n_lwe, 1, K, one, xpa, block, atk, tsk, K, rank, dnum_res, res_size, 1)
+            def cbt():
+                if mode == "constant":
+                    circuit.circuit_bootstrap_to_constant(m, lwe_dev, B, n_lwe, 1, K, one, xpa, block, atk, tsk, K, rank, dnum_res, res_size, 1)
+                else:
+                    circuit.circuit_bootstrap_to_exponent(m, 2, lwe_dev, B, n_lwe, 1, K, one, xpa, block, atk, tsk, K, rank, dnum_res, ksz, 1)
 
-        l0 = m.launch_count
-        ms = _time_ms(torch, stream, cbt, 2, warm=1)
-        aux[f"circuit_bootstraps_per_s_fft64_n1024_nlwe574_rank2_b{B}"] = {"value": B / (ms * 1e-3), "ms_per_batch": ms,
-                                                                          "launches_per_batch": (m.launch_count - l0) // 3}
-        del m, brk_buf, atk, tsk, lwe_dev, xpa
-    except Exception as e:
-        aux["circuit_bootstraps_per_s_fft64_n1024_nlwe574_rank2"] = {"error": repr(e)}
+            l0 = m.launch_count
+            ms = _time_ms(torch, stream, cbt, 2, warm=1)
+            aux[key + f"_b{B}"] = {"value": B / (ms * 1e-3), "ms_per_batch": ms, "launches_per_batch": (m.launch_count - l0) // 3}
+            del m, brk_buf, atk, tsk, lwe_dev, xpa
+            pb.hal.pool_trim()
+        except Exception as e:
+            aux[key] = {"error": repr(e)}
     return aux
 
 
