@@ -492,14 +492,14 @@ int cggi_blind_rotate_impl(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2
                             (uint32_t)(cols * bsize), (uint32_t)block_size};
             ProfScope _ps(m, PROF_VMP);
             // staging per CTA: (BT * RMAX + BT * block_size) slots of 256 x 16 bytes; two CTAs per SM need <= 113 KB each
-            #define BLOCK_LAUNCH(RM, BTV)                                                                                         \
+            #define BLOCK_LAUNCH(RM, BTV, LIMKB)                                                                                  \
                 {                                                                                                                 \
                     const dim3 grid(((uint32_t)n + 255) / 256, 1, (uint32_t)((B + (BTV) - 1) / (BTV)));                           \
                     const size_t sb = (size_t)((BTV) * (RM) + (BTV) * block_size) * 256 * 16;                                     \
-                    if (sb <= (size_t)(113 << 10)) {                                                                              \
+                    if (sb <= (size_t)((LIMKB) << 10)) {                                                                          \
                         static bool attr_dev[32] = {};                                                                            \
                         if (!attr_dev[m->device & 31]) {                                                                          \
-                            PGB_CHECK_CUDA(cudaFuncSetAttribute(cggi_block_ntt120_kernel<RM, BTV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 << 10)); \
+                            PGB_CHECK_CUDA(cudaFuncSetAttribute(cggi_block_ntt120_kernel<RM, BTV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (LIMKB) << 10)); \
                             attr_dev[m->device & 31] = true;                                                                      \
                         }                                                                                                         \
                         cggi_block_ntt120_kernel<RM, BTV, 1><<<grid, 256, sb, m->stream>>>(ba, (uint32_t)B);                      \
@@ -507,9 +507,15 @@ int cggi_blind_rotate_impl(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2
                         cggi_block_ntt120_kernel<RM, BTV, 0><<<grid, 256, 0, m->stream>>>(ba, (uint32_t)B);                       \
                     }                                                                                                             \
                 }
-            if (cols * dnum <= 4) BLOCK_LAUNCH(4, 4)
-            else if (cols * dnum <= 8) BLOCK_LAUNCH(8, 2)
-            else BLOCK_LAUNCH(16, 1)
+            // the row loops are unrolled over RMAX: rows beyond R cost their multiply-adds anyway, so the tile follows R closely (R = 9,
+            // the circuit-bootstrapping shape: 57 ms per blind rotation of 512 with RMAX = 16, 44 ms with 12).  Two ciphertexts per
+            // thread at RMAX = 12 need 152 KB of staging = one CTA per SM: measured slower (59 ms).
+            if (cols * dnum <= 4) BLOCK_LAUNCH(4, 4, 113)
+            else if (cols * dnum <= 8) BLOCK_LAUNCH(8, 2, 113)
+            else if (cols * dnum <= 9) BLOCK_LAUNCH(9, 1, 113)
+            else if (cols * dnum <= 10) BLOCK_LAUNCH(10, 1, 113)
+            else if (cols * dnum <= 12) BLOCK_LAUNCH(12, 1, 113)
+            else BLOCK_LAUNCH(16, 1, 113)
             #undef BLOCK_LAUNCH
             PGB_CHECK_CUDA(cudaGetLastError());
         } else if (m->flavour == PGB_FFT64 && n >= 8 && !getenv("PGB_NO_FUSION")) {

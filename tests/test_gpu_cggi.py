@@ -197,3 +197,29 @@ def test_blind_rotate_extended_matches_oracle(fl, ext):
     for b in range(batch):
         o.cggi_blind_rotate_block_binary_extended(want[b], lwe_2n[b], [luts[j] for j in range(ext)], brk_o, xpa, block, k)
     assert np.array_equal(g.vec_znx_to_numpy(res_g), want)
+
+
+@pytest.mark.parametrize("fl", [pb.NTT120, pb.FFT64])
+@pytest.mark.parametrize("rank,dnum,size,brk_size", [(2, 3, 4, 4), (4, 2, 2, 2), (3, 3, 2, 3), (3, 4, 3, 4)])
+def test_blind_rotate_tall_keys(fl, rank, dnum, size, brk_size):
+    """cols * dnum = 9, 10, 12, 16 input polys: the row tiles of cggi_block_ntt120_kernel (RMAX = 9 / 10 / 12 / 16) and, in FFT64, the block
+    kernel with two ciphertexts per thread + fft64_back_kernel (these shapes are outside the fully fused kernel); (2, 3, 4, 4) is the
+    circuit-bootstrapping bench layout.  batch = 3 leaves a half-filled pair."""
+    n, k, n_lwe, block, batch = 512, 12, 8, 4, 3  # n >= 512: the NTT120 fused back end (ntt120_fused_supported)
+    rng = np.random.default_rng(4100 + 10 * rank + dnum + fl)
+    g, o, gbrk, obrk = _setup(n, fl, rank, dnum, brk_size, n_lwe, k, rng)
+    xg, xo = g.cggi_x_pow_a(), o.cggi_x_pow_a()
+    lut = fill_uniform(rng, (size, 1, n), k)
+    lwe = rng.integers(-n, n, size=(batch, n_lwe + 1), dtype=np.int64)
+    want = np.zeros((batch, size, rank + 1, n), dtype=np.int64)
+    for b in range(batch):
+        o.cggi_blind_rotate_block_binary(want[b], lwe[b], lut, obrk, xo, block, k)
+    res = g.vec_znx_from_numpy(fill_uniform(rng, want.shape, k))
+    lwe_dev = pb.DevBuf(lwe.nbytes)
+    lwe_dev.upload(lwe)
+    l0 = g.launch_count
+    g.cggi_blind_rotate(res, lwe_dev, n_lwe, g.vec_znx_from_numpy(lut), gbrk, xg, block, k)
+    g.sync()
+    if size >= dnum:  # (accumulators shorter than the key's row count transform column by column and zero-fill)
+        assert g.launch_count - l0 <= 2 + 3 * (n_lwe // block)  # init + per block: forward, block kernel, fused back end
+    assert np.array_equal(g.vec_znx_to_numpy(res), want)
