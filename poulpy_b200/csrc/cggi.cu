@@ -511,6 +511,7 @@ int cggi_blind_rotate_impl(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2
             // the circuit-bootstrapping shape: 57 ms per blind rotation of 512 with RMAX = 16, 44 ms with 12).  Two ciphertexts per
             // thread at RMAX = 12 need 152 KB of staging = one CTA per SM: measured slower (59 ms).
             if (cols * dnum <= 4) BLOCK_LAUNCH(4, 4, 113)
+            else if (cols * dnum <= 6) BLOCK_LAUNCH(6, 2, 113)
             else if (cols * dnum <= 8) BLOCK_LAUNCH(8, 2, 113)
             else if (cols * dnum <= 9) BLOCK_LAUNCH(9, 1, 113)
             else if (cols * dnum <= 10) BLOCK_LAUNCH(10, 1, 113)
