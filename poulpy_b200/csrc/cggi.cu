@@ -259,7 +259,8 @@ template <int CT> __global__ void __launch_bounds__(128) cggi_block_fft64_kernel
 // BT ciphertexts per thread: a key word loaded from L2 serves all of them, and the block's inputs a[bi][r] are staged once in
 // thread-private shared-memory slots instead of being re-read for every LWE coefficient of the block (the one-ciphertext version moves
 // 6.2 MB of key words + 1.5 MB of inputs per ciphertext and block through L2 at the circuit-bootstrapping shape: its limiter).
-// Same operations and order per (ciphertext, frequency, output poly) as cggi_block_fft64_kernel.
+// Same sums in the same row order per (ciphertext, frequency, output poly) as cggi_block_fft64_kernel, with the row products FMA-contracted
+// as in fft64_gadget_kernel (the f64 pipeline is exact after rounding as long as the error stays below 1/2: DESIGN section 4).
 template <int CT, int BT> __global__ void __launch_bounds__(128) cggi_block_fft64_bt_kernel(BlockArgs p, uint32_t B) {
     extern __shared__ __align__(16) double2 a_s[]; // [BT][R][re | im][128]
     const uint32_t m2 = p.n / 4;
@@ -311,10 +312,11 @@ template <int CT, int BT> __global__ void __launch_bounds__(128) cggi_block_fft6
                 const double2 ar = a_s[((bi * p.R + r) * 2 + 0) * 128 + tid], ai2 = a_s[((bi * p.R + r) * 2 + 1) * 128 + tid];
 #pragma unroll
                 for (int c = 0; c < CT; c++) {
-                    vr[bi][c].x += ar.x * br[c].x - ai2.x * bim[c].x;
-                    vr[bi][c].y += ar.y * br[c].y - ai2.y * bim[c].y;
-                    vi[bi][c].x += ar.x * bim[c].x + ai2.x * br[c].x;
-                    vi[bi][c].y += ar.y * bim[c].y + ai2.y * br[c].y;
+                    // rows accumulate in row order, FMA-contracted like fft64_gadget_kernel (reim4_add_mul): 4 instead of 6 FP64 instructions
+                    vr[bi][c].x = fma(ar.x, br[c].x, vr[bi][c].x); vr[bi][c].x = fma(-ai2.x, bim[c].x, vr[bi][c].x);
+                    vr[bi][c].y = fma(ar.y, br[c].y, vr[bi][c].y); vr[bi][c].y = fma(-ai2.y, bim[c].y, vr[bi][c].y);
+                    vi[bi][c].x = fma(ar.x, bim[c].x, vi[bi][c].x); vi[bi][c].x = fma(ai2.x, br[c].x, vi[bi][c].x);
+                    vi[bi][c].y = fma(ar.y, bim[c].y, vi[bi][c].y); vi[bi][c].y = fma(ai2.y, br[c].y, vi[bi][c].y);
                 }
             }
         }
