@@ -100,6 +100,30 @@ def main():
 
     t = timeit(mul, 2.0)
     out["M6_ckks_mul_ntt120_n32768"] = {"mul_per_s_1T": 1 / t, "mul_per_s_all_cores_extrapolated": threads / t}
+    # N4: glwe_automorphism and glwe_trace at the key-switch shape (n = 4096, rank 1, 3 limbs, key 3 rows x 4 limbs), single thread
+    for fl, nm in ((O.NTT120, "ntt120"), (O.FFT64, "fft64")):
+        m = O.OracleModule(4096, fl)
+        keys = []
+        for _ in range(12):
+            pm = m.vmp_pmat_alloc(3, 1, 2, 4)
+            m.vmp_prepare(pm, u((3, 1, 4, 2, 4096), 18))
+            keys.append(pm)
+        a1, r1 = u((3, 2, 4096), 18), np.zeros((3, 2, 4096), dtype=np.int64)
+        ta = timeit(lambda: m.glwe_automorphism(r1, 18, a1, 18, keys[0], 18, 5), 1.0)
+        tt = timeit(lambda: m.glwe_trace_assign(r1, 18, 0, keys, 18, 1), 1.0)
+        out[f"N4_automorphism_trace_{nm}_n4096"] = {"automorphisms_per_s_1T": 1 / ta, "traces_per_s_1T": 1 / tt,
+                                                    "all_cores_extrapolated": {"automorphisms_per_s": threads / ta, "traces_per_s": threads / tt}}
+    # N4c: the blind rotation of circuit bootstrapping at the reference's bench shape (n = 1024, n_lwe = 574, block 7, rank 2, dnum 3,
+    # 4-limb keys) = ~90 % of a circuit bootstrap, FFT64, single thread, one matrix replicated
+    n, n_lwe = 1024, 574
+    m = O.OracleModule(n, O.FFT64)
+    pm = m.vmp_pmat_alloc(3, 3, 3, 4)
+    m.vmp_prepare(pm, u((3, 3, 4, 3, n), 13))
+    brk = [pm] * n_lwe
+    lut, lwe = u((4, 1, n), 13), rng.integers(-n, n, size=n_lwe + 1, dtype=np.int64)
+    xo, res = m.cggi_x_pow_a(), np.zeros((4, 3, n), dtype=np.int64)
+    t = timeit(lambda: m.cggi_blind_rotate_block_binary(res, lwe, lut, brk, xo, 7, 13), 2.0)
+    out["N4c_circuit_bootstrap_blind_rotation_fft64_n1024_nlwe574"] = {"per_s_1T": 1 / t, "per_s_all_cores_extrapolated": threads / t}
     print(json.dumps(out, indent=1))
 
 
