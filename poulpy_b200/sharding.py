@@ -39,3 +39,25 @@ def gather_shards(local, total: int):
     res = np.concatenate(outs, axis=0)
     assert res.shape[0] == total
     return res
+
+
+class _DeviceBytes:
+    """__cuda_array_interface__ view of a raw device allocation (lets torch.distributed move it without a copy)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def broadcast_prepared(module, buf, src: int = 0):
+    """Replicate prepared key material (a hal.DevBuf: VmpPMat / SvpPPol data) from rank `src` to every rank of the process group, in
+    place, over NCCL (NVLink broadcast at setup -- SURVEY.md section 8e; the hot path itself never communicates).  The prepared layout is
+    plain bytes, identical on every GPU, so the key is prepared once and not once per rank.  No-op without a process group."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    module.sync()  # the prepare kernels run on the module's stream, the collective on torch's
+    t = torch.as_tensor(_DeviceBytes(buf.ptr, buf.nbytes), device=torch.device("cuda", torch.cuda.current_device()))
+    dist.broadcast(t, src=src)
+    torch.cuda.synchronize()

@@ -549,3 +549,24 @@ def test_vmp_batch_tiled_large_key():
 def _first_item(g, v):
     """View of batch item 0 of a batched device container."""
     return type(v)(v.buf, v.n, v.cols, v.size, v.offset, 1, v.batch_stride)
+
+
+def test_device_bytes_view_for_collectives():
+    """sharding._DeviceBytes: torch sees a raw device allocation through __cuda_array_interface__ without a copy (what broadcast_prepared hands
+    to NCCL); without a process group broadcast_prepared is a no-op."""
+    import torch
+
+    from poulpy_b200.sharding import _DeviceBytes, broadcast_prepared
+    g = pb.Module(256, pb.NTT120)
+    rng = np.random.default_rng(77)
+    pm = g.vmp_pmat_alloc(2, 1, 2, 2)
+    g.vmp_prepare(pm, g.mat_znx_from_numpy(rng.integers(-100, 100, size=(2, 1, 2, 2, 256), dtype=np.int64)))
+    g.sync()
+    want = pm.buf.download(np.uint8, (pm.buf.nbytes,))
+    t = torch.as_tensor(_DeviceBytes(pm.buf.ptr, pm.buf.nbytes), device="cuda")
+    assert t.data_ptr() == pm.buf.ptr and t.numel() == pm.buf.nbytes
+    assert np.array_equal(t.cpu().numpy(), want)
+    t.zero_()  # writes through to the allocation
+    torch.cuda.synchronize()
+    assert not pm.buf.download(np.uint8, (pm.buf.nbytes,)).any()
+    broadcast_prepared(g, pm.buf)
