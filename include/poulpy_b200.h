@@ -347,7 +347,11 @@ int pgb_glwe_automorphism_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_
 
 /* glwe_automorphism_add_assign (poulpy-core/src/automorphism/glwe_ct.rs:142-183): res += automorphism_p(key-switch(res)), the step the
  * trace is made of; glwe_trace_assign (poulpy-core/src/glwe_trace.rs:129-175): for i in skip..log_n { glwe_rsh(1); automorphism_add_assign
- * with the key of trace_galois_elements()[i] } (glwe_trace.rs:34-44).  `keys` is a HOST array of log_n prepared automorphism keys. */
+ * with the key of trace_galois_elements()[i] } (glwe_trace.rs:34-44).  `keys` is a HOST array of log_n prepared automorphism keys.
+ * With one base2k on both sides and n = 2^10..2^12 (NTT120) / 2^9..2^12 (FFT64) the whole family is ONE launch of the gadget kernel per
+ * batch (automorphism epilogue); the _tmp_bytes below include the staging of the outputs that the in-place forms need
+ * there and, for the trace, the second GLWE buffer its rounds alternate with.  The NTT120 route reads one 4-byte flag count back per
+ * call (stream synchronisation) to decide whether any ciphertext left the collapsed-key bound and the limb-wise sequence must redo the batch. */
 size_t pgb_glwe_automorphism_add_assign_tmp_bytes(const pgb_module *m, uint64_t res_size, uint64_t res_base2k, const pgb_vmp_pmat *key,
                                                   uint64_t key_base2k, uint64_t dsize, uint64_t batch);
 int pgb_glwe_automorphism_add_assign_batched(pgb_module *m, pgb_vec_znx *res, uint64_t res_base2k, const pgb_vmp_pmat *key, uint64_t key_base2k,
