@@ -466,11 +466,12 @@ __global__ void __launch_bounds__(256) znx_rsh_assign_kernel(RshArgs q) {
     }
 #undef R_AT
 }
-int znx_rsh_assign(pgb_module *m, LimbSet r, int size, int base2k, int k, uint32_t batch) {
+int znx_rsh_assign(pgb_module *m, LimbSet r, int size, int base2k, int k, uint32_t batch, uint32_t words) {
     if (size == 0 || batch == 0) return PGB_OK;
     ProfScope _ps(m, PROF_NORMALIZE);
-    RshArgs q = {r, (uint32_t)m->n, size, base2k, k};
-    znx_rsh_assign_kernel<<<dim3(((uint32_t)m->n + 255) / 256, batch), 256, 0, m->stream>>>(q);
+    const uint32_t nw = words ? words : (uint32_t)m->n; // words per limb to shift: n, or cols * n for all (adjacent) columns of a limb at once
+    RshArgs q = {r, nw, size, base2k, k};
+    znx_rsh_assign_kernel<<<dim3((nw + 255) / 256, batch), 256, 0, m->stream>>>(q);
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;
 }

@@ -762,7 +762,11 @@ extern "C" int pgb_glwe_trace_assign_batched(pgb_module *m, pgb_vec_znx *res, ui
     uint64_t alt_stride = alt_bs;
     for (uint64_t i = skip; i < (uint64_t)m->log_n; i++) { // (:166-177)
         pgb_batch btc = {B, cur_bs, 0, 0};
-        for (uint64_t c = 0; c < cur.cols; c++) PGB_TRY(rsh_assign_impl(m, key_base2k, 1, &cur, c, &btc)); // glwe_rsh(1)
+        { // glwe_rsh(1) on every column: the columns of a limb are adjacent, so one launch shifts cols * n words per limb
+            PGB_REQUIRE(key_base2k >= 1 && key_base2k <= 63 && cur.size >= 1, "glwe_trace: base2k must be in [1, 63]");
+            LimbSet RS = {(char *)cur.data, cur.cols * n * 8, btc.stride_res};
+            PGB_TRY(znx_rsh_assign(m, RS, (int)cur.size, (int)key_base2k, 1, (uint32_t)B, (uint32_t)(cur.cols * n)));
+        }
         pgb_batch bto = {B, alt_stride, cur_bs, 0};
         PGB_TRY(pgb_glwe_automorphism_op_batched(m, 0, &alt, key_base2k, &cur, &keys[i], key_base2k, pgb_trace_galois_element(m, i), dsize, &bto,
                                                  sc, sc_len));
