@@ -75,3 +75,12 @@ def test_shard_range_partitions():
             assert parts[0][0] == 0 and parts[-1][1] == total
             assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
             assert max(b - a for a, b in parts) - min(b - a for a, b in parts) <= 1
+
+
+def test_broadcast_prepared_is_a_noop_without_a_group():
+    """Single-process runs (N = 1, the tests, smoke) never initialise torch.distributed: the key replication helper must not touch its
+    arguments then (its NCCL leg is exercised by the 2- and 8-GPU bench runs, profiles/r1_bench_v10_n2.json / r1_bench_v11_n8.json)."""
+    from poulpy_b200.sharding import _DeviceBytes, broadcast_prepared
+    assert broadcast_prepared(None, None) is None
+    view = _DeviceBytes(0x7F0000000000, 4096).__cuda_array_interface__
+    assert view["shape"] == (4096,) and view["typestr"] == "|u1" and view["data"] == (0x7F0000000000, False)
