@@ -220,6 +220,7 @@ fft64_gadget_kernel(const __grid_constant__ FGadgetArgs p, const double2 *__rest
                 GInv<LM, (LM - 6 >= G::R0) ? LM - 6 : -1, TWS>::run(work, twi, t, slot);
 #pragma unroll
                 for (int jj = 0; jj < 8; jj++) x[jj] = work[FPAD(t + jj * T)];
+                if (LPR == 1) slot_sync<T>(slot); // the next round's products overwrite the plane (write-after-read found by racecheck)
                 fgs_radix8<G::R0, TWS>(x, twi, 1u);
             }
             if (LPR == 1) {
