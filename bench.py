@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="ciphertexts per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary measurements")
+    ap.add_argument("--no-cggi", action="store_true", help="skip the CGGI bootstraps/s object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -206,23 +207,19 @@ def main():
     pmat = m.vmp_pmat_alloc(w["dnum"], w["rank"], w["rank"] + 1, w["key_size"])
     # setup, not timed: the key is prepared on rank 0 and replicated to the other GPUs over NCCL (the prepared layout is
     # plain bytes); the hot path itself never communicates
-    replicated = False
-    if world > 1:
+    from poulpy_b200.sharding import broadcast_prepared, replicate_prepared
+
+    how = replicate_prepared(lambda: m.vmp_prepare(pmat, m.mat_znx_from_numpy(mat)), lambda: broadcast_prepared(m, pmat.buf))
+    if world > 1:  # every rank must hold the same bytes (a CRC per rank, compared everywhere); a mismatch falls back to a local prepare
         import zlib
 
-        from poulpy_b200.sharding import broadcast_prepared
-        try:
-            if rank == 0:
-                m.vmp_prepare(pmat, m.mat_znx_from_numpy(mat))
-            broadcast_prepared(m, pmat.buf)
-            probe = zlib.crc32(pmat.buf.download(np.uint8, (pmat.buf.nbytes,)).tobytes())
-            probes = [None] * world
-            dist.all_gather_object(probes, probe)
-            replicated = len(set(probes)) == 1
-        except Exception as e:  # the same code runs on every rank, so a failure here is symmetric: fall back to a local prepare
-            print(f"[bench] key broadcast unavailable ({e!r}); preparing the key on every rank", file=sys.stderr)
-    if not replicated:
-        m.vmp_prepare(pmat, m.mat_znx_from_numpy(mat))
+        probes = [None] * world
+        dist.all_gather_object(probes, zlib.crc32(pmat.buf.download(np.uint8, (pmat.buf.nbytes,)).tobytes()))
+        if len(set(probes)) != 1:
+            print("[bench] replicated key differs across ranks; preparing it on every rank", file=sys.stderr)
+            m.vmp_prepare(pmat, m.mat_znx_from_numpy(mat))
+            how = "local"
+    m.gadget_key_pin(pmat)  # the prepared key is immutable for the whole run (a GGLWEPrepared in the reference): derive its gadget forms once
     a_dev = m.vec_znx_from_numpy(a_np)
     res_dev = m.vec_znx_alloc(w["rank"] + 1, w["a_size"], B)
     scratch = None
@@ -338,12 +335,23 @@ def main():
                     "peak_source": "scripts/pipe_peaks.cu on B200: in-register butterfly loop on all SMs, chip-wide rate from CUDA events "
                                    "(profiles/r1_pipe_peaks.json)",
                     "butterflies_per_keyswitch": bf_per_ks}
-    roofline = {"kernel": kernel_names.get(dom, dom), "category": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": traffic, "peak_source": peak_src, "int_pipe": int_pipe,
-                "note": "algorithmic bytes per launch (fused minimum: GLWE in + GLWE out + key once) / CUDA-event duration on the launching "
-                        "stream (DESIGN.md section 3).  HBM is the only roof MEASURED_PEAKS.json offers, but the kernel is bound by integer "
-                        "issue (five NTTs of four primes per key-switch, FMA-heavy pipe: IMAD / IMAD.HI): int_pipe gives the fraction of the "
-                        "measured in-register butterfly rate"}
+    hbm_view = {"achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["achieved_gbs"] / peak,
+                "peak_source": peak_src, "traffic": traffic,
+                "note": "algorithmic bytes per launch (fused minimum: GLWE in + GLWE out + collapsed key once) / CUDA-event duration; "
+                        "traffic = ncu dram__bytes of the same kernel"}
+    if int_pipe is not None:
+        # the binding roof: time at the butterfly peak (0.51 ms per 4096 key-switches) exceeds time at the HBM peak (0.25 ms), so the
+        # headline fraction is against integer issue; the HBM view stays as the secondary field
+        roofline = {"kernel": kernel_names.get(dom, dom), "category": dom, "bound": "int_issue", "achieved": int_pipe["achieved"],
+                    "peak": int_pipe["peak"], "unit": int_pipe["unit"], "frac": int_pipe["frac"], "traffic": traffic,
+                    "peak_source": int_pipe["peak_source"], "butterflies_per_keyswitch": bf_per_ks, "hbm": hbm_view,
+                    "time_at_peak_ms": {"int_issue": bf_per_ks * B / int_pipe["peak"] * 1e3,
+                                        "hbm": bytes_per_launch[dom] / (peak * 1e9) * 1e3},
+                    "note": "five NTTs of four primes per key-switch (3 forward + 2 inverse on the collapsed key); achieved = Shoup/Harvey "
+                            "butterflies per second of the dominant kernel from CUDA events on the launching stream; the kernel is bound by "
+                            "integer issue (IMAD / IMAD.HI on the FMA-heavy pipe), not by bytes: see time_at_peak_ms"}
+    else:
+        roofline = {"kernel": kernel_names.get(dom, dom), "category": dom, "bound": "hbm", **hbm_view}
     # whole-pipeline view: bytes the fused pipeline must move per key-switch vs what the unfused HAL sequence moves in this backend's
     # 16 B layout
     fused_bytes = bytes_per_launch[dom] / B if dom == "gadget_fused" else (bytes_per_launch["dft_forward"] + bytes_per_launch["dft_inverse"]) / B
@@ -361,6 +369,14 @@ def main():
                      "frac_of_hbm_peak": step_gbs / peak},
     }
 
+    if not args.no_cggi:
+        # CGGI bootstraps/s: measured on every rank under every world size (collectives inside: all ranks must enter)
+        try:
+            out["cggi"] = cggi_measure(pb, torch, dist, world, rank, local, with_cpu=(world == 1 and not args.no_cpu))
+        except Exception as e:
+            if world > 1:
+                raise  # a one-sided failure would leave the other ranks inside a collective: fail loudly instead
+            out["cggi"] = {"error": repr(e)}
     if rank == 0 and world == 1 and not args.no_cpu:
         cb, _, _ = cpu_port()
         out["cpu_baseline"] = cb
@@ -374,6 +390,157 @@ def main():
         os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
+
+
+CGGI = dict(n=512, n_lwe=687, rank=3, block=3, base2k=18, brk_size=2, dnum=1, acc_size=1, batch=2368)
+
+
+def cggi_ops_per_bootstrap(fl_name):
+    """Algorithmic operation counts of one block-binary blind rotation at the bench shape, in the unit of the pipe
+    that binds the flavour.  FFT64: FP64-pipe instructions (FMA / MUL / ADD each count 1): a radix-2 complex butterfly = 2 MUL + 2 FMA +
+    4 ADD = 8, a complex multiply-accumulate of the key products = 4 FMA, the (X^a - 1) update per (frequency, output poly, key) = 2 MUL +
+    2 FMA + 4 ADD = 8, the scaling of the rounded coefficients = 1 MUL.  NTT120: Shoup/Harvey butterflies of the transforms (the unit of
+    profiles/r1_pipe_peaks.json); the key products (IMAD.WIDE) are reported beside them."""
+    c = CGGI
+    n, m = c["n"], c["n"] // 2
+    cols = c["rank"] + 1
+    R, C, bs, blocks = cols * c["dnum"], cols * c["brk_size"], c["block"], c["n_lwe"] // c["block"]
+    if fl_name == "fft64":
+        log_m = m.bit_length() - 1
+        fft = (R + C) * (m // 2) * log_m * 8
+        prod = m * C * bs * (R * 4 + 8)
+        tail = C * n
+        return blocks * (fft + prod + tail), "FP64-pipe instructions (FMA/MUL/ADD)"
+    log_n = n.bit_length() - 1
+    return blocks * (R + C) * (n // 2) * log_n, "Shoup/Harvey butterflies per prime"
+
+
+def cggi_measure(pb, torch, dist, world, rank, local, with_cpu):
+    """CGGI gate-bootstrap throughput (the first half of BASELINE.json's metric), measured under EVERY world size: block-binary blind
+    rotation at the reference's bench configuration (poulpy-bench/src/bench_suite/schemes/blind_rotation.rs:39-72: n=512, n_lwe=687,
+    rank 3, block 3, base2k 18, k_brk=36, k_glwe=18), a batch of 2368 LWEs per GPU (148 SMs x 4 ciphertexts x 4 waves), BRK replicated
+    per GPU, no collective.  Per flavour: `value` = bootstraps/s with the LWEs resident in HBM (CUDA events, max over ranks);
+    `e2e` = the same through pgb_cggi_blind_rotate_host (pinned HOST LWEs in, mod switch + rotation on the device, HOST GLWEs out; copies
+    inside the timed region); `roofline` against the measured FP64 / integer issue rates; `cpu_baseline` = the oracle port on the host
+    cores (N = 1 only).  Parity at exactly this configuration: tests/test_gpu_bench_shapes.py."""
+    import ctypes as C
+
+    lib = pb.lib()
+    c = CGGI
+    n, n_lwe, rank_g, block, k, B = c["n"], c["n_lwe"], c["rank"], c["block"], c["base2k"], c["batch"]
+    cols = rank_g + 1
+    out = {"config": {"workload": "cggi_blind_rotate block-binary n=512 n_lwe=687 rank=3 block=3 base2k=18 k_brk=36 k_glwe=18 "
+                                  "(poulpy-bench blind_rotation defaults)", "batch_per_gpu": B, "global_batch": B * world, **c},
+           "metric": "cggi_bootstraps_per_s", "unit": "bootstraps/s", "n_gpus": world, "scaling": "weak"}
+    stream = torch.cuda.Stream(device=local)
+    rng = np.random.default_rng(77 + rank)
+    pp = os.path.join(ROOT, "profiles", "r1_pipe_peaks.json")
+    pk = json.load(open(pp)) if os.path.exists(pp) else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_ranks(x):
+        t = torch.tensor([x], device=f"cuda:{local}", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for fl, nm in ((pb.FFT64, "fft64"), (pb.NTT120, "ntt120")):
+        m = pb.Module(n, fl, device=local)
+        m.set_stream(stream.cuda_stream)
+        per = n * cols * cols * c["brk_size"] * c["dnum"] * m.prep_bytes
+        brk_buf = pb.DevBuf(per * n_lwe, device=local)
+        one = pb.hal.VmpPMat(brk_buf, n, c["dnum"], cols, cols, c["brk_size"])
+        # synthetic (non-cryptographic) key material as in the reference's HAL benches; 8 distinct random GGSWs cycled over the 687 slots
+        mats = np.random.default_rng(4242).integers(-(1 << (k - 1)), 1 << (k - 1), size=(8, c["dnum"], cols, c["brk_size"], cols, n), dtype=np.int64)
+        for i in range(8):
+            m.vmp_prepare(pb.hal.VmpPMat(brk_buf, n, c["dnum"], cols, cols, c["brk_size"], offset=i * per), m.mat_znx_from_numpy(mats[i]))
+        for i in range(8, n_lwe):
+            lib.pgb_memcpy_d2d(C.c_void_p(brk_buf.ptr + i * per), C.c_void_p(brk_buf.ptr + (i % 8) * per), C.c_size_t(per))
+        xpa = m.cggi_x_pow_a()
+        lut_np = rng.integers(-(1 << (k - 2)), 1 << (k - 2), size=(1, 1, n), dtype=np.int64)
+        lut = m.vec_znx_from_numpy(lut_np)
+        lwe_raw = rng.integers(-(1 << (k - 1)), 1 << (k - 1), size=(B, 1, 1, n_lwe + 1), dtype=np.int64)  # base-2^18 LWE digits
+        raw_dev = pb.DevBuf(lwe_raw.nbytes, device=local)
+        raw_dev.upload(lwe_raw)
+        lwe_dev = m.cggi_mod_switch_2n(raw_dev, B, n_lwe, 1, k, 2 * n, True)
+        res = m.vec_znx_alloc(cols, c["acc_size"], B)
+        sc = [None]
+
+        def br():
+            sc[0] = m.cggi_blind_rotate(res, lwe_dev, n_lwe, lut, one, xpa, block, k, sc[0])
+
+        steps = 3
+        br()
+        barrier()
+        l0 = m.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                br()
+            e1.record(stream)
+        torch.cuda.synchronize()
+        launches = (m.launch_count - l0) // steps
+        ms = max_ranks(e0.elapsed_time(e1)) / steps
+        barrier()
+        # e2e: host LWEs -> host GLWEs
+        lwe_h = pb.pinned_empty(lwe_raw.shape)
+        lwe_h[:] = lwe_raw
+        res_h = pb.pinned_empty((B, c["acc_size"], cols, n))
+        m.cggi_blind_rotate_host(res_h, lwe_h, k, lut, one, xpa, block, k)  # warm-up: grows the staging workspace
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            m.cggi_blind_rotate_host(res_h, lwe_h, k, lut, one, xpa, block, k)
+        barrier()
+        e2e_s = max_ranks(time.perf_counter() - t0) / steps
+        same = bool(np.array_equal(res_h, m.vec_znx_to_numpy(res)))
+        ops, unit = cggi_ops_per_bootstrap(nm)
+        d = {"value": world * B / (ms * 1e-3), "ms_per_batch": ms, "launches_per_batch": int(launches),
+             "e2e": {"value": world * B / e2e_s, "unit": "bootstraps/s", "h2d_bytes_per_step": int(lwe_raw.nbytes),
+                     "d2h_bytes_per_step": int(res_h.nbytes), "api": "pgb_cggi_blind_rotate_host (pinned host LWEs in, host GLWEs out)",
+                     "matches_device_resident": same}}
+        if pk:
+            peak_key = "dfma" if nm == "fft64" else "ct_butterfly(harvey,shoup)"
+            primes = 4 if nm == "ntt120" else 1
+            ach = ops * primes * B / (ms * 1e-3) if nm == "ntt120" else ops * B / (ms * 1e-3)
+            d["roofline"] = {"bound": "fp64_issue" if nm == "fft64" else "int_issue", "achieved": ach, "peak": pk[peak_key]["chip_per_s"],
+                             "unit": unit + "/s", "frac": ach / pk[peak_key]["chip_per_s"], "ops_per_bootstrap": ops * primes,
+                             "peak_source": "scripts/pipe_peaks.cu on B200 (profiles/r1_pipe_peaks.json)",
+                             "note": ("four-prime count; the whole-rotation kernel runs fewer primes when the device-checked bound allows "
+                                      "(DESIGN.md): the fraction is quoted against the reference's four-prime work"
+                                      if nm == "ntt120" else "DFMA issue rate; operation count from cggi_ops_per_bootstrap")}
+        out[nm] = d
+        if with_cpu and nm == "fft64":  # the reference benches CGGI in FFT64: oracle port on the host cores, bounded sample
+            from oracle import pyoracle as O
+
+            om = O.OracleModule(n, O.FFT64)
+            opm = []
+            for i in range(8):
+                pm_ = om.vmp_pmat_alloc(c["dnum"], cols, cols, c["brk_size"])
+                om.vmp_prepare(pm_, mats[i])
+                opm.append(pm_)
+            obrk = [opm[i % 8] for i in range(n_lwe)]
+            oxp = om.cggi_x_pow_a()
+            threads = O.num_threads()
+            cnt = 4 * threads
+            l2n = m.cggi_mod_switch_2n(raw_dev, B, n_lwe, 1, k, 2 * n, True).download(np.int64, (B, n_lwe + 1))[:cnt]
+            want = np.zeros((cnt, c["acc_size"], cols, n), dtype=np.int64)
+            t0 = time.perf_counter()
+            om.cggi_blind_rotate_block_binary_batch(want, l2n, lut_np, obrk, oxp, block, k, threads=threads)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": cnt / dt, "unit": "bootstraps/s", "cores": threads, "kind": "port", "flavour": "fft64",
+                                   "sample": f"{cnt} blind rotations of the bench workload, oracle C port of poulpy-cpu-ref (FFT64), {threads} threads",
+                                   "matches_gpu": bool(np.array_equal(want, m.vec_znx_to_numpy(res)[:cnt]))}
+        del m, brk_buf, xpa, lut, raw_dev, lwe_dev, res, sc
+        pb.hal.pool_trim()
+    out["value"] = out["fft64"]["value"]  # the reference's CGGI flavour is the headline of this object
+    out["e2e"] = out["fft64"]["e2e"]
+    return out
 
 
 def _time_ms(torch, stream, fn, iters, warm=3):
@@ -403,6 +570,7 @@ def aux_measurements(pb, torch, local, peak):
         mat = rng.integers(-(1 << 17), 1 << 17, size=(3, 2, 3, 2, n), dtype=np.int64)
         pm = m.vmp_pmat_alloc(3, 2, 2, 3)
         m.vmp_prepare(pm, m.mat_znx_from_numpy(mat))
+        m.gadget_key_pin(pm)
         a = m.vec_znx_from_numpy(rng.integers(-(1 << 17), 1 << 17, size=(B, 3, 2, n), dtype=np.int64))
         r = m.vec_znx_alloc(2, 3, B)
         sc = [None]
@@ -420,6 +588,7 @@ def aux_measurements(pb, torch, local, peak):
     mat = rng.integers(-(1 << 17), 1 << 17, size=(3, 1, 4, 2, n), dtype=np.int64)
     pm = m.vmp_pmat_alloc(3, 1, 2, 4)
     m.vmp_prepare(pm, m.mat_znx_from_numpy(mat))
+    m.gadget_key_pin(pm)
     a = m.vec_znx_from_numpy(rng.integers(-(1 << 17), 1 << 17, size=(B, 3, 2, n), dtype=np.int64))
     r = m.vec_znx_alloc(2, 3, B)
     sc = [None]
@@ -430,50 +599,62 @@ def aux_measurements(pb, torch, local, peak):
     ms = _time_ms(torch, stream, f2, 10)
     aux["glwe_keyswitch_per_s_fft64_n4096_b4096"] = B / (ms * 1e-3)
     del m, a, r, pm, sc
-    # vmp_apply_dft_to_dft alone, single product, the reference's sweep (poulpy-bench/src/params.rs:75-81); an L2 flush (write of a
-    # 256 MB buffer) precedes every timed launch for the shapes whose operands would otherwise sit in the 126 MB L2
+    # vmp_apply_dft_to_dft alone ("vmp_apply HBM GB/s" of BASELINE.json): the reference's whole sweep (poulpy-bench/src/params.rs:75-81)
+    # plus the CKKS relinearisation shape, both flavours.  Two regimes per shape:
+    #   stream : the batched twin over enough independent products, EACH WITH ITS OWN MATRIX (stride_b = matrix bytes), that the operands
+    #            exceed L2 several times -- kernel time from CUDA events, the HBM-streaming number;
+    #   single : one product per launch after an L2 flush -- what one HalImpl call costs; for the small shapes this is launch latency
+    #            (a few microseconds for < 10 MB), labelled as such.
     import ctypes as C
 
     lib = pb.lib()
     flush = pb.DevBuf(256 << 20)
-    vm = {}
-    for (log_n, rows, cols_in, cols_out, size) in ((12, 7, 1, 2, 8), (13, 15, 1, 2, 16), (14, 31, 1, 2, 32)):
-        n = 1 << log_n
-        m = pb.Module(n, pb.NTT120, device=local)
-        m.set_stream(stream.cuda_stream)
-        pm = m.vmp_pmat_alloc(rows, cols_in, cols_out, size)  # content irrelevant for bandwidth
-        a = m.vec_znx_dft_alloc(cols_in, rows)
-        r = m.vec_znx_dft_alloc(cols_out, size)
-        rs, as_, ps = r.struct(), a.struct(), pm.struct()
-        bt = pb.hal._BT(1, 0, 0, 0)
-        R, Cc = rows * cols_in, cols_out * size
-        byts = (R + R * Cc + Cc) * n * 16
-        if byts > (256 << 20):  # operands exceed L2 twice over: back-to-back launches, no flush needed
+    shapes = ((10, 2, 1, 2, 3), (11, 4, 1, 2, 5), (12, 7, 1, 2, 8), (13, 15, 1, 2, 16), (14, 31, 1, 2, 32), (15, 14, 1, 2, 15))
+    for fl, nm in ((pb.NTT120, "ntt120"), (pb.FFT64, "fft64")):
+        vm = {}
+        for (log_n, rows, cols_in, cols_out, size) in shapes:
+            n = 1 << log_n
+            m = pb.Module(n, fl, device=local)
+            m.set_stream(stream.cuda_stream)
+            s = m.prep_bytes
+            R, Cc = rows * cols_in, cols_out * size
+            byts = (R + R * Cc + Cc) * n * s
+            count = int(max(1, min(4096, -(-(1 << 30) // byts))))  # >= 1 GB of operands per launch
+            pm_one = n * R * Cc * s
+            pm = pb.DevBuf(pm_one * count)  # content irrelevant for bandwidth (zeros)
+            a = m.vec_znx_dft_alloc(cols_in, rows, count)
+            r = m.vec_znx_dft_alloc(cols_out, size, count)
+            rs, as_ = r.struct(), a.struct()
+            ps = pb.hal._PM(pm.ptr, n, size, rows, cols_in, cols_out)
+            bt = pb.hal._BT(count, r.batch_stride, a.batch_stride, pm_one)
+
             def f3():
-                lib.pgb_vmp_apply_dft_to_dft_batched(m._h, C.byref(rs), C.byref(as_), C.byref(ps), C.c_uint64(0), C.byref(bt))
-            ms = _time_ms(torch, stream, f3, 20, warm=3)
-            vm[f"log_n={log_n},rows={rows},cols_in={cols_in},cols_out={cols_out},size={size}"] = {
-                "ms": ms, "algorithmic_bytes": byts, "achieved_gbs": byts / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": byts / (ms * 1e-3) / 1e9 / peak,
-                "l2": "operands 4x larger than L2, 20 back-to-back launches"}
+                pb.hal._check(lib.pgb_vmp_apply_dft_to_dft_batched(m._h, C.byref(rs), C.byref(as_), C.byref(ps), C.c_uint64(0), C.byref(bt)))
+
+            ms = _time_ms(torch, stream, f3, 5, warm=2)
+            e = {"stream": {"products_per_launch": count, "ms": ms, "algorithmic_bytes": byts * count, "achieved_gbs": byts * count / (ms * 1e-3) / 1e9,
+                            "frac_of_hbm_peak": byts * count / (ms * 1e-3) / 1e9 / peak}}
+            bt1 = pb.hal._BT(1, 0, 0, 0)
+            times = []
+            for it in range(7):
+                lib.pgb_memset(C.c_void_p(flush.ptr), it, C.c_size_t(flush.nbytes))
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(stream):
+                    e0.record(stream)
+                    lib.pgb_vmp_apply_dft_to_dft_batched(m._h, C.byref(rs), C.byref(as_), C.byref(ps), C.c_uint64(0), C.byref(bt1))
+                    e1.record(stream)
+                torch.cuda.synchronize()
+                if it >= 2:
+                    times.append(e0.elapsed_time(e1))
+            ms1 = float(np.median(times))
+            e["single"] = {"ms": ms1, "algorithmic_bytes": byts, "achieved_gbs": byts / (ms1 * 1e-3) / 1e9,
+                           "frac_of_hbm_peak": byts / (ms1 * 1e-3) / 1e9 / peak,
+                           "regime": "hbm-streaming (operands exceed L2)" if byts > (200 << 20) else
+                                     ("launch-latency bound: %.1f MB per launch, time-at-HBM-peak %.1f us" % (byts / 1e6, byts / (peak * 1e3)))}
+            vm[f"log_n={log_n},rows={rows},cols_in={cols_in},cols_out={cols_out},size={size}"] = e
             del m, a, r, pm
-            continue
-        times = []
-        for it in range(8):
-            lib.pgb_memset(C.c_void_p(flush.ptr), it, C.c_size_t(flush.nbytes))
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            with torch.cuda.stream(stream):
-                e0.record(stream)
-                lib.pgb_vmp_apply_dft_to_dft_batched(m._h, C.byref(rs), C.byref(as_), C.byref(ps), C.c_uint64(0), C.byref(bt))
-                e1.record(stream)
-            torch.cuda.synchronize()
-            if it >= 3:
-                times.append(e0.elapsed_time(e1))
-        ms = float(np.median(times))
-        vm[f"log_n={log_n},rows={rows},cols_in={cols_in},cols_out={cols_out},size={size}"] = {
-            "ms": ms, "algorithmic_bytes": byts, "achieved_gbs": byts / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": byts / (ms * 1e-3) / 1e9 / peak,
-            "l2": "flushed before every launch"}
-        del m, a, r, pm
-    aux["vmp_apply_dft_to_dft_ntt120"] = vm
+            pb.hal.pool_trim()
+        aux[f"vmp_apply_dft_to_dft_{nm}"] = vm
     del flush
 
     # CKKS relinearisation core (BASELINE config 4): key-switch with VmpPMat(14, 1, 2, 15) at N = 2^15, base2k = 52
@@ -582,36 +763,6 @@ def aux_measurements(pb, torch, local, peak):
             del m, a, d, big
     aux["dft_sweep"] = sweep
 
-    # CGGI blind rotation (BASELINE config 3): n=512, n_lwe=687, rank=3, block=3, base2k=18, k_brk=36, dnum=1, k_glwe=18
-    for fl, nm in ((pb.FFT64, "fft64"), (pb.NTT120, "ntt120")):
-        n, n_lwe, rank, block, k, B = 512, 687, 3, 3, 18, 2368  # 148 SMs x 4 ciphertexts per CTA x 4 waves
-        m = pb.Module(n, fl, device=local)
-        m.set_stream(stream.cuda_stream)
-        cols = rank + 1
-        per = n * cols * cols * 2 * m.prep_bytes
-        brk_buf = pb.DevBuf(per * n_lwe)
-        # synthetic (non-cryptographic) key material, as the reference's HAL benches do: one prepared matrix replicated
-        mat = rng.integers(-(1 << 17), 1 << 17, size=(1, cols, 2, cols, n), dtype=np.int64)
-        one = pb.hal.VmpPMat(brk_buf, n, 1, cols, cols, 2)
-        m.vmp_prepare(one, m.mat_znx_from_numpy(mat))
-        for i in range(1, n_lwe):
-            lib.pgb_memcpy_d2d(C.c_void_p(brk_buf.ptr + i * per), C.c_void_p(brk_buf.ptr), C.c_size_t(per))
-        xpa = m.cggi_x_pow_a()
-        lut = m.vec_znx_from_numpy(rng.integers(-(1 << 16), 1 << 16, size=(1, 1, n), dtype=np.int64))
-        lwe = rng.integers(-n, n, size=(B, n_lwe + 1), dtype=np.int64)
-        lwe_dev = pb.DevBuf(lwe.nbytes)
-        lwe_dev.upload(lwe)
-        res = m.vec_znx_alloc(cols, 1, B)
-        sc = [None]
-
-        def br():
-            sc[0] = m.cggi_blind_rotate(res, lwe_dev, n_lwe, lut, one, xpa, block, k, sc[0])
-
-        l0 = m.launch_count
-        ms = _time_ms(torch, stream, br, 2, warm=1)
-        aux[f"cggi_bootstraps_per_s_{nm}_n512_nlwe687_b{B}"] = {"value": B / (ms * 1e-3), "ms_per_batch": ms,
-                                                                 "launches_per_batch": (m.launch_count - l0) // 3}
-        del m, brk_buf, xpa, lut, lwe_dev, res, sc
     # N4 compositions at the headline key-switch shape (n=4096, base2k=18, rank 1, 3 limbs, key dnum 3 x 4 limbs): automorphism
     # (key-switch + X -> X^p) and trace (log_n key-switch/automorphism/add rounds), batch of ciphertexts per call
     try:
@@ -623,6 +774,7 @@ def aux_measurements(pb, torch, local, peak):
             for _ in range(12):
                 pm = m.vmp_pmat_alloc(3, 1, 2, 4)
                 m.vmp_prepare(pm, m.mat_znx_from_numpy(rng.integers(-(1 << 17), 1 << 17, size=(3, 1, 4, 2, n), dtype=np.int64)))
+                m.gadget_key_pin(pm)
                 keys.append(pm)
             a = m.vec_znx_from_numpy(rng.integers(-(1 << 17), 1 << 17, size=(B, 3, 2, n), dtype=np.int64))
             r = m.vec_znx_alloc(2, 3, B)

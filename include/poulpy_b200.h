@@ -79,6 +79,24 @@ int pgb_module_flavour(const pgb_module *m);
 /* Use an externally owned CUDA stream (e.g. torch's current stream) for all launches; 0 = own stream. */
 int pgb_module_set_stream(pgb_module *m, void *cuda_stream);
 int pgb_module_sync(pgb_module *m);
+/* Route / tuning knobs of one module (test and profiling aids; the defaults are the product paths).  Each knob is seeded ONCE, when the
+ * module is created, from the environment variable named below, and can be changed afterwards with pgb_module_set_option; no entry
+ * point reads the environment. */
+typedef enum {
+    PGB_OPT_NO_FUSION = 0,      /* PGB_NO_FUSION: limb-wise HAL sequences instead of the fused single-kernel routes */
+    PGB_OPT_NO_GADGET = 1,      /* PGB_NO_GADGET: disable the single-kernel gadget products only */
+    PGB_OPT_NO_COLLAPSE = 2,    /* PGB_NO_COLLAPSE: per-limb inverse transforms in ntt120_fused_back */
+    PGB_OPT_CGGI_VARIANT = 3,   /* PGB_CGGI_VARIANT: 0 = newest fused CGGI kernel, 1 / 2 / 3 = older generations (FFT64) */
+    PGB_OPT_CGGI_BLOCK_BT1 = 4, /* PGB_CGGI_BLOCK_BT1: one ciphertext per thread in the FFT64 block kernel */
+    PGB_OPT_VMP_NO_BT = 5,      /* PGB_VMP_NO_BT: no batch tiling in the NTT120 vmp */
+    PGB_OPT_VMP_CT = 6,         /* PGB_VMP_CT: output polys per thread of the NTT120 vmp (default 4) */
+    PGB_OPT_GADGET_MB = 7,      /* PGB_GADGET_MB: resident clusters per SM the NTT120 gadget kernel is compiled for (3 or 4) */
+    PGB_OPT_HOST_CHUNK_MB = 8,  /* PGB_HOST_CHUNK_MB: staging bytes per slot of the *_host pipelines (default 32) */
+    PGB_OPT_CGGI_NTT_PRIMES = 9, /* PGB_CGGI_NTT_PRIMES: 0 = adaptive prime count in the NTT120 whole-rotation kernel, 2 / 3 / 4 = forced */
+    PGB_OPT_COUNT = 16
+} pgb_option;
+int pgb_module_set_option(pgb_module *m, int option, int64_t value);
+int64_t pgb_module_get_option(const pgb_module *m, int option);
 /* number of kernels launched by this module since creation (bench.py's gpu_launches) */
 uint64_t pgb_module_launch_count(const pgb_module *m);
 
@@ -104,6 +122,10 @@ int pgb_memset(void *dst, int byte, size_t len);
 /* zero fill of a block a host-side pool hands out again (device-wide synchronisation on both sides) */
 int pgb_recycle_device_bytes(void *p, size_t len);
 int pgb_current_device(void); /* the device pgb_alloc_device_bytes allocates on (-1 on error) */
+/* The allocation / copy helpers above act on the CURRENT device (as cudaMalloc does); a caller that drives modules on several devices from
+ * one thread selects the device first.  Entry points that take a module make the module's device current themselves before any launch. */
+int pgb_set_device(int device);
+int pgb_module_device(const pgb_module *m);
 
 /* Backend::bytes_of_* (layouts/module.rs:44-70) */
 size_t pgb_size_of_scalar_prep(const pgb_module *m);
@@ -248,6 +270,16 @@ int pgb_glwe_external_product_batched(pgb_module *m, pgb_vec_znx *res, uint64_t 
                                       uint64_t a_base2k, const pgb_vmp_pmat *ggsw, uint64_t ggsw_base2k, uint64_t dsize,
                                       const pgb_batch *bt, void *scratch, size_t scratch_len);
 
+/* Pinned keys.  The single-kernel gadget products derive per-key forms of a prepared key before they run (NTT120: the collapsed key and
+ * the bit bound of the key's coefficients, three small launches; FFT64: a re-laid-out copy, one launch).  Every buffer is caller-owned, so
+ * the library cannot know that a key's bytes are unchanged between two calls -- unless the caller says so: after pgb_gadget_key_pin(key)
+ * the module keeps those forms across calls (keyed on key->data and the call's shape) until pgb_gadget_key_unpin(key), module
+ * destruction, or a pgb_vmp_prepare into that memory (which drops them).  Rewriting a pinned key's bytes by any other means without
+ * unpinning it first is a contract violation.  Unpinned keys behave as before (forms re-derived on every call).  In the reference the
+ * analogue is the lifetime of a `GGLWEPrepared` / `GGSWPrepared` value: prepared once, borrowed immutably by every product. */
+int pgb_gadget_key_pin(pgb_module *m, const pgb_vmp_pmat *key);
+int pgb_gadget_key_unpin(pgb_module *m, const pgb_vmp_pmat *key);
+
 /* Host-buffer front ends: `res_host` / `a_host` are ordinary host arrays of `count` GLWE VecZnx; the
  * library stages them through pinned memory in chunks, overlapping H2D, compute and D2H on the module's
  * streams, and returns when `res_host` is complete.  This is what a HalImpl/CoreImpl over host-resident
@@ -387,6 +419,15 @@ size_t pgb_cggi_blind_rotate_tmp_bytes(const pgb_module *m, uint64_t rank, uint6
 int pgb_cggi_blind_rotate_batched(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2n, uint64_t n_lwe, const pgb_vec_znx *lut,
                                   const pgb_vmp_pmat *brk, const pgb_svp_ppol *x_pow_a, uint64_t block_size, uint64_t base2k,
                                   const pgb_batch *bt, void *scratch, size_t scratch_len);
+/* Host-buffer front end of the above = BlindRotationExecute::execute (cggi/algorithm.rs:88-117) for a caller whose LWE inputs and GLWE
+ * outputs live in host memory: `lwe_host` = `count` one-column VecZnx(n_lwe + 1 coefficients (b, a_0, ..), lwe_size limbs of base
+ * 2^lwe_base2k) back to back, `res_host` = `count` GLWE VecZnx(rank+1, res_size) back to back.  Uploads the LWEs, runs mod_switch_2n and
+ * the rotation on the device in chunks and copies every finished chunk back while the next one computes; returns when res_host is
+ * complete.  lut / brk / x_pow_a are the device-resident prepared objects of pgb_cggi_blind_rotate_batched; rot_left as in
+ * pgb_cggi_mod_switch_2n_batched.  Pinned host buffers (pgb_alloc_pinned_bytes) make both copies asynchronous. */
+int pgb_cggi_blind_rotate_host(pgb_module *m, int64_t *res_host, uint64_t rank, uint64_t res_size, const int64_t *lwe_host, uint64_t n_lwe,
+                               uint64_t lwe_size, uint64_t lwe_base2k, int rot_left, const pgb_vec_znx *lut, const pgb_vmp_pmat *brk,
+                               const pgb_svp_ppol *x_pow_a, uint64_t block_size, uint64_t base2k, uint64_t count);
 /* execute_block_binary_extended (algorithm.rs:121-273): lut = `ext` VecZnx(1 col, lut_size) stored consecutively (LookupTable.data), lwe_2n
  * mod-switched to 2 * n * ext; res receives ring 0 of the accumulator */
 size_t pgb_cggi_blind_rotate_extended_tmp_bytes(const pgb_module *m, uint64_t rank, uint64_t res_size, uint64_t dnum, uint64_t brk_size,

@@ -82,3 +82,28 @@ void orc_glwe_external_product_batch(int flavour, const void *mod, int64_t *res,
                ggsw_base2k, dsize, ggsw};
     parallel_for(batch, threads, job_fn, &j);
 }
+
+/* CGGI block-binary blind rotation over a batch of mod-switched LWEs (bench.py's CGGI cpu_baseline): one call of
+ * orc_cggi_blind_rotate_block_binary per ciphertext, ciphertexts spread over the host threads. */
+typedef struct {
+    int flavour;
+    const void *mod;
+    int64_t *res;
+    const int64_t *lwe;
+    size_t n, cols, res_size, n_lwe, block_size, base2k;
+    const orc_vec_znx *lut;
+    const orc_vmp_pmat *brk;
+    const orc_svp_ppol *x_pow_a;
+} cggi_job_t;
+static void cggi_job_fn(size_t i, void *ctx) {
+    cggi_job_t *j = (cggi_job_t *)ctx;
+    orc_vec_znx rv = {j->res + j->n * j->cols * j->res_size * i, j->n, j->cols, j->res_size};
+    orc_cggi_blind_rotate_block_binary(j->flavour, j->mod, &rv, j->lwe + (j->n_lwe + 1) * i, j->n_lwe, j->lut, j->brk, j->x_pow_a,
+                                       j->block_size, j->base2k);
+}
+void orc_cggi_blind_rotate_block_binary_batch(int flavour, const void *mod, int64_t *res, size_t n, size_t cols, size_t res_size,
+                                              const int64_t *lwe_2n, size_t n_lwe, const orc_vec_znx *lut, const orc_vmp_pmat *brk,
+                                              const orc_svp_ppol *x_pow_a, size_t block_size, size_t base2k, size_t batch, int threads) {
+    cggi_job_t j = {flavour, mod, res, lwe_2n, n, cols, res_size, n_lwe, block_size, base2k, lut, brk, x_pow_a};
+    parallel_for(batch, threads, cggi_job_fn, &j);
+}

@@ -259,4 +259,8 @@ int orc_num_threads(void);
 #ifdef __cplusplus
 }
 #endif
+/* batch.c: the block-binary blind rotation over `batch` mod-switched LWEs [batch][n_lwe + 1], ciphertexts spread over host threads */
+void orc_cggi_blind_rotate_block_binary_batch(int flavour, const void *mod, int64_t *res, size_t n, size_t cols, size_t res_size,
+                                              const int64_t *lwe_2n, size_t n_lwe, const orc_vec_znx *lut, const orc_vmp_pmat *brk,
+                                              const orc_svp_ppol *x_pow_a, size_t block_size, size_t base2k, size_t batch, int threads);
 #endif

@@ -373,6 +373,17 @@ class OracleModule:
         lib().orc_cggi_blind_rotate_block_binary(C.c_int(self.flavour), self._h, C.byref(r), _p(lwe_2n), _sz(n_lwe),
                                                  C.byref(lv), arr, C.byref(xp), _sz(block_size), _sz(base2k))
 
+    def cggi_blind_rotate_block_binary_batch(self, res, lwe_2n, lut, brk, x_pow_a, block_size, base2k, threads=0):
+        """res: (batch, size, cols, n) int64; lwe_2n: (batch, n_lwe + 1); ciphertexts spread over `threads` host threads (0 = all)."""
+        n_lwe = len(brk)
+        arr = (_PM * n_lwe)(*[b.struct() for b in brk])
+        lv, xp = _vz(lut), _pp(x_pow_a)
+        lwe_2n = np.ascontiguousarray(lwe_2n, dtype=np.int64)
+        batch, size, cols, n = res.shape
+        assert res.flags["C_CONTIGUOUS"] and lwe_2n.shape == (batch, n_lwe + 1)
+        lib().orc_cggi_blind_rotate_block_binary_batch(C.c_int(self.flavour), self._h, _p(res), _sz(n), _sz(cols), _sz(size), _p(lwe_2n),
+                                                       _sz(n_lwe), C.byref(lv), arr, C.byref(xp), _sz(block_size), _sz(base2k), _sz(batch),
+                                                       C.c_int(threads))
 
     def cggi_blind_rotate_block_binary_extended(self, res, lwe_2n, luts, brk, x_pow_a, block_size, base2k):
         """execute_block_binary_extended (algorithm.rs:121-273); luts: list of extension_factor arrays (size, 1, n) = LookupTable.data,

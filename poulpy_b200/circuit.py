@@ -112,7 +112,7 @@ def circuit_bootstrap_to_constant(module: "hal.Module", lwe_dev: "hal.DevBuf", b
     gap = 2 * drift // ext  # circuit.rs:336
     assert gap > 0
     ggsw_stride = n * dnum_res * cols * cols * res_size * 8
-    ggsw = hal.DevBuf(batch * ggsw_stride)
+    ggsw = hal.DevBuf(batch * ggsw_stride, device=module.device)
     tmp_size = max(acc_size, res_size)
     tmp = module.vec_znx_alloc(cols, tmp_size, batch)
     acc2 = module.vec_znx_alloc(cols, acc_size, batch)
@@ -296,7 +296,7 @@ def circuit_bootstrap_to_exponent(module: "hal.Module", log_gap_out, lwe_dev: "h
     assert gap > 0
     log_gap_in = (gap * alpha - 1).bit_length()
     ggsw_stride = n * dnum_res * cols * cols * size * 8
-    ggsw = hal.DevBuf(batch * ggsw_stride)
+    ggsw = hal.DevBuf(batch * ggsw_stride, device=module.device)
     row = ops.new()
     for i in range(dnum_res):
         post_process(ops, row, acc, log_gap_in, log_gap_out, log_domain)

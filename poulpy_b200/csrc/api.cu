@@ -106,6 +106,18 @@ extern "C" int pgb_module_new(uint64_t n, int flavour, int device, pgb_module **
     m->log_n = ilog2_u64(n);
     m->flavour = flavour;
     m->device = device;
+    {   // the environment seeds the knobs once per module (pgb_module_set_option changes them later)
+        static const struct { int opt; const char *env; int64_t dflt; bool flag; } seeds[] = {
+            {PGB_OPT_NO_FUSION, "PGB_NO_FUSION", 0, true},   {PGB_OPT_NO_GADGET, "PGB_NO_GADGET", 0, true},
+            {PGB_OPT_NO_COLLAPSE, "PGB_NO_COLLAPSE", 0, true}, {PGB_OPT_CGGI_VARIANT, "PGB_CGGI_VARIANT", 0, false},
+            {PGB_OPT_CGGI_BLOCK_BT1, "PGB_CGGI_BLOCK_BT1", 0, true}, {PGB_OPT_VMP_NO_BT, "PGB_VMP_NO_BT", 0, true},
+            {PGB_OPT_VMP_CT, "PGB_VMP_CT", 4, false},       {PGB_OPT_GADGET_MB, "PGB_GADGET_MB", 3, false},
+            {PGB_OPT_HOST_CHUNK_MB, "PGB_HOST_CHUNK_MB", 32, false}, {PGB_OPT_CGGI_NTT_PRIMES, "PGB_CGGI_NTT_PRIMES", 0, false}};
+        for (const auto &sd : seeds) {
+            const char *e = getenv(sd.env);
+            m->opt[sd.opt] = e ? (sd.flag ? 1 : (int64_t)atoll(e)) : sd.dflt;
+        }
+    }
     PGB_CHECK_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     m->own_stream = true;
     for (int i = 0; i < 2; i++) PGB_CHECK_CUDA(cudaStreamCreateWithFlags(&m->aux_stream[i], cudaStreamNonBlocking));
@@ -134,6 +146,7 @@ extern "C" void pgb_module_destroy(pgb_module *m) {
     cudaFree(m->ws);
     cudaFree(m->carry_ws);
     cudaFree(m->aux_ws);
+    key_cache_destroy(m);
     if (m->prof) {
         for (cudaEvent_t e : m->prof->pool) cudaEventDestroy(e);
         delete m->prof;
@@ -146,6 +159,14 @@ extern "C" void pgb_module_destroy(pgb_module *m) {
     for (int i = 0; i < 8; i++)
         if (m->ev[i]) cudaEventDestroy(m->ev[i]);
     free(m);
+}
+extern "C" int pgb_module_set_option(pgb_module *m, int option, int64_t value) {
+    PGB_REQUIRE(m && option >= 0 && option < PGB_OPT_COUNT, "pgb_module_set_option: unknown option %d", option);
+    m->opt[option] = value;
+    return PGB_OK;
+}
+extern "C" int64_t pgb_module_get_option(const pgb_module *m, int option) {
+    return (m && option >= 0 && option < PGB_OPT_COUNT) ? m->opt[option] : -1;
 }
 extern "C" uint64_t pgb_module_n(const pgb_module *m) { return m->n; }
 extern "C" int pgb_module_flavour(const pgb_module *m) { return m->flavour; }
@@ -217,6 +238,11 @@ extern "C" int pgb_memset(void *dst, int byte, size_t len) {
 }
 // Zero fill of a block that is being recycled by a host-side pool: ordered against every module stream on both sides (work that still
 // uses the block's previous life finishes first; nothing launched afterwards can overtake the fill).
+extern "C" int pgb_set_device(int device) {
+    PGB_CHECK_CUDA(cudaSetDevice(device));
+    return PGB_OK;
+}
+extern "C" int pgb_module_device(const pgb_module *m) { return m ? m->device : -1; }
 extern "C" int pgb_current_device(void) {
     int d = -1;
     return cudaGetDevice(&d) == cudaSuccess ? d : -1;
@@ -565,6 +591,7 @@ extern "C" int pgb_vmp_prepare(pgb_module *m, pgb_vmp_pmat *res, const pgb_mat_z
     // forward transform per polynomial, written straight into the [row][col] layout.
     const uint64_t n = m->n, pb = prep_bytes(m);
     const uint64_t polys = a->rows * a->cols_in * a->cols_out * a->size;
+    key_cache_invalidate(m, res->data, polys * n * pb); // a pinned key that is prepared again loses its cached gadget forms
     LimbSet in = {(char *)a->data, n * 8, 0};
     LimbSet out = {(char *)res->data, n * pb, 0};
     if (m->flavour == PGB_NTT120) PGB_TRY(ntt120_forward(m, in, out, (int)polys, 1));
@@ -643,6 +670,7 @@ extern "C" int pgb_vmp_apply_dft(pgb_module *m, pgb_vec_znx_dft *res, const pgb_
 }
 extern "C" int pgb_vmp_zero(pgb_module *m, pgb_vmp_pmat *res) {
     CHECK_N(res, "vmp_zero(res)");
+    key_cache_invalidate(m, res->data, pgb_bytes_of_vmp_pmat(m, res->rows, res->cols_in, res->cols_out, res->size));
     PGB_CHECK_CUDA(cudaMemsetAsync(res->data, 0, pgb_bytes_of_vmp_pmat(m, res->rows, res->cols_in, res->cols_out, res->size), m->stream));
     return sync_if(m, true);
 }
@@ -761,7 +789,7 @@ extern "C" int pgb_vec_znx_rotate_batched(pgb_module *m, int64_t p, pgb_vec_znx 
     CHECK_N(a, "vec_znx_rotate(a)");
     CHECK_COL(res, res_col, "vec_znx_rotate(res)");
     CHECK_COL(a, a_col, "vec_znx_rotate(a)");
-    PGB_REQUIRE(res->data != a->data, "vec_znx_rotate: res and a must not alias");
+    PGB_REQUIRE_DISJOINT(res, bt->stride_res, a, bt->stride_a, bt->count, 8, "vec_znx_rotate");
     const uint64_t n = m->n;
     LimbSet R = {(char *)res->data + limb_off(n, res->cols, res_col, 0, 8), res->cols * n * 8, bt->stride_res};
     LimbSet A = {(char *)a->data + limb_off(n, a->cols, a_col, 0, 8), a->cols * n * 8, bt->stride_a};
@@ -780,7 +808,7 @@ extern "C" int pgb_vec_znx_rotate(pgb_module *m, int64_t p, pgb_vec_znx *res, ui
     CHECK_N(a, "vec_znx_rotate(a)");
     CHECK_COL(res, res_col, "vec_znx_rotate(res)");
     CHECK_COL(a, a_col, "vec_znx_rotate(a)");
-    PGB_REQUIRE(res->data != a->data, "vec_znx_rotate: res and a must not alias (use the _assign form)");
+    PGB_REQUIRE_DISJOINT(res, 0, a, 0, 1, 8, "vec_znx_rotate");
     const uint64_t n = m->n;
     LimbSet R = {(char *)res->data + limb_off(n, res->cols, res_col, 0, 8), res->cols * n * 8, 0};
     LimbSet A = {(char *)a->data + limb_off(n, a->cols, a_col, 0, 8), a->cols * n * 8, 0};
@@ -826,7 +854,7 @@ extern "C" int pgb_vec_znx_mul_xp_minus_one(pgb_module *m, int64_t p, pgb_vec_zn
     CHECK_N(a, "vec_znx_mul_xp_minus_one(a)");
     CHECK_COL(res, res_col, "vec_znx_mul_xp_minus_one(res)");
     CHECK_COL(a, a_col, "vec_znx_mul_xp_minus_one(a)");
-    PGB_REQUIRE(res->data != a->data, "vec_znx_mul_xp_minus_one: res and a must not alias");
+    PGB_REQUIRE_DISJOINT(res, 0, a, 0, 1, 8, "vec_znx_mul_xp_minus_one");
     const uint64_t n = m->n, mn = umin64(res->size, a->size);
     LimbSet R = {(char *)res->data + limb_off(n, res->cols, res_col, 0, 8), res->cols * n * 8, 0};
     LimbSet A = {(char *)a->data + limb_off(n, a->cols, a_col, 0, 8), a->cols * n * 8, 0};
@@ -961,7 +989,7 @@ static int automorphism_impl(pgb_module *m, int64_t p, pgb_vec_znx *res, uint64_
     CHECK_N(a, "vec_znx_automorphism(a)");
     CHECK_COL(res, res_col, "vec_znx_automorphism(res)");
     CHECK_COL(a, a_col, "vec_znx_automorphism(a)");
-    PGB_REQUIRE(res->data != a->data, "vec_znx_automorphism: res and a must not alias");
+    PGB_REQUIRE_DISJOINT(res, bt->stride_res, a, bt->stride_a, bt->count, 8, "vec_znx_automorphism");
     PGB_REQUIRE((p & 1) != 0, "vec_znx_automorphism: the Galois element must be odd");
     const uint64_t n = m->n, mn = umin64(res->size, a->size);
     LimbSet R = {(char *)res->data + limb_off(n, res->cols, res_col, 0, 8), res->cols * n * 8, bt->stride_res};
@@ -977,7 +1005,7 @@ int big_automorphism_impl(pgb_module *m, int64_t p, pgb_vec_znx_big *res, uint64
     CHECK_N(a, "vec_znx_big_automorphism(a)");
     CHECK_COL(res, res_col, "vec_znx_big_automorphism(res)");
     CHECK_COL(a, a_col, "vec_znx_big_automorphism(a)");
-    PGB_REQUIRE(res->data != a->data, "vec_znx_big_automorphism: res and a must not alias (use the _assign entry)");
+    PGB_REQUIRE_DISJOINT(res, bt->stride_res, a, bt->stride_a, bt->count, big_bytes(m), "vec_znx_big_automorphism");
     PGB_REQUIRE((p & 1) != 0, "vec_znx_big_automorphism: the Galois element must be odd");
     const uint64_t n = m->n, bb = big_bytes(m), mn = umin64(res->size, a->size);
     LimbSet R = {(char *)res->data + limb_off(n, res->cols, res_col, 0, bb), res->cols * n * bb, bt->stride_res};

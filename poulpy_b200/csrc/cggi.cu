@@ -471,7 +471,7 @@ int cggi_blind_rotate_impl(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2
         LimbSet L = {(char *)lut->data, lut->cols * n * 8, 0};
         PGB_TRY(znx_rotate(m, R, L, 0, (const long long *)lwe_2n, (uint32_t)lwe_stride, (uint32_t)mn, (uint32_t)B));
     }
-    if (cggi_fused_supported(m, cols, dnum, bsize) && (R_ok(cols, dnum)) && !getenv("PGB_NO_FUSION")) {
+    if (cggi_fused_supported(m, cols, dnum, bsize) && (R_ok(cols, dnum)) && !opt_on(m, PGB_OPT_NO_FUSION)) {
         PGB_REQUIRE(bt->stride_res % 8 == 0, "cggi_blind_rotate: res stride must be a multiple of 8 bytes");
         return cggi_fused_fft64(m, (long long *)res->data, bt->stride_res / 8, (const long long *)lwe_2n, lwe_stride, (const double *)brk->data,
                                 brk_bytes / 8, (const double *)x_pow_a->data, (int)n_lwe, (int)block_size, (int)base2k, (int)cols, (int)dnum,
@@ -479,7 +479,7 @@ int cggi_blind_rotate_impl(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2
     }
     for (uint64_t blk = 0; blk + block_size <= n_lwe; blk += block_size) { // chunks_exact
         pgb_batch btd = {B, acc_bs, bt->stride_res, 0};
-        if (res->size >= dnum && !getenv("PGB_NO_FUSION")) {
+        if (res->size >= dnum && !opt_on(m, PGB_OPT_NO_FUSION)) {
             // the first dnum limbs of every column are the polys 0 .. cols * dnum - 1 of both layouts: one transform launch per block
             LimbSet fin = {(char *)res->data, n * 8, bt->stride_res}, fout = {(char *)acc_dft.data, n * pb, acc_bs};
             if (m->flavour == PGB_NTT120) PGB_TRY(ntt120_forward(m, fin, fout, (int)(cols * dnum), (int)B));
@@ -487,7 +487,7 @@ int cggi_blind_rotate_impl(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2
         } else {
             for (uint64_t j = 0; j < cols; j++) PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &acc_dft, j, res, j, &btd));
         }
-        if (m->flavour == PGB_NTT120 && cols * dnum <= 16 && block_size <= 8 && !getenv("PGB_NO_FUSION")) {
+        if (m->flavour == PGB_NTT120 && cols * dnum <= 16 && block_size <= 8 && !opt_on(m, PGB_OPT_NO_FUSION)) {
             // the block's key products and X^{a_t} - 1 updates in one launch (cggi_block_ntt120_kernel)
             BlockArgs ba = {(const char *)acc_dft.data, acc_bs, (char *)acc_add.data, vres_bs, (const char *)brk->data + blk * brk_bytes, brk_bytes,
                             (const char *)x_pow_a->data, (const long long *)lwe_2n + 1 + blk, lwe_stride, (uint32_t)n, (uint32_t)(cols * dnum),
@@ -521,14 +521,14 @@ int cggi_blind_rotate_impl(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2
             else BLOCK_LAUNCH(16, 1, 113)
             #undef BLOCK_LAUNCH
             PGB_CHECK_CUDA(cudaGetLastError());
-        } else if (m->flavour == PGB_FFT64 && n >= 8 && !getenv("PGB_NO_FUSION")) {
+        } else if (m->flavour == PGB_FFT64 && n >= 8 && !opt_on(m, PGB_OPT_NO_FUSION)) {
             BlockArgs ba = {(const char *)acc_dft.data, acc_bs, (char *)acc_add.data, vres_bs, (const char *)brk->data + blk * brk_bytes, brk_bytes,
                             (const char *)x_pow_a->data, (const long long *)lwe_2n + 1 + blk, lwe_stride, (uint32_t)n, (uint32_t)(cols * dnum),
                             (uint32_t)(cols * bsize), (uint32_t)block_size};
             ProfScope _ps(m, PROF_VMP);
             constexpr int CT = 4, CT2 = 2, BT = 2;
             const size_t sb = (size_t)BT * cols * dnum * 2 * 128 * sizeof(double2);
-            if (B >= 2 && sb <= (size_t)(100 << 10) && !getenv("PGB_CGGI_BLOCK_BT1")) { // two ciphertexts per thread share every key word
+            if (B >= 2 && sb <= (size_t)(100 << 10) && !opt_on(m, PGB_OPT_CGGI_BLOCK_BT1)) { // two ciphertexts per thread share every key word
                 static bool attr_dev[32] = {};
                 if (!attr_dev[m->device & 31]) {
                     PGB_CHECK_CUDA(cudaFuncSetAttribute(cggi_block_fft64_bt_kernel<CT2, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 << 10));
@@ -561,7 +561,7 @@ int cggi_blind_rotate_impl(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2
             PGB_CHECK_CUDA(cudaGetLastError());
         }
         }
-        if (m->flavour == PGB_NTT120 && ntt120_fused_supported(m) && !getenv("PGB_NO_FUSION")) {
+        if (m->flavour == PGB_NTT120 && ntt120_fused_supported(m) && !opt_on(m, PGB_OPT_NO_FUSION)) {
             // algorithm.rs:361-365 for all columns in one launch: inverse transform + CRT + add_small (the accumulator column itself) +
             // normalize, nothing but acc_add and the accumulator touches HBM
             PGB_TRY(ntt120_fused_back(m, (const char *)acc_add.data, vres_bs, nullptr, 0, (int)(cols * bsize), (int)cols, (const char *)res->data,
@@ -569,7 +569,7 @@ int cggi_blind_rotate_impl(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2
                                       res->cols * n * 8, (int)res->size, (int)base2k, 0, (int)B, nullptr, 0, 0, nullptr, false, true, true));
             continue;
         }
-        if (m->flavour == PGB_FFT64 && base2k >= 1 && base2k <= 63 && fft64_fused_back_supported(m, (int)bsize) && !getenv("PGB_NO_FUSION")) {
+        if (m->flavour == PGB_FFT64 && base2k >= 1 && base2k <= 63 && fft64_fused_back_supported(m, (int)bsize) && !opt_on(m, PGB_OPT_NO_FUSION)) {
             // algorithm.rs:361-365 for all columns in one launch (fft64_back_kernel): acc_add is read once, the accumulator updated in place
             PGB_TRY(fft64_fused_back(m, (const char *)acc_add.data, vres_bs, (int)cols, (int)bsize, (char *)res->data, bt->stride_res,
                                      (int)res->size, (int)base2k, (int)B));
@@ -635,7 +635,7 @@ extern "C" int pgb_cggi_blind_rotate_extended_batched(pgb_module *m, pgb_vec_znx
     }
     for (uint64_t blk = 0; blk + block_size <= n_lwe; blk += block_size) {
         pgb_batch btd = {items, accd_bs, acc_item, 0};
-        const bool fuse = !getenv("PGB_NO_FUSION");
+        const bool fuse = !opt_on(m, PGB_OPT_NO_FUSION);
         if (acc.size >= dnum && fuse) { // one transform launch for all columns (see cggi_blind_rotate_impl)
             LimbSet fin = {(char *)acc.data, n * 8, acc_item}, fout = {(char *)acc_dft.data, n * pb, accd_bs};
             if (m->flavour == PGB_NTT120) PGB_TRY(ntt120_forward(m, fin, fout, (int)(cols * dnum), (int)items));
@@ -805,5 +805,60 @@ extern "C" int pgb_cggi_blind_rotate_standard_batched(pgb_module *m, pgb_vec_znx
     pgb_batch btn = {B, bt->stride_res, bt->stride_res, 0};
     for (uint64_t c = 0; c < cols; c++) // glwe_normalize_assign (:440): in place, one thread owns a coefficient across limbs
         PGB_TRY(big_normalize_impl(m, res, res_base2k, 0, c, res, res_base2k, c, 0, false, &btn));
+    return PGB_OK;
+}
+
+// ---- host-buffer front end (BlindRotationExecute::execute over host-resident LWE in / GLWE out, cggi/algorithm.rs:88-117) --------------
+// Per bootstrap lwe_size * (n_lwe + 1) * 8 bytes go up and (rank + 1) * res_size * n * 8 bytes come back (5.5 KB / 16 KB at the bench
+// shape against ~10 us of compute), so unlike the key-switch this path is not PCIe bound: all LWEs go up in one copy, the mod switch and
+// the rotations run in whole-wave chunks on the module's stream and every finished chunk is copied back on a second stream while the
+// next one computes.
+static uint64_t cggi_host_chunk(const pgb_module *m, uint64_t count) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+    const uint64_t wave = (uint64_t)sms * 4; // ciphertexts one wave of the persistent kernels holds (4 per SM at n = 512)
+    if (count <= 2 * wave) return count;
+    const uint64_t waves = div_ceil64(count, wave), per = div_ceil64(waves, 4);
+    return umin64(per * wave, 65535 / wave * wave);
+}
+extern "C" int pgb_cggi_blind_rotate_host(pgb_module *m, int64_t *res_host, uint64_t rank, uint64_t res_size, const int64_t *lwe_host,
+                                          uint64_t n_lwe, uint64_t lwe_size, uint64_t lwe_base2k, int rot_left, const pgb_vec_znx *lut,
+                                          const pgb_vmp_pmat *brk, const pgb_svp_ppol *x_pow_a, uint64_t block_size, uint64_t base2k,
+                                          uint64_t count) {
+    PGB_REQUIRE(res_host && lwe_host && lut && brk && x_pow_a, "cggi_blind_rotate_host: null argument");
+    PGB_REQUIRE(lwe_size >= 1 && res_size >= 1 && n_lwe >= 1, "cggi_blind_rotate_host: empty shapes");
+    if (count == 0) return PGB_OK;
+    const uint64_t n = m->n, cols = rank + 1, len = n_lwe + 1;
+    const uint64_t lwe_item = lwe_size * len * 8, res_item = n * cols * res_size * 8;
+    const uint64_t chunk = cggi_host_chunk(m, count);
+    const size_t tmp = pgb_cggi_blind_rotate_tmp_bytes(m, rank, res_size, brk->rows, brk->size, chunk);
+    const uint64_t o_lwe = 0, o_2n = o_lwe + align_up(count * lwe_item), o_res = o_2n + align_up(count * len * 8),
+                   o_tmp = o_res + align_up(count * res_item);
+    PGB_TRY(ensure_ws(m, o_tmp + align_up(tmp) + ALIGN));
+    char *ws = (char *)m->ws;
+    cudaStream_t s_in = m->aux_stream[0], s_out = m->aux_stream[1], s_c = m->stream;
+    PGB_CHECK_CUDA(cudaMemcpyAsync(ws + o_lwe, lwe_host, count * lwe_item, cudaMemcpyHostToDevice, s_in));
+    PGB_CHECK_CUDA(cudaEventRecord(m->ev[0], s_in));
+    PGB_CHECK_CUDA(cudaStreamWaitEvent(s_c, m->ev[0], 0));
+    // mod_switch_2n of every LWE (algorithms/mod.rs:136-176), at most 65535 per launch
+    for (uint64_t first = 0; first < count; first += 65535) {
+        const uint64_t cnt = umin64(65535, count - first);
+        pgb_vec_znx lv = {ws + o_lwe + first * lwe_item, len, 1, lwe_size, lwe_size};
+        pgb_batch btm = {cnt, 0, lwe_item, 0};
+        PGB_TRY(pgb_cggi_mod_switch_2n_batched(m, (int64_t *)(ws + o_2n) + first * len, &lv, lwe_base2k, 2 * n, rot_left, &btm));
+    }
+    int slot = 0;
+    for (uint64_t first = 0; first < count; first += chunk, slot ^= 1) {
+        const uint64_t cnt = umin64(chunk, count - first);
+        pgb_vec_znx rv = {ws + o_res + first * res_item, n, cols, res_size, res_size};
+        pgb_batch bt = {cnt, res_item, 0, 0};
+        PGB_TRY(cggi_blind_rotate_impl(m, &rv, (const int64_t *)(ws + o_2n) + first * len, n_lwe, lut, brk, x_pow_a, block_size, base2k, &bt,
+                                       ws + o_tmp, m->ws_len - o_tmp));
+        PGB_CHECK_CUDA(cudaEventRecord(m->ev[2 + slot], s_c));
+        PGB_CHECK_CUDA(cudaStreamWaitEvent(s_out, m->ev[2 + slot], 0));
+        PGB_CHECK_CUDA(cudaMemcpyAsync((char *)res_host + first * res_item, rv.data, cnt * res_item, cudaMemcpyDeviceToHost, s_out));
+    }
+    PGB_CHECK_CUDA(cudaStreamSynchronize(s_out));
+    PGB_CHECK_CUDA(cudaStreamSynchronize(s_c));
     return PGB_OK;
 }

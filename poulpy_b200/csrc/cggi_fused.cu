@@ -762,7 +762,7 @@ int cggi_fused_fft64(pgb_module *m, long long *res, uint64_t res_stride_words, c
                      int out_size, int batch) {
     CggiFusedArgs p = {res, res_stride_words, lwe, lwe_stride, brk, brk_doubles, xpa, n_lwe, block_size, base2k, cols, dnum, brk_size, out_size, batch};
     const int R = cols * dnum, C = cols * brk_size;
-    if (block_size <= 8 && !getenv("PGB_CGGI_V1") && !getenv("PGB_CGGI_V2") && (brk_doubles % 2) == 0 && brk_size <= 4) {
+    if (block_size <= 8 && (m->opt[PGB_OPT_CGGI_VARIANT] == 0 || m->opt[PGB_OPT_CGGI_VARIANT] >= 3) && (brk_doubles % 2) == 0 && brk_size <= 4) {
         // TMA key stream (tiles must be 16-byte aligned: brk is a cudaMalloc'd / 64-byte aligned buffer of whole polys)
         bool handled = false;
         int s = PGB_OK;
@@ -774,7 +774,7 @@ int cggi_fused_fft64(pgb_module *m, long long *res, uint64_t res_stride_words, c
         }
         if (handled) return s;
     }
-    if (block_size <= 8 && !getenv("PGB_CGGI_V1")) {
+    if (block_size <= 8 && m->opt[PGB_OPT_CGGI_VARIANT] != 1) {
         bool handled = false;
         int s = PGB_OK;
         switch (m->log_n) {

@@ -79,7 +79,13 @@ struct pgb_module {
     // collapsed key, key coefficient scratch and per-ciphertext guard flags of the collapsed-key fast path
     void *aux_ws;
     size_t aux_len;
+    // route / tuning knobs (pgb_module_set_option); the PGB_* environment variables only seed them when the module is created, so no
+    // hot-path call ever reads the environment
+    int64_t opt[PGB_OPT_COUNT];
+    // cached per-key forms of pinned keys (key_cache.cu; pgb_gadget_key_pin / _unpin)
+    struct KeyCache *key_cache;
 };
+static inline bool opt_on(const pgb_module *m, int o) { return m->opt[o] != 0; }
 
 // kernel categories of the profiler
 enum { PROF_DFT_FWD = 0, PROF_DFT_INV = 1, PROF_VMP = 2, PROF_NORMALIZE = 3, PROF_ELEMENTWISE = 4, PROF_OTHER = 5, PROF_GADGET = 6, PROF_NCAT = 7 };
@@ -87,7 +93,9 @@ void prof_begin(pgb_module *m, int cat);
 void prof_end(pgb_module *m);
 struct ProfScope {
     pgb_module *m;
-    ProfScope(pgb_module *mm, int cat) : m(mm) { m->launches++; if (m->prof_on) prof_begin(m, cat); }
+    // every kernel launch goes through here: the module's device is made current first (a kernel must be launched with its stream's device
+    // current; the caller may drive several modules on several devices from one thread, or torch may have switched devices in between)
+    ProfScope(pgb_module *mm, int cat) : m(mm) { cudaSetDevice(m->device); m->launches++; if (m->prof_on) prof_begin(m, cat); }
     ~ProfScope() { if (m->prof_on) prof_end(m); }
 };
 

@@ -107,6 +107,12 @@ extern "C" int pgb_glwe_keyswitch_batched(pgb_module *m, pgb_vec_znx *res, uint6
     }
     const uint64_t n = m->n, pb = prep_bytes(m), B = bt->count;
     const uint64_t rank_in = key->cols_in, cols_out = key->cols_out;
+    // res may BE a (glwe_keyswitch_assign, keyswitching/glwe.rs:111-165: same pointer, rank and stride); any other overlap is rejected
+    const int alias = vec_znx_alias_class(res, bt->stride_res, a, bt->stride_a, B);
+    if (alias < 0) {
+        pgb_set_error("glwe_keyswitch: res and a overlap without being the same ciphertexts (in place needs equal pointer, rank and stride)");
+        return PGB_ERR_ALIAS;
+    }
     Arena ar = {(char *)scratch, scratch_len, 0};
 
     // (:89-90) res_dft = take_vec_znx_dft(rank_out + 1, key.size()); zero
@@ -127,14 +133,14 @@ extern "C" int pgb_glwe_keyswitch_batched(pgb_module *m, pgb_vec_znx *res, uint6
     const uint64_t a_dft_bs = n * rank_in * ain.size * pb;
     pgb_vec_znx_dft a_dft = mk(ar.take(B * a_dft_bs), n, rank_in, ain.size);
     pgb_batch btd = {B, a_dft_bs, ain_bs, 0};
-    if (dsize == 1 && res_base2k == key_base2k && m->flavour == PGB_FFT64 && !getenv("PGB_NO_FUSION")) {
+    if (dsize == 1 && res_base2k == key_base2k && m->flavour == PGB_FFT64 && !opt_on(m, PGB_OPT_NO_FUSION)) {
         const uint64_t R = umin64(key->rows * key->cols_in, rank_in * ain.size);
         if (fft64_gadget_supported(m, (int)R, (int)cols_out, (int)key->size, (int)key_base2k, (int)B)) // one kernel per batch (fft64_gadget.cu)
             return fft64_gadget_fused(m, (const char *)ain.data, ain_bs, (int)ain.cols, (int)rank_in, 1, (int)R, (const char *)key->data,
                                       (int)(cols_out * key->size), (int)cols_out, (int)umin64(ain.size, key->size), (char *)res->data,
                                       bt->stride_res, (int)res->size, (int)key_base2k, (int)B);
     }
-    if (dsize == 1 && res_base2k == key_base2k && ntt120_fused_supported(m) && !getenv("PGB_NO_FUSION")) {
+    if (dsize == 1 && res_base2k == key_base2k && ntt120_fused_supported(m) && !opt_on(m, PGB_OPT_NO_FUSION)) {
         const uint64_t R = umin64(key->rows * key->cols_in, rank_in * ain.size);
         const int small_size = (int)umin64(ain.size, key->size);
         if (ntt120_gadget_supported(m, (int)R, (int)cols_out, (int)key->size, (int)key_base2k, (int)B)) {
@@ -161,28 +167,40 @@ extern "C" int pgb_glwe_keyswitch_batched(pgb_module *m, pgb_vec_znx *res, uint6
                                  (char *)res->data, bt->stride_res, res->cols * n * 8, (int)res->size, (int)key_base2k, 0, (int)B,
                                  (const char *)ain.data, ain_bs, n * ain.cols * ain.size);
     }
-    if (dsize == 2 && res_base2k == key_base2k && m->flavour == PGB_FFT64 && !getenv("PGB_NO_FUSION") && rank_in * ain.size <= 16 &&
+    if (dsize == 2 && res_base2k == key_base2k && m->flavour == PGB_FFT64 && !opt_on(m, PGB_OPT_NO_FUSION) && rank_in * ain.size <= 16 &&
         fft64_gadget_supported(m, (int)(rank_in * ain.size), (int)cols_out, (int)key->size, (int)key_base2k, (int)B))
         return fft64_gadget_fused(m, (const char *)ain.data, ain_bs, (int)ain.cols, (int)rank_in, 1, (int)(rank_in * ain.size), (const char *)key->data,
                                   (int)(cols_out * key->size), (int)cols_out, (int)umin64(ain.size, key->size), (char *)res->data, bt->stride_res,
                                   (int)res->size, (int)key_base2k, (int)B, 2, (int)ain.size, (int)(key->rows * key->cols_in), (int)key->rows);
-    if (dsize > 1 && res_base2k == key_base2k && m->flavour == PGB_NTT120 && !getenv("PGB_NO_FUSION") &&
+    if (dsize > 1 && res_base2k == key_base2k && m->flavour == PGB_NTT120 && !opt_on(m, PGB_OPT_NO_FUSION) &&
         ntt120_gadget_supported(m, (int)(rank_in * ain.size), (int)cols_out, (int)key->size, (int)key_base2k, (int)B) &&
         gadget_likely_fits(n, rank_in * ain.size, key->size, key_base2k)) {
         // digit groups folded into the collapsed key (ntt120_gadget_fused): same single kernel as dsize == 1.  The per-limb fallback for
         // flagged ciphertexts is the generic sequence below, so the count of flagged ones is read back (one 4-byte copy + sync).
-        const size_t mark = ar.used;
-        int *ok = (int *)ar.take((2 * B + 1) * sizeof(int));
-        PGB_REQUIRE(ok != nullptr, "glwe_keyswitch: scratch exhausted");
-        PGB_TRY(ntt120_gadget_fused(m, (const char *)ain.data, ain_bs, (int)ain.cols, (int)rank_in, 1, (int)(rank_in * ain.size), (const char *)key->data,
-                                    (int)(cols_out * key->size), (int)cols_out, (int)umin64(ain.size, key->size), (char *)res->data, bt->stride_res,
-                                    (int)res->size, (int)key_base2k, (int)B, ok, (int)dsize, (int)ain.size, (int)(key->rows * key->cols_in),
-                                    (int)key->rows));
-        int nfail = 0;
-        PGB_CHECK_CUDA(cudaMemcpyAsync(&nfail, ok + B, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
-        PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
-        if (nfail == 0) return PGB_OK;
-        ar.used = mark; // some integers could leave the collapsed-key bound: redo the batch limb by limb
+        // In place (res == a) the kernel's output is staged in the (otherwise unused) res_dft block: a flagged ciphertext sends the WHOLE
+        // batch to the limb-wise sequence below, which must still find the inputs intact.  An in-place call whose staging does not fit
+        // there takes the limb-wise sequence directly.
+        const uint64_t stage_bs = n * cols_out * res->size * 8;
+        const bool stage = alias == 1;
+        if (!stage || stage_bs <= res_dft_bs) {
+            const size_t mark = ar.used;
+            int *ok = (int *)ar.take((2 * B + 1) * sizeof(int));
+            PGB_REQUIRE(ok != nullptr, "glwe_keyswitch: scratch exhausted");
+            char *out = stage ? (char *)res_dft.data : (char *)res->data;
+            const uint64_t out_bs = stage ? stage_bs : bt->stride_res;
+            PGB_TRY(ntt120_gadget_fused(m, (const char *)ain.data, ain_bs, (int)ain.cols, (int)rank_in, 1, (int)(rank_in * ain.size), (const char *)key->data,
+                                        (int)(cols_out * key->size), (int)cols_out, (int)umin64(ain.size, key->size), out, out_bs,
+                                        (int)res->size, (int)key_base2k, (int)B, ok, (int)dsize, (int)ain.size, (int)(key->rows * key->cols_in),
+                                        (int)key->rows));
+            int nfail = 0;
+            PGB_CHECK_CUDA(cudaMemcpyAsync(&nfail, ok + B, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+            PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+            if (nfail == 0) {
+                if (stage) PGB_CHECK_CUDA(cudaMemcpy2DAsync(res->data, bt->stride_res, out, out_bs, out_bs, B, cudaMemcpyDeviceToDevice, m->stream));
+                return PGB_OK;
+            }
+            ar.used = mark; // some integers could leave the collapsed-key bound: redo the batch limb by limb
+        }
     }
     for (uint64_t c = 0; c < rank_in; c++) PGB_TRY(pgb_vec_znx_dft_apply_batched(m, 1, 0, &a_dft, c, &ain, c + 1, &btd));
     pgb_vec_znx_dft ai = a_dft, tmp = res_dft;
@@ -241,6 +259,12 @@ extern "C" int pgb_glwe_external_product_batched(pgb_module *m, pgb_vec_znx *res
         return PGB_ERR_SCRATCH;
     }
     const uint64_t n = m->n, pb = prep_bytes(m), B = bt->count, cols = ggsw->cols_in;
+    // res may BE a (glwe_external_product_assign, external_product/glwe.rs:143-195); any other overlap is rejected
+    const int alias = vec_znx_alias_class(res, bt->stride_res, a, bt->stride_a, B);
+    if (alias < 0) {
+        pgb_set_error("glwe_external_product: res and a overlap without being the same ciphertexts (in place needs equal pointer and stride)");
+        return PGB_ERR_ALIAS;
+    }
     Arena ar = {(char *)scratch, scratch_len, 0};
     const uint64_t res_dft_bs = n * cols * ggsw->size * pb;
     pgb_vec_znx_dft res_dft = mk(ar.take(B * res_dft_bs), n, cols, ggsw->size);
@@ -261,14 +285,14 @@ extern "C" int pgb_glwe_external_product_batched(pgb_module *m, pgb_vec_znx *res
     pgb_vec_znx_dft a_dft = mk(ar.take(B * a_dft_bs), n, cols, a_dft_max);
     if (dsize == 1) {
         pgb_batch btd = {B, a_dft_bs, ain_bs, 0};
-        if (res_base2k == ggsw_base2k && m->flavour == PGB_FFT64 && !getenv("PGB_NO_FUSION")) {
+        if (res_base2k == ggsw_base2k && m->flavour == PGB_FFT64 && !opt_on(m, PGB_OPT_NO_FUSION)) {
             const uint64_t R = umin64(ggsw->rows * ggsw->cols_in, cols * a_size);
             if (fft64_gadget_supported(m, (int)R, (int)cols, (int)ggsw->size, (int)ggsw_base2k, (int)B)) // fft64_gadget.cu
                 return fft64_gadget_fused(m, (const char *)ain.data, ain_bs, (int)ain.cols, (int)cols, 0, (int)R, (const char *)ggsw->data,
                                           (int)(cols * ggsw->size), (int)cols, 0, (char *)res->data, bt->stride_res, (int)res->size,
                                           (int)ggsw_base2k, (int)B);
         }
-        if (res_base2k == ggsw_base2k && ntt120_fused_supported(m) && !getenv("PGB_NO_FUSION")) {
+        if (res_base2k == ggsw_base2k && ntt120_fused_supported(m) && !opt_on(m, PGB_OPT_NO_FUSION)) {
             const uint64_t R = umin64(ggsw->rows * ggsw->cols_in, cols * a_size);
             if (ntt120_gadget_supported(m, (int)R, (int)cols, (int)ggsw->size, (int)ggsw_base2k, (int)B)) {
                 int *ok = (int *)ar.take((2 * B + 1) * sizeof(int)); // flags | count of flagged | their indices
@@ -295,26 +319,36 @@ extern "C" int pgb_glwe_external_product_batched(pgb_module *m, pgb_vec_znx *res
         pgb_batch btv = {B, res_dft_bs, a_dft_bs, 0};
         PGB_TRY(vmp_apply_impl(m, &res_dft, &a_dft, ggsw, 0, &btv));
     } else {
-        if (dsize == 2 && res_base2k == ggsw_base2k && m->flavour == PGB_FFT64 && !getenv("PGB_NO_FUSION") && cols * a_size <= 16 &&
+        if (dsize == 2 && res_base2k == ggsw_base2k && m->flavour == PGB_FFT64 && !opt_on(m, PGB_OPT_NO_FUSION) && cols * a_size <= 16 &&
             fft64_gadget_supported(m, (int)(cols * a_size), (int)cols, (int)ggsw->size, (int)ggsw_base2k, (int)B))
             return fft64_gadget_fused(m, (const char *)ain.data, ain_bs, (int)ain.cols, (int)cols, 0, (int)(cols * a_size), (const char *)ggsw->data,
                                       (int)(cols * ggsw->size), (int)cols, 0, (char *)res->data, bt->stride_res, (int)res->size, (int)ggsw_base2k,
                                       (int)B, 2, (int)a_size, (int)(ggsw->rows * ggsw->cols_in), 0);
-        if (res_base2k == ggsw_base2k && m->flavour == PGB_NTT120 && !getenv("PGB_NO_FUSION") &&
+        if (res_base2k == ggsw_base2k && m->flavour == PGB_NTT120 && !opt_on(m, PGB_OPT_NO_FUSION) &&
             ntt120_gadget_supported(m, (int)(cols * a_size), (int)cols, (int)ggsw->size, (int)ggsw_base2k, (int)B) &&
             gadget_likely_fits(n, cols * a_size, ggsw->size, ggsw_base2k)) {
-            // digit groups folded into the collapsed key, as in the key-switch; no bound on the limbs of a group here (:233)
-            const size_t mark = ar.used;
-            int *ok = (int *)ar.take((2 * B + 1) * sizeof(int));
-            PGB_REQUIRE(ok != nullptr, "glwe_external_product: scratch exhausted");
-            PGB_TRY(ntt120_gadget_fused(m, (const char *)ain.data, ain_bs, (int)ain.cols, (int)cols, 0, (int)(cols * a_size), (const char *)ggsw->data,
-                                        (int)(cols * ggsw->size), (int)cols, 0, (char *)res->data, bt->stride_res, (int)res->size, (int)ggsw_base2k,
-                                        (int)B, ok, (int)dsize, (int)a_size, (int)(ggsw->rows * ggsw->cols_in), 0));
-            int nfail = 0;
-            PGB_CHECK_CUDA(cudaMemcpyAsync(&nfail, ok + B, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
-            PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
-            if (nfail == 0) return PGB_OK;
-            ar.used = mark; // redo the batch limb by limb
+            // digit groups folded into the collapsed key, as in the key-switch; no bound on the limbs of a group here (:233).  In place the
+            // output is staged in the unused res_dft block so that a flagged ciphertext can still redo the batch from intact inputs.
+            const uint64_t stage_bs = n * cols * res->size * 8;
+            const bool stage = alias == 1;
+            if (!stage || stage_bs <= res_dft_bs) {
+                const size_t mark = ar.used;
+                int *ok = (int *)ar.take((2 * B + 1) * sizeof(int));
+                PGB_REQUIRE(ok != nullptr, "glwe_external_product: scratch exhausted");
+                char *out = stage ? (char *)res_dft.data : (char *)res->data;
+                const uint64_t out_bs = stage ? stage_bs : bt->stride_res;
+                PGB_TRY(ntt120_gadget_fused(m, (const char *)ain.data, ain_bs, (int)ain.cols, (int)cols, 0, (int)(cols * a_size), (const char *)ggsw->data,
+                                            (int)(cols * ggsw->size), (int)cols, 0, out, out_bs, (int)res->size, (int)ggsw_base2k,
+                                            (int)B, ok, (int)dsize, (int)a_size, (int)(ggsw->rows * ggsw->cols_in), 0));
+                int nfail = 0;
+                PGB_CHECK_CUDA(cudaMemcpyAsync(&nfail, ok + B, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+                PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+                if (nfail == 0) {
+                    if (stage) PGB_CHECK_CUDA(cudaMemcpy2DAsync(res->data, bt->stride_res, out, out_bs, out_bs, B, cudaMemcpyDeviceToDevice, m->stream));
+                    return PGB_OK;
+                }
+                ar.used = mark; // redo the batch limb by limb
+            }
         }
         PGB_CHECK_CUDA(cudaMemsetAsync(res_dft.data, 0, B * res_dft_bs, m->stream)); // res_dft.zero() (:123)
         pgb_vec_znx_dft tmp = mk(ar.take(B * res_dft_bs), n, cols, ggsw->size);
@@ -526,7 +560,7 @@ extern "C" int pgb_glwe_tensor_relinearize_batched(pgb_module *m, pgb_vec_znx *r
 // buffer of the outputs (the epilogue gathers column 0 of a at permuted positions, so it cannot run in place).
 static int automorphism_fused(pgb_module *m, int aut_mode, pgb_vec_znx *res, uint64_t res_bs, const pgb_vec_znx *a, uint64_t a_bs,
                               const pgb_vmp_pmat *key, uint64_t base2k, int64_t p, uint64_t dsize, uint64_t B, Arena &ar) {
-    if (getenv("PGB_NO_FUSION") || getenv("PGB_NO_AUT_FUSION")) return 0;
+    if (opt_on(m, PGB_OPT_NO_FUSION)) return 0;
     const uint64_t n = m->n, rank_in = key->cols_in, cols = key->cols_out;
     const uint64_t Rfull = rank_in * a->size, R = dsize == 1 ? umin64(key->rows * key->cols_in, Rfull) : Rfull;
     const bool f64 = m->flavour == PGB_FFT64;
@@ -874,7 +908,8 @@ extern "C" int pgb_ggsw_expand_row_batched(pgb_module *m, pgb_mat_znx *ggsw, uin
 
 // ---- host-buffer front ends ---------------------------------------------------------------------------------------------------
 // Chunked three-stage pipeline (H2D on aux stream 0, compute on the module stream, D2H on aux stream 1), double buffered.
-static int ensure_ws(pgb_module *m, size_t len) {
+int ensure_ws(pgb_module *m, size_t len) {
+    PGB_CHECK_CUDA(cudaSetDevice(m->device));
     if (m->ws_len >= len) return PGB_OK;
     if (m->ws) cudaFree(m->ws);
     m->ws = nullptr;
@@ -898,7 +933,7 @@ static int ensure_pinned(pgb_module *m, size_t len) {
 typedef int (*core_fn)(pgb_module *, pgb_vec_znx *, uint64_t, const pgb_vec_znx *, uint64_t, const pgb_vmp_pmat *, uint64_t, uint64_t,
                        const pgb_batch *, void *, size_t);
 
-static bool is_pinned(const void *p) {
+bool is_pinned(const void *p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
         cudaGetLastError();
@@ -919,7 +954,7 @@ static int host_pipeline(pgb_module *m, bool ext, int64_t *res_host, uint64_t re
     const uint64_t a_bytes = n * a_cols * a_size * 8, r_bytes = n * res_cols * res_size * 8;
     // small chunks keep the three stages overlapped and the fill / drain of the pipeline short; 32 MB of staging per slot measured best
     // (scripts/e2e_probe.py: 229 k key-switches/s against a 250 k ceiling of this box's pinned H2D rate, 49 GB/s)
-    static const uint64_t stage_bytes = (uint64_t)(getenv("PGB_HOST_CHUNK_MB") ? atoi(getenv("PGB_HOST_CHUNK_MB")) : 32) << 20;
+    const uint64_t stage_bytes = (uint64_t)(m->opt[PGB_OPT_HOST_CHUNK_MB] > 0 ? m->opt[PGB_OPT_HOST_CHUNK_MB] : 32) << 20;
     const uint64_t chunk = umin64(count, umin64(2048, (a_bytes > r_bytes ? stage_bytes / a_bytes : stage_bytes / r_bytes) + 1));
     const size_t tmp = ext ? pgb_glwe_external_product_tmp_bytes(m, res_size, a_size, a_base2k, key, key_base2k, dsize, chunk)
                            : pgb_glwe_keyswitch_tmp_bytes(m, res_size, a_size, a_base2k, key, key_base2k, dsize, chunk);

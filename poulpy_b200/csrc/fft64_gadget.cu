@@ -373,7 +373,7 @@ bool plan(const pgb_module *m, int R, int cols_out, int S, int *lpr_out, bool *t
 
 bool fft64_gadget_supported(const pgb_module *m, int R, int cols_out, int S, int base2k, int batch) {
     if (m->flavour != PGB_FFT64 || m->log_n < 9 || m->log_n > 12) return false;
-    if (getenv("PGB_NO_GADGET")) return false;
+    if (opt_on(m, PGB_OPT_NO_GADGET)) return false;
     if (cols_out < 1 || cols_out > 4 || R < 1 || S < 1 || base2k < 1 || base2k > 63 || batch < 1) return false;
     int lpr;
     bool tws;
@@ -424,24 +424,34 @@ int fft64_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_col
     p.in_cols = in_cols; p.row_cols = row_cols; p.row_col0 = row_col0; p.R = R; p.C = C; p.cols_out = cols_out; p.small_size = small_size;
     p.K = base2k; p.S = C / cols_out; p.res_size = res_size; p.batch = batch;
     p.inv_m = 1.0 / (double)(m->n / 2);
-    // workspace: the key in the kernel's layout
+    // workspace: the key in the kernel's layout; kept in the module's key cache for a PINNED key (pgb_gadget_key_pin)
     const uint64_t M = m->n / 2;
-    const uint64_t key_bytes = (uint64_t)key_rows * C * m->n * 8, need = key_bytes + 256;
-    if (m->aux_len < need) {
-        if (m->aux_ws) {
-            PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
-            cudaFree(m->aux_ws);
+    const uint64_t key_bytes = (uint64_t)key_rows * C * m->n * 8;
+    const uint64_t sig[KEY_SIG_WORDS] = {2, (uint64_t)key_rows, (uint64_t)C, 0, 0, 0, 0, 0, 0, 0};
+    const bool pinned = key_is_pinned(m, pmat);
+    double2 *kperm = pinned ? (double2 *)key_cache_find(m, pmat, sig) : nullptr;
+    const bool have = kperm != nullptr;
+    if (pinned && !have) PGB_TRY(key_cache_insert(m, pmat, key_bytes, sig, key_bytes + 256, (void **)&kperm));
+    if (!pinned) {
+        const uint64_t need = key_bytes + 256;
+        if (m->aux_len < need) {
+            if (m->aux_ws) {
+                PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+                cudaFree(m->aux_ws);
+            }
+            m->aux_ws = nullptr;
+            m->aux_len = 0;
+            PGB_CHECK_CUDA(cudaMalloc(&m->aux_ws, need));
+            m->aux_len = need;
         }
-        m->aux_ws = nullptr;
-        m->aux_len = 0;
-        PGB_CHECK_CUDA(cudaMalloc(&m->aux_ws, need));
-        m->aux_len = need;
+        kperm = (double2 *)m->aux_ws;
     }
-    double2 *kperm = (double2 *)m->aux_ws;
-    { ProfScope _ps(m, PROF_OTHER);
-    fft64_gadget_key_kernel<<<dim3(((unsigned)(M / 2) + 255) / 256, key_rows * C, 2), 256, 0, m->stream>>>((const double *)pmat, kperm, (int)M, key_rows * C);
+    if (!have) {
+        { ProfScope _ps(m, PROF_OTHER);
+        fft64_gadget_key_kernel<<<dim3(((unsigned)(M / 2) + 255) / 256, key_rows * C, 2), 256, 0, m->stream>>>((const double *)pmat, kperm, (int)M, key_rows * C);
+        }
+        PGB_CHECK_CUDA(cudaGetLastError());
     }
-    PGB_CHECK_CUDA(cudaGetLastError());
     p.pmat = (const double *)kperm;
     p.twl_f = m->fft_last_f;
     p.twl_i = m->fft_last_i;

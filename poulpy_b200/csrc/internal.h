@@ -5,6 +5,30 @@
 static inline uint64_t prep_bytes(const pgb_module *m) { return m->flavour == PGB_NTT120 ? 16 : 8; }
 static inline uint64_t big_bytes(const pgb_module *m) { return m->flavour == PGB_NTT120 ? 16 : 8; }
 
+// ---- aliasing (poulpy-hal/docs/backend_safety_contract.md "Aliasing": never UB, detect and reject) ----------------------------------
+// byte extent of `count` items of `item` bytes laid out `stride` bytes apart (stride 0 = one shared item)
+static inline uint64_t batch_extent(uint64_t item, uint64_t stride, uint64_t count) { return (count ? (count - 1) * stride : 0) + item; }
+static inline bool ranges_overlap(const void *a, uint64_t alen, const void *b, uint64_t blen) {
+    const char *a0 = (const char *)a, *b0 = (const char *)b;
+    return alen && blen && a0 < b0 + blen && b0 < a0 + alen;
+}
+// 0: disjoint; 1: res IS a (same pointer, column count and batch stride, so limb (j, col) has one address on both sides: the reference's
+// `_assign` forms); -1: any other overlap
+static inline int vec_znx_alias_class(const pgb_vec_znx *res, uint64_t res_stride, const pgb_vec_znx *a, uint64_t a_stride, uint64_t count,
+                                      uint64_t scalar_bytes = 8) {
+    const uint64_t ri = res->n * res->cols * res->size * scalar_bytes, ai = a->n * a->cols * a->size * scalar_bytes;
+    if (!ranges_overlap(res->data, batch_extent(ri, res_stride, count), a->data, batch_extent(ai, a_stride, count))) return 0;
+    if (res->data == a->data && res->cols == a->cols && (count <= 1 || res_stride == a_stride)) return 1;
+    return -1;
+}
+#define PGB_REQUIRE_DISJOINT(res, res_stride, a, a_stride, count, scalar_bytes, what)                                       \
+    do {                                                                                                                   \
+        if (vec_znx_alias_class((res), (res_stride), (a), (a_stride), (count), (scalar_bytes)) != 0) {                       \
+            pgb_set_error("%s: res and a must not overlap", (what));                                                        \
+            return PGB_ERR_ALIAS;                                                                                          \
+        }                                                                                                                  \
+    } while (0)
+
 enum { EW_ADD = 0, EW_SUB = 1, EW_NEG = 2, EW_COPY = 3, EW_ZERO = 4, EW_MUL = 5 };
 enum { BIG_ADD_SMALL = 0, BIG_FROM_SMALL = 1, BIG_ZERO = 2, BIG_SUB_SMALL = 3, BIG_SUB_SMALL_NEG = 4, BIG_NEG = 5 };
 
@@ -69,6 +93,16 @@ int cnv_apply(pgb_module *m, LimbSet res, int res_size, LimbSet a, LimbSet a2, i
 int cnv_by_const(pgb_module *m, LimbSet res, int res_size, LimbSet a, int a_size, const long long *b_dev, int b_size, uint64_t cnv_offset,
                  uint32_t batch);
 int cnv_prepare_impl(pgb_module *m, pgb_vec_znx_dft *res, const pgb_vec_znx *a, int64_t mask, const pgb_batch *bt);
+// key_cache.cu: cached gadget-kernel forms of pinned keys.  sig = what the cached bytes depend on besides the key itself
+enum { KEY_SIG_WORDS = 10 };
+bool key_is_pinned(const pgb_module *m, const void *key);
+void *key_cache_find(pgb_module *m, const void *key, const uint64_t *sig);
+int key_cache_insert(pgb_module *m, const void *key, uint64_t key_len, const uint64_t *sig, size_t bytes, void **out);
+void key_cache_invalidate(pgb_module *m, const void *p, uint64_t len);
+void key_cache_destroy(pgb_module *m);
+// core.cu: lazily grown device workspace of the host front ends; whether a host pointer is page-locked
+int ensure_ws(pgb_module *m, size_t len);
+bool is_pinned(const void *p);
 // api.cu (used by core.cu)
 int vmp_apply_impl(pgb_module *m, pgb_vec_znx_dft *res, const pgb_vec_znx_dft *a, const pgb_vmp_pmat *pmat, uint64_t limb_offset,
                    const pgb_batch *bt);

@@ -1142,7 +1142,7 @@ int ntt120_fused_back(pgb_module *m, const char *a_dft, uint64_t a_bs, const cha
     const uint64_t key_bytes = (uint64_t)R * C * poly_bytes;
     const int *ok = skip;
     const bool try_collapse = glwe && !skip && !direct && res_offset == 0 && S >= 2 && S <= 32 && (int64_t)batch * cols_out >= 64 && key_bytes <= ((uint64_t)64 << 20) &&
-                              (S - 1) * base2k + 3 < 118 && !getenv("PGB_NO_COLLAPSE");
+                              (S - 1) * base2k + 3 < 118 && !opt_on(m, PGB_OPT_NO_COLLAPSE);
     if (try_collapse) {
         // workspace: [collapsed key | key coefficients (i128) | key_bits | ok flags]
         const uint64_t ck_bytes = (uint64_t)R * cols_out * poly_bytes;

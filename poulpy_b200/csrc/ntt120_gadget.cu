@@ -733,9 +733,8 @@ static uint32_t pow2_mod(uint64_t e, uint32_t q) {
 
 template <int L, int MB, bool AUT> int launch_gadget_mb(pgb_module *m, const GadgetArgs &p, size_t smem);
 template <int L> int launch_gadget(pgb_module *m, const GadgetArgs &p, size_t smem) {
-    const char *e = getenv("PGB_GADGET_MB");
     if (p.aut_mode) return launch_gadget_mb<L, 3, true>(m, p, smem);
-    if (e && atoi(e) == 4) return launch_gadget_mb<L, 4, false>(m, p, smem);
+    if (m->opt[PGB_OPT_GADGET_MB] == 4) return launch_gadget_mb<L, 4, false>(m, p, smem);
     return launch_gadget_mb<L, 3, false>(m, p, smem);
 }
 template <int L, int MB, bool AUT> int launch_gadget_mb(pgb_module *m, const GadgetArgs &p, size_t smem) {
@@ -748,8 +747,7 @@ template <int L, int MB, bool AUT> int launch_gadget_mb(pgb_module *m, const Gad
     cfg.stream = m->stream;
     if (!max_clusters) {
         PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_gadget_kernel<L, MB, AUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 << 10)));
-        const char *cv = getenv("PGB_GADGET_CARVEOUT");
-        PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_gadget_kernel<L, MB, AUT>, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : 100));
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_gadget_kernel<L, MB, AUT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
     // resident clusters for this shared-memory footprint (depends on R through smem)
     cfg.gridDim = dim3(4 * 148);
@@ -773,7 +771,7 @@ template <int L, int MB, bool AUT> int launch_gadget_mb(pgb_module *m, const Gad
 
 bool ntt120_gadget_supported(const pgb_module *m, int R, int cols_out, int S, int base2k, int batch) {
     if (m->flavour != PGB_NTT120 || m->log_n < 10 || m->log_n > 12) return false;
-    if (getenv("PGB_NO_GADGET")) return false;
+    if (opt_on(m, PGB_OPT_NO_GADGET)) return false;
     const int planes = R > cols_out ? R : cols_out;
     if ((size_t)planes * m->n * 4 > (size_t)(96 << 10)) return false;
     if (cols_out < 1 || cols_out > 4 || R < 1 || R > 8) return false;
@@ -798,9 +796,15 @@ int ntt120_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_co
     const int S = C / cols_out;
     if (dsize < 1) dsize = 1;
     if (dsize == 1) key_rows = R;
-    // workspace: [collapsed key | key coefficients (i128) | key_bits]
+    // workspace: [collapsed key | key coefficients (i128) | key_bits].  For a PINNED key (pgb_gadget_key_pin) the collapsed key and the bit
+    // bound live in the module's key cache and the three pre-pass launches below run once, not once per call.
     const uint64_t ck_bytes = (uint64_t)R * cols_out * poly_bytes, key_bytes = (uint64_t)key_rows * C * poly_bytes;
-    const uint64_t need = ck_bytes + key_bytes + 256;
+    const uint64_t sig[KEY_SIG_WORDS] = {1, (uint64_t)R, (uint64_t)C, (uint64_t)cols_out, (uint64_t)base2k, (uint64_t)dsize, (uint64_t)a_size,
+                                         (uint64_t)key_rows, (uint64_t)group_limit, (uint64_t)row_cols};
+    const bool pinned = key_is_pinned(m, pmat);
+    char *cached = pinned ? (char *)key_cache_find(m, pmat, sig) : nullptr;
+    const bool have = cached != nullptr;
+    const uint64_t need = have ? 0 : (pinned ? key_bytes : ck_bytes + key_bytes + 256);
     if (m->aux_len < need) {
         if (m->aux_ws) {
             PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
@@ -811,8 +815,10 @@ int ntt120_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_co
         PGB_CHECK_CUDA(cudaMalloc(&m->aux_ws, need));
         m->aux_len = need;
     }
-    char *ck = (char *)m->aux_ws, *kcoef = ck + ck_bytes;
-    int *key_bits = (int *)(kcoef + key_bytes);
+    if (pinned && !have) PGB_TRY(key_cache_insert(m, pmat, key_bytes, sig, ck_bytes + 256, (void **)&cached));
+    char *ck = pinned ? cached : (char *)m->aux_ws;
+    char *kcoef = pinned ? (char *)m->aux_ws : ck + ck_bytes;
+    int *key_bits = pinned ? (int *)(cached + ck_bytes) : (int *)(kcoef + key_bytes);
     CollapseArgs2 ca;
     memset(&ca, 0, sizeof ca);
     ca.pmat = pmat; ca.out = (uint32_t *)ck; ca.n = (int)n; ca.R = R; ca.C = C; ca.cols_out = cols_out; ca.S = S;
@@ -832,11 +838,13 @@ int ntt120_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_co
         if (jl >= group || src >= key_rows || jm < 0) jm = 0; // this limb takes no part: its collapsed key is zero
         ca.src_row[r] = (signed char)(jm ? src : 0); ca.di[r] = (signed char)(jm ? di : 0); ca.jmax[r] = (signed char)jm;
     }
-    { ProfScope _ps(m, PROF_OTHER);
-    gadget_collapse_key_kernel<<<dim3(((unsigned)(n / 4) + 255) / 256, R * cols_out, 4), 256, 0, m->stream>>>(ca);
+    if (!have) {
+        { ProfScope _ps(m, PROF_OTHER);
+        gadget_collapse_key_kernel<<<dim3(((unsigned)(n / 4) + 255) / 256, R * cols_out, 4), 256, 0, m->stream>>>(ca);
+        }
+        PGB_CHECK_CUDA(cudaGetLastError());
+        PGB_TRY(ntt120_key_max_bits(m, pmat, key_rows * C, kcoef, key_bits));
     }
-    PGB_CHECK_CUDA(cudaGetLastError());
-    PGB_TRY(ntt120_key_max_bits(m, pmat, key_rows * C, kcoef, key_bits));
 
     GadgetArgs p;
     memset(&p, 0, sizeof p);

@@ -123,20 +123,39 @@ int ntt120_vmp(pgb_module *m, const char *a, uint64_t a_bs, char *res, uint64_t 
     VmpArgs p = {a, a_bs, res, res_bs, pm, pm_bs, (uint32_t)(m->n / 4), row_max, C, col0, ncols_out};
     const uint32_t words = (uint32_t)m->n; // uint4 words per poly
     dim3 block(256);
-    static int ct_sel = getenv("PGB_VMP_CT") ? atoi(getenv("PGB_VMP_CT")) : 4;
+    const int ct_sel = (int)m->opt[PGB_OPT_VMP_CT];
     const uint64_t key_bytes = (uint64_t)row_max * C * 16 * m->n;
-    if (pm_bs == 0 && batch >= 4 && key_bytes >= ((uint64_t)48 << 20) && !getenv("PGB_VMP_NO_BT")) {
+    if (pm_bs == 0 && batch >= 4 && key_bytes >= ((uint64_t)48 << 20) && !opt_on(m, PGB_OPT_VMP_NO_BT)) {
         ProfScope _ps(m, PROF_VMP);
         dim3 grid((words + 255) / 256, (ncols_out + 1) / 2, (batch + 3) / 4);
         ntt120_vmp_bt_kernel<2, 4><<<grid, block, 0, m->stream>>>(p, batch);
         PGB_CHECK_CUDA(cudaGetLastError());
         return PGB_OK;
     }
+    // Output polys per thread: 4 halves the re-reads of `a` (L2 hits), 2 gives twice the CTAs at two thirds of the registers.  A launch of
+    // a few waves pays for every started wave, so the variant whose whole waves cover the fewest bytes wins: e.g. one product of the
+    // sweep's largest shape [14, 31, 1, 2, 32] is 2.3 waves of CT = 4 (3 CTAs/SM) but 2.8 waves of CT = 2 (5 CTAs/SM): 80 % vs 97 % useful.
+    int ct = ct_sel;
+    if (ct_sel == 4 && ncols_out > 2) {
+        static int occ_dev[32][2] = {};
+        int *occ = occ_dev[m->device & 31];
+        if (!occ[0]) {
+            PGB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], ntt120_vmp_kernel<2>, 256, 0));
+            PGB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], ntt120_vmp_kernel<4>, 256, 0));
+        }
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+        const uint64_t xb = (words + 255) / 256;
+        const uint64_t items2 = xb * ((ncols_out + 1) / 2) * batch, items4 = xb * ((ncols_out + 3) / 4) * batch;
+        const uint64_t slots2 = (uint64_t)sms * occ[0], slots4 = (uint64_t)sms * occ[1];
+        const uint64_t cost2 = div_ceil64(items2, slots2) * slots2 * 2, cost4 = div_ceil64(items4, slots4) * slots4 * 4;
+        if (items4 < 16 * slots4 && cost2 < cost4) ct = 2; // many waves: quantisation is noise, keep the variant with fewer re-reads
+    }
     { ProfScope _ps(m, PROF_VMP);
-    if (ct_sel == 2 || ncols_out <= 2) {
+    if (ct == 2 || ncols_out <= 2) {
         dim3 grid((words + 255) / 256, (ncols_out + 1) / 2, batch);
         ntt120_vmp_kernel<2><<<grid, block, 0, m->stream>>>(p);
-    } else if (ct_sel == 8 && ncols_out >= 8) {
+    } else if (ct == 8 && ncols_out >= 8) {
         dim3 grid((words + 255) / 256, (ncols_out + 7) / 8, batch);
         ntt120_vmp_kernel<8><<<grid, block, 0, m->stream>>>(p);
     } else {

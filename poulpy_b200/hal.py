@@ -19,6 +19,9 @@ LIB_PATH = os.path.join(_HERE, "libpoulpy_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "poulpy_b200.h")
 
 NTT120, FFT64 = 0, 1
+# pgb_option (include/poulpy_b200.h)
+(OPT_NO_FUSION, OPT_NO_GADGET, OPT_NO_COLLAPSE, OPT_CGGI_VARIANT, OPT_CGGI_BLOCK_BT1, OPT_VMP_NO_BT, OPT_VMP_CT, OPT_GADGET_MB,
+ OPT_HOST_CHUNK_MB, OPT_CGGI_NTT_PRIMES) = range(10)
 Q = (1073479681, 1071513601, 1070727169, 1068236801)
 
 
@@ -65,6 +68,9 @@ def lib():
         _lib.pgb_recycle_device_bytes.argtypes = [C.c_void_p, C.c_size_t]
         _lib.pgb_module_new.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         _lib.pgb_module_destroy.argtypes = [C.c_void_p]
+        _lib.pgb_module_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int64]
+        _lib.pgb_module_get_option.argtypes = [C.c_void_p, C.c_int]
+        _lib.pgb_module_get_option.restype = C.c_int64
         _lib.pgb_module_launch_count.restype = C.c_uint64
         _lib.pgb_module_launch_count.argtypes = [C.c_void_p]
         _lib.pgb_module_set_stream.argtypes = [C.c_void_p, C.c_void_p]
@@ -101,10 +107,12 @@ class DevBuf:
     again after a device-wide synchronisation and a zero fill (pgb_recycle_device_bytes), so loops that allocate their temporaries per
     call do not pay cudaMalloc / cudaFree."""
 
-    def __init__(self, nbytes, managed=False):
+    def __init__(self, nbytes, managed=False, device=None):
         self.nbytes = int(nbytes)
         self.managed = managed
-        self._key = None if managed else (lib().pgb_current_device(), self.nbytes)
+        self.device = lib().pgb_current_device() if device is None else int(device)
+        self._bind()
+        self._key = None if managed else (self.device, self.nbytes)
         free = None if managed else _POOL.get(self._key)
         if free:
             self.ptr = free.pop()
@@ -118,6 +126,11 @@ class DevBuf:
             self.ptr = f(self.nbytes)
         if not self.ptr:
             raise PoulpyError(f"device allocation of {nbytes} bytes failed")
+
+    def _bind(self):
+        """The allocation / copy helpers act on the current device: select this buffer's."""
+        if lib().pgb_current_device() != self.device:
+            _check(lib().pgb_set_device(C.c_int(self.device)))
 
     def __del__(self):
         try:
@@ -136,11 +149,13 @@ class DevBuf:
     def upload(self, arr: np.ndarray, offset=0):
         arr = np.ascontiguousarray(arr)
         assert offset + arr.nbytes <= self.nbytes
+        self._bind()
         _check(lib().pgb_memcpy_h2d(C.c_void_p(self.ptr + offset), C.c_void_p(arr.ctypes.data), arr.nbytes))
 
     def download(self, dtype, shape, offset=0):
         out = np.empty(shape, dtype=dtype)
         assert offset + out.nbytes <= self.nbytes
+        self._bind()
         _check(lib().pgb_memcpy_d2h(C.c_void_p(out.ctypes.data), C.c_void_p(self.ptr + offset), out.nbytes))
         return out
 
@@ -242,7 +257,11 @@ class Module:
 
     # --- allocation / transfer ---------------------------------------------------------------------------------
     def _buf(self, nbytes):
-        return DevBuf(nbytes, managed=self.managed)
+        return DevBuf(nbytes, managed=self.managed, device=self.device)
+
+    def set_option(self, option, value):
+        """pgb_module_set_option (route / tuning knobs; include/poulpy_b200.h pgb_option)."""
+        _check(lib().pgb_module_set_option(self._h, C.c_int(option), C.c_int64(int(value))))
 
     def _scratch(self, need):
         """Grow-only scratch owned by the module, handed to every call that was not given one: the calls of one module are ordered on
@@ -250,7 +269,7 @@ class Module:
         c = getattr(self, "_scratch_cache", None)
         if c is None or c.nbytes < need:
             self._scratch_cache = c = None  # cudaFree of the old block synchronises the device
-            self._scratch_cache = c = DevBuf(max(int(need), 1 << 20))
+            self._scratch_cache = c = DevBuf(max(int(need), 1 << 20), device=self.device)
         return c
 
     def vec_znx_alloc(self, cols, size, batch=1):
@@ -507,6 +526,15 @@ class Module:
                                                        C.c_size_t(scratch.nbytes)))
         return scratch
 
+    def gadget_key_pin(self, key: VmpPMat):
+        """pgb_gadget_key_pin: promise that the key's bytes stay unchanged, so its gadget-kernel forms are derived once."""
+        ks = key.struct()
+        _check(lib().pgb_gadget_key_pin(self._h, C.byref(ks)))
+
+    def gadget_key_unpin(self, key: VmpPMat):
+        ks = key.struct()
+        _check(lib().pgb_gadget_key_unpin(self._h, C.byref(ks)))
+
     def glwe_keyswitch_host(self, res: np.ndarray, res_base2k, a: np.ndarray, a_base2k, key: VmpPMat, key_base2k, dsize=1):
         """res/a: host int64 arrays (batch, size, cols, n); synchronous, copies included (the e2e path)."""
         B, a_size, a_cols, n = a.shape
@@ -708,6 +736,18 @@ class Module:
         return scratch
 
 
+    def cggi_blind_rotate_host(self, res: np.ndarray, lwe: np.ndarray, lwe_base2k, lut: VecZnx, brk: VmpPMat, x_pow_a: SvpPPol, block_size,
+                               base2k, rot_left=True):
+        """res: host int64 (batch, res_size, rank+1, n); lwe: host int64 (batch, lwe_size, 1, n_lwe+1) NOT yet mod-switched; synchronous,
+        copies included (the e2e path of the blind rotation)."""
+        B, lwe_size, _, len_ = lwe.shape
+        assert res.shape[0] == B and res.flags["C_CONTIGUOUS"] and lwe.flags["C_CONTIGUOUS"]
+        lv, bs, xp = lut.struct(), brk.struct(), x_pow_a.struct()
+        _check(lib().pgb_cggi_blind_rotate_host(self._h, C.c_void_p(res.ctypes.data), _u64(res.shape[2] - 1), _u64(res.shape[1]),
+                                                C.c_void_p(lwe.ctypes.data), _u64(len_ - 1), _u64(lwe_size), _u64(lwe_base2k),
+                                                C.c_int(1 if rot_left else 0), C.byref(lv), C.byref(bs), C.byref(xp), _u64(block_size),
+                                                _u64(base2k), _u64(B)))
+
     def cggi_blind_rotate_extended(self, res: VecZnx, lwe_2n: DevBuf, n_lwe, luts: VecZnx, ext, brk: VmpPMat, x_pow_a: SvpPPol, block_size,
                                    base2k, scratch: DevBuf = None):
         """execute_block_binary_extended (algorithm.rs:121-273); luts: VecZnx(1 col) with `ext` batch items (LookupTable.data), lwe_2n
@@ -725,7 +765,7 @@ class Module:
 
     def cggi_mod_switch_2n(self, lwe_dev: DevBuf, batch, n_lwe, size, lwe_base2k, two_n_domain, rot_left=True) -> DevBuf:
         """mod_switch_2n of `batch` LWEs stored as (batch, size, 1, n_lwe + 1) int64 on the device -> DevBuf int64 [batch][n_lwe + 1]."""
-        out = DevBuf(batch * (n_lwe + 1) * 8)
+        out = DevBuf(batch * (n_lwe + 1) * 8, device=self.device)
         lv = _VZ(lwe_dev.ptr, n_lwe + 1, 1, size, size)
         bt = _BT(batch, 0, size * (n_lwe + 1) * 8, 0)
         _check(lib().pgb_cggi_mod_switch_2n_batched(self._h, C.c_void_p(out.ptr), C.byref(lv), _u64(lwe_base2k), _u64(two_n_domain),

@@ -19,9 +19,19 @@ def max_over_ranks(value: float, device=None) -> float:
 
     if not (dist.is_available() and dist.is_initialized()):
         return float(value)
-    t = torch.tensor([value], dtype=torch.float64, device=device if device is not None else "cpu")
+    t = torch.tensor([value], dtype=torch.float64, device=device if device is not None else _collective_device())
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def _collective_device():
+    """Where the tensors of a collective must live: the current CUDA device under NCCL (which cannot move host tensors), the host under gloo."""
+    import torch
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
 
 
 def gather_shards(local, total: int):
@@ -61,3 +71,38 @@ def broadcast_prepared(module, buf, src: int = 0):
     t = torch.as_tensor(_DeviceBytes(buf.ptr, buf.nbytes), device=torch.device("cuda", torch.cuda.current_device()))
     dist.broadcast(t, src=src)
     torch.cuda.synchronize()
+
+
+def replicate_prepared(prepare, broadcast=None, src: int = 0) -> str:
+    """Prepare key material on rank `src` and replicate it, with every rank taking the SAME branch whatever happens on `src`:
+
+        rank src runs prepare() and catches its failure -> all ranks all-reduce(MIN) a status flag ->
+        flag 1: every rank runs broadcast() (the collective that ships the prepared bytes)   -> "broadcast"
+        flag 0: nobody enters the broadcast; every rank runs prepare() locally (rank src again: its error, if it persists, is raised
+                there and nowhere is a rank left waiting inside a collective)                   -> "local"
+
+    Without a process group: prepare() only -> "local".  (the previous bench code let rank 0 skip the broadcast on an
+    exception while the other ranks blocked in it.)"""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        prepare()
+        return "local"
+    ok = 1
+    if dist.get_rank() == src:
+        try:
+            prepare()
+        except Exception as e:  # noqa: BLE001 -- reported through the flag; raised again below on the local path
+            import sys
+
+            print(f"[sharding] prepare failed on rank {src}: {e!r}; every rank prepares locally", file=sys.stderr)
+            ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=_collective_device())
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 1:
+        if broadcast is not None:
+            broadcast()
+        return "broadcast"
+    prepare()
+    return "local"

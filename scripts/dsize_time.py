@@ -14,8 +14,7 @@ a = m.vec_znx_alloc(2, 4, B)
 a.buf.upload(rng.integers(-(1 << 17), 1 << 17, size=(64 * 4 * 2 * n,), dtype=np.int64))
 r = m.vec_znx_alloc(2, 4, B)
 for env in (None, "1"):
-    if env: os.environ["PGB_NO_FUSION"] = "1"
-    else: os.environ.pop("PGB_NO_FUSION", None)
+    m.set_option(pb.hal.OPT_NO_FUSION, 1 if env else 0)
     sc = None
     for _ in range(3): sc = m.glwe_keyswitch(r, k, a, k, pm, k, dsize, sc)
     torch.cuda.synchronize()

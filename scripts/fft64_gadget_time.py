@@ -32,10 +32,9 @@ for name, n, ext in (("keyswitch n=4096", 4096, False), ("ext product n=2048", 2
     r = m.vec_znx_alloc(2, 3, B)
     fn = m.glwe_external_product if ext else m.glwe_keyswitch
     for env in (None, "1"):
-        if env: os.environ["PGB_NO_FUSION"] = "1"
-        else: os.environ.pop("PGB_NO_FUSION", None)
+        m.set_option(pb.hal.OPT_NO_FUSION, 1 if env else 0)
         sc = [None]
         def f(): sc[0] = fn(r, k, a, k, pm, k, 1, sc[0])
         ms = timeit(f)
         print(name, "unfused" if env else "fused  ", "ms/batch", round(ms, 4), "per s", round(B / ms * 1e3))
-    os.environ.pop("PGB_NO_FUSION", None)
+    m.set_option(pb.hal.OPT_NO_FUSION, 0)

@@ -383,16 +383,15 @@ def test_fft64_gadget_bench_shape():
     a = fill_uniform(rng, (batch, 3, 2, n), k)
     want = np.zeros((batch, 3, 2, n), dtype=np.int64)
     o.glwe_keyswitch_batch(want, k, a, k, po, k)
-    for env in (None, "1"):
-        if env:
-            os.environ["PGB_NO_FUSION"] = env
+    for no_fusion in (0, 1):
+        g.set_option(pb.hal.OPT_NO_FUSION, no_fusion)
         try:
             res_g = g.vec_znx_alloc(2, 3, batch)
             g.glwe_keyswitch(res_g, k, g.vec_znx_from_numpy(a), k, pg, k)
             g.sync()
         finally:
-            os.environ.pop("PGB_NO_FUSION", None)
-        assert np.array_equal(g.vec_znx_to_numpy(res_g), want), env
+            g.set_option(pb.hal.OPT_NO_FUSION, 0)
+        assert np.array_equal(g.vec_znx_to_numpy(res_g), want), no_fusion
 
 
 @pytest.mark.parametrize("fl", FLAVOURS)
@@ -512,3 +511,85 @@ def test_fft64_gadget_kernel_dsize2(n):
         got = g.vec_znx_to_numpy(res_g)
         bad = [b for b in range(batch) if not np.array_equal(got[b], want[b])]
         assert not bad, ("ep", rank, a_size, g_size, res_size, bad)
+
+
+@pytest.mark.parametrize("fl", FLAVOURS)
+@pytest.mark.parametrize("dsize", [1, 2])
+@pytest.mark.parametrize("ext", [False, True])
+def test_in_place_with_flagged_ciphertext(fl, dsize, ext):
+    """The `_assign` forms (res IS a: keyswitching/glwe.rs:111-165, external_product/glwe.rs:143-195) through every route, with one
+    ciphertext outside the collapsed-key bound: with dsize > 1 a flagged ciphertext sends the WHOLE batch to the limb-wise sequence, which
+    must still find intact inputs although the single kernel has already produced outputs for the others (core.cu:169)."""
+    n, k, batch, size = 1024, 18, 7, 4
+    g, o = pb.Module(n, fl), O.OracleModule(n, fl)
+    rng = np.random.default_rng(1700 + fl + 2 * dsize + ext)
+    cols_in = 2 if ext else 1
+    pg, po = _key(g, o, rng, -(-size // dsize), cols_in, 2, size, k)
+    for flagged in (False, True):
+        a = fill_uniform(rng, (batch, size, 2, n), k)
+        if flagged and fl == pb.NTT120:
+            a[3, 0, 1, 5] = 1 << 61
+        want = np.zeros_like(a)
+        (o.glwe_external_product_batch if ext else o.glwe_keyswitch_batch)(want, k, a, k, po, k, dsize)
+        a_g = g.vec_znx_from_numpy(a)
+        (g.glwe_external_product if ext else g.glwe_keyswitch)(a_g, k, a_g, k, pg, k, dsize)
+        g.sync()
+        got = g.vec_znx_to_numpy(a_g)
+        bad = [b for b in range(batch) if not np.array_equal(got[b], want[b])]
+        assert not bad, (flagged, bad)
+
+
+@pytest.mark.parametrize("fl", FLAVOURS)
+def test_partial_overlap_is_rejected(fl):
+    """backend_safety_contract.md "Aliasing": overlapping operands that are not the same ciphertexts return PGB_ERR_ALIAS (-3) instead of
+    computing garbage: shifted views of one buffer for the compositions, and any overlap for the out-of-place-only helpers."""
+    n, k, batch = 1024, 18, 4
+    g, o = pb.Module(n, fl), O.OracleModule(n, fl)
+    rng = np.random.default_rng(1750)
+    pg, _ = _key(g, o, rng, 3, 1, 2, 3, k)
+    big = g.vec_znx_alloc(2, 3, batch + 1)
+    item = big.batch_stride
+    a = pb.hal.VecZnx(big.buf, n, 2, 3, offset=0, batch=batch, batch_stride=item)
+    r = pb.hal.VecZnx(big.buf, n, 2, 3, offset=item // 2, batch=batch, batch_stride=item)
+    for fn in (lambda: g.glwe_keyswitch(r, k, a, k, pg, k), lambda: g.vec_znx_automorphism(3, r, 0, a, 0),
+               lambda: g.vec_znx_rotate(3, r, 0, a, 0), lambda: g.vec_znx_mul_xp_minus_one(3, a, 0, a, 1)):
+        with pytest.raises(pb.PoulpyError, match=r"\[-3\]"):
+            fn()
+
+
+@pytest.mark.parametrize("fl", FLAVOURS)
+def test_pinned_key_cache(fl):
+    """pgb_gadget_key_pin: the per-key pre-passes of the single-kernel gadget product run once for a pinned key (fewer launches per call,
+    identical results), a vmp_prepare into the pinned key drops the cached forms (the next call sees the NEW key), two call shapes on one
+    pinned key keep separate forms, and unpin restores the per-call behaviour."""
+    n, k, batch = 1024, 18, 5
+    g, o = pb.Module(n, fl), O.OracleModule(n, fl)
+    rng = np.random.default_rng(1800 + fl)
+    mats = [fill_uniform(rng, (3, 1, 4, 2, n), k) for _ in range(2)]
+    pg, po = g.vmp_pmat_alloc(3, 1, 2, 4), o.vmp_pmat_alloc(3, 1, 2, 4)
+
+    def run(a_size):
+        a = fill_uniform(rng, (batch, a_size, 2, n), k)
+        want = np.zeros((batch, a_size, 2, n), dtype=np.int64)
+        o.glwe_keyswitch_batch(want, k, a, k, po, k, 1)
+        res = g.vec_znx_from_numpy(fill_uniform(rng, want.shape, k))
+        a_g = g.vec_znx_from_numpy(a)
+        l0 = g.launch_count
+        g.glwe_keyswitch(res, k, a_g, k, pg, k, 1)
+        g.sync()
+        assert np.array_equal(g.vec_znx_to_numpy(res), want)
+        return g.launch_count - l0
+
+    g.vmp_prepare(pg, g.mat_znx_from_numpy(mats[0]))
+    o.vmp_prepare(po, mats[0])
+    unpinned = run(3)
+    g.gadget_key_pin(pg)
+    first, second = run(3), run(3)
+    assert first == unpinned and second < first, (unpinned, first, second)   # pre-passes only on the first pinned call
+    other_first, other_second = run(2), run(2)                                # another call shape: its own cached form
+    assert other_second < other_first and run(3) == second
+    g.vmp_prepare(pg, g.mat_znx_from_numpy(mats[1]))                          # new key bytes in the pinned buffer
+    o.vmp_prepare(po, mats[1])
+    assert run(3) == first and run(3) == second
+    g.gadget_key_unpin(pg)
+    assert run(3) == unpinned

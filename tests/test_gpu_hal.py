@@ -520,8 +520,7 @@ def test_vmp_batch_tiled_large_key():
     g.vec_znx_dft_apply(1, 0, adg, 0, a_g, 0)
     outs = []
     for no_bt in (False, True):
-        if no_bt:
-            os.environ["PGB_VMP_NO_BT"] = "1"
+        g.set_option(pb.hal.OPT_VMP_NO_BT, int(no_bt))
         try:
             rg = g.vec_znx_dft_alloc(cols_out, size, batch)
             rg.buf.upload(rng.integers(0, 255, rg.buf.nbytes, dtype=np.uint8))
@@ -529,7 +528,7 @@ def test_vmp_batch_tiled_large_key():
             g.sync()
             outs.append(rg.buf.download(np.uint32, (rg.buf.nbytes // 4,)).copy())
         finally:
-            os.environ.pop("PGB_VMP_NO_BT", None)
+            g.set_option(pb.hal.OPT_VMP_NO_BT, 0)
     assert np.array_equal(outs[0], outs[1])
     o.vmp_prepare(pmo, mat)
     ado, ro = o.vec_znx_dft_alloc(1, rows), o.vec_znx_dft_alloc(cols_out, size)

@@ -84,3 +84,55 @@ def test_broadcast_prepared_is_a_noop_without_a_group():
     assert broadcast_prepared(None, None) is None
     view = _DeviceBytes(0x7F0000000000, 4096).__cuda_array_interface__
     assert view["shape"] == (4096,) and view["typestr"] == "|u1" and view["data"] == (0x7F0000000000, False)
+
+
+def _replicate_worker(rank, world, port, fail_first, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from poulpy_b200.sharding import max_over_ranks, replicate_prepared
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    key = torch.zeros(4, dtype=torch.int64)
+    calls = {"prepare": 0, "broadcast": 0}
+
+    def prepare():
+        calls["prepare"] += 1
+        if fail_first and rank == 0 and calls["prepare"] == 1:
+            raise RuntimeError("injected prepare failure on the source rank")
+        key[:] = torch.arange(4) + 10
+
+    def broadcast():
+        calls["broadcast"] += 1
+        dist.broadcast(key, src=0)
+
+    how = replicate_prepared(prepare, broadcast)
+    t = max_over_ranks(float(rank))  # default device under gloo: the host
+    q.put((rank, how, calls["prepare"], calls["broadcast"], key.tolist(), t))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_first", [False, True])
+def test_replicate_prepared_takes_one_branch_on_every_rank(fail_first):
+    """Key replication: rank 0 prepares and broadcasts; when rank 0's prepare raises, NO rank enters the broadcast (nobody hangs) and every
+    rank prepares locally -- the status flag makes the branch symmetric."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_replicate_worker, args=(r, 2, port, fail_first, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, how, n_prep, n_bc, key, t in got:
+        assert key == [10, 11, 12, 13] and t == 1.0
+        if fail_first:
+            assert how == "local" and n_bc == 0 and n_prep == (2 if rank == 0 else 1)
+        else:
+            assert how == "broadcast" and n_bc == 1 and n_prep == (1 if rank == 0 else 0)
