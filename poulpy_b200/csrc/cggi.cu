@@ -464,12 +464,24 @@ int cggi_blind_rotate_impl(pgb_module *m, pgb_vec_znx *res, const int64_t *lwe_2
     const uint64_t lwe_stride = n_lwe + 1;
 
     // out.zero(); out[0] = X^b * LUT (algorithm.rs:317-320)
-    PGB_CHECK_CUDA(cudaMemset2DAsync(res->data, bt->stride_res, 0, n * cols * res->size * 8, B, m->stream));
-    {
+    auto init_acc = [&]() -> int {
+        PGB_CHECK_CUDA(cudaMemset2DAsync(res->data, bt->stride_res, 0, n * cols * res->size * 8, B, m->stream));
         const uint64_t mn = umin64(res->size, lut->size);
         LimbSet R = {(char *)res->data, res->cols * n * 8, bt->stride_res};
         LimbSet L = {(char *)lut->data, lut->cols * n * 8, 0};
-        PGB_TRY(znx_rotate(m, R, L, 0, (const long long *)lwe_2n, (uint32_t)lwe_stride, (uint32_t)mn, (uint32_t)B));
+        return znx_rotate(m, R, L, 0, (const long long *)lwe_2n, (uint32_t)lwe_stride, (uint32_t)mn, (uint32_t)B);
+    };
+    PGB_TRY(init_acc());
+    if (m->flavour == PGB_NTT120 && !opt_on(m, PGB_OPT_NO_FUSION) && bt->stride_res % 8 == 0 &&
+        cggi_ntt_fused_supported(m, cols, dnum, bsize, block_size) && lut->cols == 1) {
+        // whole rotation in one launch on two of the four primes when the device-measured bound allows (cggi_ntt_fused.cu); otherwise,
+        // or when the kernel found an accumulator coefficient outside the bound, the four-prime sequence below redoes the batch
+        bool handled = false;
+        PGB_TRY(cggi_fused_ntt120(m, (long long *)res->data, bt->stride_res / 8, (const long long *)lwe_2n, lwe_stride, (const char *)brk->data,
+                                  brk_bytes, (const char *)x_pow_a->data, (int)n_lwe, (int)block_size, (int)base2k, (int)cols, (int)dnum,
+                                  (int)bsize, (int)res->size, (int)B, (const long long *)lut->data, n * umin64(res->size, lut->size), &handled));
+        if (handled) return PGB_OK;
+        PGB_TRY(init_acc());
     }
     if (cggi_fused_supported(m, cols, dnum, bsize) && (R_ok(cols, dnum)) && !opt_on(m, PGB_OPT_NO_FUSION)) {
         PGB_REQUIRE(bt->stride_res % 8 == 0, "cggi_blind_rotate: res stride must be a multiple of 8 bytes");

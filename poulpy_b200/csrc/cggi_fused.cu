@@ -10,6 +10,7 @@
 
 #include "internal.h"
 #include "fft64.cuh"
+#include "tma.cuh"
 
 struct CggiFusedArgs {
     long long *res;          uint64_t res_stride;   // GLWE VecZnx(cols, out_size), i64 words between ciphertexts
@@ -425,31 +426,6 @@ template <int L> struct SmInvP<L, -1> {
 // rows of one output poly of one key = RT contiguous chunks of 8n bytes, completion on an mbarrier), running ahead of the compute
 // threads across the transform phases.  A thread owns one frequency of TWO ciphertexts (g and g + G/2): a key value read from the
 // tile feeds both, and the 2 x (RT + C) complex values it needs stay in registers for the whole block.
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
-                 "r"(bar)
-                 : "memory");
-}
-
 template <int LM, int G, int RT, int CT, int NSTAGE> __global__ void __launch_bounds__(512, 1)
 cggi_fused3_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, const double2 *__restrict__ twi_g, const double2 *__restrict__ twlf_g,
                          const double2 *__restrict__ twli_g, double inv_m) {

@@ -78,6 +78,12 @@ bool cggi_fused_supported(const pgb_module *m, uint64_t cols, uint64_t dnum, uin
 int cggi_fused_fft64(pgb_module *m, long long *res, uint64_t res_stride_words, const long long *lwe, uint64_t lwe_stride, const double *brk,
                      uint64_t brk_doubles, const double *xpa, int n_lwe, int block_size, int base2k, int cols, int dnum, int brk_size,
                      int out_size, int batch);
+// cggi_ntt_fused.cu: whole-rotation NTT120 kernel with two primes when the device-measured bound allows; *handled = false -> caller runs
+// the four-prime limb-wise path (after re-initialising res)
+bool cggi_ntt_fused_supported(const pgb_module *m, uint64_t cols, uint64_t dnum, uint64_t brk_size, uint64_t block_size);
+int cggi_fused_ntt120(pgb_module *m, long long *res, uint64_t res_stride_words, const long long *lwe, uint64_t lwe_stride, const char *brk,
+                      uint64_t brk_bytes, const char *xpa, int n_lwe, int block_size, int base2k, int cols, int dnum, int brk_size,
+                      int out_size, int batch, const long long *lut, uint64_t lut_words, bool *handled);
 // big.cu
 int big_normalize(pgb_module *m, bool big_is_i128, LimbSet res, int res_size, int res_k, int64_t res_offset, LimbSet a, int a_size,
                   int a_k, int op, uint32_t batch);
@@ -98,6 +104,7 @@ enum { KEY_SIG_WORDS = 10 };
 bool key_is_pinned(const pgb_module *m, const void *key);
 void *key_cache_find(pgb_module *m, const void *key, const uint64_t *sig);
 int key_cache_insert(pgb_module *m, const void *key, uint64_t key_len, const uint64_t *sig, size_t bytes, void **out);
+int64_t *key_cache_host_slot(pgb_module *m, const void *key, uint64_t key_len, const uint64_t *sig);
 void key_cache_invalidate(pgb_module *m, const void *p, uint64_t len);
 void key_cache_destroy(pgb_module *m);
 // core.cu: lazily grown device workspace of the host front ends; whether a host pointer is page-locked

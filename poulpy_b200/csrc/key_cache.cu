@@ -14,7 +14,8 @@ struct KeyCacheEntry {
     const char *key;
     uint64_t key_len;
     uint64_t sig[KEY_SIG_WORDS];
-    void *dev;
+    void *dev;       // device-resident cached form (may be null for host-only entries)
+    int64_t host_val; // host-resident cached scalar (e.g. the bit bound of the key's coefficients); 0 = not set
 };
 struct KeyCache {
     std::vector<std::pair<const char *, uint64_t>> pinned; // (data pointer, bytes)
@@ -49,11 +50,27 @@ int key_cache_insert(pgb_module *m, const void *key, uint64_t key_len, const uin
     e.key_len = key_len;
     memcpy(e.sig, sig, sizeof e.sig);
     e.dev = nullptr;
+    e.host_val = 0;
     PGB_CHECK_CUDA(cudaSetDevice(m->device));
     PGB_CHECK_CUDA(cudaMalloc(&e.dev, bytes));
     c->entries.push_back(e);
     *out = e.dev;
     return PGB_OK;
+}
+
+// host-only entry of a pinned key (created on first use): a scalar derived from the key that the HOST needs before a launch
+int64_t *key_cache_host_slot(pgb_module *m, const void *key, uint64_t key_len, const uint64_t *sig) {
+    KeyCache *c = cache_of(m, true);
+    for (auto &e : c->entries)
+        if (e.key == (const char *)key && memcmp(e.sig, sig, sizeof e.sig) == 0) return &e.host_val;
+    KeyCacheEntry e;
+    e.key = (const char *)key;
+    e.key_len = key_len;
+    memcpy(e.sig, sig, sizeof e.sig);
+    e.dev = nullptr;
+    e.host_val = 0;
+    c->entries.push_back(e);
+    return &c->entries.back().host_val;
 }
 
 // drops every cached form of a key whose bytes overlap [p, p + len)
@@ -68,7 +85,7 @@ void key_cache_invalidate(pgb_module *m, const void *p, uint64_t len) {
                 cudaStreamSynchronize(m->stream); // a kernel reading the cached form may still be in flight
                 synced = true;
             }
-            cudaFree(e.dev);
+            if (e.dev) cudaFree(e.dev);
             c->entries.erase(c->entries.begin() + (long)i);
         } else {
             i++;
@@ -79,7 +96,8 @@ void key_cache_invalidate(pgb_module *m, const void *p, uint64_t len) {
 void key_cache_destroy(pgb_module *m) {
     KeyCache *c = m->key_cache;
     if (!c) return;
-    for (const auto &e : c->entries) cudaFree(e.dev);
+    for (const auto &e : c->entries)
+        if (e.dev) cudaFree(e.dev);
     delete c;
     m->key_cache = nullptr;
 }

@@ -1,12 +1,15 @@
 import sys, time, ctypes as C
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import poulpy_b200 as pb
 lib = pb.lib()
 rng = np.random.default_rng(5)
 stream = torch.cuda.Stream()
-for fl, nm in ((pb.FFT64, "fft64"),):
-    for B in (592, 2368, 4736):
+import os
+FLS = {"fft64": ((pb.FFT64, "fft64"),), "ntt120": ((pb.NTT120, "ntt120"),)}.get(os.environ.get("CGGI_FL", ""), ((pb.FFT64, "fft64"), (pb.NTT120, "ntt120")))
+for fl, nm in FLS:
+    for B in (592, 2368):
         n, n_lwe, rank, block, k = 512, 687, 3, 3, 18
         m = pb.Module(n, fl)
         m.set_stream(stream.cuda_stream)
@@ -29,7 +32,8 @@ for fl, nm in ((pb.FFT64, "fft64"),):
         br(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
+            l0 = m.launch_count
             e0.record(stream); br(); br(); e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 2
-        print(nm, "B", B, "ms", round(ms, 2), "bootstraps/s", round(B / ms * 1e3))
+        print(nm, "B", B, "ms", round(ms, 2), "bootstraps/s", round(B / ms * 1e3), "launches/call", (m.launch_count - l0) // 2)
