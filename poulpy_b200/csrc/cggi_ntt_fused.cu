@@ -41,7 +41,8 @@ struct CggiNttArgs {
     int n_lwe, block_size, base2k, cols, dnum, brk_size, out_size, batch;
     long long acc_limit;                             // |accumulator coefficient| must stay below this (device-checked)
     int *fail;                                       // set to 1 when a loaded coefficient is not
-    uint32_t q[2], ninv[2], ninv_sh[2];              // primes 0 / 1, n^-1 mod q (Shoup pair)
+    uint32_t q[2], qneg_inv[2];                      // primes 0 / 1, -q^-1 mod 2^32 (Montgomery)
+    uint32_t cw[2], cw_sh[2];                        // 2^64 / n mod q (Shoup pair): pays the two Montgomery reductions and the 1 / n
     uint32_t q1inv, q1inv_sh;                        // q1^-1 mod q0 (Shoup pair)
     unsigned long long Q2, half2;                    // q0 q1, (q0 q1 + 1) / 2
 };
@@ -123,24 +124,37 @@ template <int T> __device__ __forceinline__ void slot_sync(int slot) {
     else named_sync(slot + 1, T);
 }
 
+// Offset of element base + j * 2^SL inside a padded plane relative to NPAD(base), for the bases the passes use (base = (a << (SL + 3)) | b
+// with b < 2^SL): a compile-time constant per j, so a pass computes one padded address and the rest are immediates.
+template <int SL> __device__ __forceinline__ constexpr int poff(int j) {
+    return SL >= 5 ? j * ((1 << SL) + (1 << SL) / 8) : SL == 4 ? 16 * j + 4 * (j >> 1) : SL == 3 ? 8 * j + 4 * (j >> 2) : SL == 0 ? j : -1;
+}
+static_assert(poff<6>(3) == 216 && poff<3>(5) == 44 && poff<0>(7) == 7, "padded offsets");
+
 // forward passes after the top one (L0 = levels done so far); the last pass leaves canonical residues
 template <int L, int L0> struct NFwd {
     static __device__ __forceinline__ void run(uint32_t *buf, const uint2 *tw, const uint2 *twl, int t, int slot, bool valid, uint32_t q) {
         constexpr int SL = L - L0 - 3;
+        static_assert(poff<SL>(1) > 0, "stride not covered by poff");
         if (valid) {
-            const int a = t >> SL, b = t & ((1 << SL) - 1), base = (a << (SL + 3)) | b;
+            const int a = t >> SL, b = t & ((1 << SL) - 1);
+            uint32_t *pb = buf + NPAD((a << (SL + 3)) | b);
             uint32_t x[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) x[j] = buf[NPAD(base + (j << SL))];
             if (SL == 0) {
+                const uint4 u0 = reinterpret_cast<const uint4 *>(pb)[0], u1 = reinterpret_cast<const uint4 *>(pb)[1];
+                x[0] = u0.x; x[1] = u0.y; x[2] = u0.z; x[3] = u0.w; x[4] = u1.x; x[5] = u1.y; x[6] = u1.z; x[7] = u1.w;
                 ct_r8_w(x, twl, NGeo<L>::T, t, q);
 #pragma unroll
                 for (int j = 0; j < 8; j++) x[j] = csub(csub(x[j], 2 * q), q);
+                reinterpret_cast<uint4 *>(pb)[0] = make_uint4(x[0], x[1], x[2], x[3]);
+                reinterpret_cast<uint4 *>(pb)[1] = make_uint4(x[4], x[5], x[6], x[7]);
             } else {
-                ct_r8<3>(x, tw, (1u << L0) | (uint32_t)a, q);
-            }
 #pragma unroll
-            for (int j = 0; j < 8; j++) buf[NPAD(base + (j << SL))] = x[j];
+                for (int j = 0; j < 8; j++) x[j] = pb[poff<SL>(j)];
+                ct_r8<3>(x, tw, (1u << L0) | (uint32_t)a, q);
+#pragma unroll
+                for (int j = 0; j < 8; j++) pb[poff<SL>(j)] = x[j];
+            }
         }
         slot_sync<NGeo<L>::T>(slot);
         NFwd<L, (L0 + 3 < L) ? L0 + 3 : L>::run(buf, tw, twl, t, slot, valid, q);
@@ -153,14 +167,16 @@ template <int L> struct NFwd<L, L> {
 template <int L, int L0> struct NInv {
     static __device__ __forceinline__ void run(uint32_t *buf, const uint2 *tw, int t, int slot, bool valid, uint32_t q) {
         constexpr int SL = L - L0 - 3;
+        static_assert(poff<SL>(1) > 0, "stride not covered by poff");
         if (valid) {
-            const int a = t >> SL, b = t & ((1 << SL) - 1), base = (a << (SL + 3)) | b;
+            const int a = t >> SL, b = t & ((1 << SL) - 1);
+            uint32_t *pb = buf + NPAD((a << (SL + 3)) | b);
             uint32_t x[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) x[j] = buf[NPAD(base + (j << SL))];
+            for (int j = 0; j < 8; j++) x[j] = pb[poff<SL>(j)];
             gs_r8<3>(x, tw, (1u << L0) | (uint32_t)a, q);
 #pragma unroll
-            for (int j = 0; j < 8; j++) buf[NPAD(base + (j << SL))] = x[j];
+            for (int j = 0; j < 8; j++) pb[poff<SL>(j)] = x[j];
         }
         slot_sync<NGeo<L>::T>(slot);
         NInv<L, (L0 - 3 >= NGeo<L>::R0) ? L0 - 3 : -1>::run(buf, tw, t, slot, valid, q);
@@ -170,16 +186,19 @@ template <int L> struct NInv<L, -1> {
     static __device__ __forceinline__ void run(uint32_t *, const uint2 *, int, int, bool, uint32_t) {}
 };
 
-// any u64 -> [0, 2q) (one Shoup product of the high word, folded low word)
-__device__ __forceinline__ uint32_t lazy64(unsigned long long x, uint32_t q, uint32_t c32, uint32_t c32s) {
-    const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x;
-    return csub(mul_shoup(hi, c32, c32s, q) + (lo - (lo >> 30) * q), 2 * q);
+// Montgomery reduction of a u64: x * 2^-32 mod q as a value in [0, x / 2^32 + q) -- two instructions (IMAD + IMAD.WIDE) where a Shoup-style
+// reduction of a 64-bit value takes seven.  The factor 2^-32 is compensated in the constants the value is multiplied with next.
+// qneg_inv = -q^-1 mod 2^32.  x + m q is a multiple of 2^32 and < 2^64 for every x the kernel feeds (x < 2^63, m q < 2^62).
+__device__ __forceinline__ uint32_t redc64(unsigned long long x, uint32_t q, uint32_t qneg_inv) {
+    const uint32_t m = (uint32_t)x * qneg_inv;
+    return (uint32_t)((x + (unsigned long long)m * q) >> 32);
 }
 
 constexpr int CGN_COMPUTE = 512; // compute threads; warp 16 is the key-stream producer
-constexpr int CGN_BSMAX = 4;     // keys per block whose (w - 1) factors are held in registers
+constexpr int CGN_BSMAX = 4;     // keys per block whose (X^a - 1) factors are held in registers
 
-template <int L, int G, int RT, int CT, int NSTAGE> __global__ void __launch_bounds__(CGN_COMPUTE + 32, 1)
+// EXACT: RT and CT are the run-time row / output-poly counts (the BASELINE shape), so every index computation is by constants
+template <int L, int G, int RT, int CT, int NSTAGE, bool EXACT> __global__ void __launch_bounds__(CGN_COMPUTE + 32, 1)
 cggi_fused_ntt120_p2_kernel(CggiNttArgs p, const uint2 *__restrict__ twf_g, const uint2 *__restrict__ twi_g) {
     typedef NGeo<L> NG;
     constexpr int N = NG::N, T = NG::T, NT = CGN_COMPUTE, PL = NG::PLANE, NSLOT = NT / T, GH = G / 2, P = 2;
@@ -217,21 +236,32 @@ cggi_fused_ntt120_p2_kernel(CggiNttArgs p, const uint2 *__restrict__ twf_g, cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int cols = p.cols, C = cols * p.brk_size, K = p.base2k, bs = p.block_size;
+    const int cols = p.cols, C = EXACT ? CT : cols * p.brk_size, K = p.base2k, bs = p.block_size;
     const int nblk = p.n_lwe / bs, total_tiles = nblk * C * bs;
 
     // ---- producer warp: tile gk = (block, output poly c, key t) in that order -------------------------------------------------------
     if (tid >= NT) {
         if (tid == NT) {
+            int t = 0, c = 0;
+            const uint32_t *key0 = p.brk; // first key of the current block
             for (int gk = 0; gk < total_tiles; gk++) {
                 const int st = gk % NSTAGE;
-                if (gk >= NSTAGE) mbar_wait(empty_s + st * 8, (uint32_t)((gk / NSTAGE - 1) & 1));
-                const int t = gk % bs, c = (gk / bs) % C, blk = gk / (bs * C);
-                const uint32_t *src = p.brk + (size_t)(blk * bs + t) * p.brk_words + (size_t)c * 4 * N;
+                if (gk >= NSTAGE) {
+                    const uint32_t bar = empty_s + st * 8, par = (uint32_t)((gk / NSTAGE - 1) & 1);
+                    while (!mbar_test(bar, par)) __nanosleep(64); // polite: the spin would otherwise take issue slots of compute warps
+                }
+                const uint32_t *src = key0 + (size_t)t * p.brk_words + (size_t)c * 4 * N;
                 const uint32_t bar = full_s + st * 8;
                 mbar_expect_tx(bar, TILE);
 #pragma unroll
                 for (int r = 0; r < RT; r++) bulk_g2s(ring_s + (uint32_t)(st * RT + r) * CHUNK, src + (size_t)r * C * 4 * N, CHUNK, bar);
+                if (++t == bs) {
+                    t = 0;
+                    if (++c == C) {
+                        c = 0;
+                        key0 += (size_t)bs * p.brk_words;
+                    }
+                }
             }
         }
         return;
@@ -240,7 +270,7 @@ cggi_fused_ntt120_p2_kernel(CggiNttArgs p, const uint2 *__restrict__ twf_g, cons
     const int slot = tid / T, t = tid % T, lane = tid & 31;
     const int ct0 = blockIdx.x * G;
     const int gp = tid / U4, u = tid % U4, kq = u / (N / 4), f4 = u % (N / 4); // products: ciphertexts gp, gp + GH; prime kq; freqs 4 f4 ..
-    const uint32_t qk_ = p.q[kq], c32 = (uint32_t)((1ull << 32) % qk_), c32s = (uint32_t)(((unsigned long long)c32 << 32) / qk_);
+    const uint32_t qk_ = p.q[kq], qni = p.qneg_inv[kq];
     const int mn_small = min(p.brk_size, p.out_size);
     const int a_start = min(p.out_size, p.brk_size); // same-base2k plan with offset 0: limbs >= a_start only feed the carry
     int gk = 0;
@@ -265,15 +295,22 @@ cggi_fused_ntt120_p2_kernel(CggiNttArgs p, const uint2 *__restrict__ twf_g, cons
                 const bool live = ct < p.batch && limb < p.out_size;
                 const long long *src = p.res + (size_t)(live ? ct : 0) * p.res_stride + (size_t)(limb * cols + col) * N;
                 uint32_t x[8];
+                long long v[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) v[jj] = live ? src[t + jj * T] : 0;
+                if (blk == 0) { // only the initial accumulator (X^b * LUT) can leave the bound: later ones are digits this kernel wrote
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj++) bad |= (v[jj] > p.acc_limit) | (v[jj] < -p.acc_limit);
+                }
 #pragma unroll
                 for (int jj = 0; jj < 8; jj++) {
-                    const long long v = live ? src[t + jj * T] : 0;
-                    bad |= (v > p.acc_limit) | (v < -p.acc_limit);
-                    x[jj] = v < 0 ? (uint32_t)(v + (long long)q) : (uint32_t)v; // |v| <= acc_limit <= 2^29 < q
+                    const int lo = (int)v[jj]; // |v| <= acc_limit <= 2^29 < q: the low word is the value
+                    x[jj] = lo < 0 ? (uint32_t)lo + q : (uint32_t)lo;
                 }
                 ct_r8<NG::R0>(x, twf, 1u, q);
+                uint32_t *pb = buf + NPAD(t);
 #pragma unroll
-                for (int jj = 0; jj < 8; jj++) buf[NPAD(t + jj * T)] = x[jj];
+                for (int jj = 0; jj < 8; jj++) pb[poff<L - 3>(jj)] = x[jj];
             }
             slot_sync<T>(slot);
             NFwd<L, NG::R0>::run(buf, twf, twf + T, t, slot, valid, q);
@@ -289,14 +326,18 @@ cggi_fused_ntt120_p2_kernel(CggiNttArgs p, const uint2 *__restrict__ twf_g, cons
                 a0[r] = *reinterpret_cast<const uint4 *>(mine0 + (size_t)r * P * PL);
                 a1[r] = *reinterpret_cast<const uint4 *>(mine1 + (size_t)r * P * PL);
             }
-            uint4 w0[CGN_BSMAX], w1[CGN_BSMAX]; // X^{a_t} - 1 at this thread's frequencies, per ciphertext and key
+            // (X^{a_t} - 1) * 2^64 / n at this thread's frequencies, per ciphertext and key: the two Montgomery reductions below each leave a
+            // factor 2^-32 and the inverse transform a factor n; both are paid here, once per block, instead of per product
+            uint4 w0[CGN_BSMAX], w1[CGN_BSMAX];
+            const uint32_t cw = p.cw[kq], cws = p.cw_sh[kq];
+            auto wfac = [&](uint32_t x) { return csub(mul_shoup(x ? x - 1 : qk_ - 1, cw, cws, qk_), qk_); };
 #pragma unroll
             for (int tt = 0; tt < CGN_BSMAX; tt++) {
                 if (tt < bs) {
                     const uint4 x0 = __ldg(reinterpret_cast<const uint4 *>(p.xpa + ((size_t)s_pos[gp * 8 + tt] * 4 + kq) * N) + f4);
                     const uint4 x1 = __ldg(reinterpret_cast<const uint4 *>(p.xpa + ((size_t)s_pos[(gp + GH) * 8 + tt] * 4 + kq) * N) + f4);
-                    w0[tt] = make_uint4(x0.x ? x0.x - 1 : qk_ - 1, x0.y ? x0.y - 1 : qk_ - 1, x0.z ? x0.z - 1 : qk_ - 1, x0.w ? x0.w - 1 : qk_ - 1);
-                    w1[tt] = make_uint4(x1.x ? x1.x - 1 : qk_ - 1, x1.y ? x1.y - 1 : qk_ - 1, x1.z ? x1.z - 1 : qk_ - 1, x1.w ? x1.w - 1 : qk_ - 1);
+                    w0[tt] = make_uint4(wfac(x0.x), wfac(x0.y), wfac(x0.z), wfac(x0.w));
+                    w1[tt] = make_uint4(wfac(x1.x), wfac(x1.y), wfac(x1.z), wfac(x1.w));
                 }
             }
 #pragma unroll 1
@@ -310,7 +351,7 @@ cggi_fused_ntt120_p2_kernel(CggiNttArgs p, const uint2 *__restrict__ twf_g, cons
                         const uint32_t *tile = ring + (size_t)st * RT * P * N + (size_t)kq * N + 4 * f4;
                         unsigned long long v0[4] = {0, 0, 0, 0}, v1[4] = {0, 0, 0, 0};
 #pragma unroll
-                        for (int r = 0; r < RT; r++) { // canonical a (< 2^30) x canonical key (< 2^30): RT <= 16 rows fit u64
+                        for (int r = 0; r < RT; r++) { // canonical a (< 2^30) x canonical key (< 2^30): RT <= 4 rows stay below 2^62
                             const uint4 kv = *reinterpret_cast<const uint4 *>(tile + (size_t)r * P * N);
                             v0[0] += (unsigned long long)a0[r].x * kv.x; v0[1] += (unsigned long long)a0[r].y * kv.y;
                             v0[2] += (unsigned long long)a0[r].z * kv.z; v0[3] += (unsigned long long)a0[r].w * kv.w;
@@ -320,25 +361,27 @@ cggi_fused_ntt120_p2_kernel(CggiNttArgs p, const uint2 *__restrict__ twf_g, cons
                         // release the stage: one arrival per warp once all its lanes have read the tile
                         __syncwarp();
                         if (lane == 0) mbar_arrive(empty_s + st * 8);
-                        // (s + w v) - v = s + (w - 1) v: u64 products of (w - 1) in [0, q) and a lazy v in [0, 2q), at most CGN_BSMAX per sum
-                        s0[0] += (unsigned long long)w0[tt].x * lazy64(v0[0], qk_, c32, c32s); s0[1] += (unsigned long long)w0[tt].y * lazy64(v0[1], qk_, c32, c32s);
-                        s0[2] += (unsigned long long)w0[tt].z * lazy64(v0[2], qk_, c32, c32s); s0[3] += (unsigned long long)w0[tt].w * lazy64(v0[3], qk_, c32, c32s);
-                        s1[0] += (unsigned long long)w1[tt].x * lazy64(v1[0], qk_, c32, c32s); s1[1] += (unsigned long long)w1[tt].y * lazy64(v1[1], qk_, c32, c32s);
-                        s1[2] += (unsigned long long)w1[tt].z * lazy64(v1[2], qk_, c32, c32s); s1[3] += (unsigned long long)w1[tt].w * lazy64(v1[3], qk_, c32, c32s);
+                        // (s + w v) - v = s + (w - 1) v: u64 products of the canonical factor (< 2^30) and the Montgomery-reduced row sum
+                        // (< 2^31): at most CGN_BSMAX = 4 terms of < 2^61 per sum
+                        s0[0] += (unsigned long long)w0[tt].x * redc64(v0[0], qk_, qni); s0[1] += (unsigned long long)w0[tt].y * redc64(v0[1], qk_, qni);
+                        s0[2] += (unsigned long long)w0[tt].z * redc64(v0[2], qk_, qni); s0[3] += (unsigned long long)w0[tt].w * redc64(v0[3], qk_, qni);
+                        s1[0] += (unsigned long long)w1[tt].x * redc64(v1[0], qk_, qni); s1[1] += (unsigned long long)w1[tt].y * redc64(v1[1], qk_, qni);
+                        s1[2] += (unsigned long long)w1[tt].z * redc64(v1[2], qk_, qni); s1[3] += (unsigned long long)w1[tt].w * redc64(v1[3], qk_, qni);
                         gk++;
                     }
                 }
-                // canonical residues of output poly c (the planes of polys < RT were read into registers above: in place is safe)
+                // output poly c in [0, 2q) (s < 2^63: redc < 2^31 + q < 4q, one conditional subtraction), already scaled by 1 / n; the planes of
+                // polys < RT were read into registers above, so writing in place is safe
                 *reinterpret_cast<uint4 *>(mine0 + (size_t)c * P * PL) =
-                    make_uint4(csub(lazy64(s0[0], qk_, c32, c32s), qk_), csub(lazy64(s0[1], qk_, c32, c32s), qk_),
-                               csub(lazy64(s0[2], qk_, c32, c32s), qk_), csub(lazy64(s0[3], qk_, c32, c32s), qk_));
+                    make_uint4(csub(redc64(s0[0], qk_, qni), 2 * qk_), csub(redc64(s0[1], qk_, qni), 2 * qk_),
+                               csub(redc64(s0[2], qk_, qni), 2 * qk_), csub(redc64(s0[3], qk_, qni), 2 * qk_));
                 *reinterpret_cast<uint4 *>(mine1 + (size_t)c * P * PL) =
-                    make_uint4(csub(lazy64(s1[0], qk_, c32, c32s), qk_), csub(lazy64(s1[1], qk_, c32, c32s), qk_),
-                               csub(lazy64(s1[2], qk_, c32, c32s), qk_), csub(lazy64(s1[3], qk_, c32, c32s), qk_));
+                    make_uint4(csub(redc64(s1[0], qk_, qni), 2 * qk_), csub(redc64(s1[1], qk_, qni), 2 * qk_),
+                               csub(redc64(s1[2], qk_, qni), 2 * qk_), csub(redc64(s1[3], qk_, qni), 2 * qk_));
             }
         }
         named_sync(15, NT);
-        // ---- inverse transforms of the C output polys modulo both primes, scaled by 1/n ---------------------------------------------
+        // ---- inverse transforms of the C output polys modulo both primes (the 1 / n is already in the products) ------------------------
         for (int base = 0; base < G * C * P; base += NSLOT) {
             const int job = base + slot;
             const bool valid = job < G * C * P;
@@ -348,26 +391,26 @@ cggi_fused_ntt120_p2_kernel(CggiNttArgs p, const uint2 *__restrict__ twf_g, cons
             const uint2 *twi = tws + (size_t)(P + k) * 8 * T;
             if (valid) {
                 uint32_t x[8];
-                const uint4 *pp = reinterpret_cast<const uint4 *>(buf + NPAD(8 * t));
+                uint4 *pp = reinterpret_cast<uint4 *>(buf + NPAD(8 * t));
                 const uint4 u0 = pp[0], u1 = pp[1];
                 x[0] = u0.x; x[1] = u0.y; x[2] = u0.z; x[3] = u0.w; x[4] = u1.x; x[5] = u1.y; x[6] = u1.z; x[7] = u1.w;
                 gs_r8_w(x, twi + T, T, t, q);
-                uint4 *po = reinterpret_cast<uint4 *>(buf + NPAD(8 * t));
-                po[0] = make_uint4(x[0], x[1], x[2], x[3]);
-                po[1] = make_uint4(x[4], x[5], x[6], x[7]);
+                pp[0] = make_uint4(x[0], x[1], x[2], x[3]);
+                pp[1] = make_uint4(x[4], x[5], x[6], x[7]);
             }
             slot_sync<T>(slot);
             NInv<L, (L - 6 >= NG::R0) ? L - 6 : -1>::run(buf, twi, t, slot, valid, q);
             uint32_t x[8];
+            uint32_t *pb = buf + NPAD(t);
             if (valid) {
 #pragma unroll
-                for (int jj = 0; jj < 8; jj++) x[jj] = buf[NPAD(t + jj * T)];
+                for (int jj = 0; jj < 8; jj++) x[jj] = pb[poff<L - 3>(jj)];
                 gs_r8<NG::R0>(x, twi, 1u, q);
             }
-            slot_sync<T>(slot); // every thread of the transform has read its inputs before the scaled values overwrite them
+            slot_sync<T>(slot); // every thread of the transform has read its inputs before the canonical values overwrite them
             if (valid) {
 #pragma unroll
-                for (int jj = 0; jj < 8; jj++) buf[NPAD(t + jj * T)] = csub(mul_shoup(x[jj], p.ninv[k], p.ninv_sh[k], q), q);
+                for (int jj = 0; jj < 8; jj++) pb[poff<L - 3>(jj)] = csub(x[jj], q); // [0, 2q) -> canonical for the CRT
             }
         }
         named_sync(15, NT);
@@ -392,8 +435,8 @@ cggi_fused_ntt120_p2_kernel(CggiNttArgs p, const uint2 *__restrict__ twf_g, cons
                     for (int i = tid; i < N; i += NT) {
                         const int o = col * N + i;
                         if (two_to_one) {
-                            const long long v0 = crt(pg + (size_t)col * P * PL, i), v1 = crt(pg + (size_t)(cols + col) * P * PL, i);
                             const long long a0v = acc_g[o];
+                            const long long v0 = crt(pg + (size_t)col * P * PL, i), v1 = crt(pg + (size_t)(cols + col) * P * PL, i);
                             const long long o1 = (long long)((unsigned long long)v1 << (64 - K)) >> (64 - K);
                             const long long cy = (long long)((unsigned long long)v1 - (unsigned long long)o1) >> K;
                             const long long tsum = (long long)((unsigned long long)v0 + (unsigned long long)a0v + (unsigned long long)cy);
@@ -426,18 +469,18 @@ cggi_fused_ntt120_p2_kernel(CggiNttArgs p, const uint2 *__restrict__ twf_g, cons
     if (bad) atomicOr(p.fail, 1);
 }
 
-template <int L, int G, int RT, int CT, int NSTAGE> int launch_p2(pgb_module *m, const CggiNttArgs &p) {
+template <int L, int G, int RT, int CT, int NSTAGE, bool EXACT> int launch_p2(pgb_module *m, const CggiNttArgs &p) {
     typedef NGeo<L> NG;
     constexpr int PMAX = RT > CT ? RT : CT;
     const size_t smem = ((size_t)G * PMAX * 2 * NG::PLANE + (size_t)NSTAGE * RT * 2 * NG::N) * 4 + (size_t)2 * 2 * 8 * NG::T * sizeof(uint2);
     static bool attr_dev[32] = {};
     if (!attr_dev[m->device & 31]) {
-        PGB_CHECK_CUDA(cudaFuncSetAttribute(cggi_fused_ntt120_p2_kernel<L, G, RT, CT, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(cggi_fused_ntt120_p2_kernel<L, G, RT, CT, NSTAGE, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_dev[m->device & 31] = true;
     }
     const int grid = (p.batch + G - 1) / G;
     { ProfScope _ps(m, PROF_OTHER);
-    cggi_fused_ntt120_p2_kernel<L, G, RT, CT, NSTAGE><<<grid, CGN_COMPUTE + 32, smem, m->stream>>>(p, m->ntt_fwd, m->ntt_inv);
+    cggi_fused_ntt120_p2_kernel<L, G, RT, CT, NSTAGE, EXACT><<<grid, CGN_COMPUTE + 32, smem, m->stream>>>(p, m->ntt_fwd, m->ntt_inv);
     }
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;
@@ -566,18 +609,23 @@ int cggi_fused_ntt120(pgb_module *m, long long *res, uint64_t res_stride_words, 
     for (int k = 0; k < 2; k++) {
         const uint32_t q = qk(k);
         p.q[k] = q;
-        p.ninv[k] = modpow_u32((uint32_t)(n % q), q - 2, q);
-        p.ninv_sh[k] = (uint32_t)(((uint64_t)p.ninv[k] << 32) / q);
+        uint32_t inv = q; // Newton: q^-1 mod 2^32 (q odd), five doublings of the correct low bits
+        for (int it = 0; it < 5; it++) inv *= 2u - q * inv;
+        p.qneg_inv[k] = 0u - inv;
+        const uint64_t r32 = ((uint64_t)1 << 32) % q, ninv = modpow_u32((uint32_t)(n % q), q - 2, q);
+        p.cw[k] = (uint32_t)(r32 * r32 % q * ninv % q);
+        p.cw_sh[k] = (uint32_t)(((uint64_t)p.cw[k] << 32) / q);
     }
     p.q1inv = modpow_u32(qk(1) % qk(0), qk(0) - 2, qk(0));
     p.q1inv_sh = (uint32_t)(((uint64_t)p.q1inv << 32) / qk(0));
     p.Q2 = (unsigned long long)qk(0) * qk(1);
     p.half2 = (p.Q2 + 1) / 2;
     int s;
-    if (R == 4 && C > 4) s = launch_p2<9, 4, 4, 8, 4>(m, p);
-    else if (R == 4) s = launch_p2<9, 4, 4, 4, 4>(m, p);
-    else if (C > 4) s = launch_p2<9, 4, 2, 8, 4>(m, p);
-    else s = launch_p2<9, 4, 2, 4, 4>(m, p);
+    if (R == 4 && C == 8) s = launch_p2<9, 4, 4, 8, 4, true>(m, p);
+    else if (R == 4 && C > 4) s = launch_p2<9, 4, 4, 8, 4, false>(m, p);
+    else if (R == 4) s = launch_p2<9, 4, 4, 4, 4, false>(m, p);
+    else if (C > 4) s = launch_p2<9, 4, 2, 8, 4, false>(m, p);
+    else s = launch_p2<9, 4, 2, 4, 4, false>(m, p);
     PGB_TRY(s);
     int fail = 0;
     PGB_CHECK_CUDA(cudaMemcpyAsync(&fail, flags + 1, sizeof(int), cudaMemcpyDeviceToHost, m->stream));

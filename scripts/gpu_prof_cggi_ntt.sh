@@ -1,0 +1,6 @@
+#!/usr/bin/env bash
+set -u
+mkdir -p gpurun_out
+CGGI_FL=ntt120 timeout 600 ncu --set full --clock-control none --import-source on -k regex:cggi_fused_ntt120 -s 1 -c 1 -f -o gpurun_out/prof_cggi_ntt_${TAG:-1} python scripts/cggi_prof.py > gpurun_out/prof_cggi_ntt.log 2>&1
+tail -5 gpurun_out/prof_cggi_ntt.log
+ls -la gpurun_out/*.ncu-rep
