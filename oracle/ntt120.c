@@ -384,6 +384,71 @@ static inline uint64_t modq_red(uint64_t x, uint64_t h, uint64_t mask, uint64_t 
     return (x & mask) + (x >> h) * cst;
 }
 
+/* ---- "cpu-avx-style" leaves ------------------------------------------------------------------------------------------------------
+ * poulpy-cpu-avx keeps the four primes of one coefficient in one __m256i (4 x u64 lanes) and runs the SAME lazy arithmetic with
+ * _mm256_mul_epu32 (poulpy-cpu-avx/src/ntt120/ntt.rs:81-110 for the butterflies, mat_vec_avx.rs for the bbc products).  The functions
+ * below are that data path: lane k computes exactly what the scalar loop over k computes (same split products, same reduction schedule),
+ * so every intermediate u64 is identical to the scalar port and the switch changes speed only (tests/test_oracle_kat.py checks it).
+ * orc_ntt120_set_simd(1) selects them; 0 (default) = the scalar restatement of poulpy-cpu-ref. */
+#include <immintrin.h>
+static int g_simd = 0;
+void orc_ntt120_set_simd(int on) { g_simd = on ? 1 : 0; }
+int orc_ntt120_get_simd(void) { return g_simd; }
+
+static inline __m256i v_split_precompmul(__m256i inp, __m256i po, __m128i half_bs, __m256i mask) {
+    __m256i lo = _mm256_and_si256(inp, mask);
+    __m256i hi = _mm256_srl_epi64(inp, half_bs);
+    __m256i t1 = _mm256_srli_epi64(po, 32);
+    /* mul_epu32 multiplies the low 32 bits of every 64-bit lane: lo < 2^half_bs <= 2^32, hi < 2^32, t = low word of po, t1 < 2^32 */
+    return _mm256_add_epi64(_mm256_mul_epu32(lo, po), _mm256_mul_epu32(hi, t1));
+}
+static inline __m256i v_modq_red(__m256i x, __m128i h, __m256i mask, __m256i cst) {
+    return _mm256_add_epi64(_mm256_and_si256(x, mask), _mm256_mul_epu32(_mm256_srl_epi64(x, h), cst));
+}
+static void fwd_block_avx(uint64_t *d, size_t blk, size_t halfnn, const step_meta *m, const reduc_meta *r, const uint64_t *po) {
+    const __m256i q2bs = _mm256_loadu_si256((const __m256i *)m->q2bs), mask = _mm256_set1_epi64x((long long)m->mask);
+    const __m256i rmask = _mm256_set1_epi64x((long long)r->mask), rcst = _mm256_loadu_si256((const __m256i *)r->cst);
+    const __m128i hb = _mm_cvtsi64_si128((long long)m->half_bs), rh = _mm_cvtsi64_si128((long long)r->h);
+    for (size_t i = 0; i < halfnn; i++) {
+        __m256i *pa = (__m256i *)(d + 4 * (blk + i)), *pb = (__m256i *)(d + 4 * (blk + halfnn + i));
+        __m256i a = _mm256_loadu_si256(pa), b = _mm256_loadu_si256(pb);
+        if (m->reduce) {
+            a = v_modq_red(a, rh, rmask, rcst);
+            b = v_modq_red(b, rh, rmask, rcst);
+        }
+        _mm256_storeu_si256(pa, _mm256_add_epi64(a, b));
+        __m256i b1 = _mm256_sub_epi64(_mm256_add_epi64(a, q2bs), b);
+        if (i) b1 = v_split_precompmul(b1, _mm256_loadu_si256((const __m256i *)(po + 4 * (i - 1))), hb, mask);
+        _mm256_storeu_si256(pb, b1);
+    }
+}
+static void inv_block_avx(uint64_t *d, size_t blk, size_t halfnn, const step_meta *m, const reduc_meta *r, const uint64_t *po) {
+    const __m256i q2bs = _mm256_loadu_si256((const __m256i *)m->q2bs), mask = _mm256_set1_epi64x((long long)m->mask);
+    const __m256i rmask = _mm256_set1_epi64x((long long)r->mask), rcst = _mm256_loadu_si256((const __m256i *)r->cst);
+    const __m128i hb = _mm_cvtsi64_si128((long long)m->half_bs), rh = _mm_cvtsi64_si128((long long)r->h);
+    for (size_t i = 0; i < halfnn; i++) {
+        __m256i *pa = (__m256i *)(d + 4 * (blk + i)), *pb = (__m256i *)(d + 4 * (blk + halfnn + i));
+        __m256i a = _mm256_loadu_si256(pa), b = _mm256_loadu_si256(pb);
+        if (m->reduce) {
+            a = v_modq_red(a, rh, rmask, rcst);
+            b = v_modq_red(b, rh, rmask, rcst);
+        }
+        if (i) b = v_split_precompmul(b, _mm256_loadu_si256((const __m256i *)(po + 4 * (i - 1))), hb, mask);
+        _mm256_storeu_si256(pa, _mm256_add_epi64(a, b));
+        _mm256_storeu_si256(pb, _mm256_sub_epi64(_mm256_add_epi64(a, q2bs), b));
+    }
+}
+static void twist_pass_avx(uint64_t *d, size_t n, const uint64_t *po, const step_meta *m, const reduc_meta *r, int reduce) {
+    const __m256i mask = _mm256_set1_epi64x((long long)m->mask);
+    const __m256i rmask = _mm256_set1_epi64x((long long)r->mask), rcst = _mm256_loadu_si256((const __m256i *)r->cst);
+    const __m128i hb = _mm_cvtsi64_si128((long long)m->half_bs), rh = _mm_cvtsi64_si128((long long)r->h);
+    for (size_t i = 0; i < n; i++) {
+        __m256i x = _mm256_loadu_si256((const __m256i *)(d + 4 * i));
+        if (reduce) x = v_modq_red(x, rh, rmask, rcst);
+        _mm256_storeu_si256((__m256i *)(d + 4 * i), v_split_precompmul(x, _mm256_loadu_si256((const __m256i *)(po + 4 * i)), hb, mask));
+    }
+}
+
 /* ntt.rs:695-749 */
 static void fwd_block(uint64_t *d, size_t blk, size_t halfnn, const step_meta *m, const reduc_meta *r,
                       const uint64_t *po) {
@@ -424,6 +489,8 @@ void orc_ntt120_ntt(const orc_ntt120_module *mod, uint64_t *d) { /* ntt.rs:558-6
     size_t po = 0, mi = 0;
     {
         const step_meta *m = &t->levels[mi++];
+        if (g_simd) twist_pass_avx(d, n, t->powomega + po, m, &t->reduc, 0);
+        else
         for (size_t i = 0; i < n; i++)
             for (int k = 0; k < 4; k++)
                 d[4 * i + k] = split_precompmul(d[4 * i + k], t->powomega[po + 4 * i + k], m->half_bs, m->mask);
@@ -432,6 +499,8 @@ void orc_ntt120_ntt(const orc_ntt120_module *mod, uint64_t *d) { /* ntt.rs:558-6
     for (size_t nn = n; nn >= 2; nn /= 2) {
         size_t halfnn = nn / 2;
         const step_meta *m = &t->levels[mi++];
+        if (g_simd) for (size_t blk = 0; blk < n; blk += nn) fwd_block_avx(d, blk, halfnn, m, &t->reduc, t->powomega + po);
+        else
         for (size_t blk = 0; blk < n; blk += nn) fwd_block(d, blk, halfnn, m, &t->reduc, t->powomega + po);
         po += 4 * (halfnn > 0 ? halfnn - 1 : 0);
     }
@@ -444,16 +513,22 @@ void orc_ntt120_intt(const orc_ntt120_module *mod, uint64_t *d) { /* ntt.rs:617-
     size_t po = 0, mi = 0;
     {
         const step_meta *m = &t->levels[mi++];
+        if (g_simd) for (size_t blk = 0; blk < n; blk += 2) inv_block_avx(d, blk, 1, m, &t->reduc, t->powomega + po);
+        else
         for (size_t blk = 0; blk < n; blk += 2) inv_block(d, blk, 1, m, &t->reduc, t->powomega + po);
     }
     for (size_t nn = 4; nn <= n; nn *= 2) {
         size_t halfnn = nn / 2;
         const step_meta *m = &t->levels[mi++];
+        if (g_simd) for (size_t blk = 0; blk < n; blk += nn) inv_block_avx(d, blk, halfnn, m, &t->reduc, t->powomega + po);
+        else
         for (size_t blk = 0; blk < n; blk += nn) inv_block(d, blk, halfnn, m, &t->reduc, t->powomega + po);
         po += 4 * (halfnn - 1);
     }
     {
         const step_meta *m = &t->levels[mi];
+        if (g_simd) twist_pass_avx(d, n, t->powomega + po, m, &t->reduc, m->reduce);
+        else
         for (size_t i = 0; i < n; i++)
             for (int k = 0; k < 4; k++) {
                 uint64_t x = d[4 * i + k];
@@ -472,6 +547,23 @@ static inline void accum_mul_q120_bc(uint64_t s[8], const uint32_t *x, const uin
         s[2 * i + 1] += (lo >> 32) + (hi >> 32);
     }
 }
+/* mat_vec_avx.rs: x = 4 lazy residues as u64 (low word xl, high word xh), y = 4 x (r, r 2^32 mod q) as u32 pairs; the sums of the low and
+ * of the high product words are kept in two vectors (the scalar s[2i] / s[2i+1]) */
+static inline void v_accum_mul_q120_bc(__m256i *s_lo, __m256i *s_hi, const uint32_t *x, const uint32_t *y) {
+    const __m256i lomask = _mm256_set1_epi64x(0xFFFFFFFFll);
+    __m256i vx = _mm256_loadu_si256((const __m256i *)x), vy = _mm256_loadu_si256((const __m256i *)y);
+    __m256i lo = _mm256_mul_epu32(vx, vy), hi = _mm256_mul_epu32(_mm256_srli_epi64(vx, 32), _mm256_srli_epi64(vy, 32));
+    *s_lo = _mm256_add_epi64(*s_lo, _mm256_add_epi64(_mm256_and_si256(lo, lomask), _mm256_and_si256(hi, lomask)));
+    *s_hi = _mm256_add_epi64(*s_hi, _mm256_add_epi64(_mm256_srli_epi64(lo, 32), _mm256_srli_epi64(hi, 32)));
+}
+static inline void v_accum_to_q120b(uint64_t res[4], __m256i s_lo, __m256i s_hi, const bbc_meta *m) {
+    const __m256i mask2 = _mm256_set1_epi64x((long long)((1ull << m->h) - 1));
+    const __m128i h = _mm_cvtsi64_si128((long long)m->h);
+    __m256i s2l = _mm256_and_si256(s_hi, mask2), s2h = _mm256_srl_epi64(s_hi, h);
+    __m256i r = _mm256_add_epi64(s_lo, _mm256_add_epi64(_mm256_mul_epu32(s2l, _mm256_loadu_si256((const __m256i *)m->s2l)),
+                                                       _mm256_mul_epu32(s2h, _mm256_loadu_si256((const __m256i *)m->s2h))));
+    _mm256_storeu_si256((__m256i *)res, r);
+}
 static inline void accum_to_q120b(uint64_t res[4], const uint64_t s[8], const bbc_meta *m) {
     uint64_t mask2 = (1ull << m->h) - 1;
     for (int k = 0; k < 4; k++) {
@@ -487,6 +579,16 @@ static void mat1col_bbc(const bbc_meta *m, size_t ell, uint64_t *res, const uint
 }
 /* mat_vec.rs:391-418 */
 static void mat1col_x2_bbc(const bbc_meta *m, size_t ell, uint64_t *res, const uint32_t *x, const uint32_t *y) {
+    if (g_simd) {
+        __m256i l0 = _mm256_setzero_si256(), h0 = l0, l1 = l0, h1 = l0;
+        for (size_t i = 0; i < ell; i++) {
+            v_accum_mul_q120_bc(&l0, &h0, x + 16 * i, y + 16 * i);
+            v_accum_mul_q120_bc(&l1, &h1, x + 16 * i + 8, y + 16 * i + 8);
+        }
+        v_accum_to_q120b(res, l0, h0, m);
+        v_accum_to_q120b(res + 4, l1, h1, m);
+        return;
+    }
     uint64_t s[2][8] = {{0}};
     for (size_t i = 0; i < ell; i++) {
         accum_mul_q120_bc(s[0], x + 16 * i, y + 16 * i);
@@ -497,6 +599,19 @@ static void mat1col_x2_bbc(const bbc_meta *m, size_t ell, uint64_t *res, const u
 }
 /* mat_vec.rs:423-447 */
 static void mat2cols_x2_bbc(const bbc_meta *m, size_t ell, uint64_t *res, const uint32_t *x, const uint32_t *y) {
+    if (g_simd) {
+        __m256i l[4], h[4];
+        for (int o = 0; o < 4; o++) l[o] = h[o] = _mm256_setzero_si256();
+        for (size_t i = 0; i < ell; i++) {
+            const uint32_t *x0 = x + 16 * i, *x1 = x + 16 * i + 8;
+            v_accum_mul_q120_bc(&l[0], &h[0], x0, y + 32 * i);
+            v_accum_mul_q120_bc(&l[1], &h[1], x1, y + 32 * i + 8);
+            v_accum_mul_q120_bc(&l[2], &h[2], x0, y + 32 * i + 16);
+            v_accum_mul_q120_bc(&l[3], &h[3], x1, y + 32 * i + 24);
+        }
+        for (int o = 0; o < 4; o++) v_accum_to_q120b(res + 4 * o, l[o], h[o], m);
+        return;
+    }
     uint64_t s[4][8] = {{0}};
     for (size_t i = 0; i < ell; i++) {
         const uint32_t *x0 = x + 16 * i, *x1 = x + 16 * i + 8;

@@ -263,4 +263,8 @@ int orc_num_threads(void);
 void orc_cggi_blind_rotate_block_binary_batch(int flavour, const void *mod, int64_t *res, size_t n, size_t cols, size_t res_size,
                                               const int64_t *lwe_2n, size_t n_lwe, const orc_vec_znx *lut, const orc_vmp_pmat *brk,
                                               const orc_svp_ppol *x_pow_a, size_t block_size, size_t base2k, size_t batch, int threads);
+/* ntt120.c: 1 = "cpu-avx-style" data path (four primes per __m256i, poulpy-cpu-avx/src/ntt120/ntt.rs:81-110, mat_vec_avx.rs) for the NTT
+ * butterflies and the bbc products; 0 (default) = scalar restatement of poulpy-cpu-ref.  Identical lazy values either way. */
+void orc_ntt120_set_simd(int on);
+int orc_ntt120_get_simd(void);
 #endif

@@ -441,6 +441,11 @@ def mod_switch_2n(two_n_domain, lwe, base2k, rot_left=True):
     return res
 
 
+def ntt120_set_simd(on: bool):
+    """Select the AVX2 four-primes-per-__m256i data path (poulpy-cpu-avx style) for the NTT120 butterflies and bbc products."""
+    lib().orc_ntt120_set_simd(C.c_int(1 if on else 0))
+
+
 def num_threads():
     return int(lib().orc_num_threads())
 

@@ -479,7 +479,6 @@ cggi_fused3_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
     __syncthreads();
     if (tid == 0)
         for (int gk = 0; gk < NSTAGE && gk < total_tiles; gk++) issue(gk);
-
     const int gp = tid % GH, f = tid / GH; // this thread's frequency and its two ciphertexts gp, gp + GH
     double2 *mine0 = csm + (size_t)gp * GS + FPAD(f), *mine1 = csm + (size_t)(gp + GH) * GS + FPAD(f);
     int gk = 0;
@@ -548,7 +547,10 @@ cggi_fused3_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
                         const double p1r = fma(w1r, v1r, -(w1i * v1i)), p1i = fma(w1r, v1i, w1i * v1r);
                         s0r[q] = (s0r[q] + p0r) - v0r; s0i[q] = (s0i[q] + p0i) - v0i; // dft_add_assign then dft_sub_assign
                         s1r[q] = (s1r[q] + p1r) - v1r; s1i[q] = (s1i[q] + p1i) - v1i;
-                        // consumer release; thread 0 refills the stage once all 512 threads have released it (only its warp waits)
+                        // consumer release; thread 0 refills the stage once all 512 threads have released it (only its warp waits).  Measured
+                        // alternatives: one arrival per warp after __syncwarp 94.9 k bootstraps/s (against 99.7 k), a non-blocking thread 0
+                        // that polls at tile boundaries 75.6 k -- the refill must be requested the moment the stage is free; version 4 below
+                        // gives the ring its own warp
                         mbar_arrive(empty_s + st * 8);
                         if (tid == 0 && gk + NSTAGE < total_tiles) {
                             mbar_wait(empty_s + st * 8, (uint32_t)((gk / NSTAGE) & 1));
@@ -654,6 +656,250 @@ cggi_fused3_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
     }
 }
 
+// ---- version 4: the key ring gets its own warp ------------------------------------------------------------------------------
+// ncu on version 3 at the BASELINE shape (profiles/r2_ncu_cggi.md): 18.7 % of the stall samples and 24 % of the executed instructions are
+// the try-wait spin on the tile-full barrier -- the compute warps outrun a ring whose refills are requested by a thread that is itself
+// one of the consumers.  Here warp 16 does nothing but the ring (as in cggi_ntt_fused.cu, where the same wait is 3 % of the instructions).
+// A 17th warp caps the kernel at 96 registers per thread, so the key products are reorganised around ONE output poly at a time (tiles in
+// (poly, key) order): 4 partial-sum doubles per thread instead of 64, the X^{a_t} factors of all keys of the block loaded once, no spills.
+// Per (ciphertext, frequency, output poly) the floating-point operations and their order are exactly those of version 3 (rows in row
+// order inside a key, keys in block order), so the results are bit-identical to it.
+template <int LM, int G, int RT, int CT, int NSTAGE, int BS> __global__ void __launch_bounds__(512 + 32, 1)
+cggi_fused4_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, const double2 *__restrict__ twi_g, const double2 *__restrict__ twlf_g,
+                         const double2 *__restrict__ twli_g, double inv_m) {
+    typedef FGeo<LM> FG;
+    constexpr int M = 1 << LM, N = 2 * M, T = FG::T, NT = 512, PL = FG::PLANE, NSLOT = NT / T, GH = G / 2;
+    constexpr int PMAX = RT > CT ? RT : CT;
+    // planes of consecutive ciphertexts start 64 bytes (mod 128) apart: in the key products neighbouring threads hold the same frequency of
+    // two different ciphertexts, and a plane stride that is a multiple of 128 bytes put both on the same banks (2-way conflicts)
+    constexpr int GS = PMAX * PL + 4;
+    constexpr uint32_t CHUNK = N * 8, TILE = RT * CHUNK; // bytes
+    static_assert(GH * M == NT && GH >= 1 && LM > FG::R0, "geometry");
+    extern __shared__ __align__(128) double2 csm[];
+    __shared__ int s_pos[G * 8];
+    __shared__ __align__(8) unsigned long long s_bar[NSTAGE], s_empty[NSTAGE]; // tile filled / tile consumed by all threads
+    double *ring = reinterpret_cast<double *>(csm + (size_t)G * GS); // [NSTAGE][RT][N]
+    // both twiddle tables (m complex values each) live in shared memory: with ~210 KB of it in use the L1 is too small to keep them
+    // M entries per direction as before, split into the first T block twiddles and the [7][T] last-pass table
+    double2 *twf = reinterpret_cast<double2 *>(ring + (size_t)NSTAGE * RT * N), *twlf = twf + T, *twi = twf + M, *twli = twi + T;
+    for (int i = threadIdx.x; i < T; i += 512 + 32) {
+        twf[i] = twf_g[i];
+        twi[i] = twi_g[i];
+    }
+    for (int i = threadIdx.x; i < 7 * T; i += 512 + 32) {
+        twlf[i] = twlf_g[i];
+        twli[i] = twli_g[i];
+    }
+    const int cols = p.cols, C = cols * p.brk_size, K = p.base2k, bs = p.block_size;
+    const int tid = threadIdx.x, slot = tid / T, t = tid % T;
+    const int ct0 = blockIdx.x * G;
+    const int mn_small = min(p.brk_size, p.out_size);
+    const int a_start = min(p.out_size, p.brk_size);
+    const int nblk = p.n_lwe / bs, tiles_per_blk = bs * C, total_tiles = nblk * tiles_per_blk;
+    const uint32_t ring_s = smem_u32(ring), bar_s = smem_u32(s_bar), empty_s = smem_u32(s_empty);
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; s++) {
+            mbar_init(bar_s + s * 8, 1);
+            mbar_init(empty_s + s * 8, NT);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // ---- producer warp (warp 16): tiles in (block, output poly c, key t) order, refilled the moment all consumers released the stage -----
+    if (tid >= NT) {
+        if (tid == NT) {
+            int tt = 0, c = 0;
+            const double *key0 = p.brk; // first key of the current block
+            for (int gk = 0; gk < total_tiles; gk++) {
+                const int st = gk % NSTAGE;
+                if (gk >= NSTAGE) mbar_wait(empty_s + st * 8, (uint32_t)((gk / NSTAGE - 1) & 1));
+                const uint32_t bar = bar_s + st * 8;
+                mbar_expect_tx(bar, TILE);
+                const double *src = key0 + (size_t)tt * p.brk_doubles + (size_t)c * N;
+#pragma unroll
+                for (int r = 0; r < RT; r++) bulk_g2s(ring_s + (uint32_t)(st * RT + r) * CHUNK, src + (size_t)r * C * N, CHUNK, bar);
+                if (++tt == bs) {
+                    tt = 0;
+                    if (++c == C) {
+                        c = 0;
+                        key0 += (size_t)bs * p.brk_doubles;
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    const int gp = tid % GH, f = tid / GH; // this thread's frequency and its two ciphertexts gp, gp + GH
+    double2 *mine0 = csm + (size_t)gp * GS + FPAD(f), *mine1 = csm + (size_t)(gp + GH) * GS + FPAD(f);
+    int gk = 0;
+
+    for (int blk = 0; blk + bs <= p.n_lwe; blk += bs) {
+        if (tid < G * bs) {
+            const int g = tid / bs, tt = tid % bs, ct = ct0 + g;
+            const long long ai = ct < p.batch ? p.lwe[(size_t)ct * p.lwe_stride + 1 + blk + tt] : 0;
+            s_pos[g * 8 + tt] = (int)((ai + (long long)(2 * N)) & (long long)(2 * N - 1));
+        }
+        // ---- acc_dft = FFT(acc) ------------------------------------------------------------------------------------------
+        for (int base = 0; base < G * RT; base += NSLOT) {
+            const int job = base + slot;
+            const bool valid = job < G * RT;
+            const int g = valid ? job / RT : 0, r = valid ? job % RT : 0, limb = r / cols, col = r % cols;
+            double2 *buf = csm + g * GS + r * PL;
+            if (valid) {
+                const int ct = ct0 + g;
+                const bool live = ct < p.batch && limb < p.out_size;
+                const long long *src = p.res + (size_t)(live ? ct : 0) * p.res_stride + (size_t)(limb * cols + col) * N;
+                double2 x[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) {
+                    const int idx = t + jj * T;
+                    x[jj] = live ? make_double2((double)src[idx], (double)src[idx + M]) : make_double2(0.0, 0.0);
+                }
+                fct_radix8<FG::R0, true>(x, twf, 1u);
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) buf[FPAD(t + jj * T)] = x[jj];
+            }
+            poly_sync<T>(slot);
+            SmFwdP<LM, FG::R0>::run(buf, twf, twlf, t, slot, valid);
+        }
+        named_sync(15, NT); // every transform of the block is complete before the key products read across them
+        // ---- key products: tiles in (output poly, key) order; the partial sums of ONE output poly at a time live in registers -------------
+        {
+            double a0r[RT], a0i[RT], a1r[RT], a1i[RT];
+#pragma unroll
+            for (int r = 0; r < RT; r++) {
+                const double2 u = mine0[r * PL], v = mine1[r * PL];
+                a0r[r] = u.x; a0i[r] = u.y; a1r[r] = v.x; a1i[r] = v.y;
+            }
+            double w0r[BS], w0i[BS], w1r[BS], w1i[BS]; // X^{a_t} at this frequency for both ciphertexts and every key of the block
+#pragma unroll
+            for (int tt = 0; tt < BS; tt++) {
+                if (tt < bs) {
+                    const double *w0 = p.xpa + (size_t)s_pos[gp * 8 + tt] * N + f, *w1 = p.xpa + (size_t)s_pos[(gp + GH) * 8 + tt] * N + f;
+                    w0r[tt] = __ldg(w0); w0i[tt] = __ldg(w0 + M); w1r[tt] = __ldg(w1); w1i[tt] = __ldg(w1 + M);
+                }
+            }
+#pragma unroll 1
+            for (int q = 0; q < C; q++) {
+                double s0r = 0.0, s0i = 0.0, s1r = 0.0, s1i = 0.0;
+#pragma unroll
+                for (int tt = 0; tt < BS; tt++) {
+                    if (tt < bs) { // uniform
+                        const int st = gk % NSTAGE;
+                        mbar_wait(bar_s + st * 8, (uint32_t)((gk / NSTAGE) & 1));
+                        const double *tile = ring + (size_t)st * RT * N + f;
+                        double v0r = 0.0, v0i = 0.0, v1r = 0.0, v1i = 0.0;
+#pragma unroll
+                        for (int r = 0; r < RT; r++) { // row order of reim4_add_mul (reim4/arithmetic_ref.rs:223-232), FMA-contracted
+                            const double br = tile[r * N], bi = tile[r * N + M];
+                            v0r = fma(a0r[r], br, v0r); v0r = fma(-a0i[r], bi, v0r);
+                            v0i = fma(a0r[r], bi, v0i); v0i = fma(a0i[r], br, v0i);
+                            v1r = fma(a1r[r], br, v1r); v1r = fma(-a1i[r], bi, v1r);
+                            v1i = fma(a1r[r], bi, v1i); v1i = fma(a1i[r], br, v1i);
+                        }
+                        mbar_arrive(empty_s + st * 8); // the key values are in registers: release the stage to the producer warp
+                        const double p0r = fma(w0r[tt], v0r, -(w0i[tt] * v0i)), p0i = fma(w0r[tt], v0i, w0i[tt] * v0r); // svp: reim_mul(ppol, v)
+                        const double p1r = fma(w1r[tt], v1r, -(w1i[tt] * v1i)), p1i = fma(w1r[tt], v1i, w1i[tt] * v1r);
+                        s0r = (s0r + p0r) - v0r; s0i = (s0i + p0i) - v0i; // dft_add_assign then dft_sub_assign, keys in block order
+                        s1r = (s1r + p1r) - v1r; s1i = (s1i + p1i) - v1i;
+                        gk++;
+                    }
+                }
+                mine0[q * PL] = make_double2(s0r, s0i); // the planes of polys < RT were read into registers above: in place is safe
+                mine1[q * PL] = make_double2(s1r, s1i);
+            }
+        }
+        named_sync(15, NT);
+        // ---- acc = normalize(round(IFFT(out) / m) + acc) -----------------------------------------------------------------------
+        for (int base = 0; base < G * C; base += NSLOT) {
+            const int job = base + slot;
+            const bool valid = job < G * C;
+            const int g = valid ? job / C : 0, q = valid ? job % C : 0;
+            double2 *buf = csm + g * GS + q * PL;
+            if (valid) {
+                double2 x[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) x[jj] = buf[FPAD(8 * t + jj)];
+                double2 w[7];
+                load_tw7<true>(w, twli, T, t);
+                fgs_radix8_w(x, w);
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) buf[FPAD(8 * t + jj)] = x[jj];
+            }
+            poly_sync<T>(slot);
+            SmInvP<LM, (LM - 6 >= FG::R0) ? LM - 6 : -1>::run(buf, twi, t, slot, valid);
+            double2 x[8];
+            if (valid) {
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) x[jj] = buf[FPAD(t + jj * T)];
+                fgs_radix8<FG::R0, true>(x, twi, 1u);
+            }
+            poly_sync<T>(slot); // the transform has read its inputs: the buffer is reused for the rounded i64 coefficients
+            if (valid) {
+                long long *big = reinterpret_cast<long long *>(buf);
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) {
+                    const int idx = t + jj * T;
+                    big[idx] = (long long)round(x[jj].x * inv_m); // reim_to_znx_i64 (conversion.rs:43-52)
+                    big[idx + M] = (long long)round(x[jj].y * inv_m);
+                }
+            }
+        }
+        named_sync(15, NT);
+        // brk_size <= 4 here (checked on the host): all loads of a coefficient are issued before its carry chain; 32-bit offsets
+        {
+            const int limb_w = cols * N, bsz = p.brk_size;
+            const bool two_to_one = bsz == 2 && p.out_size == 1; // the bench shape (k_brk = 2 limbs, k_glwe = 1 limb): no predicated loads
+            for (int g = 0; g < G; g++) {
+                if (ct0 + g >= p.batch) break;
+                long long *acc_g = p.res + (size_t)(ct0 + g) * p.res_stride;
+                const long long *big_g = reinterpret_cast<const long long *>(csm + (size_t)g * GS);
+                if (two_to_one) {
+                    for (int col = 0; col < cols; col++) {
+#pragma unroll
+                        for (int i = tid; i < N; i += NT) {
+                            const long long v0 = big_g[col * (2 * PL) + i], v1 = big_g[(cols + col) * (2 * PL) + i];
+                            long long *ap = acc_g + col * N + i;
+                            const long long a0 = *ap;
+                            const long long o1 = (long long)((unsigned long long)v1 << (64 - K)) >> (64 - K);
+                            const long long c = (long long)((unsigned long long)v1 - (unsigned long long)o1) >> K;
+                            const long long tsum = (long long)((unsigned long long)v0 + (unsigned long long)a0 + (unsigned long long)c);
+                            *ap = (long long)((unsigned long long)tsum << (64 - K)) >> (64 - K);
+                        }
+                    }
+                    continue;
+                }
+                for (int col = 0; col < cols; col++) {
+#pragma unroll
+                    for (int i = tid; i < N; i += NT) {
+                        const int o = col * N + i;
+                        long long vv[4], aa[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            vv[j] = j < bsz ? big_g[(j * cols + col) * (2 * PL) + i] : 0;
+                            aa[j] = j < mn_small ? acc_g[o + j * limb_w] : 0;
+                        }
+                        long long c = 0;
+#pragma unroll
+                        for (int j = 3; j >= 0; j--) {
+                            if (j < bsz) {
+                                const long long tsum = (long long)((unsigned long long)vv[j] + (unsigned long long)aa[j] + (unsigned long long)c);
+                                const long long out = (long long)((unsigned long long)tsum << (64 - K)) >> (64 - K);
+                                c = (long long)((unsigned long long)tsum - (unsigned long long)out) >> K;
+                                if (j < a_start) acc_g[o + j * limb_w] = out;
+                            }
+                        }
+                        for (int j = a_start; j < p.out_size; j++) acc_g[o + j * limb_w] = 0;
+                    }
+                }
+            }
+        }
+        named_sync(15, NT);
+    }
+}
+
 template <int LM, int G, int RT, int CT, int NSTAGE> static int launch_cggi3(pgb_module *m, const CggiFusedArgs &p) {
     typedef FGeo<LM> FG;
     constexpr int PMAX = RT > CT ? RT : CT;
@@ -674,6 +920,24 @@ template <int LM, int G, int NSTAGE> static int launch_cggi3_shape(pgb_module *m
     if (R == 2 && C > 4 && C <= 8) return launch_cggi3<LM, G, 2, 8, NSTAGE>(m, p);
     if (R == 2 && C <= 4) return launch_cggi3<LM, G, 2, 4, NSTAGE>(m, p);
     *handled = false;
+    return PGB_OK;
+}
+
+template <int LM, int G, int RT, int CT, int NSTAGE, int BS> static int launch_cggi4(pgb_module *m, const CggiFusedArgs &p) {
+    typedef FGeo<LM> FG;
+    constexpr int PMAX = RT > CT ? RT : CT;
+    const size_t smem = (size_t)G * (PMAX * FG::PLANE + 4) * sizeof(double2) + (size_t)NSTAGE * RT * (2 << LM) * 8 + (size_t)2 * (1 << LM) * sizeof(double2);
+    static bool attr_dev[32] = {};
+    if (!attr_dev[m->device & 31]) {
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(cggi_fused4_fft64_kernel<LM, G, RT, CT, NSTAGE, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_dev[m->device & 31] = true;
+    }
+    const int grid = (p.batch + G - 1) / G;
+    { ProfScope _ps(m, PROF_OTHER);
+    cggi_fused4_fft64_kernel<LM, G, RT, CT, NSTAGE, BS><<<grid, 512 + 32, smem, m->stream>>>(p, m->fft_fwd, m->fft_inv, m->fft_last_f, m->fft_last_i,
+                                                                                         1.0 / (double)(1 << LM));
+    }
+    PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;
 }
 
@@ -738,6 +1002,10 @@ int cggi_fused_fft64(pgb_module *m, long long *res, uint64_t res_stride_words, c
                      int out_size, int batch) {
     CggiFusedArgs p = {res, res_stride_words, lwe, lwe_stride, brk, brk_doubles, xpa, n_lwe, block_size, base2k, cols, dnum, brk_size, out_size, batch};
     const int R = cols * dnum, C = cols * brk_size;
+    if (block_size <= 3 && m->opt[PGB_OPT_CGGI_VARIANT] == 0 && (brk_doubles % 2) == 0 && brk_size <= 4 && m->log_n == 9 && R == 4 && C <= 8) {
+        // version 4 (dedicated ring warp), instantiated for the BASELINE family: n = 512, four input polys, blocks of at most three keys
+        return C > 4 ? launch_cggi4<8, 4, 4, 8, 4, 3>(m, p) : launch_cggi4<8, 4, 4, 4, 4, 3>(m, p);
+    }
     if (block_size <= 8 && (m->opt[PGB_OPT_CGGI_VARIANT] == 0 || m->opt[PGB_OPT_CGGI_VARIANT] >= 3) && (brk_doubles % 2) == 0 && brk_size <= 4) {
         // TMA key stream (tiles must be 16-byte aligned: brk is a cudaMalloc'd / 64-byte aligned buffer of whole polys)
         bool handled = false;

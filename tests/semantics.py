@@ -72,10 +72,12 @@ def external_product_torus(ain, ggsw, ggsw_k, dsize):
     return [torus(big[c], ggsw_k) for c in range(len(big))]
 
 
-def assert_normalised_equals(out, out_k, want_torus, prec_bits, what=""):
-    """out: (size, n) digits of base 2^out_k.  Every digit is balanced and the torus value equals `want_torus` modulo 1 up to the
-    rounding of a normalisation to `prec_bits` bits (|diff| <= 2^-prec_bits; exact when prec_bits is None)."""
-    half = 1 << (out_k - 1)
+def assert_normalised_equals(out, out_k, want_torus, prec_bits, what="", balanced=True):
+    """out: (size, n) digits of base 2^out_k.  The torus value equals `want_torus` modulo 1 up to the rounding of a normalisation to
+    `prec_bits` bits (|diff| <= 2^-prec_bits; exact when prec_bits is None).  balanced: every digit lies in [-2^(k-1), 2^(k-1)] -- what the
+    same-base2k carry chain guarantees; the cross-base2k path of the reference (reference/vec_znx/normalize.rs:151-) re-packs bits and can
+    leave a digit a few units outside (its own property tests only bound the torus value), so there only |digit| < 2^k is asserted."""
+    half = 1 << (out_k - 1) if balanced else (1 << out_k) - 1
     for j in range(len(out)):
         for v in out[j]:
             assert -half <= int(v) <= half, (what, "digit out of range", j, int(v))

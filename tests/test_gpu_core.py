@@ -593,3 +593,77 @@ def test_pinned_key_cache(fl):
     assert run(3) == first and run(3) == second
     g.gadget_key_unpin(pg)
     assert run(3) == unpinned
+
+
+def _negacyclic_np(a, b):
+    """Exact negacyclic product of two small-integer polynomials with numpy (|result| < 2^62 for the digit sizes used here)."""
+    n = len(a)
+    full = np.convolve(np.asarray(a, dtype=np.int64), np.asarray(b, dtype=np.int64))
+    res = full[:n].copy()
+    res[: n - 1] -= full[n:]
+    return res
+
+
+def _phase_int(ct, secrets, k):
+    """body + sum mask_c (*) s_c as exact integers scaled by 2^(size k) (Python ints), for ct (size, cols, n)."""
+    size, _, n = ct.shape
+    out = [0] * n
+    for j in range(size):
+        v = ct[j, 0].astype(np.int64).copy()
+        for c, s in enumerate(secrets):
+            v = v + _negacyclic_np(ct[j, 1 + c], s)
+        w = 1 << ((size - 1 - j) * k)
+        out = [o + int(x) * w for o, x in zip(out, v)]
+    return out
+
+
+@pytest.mark.parametrize("fl", FLAVOURS)
+@pytest.mark.parametrize("n", [1024, 4096])
+def test_noiseless_keyswitch_preserves_the_phase_on_the_device(fl, n):
+    """L4 (reference: poulpy-core/src/test_suite/keyswitch/glwe_ct.rs:132-156): with a NOISE-FREE key-switching key from s to s'
+    the single-kernel key-switch maps any ciphertext to one with the same phase under s' -- exactly (no limb is truncated here), checked
+    with integer arithmetic that shares nothing with the oracle.  n = 4096 / base2k 18 is the headline shape."""
+    k, a_size = 18, 3
+    key_size = a_size + 1
+    rng = np.random.default_rng(1900 + fl + n)
+    g = pb.Module(n, fl)
+    s_in = rng.integers(-1, 2, size=n).astype(np.int64)
+    s_out = rng.integers(-1, 2, size=n).astype(np.int64)
+    key = np.zeros((a_size, 1, key_size, 2, n), dtype=np.int64)
+    for d in range(a_size):
+        mask = fill_uniform(rng, (key_size, n), k)
+        acc = [0] * n  # s_in * 2^-((d+1)k) - mask (*) s_out, scaled by 2^(key_size k)
+        for j in range(key_size):
+            w = 1 << ((key_size - 1 - j) * k)
+            prod = _negacyclic_np(mask[j], s_out)
+            for i in range(n):
+                acc[i] -= int(prod[i]) * w
+        wmsg = 1 << ((key_size - 1 - d) * k)
+        for i in range(n):
+            acc[i] += int(s_in[i]) * wmsg
+        mod = 1 << (key_size * k)
+        body = np.zeros((key_size, n), dtype=np.int64)
+        for i in range(n):
+            v = acc[i] % mod
+            for j in range(key_size - 1, -1, -1):
+                dgt = v & ((1 << k) - 1)
+                if dgt >= 1 << (k - 1):
+                    dgt -= 1 << k
+                body[j, i] = dgt
+                v = (v - dgt) >> k
+        key[d, 0, :, 0, :] = body
+        key[d, 0, :, 1, :] = mask
+    pg = g.vmp_pmat_alloc(a_size, 1, 2, key_size)
+    g.vmp_prepare(pg, g.mat_znx_from_numpy(key))
+    batch = 3
+    a = fill_uniform(rng, (batch, a_size, 2, n), k)
+    res = g.vec_znx_alloc(2, key_size, batch)
+    g.glwe_keyswitch(res, k, g.vec_znx_from_numpy(a), k, pg, k)
+    g.sync()
+    got = g.vec_znx_to_numpy(res)
+    for b in range(batch):
+        want = _phase_int(a[b], [s_in], k)       # scaled by 2^(a_size k)
+        have = _phase_int(got[b], [s_out], k)    # scaled by 2^(key_size k)
+        mod = 1 << (key_size * k)
+        shift = 1 << ((key_size - a_size) * k)
+        assert all((h - w * shift) % mod == 0 for h, w in zip(have, want)), b

@@ -67,7 +67,8 @@ def test_keyswitch_equals_bigint_model(fl, dsize, a_k, key_k, res_k, a_size, key
         want = S.keyswitch_torus(ain.tolist(), key.tolist(), key_k, dsize)
         exact = res_size * res_k >= key_size * key_k
         for c in range(rank_out + 1):
-            S.assert_normalised_equals(res[:, c, :].tolist(), res_k, want[c], None if exact else res_size * res_k, ("ks", rank_in, rank_out, c))
+            S.assert_normalised_equals(res[:, c, :].tolist(), res_k, want[c], None if exact else res_size * res_k, ("ks", rank_in, rank_out, c),
+                                       balanced=res_k == key_k)
 
 
 @pytest.mark.parametrize("fl", [O.NTT120, O.FFT64])
@@ -86,7 +87,8 @@ def test_external_product_equals_bigint_model(fl, dsize, a_k, key_k, res_k, a_si
         want = S.external_product_torus(ain.tolist(), ggsw.tolist(), key_k, dsize)
         exact = res_size * res_k >= key_size * key_k
         for c in range(rank + 1):
-            S.assert_normalised_equals(res[:, c, :].tolist(), res_k, want[c], None if exact else res_size * res_k, ("ep", rank, c))
+            S.assert_normalised_equals(res[:, c, :].tolist(), res_k, want[c], None if exact else res_size * res_k, ("ep", rank, c),
+                                       balanced=res_k == key_k)
 
 
 # ---- L4: noiseless keys ---------------------------------------------------------------------------------------------------------------
@@ -138,8 +140,9 @@ def test_noiseless_keyswitch_preserves_the_phase(fl, dsize):
 
 @pytest.mark.parametrize("fl", [O.NTT120, O.FFT64])
 def test_noiseless_external_product_multiplies_the_phase(fl):
-    """GGSW(m) with zero noise (poulpy-core/src/encryption/ggsw.rs: row d, column 0 encrypts m * 2^(-(d+1)k); column c > 0 encrypts
-    -m * s_{c-1} * 2^(-(d+1)k), so that sum_c a_c (*) row_c decrypts to m * phase(a)); m = X^e: the phase comes out rotated."""
+    """GGSW(m) with zero noise (poulpy-core/src/encryption/ggsw.rs:62-120 with glwe_encrypt_sk_internal, encryption/glwe.rs:426-510: row d,
+    column 0 has phase m * 2^(-(d+1)k), column c > 0 has phase m * s_{c-1} * 2^(-(d+1)k)), so sum_c a_c (*) row_c has phase
+    m * phase(a); m = X^e: the phase comes out rotated."""
     k, size, rank, e = 12, 4, 2, 5
     rng = np.random.default_rng(800 + fl)
     o = O.OracleModule(N, fl)
