@@ -198,3 +198,37 @@ def test_fft_roundtrip_and_evaluation(log_m):
             assert abs(want - (d[p] + 1j * d[m + p])) <= 1e-9 * m
     L.orc_fft64_ifft(md._h, O._p(d))
     assert np.max(np.abs(d / m - ramp)) <= 2.0 ** -(53 - log_m - 1) * 4
+
+
+def test_avx2_data_path_is_bit_identical_to_the_scalar_port():
+    """The "cpu-avx-style" leaves (four primes per __m256i: poulpy-cpu-avx/src/ntt120/ntt.rs:81-110, mat_vec_avx.rs) compute the same lazy
+    u64 in every lane as the scalar restatement of poulpy-cpu-ref: forward / inverse NTT values, vmp results and a whole key-switch and
+    blind rotation agree bit for bit (not just modulo Q_k), for every n the reduction schedule changes at."""
+    from util import fill_uniform
+    rng = np.random.default_rng(77)
+    try:
+        for n in (8, 64, 1024, 4096, 16384):
+            o = O.OracleModule(n, O.NTT120)
+            a = fill_uniform(rng, (3, 2, n), 40)
+            mat = fill_uniform(rng, (3, 1, 4, 2, n), 18)
+            got = []
+            for simd in (False, True):
+                O.ntt120_set_simd(simd)
+                d = o.vec_znx_dft_alloc(2, 3)
+                for c in range(2):
+                    o.vec_znx_dft_apply(1, 0, d, c, a, c)
+                fwd = np.array(d, copy=True)
+                pm = o.vmp_pmat_alloc(3, 1, 2, 4)
+                o.vmp_prepare(pm, mat)
+                a1 = np.ascontiguousarray(d[:, :1])
+                r = o.vec_znx_dft_alloc(2, 4)
+                o.vmp_apply_dft_to_dft(r, a1, pm, 0)
+                prod = np.array(r, copy=True)
+                big = o.vec_znx_idft_apply_consume(r)
+                res = np.zeros((3, 2, n), dtype=np.int64)
+                o.glwe_keyswitch(res, 18, fill_uniform(np.random.default_rng(5), (3, 2, n), 18), 18, pm, 18, 1)
+                got.append((fwd, prod, np.array(big, copy=True), res))
+            for x, y in zip(*got):
+                assert np.array_equal(x, y), n
+    finally:
+        O.ntt120_set_simd(False)
