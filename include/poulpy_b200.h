@@ -89,7 +89,7 @@ typedef enum {
     PGB_OPT_CGGI_VARIANT = 3,   /* PGB_CGGI_VARIANT: 0 = newest fused CGGI kernel, 1 / 2 / 3 = older generations (FFT64) */
     PGB_OPT_CGGI_BLOCK_BT1 = 4, /* PGB_CGGI_BLOCK_BT1: one ciphertext per thread in the FFT64 block kernel */
     PGB_OPT_VMP_NO_BT = 5,      /* PGB_VMP_NO_BT: no batch tiling in the NTT120 vmp */
-    PGB_OPT_VMP_CT = 6,         /* PGB_VMP_CT: output polys per thread of the NTT120 vmp (default 4) */
+    PGB_OPT_VMP_CT = 6,         /* PGB_VMP_CT: output polys per thread of the vmp kernels: 0 = chosen per launch (default), 2 / 4 (/ 8 NTT120) forced */
     PGB_OPT_GADGET_MB = 7,      /* PGB_GADGET_MB: resident clusters per SM the NTT120 gadget kernel is compiled for (3 or 4) */
     PGB_OPT_HOST_CHUNK_MB = 8,  /* PGB_HOST_CHUNK_MB: staging bytes per slot of the *_host pipelines (default 32) */
     PGB_OPT_CGGI_NTT_PRIMES = 9, /* PGB_CGGI_NTT_PRIMES: 0 = adaptive prime count in the NTT120 whole-rotation kernel, 2 / 3 / 4 = forced */
@@ -290,6 +290,14 @@ int pgb_glwe_keyswitch_host(pgb_module *m, int64_t *res_host, uint64_t res_size,
 int pgb_glwe_external_product_host(pgb_module *m, int64_t *res_host, uint64_t res_size, uint64_t res_base2k,
                                    const int64_t *a_host, uint64_t a_size, uint64_t a_base2k, uint64_t rank,
                                    const pgb_vmp_pmat *ggsw, uint64_t ggsw_base2k, uint64_t dsize, uint64_t count);
+
+/* One host call over several devices: `modules[i]` lives on its own CUDA device (or shares one), `keys[i]` is the replica of the prepared
+ * key in that device's memory; the `count` ciphertexts are split contiguously over the modules and every shard runs
+ * pgb_glwe_keyswitch_host on its own host thread.  This is what a Rust caller holding one `Module<B>` per GPU (Module is Sync + Send,
+ * poulpy-hal/src/layouts/module.rs:103-104) does with a thread pool; no collective is involved. */
+int pgb_glwe_keyswitch_host_sharded(pgb_module *const *modules, const pgb_vmp_pmat *keys, uint64_t n_modules, int64_t *res_host,
+                                    uint64_t res_size, uint64_t res_base2k, const int64_t *a_host, uint64_t a_size, uint64_t a_base2k,
+                                    uint64_t rank_in, uint64_t rank_out, uint64_t key_base2k, uint64_t dsize, uint64_t count);
 
 /* ---- bivariate convolution (oep/hal_impl.rs:670-754) ---------------------------------------------------
  * CnvPVecL / CnvPVecR (poulpy-hal/src/layouts/cnv_pvec.rs) are backend-owned prepared layouts; here both are DFT limbs in the

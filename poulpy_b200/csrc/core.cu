@@ -6,6 +6,10 @@
 // stream with no host round trip in between.
 #include <stdlib.h>
 
+#include <string>
+#include <thread>
+#include <vector>
+
 #include "internal.h"
 
 static const uint64_t ALIGN = 256;
@@ -1025,4 +1029,46 @@ extern "C" int pgb_glwe_external_product_host(pgb_module *m, int64_t *res_host, 
     PGB_REQUIRE(ggsw->cols_in == rank + 1 && ggsw->cols_out == rank + 1, "glwe_external_product_host: ggsw shape does not match the rank");
     return host_pipeline(m, true, res_host, rank + 1, res_size, res_base2k, a_host, rank + 1, a_size, a_base2k, ggsw, ggsw_base2k, dsize,
                          count);
+}
+
+// ---- one host call, several devices (Module is Sync + Send in the reference, poulpy-hal/src/layouts/module.rs:103-104: a Rust caller may
+// drive one Module per GPU from one thread pool).  The batch is split contiguously over the modules (the first count % n_modules shards get
+// one extra ciphertext, as poulpy_b200/sharding.py: shard_range), every shard runs the host pipeline of its module on its own host thread
+// and device, and the call returns when every shard of res_host is complete.  keys[i] is the replica of the prepared key on modules[i]'s
+// device (prepared keys are per-device memory).  No collective: the shards are independent.
+extern "C" int pgb_glwe_keyswitch_host_sharded(pgb_module *const *modules, const pgb_vmp_pmat *keys, uint64_t n_modules, int64_t *res_host,
+                                               uint64_t res_size, uint64_t res_base2k, const int64_t *a_host, uint64_t a_size,
+                                               uint64_t a_base2k, uint64_t rank_in, uint64_t rank_out, uint64_t key_base2k, uint64_t dsize,
+                                               uint64_t count) {
+    PGB_REQUIRE(modules && keys && n_modules >= 1, "glwe_keyswitch_host_sharded: no modules");
+    for (uint64_t i = 0; i < n_modules; i++) {
+        PGB_REQUIRE(modules[i] && modules[i]->n == modules[0]->n && modules[i]->flavour == modules[0]->flavour,
+                    "glwe_keyswitch_host_sharded: modules must share n and flavour");
+        for (uint64_t j = 0; j < i; j++) PGB_REQUIRE(modules[i] != modules[j], "glwe_keyswitch_host_sharded: a module may appear only once");
+    }
+    const uint64_t n = modules[0]->n;
+    const uint64_t a_item = n * (rank_in + 1) * a_size, r_item = n * (rank_out + 1) * res_size; // i64 words per ciphertext
+    std::vector<int> status(n_modules, PGB_OK);
+    std::vector<std::string> message(n_modules);
+    std::vector<std::thread> workers;
+    const uint64_t base = count / n_modules, extra = count % n_modules;
+    uint64_t first = 0;
+    for (uint64_t i = 0; i < n_modules; i++) {
+        const uint64_t cnt = base + (i < extra ? 1 : 0), start = first;
+        first += cnt;
+        if (cnt == 0) continue;
+        workers.emplace_back([=, &status, &message]() {
+            cudaSetDevice(modules[i]->device);
+            status[i] = pgb_glwe_keyswitch_host(modules[i], res_host + start * r_item, res_size, res_base2k, a_host + start * a_item, a_size,
+                                                a_base2k, rank_in, rank_out, &keys[i], key_base2k, dsize, cnt);
+            if (status[i] != PGB_OK) message[i] = pgb_last_error(); // the message lives in the worker's thread-local slot
+        });
+    }
+    for (auto &w : workers) w.join();
+    for (uint64_t i = 0; i < n_modules; i++)
+        if (status[i] != PGB_OK) {
+            pgb_set_error("glwe_keyswitch_host_sharded: shard %llu (device %d): %s", (unsigned long long)i, modules[i]->device, message[i].c_str());
+            return status[i];
+        }
+    return PGB_OK;
 }

@@ -537,7 +537,7 @@ struct FVmpArgs {
     uint32_t row_max, C, col0, ncols_out;
 };
 // each thread: two consecutive complex frequencies (double2 of re, double2 of im), CT output columns
-template <int CT> __global__ void __launch_bounds__(256) fft64_vmp_kernel(FVmpArgs p) {
+template <int CT> __global__ void __launch_bounds__(128) fft64_vmp_kernel(FVmpArgs p) {
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= p.m2) return;
     const uint32_t c0 = blockIdx.y * CT;
@@ -549,13 +549,14 @@ template <int CT> __global__ void __launch_bounds__(256) fft64_vmp_kernel(FVmpAr
     double2 accr[CT], acci[CT];
 #pragma unroll
     for (int c = 0; c < CT; c++) accr[c] = acci[c] = make_double2(0.0, 0.0);
-    for (uint32_t r = 0; r < p.row_max; r++) {
+#pragma unroll 2
+    for (uint32_t r = 0; r < p.row_max; r++) { // two rows of loads in flight per thread: the matrix is streamed once (evict-first)
         const double2 ar = __ldg(a + (size_t)r * poly_words), ai = __ldg(a + (size_t)r * poly_words + p.m2);
         const double2 *mrow = pm + (size_t)r * p.C * poly_words;
 #pragma unroll
         for (int c = 0; c < CT; c++) {
             if (c < nc) {
-                const double2 br = __ldg(mrow + (size_t)c * poly_words), bi = __ldg(mrow + (size_t)c * poly_words + p.m2);
+                const double2 br = __ldcs(mrow + (size_t)c * poly_words), bi = __ldcs(mrow + (size_t)c * poly_words + p.m2);
                 accr[c].x += ar.x * br.x - ai.x * bi.x;
                 accr[c].y += ar.y * br.y - ai.y * bi.y;
                 acci[c].x += ar.x * bi.x + ai.x * br.x;
@@ -575,10 +576,14 @@ int fft64_vmp(pgb_module *m, const char *a, uint64_t a_bs, char *res, uint64_t r
               uint32_t row_max, uint32_t C, uint32_t col0, uint32_t ncols_out, uint32_t batch) {
     if (ncols_out == 0 || batch == 0) return PGB_OK;
     FVmpArgs p = {a, a_bs, res, res_bs, pm, pm_bs, (uint32_t)(m->n / 4), row_max, C, col0, ncols_out};
-    constexpr int CT = 4;
-    dim3 block(128), grid((p.m2 + 127) / 128, (ncols_out + CT - 1) / CT, batch);
+    // output polys per thread: 2 (default) or 4 (PGB_OPT_VMP_CT).  Measured on B200 in the streaming regime (scripts/vmp_stream.py,
+    // profiles/r2_vmp_stream.md): two polys per thread reach 95-103 % of the measured copy bandwidth at every sweep shape, four 74-89 % --
+    // the re-reads of `a` that four would save are L2 hits, the extra CTAs and the 70 (vs 128) registers are what the stream needs
+    const int ct = m->opt[PGB_OPT_VMP_CT] == 4 ? 4 : 2;
+    dim3 block(128);
     { ProfScope _ps(m, PROF_VMP);
-    fft64_vmp_kernel<CT><<<grid, block, 0, m->stream>>>(p);
+    if (ct == 2) fft64_vmp_kernel<2><<<dim3((p.m2 + 127) / 128, (ncols_out + 1) / 2, batch), block, 0, m->stream>>>(p);
+    else fft64_vmp_kernel<4><<<dim3((p.m2 + 127) / 128, (ncols_out + 3) / 4, batch), block, 0, m->stream>>>(p);
     }
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;

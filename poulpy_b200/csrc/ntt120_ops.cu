@@ -132,25 +132,11 @@ int ntt120_vmp(pgb_module *m, const char *a, uint64_t a_bs, char *res, uint64_t 
         PGB_CHECK_CUDA(cudaGetLastError());
         return PGB_OK;
     }
-    // Output polys per thread: 4 halves the re-reads of `a` (L2 hits), 2 gives twice the CTAs at two thirds of the registers.  A launch of
-    // a few waves pays for every started wave, so the variant whose whole waves cover the fewest bytes wins: e.g. one product of the
-    // sweep's largest shape [14, 31, 1, 2, 32] is 2.3 waves of CT = 4 (3 CTAs/SM) but 2.8 waves of CT = 2 (5 CTAs/SM): 80 % vs 97 % useful.
-    int ct = ct_sel;
-    if (ct_sel == 4 && ncols_out > 2) {
-        static int occ_dev[32][2] = {};
-        int *occ = occ_dev[m->device & 31];
-        if (!occ[0]) {
-            PGB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], ntt120_vmp_kernel<2>, 256, 0));
-            PGB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], ntt120_vmp_kernel<4>, 256, 0));
-        }
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
-        const uint64_t xb = (words + 255) / 256;
-        const uint64_t items2 = xb * ((ncols_out + 1) / 2) * batch, items4 = xb * ((ncols_out + 3) / 4) * batch;
-        const uint64_t slots2 = (uint64_t)sms * occ[0], slots4 = (uint64_t)sms * occ[1];
-        const uint64_t cost2 = div_ceil64(items2, slots2) * slots2 * 2, cost4 = div_ceil64(items4, slots4) * slots4 * 4;
-        if (items4 < 16 * slots4 && cost2 < cost4) ct = 2; // many waves: quantisation is noise, keep the variant with fewer re-reads
-    }
+    // Output polys per thread: 2 (default), 4 or 8 (PGB_OPT_VMP_CT).  Measured on B200 (scripts/vmp_stream.py, profiles/r2_vmp_stream.md):
+    // two polys per thread are never slower than four (streaming regime 0.88-0.94 of the measured copy bandwidth against 0.77-0.81, one
+    // product of the largest sweep shape 0.88 against 0.71): the re-reads of `a` that a wider tile saves are L2 hits, while 52 registers
+    // (5 CTAs / SM) instead of 78 (3 CTAs / SM) give the stream the loads in flight it needs and a finer wave granularity
+    const int ct = ct_sel ? ct_sel : 2;
     { ProfScope _ps(m, PROF_VMP);
     if (ct == 2 || ncols_out <= 2) {
         dim3 grid((words + 255) / 256, (ncols_out + 1) / 2, batch);

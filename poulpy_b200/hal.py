@@ -788,6 +788,21 @@ class Module:
         return scratch
 
 
+def glwe_keyswitch_host_sharded(modules, keys, res: np.ndarray, res_base2k, a: np.ndarray, a_base2k, key_base2k, dsize=1):
+    """pgb_glwe_keyswitch_host_sharded: one call, one Module (and one replica of the prepared key) per device; res / a are host int64
+    arrays (batch, size, cols, n) split contiguously over the modules."""
+    B, a_size, a_cols, n = a.shape
+    hs = (C.c_void_p * len(modules))(*[m._h for m in modules])
+    ks = (_PM * len(keys))(*[k.struct() for k in keys])
+    _check(lib().pgb_glwe_keyswitch_host_sharded(hs, ks, _u64(len(modules)), C.c_void_p(res.ctypes.data), _u64(res.shape[1]), _u64(res_base2k),
+                                                 C.c_void_p(a.ctypes.data), _u64(a_size), _u64(a_base2k), _u64(a_cols - 1),
+                                                 _u64(res.shape[2] - 1), _u64(key_base2k), _u64(dsize), _u64(B)))
+
+
+def device_count():
+    return int(lib().pgb_device_count())
+
+
 def pool_trim():
     """cudaFree every block parked in the DevBuf pool."""
     for blocks in _POOL.values():

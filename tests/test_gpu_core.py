@@ -667,3 +667,36 @@ def test_noiseless_keyswitch_preserves_the_phase_on_the_device(fl, n):
         mod = 1 << (key_size * k)
         shift = 1 << ((key_size - a_size) * k)
         assert all((h - w * shift) % mod == 0 for h, w in zip(have, want)), b
+
+
+@pytest.mark.parametrize("two_devices", [False, True])
+def test_keyswitch_host_sharded_over_modules(two_devices):
+    """pgb_glwe_keyswitch_host_sharded: ONE host call drives several modules from several host threads (Module is Sync + Send in the
+    reference, poulpy-hal/src/layouts/module.rs:103-104).  two_devices = False: two modules on device 0 (thread safety of the library on
+    one GPU: separate streams, workspaces, thread-local errors); True: one module per GPU, each with its replica of the key (skipped on a
+    one-GPU box).  A ragged batch checks the contiguous split; results bit for bit against the oracle."""
+    if two_devices and pb.hal.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    n, k, batch = 1024, 18, 37
+    devs = (0, 1) if two_devices else (0, 0)
+    rng = np.random.default_rng(2000)
+    mat = fill_uniform(rng, (3, 1, 4, 2, n), k)
+    o = O.OracleModule(n, O.NTT120)
+    po = o.vmp_pmat_alloc(3, 1, 2, 4)
+    o.vmp_prepare(po, mat)
+    mods, keys = [], []
+    for d in devs:
+        m = pb.Module(n, pb.NTT120, device=d)
+        pm = m.vmp_pmat_alloc(3, 1, 2, 4)
+        m.vmp_prepare(pm, m.mat_znx_from_numpy(mat))
+        m.gadget_key_pin(pm)
+        mods.append(m)
+        keys.append(pm)
+    a = fill_uniform(rng, (batch, 3, 2, n), k)
+    want = np.zeros_like(a)
+    o.glwe_keyswitch_batch(want, k, a, k, po, k, 1)
+    res = np.full_like(a, -3)
+    pb.hal.glwe_keyswitch_host_sharded(mods, keys, res, k, a, k, k)
+    assert np.array_equal(res, want)
+    with pytest.raises(pb.PoulpyError):  # an error inside a shard surfaces in the caller's thread with the shard named
+        pb.hal.glwe_keyswitch_host_sharded(mods, keys, res[:, :, :1], k, a, k, k)
