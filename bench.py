@@ -486,6 +486,7 @@ def cggi_measure(pb, torch, dist, world, rank, local, with_cpu):
             m.vmp_prepare(pb.hal.VmpPMat(brk_buf, n, c["dnum"], cols, cols, c["brk_size"], offset=i * per), m.mat_znx_from_numpy(mats[i]))
         for i in range(8, n_lwe):
             lib.pgb_memcpy_d2d(C.c_void_p(brk_buf.ptr + i * per), C.c_void_p(brk_buf.ptr + (i % 8) * per), C.c_size_t(per))
+        m.gadget_key_pin(one)  # the BRK is immutable for the run: its coefficient bound (NTT120 prime count) is derived once
         xpa = m.cggi_x_pow_a()
         lut_np = rng.integers(-(1 << (k - 2)), 1 << (k - 2), size=(1, 1, n), dtype=np.int64)
         lut = m.vec_znx_from_numpy(lut_np)
