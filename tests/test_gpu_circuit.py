@@ -230,3 +230,58 @@ def test_circuit_bootstrap_to_exponent(fl, ext):
         o.ggsw_expand_row(want[b], K, tsk[1], K)
     assert np.array_equal(got, want)
     assert np.any(got[:, :, 0]) and np.any(got[:, :, 1])
+
+
+@pytest.mark.parametrize("fl", [pb.FFT64, pb.NTT120])
+@pytest.mark.parametrize("rank", [1, 2])
+def test_noiseless_circuit_bootstrap_on_the_device(fl, rank):
+    """L4 for circuit bootstrapping: noise-free BRK / ATK / TSK and noise-free LWEs of every message m.  The device
+    orchestration (poulpy_b200/circuit.py over the C ABI) must (a) equal, bit for bit, an INDEPENDENT restatement of
+    circuit_bootstrap_core written from circuit.rs over oracle primitives (tests/semantics_circuit.py -- nothing of circuit.py on that side)
+    and (b) produce GGSW(m): every row / column decrypts, with exact integer arithmetic, to m (resp. m s_c) at its gadget position."""
+    import semantics_circuit as SC
+    from test_oracle_circuit_semantics import check_ggsw
+    n, k, n_lwe, block, log_domain = 256, 12, 12, 3, 2
+    brk_size, dnum_res, res_size, lwe_size = 4, 2, 3, 2
+    cols = rank + 1
+    rng = np.random.default_rng(3100 + fl + rank)
+    g, o = pb.Module(n, fl), O.OracleModule(n, fl)
+    s_lwe, s, brk, atk, tsk = SC.build_keys(rng, n, k, rank, n_lwe, block, brk_size, brk_size, brk_size, brk_size + 1, res_size, res_size + 1)
+
+    def prep_o(mats):
+        out = []
+        for mat in mats:
+            d, ci, sz, co, _ = mat.shape
+            pm = o.vmp_pmat_alloc(d, ci, co, sz)
+            o.vmp_prepare(pm, mat)
+            out.append(pm)
+        return out
+
+    def prep_g(mats):
+        out = []
+        for mat in mats:
+            d, ci, sz, co, _ = mat.shape
+            pm = g.vmp_pmat_alloc(d, ci, co, sz)
+            g.vmp_prepare(pm, g.mat_znx_from_numpy(mat))
+            out.append(pm)
+        return out
+
+    per = n * brk_size * cols * cols * brk_size * g.prep_bytes
+    brk_buf = pb.DevBuf(per * n_lwe)
+    for i, mat in enumerate(brk):
+        g.vmp_prepare(pb.hal.VmpPMat(brk_buf, n, brk_size, cols, cols, brk_size, offset=i * per), g.mat_znx_from_numpy(mat))
+    brk_g = pb.hal.VmpPMat(brk_buf, n, brk_size, cols, cols, brk_size)
+    brk_o, atk_o, tsk_o = prep_o(brk), prep_o(atk), prep_o(tsk)
+    atk_g, tsk_g = prep_g(atk), prep_g(tsk)
+    msgs = list(range(1 << log_domain))
+    lwe = np.stack([SC.noiseless_lwe(rng, m, log_domain, s_lwe, k, lwe_size) for m in msgs])
+    lwe_dev = pb.DevBuf(lwe.nbytes)
+    lwe_dev.upload(lwe)
+    ggsw = circuit.circuit_bootstrap_to_constant(g, lwe_dev, len(msgs), n_lwe, lwe_size, k, brk_g, g.cggi_x_pow_a(), block, atk_g, tsk_g, k, rank,
+                                                 dnum_res, res_size, log_domain)
+    got = ggsw.download(np.int64, (len(msgs), dnum_res, cols, res_size, cols, n))
+    xpa = o.cggi_x_pow_a()
+    for b, m in enumerate(msgs):
+        want = SC.circuit_bootstrap_to_constant_ref(o, lwe[b], k, brk_o, xpa, block, atk_o, tsk_o, rank, dnum_res, res_size, log_domain, brk_size)
+        assert np.array_equal(got[b], want), m
+        check_ggsw(got[b], m, s, k, res_size)
