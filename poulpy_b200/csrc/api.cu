@@ -615,8 +615,16 @@ int vmp_apply_impl(pgb_module *m, pgb_vec_znx_dft *res, const pgb_vec_znx_dft *a
         const uint64_t col_max = umin64(ncols, res_polys + off); // ntt120/vmp.rs:189-190
         if (off >= col_max) return raw_limbs(m, true, R, R, poly, (uint32_t)res_polys, (uint32_t)bt->count);
         const uint64_t active = col_max - off;
+        // an odd col_max short of the matrix: the reference reads the last poly's column pair with the single-column stride (:262-273);
+        // reproduced verbatim by ntt120_vmp_odd_last (the columns before it are the plain product)
+        const bool quirk = (col_max & 1) && col_max < ncols;
         PGB_TRY(ntt120_vmp(m, (const char *)a->data, bt->stride_a, (char *)res->data, bt->stride_res, (const char *)pmat->data,
-                           bt->stride_b, (uint32_t)row_max, (uint32_t)ncols, (uint32_t)off, (uint32_t)active, (uint32_t)bt->count));
+                           bt->stride_b, (uint32_t)row_max, (uint32_t)ncols, (uint32_t)off, (uint32_t)(active - (quirk ? 1 : 0)),
+                           (uint32_t)bt->count));
+        if (quirk)
+            PGB_TRY(ntt120_vmp_odd_last(m, (const char *)a->data, bt->stride_a, (char *)res->data + (active - 1) * poly, bt->stride_res,
+                                        (const char *)pmat->data, bt->stride_b, (uint32_t)row_max, (uint32_t)ncols, (uint32_t)(col_max - 1),
+                                        (uint32_t)bt->count));
         return raw_limbs(m, true, shift(R, active), shift(R, active), poly, (uint32_t)(res_polys - active), (uint32_t)bt->count); // :282-287
     } else {
         const uint64_t col_max = umin64(ncols, res_polys); // fft64/vmp.rs:214-215

@@ -65,6 +65,8 @@ int fft64_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_col
 // ntt120_ops.cu
 int ntt120_vmp(pgb_module *m, const char *a, uint64_t a_bs, char *res, uint64_t res_bs, const char *pm, uint64_t pm_bs,
                uint32_t row_max, uint32_t C, uint32_t col0, uint32_t ncols_out, uint32_t batch);
+int ntt120_vmp_odd_last(pgb_module *m, const char *a, uint64_t a_bs, char *res_poly, uint64_t res_bs, const char *pm, uint64_t pm_bs,
+                        uint32_t row_max, uint32_t C, uint32_t last, uint32_t batch);
 int ntt120_ew(pgb_module *m, int op, LimbSet dst, LimbSet a, LimbSet b, uint32_t jobs, uint32_t batch);
 // fft64.cu
 int fft64_module_init(pgb_module *m);

@@ -153,6 +153,39 @@ int ntt120_vmp(pgb_module *m, const char *a, uint64_t a_bs, char *res, uint64_t 
     return PGB_OK;
 }
 
+// The reference's NTT120 vmp computes the LAST output poly of an odd col_max < ncols from the paired-column block of the prepared layout read
+// with the single-column stride (reference/ntt120/vmp.rs:262-273: vec_mat1col_product_x2 at `last * nrows * 16`): row i of the product
+// takes matrix row i >> 1, column last + (i & 1).  "Identical to the reference on the same inputs" includes this, so the shape gets its
+// own (cold) kernel instead of the mathematically defined product.
+__global__ void __launch_bounds__(256) ntt120_vmp_odd_last_kernel(VmpArgs p, uint32_t last) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= 4 * p.n4) return;
+    const PrimeRt pr(u / p.n4);
+    const size_t poly_words = (size_t)4 * p.n4;
+    const uint4 *a = reinterpret_cast<const uint4 *>(p.a + (size_t)blockIdx.z * p.a_bs) + u;
+    const uint4 *pm = reinterpret_cast<const uint4 *>(p.pm + (size_t)blockIdx.z * p.pm_bs) + u;
+    unsigned long long acc[4] = {0, 0, 0, 0};
+    for (uint32_t i = 0; i < p.row_max; i++) {
+        const uint4 av = __ldg(a + (size_t)i * poly_words);
+        const uint4 mv = __ldg(pm + ((size_t)(i >> 1) * p.C + last + (i & 1)) * poly_words);
+        acc[0] += (unsigned long long)av.x * mv.x; acc[1] += (unsigned long long)av.y * mv.y;
+        acc[2] += (unsigned long long)av.z * mv.z; acc[3] += (unsigned long long)av.w * mv.w;
+        if ((i & 15) == 15)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[j] = pr.reduce(acc[j]);
+    }
+    (reinterpret_cast<uint4 *>(p.res + (size_t)blockIdx.z * p.res_bs) + u)[0] =
+        make_uint4(pr.reduce(acc[0]), pr.reduce(acc[1]), pr.reduce(acc[2]), pr.reduce(acc[3]));
+}
+int ntt120_vmp_odd_last(pgb_module *m, const char *a, uint64_t a_bs, char *res_poly, uint64_t res_bs, const char *pm, uint64_t pm_bs,
+                        uint32_t row_max, uint32_t C, uint32_t last, uint32_t batch) {
+    VmpArgs p = {a, a_bs, res_poly, res_bs, pm, pm_bs, (uint32_t)(m->n / 4), row_max, C, 0, 1};
+    ProfScope _ps(m, PROF_VMP);
+    ntt120_vmp_odd_last_kernel<<<dim3(((uint32_t)m->n + 255) / 256, 1, batch), 256, 0, m->stream>>>(p, last);
+    PGB_CHECK_CUDA(cudaGetLastError());
+    return PGB_OK;
+}
+
 // ---- element-wise over limb sets ---------------------------------------------------------------------
 
 struct EwArgs {

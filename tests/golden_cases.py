@@ -12,18 +12,35 @@ N = 256
 
 
 def _k(fl):
-    return 12 if fl == 1 else 18  # FFT64 = 1 keeps products inside the f64 mantissa; NTT120 = 0 takes the bench base2k
+    return 12 if fl == 1 else 18  # the first FFT64 fixtures use base2k 12; the *_k18 cases below take the bench base2k in FFT64 too
+
+
+_K_OVERRIDE = [None]  # set by the *_k18 cases (FFT64 at the bench base2k = 18: |values| < 2^45 at N = 256, exact after rounding)
+
+
+def _kk(fl):
+    return _K_OVERRIDE[0] if _K_OVERRIDE[0] is not None else _k(fl)
+
+
+def _with_k(k, fn):
+    def run(*a):
+        _K_OVERRIDE[0] = k
+        try:
+            return fn(*a)
+        finally:
+            _K_OVERRIDE[0] = None
+    return run
 
 
 # ---- GLWE key-switch (rank 1 -> 1, 3 limbs, key of 3 rows x 4 limbs) and GGSW x GLWE external product ------------------------------
 def ks_inputs(rng, fl, cols_in):
-    k = _k(fl)
+    k = _kk(fl)
     return {"key": fill_uniform(rng, (3, cols_in, 4, 2, N), k), "a": fill_uniform(rng, (2, 3, 2, N), k)}
 
 
 def ks_oracle(fl, inp, ext):
     from oracle import pyoracle as O
-    o, k = O.OracleModule(N, fl), _k(fl)
+    o, k = O.OracleModule(N, fl), _kk(fl)
     cols_in = inp["key"].shape[1]
     pm = o.vmp_pmat_alloc(3, cols_in, 2, 4)
     o.vmp_prepare(pm, inp["key"])
@@ -34,7 +51,7 @@ def ks_oracle(fl, inp, ext):
 
 def ks_gpu(fl, inp, ext):
     import poulpy_b200 as pb
-    g, k = pb.Module(N, fl), _k(fl)
+    g, k = pb.Module(N, fl), _kk(fl)
     cols_in = inp["key"].shape[1]
     pm = g.vmp_pmat_alloc(3, cols_in, 2, 4)
     g.vmp_prepare(pm, g.mat_znx_from_numpy(inp["key"]))
@@ -46,14 +63,14 @@ def ks_gpu(fl, inp, ext):
 
 # ---- CGGI block-binary blind rotation (rank 1, one-limb accumulator, 6 LWE coefficients in blocks of 3) ------------------------------
 def br_inputs(rng, fl):
-    k = _k(fl)
+    k = _kk(fl)
     return {"brk": fill_uniform(rng, (6, 1, 2, 2, 2, N), k), "lut": fill_uniform(rng, (1, 1, N), k),
             "lwe": rng.integers(-N, N, size=(2, 7), dtype=np.int64)}
 
 
 def br_oracle(fl, inp):
     from oracle import pyoracle as O
-    o, k = O.OracleModule(N, fl), _k(fl)
+    o, k = O.OracleModule(N, fl), _kk(fl)
     brk = []
     for mat in inp["brk"]:
         pm = o.vmp_pmat_alloc(1, 2, 2, 2)
@@ -67,7 +84,7 @@ def br_oracle(fl, inp):
 
 def br_gpu(fl, inp):
     import poulpy_b200 as pb
-    g, k = pb.Module(N, fl), _k(fl)
+    g, k = pb.Module(N, fl), _kk(fl)
     per = N * 2 * 2 * 2 * g.prep_bytes
     buf = pb.DevBuf(per * 6)
     for i, mat in enumerate(inp["brk"]):
@@ -124,3 +141,11 @@ for _fl, _nm in ((0, "ntt120"), (1, "fft64")):
                                          lambda inp, fl=_fl: br_gpu(fl, inp))
     CASES[f"glwe_trace_{_nm}"] = (lambda rng, fl=_fl: tr_inputs(rng, fl), lambda inp, fl=_fl: tr_oracle(fl, inp),
                                   lambda inp, fl=_fl: tr_gpu(fl, inp))
+
+# FFT64 at the bench base2k ("add an FFT64 golden case at base2k 18")
+CASES["glwe_keyswitch_fft64_k18"] = (_with_k(18, lambda rng: ks_inputs(rng, 1, 1)), _with_k(18, lambda inp: ks_oracle(1, inp, False)),
+                                     _with_k(18, lambda inp: ks_gpu(1, inp, False)))
+CASES["glwe_external_product_fft64_k18"] = (_with_k(18, lambda rng: ks_inputs(rng, 1, 2)), _with_k(18, lambda inp: ks_oracle(1, inp, True)),
+                                            _with_k(18, lambda inp: ks_gpu(1, inp, True)))
+CASES["cggi_blind_rotate_fft64_k18"] = (_with_k(18, lambda rng: br_inputs(rng, 1)), _with_k(18, lambda inp: br_oracle(1, inp)),
+                                        _with_k(18, lambda inp: br_gpu(1, inp)))
