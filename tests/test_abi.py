@@ -58,3 +58,16 @@ def test_product_does_not_reference_the_oracle():
 
 def test_struct_layouts_match_header():
     assert C.sizeof(hal._VZ) == 40 and C.sizeof(hal._PP) == 24 and C.sizeof(hal._PM) == 48 and C.sizeof(hal._BT) == 32
+
+
+def test_rust_ffi_is_generated_from_the_header():
+    """rust/poulpy-gpu-b200/src/ffi.rs (the `extern "C"` block of the backend crate of INTEGRATION.md) is generated from the header: the
+    committed file must equal what scripts/gen_rust_ffi.py produces, and it binds every exported symbol."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(hal.HEADER_PATH))
+    spec = importlib.util.spec_from_file_location("gen_rust_ffi", os.path.join(root, "scripts", "gen_rust_ffi.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    src, fns = gen.generate()
+    assert open(gen.OUT).read() == src, "run python scripts/gen_rust_ffi.py"
+    assert sorted(n for n, _, _ in fns) == _declared()
