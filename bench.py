@@ -423,10 +423,14 @@ CGGI = dict(n=512, n_lwe=687, rank=3, block=3, base2k=18, brk_size=2, dnum=1, ac
 
 def cggi_ops_per_bootstrap(fl_name):
     """Algorithmic operation counts of one block-binary blind rotation at the bench shape, in the unit of the pipe
-    that binds the flavour.  FFT64: FP64-pipe instructions (FMA / MUL / ADD each count 1): a radix-2 complex butterfly = 2 MUL + 2 FMA +
-    4 ADD = 8, a complex multiply-accumulate of the key products = 4 FMA, the (X^a - 1) update per (frequency, output poly, key) = 2 MUL +
-    2 FMA + 4 ADD = 8, the scaling of the rounded coefficients = 1 MUL.  NTT120: Shoup/Harvey butterflies of the transforms (the unit of
-    profiles/r1_pipe_peaks.json); the key products (IMAD.WIDE) are reported beside them."""
+    that binds the flavour.
+    FFT64: FP64-pipe instructions (FMA / MUL / ADD each count 1): a radix-2 complex butterfly = 2 MUL + 2 FMA + 4 ADD = 8, a complex
+    multiply-accumulate of the key products = 4 FMA, the (X^a - 1) update per (frequency, output poly, key) = 2 MUL + 2 FMA + 4 ADD = 8,
+    the scaling of the rounded coefficients = 1 MUL.
+    NTT120: issue slots of the FMA-heavy integer pipe (the pipe profiles/r1_pipe_peaks.json measures with imad_lo_u32; IMAD.HI is half
+    rate = 2 slots): a Shoup / Harvey butterfly = IMAD.HI + 2 IMAD = 4 slots, a modular multiply-accumulate of the key products = 1
+    IMAD.WIDE = 1 slot, the (X^a - 1) product per (frequency, output poly, key) = 1 slot; reductions and address arithmetic are not
+    counted.  Returned per PRIME: the kernel runs two primes when the device-checked bound allows, the reference always four."""
     c = CGGI
     n, m = c["n"], c["n"] // 2
     cols = c["rank"] + 1
@@ -438,7 +442,9 @@ def cggi_ops_per_bootstrap(fl_name):
         tail = C * n
         return blocks * (fft + prod + tail), "FP64-pipe instructions (FMA/MUL/ADD)"
     log_n = n.bit_length() - 1
-    return blocks * (R + C) * (n // 2) * log_n, "Shoup/Harvey butterflies per prime"
+    butterflies = (R + C) * (n // 2) * log_n
+    macs = n * C * bs * (R + 1)
+    return blocks * (4 * butterflies + macs), "FMA-heavy integer pipe slots (butterfly = 4, modular MAC = 1)"
 
 
 def cggi_measure(pb, torch, dist, world, rank, local, with_cpu):
@@ -532,15 +538,20 @@ def cggi_measure(pb, torch, dist, world, rank, local, with_cpu):
                      "d2h_bytes_per_step": int(res_h.nbytes), "api": "pgb_cggi_blind_rotate_host (pinned host LWEs in, host GLWEs out)",
                      "matches_device_resident": same}}
         if pk:
-            peak_key = "dfma" if nm == "fft64" else "ct_butterfly(harvey,shoup)"
-            primes = 4 if nm == "ntt120" else 1
-            ach = ops * primes * B / (ms * 1e-3) if nm == "ntt120" else ops * B / (ms * 1e-3)
-            d["roofline"] = {"bound": "fp64_issue" if nm == "fft64" else "int_issue", "achieved": ach, "peak": pk[peak_key]["chip_per_s"],
-                             "unit": unit + "/s", "frac": ach / pk[peak_key]["chip_per_s"], "ops_per_bootstrap": ops * primes,
-                             "peak_source": "scripts/pipe_peaks.cu on B200 (profiles/r1_pipe_peaks.json)",
-                             "note": ("four-prime count; the whole-rotation kernel runs fewer primes when the device-checked bound allows "
-                                      "(DESIGN.md): the fraction is quoted against the reference's four-prime work"
-                                      if nm == "ntt120" else "DFMA issue rate; operation count from cggi_ops_per_bootstrap")}
+            if nm == "fft64":
+                ach, peak_v = ops * B / (ms * 1e-3), pk["dfma"]["chip_per_s"]
+                d["roofline"] = {"bound": "fp64_issue", "achieved": ach, "peak": peak_v, "unit": unit + "/s", "frac": ach / peak_v,
+                                 "ops_per_bootstrap": ops, "peak_source": "scripts/pipe_peaks.cu on B200 (profiles/r1_pipe_peaks.json: dfma)",
+                                 "note": "operation count from cggi_ops_per_bootstrap; ncu: FP64 pipe 40 % busy (profiles/r2_ncu_cggi.md)"}
+            else:
+                primes = 2 if launches <= 4 else 4  # the whole-rotation kernel (one launch) runs two primes; the limb-wise route four
+                ach, peak_v = ops * primes * B / (ms * 1e-3), pk["imad_lo_u32"]["chip_per_s"]
+                d["roofline"] = {"bound": "int_issue", "achieved": ach, "peak": peak_v, "unit": unit + "/s", "frac": ach / peak_v,
+                                 "ops_per_bootstrap": ops * primes, "primes_computed": primes,
+                                 "frac_if_counted_as_four_prime_work": ops * 4 * B / (ms * 1e-3) / peak_v,
+                                 "peak_source": "scripts/pipe_peaks.cu on B200 (profiles/r1_pipe_peaks.json: imad_lo_u32)",
+                                 "note": "algorithmic slots of the primes actually computed (two when the device-checked bound allows: DESIGN.md "
+                                         "3.6); ncu: FMA-heavy pipe 67 % busy including reductions and address arithmetic (profiles/r2_ncu_cggi.md)"}
         out[nm] = d
         if with_cpu and nm == "fft64":  # the reference benches CGGI in FFT64: oracle port on the host cores, bounded sample
             from oracle import pyoracle as O
