@@ -156,3 +156,42 @@ def test_cggi_blind_rotate_host_front_end(fl):
         res_h[:] = -7
         g.cggi_blind_rotate_host(res_h, lwe_h, k, g.vec_znx_from_numpy(lut), gbrk, xg, block, k)
         assert np.array_equal(res_h, want[idx]), pinned
+
+
+@pytest.mark.parametrize("fl", [pb.FFT64, pb.NTT120])
+def test_circuit_bootstrap_bench_shape_whole_circuit(fl):
+    """The WHOLE constant-mode circuit bootstrap at the reference's bench shape (poulpy-bench circuit_bootstrapping.rs:47-129 as bench.py
+    times it: n=1024, n_lwe=574, block 7, rank 2, base2k 13, BRK / ATK / TSK with 3 rows x 4 limbs, result 2 rows x 2 limbs, 1-bit
+    domain) with uniform random key digits: the device orchestration against the independent restatement of circuit_bootstrap_core over
+    the oracle (tests/semantics_circuit.py), bit for bit, for three LWEs."""
+    import semantics_circuit as SC
+    from poulpy_b200 import circuit
+    n, log_n, n_lwe, block, rank, k, batch = 1024, 10, 574, 7, 2, 13, 3
+    cols, ksz, kd, res_size, dnum_res, log_domain = rank + 1, 4, 3, 2, 2, 1
+    rng = np.random.default_rng(4060 + fl)
+    g, o = pb.Module(n, fl), O.OracleModule(n, fl)
+    gbrk, obrk = _brk(g, o, n, cols, kd, ksz, n_lwe, k, rng)
+
+    def keys(count):
+        out_g, out_o = [], []
+        for _ in range(count):
+            mt = fill_uniform(rng, (kd, rank, ksz, cols, n), k)
+            pg, po = g.vmp_pmat_alloc(kd, rank, cols, ksz), o.vmp_pmat_alloc(kd, rank, cols, ksz)
+            g.vmp_prepare(pg, g.mat_znx_from_numpy(mt))
+            o.vmp_prepare(po, mt)
+            out_g.append(pg)
+            out_o.append(po)
+        return out_g, out_o
+
+    atk_g, atk_o = keys(log_n)
+    tsk_g, tsk_o = keys(rank)
+    lwe = fill_uniform(rng, (batch, 1, 1, n_lwe + 1), k)
+    lwe_dev = pb.DevBuf(lwe.nbytes)
+    lwe_dev.upload(lwe)
+    ggsw = circuit.circuit_bootstrap_to_constant(g, lwe_dev, batch, n_lwe, 1, k, gbrk, g.cggi_x_pow_a(), block, atk_g, tsk_g, k, rank, dnum_res,
+                                                 res_size, log_domain)
+    got = ggsw.download(np.int64, (batch, dnum_res, cols, res_size, cols, n))
+    xpa = o.cggi_x_pow_a()
+    for b in range(batch):
+        want = SC.circuit_bootstrap_to_constant_ref(o, lwe[b], k, obrk, xpa, block, atk_o, tsk_o, rank, dnum_res, res_size, log_domain, ksz)
+        assert np.array_equal(got[b], want), b
