@@ -242,7 +242,7 @@ def test_noiseless_circuit_bootstrap_on_the_device(fl, rank):
     import semantics_circuit as SC
     from test_oracle_circuit_semantics import check_ggsw
     n, k, n_lwe, block, log_domain = 256, 12, 12, 3, 2
-    brk_size, dnum_res, res_size, lwe_size = 4, 2, 3, 2
+    brk_size, dnum_res, res_size, lwe_size = 4, 2, 4, 2
     cols = rank + 1
     rng = np.random.default_rng(3100 + fl + rank)
     g, o = pb.Module(n, fl), O.OracleModule(n, fl)
