@@ -1002,11 +1002,17 @@ int cggi_fused_fft64(pgb_module *m, long long *res, uint64_t res_stride_words, c
                      int out_size, int batch) {
     CggiFusedArgs p = {res, res_stride_words, lwe, lwe_stride, brk, brk_doubles, xpa, n_lwe, block_size, base2k, cols, dnum, brk_size, out_size, batch};
     const int R = cols * dnum, C = cols * brk_size;
-    if (block_size <= 3 && m->opt[PGB_OPT_CGGI_VARIANT] == 0 && (brk_doubles % 2) == 0 && brk_size <= 4 && m->log_n == 9 && (R == 4 || R == 2) && C <= 8) {
-        // version 4 (dedicated ring warp), instantiated for the BASELINE family: n = 512, four (rank 3) or two (rank 1) input polys, blocks
-        // of at most three keys
-        if (R == 4) return C > 4 ? launch_cggi4<8, 4, 4, 8, 4, 3>(m, p) : launch_cggi4<8, 4, 4, 4, 4, 3>(m, p);
-        return C > 4 ? launch_cggi4<8, 4, 2, 8, 4, 3>(m, p) : launch_cggi4<8, 4, 2, 4, 4, 3>(m, p);
+    if (block_size <= 3 && m->opt[PGB_OPT_CGGI_VARIANT] == 0 && (brk_doubles % 2) == 0 && brk_size <= 4 && m->log_n >= 8 && m->log_n <= 10 &&
+        (R == 4 || R == 2) && C <= 8) {
+        // version 4 (dedicated ring warp): n = 256 / 512 / 1024 (8 / 4 / 2 ciphertexts per CTA), four (rank 3) or two (rank 1) input polys,
+        // blocks of at most three keys -- the BASELINE family
+#define CGGI4_SHAPES(LM, G, NS)                                                                                          \
+        if (R == 4) return C > 4 ? launch_cggi4<LM, G, 4, 8, NS, 3>(m, p) : launch_cggi4<LM, G, 4, 4, NS, 3>(m, p);       \
+        return C > 4 ? launch_cggi4<LM, G, 2, 8, NS, 3>(m, p) : launch_cggi4<LM, G, 2, 4, NS, 3>(m, p);
+        if (m->log_n == 8) { CGGI4_SHAPES(7, 8, 4) }
+        if (m->log_n == 9) { CGGI4_SHAPES(8, 4, 4) }
+        { CGGI4_SHAPES(9, 2, 2) }
+#undef CGGI4_SHAPES
     }
     if (block_size <= 8 && (m->opt[PGB_OPT_CGGI_VARIANT] == 0 || m->opt[PGB_OPT_CGGI_VARIANT] >= 3) && (brk_doubles % 2) == 0 && brk_size <= 4) {
         // TMA key stream (tiles must be 16-byte aligned: brk is a cudaMalloc'd / 64-byte aligned buffer of whole polys)

@@ -14,6 +14,8 @@ rng = np.random.default_rng(1)
 mat = rng.integers(-(1 << 17), 1 << 17, size=(3, 1, 4, 2, n), dtype=np.int64)
 pm = m.vmp_pmat_alloc(3, 1, 2, 4)
 m.vmp_prepare(pm, m.mat_znx_from_numpy(mat))
+if os.environ.get("KS_PIN"):
+    m.gadget_key_pin(pm)
 a = m.vec_znx_from_numpy(rng.integers(-(1 << 17), 1 << 17, size=(B, 3, 2, n), dtype=np.int64))
 r = m.vec_znx_alloc(2, 3, B)
 sc = None
