@@ -618,6 +618,8 @@ def aux_measurements(pb, torch, local, peak):
 
         ms = _time_ms(torch, stream, f, 10)
         aux[f"glwe_external_product_per_s_{nm}_n2048_b4096"] = B / (ms * 1e-3)
+        if fl == pb.NTT120:  # three primes carry the integers of this shape (pinned key, device-checked bound; ntt120_gadget.cu)
+            aux["glwe_external_product_ntt120_primes"] = m.get_option(pb.hal.OPT_LAST_GADGET_PRIMES)
         del m, a, r, pm, sc
     # key-switch in the FFT64 flavour (row M1f)
     n, B, k = 4096, 4096, 18

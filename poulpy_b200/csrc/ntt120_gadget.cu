@@ -12,7 +12,6 @@
 //   * max(R, cols_out) polynomials live in swizzled (unpadded) shared memory, 16 coefficients per thread;
 //   * radix-16 register passes (four butterfly levels per shared-memory round trip), Shoup multiplication, Harvey lazy ranges;
 //   * the R forward transforms run in lock step so that the per-thread twiddles are fetched once per pass;
-//   * the first pass' 15 twiddles are CTA-uniform and come from the kernel parameter bank;
 //   * products with the collapsed key accumulate in u64 and are reduced once;
 //   * CRT needs all four residues of a coefficient: CTA k reconstructs the k-th quarter of the coefficients and reads the other
 //     three residues from its peers through distributed shared memory (ld.shared::cluster), then emits the base-2^K digits.
@@ -29,10 +28,6 @@ using namespace n120;
 
 namespace {
 
-struct TopTw {
-    uint2 f[16], i[16]; // block twiddles 1..15 of one prime, forward / inverse (index 0 unused)
-};
-
 struct GadgetArgs {
     const char *in;  unsigned long long in_bs;      // GLWE inputs (i64), limb (j, col) at ((j * in_cols + col) * n) words
     char *res;       unsigned long long res_bs;     // GLWE outputs (i64), limb (j, col) at ((j * cols_out + col) * n) words
@@ -42,7 +37,7 @@ struct GadgetArgs {
     int in_cols, row_cols, row_col0, R, cols_out;
     int small_size;                                 // limbs of input column 0 added to output column 0 (key-switch), 0 = none
     int K, S, res_size;                             // base2k, key size (digits of the collapsed integer), output limbs
-    int base_bits;                                  // ceil(log2(R * n)) + (S - 1) * K + 3
+    int bound_bits;                                 // an input passes when its bit length <= bound_bits - key_bits (see ntt120_gadget_fused)
     int batch;
     // automorphism epilogue (AUT instances only): output coefficient j' takes source coefficient j = j' * aut_pinv mod 2n (sign flipped
     // when that product lands in [n, 2n)).  x = CRT value + body.  mode 1: res = normalize(aut(x) + a), 2: normalize(aut(x) - a),
@@ -52,12 +47,13 @@ struct GadgetArgs {
     int aut_mode, post_size;
     uint32_t aut_pinv;
     uint32_t zero;                                  // always 0 (see ct_bfz)
-    uint32_t m_w[4][4];                             // M_k = Q / Q[k], four 32-bit words each (arithmetic.rs:119-140)
+    // CRT over the NP primes the launch works with (Q = their product): NP = 4 is the reference's Q120 (arithmetic.rs:119-140), NP = 3
+    // the same integers reconstructed from three residues when they are known to stay below Q[0] Q[1] Q[2] / 2
+    uint32_t m_w[4][4];                             // M_k = Q / Q[k], four 32-bit words each
     uint32_t nq_w[4];                               // 2^128 - Q
     unsigned long long half_lo, half_hi;            // sum_j 2^(K-1) 2^(jK), j < S (mod 2^128)
     uint32_t inv60[4];                              // floor(2^60 / Q[k]) (31 bits)
-    uint32_t crt_ninv[4], crt_ninv_sh[4];           // CRT_CST[k] / n mod Q[k] and its Shoup companion
-    TopTw top[4];
+    uint32_t crt_ninv[4], crt_ninv_sh[4];           // (Q / Q[k])^-1 / n mod Q[k] (CRT_CST[k] / n for NP = 4) and its Shoup companion
     struct { uint32_t q, c32, c32s, neg64; } prime[4];
 };
 
@@ -213,21 +209,6 @@ struct TwLast {
         }
     }
 };
-// the 15 CTA-uniform twiddles of the top pass, straight from the kernel parameter bank
-struct TwTopConst {
-    const uint2 *w; // 16 entries, node indices 1..15
-    __device__ __forceinline__ uint2 get1() const { return w[1]; }
-    __device__ __forceinline__ void get2(uint2 (&o)[2]) const { o[0] = w[2]; o[1] = w[3]; }
-    __device__ __forceinline__ void get4(uint2 (&o)[4]) const {
-#pragma unroll
-        for (int i = 0; i < 4; i++) o[i] = w[4 + i];
-    }
-    __device__ __forceinline__ void get8(uint2 (&o)[8]) const {
-#pragma unroll
-        for (int i = 0; i < 8; i++) o[i] = w[8 + i];
-    }
-};
-
 // L2 prefetch of a contiguous global range by one thread (TMA bulk prefetch; bytes must be a multiple of 16)
 __device__ __forceinline__ void prefetch_l2_bulk(const void *gptr, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
@@ -276,7 +257,45 @@ template <int L> __host__ __device__ constexpr int fmask(int i) {
     return (((i >> 5) & 3) << 2) ^ (GGeo<L>::SIG3 ? (((i >> 7) & 3) << 3) : (((i >> 8) & 1) << 4));
 }
 
-template <int L, bool AUT> __device__ __forceinline__ void gadget_body(const GadgetArgs &p, uint32_t *__restrict__ sm, const uint2 *__restrict__ twf,
+// Low 32-bit words of v = sum_k t_k M_k - e Q (mod 2^128) for the coefficient at byte offset `off` of every CTA's planes, with
+// e = round(sum t_k / Q[k]): |v| < Q (1/2 - 2^-27) here, so a 2^-28-accurate estimate of the fraction (60 fractional bits, truncated
+// constants) always rounds to the right integer.  Column sums of 32-bit words, -e Q folded in as + e (2^128 - Q); `nwords` = how many
+// words the digits need (ceil(S K / 32)), the others are returned as 0.
+template <int NP> __device__ __forceinline__ void crt_low_words(const GadgetArgs &p, const uint32_t (&rb)[NP], const uint32_t off, const int nwords,
+                                                               uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3) {
+    uint32_t tk[NP];
+#pragma unroll
+    for (int k = 0; k < NP; k++) tk[k] = ld_cluster(rb[k] + off);
+    unsigned long long fr = 1ull << 59;
+#pragma unroll
+    for (int k = 0; k < NP; k++) fr += (unsigned long long)tk[k] * p.inv60[k];
+    const uint32_t e = (uint32_t)(fr >> 60);
+    unsigned long long a0 = (unsigned long long)e * p.nq_w[0];
+#pragma unroll
+    for (int k = 0; k < NP; k++) a0 += (unsigned long long)tk[k] * p.m_w[k][0];
+    unsigned long long a1 = (a0 >> 32) + (unsigned long long)e * p.nq_w[1];
+#pragma unroll
+    for (int k = 0; k < NP; k++) a1 += (unsigned long long)tk[k] * p.m_w[k][1];
+    w0 = (uint32_t)a0; w1 = (uint32_t)a1; w2 = 0; w3 = 0;
+    if (nwords > 2) {
+        unsigned long long a2 = (a1 >> 32) + (unsigned long long)e * p.nq_w[2];
+        if (NP == 4) { // three-prime M_k are below 2^60
+#pragma unroll
+            for (int k = 0; k < NP; k++) a2 += (unsigned long long)tk[k] * p.m_w[k][2];
+        }
+        w2 = (uint32_t)a2;
+        if (nwords > 3) {
+            unsigned long long a3 = (a2 >> 32) + (unsigned long long)e * p.nq_w[3];
+            if (NP == 4) {
+#pragma unroll
+                for (int k = 0; k < NP; k++) a3 += (unsigned long long)tk[k] * p.m_w[k][3];
+            }
+            w3 = (uint32_t)a3;
+        }
+    }
+}
+
+template <int L, bool AUT, int NP> __device__ __forceinline__ void gadget_body(const GadgetArgs &p, uint32_t *__restrict__ sm, const uint2 *__restrict__ twf,
                                                              const uint2 *__restrict__ twi, const uint4 *__restrict__ lastf,
                                                              const uint4 *__restrict__ lasti, const int K) {
     typedef GGeo<L> G;
@@ -285,14 +304,14 @@ template <int L, bool AUT> __device__ __forceinline__ void gadget_body(const Gad
     const uint32_t q = pc.q, z = p.zero;
     const int t = threadIdx.x;
     cg::cluster_group cluster = cg::this_cluster();
-    const int nclusters = gridDim.x / 4, cid = blockIdx.x / 4;
+    const int nclusters = gridDim.x / NP, cid = blockIdx.x / NP;
     const TwGlobal top_f = {twf, 1u}, top_i = {twi, 1u}; // CTA-uniform addresses: one L1 broadcast per load
     const int R = p.R, cols_out = p.cols_out;
-    const int amax_allowed = 118 - p.base_bits - __ldg(p.key_bits) - 1; // see ntt120_dft.cu (collapsed-key bound), one spare bit
+    const int amax_allowed = p.bound_bits - __ldg(p.key_bits); // see ntt120_gadget_fused (collapsed-key bound)
     const uint32_t sm_base = (uint32_t)__cvta_generic_to_shared(sm);
-    uint32_t rb[4]; // shared::cluster addresses of the four CTAs' plane 0
+    uint32_t rb[NP]; // shared::cluster addresses of the NP CTAs' plane 0
 #pragma unroll
-    for (int k = 0; k < 4; k++) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb[k]) : "r"(sm_base), "r"(k));
+    for (int k = 0; k < NP; k++) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb[k]) : "r"(sm_base), "r"(k));
     // swizzled word addresses: stride-T pattern = (st ^ const) + j*T, 16-consecutive pattern = qa[c], stride-2^SG2 pattern = sb ^ const
     const int st = swz<L>(t);
     const int sb = swz<L>(pass_base<L, G::SG2>(t));
@@ -306,8 +325,8 @@ template <int L, bool AUT> __device__ __forceinline__ void gadget_body(const Gad
         const long long *in = reinterpret_cast<const long long *>(p.in + (size_t)ct * p.in_bs);
         // L2 prefetch (one thread per 8n-byte limb, spread over the four CTAs): the body limbs this ciphertext needs in its CRT phase and
         // the mask limbs of the cluster's next ciphertext
-        if ((t & 3) == K && (t >> 2) < R + p.small_size) {
-            const int u = t >> 2;
+        if ((t % NP) == K && (t / NP) < R + p.small_size) {
+            const int u = t / NP;
             if (u < p.small_size) {
                 prefetch_l2_bulk(in + (size_t)u * p.in_cols * n, n * 8);
             } else if (ct + nclusters < p.batch) {
@@ -475,46 +494,36 @@ template <int L, bool AUT> __device__ __forceinline__ void gadget_body(const Gad
         }
         cl_arrive();
         cl_wait(); // all four residues of every coefficient are in place
-        // ---- CRT + digits for coefficient quarter K ----------------------------------------------------------------------------
+        // ---- CRT + digits: CTA K takes the coefficient chunks K, K + NP, ... of T consecutive coefficients (16 chunks per polynomial) ------
         {
             const int Kb = p.K, S = p.S;
             const int a_start = p.res_size < S ? p.res_size : S; // digits j >= a_start are discarded (carry only)
             const size_t res_ls = (size_t)cols_out * n, in_ls = (size_t)p.in_cols * n;
-            const bool four_words = S * Kb > 96;
+            const int nwords = (S * Kb + 31) >> 5;
             const bool narrow = Kb < 32; // digit fields inside one 32-bit word: funnel shifts over four words
             const unsigned long long kmask = (1ull << Kb) - 1, khalf = 1ull << (Kb - 1);
             const uint32_t kmask32 = (uint32_t)kmask, khalf32 = (uint32_t)khalf;
             const uint32_t hw0 = (uint32_t)p.half_lo, hw1 = (uint32_t)(p.half_lo >> 32), hw2 = (uint32_t)p.half_hi, hw3 = (uint32_t)(p.half_hi >> 32);
-            long long *res_ct = reinterpret_cast<long long *>(p.res + (size_t)ct * p.res_bs) + K * (n / 4) + t;
-            const long long *in_kt = in + K * (n / 4) + t + (size_t)(S - 1) * in_ls; // body limb S - 1 (column 0)
+            long long *res_ct = reinterpret_cast<long long *>(p.res + (size_t)ct * p.res_bs) + t;
+            const long long *in_kt = in + t + (size_t)(S - 1) * in_ls; // body limb S - 1 (column 0)
             if constexpr (AUT) {
-                // Automorphism epilogue (see GadgetArgs): this thread still owns OUTPUT coefficients K n/4 + i T + t (coalesced stores and
+                // Automorphism epilogue (see GadgetArgs): this thread still owns OUTPUT coefficients chunk T + t (coalesced stores and
                 // reads of `a`); residues and body limbs are gathered at the source coefficient.
                 const int mode = p.aut_mode;
                 for (int o = 0; o < cols_out; o++) {
                     const bool with_small = o == 0 && p.small_size > 0;
 #pragma unroll 1
-                    for (int i = 0; i < 4; i++) {
-                        const int jo = K * (n / 4) + i * T + t;
+                    for (int chunk = K; chunk < 16; chunk += NP) {
+                        const int jo = chunk * T + t;
                         const uint32_t j0 = ((uint32_t)jo * p.aut_pinv) & (uint32_t)(2 * n - 1);
                         const int js = (int)(j0 & (uint32_t)(n - 1));
                         const bool flip = j0 >= (uint32_t)n;            // sign of the permuted coefficient
                         const bool negx = mode == 4 ? false : (mode == 3 ? !flip : flip); // sign applied to x before the digits
                         const uint32_t off = (uint32_t)(o * n + swz<L>(js)) * 4u;
-                        const uint32_t t0 = ld_cluster(rb[0] + off), t1 = ld_cluster(rb[1] + off), t2 = ld_cluster(rb[2] + off), t3 = ld_cluster(rb[3] + off);
-                        const unsigned long long fr = (unsigned long long)t0 * p.inv60[0] + (unsigned long long)t1 * p.inv60[1] +
-                                                      (unsigned long long)t2 * p.inv60[2] + (unsigned long long)t3 * p.inv60[3];
-                        const uint32_t e = (uint32_t)((fr + (1ull << 59)) >> 60);
-                        const unsigned long long a0 = (unsigned long long)t0 * p.m_w[0][0] + (unsigned long long)t1 * p.m_w[1][0] +
-                                                      (unsigned long long)t2 * p.m_w[2][0] + (unsigned long long)t3 * p.m_w[3][0] + (unsigned long long)e * p.nq_w[0];
-                        const unsigned long long a1 = (a0 >> 32) + (unsigned long long)t0 * p.m_w[0][1] + (unsigned long long)t1 * p.m_w[1][1] +
-                                                      (unsigned long long)t2 * p.m_w[2][1] + (unsigned long long)t3 * p.m_w[3][1] + (unsigned long long)e * p.nq_w[1];
-                        const unsigned long long a2 = (a1 >> 32) + (unsigned long long)t0 * p.m_w[0][2] + (unsigned long long)t1 * p.m_w[1][2] +
-                                                      (unsigned long long)t2 * p.m_w[2][2] + (unsigned long long)t3 * p.m_w[3][2] + (unsigned long long)e * p.nq_w[2];
-                        const unsigned long long a3 = (a2 >> 32) + (unsigned long long)t0 * p.m_w[0][3] + (unsigned long long)t1 * p.m_w[1][3] +
-                                                      (unsigned long long)t2 * p.m_w[2][3] + (unsigned long long)t3 * p.m_w[3][3] + (unsigned long long)e * p.nq_w[3];
+                        uint32_t w0, w1, w2, w3;
+                        crt_low_words<NP>(p, rb, off, 4, w0, w1, w2, w3);
                         // u = +-v + half as a 128-bit integer in two 64-bit words (mod 2^128; only the low S K bits are read)
-                        unsigned long long lo = (a0 & 0xffffffffull) | (a1 << 32), hi = (a2 & 0xffffffffull) | (a3 << 32);
+                        unsigned long long lo = (unsigned long long)w0 | ((unsigned long long)w1 << 32), hi = (unsigned long long)w2 | ((unsigned long long)w3 << 32);
                         if (negx) {
                             lo = ~lo + 1;
                             hi = ~hi + (lo == 0);
@@ -566,11 +575,11 @@ template <int L, bool AUT> __device__ __forceinline__ void gadget_body(const Gad
             for (int o = 0; o < cols_out; o++) {
                 const bool with_small = o == 0 && p.small_size > 0;
 #pragma unroll 1
-                for (int i = 0; i < 4; i++) {
+                for (int chunk = K; chunk < 16; chunk += NP) {
                     // body limbs that join column 0 (vec_znx_big_add_small_assign), least significant digit first: sm4[s] belongs to
                     // digit step s (limb S-1-s); issued first so that their latency hides behind the CRT arithmetic
                     long long sm4[4] = {0, 0, 0, 0};
-                    const long long *sp = in_kt + i * T;
+                    const long long *sp = in_kt + chunk * T;
                     if (with_small) {
 #pragma unroll
                         for (int s4 = 0; s4 < 4; s4++) {
@@ -578,34 +587,48 @@ template <int L, bool AUT> __device__ __forceinline__ void gadget_body(const Gad
                             sp -= in_ls;
                         }
                     }
-                    const uint32_t off = (uint32_t)(o * n + (swz<L>(K * (n / 4) + i * T) ^ st)) * 4u;
-                    const uint32_t t0 = ld_cluster(rb[0] + off), t1 = ld_cluster(rb[1] + off), t2 = ld_cluster(rb[2] + off), t3 = ld_cluster(rb[3] + off);
-                    // v = sum t_k M_k - e Q with e = round(sum t_k / Q[k]); |v| < 2^118 < Q/4 here, so a 2^-28-accurate estimate of
-                    // the fraction (60 fractional bits, truncated constants) always rounds to the right integer.  Only the low
-                    // S*K <= 128 bits of v matter for the digits: column sums of 32-bit words, -e Q folded in as + e (2^128 - Q).
-                    const unsigned long long fr = (unsigned long long)t0 * p.inv60[0] + (unsigned long long)t1 * p.inv60[1] +
-                                                  (unsigned long long)t2 * p.inv60[2] + (unsigned long long)t3 * p.inv60[3];
-                    const uint32_t e = (uint32_t)((fr + (1ull << 59)) >> 60);
-                    const unsigned long long a0 = (unsigned long long)t0 * p.m_w[0][0] + (unsigned long long)t1 * p.m_w[1][0] +
-                                                  (unsigned long long)t2 * p.m_w[2][0] + (unsigned long long)t3 * p.m_w[3][0] + (unsigned long long)e * p.nq_w[0];
-                    const unsigned long long a1 = (a0 >> 32) + (unsigned long long)t0 * p.m_w[0][1] + (unsigned long long)t1 * p.m_w[1][1] +
-                                                  (unsigned long long)t2 * p.m_w[2][1] + (unsigned long long)t3 * p.m_w[3][1] + (unsigned long long)e * p.nq_w[1];
-                    const unsigned long long a2 = (a1 >> 32) + (unsigned long long)t0 * p.m_w[0][2] + (unsigned long long)t1 * p.m_w[1][2] +
-                                                  (unsigned long long)t2 * p.m_w[2][2] + (unsigned long long)t3 * p.m_w[3][2] + (unsigned long long)e * p.nq_w[2];
-                    uint32_t w0 = (uint32_t)a0, w1 = (uint32_t)a1, w2 = (uint32_t)a2, w3 = 0;
-                    if (four_words) {
-                        const unsigned long long a3 = (a2 >> 32) + (unsigned long long)t0 * p.m_w[0][3] + (unsigned long long)t1 * p.m_w[1][3] +
-                                                      (unsigned long long)t2 * p.m_w[2][3] + (unsigned long long)t3 * p.m_w[3][3] +
-                                                      (unsigned long long)e * p.nq_w[3];
-                        w3 = (uint32_t)a3;
-                    }
+                    const uint32_t off = (uint32_t)(o * n + (swz<L>(chunk * T) ^ st)) * 4u;
+                    uint32_t w0, w1, w2, w3;
+                    crt_low_words<NP>(p, rb, off, nwords, w0, w1, w2, w3);
                     // Balanced digits of W = v + sum_j body_j 2^((S-1-j)K): the unsigned K-bit fields of u = W + sum_j 2^(K-1) 2^(jK), each
                     // minus 2^(K-1).  u is kept modulo 2^128 and shifted right by K per digit; body limb j joins at bit 0 just before its
                     // own digit is read (same as adding it at bit (S-1-j)K up front; the carry out of the top digit is dropped as in
                     // vec_znx_big_normalize).
+                    long long *out_p = res_ct + (size_t)(S - 1) * res_ls + (size_t)o * n + chunk * T;
+                    if (narrow && nwords <= 2) {
+                        // S K <= 64: every digit is read below bit 64 of u, and nothing above bit 64 ever moves down into a digit that is
+                        // still to be read (a digit at step s sits below bit 64 - s K of the shifted value): two words are the whole state
+                        asm("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;" : "+r"(w0), "+r"(w1) : "r"(hw0), "r"(hw1));
+#define ADD_BODY2(SV)                                                                                                      \
+    {                                                                                                                      \
+        const long long sv_ = (SV);                                                                                        \
+        asm("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;"                                                                  \
+            : "+r"(w0), "+r"(w1) : "r"((uint32_t)sv_), "r"((uint32_t)((unsigned long long)sv_ >> 32)));                    \
+    }
+#define DIGIT_STEP2                                                                                                        \
+    {                                                                                                                      \
+        if (j < a_start) *out_p = (long long)((int)(w0 & kmask32) - (int)khalf32);                                         \
+        out_p -= res_ls;                                                                                                   \
+        w0 = __funnelshift_r(w0, w1, Kb); w1 >>= Kb;                                                                       \
+    }
+#pragma unroll
+                        for (int s4 = 0; s4 < 4; s4++) {
+                            const int j = S - 1 - s4;
+                            if (j >= 0) {
+                                if (with_small && j < p.small_size) ADD_BODY2(sm4[s4])
+                                DIGIT_STEP2
+                            }
+                        }
+                        for (int j = S - 5; j >= 0; j--) {
+                            if (with_small && j < p.small_size) ADD_BODY2(__ldg(sp))
+                            sp -= in_ls;
+                            DIGIT_STEP2
+                        }
+#undef DIGIT_STEP2
+#undef ADD_BODY2
+                    } else {
                     asm("add.cc.u32 %0, %0, %4; addc.cc.u32 %1, %1, %5; addc.cc.u32 %2, %2, %6; addc.u32 %3, %3, %7;"
                         : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(w3) : "r"(hw0), "r"(hw1), "r"(hw2), "r"(hw3));
-                    long long *out_p = res_ct + (size_t)(S - 1) * res_ls + (size_t)o * n + i * T;
 #define ADD_BODY(SV)                                                                                                       \
     {                                                                                                                      \
         const long long sv_ = (SV);                                                                                        \
@@ -660,7 +683,8 @@ template <int L, bool AUT> __device__ __forceinline__ void gadget_body(const Gad
 #undef DIGIT_STEP64
                     }
 #undef ADD_BODY
-                    long long *zp = res_ct + (size_t)o * n + i * T;
+                    }
+                    long long *zp = res_ct + (size_t)o * n + chunk * T;
                     for (int j = a_start; j < p.res_size; j++) zp[(size_t)j * res_ls] = 0;
                 }
             }
@@ -673,16 +697,15 @@ template <int L, bool AUT> __device__ __forceinline__ void gadget_body(const Gad
 #undef P2_ADDR
 }
 
-template <int L, int MB, bool AUT> __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(GGeo<L>::T, MB * 256 / GGeo<L>::T) ntt120_gadget_kernel(const __grid_constant__ GadgetArgs p,
-                                                                                                            const uint2 *__restrict__ twf,
-                                                                                                            const uint2 *__restrict__ twi,
-                                                                                                            const uint4 *__restrict__ lastf,
-                                                                                                            const uint4 *__restrict__ lasti) {
+template <int L, int MB, bool AUT, int NP>
+__global__ void __cluster_dims__(NP, 1, 1) __launch_bounds__(GGeo<L>::T, MB * 256 / GGeo<L>::T)
+    ntt120_gadget_kernel(const __grid_constant__ GadgetArgs p, const uint2 *__restrict__ twf, const uint2 *__restrict__ twi,
+                         const uint4 *__restrict__ lastf, const uint4 *__restrict__ lasti) {
     extern __shared__ __align__(16) uint32_t smem[];
     constexpr int n = GGeo<L>::N;
     cl_arrive(); // primes the arrive/wait pairing used by the per-ciphertext loop
-    const int k = blockIdx.x & 3; // = rank in the cluster; one code body for all four primes (instruction-cache footprint)
-    gadget_body<L, AUT>(p, smem, twf + (size_t)k * n, twi + (size_t)k * n, lastf + (size_t)k * (n / 2), lasti + (size_t)k * (n / 2), k);
+    const int k = blockIdx.x % NP; // = rank in the cluster; one code body for all primes (instruction-cache footprint)
+    gadget_body<L, AUT, NP>(p, smem, twf + (size_t)k * n, twi + (size_t)k * n, lastf + (size_t)k * (n / 2), lasti + (size_t)k * (n / 2), k);
 }
 
 // collapsed key in the gadget kernel's layout: out[r][col][k][chunk][t][4] = sum_j 2^((S-1-j)K) * pmat[r][j * cols_out + col][k][16t + 4 chunk + w]
@@ -731,40 +754,42 @@ static uint32_t pow2_mod(uint64_t e, uint32_t q) {
     return (uint32_t)r;
 }
 
-template <int L, int MB, bool AUT> int launch_gadget_mb(pgb_module *m, const GadgetArgs &p, size_t smem);
-template <int L> int launch_gadget(pgb_module *m, const GadgetArgs &p, size_t smem) {
-    if (p.aut_mode) return launch_gadget_mb<L, 3, true>(m, p, smem);
-    if (m->opt[PGB_OPT_GADGET_MB] == 4) return launch_gadget_mb<L, 4, false>(m, p, smem);
-    return launch_gadget_mb<L, 3, false>(m, p, smem);
-}
-template <int L, int MB, bool AUT> int launch_gadget_mb(pgb_module *m, const GadgetArgs &p, size_t smem) {
+template <int L, int MB, bool AUT, int NP> int launch_gadget_mb(pgb_module *m, const GadgetArgs &p, size_t smem) {
     typedef GGeo<L> G;
-    static int max_clusters_dev[32] = {};
-    int &max_clusters = max_clusters_dev[m->device & 31];
+    static bool configured[32] = {};
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(G::T);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = m->stream;
-    if (!max_clusters) {
-        PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_gadget_kernel<L, MB, AUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 << 10)));
-        PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_gadget_kernel<L, MB, AUT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    if (!configured[m->device & 31]) {
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_gadget_kernel<L, MB, AUT, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 << 10)));
+        PGB_CHECK_CUDA(cudaFuncSetAttribute(ntt120_gadget_kernel<L, MB, AUT, NP>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured[m->device & 31] = true;
     }
     // resident clusters for this shared-memory footprint (depends on R through smem)
-    cfg.gridDim = dim3(4 * 148);
+    cfg.gridDim = dim3(NP * 148);
     int nc = 0;
-    PGB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&nc, ntt120_gadget_kernel<L, MB, AUT>, &cfg));
+    PGB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&nc, ntt120_gadget_kernel<L, MB, AUT, NP>, &cfg));
     if (nc < 1) {
         pgb_set_error("gadget kernel: no resident cluster fits (smem %zu)", smem);
         return PGB_ERR_UNSUPPORTED;
     }
-    max_clusters = nc;
     const int clusters = p.batch < nc ? p.batch : nc;
-    cfg.gridDim = dim3(4 * clusters);
+    cfg.gridDim = dim3(NP * clusters);
     { ProfScope _ps(m, PROF_GADGET);
-    PGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ntt120_gadget_kernel<L, MB, AUT>, p, (const uint2 *)m->ntt_fwd, (const uint2 *)m->ntt_inv,
+    PGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ntt120_gadget_kernel<L, MB, AUT, NP>, p, (const uint2 *)m->ntt_fwd, (const uint2 *)m->ntt_inv,
                                       (const uint4 *)m->ntt_last16_f, (const uint4 *)m->ntt_last16_i));
     }
     return PGB_OK;
+}
+template <int L> int launch_gadget(pgb_module *m, const GadgetArgs &p, size_t smem, int np) {
+    if (np == 3) {
+        if (p.aut_mode) return launch_gadget_mb<L, 3, true, 3>(m, p, smem);
+        return launch_gadget_mb<L, 3, false, 3>(m, p, smem);
+    }
+    if (p.aut_mode) return launch_gadget_mb<L, 3, true, 4>(m, p, smem);
+    if (m->opt[PGB_OPT_GADGET_MB] == 4) return launch_gadget_mb<L, 4, false, 4>(m, p, smem);
+    return launch_gadget_mb<L, 3, false, 4>(m, p, smem);
 }
 
 } // namespace
@@ -838,14 +863,37 @@ int ntt120_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_co
         if (jl >= group || src >= key_rows || jm < 0) jm = 0; // this limb takes no part: its collapsed key is zero
         ca.src_row[r] = (signed char)(jm ? src : 0); ca.di[r] = (signed char)(jm ? di : 0); ca.jmax[r] = (signed char)jm;
     }
+    // a pinned key's bit bound is also kept on the host: it decides, before the launch, whether three primes carry the integers
+    uint64_t sig_bits[KEY_SIG_WORDS];
+    memcpy(sig_bits, sig, sizeof sig_bits);
+    sig_bits[0] = 5;
+    int64_t *bits_slot = pinned ? key_cache_host_slot(m, pmat, key_bytes, sig_bits) : nullptr;
     if (!have) {
         { ProfScope _ps(m, PROF_OTHER);
         gadget_collapse_key_kernel<<<dim3(((unsigned)(n / 4) + 255) / 256, R * cols_out, 4), 256, 0, m->stream>>>(ca);
         }
         PGB_CHECK_CUDA(cudaGetLastError());
         PGB_TRY(ntt120_key_max_bits(m, pmat, key_rows * C, kcoef, key_bits));
+        if (bits_slot) {
+            int kb = 0;
+            PGB_CHECK_CUDA(cudaMemcpyAsync(&kb, key_bits, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+            PGB_CHECK_CUDA(cudaStreamSynchronize(m->stream));
+            *bits_slot = (int64_t)kb + 1; // 0 = not set
+        }
     }
+    int rn_bits = 0;
+    while (((uint64_t)1 << rn_bits) < (uint64_t)R * n) rn_bits++;
+    // Bound.  v = sum over R n products of an input coefficient (|a| < 2^abits) with a collapsed-key coefficient
+    // (|sum_j 2^((S-1-j)K) k_j| < 2^((S-1)K + 1 + key_bits)), so |v| < 2^(rn_bits + (S-1)K + 1 + key_bits + abits).  Four primes: the
+    // reference's own range, kept two bits inside Q/4 ~ 2^118 as in round 1.  Three primes: Q3 = Q[0] Q[1] Q[2] > 2^89.99 and the CRT
+    // rounding needs |v| < Q3 (1/2 - 2^-27), i.e. |v| < 2^88 with room to spare.  The three-prime launch is taken when the host knows the key
+    // bound (pinned key) and normalised inputs (|a| <= 2^(K-1): K bits) are certain to pass; an input beyond the bound is flagged for
+    // the per-limb route by the kernel either way, so the result never depends on which launch ran.
+    const int bound4 = 118 - (rn_bits + (S - 1) * base2k + 3) - 1, bound3 = 88 - (rn_bits + (S - 1) * base2k + 1);
+    int np = 4;
+    if (bits_slot && *bits_slot > 0 && m->opt[PGB_OPT_GADGET_PRIMES] != 4 && bound3 - (int)(*bits_slot - 1) >= base2k) np = 3;
 
+    m->opt[PGB_OPT_LAST_GADGET_PRIMES] = np;
     GadgetArgs p;
     memset(&p, 0, sizeof p);
     p.in = in; p.in_bs = in_bs; p.res = res; p.res_bs = res_bs; p.ckey = (const uint32_t *)ck; p.key_bits = key_bits; p.ok = ok_out;
@@ -866,33 +914,53 @@ int ntt120_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_co
     for (int j = 0; j < S; j++) half += (u128)1 << (j * base2k + base2k - 1);
     p.half_lo = (unsigned long long)half;
     p.half_hi = (unsigned long long)(half >> 64);
-    int rn_bits = 0;
-    while (((uint64_t)1 << rn_bits) < (uint64_t)R * n) rn_bits++;
-    p.base_bits = rn_bits + (S - 1) * base2k + 3;
+    p.bound_bits = np == 3 ? bound3 : bound4;
     u128 Q = 1;
-    for (int k = 0; k < 4; k++) Q *= qk(k);
+    for (int k = 0; k < np; k++) Q *= qk(k);
+    uint64_t ninv_n[4]; // n^-1 mod Q[k]
     for (int k = 0; k < 4; k++) {
-        const u128 mk = Q / qk(k);
-        for (int w = 0; w < 4; w++) p.m_w[k][w] = (uint32_t)(mk >> (32 * w));
-        p.nq_w[k] = (uint32_t)(((u128)0 - Q) >> (32 * k));
-        p.inv60[k] = (uint32_t)(((unsigned long long)1 << 60) / qk(k));
-        p.crt_ninv[k] = m->nc.crt_ninv[k];
-        p.crt_ninv_sh[k] = m->nc.crt_ninv_sh[k];
-        memcpy(p.top[k].f, m->tw_top_f[k], sizeof p.top[k].f);
-        memcpy(p.top[k].i, m->tw_top_i[k], sizeof p.top[k].i);
+        const uint32_t q = qk(k);
+        uint64_t r = 1, b = n % q, e = q - 2;
+        while (e) {
+            if (e & 1) r = r * b % q;
+            b = b * b % q;
+            e >>= 1;
+        }
+        ninv_n[k] = r;
+    }
+    for (int k = 0; k < 4; k++) {
         const uint32_t q = qk(k), c32 = (uint32_t)((1ull << 32) % q);
         p.prime[k].q = q;
         p.prime[k].c32 = c32;
         p.prime[k].c32s = (uint32_t)(((unsigned long long)c32 << 32) / q);
         p.prime[k].neg64 = q - (uint32_t)(((unsigned long long)c32 * c32) % q);
+        p.nq_w[k] = (uint32_t)(((u128)0 - Q) >> (32 * k));
+        if (k >= np) continue;
+        const u128 mk = Q / q;
+        for (int w = 0; w < 4; w++) p.m_w[k][w] = (uint32_t)(mk >> (32 * w));
+        p.inv60[k] = (uint32_t)(((unsigned long long)1 << 60) / q);
+        if (np == 4) {
+            p.crt_ninv[k] = m->nc.crt_ninv[k];
+            p.crt_ninv_sh[k] = m->nc.crt_ninv_sh[k];
+        } else { // (Q3 / q)^-1 / n mod q
+            uint64_t r = 1, b = (uint64_t)(mk % q), e = q - 2;
+            while (e) {
+                if (e & 1) r = r * b % q;
+                b = b * b % q;
+                e >>= 1;
+            }
+            const uint32_t c = (uint32_t)(r * ninv_n[k] % q);
+            p.crt_ninv[k] = c;
+            p.crt_ninv_sh[k] = (uint32_t)(((uint64_t)c << 32) / q);
+        }
     }
     const int planes = R > cols_out ? R : cols_out;
     const size_t smem = (size_t)planes * n * 4;
     PGB_CHECK_CUDA(cudaMemsetAsync(ok_out + batch, 0, sizeof(int), m->stream));
     switch (m->log_n) {
-    case 10: return launch_gadget<10>(m, p, smem);
-    case 11: return launch_gadget<11>(m, p, smem);
-    case 12: return launch_gadget<12>(m, p, smem);
+    case 10: return launch_gadget<10>(m, p, smem, np);
+    case 11: return launch_gadget<11>(m, p, smem, np);
+    case 12: return launch_gadget<12>(m, p, smem, np);
     default: pgb_set_error("gadget kernel: unsupported n"); return PGB_ERR_UNSUPPORTED;
     }
 }
