@@ -63,11 +63,9 @@ template <int L> struct GGeo {
     // pass p covers butterfly levels [LV + 4 - NLEV, LV + 4); in-group stride 2^SG
     static constexpr int LV2 = (L >= 12) ? 4 : (L == 11 ? 4 : 3);
     static constexpr int NL2 = (L >= 11) ? 4 : 3;
-    static constexpr int LV3 = L - 4;
     static constexpr int NL3 = L - (LV2 + 4) ;  // levels left for the last pass
     static constexpr int SG2 = L - LV2 - 4;     // log2 stride of pass 2
     static constexpr bool SIG3 = SG2 == 3;
-    static constexpr int MINB = 768 / T; // resident CTAs per SM the register budget is sized for (<= 85 registers)
 };
 
 // conflict-free XOR swizzle of a word index for the three access patterns (stride T scalar, stride 2^SG2 scalar, 16 consecutive
@@ -295,6 +293,127 @@ template <int NP> __device__ __forceinline__ void crt_low_words(const GadgetArgs
     }
 }
 
+// ---- CRT + balanced digits of one output column for base2k < 32, G coefficients of a thread at a time ------------------------------------
+// CTA K owns the coefficient chunks K, K + NP, ... (16 chunks of T coefficients per polynomial); a thread processes G of its coefficients
+// together so that the CTA-uniform work -- the CRT constants, the per-step decisions (does limb j take a body limb, is digit j stored),
+// pointer updates -- is paid once per group and step instead of once per coefficient and step (round 1: ~250 thread instructions per
+// coefficient, a quarter of them predicates, branches and constant loads).
+//
+// Per coefficient: v = sum_k t_k M_k - e Q (mod 2^(32 NW)) with e = round(sum t_k / Q[k]) as in crt_low_words, half = sum_j 2^(K-1) 2^(jK)
+// folded into the column sums.  Balanced digits of W = v + sum_j body_j 2^((S-1-j)K): the unsigned K-bit fields of u = W + half, each minus
+// 2^(K-1).  u is kept modulo 2^(32 NW) >= 2^(S K) and shifted right by K per digit; body limb j joins at bit 0 just before its own digit is
+// read (the carry out of the top digit is dropped as in vec_znx_big_normalize).  Nothing above bit S K ever moves down into a digit that is
+// still to be read, so NW = ceil(S K / 32) words are the whole state.
+template <int L, int NP, int NW, bool SMALL>
+__device__ __forceinline__ void gadget_tail_narrow(const GadgetArgs &p, const uint32_t (&rb)[NP], const int K, const int t, const int st,
+                                                   const int o, const long long *__restrict__ in, long long *__restrict__ res) {
+    typedef GGeo<L> Geo;
+    constexpr int n = Geo::N, T = Geo::T;
+    constexpr int G = NP == 4 ? 4 : 3;       // NP = 4: chunks K, K+4, K+8, K+12; NP = 3: two groups (K, K+3, K+6), (K+9, K+12, K+15 if < 16)
+    const int Kb = p.K, S = p.S, cols_out = p.cols_out;
+    const int a_start = p.res_size < S ? p.res_size : S; // digits j >= a_start are discarded (carry only)
+    const size_t res_ls = (size_t)cols_out * n, in_ls = (size_t)p.in_cols * n;
+    const uint32_t kmask32 = (1u << Kb) - 1u, khalf32 = 1u << (Kb - 1);
+    const uint32_t hw[4] = {(uint32_t)p.half_lo, (uint32_t)(p.half_lo >> 32), (uint32_t)p.half_hi, (uint32_t)(p.half_hi >> 32)};
+#pragma unroll 1
+    for (int c0 = K; c0 < 16; c0 += NP * G) {
+        bool valid[G];
+        uint32_t tk[G][NP];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const int chunk = c0 + g * NP;
+            valid[g] = NP == 4 || chunk < 16;
+            const uint32_t off = (uint32_t)(o * n + (swz<L>((valid[g] ? chunk : c0) * T) ^ st)) * 4u;
+#pragma unroll
+            for (int k = 0; k < NP; k++) tk[g][k] = ld_cluster(rb[k] + off);
+        }
+        // first body limbs in flight before the CRT arithmetic
+        const long long *bp = in + (size_t)(S - 1) * in_ls + c0 * T + t;       // body limb S - 1 (column 0), coefficient of g = 0
+        long long body[G];
+        if (SMALL) {
+#pragma unroll
+            for (int g = 0; g < G; g++) body[g] = (S - 1 < p.small_size && valid[g]) ? __ldg(bp + g * NP * T) : 0;
+        }
+        uint32_t w[G][NW];
+        {
+            unsigned long long a[G];
+            uint32_t e[G];
+#pragma unroll
+            for (int g = 0; g < G; g++) a[g] = 1ull << 59;
+#pragma unroll
+            for (int k = 0; k < NP; k++) {
+                const uint32_t c = p.inv60[k];
+#pragma unroll
+                for (int g = 0; g < G; g++) a[g] += (unsigned long long)tk[g][k] * c;
+            }
+#pragma unroll
+            for (int g = 0; g < G; g++) e[g] = (uint32_t)(a[g] >> 60);
+#pragma unroll
+            for (int wi = 0; wi < NW; wi++) {
+                const uint32_t nq = p.nq_w[wi], h = hw[wi];
+#pragma unroll
+                for (int g = 0; g < G; g++) a[g] = (wi ? (a[g] >> 32) : 0ull) + (unsigned long long)e[g] * nq + h;
+                if (NP == 4 || wi < 2) { // three-prime M_k are below 2^60
+#pragma unroll
+                    for (int k = 0; k < NP; k++) {
+                        const uint32_t mw = p.m_w[k][wi];
+#pragma unroll
+                        for (int g = 0; g < G; g++) a[g] += (unsigned long long)tk[g][k] * mw;
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < G; g++) w[g][wi] = (uint32_t)a[g];
+            }
+        }
+        long long *out_p = res + (size_t)(S - 1) * res_ls + (size_t)o * n + c0 * T + t;
+#pragma unroll 1
+        for (int j = S - 1; j >= 0; j--) {
+            long long next[G];
+            if (SMALL) { // next step's body limbs are requested before this step's arithmetic
+                bp -= in_ls;
+#pragma unroll
+                for (int g = 0; g < G; g++) next[g] = (j >= 1 && j - 1 < p.small_size && valid[g]) ? __ldg(bp + g * NP * T) : 0;
+                if (j < p.small_size) {
+#pragma unroll
+                    for (int g = 0; g < G; g++) {
+                        const uint32_t lo = (uint32_t)body[g], hi = (uint32_t)((unsigned long long)body[g] >> 32), sx = (uint32_t)(body[g] >> 63);
+                        if (NW == 1) w[g][0] += lo;
+                        else if (NW == 2) asm("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;" : "+r"(w[g][0]), "+r"(w[g][1]) : "r"(lo), "r"(hi));
+                        else if (NW == 3)
+                            asm("add.cc.u32 %0, %0, %3; addc.cc.u32 %1, %1, %4; addc.u32 %2, %2, %5;"
+                                : "+r"(w[g][0]), "+r"(w[g][1]), "+r"(w[g][NW > 2 ? 2 : 0]) : "r"(lo), "r"(hi), "r"(sx));
+                        else
+                            asm("add.cc.u32 %0, %0, %4; addc.cc.u32 %1, %1, %5; addc.cc.u32 %2, %2, %6; addc.u32 %3, %3, %6;"
+                                : "+r"(w[g][0]), "+r"(w[g][1]), "+r"(w[g][NW > 2 ? 2 : 0]), "+r"(w[g][NW > 3 ? 3 : 0]) : "r"(lo), "r"(hi), "r"(sx));
+                    }
+                }
+            }
+            if (j < a_start) {
+#pragma unroll
+                for (int g = 0; g < G; g++)
+                    if (valid[g]) out_p[g * NP * T] = (long long)((int)(w[g][0] & kmask32) - (int)khalf32);
+            }
+            out_p -= res_ls;
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+#pragma unroll
+                for (int wi = 0; wi + 1 < NW; wi++) w[g][wi] = __funnelshift_r(w[g][wi], w[g][wi + 1], Kb);
+                w[g][NW - 1] >>= Kb;
+            }
+            if (SMALL) {
+#pragma unroll
+                for (int g = 0; g < G; g++) body[g] = next[g];
+            }
+        }
+        long long *zp = res + (size_t)o * n + c0 * T + t;
+        for (int j = a_start; j < p.res_size; j++) {
+#pragma unroll
+            for (int g = 0; g < G; g++)
+                if (valid[g]) zp[(size_t)j * res_ls + g * NP * T] = 0;
+        }
+    }
+}
+
 template <int L, bool AUT, int NP> __device__ __forceinline__ void gadget_body(const GadgetArgs &p, uint32_t *__restrict__ sm, const uint2 *__restrict__ twf,
                                                              const uint2 *__restrict__ twi, const uint4 *__restrict__ lastf,
                                                              const uint4 *__restrict__ lasti, const int K) {
@@ -502,8 +621,6 @@ template <int L, bool AUT, int NP> __device__ __forceinline__ void gadget_body(c
             const int nwords = (S * Kb + 31) >> 5;
             const bool narrow = Kb < 32; // digit fields inside one 32-bit word: funnel shifts over four words
             const unsigned long long kmask = (1ull << Kb) - 1, khalf = 1ull << (Kb - 1);
-            const uint32_t kmask32 = (uint32_t)kmask, khalf32 = (uint32_t)khalf;
-            const uint32_t hw0 = (uint32_t)p.half_lo, hw1 = (uint32_t)(p.half_lo >> 32), hw2 = (uint32_t)p.half_hi, hw3 = (uint32_t)(p.half_hi >> 32);
             long long *res_ct = reinterpret_cast<long long *>(p.res + (size_t)ct * p.res_bs) + t;
             const long long *in_kt = in + t + (size_t)(S - 1) * in_ls; // body limb S - 1 (column 0)
             if constexpr (AUT) {
@@ -571,118 +688,45 @@ template <int L, bool AUT, int NP> __device__ __forceinline__ void gadget_body(c
                         for (int j = a_start; j < p.res_size; j++) zp[(size_t)j * res_ls] = 0;
                     }
                 }
+            } else if (narrow) {
+                long long *res_base = reinterpret_cast<long long *>(p.res + (size_t)ct * p.res_bs);
+                for (int o = 0; o < cols_out; o++) {
+                    if (o == 0 && p.small_size > 0) {
+                        if (nwords <= 2) gadget_tail_narrow<L, NP, 2, true>(p, rb, K, t, st, o, in, res_base);
+                        else if (nwords == 3) gadget_tail_narrow<L, NP, 3, true>(p, rb, K, t, st, o, in, res_base);
+                        else gadget_tail_narrow<L, NP, 4, true>(p, rb, K, t, st, o, in, res_base);
+                    } else {
+                        if (nwords <= 2) gadget_tail_narrow<L, NP, 2, false>(p, rb, K, t, st, o, in, res_base);
+                        else if (nwords == 3) gadget_tail_narrow<L, NP, 3, false>(p, rb, K, t, st, o, in, res_base);
+                        else gadget_tail_narrow<L, NP, 4, false>(p, rb, K, t, st, o, in, res_base);
+                    }
+                }
             } else
-            for (int o = 0; o < cols_out; o++) {
+            for (int o = 0; o < cols_out; o++) { // base2k >= 32: 64-bit digit fields, one coefficient at a time
                 const bool with_small = o == 0 && p.small_size > 0;
 #pragma unroll 1
                 for (int chunk = K; chunk < 16; chunk += NP) {
-                    // body limbs that join column 0 (vec_znx_big_add_small_assign), least significant digit first: sm4[s] belongs to
-                    // digit step s (limb S-1-s); issued first so that their latency hides behind the CRT arithmetic
-                    long long sm4[4] = {0, 0, 0, 0};
                     const long long *sp = in_kt + chunk * T;
-                    if (with_small) {
-#pragma unroll
-                        for (int s4 = 0; s4 < 4; s4++) {
-                            if (S - 1 - s4 >= 0 && S - 1 - s4 < p.small_size) sm4[s4] = __ldg(sp);
-                            sp -= in_ls;
-                        }
-                    }
                     const uint32_t off = (uint32_t)(o * n + (swz<L>(chunk * T) ^ st)) * 4u;
                     uint32_t w0, w1, w2, w3;
                     crt_low_words<NP>(p, rb, off, nwords, w0, w1, w2, w3);
-                    // Balanced digits of W = v + sum_j body_j 2^((S-1-j)K): the unsigned K-bit fields of u = W + sum_j 2^(K-1) 2^(jK), each
-                    // minus 2^(K-1).  u is kept modulo 2^128 and shifted right by K per digit; body limb j joins at bit 0 just before its
-                    // own digit is read (same as adding it at bit (S-1-j)K up front; the carry out of the top digit is dropped as in
-                    // vec_znx_big_normalize).
+                    // digits as in gadget_tail_narrow, on two 64-bit halves (words the digits do not need are 0 and stay unread)
+                    unsigned long long lo = ((unsigned long long)w1 << 32) | w0, hi = ((unsigned long long)w3 << 32) | w2;
+                    lo += p.half_lo;
+                    hi += p.half_hi + (lo < p.half_lo);
                     long long *out_p = res_ct + (size_t)(S - 1) * res_ls + (size_t)o * n + chunk * T;
-                    if (narrow && nwords <= 2) {
-                        // S K <= 64: every digit is read below bit 64 of u, and nothing above bit 64 ever moves down into a digit that is
-                        // still to be read (a digit at step s sits below bit 64 - s K of the shifted value): two words are the whole state
-                        asm("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;" : "+r"(w0), "+r"(w1) : "r"(hw0), "r"(hw1));
-#define ADD_BODY2(SV)                                                                                                      \
-    {                                                                                                                      \
-        const long long sv_ = (SV);                                                                                        \
-        asm("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;"                                                                  \
-            : "+r"(w0), "+r"(w1) : "r"((uint32_t)sv_), "r"((uint32_t)((unsigned long long)sv_ >> 32)));                    \
-    }
-#define DIGIT_STEP2                                                                                                        \
-    {                                                                                                                      \
-        if (j < a_start) *out_p = (long long)((int)(w0 & kmask32) - (int)khalf32);                                         \
-        out_p -= res_ls;                                                                                                   \
-        w0 = __funnelshift_r(w0, w1, Kb); w1 >>= Kb;                                                                       \
-    }
-#pragma unroll
-                        for (int s4 = 0; s4 < 4; s4++) {
-                            const int j = S - 1 - s4;
-                            if (j >= 0) {
-                                if (with_small && j < p.small_size) ADD_BODY2(sm4[s4])
-                                DIGIT_STEP2
-                            }
+                    for (int j = S - 1; j >= 0; j--) {
+                        if (with_small && j < p.small_size) {
+                            const long long sv = __ldg(sp);
+                            const unsigned long long sl = (unsigned long long)sv;
+                            lo += sl;
+                            hi += (unsigned long long)(sv >> 63) + (lo < sl);
                         }
-                        for (int j = S - 5; j >= 0; j--) {
-                            if (with_small && j < p.small_size) ADD_BODY2(__ldg(sp))
-                            sp -= in_ls;
-                            DIGIT_STEP2
-                        }
-#undef DIGIT_STEP2
-#undef ADD_BODY2
-                    } else {
-                    asm("add.cc.u32 %0, %0, %4; addc.cc.u32 %1, %1, %5; addc.cc.u32 %2, %2, %6; addc.u32 %3, %3, %7;"
-                        : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(w3) : "r"(hw0), "r"(hw1), "r"(hw2), "r"(hw3));
-#define ADD_BODY(SV)                                                                                                       \
-    {                                                                                                                      \
-        const long long sv_ = (SV);                                                                                        \
-        const uint32_t sx_ = (uint32_t)(sv_ >> 63);                                                                        \
-        asm("add.cc.u32 %0, %0, %4; addc.cc.u32 %1, %1, %5; addc.cc.u32 %2, %2, %6; addc.u32 %3, %3, %6;"                  \
-            : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(w3) : "r"((uint32_t)sv_), "r"((uint32_t)((unsigned long long)sv_ >> 32)), "r"(sx_)); \
-    }
-                    if (narrow) {
-#define DIGIT_STEP32                                                                                                       \
-    {                                                                                                                      \
-        if (j < a_start) *out_p = (long long)((int)(w0 & kmask32) - (int)khalf32);                                         \
-        out_p -= res_ls;                                                                                                   \
-        w0 = __funnelshift_r(w0, w1, Kb); w1 = __funnelshift_r(w1, w2, Kb); w2 = __funnelshift_r(w2, w3, Kb); w3 >>= Kb;   \
-    }
-#pragma unroll
-                        for (int s4 = 0; s4 < 4; s4++) {
-                            const int j = S - 1 - s4;
-                            if (j >= 0) {
-                                if (with_small && j < p.small_size) ADD_BODY(sm4[s4])
-                                DIGIT_STEP32
-                            }
-                        }
-                        for (int j = S - 5; j >= 0; j--) {
-                            if (with_small && j < p.small_size) ADD_BODY(__ldg(sp))
-                            sp -= in_ls;
-                            DIGIT_STEP32
-                        }
-#undef DIGIT_STEP32
-                    } else {
-#define DIGIT_STEP64                                                                                                       \
-    {                                                                                                                      \
-        unsigned long long lo_ = ((unsigned long long)w1 << 32) | w0, hi_ = ((unsigned long long)w3 << 32) | w2;           \
-        if (j < a_start) *out_p = (long long)(lo_ & kmask) - (long long)khalf;                                             \
-        out_p -= res_ls;                                                                                                   \
-        lo_ = (lo_ >> Kb) | (hi_ << (64 - Kb));                                                                            \
-        hi_ >>= Kb;                                                                                                        \
-        w0 = (uint32_t)lo_; w1 = (uint32_t)(lo_ >> 32); w2 = (uint32_t)hi_; w3 = (uint32_t)(hi_ >> 32);                    \
-    }
-#pragma unroll
-                        for (int s4 = 0; s4 < 4; s4++) {
-                            const int j = S - 1 - s4;
-                            if (j >= 0) {
-                                if (with_small && j < p.small_size) ADD_BODY(sm4[s4])
-                                DIGIT_STEP64
-                            }
-                        }
-                        for (int j = S - 5; j >= 0; j--) {
-                            if (with_small && j < p.small_size) ADD_BODY(__ldg(sp))
-                            sp -= in_ls;
-                            DIGIT_STEP64
-                        }
-#undef DIGIT_STEP64
-                    }
-#undef ADD_BODY
+                        sp -= in_ls;
+                        if (j < a_start) *out_p = (long long)(lo & kmask) - (long long)khalf;
+                        out_p -= res_ls;
+                        lo = (lo >> Kb) | (hi << (64 - Kb));
+                        hi >>= Kb;
                     }
                     long long *zp = res_ct + (size_t)o * n + chunk * T;
                     for (int j = a_start; j < p.res_size; j++) zp[(size_t)j * res_ls] = 0;
