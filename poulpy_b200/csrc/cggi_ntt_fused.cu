@@ -186,14 +186,6 @@ template <int L> struct NInv<L, -1> {
     static __device__ __forceinline__ void run(uint32_t *, const uint2 *, int, int, bool, uint32_t) {}
 };
 
-// Montgomery reduction of a u64: x * 2^-32 mod q as a value in [0, x / 2^32 + q) -- two instructions (IMAD + IMAD.WIDE) where a Shoup-style
-// reduction of a 64-bit value takes seven.  The factor 2^-32 is compensated in the constants the value is multiplied with next.
-// qneg_inv = -q^-1 mod 2^32.  x + m q is a multiple of 2^32 and < 2^64 for every x the kernel feeds (x < 2^63, m q < 2^62).
-__device__ __forceinline__ uint32_t redc64(unsigned long long x, uint32_t q, uint32_t qneg_inv) {
-    const uint32_t m = (uint32_t)x * qneg_inv;
-    return (uint32_t)((x + (unsigned long long)m * q) >> 32);
-}
-
 constexpr int CGN_COMPUTE = 512; // compute threads; warp 16 is the key-stream producer
 constexpr int CGN_BSMAX = 4;     // keys per block whose (X^a - 1) factors are held in registers
 

@@ -23,6 +23,14 @@ __host__ __device__ __forceinline__ constexpr uint32_t qk(int k) {
 static constexpr uint32_t OMEGA[4] = {1070907127u, 315046632u, 309185662u, 846468380u};
 static constexpr uint32_t CRT_CST[4] = {43599465u, 292938863u, 594011630u, 140177212u};
 
+// Montgomery reduction of a u64: x * 2^-32 mod q as a value in [0, x / 2^32 + q) -- two instructions (IMAD + IMAD.WIDE) where a Shoup-style
+// reduction of a 64-bit value takes seven.  The factor 2^-32 is compensated in the constants the value is multiplied with (before or after).
+// qneg_inv = -q^-1 mod 2^32.  x + m q is a multiple of 2^32 and < 2^64 whenever x < 2^63 (m q < 2^62).
+__device__ __forceinline__ uint32_t redc64(unsigned long long x, uint32_t q, uint32_t qneg_inv) {
+    const uint32_t m = (uint32_t)x * qneg_inv;
+    return (uint32_t)((x + (unsigned long long)m * q) >> 32);
+}
+
 // x * w mod q in [0, 2q) for any x < 2^32, w < q, wp = floor(w * 2^32 / q)   (Shoup)
 // -DPGB_SHOUP_WIDE takes the high word from a full 32x32->64 product (IMAD.WIDE, full IMAD rate in isolation) instead of __umulhi
 // (IMAD.HI, half rate: profiles/r1_pipe_peaks.json); ptxas keeps the wide form when it is spelled as mul.wide + unpack.  Measured on the

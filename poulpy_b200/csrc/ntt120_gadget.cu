@@ -54,7 +54,7 @@ struct GadgetArgs {
     unsigned long long half_lo, half_hi;            // sum_j 2^(K-1) 2^(jK), j < S (mod 2^128)
     uint32_t inv60[4];                              // floor(2^60 / Q[k]) (31 bits)
     uint32_t crt_ninv[4], crt_ninv_sh[4];           // (Q / Q[k])^-1 / n mod Q[k] (CRT_CST[k] / n for NP = 4) and its Shoup companion
-    struct { uint32_t q, c32, c32s, neg64; } prime[4];
+    struct { uint32_t q, c32, c32s, neg64, qni; } prime[4]; // qni = -q^-1 mod 2^32 (Montgomery reduction of the key products)
 };
 
 template <int L> struct GGeo {
@@ -414,6 +414,58 @@ __device__ __forceinline__ void gadget_tail_narrow(const GadgetArgs &p, const ui
     }
 }
 
+// Products with the collapsed key for the 16 coefficients of a thread (four chunks of four): out[o] = sum_r a[r] * key[r][o] mod q for CO
+// output columns.  The key is stored times 2^32 (gadget_collapse_key_kernel), the u64 row sums of up to four rows (< 8 q^2 < 2^63) take
+// one Montgomery reduction (two instructions) and one conditional subtraction, results in [0, 2q).  Every key address is the thread's
+// base plus a compile-time offset.
+template <int L, int CO>
+__device__ __forceinline__ void gadget_mac(uint32_t *__restrict__ sm, const uint4 *__restrict__ ck, const int R, const int (&qa)[4], const uint32_t q,
+                                           const uint32_t qni) {
+    constexpr int n = GGeo<L>::N, T = GGeo<L>::T;
+    constexpr int col_stride = n, row_stride = n * CO; // in uint4: [r][col][k 0..3][chunk][t]
+#pragma unroll 1
+    for (int c = 0; c < 4; c++) {
+        // rows in groups of four; the partial result of a group goes straight to the output planes: rows 0..3 have been consumed by then and
+        // CO <= 4, and the words are this thread's own
+#pragma unroll 1
+        for (int r0 = 0; r0 < R; r0 += 4) {
+            unsigned long long acc[CO][4];
+            const uint4 *ckr = ck + (size_t)r0 * row_stride + c * T;
+            const uint32_t *ar = sm + r0 * n + qa[c];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (u == 0 || r0 + u < R) {
+                    const uint4 a = *reinterpret_cast<const uint4 *>(ar + u * n);
+#pragma unroll
+                    for (int o = 0; o < CO; o++) {
+                        const uint4 m = __ldg(ckr + u * row_stride + o * col_stride);
+                        if (u == 0) {
+                            acc[o][0] = (unsigned long long)a.x * m.x; acc[o][1] = (unsigned long long)a.y * m.y;
+                            acc[o][2] = (unsigned long long)a.z * m.z; acc[o][3] = (unsigned long long)a.w * m.w;
+                        } else {
+                            acc[o][0] += (unsigned long long)a.x * m.x; acc[o][1] += (unsigned long long)a.y * m.y;
+                            acc[o][2] += (unsigned long long)a.z * m.z; acc[o][3] += (unsigned long long)a.w * m.w;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < CO; o++) {
+                uint4 *dst = reinterpret_cast<uint4 *>(sm + o * n + qa[c]);
+                uint32_t y[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) y[i] = csub(redc64(acc[o][i], q, qni), 2 * q); // redc < 2^31 + q < 4q
+                if (r0 != 0) {
+                    const uint4 prev = *dst;
+                    y[0] = csub(y[0] + prev.x, 2 * q); y[1] = csub(y[1] + prev.y, 2 * q);
+                    y[2] = csub(y[2] + prev.z, 2 * q); y[3] = csub(y[3] + prev.w, 2 * q);
+                }
+                *dst = make_uint4(y[0], y[1], y[2], y[3]);
+            }
+        }
+    }
+}
+
 template <int L, bool AUT, int NP> __device__ __forceinline__ void gadget_body(const GadgetArgs &p, uint32_t *__restrict__ sm, const uint2 *__restrict__ twf,
                                                              const uint2 *__restrict__ twi, const uint4 *__restrict__ lastf,
                                                              const uint4 *__restrict__ lasti, const int K) {
@@ -530,42 +582,12 @@ template <int L, bool AUT, int NP> __device__ __forceinline__ void gadget_body(c
         }
         // ---- products with the collapsed key (thread-private words: no barrier) ---------------------------------------------------
         {
-            const uint32_t c32 = pc.c32, c32s = pc.c32s;
             const uint4 *ck = reinterpret_cast<const uint4 *>(p.ckey) + (size_t)K * (n / 4) + t;
-            const size_t col_stride = (size_t)4 * (n / 4), row_stride = col_stride * cols_out; // in uint4
-#define MAC_CHUNKS(RLOOP)                                                                                                   \
-    _Pragma("unroll 1") for (int c = 0; c < 4; c++) {                                                                       \
-        unsigned long long acc[4][4]; /* up to four output columns */                                                       \
-        _Pragma("unroll") for (int o = 0; o < 4; o++) _Pragma("unroll") for (int i = 0; i < 4; i++) acc[o][i] = 0;          \
-        RLOOP {                                                                                                             \
-            const uint4 a = *reinterpret_cast<const uint4 *>(sm + r * n + qa[c]);                                           \
-            _Pragma("unroll") for (int o = 0; o < 4; o++) {                                                                 \
-                if (o < cols_out) {                                                                                         \
-                    const uint4 m = __ldg(ck + (size_t)r * row_stride + (size_t)o * col_stride + (size_t)c * T);            \
-                    acc[o][0] += (unsigned long long)a.x * m.x; acc[o][1] += (unsigned long long)a.y * m.y;                 \
-                    acc[o][2] += (unsigned long long)a.z * m.z; acc[o][3] += (unsigned long long)a.w * m.w;                 \
-                }                                                                                                           \
-            }                                                                                                               \
-        }                                                                                                                   \
-        _Pragma("unroll") for (int o = 0; o < 4; o++) {                                                                     \
-            if (o < cols_out) {                                                                                             \
-                uint32_t y[4];                                                                                              \
-                _Pragma("unroll") for (int i = 0; i < 4; i++) {                                                             \
-                    const uint32_t hi = (uint32_t)(acc[o][i] >> 32), lo = (uint32_t)acc[o][i];                              \
-                    y[i] = csub(mul_shoup(hi, c32, c32s, q) + (lo - (lo >> 30) * q), 2 * q);                                \
-                }                                                                                                           \
-                *reinterpret_cast<uint4 *>(sm + o * n + qa[c]) = make_uint4(y[0], y[1], y[2], y[3]);                        \
-            }                                                                                                               \
-        }                                                                                                                   \
-    }
-            if (R == 3) { // the bench shapes get all their loads in flight before the first multiply
-                MAC_CHUNKS(_Pragma("unroll") for (int r = 0; r < 3; r++))
-            } else if (R == 6) {
-                MAC_CHUNKS(_Pragma("unroll") for (int r = 0; r < 6; r++))
-            } else {
-                MAC_CHUNKS(for (int r = 0; r < R; r++))
-            }
-#undef MAC_CHUNKS
+            const uint32_t qni = p.prime[K].qni;
+            if (cols_out == 2) gadget_mac<L, 2>(sm, ck, R, qa, q, qni);
+            else if (cols_out == 3) gadget_mac<L, 3>(sm, ck, R, qa, q, qni);
+            else if (cols_out == 4) gadget_mac<L, 4>(sm, ck, R, qa, q, qni);
+            else gadget_mac<L, 1>(sm, ck, R, qa, q, qni);
         }
         // ---- inverse pass 1 (levels L-1 .. L-NL3, 16 consecutive words) --------------------------------------------------------------
         {
@@ -892,7 +914,7 @@ int ntt120_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_co
     memset(&ca, 0, sizeof ca);
     ca.pmat = pmat; ca.out = (uint32_t *)ck; ca.n = (int)n; ca.R = R; ca.C = C; ca.cols_out = cols_out; ca.S = S;
     for (int j = 0; j < S; j++)
-        for (int k = 0; k < 4; k++) ca.c[j][k] = pow2_mod((uint64_t)(S - 1 - j) * base2k, qk(k));
+        for (int k = 0; k < 4; k++) ca.c[j][k] = pow2_mod((uint64_t)(S - 1 - j) * base2k + 32, qk(k)); // times 2^32: Montgomery form (gadget_mac)
     for (int r = 0; r < R; r++) {
         if (dsize == 1) {
             ca.src_row[r] = (signed char)r; ca.di[r] = 0; ca.jmax[r] = (signed char)S;
@@ -978,6 +1000,9 @@ int ntt120_gadget_fused(pgb_module *m, const char *in, uint64_t in_bs, int in_co
         p.prime[k].c32 = c32;
         p.prime[k].c32s = (uint32_t)(((unsigned long long)c32 << 32) / q);
         p.prime[k].neg64 = q - (uint32_t)(((unsigned long long)c32 * c32) % q);
+        uint32_t qinv = q; // Newton: q^-1 mod 2^32
+        for (int it = 0; it < 5; it++) qinv *= 2u - q * qinv;
+        p.prime[k].qni = 0u - qinv;
         p.nq_w[k] = (uint32_t)(((u128)0 - Q) >> (32 * k));
         if (k >= np) continue;
         const u128 mk = Q / q;
