@@ -207,6 +207,31 @@ struct TwLast {
         }
     }
 };
+// the 15 twiddles of a pass held in registers: loaded once per pass and reused by every polynomial of the pass
+struct TwRegs {
+    uint2 w[16]; // node order: w[1], w[2..3], w[4..7], w[8..15]
+    template <class TW> __device__ __forceinline__ void load(const TW &src, const int nlev) {
+        if (nlev >= 4) w[1] = src.get1();
+        if (nlev >= 3) { uint2 a[2]; src.get2(a); w[2] = a[0]; w[3] = a[1]; }
+        if (nlev >= 2) { uint2 a[4]; src.get4(a);
+#pragma unroll
+            for (int i = 0; i < 4; i++) w[4 + i] = a[i]; }
+        { uint2 a[8]; src.get8(a);
+#pragma unroll
+            for (int i = 0; i < 8; i++) w[8 + i] = a[i]; }
+    }
+    __device__ __forceinline__ uint2 get1() const { return w[1]; }
+    __device__ __forceinline__ void get2(uint2 (&o)[2]) const { o[0] = w[2]; o[1] = w[3]; }
+    __device__ __forceinline__ void get4(uint2 (&o)[4]) const {
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = w[4 + i];
+    }
+    __device__ __forceinline__ void get8(uint2 (&o)[8]) const {
+#pragma unroll
+        for (int i = 0; i < 8; i++) o[i] = w[8 + i];
+    }
+};
+
 // L2 prefetch of a contiguous global range by one thread (TMA bulk prefetch; bytes must be a multiple of 16)
 __device__ __forceinline__ void prefetch_l2_bulk(const void *gptr, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
@@ -564,7 +589,9 @@ template <int L, bool AUT, int NP> __device__ __forceinline__ void gadget_body(c
         __syncthreads();
         // ---- forward pass 3 (16 consecutive words per thread), results reduced to [0, 2q) ------------------------------------------
         {
-            const TwLast tw = {lastf + t, T};
+            const TwLast tws = {lastf + t, T};
+            TwRegs tw;
+            tw.load(tws, G::NL3);
             for (int r = 0; r < R; r++) {
                 uint32_t *pl = sm + r * n;
                 uint32_t x[16];
@@ -591,7 +618,9 @@ template <int L, bool AUT, int NP> __device__ __forceinline__ void gadget_body(c
         }
         // ---- inverse pass 1 (levels L-1 .. L-NL3, 16 consecutive words) --------------------------------------------------------------
         {
-            const TwLast tw = {lasti + t, T};
+            const TwLast tws = {lasti + t, T};
+            TwRegs tw;
+            tw.load(tws, G::NL3);
             for (int o = 0; o < cols_out; o++) {
                 uint32_t *pl = sm + o * n;
                 uint32_t x[16];
@@ -623,12 +652,14 @@ template <int L, bool AUT, int NP> __device__ __forceinline__ void gadget_body(c
         // ---- inverse pass 3 (levels 3..0, stride T), scale by CRT_k / n, canonical residues back to the plane ----------------------
         {
             const uint32_t cn = p.crt_ninv[K], cns = p.crt_ninv_sh[K];
+            TwRegs top_r;
+            top_r.load(top_i, 4);
             for (int o = 0; o < cols_out; o++) {
                 uint32_t *pl = sm + o * n;
                 uint32_t x[16];
 #pragma unroll
                 for (int j = 0; j < 16; j++) x[j] = pl[P1_ADDR(j)];
-                gs16<4>(x, top_i, q, z);
+                gs16<4>(x, top_r, q, z);
 #pragma unroll
                 for (int j = 0; j < 16; j++) pl[P1_ADDR(j)] = csub(mul_shoup(x[j], cn, cns, q), q);
             }
