@@ -391,45 +391,48 @@ __device__ __forceinline__ void gadget_tail_narrow(const GadgetArgs &p, const ui
             }
         }
         long long *out_p = res + (size_t)(S - 1) * res_ls + (size_t)o * n + c0 * T + t;
+        // one digit step; the body limbs of the NEXT step are requested before this step's arithmetic, the two buffers alternate
+#define TAIL_STEP(J, CUR, NXT)                                                                                                     \
+    {                                                                                                                              \
+        const int j_ = (J);                                                                                                        \
+        if (SMALL) {                                                                                                               \
+            bp -= in_ls;                                                                                                           \
+            _Pragma("unroll") for (int g = 0; g < G; g++)                                                                          \
+                NXT[g] = (j_ >= 1 && j_ - 1 < p.small_size && valid[g]) ? __ldg(bp + g * NP * T) : 0;                              \
+            if (j_ < p.small_size) {                                                                                               \
+                _Pragma("unroll") for (int g = 0; g < G; g++) {                                                                    \
+                    const uint32_t lo = (uint32_t)CUR[g], hi = (uint32_t)((unsigned long long)CUR[g] >> 32), sx = (uint32_t)(CUR[g] >> 63); \
+                    if (NW == 1) w[g][0] += lo;                                                                                    \
+                    else if (NW == 2) asm("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;" : "+r"(w[g][0]), "+r"(w[g][1]) : "r"(lo), "r"(hi)); \
+                    else if (NW == 3)                                                                                              \
+                        asm("add.cc.u32 %0, %0, %3; addc.cc.u32 %1, %1, %4; addc.u32 %2, %2, %5;"                                  \
+                            : "+r"(w[g][0]), "+r"(w[g][1]), "+r"(w[g][NW > 2 ? 2 : 0]) : "r"(lo), "r"(hi), "r"(sx));               \
+                    else                                                                                                           \
+                        asm("add.cc.u32 %0, %0, %4; addc.cc.u32 %1, %1, %5; addc.cc.u32 %2, %2, %6; addc.u32 %3, %3, %6;"          \
+                            : "+r"(w[g][0]), "+r"(w[g][1]), "+r"(w[g][NW > 2 ? 2 : 0]), "+r"(w[g][NW > 3 ? 3 : 0])                 \
+                            : "r"(lo), "r"(hi), "r"(sx));                                                                          \
+                }                                                                                                                  \
+            }                                                                                                                      \
+        }                                                                                                                          \
+        if (j_ < a_start) {                                                                                                        \
+            _Pragma("unroll") for (int g = 0; g < G; g++)                                                                          \
+                if (valid[g]) out_p[g * NP * T] = (long long)((int)(w[g][0] & kmask32) - (int)khalf32);                            \
+        }                                                                                                                          \
+        out_p -= res_ls;                                                                                                           \
+        _Pragma("unroll") for (int g = 0; g < G; g++) {                                                                            \
+            _Pragma("unroll") for (int wi = 0; wi + 1 < NW; wi++) w[g][wi] = __funnelshift_r(w[g][wi], w[g][wi + 1], Kb);          \
+            w[g][NW - 1] >>= Kb;                                                                                                   \
+        }                                                                                                                          \
+    }
+        long long body2[G];
+        int j = S - 1;
 #pragma unroll 1
-        for (int j = S - 1; j >= 0; j--) {
-            long long next[G];
-            if (SMALL) { // next step's body limbs are requested before this step's arithmetic
-                bp -= in_ls;
-#pragma unroll
-                for (int g = 0; g < G; g++) next[g] = (j >= 1 && j - 1 < p.small_size && valid[g]) ? __ldg(bp + g * NP * T) : 0;
-                if (j < p.small_size) {
-#pragma unroll
-                    for (int g = 0; g < G; g++) {
-                        const uint32_t lo = (uint32_t)body[g], hi = (uint32_t)((unsigned long long)body[g] >> 32), sx = (uint32_t)(body[g] >> 63);
-                        if (NW == 1) w[g][0] += lo;
-                        else if (NW == 2) asm("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;" : "+r"(w[g][0]), "+r"(w[g][1]) : "r"(lo), "r"(hi));
-                        else if (NW == 3)
-                            asm("add.cc.u32 %0, %0, %3; addc.cc.u32 %1, %1, %4; addc.u32 %2, %2, %5;"
-                                : "+r"(w[g][0]), "+r"(w[g][1]), "+r"(w[g][NW > 2 ? 2 : 0]) : "r"(lo), "r"(hi), "r"(sx));
-                        else
-                            asm("add.cc.u32 %0, %0, %4; addc.cc.u32 %1, %1, %5; addc.cc.u32 %2, %2, %6; addc.u32 %3, %3, %6;"
-                                : "+r"(w[g][0]), "+r"(w[g][1]), "+r"(w[g][NW > 2 ? 2 : 0]), "+r"(w[g][NW > 3 ? 3 : 0]) : "r"(lo), "r"(hi), "r"(sx));
-                    }
-                }
-            }
-            if (j < a_start) {
-#pragma unroll
-                for (int g = 0; g < G; g++)
-                    if (valid[g]) out_p[g * NP * T] = (long long)((int)(w[g][0] & kmask32) - (int)khalf32);
-            }
-            out_p -= res_ls;
-#pragma unroll
-            for (int g = 0; g < G; g++) {
-#pragma unroll
-                for (int wi = 0; wi + 1 < NW; wi++) w[g][wi] = __funnelshift_r(w[g][wi], w[g][wi + 1], Kb);
-                w[g][NW - 1] >>= Kb;
-            }
-            if (SMALL) {
-#pragma unroll
-                for (int g = 0; g < G; g++) body[g] = next[g];
-            }
+        for (; j >= 1; j -= 2) {
+            TAIL_STEP(j, body, body2)
+            TAIL_STEP(j - 1, body2, body)
         }
+        if (j == 0) TAIL_STEP(0, body, body2)
+#undef TAIL_STEP
         long long *zp = res + (size_t)o * n + c0 * T + t;
         for (int j = a_start; j < p.res_size; j++) {
 #pragma unroll
@@ -533,12 +536,13 @@ template <int L, bool AUT, int NP> __device__ __forceinline__ void gadget_body(c
         // ---- forward pass 1 (levels 0..3, stride T) fused with the i64 load and the magnitude scan -------------------------------
         uint32_t mag = 0;       // OR of |v|-like patterns of the values that fit 32 bits
         bool too_big = false;
-        for (int r = 0; r < R; r++) {
-            const int limb = r / p.row_cols, col = r % p.row_cols + p.row_col0;
-            const long long *src = in + ((size_t)limb * p.in_cols + col) * n + t;
-            long long v[16];
+        long long v[16]; // the loads of polynomial r + 1 are issued before the butterflies of polynomial r
+        {
+            const long long *src = in + (size_t)p.row_col0 * n + t;
 #pragma unroll
             for (int j = 0; j < 16; j++) v[j] = __ldg(src + j * T);
+        }
+        for (int r = 0; r < R; r++) {
             uint32_t x[16];
             uint32_t wide = 0;
 #pragma unroll
@@ -556,6 +560,12 @@ template <int L, bool AUT, int NP> __device__ __forceinline__ void gadget_body(c
                     x[j] = from_i64_rt(v[j], pc);
                 }
                 too_big |= amax_allowed < 0 || (m64 >> (amax_allowed > 63 ? 63 : amax_allowed)) != 0;
+            }
+            if (r + 1 < R) {
+                const int limb = (r + 1) / p.row_cols, col = (r + 1) % p.row_cols + p.row_col0;
+                const long long *src = in + ((size_t)limb * p.in_cols + col) * n + t;
+#pragma unroll
+                for (int j = 0; j < 16; j++) v[j] = __ldg(src + j * T);
             }
             ct16<4>(x, top_f, q, z);
             if (r == 0) cl_wait(); // peers have finished reading my planes (CRT of the previous ciphertext)
