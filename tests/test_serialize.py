@@ -51,6 +51,46 @@ def test_reader_errors():
         S.read_mat_znx(io.BytesIO(bytes(m)))
 
 
+def test_untrusted_headers_are_rejected_before_the_payload_is_read():
+    """A self-consistent but implausible header must fail with ValueError without touching the payload (no allocation of `len` bytes)."""
+
+    class Tripwire(io.BytesIO):
+        def read(self, size=-1):
+            assert size <= 64, "payload read attempted"
+            return super().read(size)
+
+    huge = struct.pack("<5Q", 1 << 16, 1 << 12, 1 << 12, 1 << 12, (1 << 16) * (1 << 24) * 8)      # 8 TiB, self-consistent
+    with pytest.raises(ValueError, match="buffer too small"):
+        S.read_vec_znx(Tripwire(huge))
+    for hdr in (struct.pack("<5Q", 24, 1, 1, 1, 24 * 8),                 # n not a power of two
+                struct.pack("<5Q", 0, 1, 1, 1, 0),                       # n = 0
+                struct.pack("<5Q", 1 << 20, 1, 1, 1, (1 << 20) * 8),     # n beyond any parameter set
+                struct.pack("<5Q", 8, 0, 1, 1, 0),                       # zero columns
+                struct.pack("<5Q", 8, 1 << 40, 1, 1, (1 << 40) * 64),    # absurd column count
+                struct.pack("<5Q", 8, 1 << 61, 8, 8, 0)):                # a product that wraps a usize to 0: checked in Python integers
+        with pytest.raises(ValueError):
+            S.read_vec_znx(Tripwire(hdr))
+    with pytest.raises(ValueError):
+        S.read_mat_znx(Tripwire(struct.pack("<6Q", 8, 1, 0, 1, 1, 0)))   # zero rows
+    with pytest.raises(ValueError):
+        S.read_scalar_znx(Tripwire(struct.pack("<3Q", 12, 1, 96)))
+
+
+@pytest.mark.gpu
+def test_import_key_rejects_an_unexpected_layout():
+    import poulpy_b200 as pb
+
+    g = pb.Module(1024, pb.NTT120)
+    mat = np.zeros((3, 1, 4, 2, 1024), dtype=np.int64)
+    with pytest.raises(ValueError, match="buffer too small|key layout"):
+        S.import_key(g, io.BytesIO(S.dumps("mat_znx", mat)), expect=(2, 1, 2, 4))
+    with pytest.raises(ValueError, match="key layout"):
+        S.import_key(g, io.BytesIO(S.dumps("mat_znx", mat)), expect=(4, 1, 2, 3))
+    with pytest.raises(ValueError, match="ring degree"):
+        S.import_key(pb.Module(2048, pb.NTT120), io.BytesIO(S.dumps("mat_znx", mat)))
+    S.import_key(g, io.BytesIO(S.dumps("mat_znx", mat)), expect=(3, 1, 2, 4))
+
+
 @pytest.mark.gpu
 def test_import_key_matches_oracle_prepare():
     import poulpy_b200 as pb
