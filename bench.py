@@ -336,9 +336,11 @@ def main():
             d["frac_of_hbm_peak"] = d["achieved_gbs"] / peak
         kernels[nm] = d
     dom = max((k_ for k_ in kernels if "achieved_gbs" in kernels[k_]), key=lambda k_: kernels[k_]["launches"] * kernels[k_]["avg_ms"])
-    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/r1_traffic.json, bytes per key-switch)
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/r2_traffic.json, bytes per key-switch)
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(tp):
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp))
         if dom in tj:

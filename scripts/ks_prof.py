@@ -11,8 +11,9 @@ import poulpy_b200 as pb
 n, k, B = 4096, 18, int(os.environ.get("KS_BATCH", "2048"))
 m = pb.Module(n, pb.FFT64 if os.environ.get("KS_FLAVOUR") == "fft64" else pb.NTT120)
 rng = np.random.default_rng(1)
-mat = rng.integers(-(1 << 17), 1 << 17, size=(3, 1, 4, 2, n), dtype=np.int64)
-pm = m.vmp_pmat_alloc(3, 1, 2, 4)
+KS = 3 if os.environ.get("KS_KEY3") else 4  # KS_KEY3: a three-limb key (the three-prime launch when pinned)
+mat = rng.integers(-(1 << 17), 1 << 17, size=(3, 1, KS, 2, n), dtype=np.int64)
+pm = m.vmp_pmat_alloc(3, 1, 2, KS)
 m.vmp_prepare(pm, m.mat_znx_from_numpy(mat))
 if os.environ.get("KS_PIN"):
     m.gadget_key_pin(pm)
