@@ -664,7 +664,16 @@ cggi_fused3_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
 // (poly, key) order): 4 partial-sum doubles per thread instead of 64, the X^{a_t} factors of all keys of the block loaded once, no spills.
 // Per (ciphertext, frequency, output poly) the floating-point operations and their order are exactly those of version 3 (rows in row
 // order inside a key, keys in block order), so the results are bit-identical to it.
-template <int LM, int G, int RT, int CT, int NSTAGE, int BS> __global__ void __launch_bounds__(512 + 32, 1)
+// CG4_PRODUCER_WARP = 0 builds the measured alternative without a producer: the warp whose lane 0 is the LAST of the 16 to finish a tile (a
+// shared-memory counter per stage, ordering through the "empty" barrier) issues the bulk copies of the tile NSTAGE ahead; the 16-warp CTA
+// gets 126 registers per thread instead of 96 and no spill.  Bit-identical, and 23 % SLOWER (98.4 k vs 127.4 k bootstraps/s): the refill is
+// ~40 instructions executed by one lane of a consumer warp, which stalls that warp exactly when the ring is shortest -- the same flaw as
+// version 3's thread-0 producer.  The dedicated warp is what makes version 4 fast, not its register budget.
+#ifndef CG4_PRODUCER_WARP
+#define CG4_PRODUCER_WARP 1
+#endif
+constexpr int CG4_THREADS = 512 + (CG4_PRODUCER_WARP ? 32 : 0);
+template <int LM, int G, int RT, int CT, int NSTAGE, int BS> __global__ void __launch_bounds__(CG4_THREADS, 1)
 cggi_fused4_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, const double2 *__restrict__ twi_g, const double2 *__restrict__ twlf_g,
                          const double2 *__restrict__ twli_g, double inv_m) {
     typedef FGeo<LM> FG;
@@ -678,15 +687,16 @@ cggi_fused4_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
     extern __shared__ __align__(128) double2 csm[];
     __shared__ int s_pos[G * 8];
     __shared__ __align__(8) unsigned long long s_bar[NSTAGE], s_empty[NSTAGE]; // tile filled / tile consumed by all threads
+    __shared__ unsigned int s_done[NSTAGE]; // warps that have finished the tile of this stage (producer-less refill)
     double *ring = reinterpret_cast<double *>(csm + (size_t)G * GS); // [NSTAGE][RT][N]
     // both twiddle tables (m complex values each) live in shared memory: with ~210 KB of it in use the L1 is too small to keep them
     // M entries per direction as before, split into the first T block twiddles and the [7][T] last-pass table
     double2 *twf = reinterpret_cast<double2 *>(ring + (size_t)NSTAGE * RT * N), *twlf = twf + T, *twi = twf + M, *twli = twi + T;
-    for (int i = threadIdx.x; i < T; i += 512 + 32) {
+    for (int i = threadIdx.x; i < T; i += CG4_THREADS) {
         twf[i] = twf_g[i];
         twi[i] = twi_g[i];
     }
-    for (int i = threadIdx.x; i < 7 * T; i += 512 + 32) {
+    for (int i = threadIdx.x; i < 7 * T; i += CG4_THREADS) {
         twlf[i] = twlf_g[i];
         twli[i] = twli_g[i];
     }
@@ -701,39 +711,50 @@ cggi_fused4_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; s++) {
             mbar_init(bar_s + s * 8, 1);
-            mbar_init(empty_s + s * 8, NT);
+            mbar_init(empty_s + s * 8, CG4_PRODUCER_WARP ? NT : NT / 32);
+            s_done[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // ---- producer warp (warp 16): tiles in (block, output poly c, key t) order, refilled the moment all consumers released the stage -----
-    if (tid >= NT) {
-        if (tid == NT) {
-            int tt = 0, c = 0;
-            const double *key0 = p.brk; // first key of the current block
-            for (int gk = 0; gk < total_tiles; gk++) {
-                const int st = gk % NSTAGE;
-                if (gk >= NSTAGE) mbar_wait(empty_s + st * 8, (uint32_t)((gk / NSTAGE - 1) & 1));
-                const uint32_t bar = bar_s + st * 8;
-                mbar_expect_tx(bar, TILE);
-                const double *src = key0 + (size_t)tt * p.brk_doubles + (size_t)c * N;
+    // ---- key stream: tiles in (block, output poly c, key t) order ------------------------------------------------------------------------
+    auto issue_src = [&](const double *src, const uint32_t st_) { // one thread: bulk copies of one tile (RT key rows of one output poly)
+        const uint32_t bar = bar_s + st_ * 8;
+        mbar_expect_tx(bar, TILE);
 #pragma unroll
-                for (int r = 0; r < RT; r++) bulk_g2s(ring_s + (uint32_t)(st * RT + r) * CHUNK, src + (size_t)r * C * N, CHUNK, bar);
-                if (++tt == bs) {
-                    tt = 0;
-                    if (++c == C) {
-                        c = 0;
-                        key0 += (size_t)bs * p.brk_doubles;
+        for (int r = 0; r < RT; r++) bulk_g2s(ring_s + (uint32_t)(st_ * RT + r) * CHUNK, src + (size_t)r * C * N, CHUNK, bar);
+    };
+    auto issue_tile = [&](const uint32_t gk_, const uint32_t st_) { // the same from the tile index (producer-less mode)
+        const uint32_t b_ = gk_ / (uint32_t)tiles_per_blk, rem_ = gk_ - b_ * (uint32_t)tiles_per_blk, c_ = rem_ / (uint32_t)bs, t_ = rem_ - c_ * (uint32_t)bs;
+        issue_src(p.brk + ((size_t)b_ * bs + t_) * p.brk_doubles + (size_t)c_ * N, st_);
+    };
+    if (CG4_PRODUCER_WARP) {
+        if (tid >= NT) { // warp 16: refills a stage the moment all consumers have released it
+            if (tid == NT) {
+                int tt = 0, c = 0;
+                const double *key0 = p.brk; // first key of the current block
+                for (int gk = 0; gk < total_tiles; gk++) {
+                    const int st = gk % NSTAGE;
+                    if (gk >= NSTAGE) mbar_wait(empty_s + st * 8, (uint32_t)((gk / NSTAGE - 1) & 1));
+                    issue_src(key0 + (size_t)tt * p.brk_doubles + (size_t)c * N, (uint32_t)st);
+                    if (++tt == bs) {
+                        tt = 0;
+                        if (++c == C) {
+                            c = 0;
+                            key0 += (size_t)bs * p.brk_doubles;
+                        }
                     }
                 }
             }
+            return;
         }
-        return;
+    } else if (tid == 0) {
+        for (int gk = 0; gk < NSTAGE && gk < total_tiles; gk++) issue_tile((uint32_t)gk, (uint32_t)gk);
     }
 
     const int gp = tid % GH, f = tid / GH; // this thread's frequency and its two ciphertexts gp, gp + GH
     double2 *mine0 = csm + (size_t)gp * GS + FPAD(f), *mine1 = csm + (size_t)(gp + GH) * GS + FPAD(f);
-    int gk = 0;
+    uint32_t gk = 0;
 
     for (int blk = 0; blk + bs <= p.n_lwe; blk += bs) {
         if (tid < G * bs) {
@@ -787,8 +808,8 @@ cggi_fused4_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
 #pragma unroll
                 for (int tt = 0; tt < BS; tt++) {
                     if (tt < bs) { // uniform
-                        const int st = gk % NSTAGE;
-                        mbar_wait(bar_s + st * 8, (uint32_t)((gk / NSTAGE) & 1));
+                        const uint32_t st = gk % NSTAGE;
+                        mbar_wait(bar_s + st * 8, (gk / NSTAGE) & 1u);
                         const double *tile = ring + (size_t)st * RT * N + f;
                         double v0r = 0.0, v0i = 0.0, v1r = 0.0, v1i = 0.0;
 #pragma unroll
@@ -799,7 +820,24 @@ cggi_fused4_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
                             v1r = fma(a1r[r], br, v1r); v1r = fma(-a1i[r], bi, v1r);
                             v1i = fma(a1r[r], bi, v1i); v1i = fma(a1i[r], br, v1i);
                         }
-                        mbar_arrive(empty_s + st * 8); // the key values are in registers: release the stage to the producer warp
+                        if (CG4_PRODUCER_WARP) {
+                            mbar_arrive(empty_s + st * 8); // the key values are in registers: release the stage to the producer warp
+                        } else {
+                            __syncwarp(); // every lane's key values are in registers
+                            if ((tid & 31) == 0) {
+                                mbar_arrive(empty_s + st * 8);
+                                // the last warp out refills the stage.  The counter only elects it; the ordering comes from the barrier:
+                                // every warp arrived (release) before it counted itself, so the wait (acquire) completes at once
+                                if (atomicAdd(&s_done[st], 1u) == NT / 32 - 1) {
+                                    s_done[st] = 0;
+                                    mbar_wait(empty_s + st * 8, (gk / NSTAGE) & 1u);
+                                    if (gk + NSTAGE < (uint32_t)total_tiles) {
+                                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                                        issue_tile(gk + NSTAGE, st);
+                                    }
+                                }
+                            }
+                        }
                         const double p0r = fma(w0r[tt], v0r, -(w0i[tt] * v0i)), p0i = fma(w0r[tt], v0i, w0i[tt] * v0r); // svp: reim_mul(ppol, v)
                         const double p1r = fma(w1r[tt], v1r, -(w1i[tt] * v1i)), p1i = fma(w1r[tt], v1i, w1i[tt] * v1r);
                         s0r = (s0r + p0r) - v0r; s0i = (s0i + p0i) - v0i; // dft_add_assign then dft_sub_assign, keys in block order
@@ -934,7 +972,7 @@ template <int LM, int G, int RT, int CT, int NSTAGE, int BS> static int launch_c
     }
     const int grid = (p.batch + G - 1) / G;
     { ProfScope _ps(m, PROF_OTHER);
-    cggi_fused4_fft64_kernel<LM, G, RT, CT, NSTAGE, BS><<<grid, 512 + 32, smem, m->stream>>>(p, m->fft_fwd, m->fft_inv, m->fft_last_f, m->fft_last_i,
+    cggi_fused4_fft64_kernel<LM, G, RT, CT, NSTAGE, BS><<<grid, CG4_THREADS, smem, m->stream>>>(p, m->fft_fwd, m->fft_inv, m->fft_last_f, m->fft_last_i,
                                                                                          1.0 / (double)(1 << LM));
     }
     PGB_CHECK_CUDA(cudaGetLastError());

@@ -186,11 +186,22 @@ template <int L> struct NInv<L, -1> {
     static __device__ __forceinline__ void run(uint32_t *, const uint2 *, int, int, bool, uint32_t) {}
 };
 
-constexpr int CGN_COMPUTE = 512; // compute threads; warp 16 is the key-stream producer
+constexpr int CGN_COMPUTE = 512; // compute threads
+// Key-stream refill.  1 (default): a 17th warp owns the ring (waits on the per-stage "empty" barriers, issues the bulk copies) -- the 17-warp
+// CTA is capped at 96 registers per thread because one SM partition then holds five warps.  0: no producer at all -- the warp whose lane 0
+// is the LAST of the 16 to finish a tile (shared-memory counter per stage, ordering through the "empty" barrier) issues the copy of the tile
+// NSTAGE ahead into that stage; the 16-warp CTA gets 126 registers per thread and no spill.  Measured (profiles/r2_ncu_cggi.md): no faster
+// here (68.1 k vs 68.6 k bootstraps/s, the kernel is bound by the FMA-heavy pipe, not by its 104 bytes of spill) and 23 % SLOWER in the
+// FFT64 kernel, where the refill issued by a consumer lane stalls that consumer's warp -- so the producer warp stays.
+#ifndef CGN_PRODUCER_WARP
+#define CGN_PRODUCER_WARP 1
+#endif
+constexpr int CGN_THREADS = CGN_COMPUTE + (CGN_PRODUCER_WARP ? 32 : 0);
 constexpr int CGN_BSMAX = 4;     // keys per block whose (X^a - 1) factors are held in registers
 
-// EXACT: RT and CT are the run-time row / output-poly counts (the BASELINE shape), so every index computation is by constants
-template <int L, int G, int RT, int CT, int NSTAGE, bool EXACT> __global__ void __launch_bounds__(CGN_COMPUTE + 32, 1)
+// EXACT > 0: RT and CT are the run-time row / output-poly counts and EXACT the block size (the BASELINE shape: 4, 8, 3), so every index
+// computation is by constants and the (X^a - 1) factors take 8 EXACT registers instead of 8 CGN_BSMAX (the 17-warp CTA is capped at 96)
+template <int L, int G, int RT, int CT, int NSTAGE, int EXACT> __global__ void __launch_bounds__(CGN_THREADS, 1)
 cggi_fused_ntt120_p2_kernel(CggiNttArgs p, const uint2 *__restrict__ twf_g, const uint2 *__restrict__ twi_g) {
     typedef NGeo<L> NG;
     constexpr int N = NG::N, T = NG::T, NT = CGN_COMPUTE, PL = NG::PLANE, NSLOT = NT / T, GH = G / 2, P = 2;
@@ -202,12 +213,13 @@ cggi_fused_ntt120_p2_kernel(CggiNttArgs p, const uint2 *__restrict__ twf_g, cons
     extern __shared__ __align__(128) uint32_t nsm[];
     __shared__ int s_pos[G * 8];
     __shared__ __align__(8) unsigned long long s_full[NSTAGE], s_empty[NSTAGE];
+    __shared__ unsigned int s_done[NSTAGE]; // warps that have finished the tile in this stage (producer-less refill)
     uint32_t *planes = nsm;                                           // [G][PMAX][P][PL]
     uint32_t *ring = nsm + (size_t)G * GS;                            // [NSTAGE][RT][P][N]
     uint2 *tws = reinterpret_cast<uint2 *>(ring + (size_t)NSTAGE * RT * P * N); // [dir][prime][T + 7 T]: block twiddles < T, last-pass table
     const int tid = threadIdx.x;
     // twiddles: every thread (the producer warp included) helps, then one CTA-wide barrier
-    for (int i = tid; i < 2 * P * 8 * T; i += NT + 32) {
+    for (int i = tid; i < 2 * P * 8 * T; i += CGN_THREADS) {
         const int e = i % (8 * T), k = (i / (8 * T)) % P, dir = i / (8 * T * P);
         const uint2 *src = (dir ? twi_g : twf_g) + (size_t)k * N;
         uint2 v;
@@ -223,40 +235,52 @@ cggi_fused_ntt120_p2_kernel(CggiNttArgs p, const uint2 *__restrict__ twf_g, cons
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; s++) {
             mbar_init(full_s + s * 8, 1);
-            mbar_init(empty_s + s * 8, NT / 32);
+            mbar_init(empty_s + s * 8, CGN_PRODUCER_WARP ? NT : NT / 32);
+            s_done[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int cols = p.cols, C = EXACT ? CT : cols * p.brk_size, K = p.base2k, bs = p.block_size;
+    const int cols = p.cols, C = EXACT ? CT : cols * p.brk_size, K = p.base2k, bs = EXACT ? EXACT : p.block_size;
+    constexpr int BSA = EXACT ? EXACT : CGN_BSMAX;
     const int nblk = p.n_lwe / bs, total_tiles = nblk * C * bs;
 
-    // ---- producer warp: tile gk = (block, output poly c, key t) in that order -------------------------------------------------------
-    if (tid >= NT) {
-        if (tid == NT) {
-            int t = 0, c = 0;
-            const uint32_t *key0 = p.brk; // first key of the current block
-            for (int gk = 0; gk < total_tiles; gk++) {
-                const int st = gk % NSTAGE;
-                if (gk >= NSTAGE) {
-                    const uint32_t bar = empty_s + st * 8, par = (uint32_t)((gk / NSTAGE - 1) & 1);
-                    while (!mbar_test(bar, par)) __nanosleep(64); // polite: the spin would otherwise take issue slots of compute warps
-                }
-                const uint32_t *src = key0 + (size_t)t * p.brk_words + (size_t)c * 4 * N;
-                const uint32_t bar = full_s + st * 8;
-                mbar_expect_tx(bar, TILE);
+    // ---- key stream: tile gk = (block, output poly c, key t) in that order ---------------------------------------------------------------
+    auto issue_src = [&](const uint32_t *src, const uint32_t st_) { // one thread: bulk copies of one tile (RT key rows of one output poly)
+        const uint32_t bar = full_s + st_ * 8;
+        mbar_expect_tx(bar, TILE);
 #pragma unroll
-                for (int r = 0; r < RT; r++) bulk_g2s(ring_s + (uint32_t)(st * RT + r) * CHUNK, src + (size_t)r * C * 4 * N, CHUNK, bar);
-                if (++t == bs) {
-                    t = 0;
-                    if (++c == C) {
-                        c = 0;
-                        key0 += (size_t)bs * p.brk_words;
+        for (int r = 0; r < RT; r++) bulk_g2s(ring_s + (uint32_t)(st_ * RT + r) * CHUNK, src + (size_t)r * C * 4 * N, CHUNK, bar);
+    };
+    auto issue_tile = [&](const uint32_t gk_, const uint32_t st_) { // the same from the tile index (producer-less mode)
+        const uint32_t per_blk = (uint32_t)(C * bs), b_ = gk_ / per_blk, rem_ = gk_ - b_ * per_blk, c_ = rem_ / (uint32_t)bs, t_ = rem_ - c_ * (uint32_t)bs;
+        issue_src(p.brk + ((size_t)b_ * bs + t_) * p.brk_words + (size_t)c_ * 4 * N, st_);
+    };
+    if (CGN_PRODUCER_WARP) {
+        if (tid >= NT) {
+            if (tid == NT) {
+                int t = 0, c = 0;
+                const uint32_t *key0 = p.brk; // first key of the current block
+                for (int gk = 0; gk < total_tiles; gk++) {
+                    const int st = gk % NSTAGE;
+                    if (gk >= NSTAGE) {
+                        const uint32_t bar = empty_s + st * 8, par = (uint32_t)((gk / NSTAGE - 1) & 1);
+                        while (!mbar_try(bar, par)) __nanosleep(64); // polite: the spin would otherwise take issue slots of compute warps
+                    }
+                    issue_src(key0 + (size_t)t * p.brk_words + (size_t)c * 4 * N, (uint32_t)st);
+                    if (++t == bs) {
+                        t = 0;
+                        if (++c == C) {
+                            c = 0;
+                            key0 += (size_t)bs * p.brk_words;
+                        }
                     }
                 }
             }
+            return;
         }
-        return;
+    } else if (tid == 0) {
+        for (int gk = 0; gk < NSTAGE && gk < total_tiles; gk++) issue_tile((uint32_t)gk, (uint32_t)gk);
     }
 
     const int slot = tid / T, t = tid % T, lane = tid & 31;
@@ -265,7 +289,7 @@ cggi_fused_ntt120_p2_kernel(CggiNttArgs p, const uint2 *__restrict__ twf_g, cons
     const uint32_t qk_ = p.q[kq], qni = p.qneg_inv[kq];
     const int mn_small = min(p.brk_size, p.out_size);
     const int a_start = min(p.out_size, p.brk_size); // same-base2k plan with offset 0: limbs >= a_start only feed the carry
-    int gk = 0;
+    uint32_t gk = 0;
     bool bad = false;
 
     for (int blk = 0; blk + bs <= p.n_lwe; blk += bs) {
@@ -320,11 +344,11 @@ cggi_fused_ntt120_p2_kernel(CggiNttArgs p, const uint2 *__restrict__ twf_g, cons
             }
             // (X^{a_t} - 1) * 2^64 / n at this thread's frequencies, per ciphertext and key: the two Montgomery reductions below each leave a
             // factor 2^-32 and the inverse transform a factor n; both are paid here, once per block, instead of per product
-            uint4 w0[CGN_BSMAX], w1[CGN_BSMAX];
+            uint4 w0[BSA], w1[BSA];
             const uint32_t cw = p.cw[kq], cws = p.cw_sh[kq];
             auto wfac = [&](uint32_t x) { return csub(mul_shoup(x ? x - 1 : qk_ - 1, cw, cws, qk_), qk_); };
 #pragma unroll
-            for (int tt = 0; tt < CGN_BSMAX; tt++) {
+            for (int tt = 0; tt < BSA; tt++) {
                 if (tt < bs) {
                     const uint4 x0 = __ldg(reinterpret_cast<const uint4 *>(p.xpa + ((size_t)s_pos[gp * 8 + tt] * 4 + kq) * N) + f4);
                     const uint4 x1 = __ldg(reinterpret_cast<const uint4 *>(p.xpa + ((size_t)s_pos[(gp + GH) * 8 + tt] * 4 + kq) * N) + f4);
@@ -336,10 +360,10 @@ cggi_fused_ntt120_p2_kernel(CggiNttArgs p, const uint2 *__restrict__ twf_g, cons
             for (int c = 0; c < C; c++) {
                 unsigned long long s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
 #pragma unroll
-                for (int tt = 0; tt < CGN_BSMAX; tt++) {
+                for (int tt = 0; tt < BSA; tt++) {
                     if (tt < bs) { // uniform
-                        const int st = gk % NSTAGE;
-                        mbar_wait(full_s + st * 8, (uint32_t)((gk / NSTAGE) & 1));
+                        const uint32_t st = gk % NSTAGE;
+                        mbar_wait(full_s + st * 8, (gk / NSTAGE) & 1u);
                         const uint32_t *tile = ring + (size_t)st * RT * P * N + (size_t)kq * N + 4 * f4;
                         unsigned long long v0[4] = {0, 0, 0, 0}, v1[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -350,9 +374,26 @@ cggi_fused_ntt120_p2_kernel(CggiNttArgs p, const uint2 *__restrict__ twf_g, cons
                             v1[0] += (unsigned long long)a1[r].x * kv.x; v1[1] += (unsigned long long)a1[r].y * kv.y;
                             v1[2] += (unsigned long long)a1[r].z * kv.z; v1[3] += (unsigned long long)a1[r].w * kv.w;
                         }
-                        // release the stage: one arrival per warp once all its lanes have read the tile
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(empty_s + st * 8);
+                        // release the stage.  With the producer warp every thread arrives for itself once its key values are in registers (one
+                        // arrival per warp after __syncwarp makes the release wait for the slowest lane; measured slower in the FFT64 kernel)
+                        if (CGN_PRODUCER_WARP) {
+                            mbar_arrive(empty_s + st * 8);
+                        } else {
+                            __syncwarp();
+                            if (lane == 0) {
+                                mbar_arrive(empty_s + st * 8);
+                                // the last warp out refills the stage.  The counter only elects it; the ordering comes from the barrier: every
+                                // warp arrived (release) before it counted itself, so the wait (acquire) below completes at once
+                                if (atomicAdd(&s_done[st], 1u) == NT / 32 - 1) {
+                                    s_done[st] = 0;
+                                    mbar_wait(empty_s + st * 8, (gk / NSTAGE) & 1u);
+                                    if (gk + NSTAGE < (uint32_t)total_tiles) {
+                                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                                        issue_tile(gk + NSTAGE, st);
+                                    }
+                                }
+                            }
+                        }
                         // (s + w v) - v = s + (w - 1) v: u64 products of the canonical factor (< 2^30) and the Montgomery-reduced row sum
                         // (< 2^31): at most CGN_BSMAX = 4 terms of < 2^61 per sum
                         s0[0] += (unsigned long long)w0[tt].x * redc64(v0[0], qk_, qni); s0[1] += (unsigned long long)w0[tt].y * redc64(v0[1], qk_, qni);
@@ -461,7 +502,7 @@ cggi_fused_ntt120_p2_kernel(CggiNttArgs p, const uint2 *__restrict__ twf_g, cons
     if (bad) atomicOr(p.fail, 1);
 }
 
-template <int L, int G, int RT, int CT, int NSTAGE, bool EXACT> int launch_p2(pgb_module *m, const CggiNttArgs &p) {
+template <int L, int G, int RT, int CT, int NSTAGE, int EXACT> int launch_p2(pgb_module *m, const CggiNttArgs &p) {
     typedef NGeo<L> NG;
     constexpr int PMAX = RT > CT ? RT : CT;
     const size_t smem = ((size_t)G * PMAX * 2 * NG::PLANE + (size_t)NSTAGE * RT * 2 * NG::N) * 4 + (size_t)2 * 2 * 8 * NG::T * sizeof(uint2);
@@ -472,7 +513,7 @@ template <int L, int G, int RT, int CT, int NSTAGE, bool EXACT> int launch_p2(pg
     }
     const int grid = (p.batch + G - 1) / G;
     { ProfScope _ps(m, PROF_OTHER);
-    cggi_fused_ntt120_p2_kernel<L, G, RT, CT, NSTAGE, EXACT><<<grid, CGN_COMPUTE + 32, smem, m->stream>>>(p, m->ntt_fwd, m->ntt_inv);
+    cggi_fused_ntt120_p2_kernel<L, G, RT, CT, NSTAGE, EXACT><<<grid, CGN_THREADS, smem, m->stream>>>(p, m->ntt_fwd, m->ntt_inv);
     }
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;
@@ -613,11 +654,11 @@ int cggi_fused_ntt120(pgb_module *m, long long *res, uint64_t res_stride_words, 
     p.Q2 = (unsigned long long)qk(0) * qk(1);
     p.half2 = (p.Q2 + 1) / 2;
     int s;
-    if (R == 4 && C == 8) s = launch_p2<9, 4, 4, 8, 4, true>(m, p);
-    else if (R == 4 && C > 4) s = launch_p2<9, 4, 4, 8, 4, false>(m, p);
-    else if (R == 4) s = launch_p2<9, 4, 4, 4, 4, false>(m, p);
-    else if (C > 4) s = launch_p2<9, 4, 2, 8, 4, false>(m, p);
-    else s = launch_p2<9, 4, 2, 4, 4, false>(m, p);
+    if (R == 4 && C == 8 && block_size == 3) s = launch_p2<9, 4, 4, 8, 4, 3>(m, p);
+    else if (R == 4 && C > 4) s = launch_p2<9, 4, 4, 8, 4, 0>(m, p);
+    else if (R == 4) s = launch_p2<9, 4, 4, 4, 4, 0>(m, p);
+    else if (C > 4) s = launch_p2<9, 4, 2, 8, 4, 0>(m, p);
+    else s = launch_p2<9, 4, 2, 4, 4, 0>(m, p);
     PGB_TRY(s);
     int fail = 0;
     PGB_CHECK_CUDA(cudaMemcpyAsync(&fail, flags + 1, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
