@@ -504,11 +504,11 @@ def test_coefficient_domain_helpers():
         assert np.array_equal(g.vec_znx_to_numpy(xg), want), size
 
 
-def test_vmp_batch_tiled_large_key():
-    """Matrices beyond 48 MB take the batch-tiled vmp kernel (one matrix read per four ciphertexts).  batch = 6 leaves a partial tile;
-    the result must equal the per-item kernel bit for bit, and item 0 must match the oracle after idft + normalize."""
-    import os
-    n, rows, cols_out, size, batch, k = 16384, 13, 2, 8, 6, 30
+@pytest.mark.parametrize("batch", [6, 37])
+def test_vmp_batch_tiled_large_key(batch):
+    """Matrices beyond 48 MB take the batch-tiled vmp kernel (one matrix read per four ciphertexts).  batch = 6 leaves a partial tile of two,
+    batch = 37 one of one; the result must equal the per-item kernel bit for bit, and item 0 must match the oracle after idft + normalize."""
+    n, rows, cols_out, size, k = 16384, 13, 2, 8, 30
     g, o = pb.Module(n, pb.NTT120), O.OracleModule(n, pb.NTT120)
     rng = np.random.default_rng(29)
     mat = fill_uniform(rng, (rows, 1, size, cols_out, n), k)
