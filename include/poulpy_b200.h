@@ -95,6 +95,7 @@ typedef enum {
     PGB_OPT_CGGI_NTT_PRIMES = 9, /* PGB_CGGI_NTT_PRIMES: 0 = adaptive prime count in the NTT120 whole-rotation kernel, 2 / 3 / 4 = forced */
     PGB_OPT_GADGET_PRIMES = 10, /* PGB_GADGET_PRIMES: 0 = the NTT120 gadget kernel works on three primes when a pinned key's bound allows it, 4 = always four */
     PGB_OPT_LAST_GADGET_PRIMES = 11, /* read-only diagnostic: primes the last NTT120 gadget-kernel launch worked on (3 or 4; 0 = none yet) */
+    PGB_OPT_CGGI_CLUSTER = 12,  /* PGB_CGGI_CLUSTER: 2 = the FFT64 whole-rotation kernel runs in clusters of two CTAs that share every key tile by TMA multicast */
     PGB_OPT_COUNT = 16
 } pgb_option;
 int pgb_module_set_option(pgb_module *m, int option, int64_t value);

@@ -113,7 +113,7 @@ extern "C" int pgb_module_new(uint64_t n, int flavour, int device, pgb_module **
             {PGB_OPT_CGGI_BLOCK_BT1, "PGB_CGGI_BLOCK_BT1", 0, true}, {PGB_OPT_VMP_NO_BT, "PGB_VMP_NO_BT", 0, true},
             {PGB_OPT_VMP_CT, "PGB_VMP_CT", 0, false},       {PGB_OPT_GADGET_MB, "PGB_GADGET_MB", 3, false},
             {PGB_OPT_HOST_CHUNK_MB, "PGB_HOST_CHUNK_MB", 32, false}, {PGB_OPT_CGGI_NTT_PRIMES, "PGB_CGGI_NTT_PRIMES", 0, false},
-            {PGB_OPT_GADGET_PRIMES, "PGB_GADGET_PRIMES", 0, false}};
+            {PGB_OPT_GADGET_PRIMES, "PGB_GADGET_PRIMES", 0, false}, {PGB_OPT_CGGI_CLUSTER, "PGB_CGGI_CLUSTER", 0, false}};
         for (const auto &sd : seeds) {
             const char *e = getenv(sd.env);
             m->opt[sd.opt] = e ? (sd.flag ? 1 : (int64_t)atoll(e)) : sd.dflt;

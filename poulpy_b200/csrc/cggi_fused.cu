@@ -688,6 +688,7 @@ cggi_fused4_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
     __shared__ int s_pos[G * 8];
     __shared__ __align__(8) unsigned long long s_bar[NSTAGE], s_empty[NSTAGE]; // tile filled / tile consumed by all threads
     __shared__ unsigned int s_done[NSTAGE]; // warps that have finished the tile of this stage (producer-less refill)
+    __shared__ __align__(8) unsigned long long s_peer[NSTAGE]; // rank 0 of a cluster: the other CTAs have drained this stage and armed their barrier
     double *ring = reinterpret_cast<double *>(csm + (size_t)G * GS); // [NSTAGE][RT][N]
     // both twiddle tables (m complex values each) live in shared memory: with ~210 KB of it in use the L1 is too small to keep them
     // M entries per direction as before, split into the first T block twiddles and the [7][T] last-pass table
@@ -706,17 +707,23 @@ cggi_fused4_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
     const int mn_small = min(p.brk_size, p.out_size);
     const int a_start = min(p.out_size, p.brk_size);
     const int nblk = p.n_lwe / bs, tiles_per_blk = bs * C, total_tiles = nblk * tiles_per_blk;
-    const uint32_t ring_s = smem_u32(ring), bar_s = smem_u32(s_bar), empty_s = smem_u32(s_empty);
+    const uint32_t ring_s = smem_u32(ring), bar_s = smem_u32(s_bar), empty_s = smem_u32(s_empty), peer_s = smem_u32(s_peer);
+    // Cluster launch (PGB_OPT_CGGI_CLUSTER = 2): the CTAs of a cluster walk the same key tiles, so rank 0 fetches each tile ONCE and the copy is
+    // multicast into the ring of every CTA (same stage, same offset) -- half the L2 -> SM key traffic.  The other ranks' producers only arm
+    // their own barrier for the stage once their consumers have drained it, and tell rank 0.
+    const uint32_t csize = cluster_nctarank(), crank = csize > 1 ? cluster_ctarank() : 0;
 
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; s++) {
             mbar_init(bar_s + s * 8, 1);
             mbar_init(empty_s + s * 8, CG4_PRODUCER_WARP ? NT : NT / 32);
+            mbar_init(peer_s + s * 8, csize > 1 ? csize - 1 : 1);
             s_done[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (csize > 1) cluster_sync_all(); // every CTA's barriers exist before a peer arrives on them or a multicast copy signals them
     // ---- key stream: tiles in (block, output poly c, key t) order ------------------------------------------------------------------------
     auto issue_src = [&](const double *src, const uint32_t st_) { // one thread: bulk copies of one tile (RT key rows of one output poly)
         const uint32_t bar = bar_s + st_ * 8;
@@ -733,10 +740,23 @@ cggi_fused4_fft64_kernel(CggiFusedArgs p, const double2 *__restrict__ twf_g, con
             if (tid == NT) {
                 int tt = 0, c = 0;
                 const double *key0 = p.brk; // first key of the current block
+                const uint16_t mask = (uint16_t)((1u << csize) - 1u);
                 for (int gk = 0; gk < total_tiles; gk++) {
                     const int st = gk % NSTAGE;
                     if (gk >= NSTAGE) mbar_wait(empty_s + st * 8, (uint32_t)((gk / NSTAGE - 1) & 1));
-                    issue_src(key0 + (size_t)tt * p.brk_doubles + (size_t)c * N, (uint32_t)st);
+                    if (csize == 1) {
+                        issue_src(key0 + (size_t)tt * p.brk_doubles + (size_t)c * N, (uint32_t)st);
+                    } else if (crank != 0) {
+                        mbar_expect_tx(bar_s + st * 8, TILE);                  // armed before rank 0 can send
+                        mbar_arrive_remote(mapa_u32(peer_s + st * 8, 0));
+                    } else {
+                        mbar_wait_cluster(peer_s + st * 8, (uint32_t)((gk / NSTAGE) & 1)); // every other rank has drained and armed the stage
+                        const double *src = key0 + (size_t)tt * p.brk_doubles + (size_t)c * N;
+                        const uint32_t bar = bar_s + st * 8;
+                        mbar_expect_tx(bar, TILE);
+#pragma unroll
+                        for (int r = 0; r < RT; r++) bulk_g2s_multicast(ring_s + (uint32_t)(st * RT + r) * CHUNK, src + (size_t)r * C * N, CHUNK, bar, mask);
+                    }
                     if (++tt == bs) {
                         tt = 0;
                         if (++c == C) {
@@ -970,10 +990,22 @@ template <int LM, int G, int RT, int CT, int NSTAGE, int BS> static int launch_c
         PGB_CHECK_CUDA(cudaFuncSetAttribute(cggi_fused4_fft64_kernel<LM, G, RT, CT, NSTAGE, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_dev[m->device & 31] = true;
     }
-    const int grid = (p.batch + G - 1) / G;
+    int grid = (p.batch + G - 1) / G;
+    const int cl = (CG4_PRODUCER_WARP && m->opt[PGB_OPT_CGGI_CLUSTER] == 2 && grid >= 2) ? 2 : 1;
+    grid = (grid + cl - 1) / cl * cl; // a CTA past the batch still walks the ring with its peers (its ciphertexts are not live)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(CG4_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = m->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     { ProfScope _ps(m, PROF_OTHER);
-    cggi_fused4_fft64_kernel<LM, G, RT, CT, NSTAGE, BS><<<grid, CG4_THREADS, smem, m->stream>>>(p, m->fft_fwd, m->fft_inv, m->fft_last_f, m->fft_last_i,
-                                                                                         1.0 / (double)(1 << LM));
+    PGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, cggi_fused4_fft64_kernel<LM, G, RT, CT, NSTAGE, BS>, p, (const double2 *)m->fft_fwd, (const double2 *)m->fft_inv,
+                                      (const double2 *)m->fft_last_f, (const double2 *)m->fft_last_i, 1.0 / (double)(1 << LM)));
     }
     PGB_CHECK_CUDA(cudaGetLastError());
     return PGB_OK;

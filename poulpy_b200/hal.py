@@ -21,7 +21,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "poulpy_b200.h")
 NTT120, FFT64 = 0, 1
 # pgb_option (include/poulpy_b200.h)
 (OPT_NO_FUSION, OPT_NO_GADGET, OPT_NO_COLLAPSE, OPT_CGGI_VARIANT, OPT_CGGI_BLOCK_BT1, OPT_VMP_NO_BT, OPT_VMP_CT, OPT_GADGET_MB,
- OPT_HOST_CHUNK_MB, OPT_CGGI_NTT_PRIMES, OPT_GADGET_PRIMES, OPT_LAST_GADGET_PRIMES) = range(12)
+ OPT_HOST_CHUNK_MB, OPT_CGGI_NTT_PRIMES, OPT_GADGET_PRIMES, OPT_LAST_GADGET_PRIMES, OPT_CGGI_CLUSTER) = range(13)
 Q = (1073479681, 1071513601, 1070727169, 1068236801)
 
 

@@ -223,3 +223,30 @@ def test_blind_rotate_tall_keys(fl, rank, dnum, size, brk_size):
     if size >= dnum:  # (accumulators shorter than the key's row count transform column by column and zero-fill)
         assert g.launch_count - l0 <= 2 + 3 * (n_lwe // block)  # init + per block: forward, block kernel, fused back end
     assert np.array_equal(g.vec_znx_to_numpy(res), want)
+
+
+@pytest.mark.parametrize("n,rank,size,brk_size,batch", [(512, 3, 1, 2, 9), (512, 3, 1, 2, 16), (256, 1, 1, 2, 23), (1024, 1, 1, 2, 5)])
+def test_blind_rotate_cluster_multicast(n, rank, size, brk_size, batch):
+    """OPT_CGGI_CLUSTER = 2: the FFT64 whole-rotation kernel runs in clusters of two CTAs whose key tiles are fetched once by rank 0 and
+    multicast into both rings.  Same operations per value, so the results are those of the plain launch bit for bit and the oracle's;
+    batches that leave a partially filled CTA, an odd number of CTAs (the padding CTA walks the ring with no live ciphertext) and a single
+    cluster are covered."""
+    k, n_lwe, block = 12, 24, 3
+    rng = np.random.default_rng(7000 + n + batch)
+    g, o, gbrk, obrk = _setup(n, pb.FFT64, rank, 1, brk_size, n_lwe, k, rng)
+    xg, xo = g.cggi_x_pow_a(), o.cggi_x_pow_a()
+    lut = fill_uniform(rng, (size, 1, n), k)
+    lwe = rng.integers(-n, n, size=(batch, n_lwe + 1), dtype=np.int64)
+    want = np.zeros((batch, size, rank + 1, n), dtype=np.int64)
+    for b in range(batch):
+        o.cggi_blind_rotate_block_binary(want[b], lwe[b], lut, obrk, xo, block, k)
+    lwe_dev = pb.DevBuf(lwe.nbytes)
+    lwe_dev.upload(lwe)
+    got = []
+    for cl in (2, 0):
+        g.set_option(pb.hal.OPT_CGGI_CLUSTER, cl)
+        res = g.vec_znx_from_numpy(fill_uniform(rng, want.shape, k))
+        g.cggi_blind_rotate(res, lwe_dev, n_lwe, g.vec_znx_from_numpy(lut), gbrk, xg, block, k)
+        g.sync()
+        got.append(g.vec_znx_to_numpy(res).reshape(want.shape))
+    assert np.array_equal(got[0], want) and np.array_equal(got[1], want)
