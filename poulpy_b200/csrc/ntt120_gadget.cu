@@ -494,6 +494,139 @@ __device__ __forceinline__ void gadget_mac(uint32_t *__restrict__ sm, const uint
     }
 }
 
+// The same for the automorphism epilogue (see GadgetArgs): a thread still owns OUTPUT coefficients (coalesced stores and reads of `a`); the
+// residues and the body limbs are gathered at the source coefficient js = j' * p^-1 mod 2n, whose sign (flip) is applied to x before the
+// digits (modes 1-3) or to the digits (mode 4).  Per group: the CRT constants, the step decisions and the pointers are shared as in
+// gadget_tail_narrow; per coefficient: source index, sign, gathered loads.
+template <int L, int NP, int NW>
+__device__ __forceinline__ void gadget_tail_narrow_aut(const GadgetArgs &p, const uint32_t (&rb)[NP], const int K, const int t, const int o,
+                                                       const long long *__restrict__ in, long long *__restrict__ res) {
+    typedef GGeo<L> Geo;
+    constexpr int n = Geo::N, T = Geo::T;
+    constexpr int G = NP == 4 ? 4 : 3;
+    const int Kb = p.K, S = p.S, cols_out = p.cols_out, mode = p.aut_mode;
+    const int a_start = p.res_size < S ? p.res_size : S;
+    const size_t res_ls = (size_t)cols_out * n, in_ls = (size_t)p.in_cols * n;
+    const uint32_t kmask32 = (1u << Kb) - 1u, khalf32 = 1u << (Kb - 1);
+    const uint32_t hw[4] = {(uint32_t)p.half_lo, (uint32_t)(p.half_lo >> 32), (uint32_t)p.half_hi, (uint32_t)(p.half_hi >> 32)};
+    const bool with_small = o == 0 && p.small_size > 0;
+#pragma unroll 1
+    for (int c0 = K; c0 < 16; c0 += NP * G) {
+        bool valid[G], flip[G], negx[G];
+        int js[G];
+        uint32_t tk[G][NP];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const int chunk = c0 + g * NP;
+            valid[g] = NP == 4 || chunk < 16;
+            const int jo = (valid[g] ? chunk : c0) * T + t;
+            const uint32_t j0 = ((uint32_t)jo * p.aut_pinv) & (uint32_t)(2 * n - 1);
+            js[g] = (int)(j0 & (uint32_t)(n - 1));
+            flip[g] = j0 >= (uint32_t)n;                                          // sign of the permuted coefficient
+            negx[g] = mode == 4 ? false : (mode == 3 ? !flip[g] : flip[g]);       // sign applied to x before the digits
+            const uint32_t off = (uint32_t)(o * n + swz<L>(js[g])) * 4u;
+#pragma unroll
+            for (int k = 0; k < NP; k++) tk[g][k] = ld_cluster(rb[k] + off);
+        }
+        uint32_t w[G][NW];
+        {
+            unsigned long long a[G];
+            uint32_t e[G];
+#pragma unroll
+            for (int g = 0; g < G; g++) a[g] = 1ull << 59;
+#pragma unroll
+            for (int k = 0; k < NP; k++) {
+                const uint32_t c = p.inv60[k];
+#pragma unroll
+                for (int g = 0; g < G; g++) a[g] += (unsigned long long)tk[g][k] * c;
+            }
+#pragma unroll
+            for (int g = 0; g < G; g++) e[g] = (uint32_t)(a[g] >> 60);
+#pragma unroll
+            for (int wi = 0; wi < NW; wi++) {
+                const uint32_t nq = p.nq_w[wi];
+#pragma unroll
+                for (int g = 0; g < G; g++) a[g] = (wi ? (a[g] >> 32) : 0ull) + (unsigned long long)e[g] * nq;
+                if (NP == 4 || wi < 2) {
+#pragma unroll
+                    for (int k = 0; k < NP; k++) {
+                        const uint32_t mw = p.m_w[k][wi];
+#pragma unroll
+                        for (int g = 0; g < G; g++) a[g] += (unsigned long long)tk[g][k] * mw;
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < G; g++) w[g][wi] = (uint32_t)a[g];
+            }
+        }
+        // u = +-v + half (mod 2^(32 NW))
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            uint32_t cy = negx[g] ? 1u : 0u;
+            const uint32_t xm = negx[g] ? 0xffffffffu : 0u;
+#pragma unroll
+            for (int wi = 0; wi < NW; wi++) { // (w ^ xm) + cy + half, word by word with explicit carries
+                const unsigned long long s2 = (unsigned long long)(w[g][wi] ^ xm) + cy + hw[wi];
+                w[g][wi] = (uint32_t)s2;
+                cy = (uint32_t)(s2 >> 32);
+            }
+        }
+        const long long *bp = in + (size_t)(S - 1) * in_ls;                                   // body (column 0), gathered at js
+        const long long *pp = in + (size_t)(S - 1) * in_ls + (size_t)o * n + c0 * T + t;      // a, column o, at the output coefficient
+        long long *out_p = res + (size_t)(S - 1) * res_ls + (size_t)o * n + c0 * T + t;
+        // signed 64-bit value joined at bit 0 of the NW-word state, added (sub = false) or subtracted
+        auto join = [&](uint32_t (&ww)[NW], const long long sv, const bool sub) {
+            const uint32_t xm = sub ? 0xffffffffu : 0u;
+            const uint32_t lo = (uint32_t)sv ^ xm, hi = (uint32_t)((unsigned long long)sv >> 32) ^ xm, sx = (uint32_t)(sv >> 63) ^ xm;
+            unsigned long long s2 = (unsigned long long)ww[0] + lo + (sub ? 1u : 0u);
+            ww[0] = (uint32_t)s2;
+            if (NW > 1) { s2 = (s2 >> 32) + ww[NW > 1 ? 1 : 0] + hi; ww[NW > 1 ? 1 : 0] = (uint32_t)s2; }
+            if (NW > 2) { s2 = (s2 >> 32) + ww[NW > 2 ? 2 : 0] + sx; ww[NW > 2 ? 2 : 0] = (uint32_t)s2; }
+            if (NW > 3) { s2 = (s2 >> 32) + ww[NW > 3 ? 3 : 0] + sx; ww[NW > 3 ? 3 : 0] = (uint32_t)s2; }
+        };
+#pragma unroll 1
+        for (int j = S - 1; j >= 0; j--) {
+            if (with_small && j < p.small_size) {
+                long long b[G];
+#pragma unroll
+                for (int g = 0; g < G; g++) b[g] = valid[g] ? __ldg(bp + js[g]) : 0;
+#pragma unroll
+                for (int g = 0; g < G; g++) join(w[g], b[g], negx[g]);
+            }
+            if (mode != 4 && j < p.post_size) {
+                long long b[G];
+#pragma unroll
+                for (int g = 0; g < G; g++) b[g] = valid[g] ? __ldg(pp + g * NP * T) : 0;
+#pragma unroll
+                for (int g = 0; g < G; g++) join(w[g], b[g], mode == 2);
+            }
+            bp -= in_ls;
+            pp -= in_ls;
+            if (j < a_start) {
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    int d = (int)(w[g][0] & kmask32) - (int)khalf32;
+                    if (mode == 4 && flip[g]) d = -d;
+                    if (valid[g]) out_p[g * NP * T] = (long long)d;
+                }
+            }
+            out_p -= res_ls;
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+#pragma unroll
+                for (int wi = 0; wi + 1 < NW; wi++) w[g][wi] = __funnelshift_r(w[g][wi], w[g][wi + 1], Kb);
+                w[g][NW - 1] >>= Kb;
+            }
+        }
+        long long *zp = res + (size_t)o * n + c0 * T + t;
+        for (int j = a_start; j < p.res_size; j++) {
+#pragma unroll
+            for (int g = 0; g < G; g++)
+                if (valid[g]) zp[(size_t)j * res_ls + g * NP * T] = 0;
+        }
+    }
+}
+
 template <int L, bool AUT, int NP> __device__ __forceinline__ void gadget_body(const GadgetArgs &p, uint32_t *__restrict__ sm, const uint2 *__restrict__ twf,
                                                              const uint2 *__restrict__ twi, const uint4 *__restrict__ lastf,
                                                              const uint4 *__restrict__ lasti, const int K) {
@@ -690,6 +823,14 @@ template <int L, bool AUT, int NP> __device__ __forceinline__ void gadget_body(c
                 // Automorphism epilogue (see GadgetArgs): this thread still owns OUTPUT coefficients chunk T + t (coalesced stores and
                 // reads of `a`); residues and body limbs are gathered at the source coefficient.
                 const int mode = p.aut_mode;
+                if (narrow) { // base2k < 32: groups of coefficients, as many 32-bit words as the digits need
+                    long long *res_base = reinterpret_cast<long long *>(p.res + (size_t)ct * p.res_bs);
+                    for (int o = 0; o < cols_out; o++) {
+                        if (nwords <= 2) gadget_tail_narrow_aut<L, NP, 2>(p, rb, K, t, o, in, res_base);
+                        else if (nwords == 3) gadget_tail_narrow_aut<L, NP, 3>(p, rb, K, t, o, in, res_base);
+                        else gadget_tail_narrow_aut<L, NP, 4>(p, rb, K, t, o, in, res_base);
+                    }
+                } else
                 for (int o = 0; o < cols_out; o++) {
                     const bool with_small = o == 0 && p.small_size > 0;
 #pragma unroll 1
