@@ -279,7 +279,10 @@ int pgb_glwe_external_product_batched(pgb_module *m, pgb_vec_znx *res, uint64_t 
  * the module keeps those forms across calls (keyed on key->data and the call's shape) until pgb_gadget_key_unpin(key), module
  * destruction, or a pgb_vmp_prepare into that memory (which drops them).  Rewriting a pinned key's bytes by any other means without
  * unpinning it first is a contract violation.  Unpinned keys behave as before (forms re-derived on every call).  In the reference the
- * analogue is the lifetime of a `GGLWEPrepared` / `GGSWPrepared` value: prepared once, borrowed immutably by every product. */
+ * analogue is the lifetime of a `GGLWEPrepared` / `GGSWPrepared` value: prepared once, borrowed immutably by every product.
+ * For a pinned key the host also learns the key's coefficient bound (one 4-byte read-back when the forms are built); when that bound
+ * proves that the integers of the product stay below Q[0] Q[1] Q[2] / 2 the NTT120 gadget kernel works on three primes instead of four
+ * (same results bit for bit: every input is still checked on the device; PGB_OPT_GADGET_PRIMES = 4 disables it). */
 int pgb_gadget_key_pin(pgb_module *m, const pgb_vmp_pmat *key);
 int pgb_gadget_key_unpin(pgb_module *m, const pgb_vmp_pmat *key);
 
